@@ -1,0 +1,321 @@
+/* TEST INFRASTRUCTURE ONLY - see ds_oracle.h.  Line glyph restated from the reference's numba CPU
+ * path: Liang-Barsky clip, snapped Bresenham, full antialiased rasteriser, LinesAxis1 layout.
+ * Build with -ffp-contract=off.
+ */
+#include "ds_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+  int32_t agg_op;     /* ORA_ANY / ORA_COUNT / ORA_SUM / ORA_MAX / ORA_MIN */
+  int antialias;
+  int has_field;
+  double field;       /* value of the current line */
+  int64_t width;
+  void* agg;
+} line_ctx;
+
+/* append for line_width == 0: the plain reduction appends (same as points) */
+static inline void append_px(const line_ctx* c, int64_t x, int64_t y) {
+  int64_t cell = y * c->width + x;
+  double f = c->field;
+  switch (c->agg_op) {
+    case ORA_ANY:   /* reductions.py:843-848 / 858-862 */
+      if (c->has_field && isnan(f)) return;
+      ((uint8_t*)c->agg)[cell] = 1; return;
+    case ORA_COUNT: /* reductions.py:552-558 / 580-584 */
+      if (c->has_field && isnan(f)) return;
+      ((uint32_t*)c->agg)[cell] += 1u; return;
+    case ORA_SUM: { /* reductions.py:1054-1063 */
+      if (isnan(f)) return;
+      double* a = (double*)c->agg + cell;
+      if (isnan(*a)) *a = f; else *a += f;
+      return;
+    }
+    case ORA_MAX: { /* reductions.py:1222-1227 */
+      double* a = (double*)c->agg + cell;
+      if (!isnan(f) && (isnan(*a) || *a < f)) *a = f;
+      return;
+    }
+    case ORA_MIN: { /* reductions.py:1178-1183 */
+      double* a = (double*)c->agg + cell;
+      if (!isnan(f) && (isnan(*a) || *a > f)) *a = f;
+      return;
+    }
+  }
+}
+
+/* append for antialiased lines (single-stage combinations only) */
+static inline void append_aa(const line_ctx* c, int64_t x, int64_t y, double aa, double prev_aa) {
+  int64_t cell = y * c->width + x;
+  double f = c->field;
+  switch (c->agg_op) {
+    case ORA_ANY: { /* reductions.py:850-856 / 864-869, f32 canvas */
+      if (c->has_field && isnan(f)) return;
+      float* a = (float*)c->agg + cell;
+      if (isnan(*a) || aa > *a) *a = (float)aa;
+      return;
+    }
+    case ORA_COUNT: { /* reductions.py:560-568 / 586-592, f32 canvas, SUM_1AGG */
+      if (c->has_field && isnan(f)) return;
+      float* a = (float*)c->agg + cell;
+      if (isnan(*a)) *a = (float)(aa - prev_aa); else *a = (float)(*a + (aa - prev_aa));
+      return;
+    }
+    case ORA_SUM: { /* reductions.py:1065-1075 */
+      double v = f * (aa - prev_aa);
+      if (isnan(v)) return;
+      double* a = (double*)c->agg + cell;
+      if (isnan(*a)) *a = v; else *a += v;
+      return;
+    }
+    case ORA_MAX: { /* reductions.py:1229-1236 */
+      double v = f * aa;
+      double* a = (double*)c->agg + cell;
+      if (!isnan(v) && (isnan(*a) || v > *a)) *a = v;
+      return;
+    }
+  }
+}
+
+/* line.py:783-800 */
+static inline int clipt(double p, double q, double* t0, double* t1) {
+  if (p < 0 && q < 0) {
+    double r = q / p;
+    if (r > *t1) return 0;
+    else if (r > *t0) *t0 = r;
+  } else if (p > 0 && q < p) {
+    double r = q / p;
+    if (r < *t0) return 0;
+    else if (r < *t1) *t1 = r;
+  } else if (q < 0) {
+    return 0;
+  }
+  return 1;
+}
+
+/* line.py:734-780; returns skip */
+/* With float32 vertex arrays numba types x0..y1 as float32 inside _liang_barsky, so dx1 = x1 - x0 and
+   dy1 = y1 - y0 are rounded to float32 before being widened (checked against the reference:
+   tests/golden/lines.npz, clipped f32 segments); everything else is float64. */
+static inline int liang_barsky(double xmin, double xmax, double ymin, double ymax, double* x0, double* x1,
+                               double* y0, double* y1, int skip, int is_f32, int* clipped_start, int* clipped_end) {
+  if (*x0 < xmin && *x1 < xmin) skip = 1;
+  else if (*x0 > xmax && *x1 > xmax) skip = 1;
+  else if (*y0 < ymin && *y1 < ymin) skip = 1;
+  else if (*y0 > ymax && *y1 > ymax) skip = 1;
+  double t0 = 0, t1 = 1;
+  double dx1 = is_f32 ? (double)((float)*x1 - (float)*x0) : *x1 - *x0;
+  if (!clipt(-dx1, *x0 - xmin, &t0, &t1)) skip = 1;
+  if (!clipt(dx1, xmax - *x0, &t0, &t1)) skip = 1;
+  double dy1 = is_f32 ? (double)((float)*y1 - (float)*y0) : *y1 - *y0;
+  if (!clipt(-dy1, *y0 - ymin, &t0, &t1)) skip = 1;
+  if (!clipt(dy1, ymax - *y0, &t0, &t1)) skip = 1;
+  if (t1 < 1) { *clipped_end = 1; *x1 = *x0 + t1 * dx1; *y1 = *y0 + t1 * dy1; }
+  else *clipped_end = 0;
+  if (t0 > 0) { *clipped_start = 1; *x0 = *x0 + t0 * dx1; *y0 = *y0 + t0 * dy1; }
+  else *clipped_start = 0;
+  return skip;
+}
+
+static inline double axmap(int is_log, double v) { return is_log ? log10(v) : v; }
+static inline double clampd(double x, double lo, double hi) { return fmax(lo, fmin(x, hi)); }       /* line.py:803-806 */
+static inline double linearstep(double e0, double e1, double x) { return clampd((x - e0) / (e1 - e0), 0.0, 1.0); }
+static inline double x_intercept(double y, double cx0, double cy0, double cx1, double cy1) {      /* line.py:815-823 */
+  if (cy0 == cy1) return cx1;
+  double frac = (y - cy0) / (cy1 - cy0);
+  return cx0 + frac * (cx1 - cx0);
+}
+
+/* line.py:986-1031 */
+static void bresenham(const line_ctx* c, int segment_start, int64_t x0, int64_t x1, int64_t y0, int64_t y1, int clipped) {
+  int64_t dx = x1 - x0;
+  int64_t ix = (dx > 0) - (dx < 0);
+  dx = llabs(dx) * 2;
+  int64_t dy = y1 - y0;
+  int64_t iy = (dy > 0) - (dy < 0);
+  dy = llabs(dy) * 2;
+  if (!clipped && !(dx | dy)) { append_px(c, x0, y0); return; }
+  if (segment_start) append_px(c, x0, y0);
+  if (dx >= dy) {
+    int64_t error = 2 * dy - dx;
+    while (x0 != x1) {
+      if (error >= 0 && (error || ix > 0)) { error -= 2 * dx; y0 += iy; }
+      error += 2 * dy;
+      x0 += ix;
+      append_px(c, x0, y0);
+    }
+  } else {
+    int64_t error = 2 * dx - dy;
+    while (y0 != y1) {
+      if (error >= 0 && (error || iy > 0)) { error -= 2 * dy; x0 += ix; }
+      error += 2 * dx;
+      y0 += iy;
+      append_px(c, x0, y0);
+    }
+  }
+}
+
+/* line.py:830-981 */
+static void full_antialias(const line_ctx* c, double line_width, int overwrite, double x0, double x1, double y0,
+                           double y1, int segment_start, int segment_end, double xm, double ym, int64_t nx, int64_t ny) {
+  if (x0 == x1 && y0 == y1) return;
+  int flip_xy = fabs(x0 - x1) < fabs(y0 - y1);
+  if (flip_xy) {
+    double t;
+    t = x0; x0 = y0; y0 = t;
+    t = x1; x1 = y1; y1 = t;
+    t = xm; xm = ym; ym = t;
+  }
+  double scale = 1.0;
+  if (line_width < 1.0) { scale *= line_width; line_width = 1.0; }
+  double aa = 1.0;
+  double halfwidth = 0.5 * (line_width + aa);
+  int flip_order = y1 < y0 || (y1 == y0 && x1 < x0);
+  double alongx = x1 - x0, alongy = y1 - y0;
+  double length = sqrt(alongx * alongx + alongy * alongy);
+  alongx /= length; alongy /= length;
+  double rightx = alongy, righty = -alongx;
+  double b[8];
+  if (flip_order) {
+    b[0] = x1 - halfwidth * (rightx - alongx);
+    b[1] = x1 - halfwidth * (-rightx - alongx);
+    b[2] = x0 - halfwidth * (-rightx + alongx);
+    b[3] = x0 - halfwidth * (rightx + alongx);
+    b[4] = y1 - halfwidth * (righty - alongy);
+    b[5] = y1 - halfwidth * (-righty - alongy);
+    b[6] = y0 - halfwidth * (-righty + alongy);
+    b[7] = y0 - halfwidth * (righty + alongy);
+  } else {
+    b[0] = x0 + halfwidth * (rightx - alongx);
+    b[1] = x0 + halfwidth * (-rightx - alongx);
+    b[2] = x1 + halfwidth * (-rightx + alongx);
+    b[3] = x1 + halfwidth * (rightx + alongx);
+    b[4] = y0 + halfwidth * (righty - alongy);
+    b[5] = y0 + halfwidth * (-righty - alongy);
+    b[6] = y1 + halfwidth * (-righty + alongy);
+    b[7] = y1 + halfwidth * (righty + alongy);
+  }
+  int64_t xmax = nx - 1, ymax = ny - 1;
+  if (flip_xy) { int64_t t = xmax; xmax = ymax; ymax = t; }
+  int lowindex;
+  if (flip_order) lowindex = x0 > x1 ? 0 : 1;
+  else lowindex = x1 > x0 ? 0 : 1;
+  double prev_alongx = 0, prev_alongy = 0, prev_length = 0, prev_rightx = 0, prev_righty = 0;
+  if (!overwrite && !segment_start) {
+    prev_alongx = x0 - xm;
+    prev_alongy = y0 - ym;
+    prev_length = sqrt(prev_alongx * prev_alongx + prev_alongy * prev_alongy);
+    if (prev_length > 0.0) {
+      prev_alongx /= prev_length; prev_alongy /= prev_length;
+      prev_rightx = prev_alongy; prev_righty = -prev_alongx;
+    } else {
+      overwrite = 1;
+    }
+  }
+  int64_t ystart = (int64_t)clampd(ceil(b[4 + lowindex]), 0, (double)ymax);
+  int64_t yend = (int64_t)clampd(floor(b[4 + (lowindex + 2) % 4]), 0, (double)ymax);
+  int ll = lowindex, lu = (ll + 1) % 4, rl = lowindex, ru = (rl + 3) % 4;
+  for (int64_t y = ystart; y <= yend; y++) {
+    if (ll == lowindex && y > b[4 + lu]) { ll = lu; lu = (ll + 1) % 4; }
+    if (rl == lowindex && y > b[4 + ru]) { rl = ru; ru = (rl + 3) % 4; }
+    int64_t xleft = (int64_t)clampd(ceil(x_intercept((double)y, b[ll], b[4 + ll], b[lu], b[4 + lu])), 0, (double)xmax);
+    int64_t xright = (int64_t)clampd(floor(x_intercept((double)y, b[rl], b[4 + rl], b[ru], b[4 + ru])), 0, (double)xmax);
+    for (int64_t x = xleft; x <= xright; x++) {
+      double along = (x - x0) * alongx + (y - y0) * alongy;
+      int prev_correction = 0;
+      double distance;
+      if (along < 0.0) {
+        if (overwrite || segment_start || (x - x0) * prev_alongx + (y - y0) * prev_alongy > 0.0)
+          distance = sqrt((x - x0) * (x - x0) + (y - y0) * (y - y0));
+        else continue;
+      } else if (along > length) {
+        if (overwrite || segment_end) distance = sqrt((x - x1) * (x - x1) + (y - y1) * (y - y1));
+        else continue;
+      } else {
+        distance = fabs((x - x0) * rightx + (y - y0) * righty);
+        if (!overwrite && !segment_start) {
+          double pa = (x - x0) * prev_alongx + (y - y0) * prev_alongy;
+          if (-prev_length <= pa && pa <= 0.0 && fabs((x - x0) * prev_rightx + (y - y0) * prev_righty) <= halfwidth)
+            prev_correction = 1;
+        }
+      }
+      double value = 1.0 - linearstep(0.5 * (line_width - aa), halfwidth, distance);
+      value *= scale;
+      double prev_value = 0.0;
+      if (prev_correction) {
+        double prev_distance = fabs((x - x0) * prev_rightx + (y - y0) * prev_righty);
+        prev_value = 1.0 - linearstep(0.5 * (line_width - aa), halfwidth, prev_distance);
+        prev_value *= scale;
+        if (value <= prev_value) value = 0.0;
+      }
+      if (value > 0.0) {
+        if (flip_xy) append_aa(c, y, x, value, prev_value);
+        else append_aa(c, x, y, value, prev_value);
+      }
+    }
+  }
+}
+
+/* line.py:1045-1097 */
+static void draw_segment(const ora_view* v, const line_ctx* c, double line_width, int overwrite, int segment_start,
+                         int segment_end, double x0, double x1, double y0, double y1, double xm, double ym, int is_f32) {
+  int skip = 0;
+  if (isnan(x0) || isnan(y0) || isnan(x1) || isnan(y1)) skip = 1;
+  int clipped_start, clipped_end;
+  skip = liang_barsky(v->xmin, v->xmax, v->ymin, v->ymax, &x0, &x1, &y0, &y1, skip, is_f32, &clipped_start, &clipped_end);
+  if (skip) return;
+  int clipped = clipped_start || clipped_end;
+  segment_start = segment_start || clipped_start;
+  if (line_width > 0.0) {
+    /* map_onto_pixel_no_snap, line.py:722-726 */
+    double x0p = axmap(v->x_log, x0) * v->sx + v->tx - 0.5, y0p = axmap(v->y_log, y0) * v->sy + v->ty - 0.5;
+    double x1p = axmap(v->x_log, x1) * v->sx + v->tx - 0.5, y1p = axmap(v->y_log, y1) * v->sy + v->ty - 0.5;
+    double xmp = 0.0, ymp = 0.0;
+    if (!segment_start) {
+      xmp = axmap(v->x_log, xm) * v->sx + v->tx - 0.5;
+      ymp = axmap(v->y_log, ym) * v->sy + v->ty - 0.5;
+    }
+    int64_t nx = (int64_t)nearbyint((v->xmax - v->xmin) * v->sx);   /* Python round(): half to even */
+    int64_t ny = (int64_t)nearbyint((v->ymax - v->ymin) * v->sy);
+    full_antialias(c, line_width, overwrite, x0p, x1p, y0p, y1p, segment_start, segment_end, xmp, ymp, nx, ny);
+  } else {
+    /* map_onto_pixel_snap, line.py:689-720 */
+    int64_t xxmax = (int64_t)nearbyint(axmap(v->x_log, v->xmax) * v->sx + v->tx);
+    int64_t yymax = (int64_t)nearbyint(axmap(v->y_log, v->ymax) * v->sy + v->ty);
+    int64_t x0i = (int64_t)(axmap(v->x_log, x0) * v->sx + v->tx), y0i = (int64_t)(axmap(v->y_log, y0) * v->sy + v->ty);
+    int64_t x1i = (int64_t)(axmap(v->x_log, x1) * v->sx + v->tx), y1i = (int64_t)(axmap(v->y_log, y1) * v->sy + v->ty);
+    if (x0i == xxmax) x0i--;
+    if (y0i == yymax) y0i--;
+    if (x1i == xxmax) x1i--;
+    if (y1i == yymax) y1i--;
+    bresenham(c, segment_start, x0i, x1i, y0i, y1i, clipped);
+  }
+}
+
+static inline double ldxy(const void* p, int32_t dt, int64_t i) {
+  return dt == ORA_F32 ? (double)((const float*)p)[i] : ((const double*)p)[i];
+}
+
+void ora_lines_axis1(const ora_view* v, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                     int64_t nverts, const void* val, int32_t val_dtype, int32_t agg_op, double line_width, void* agg) {
+  line_ctx c;
+  c.agg_op = agg_op; c.antialias = line_width > 0.0; c.has_field = val_dtype != ORA_NONE;
+  c.width = v->width; c.agg = agg; c.field = 0.0;
+  /* antialias.py:30-58: overwrite unless a SUM_1AGG combination (count / sum) is present */
+  int overwrite = !(agg_op == ORA_COUNT || agg_op == ORA_SUM);
+  for (int64_t i = 0; i < nlines; i++) {          /* extend_cpu, line.py:1277-1289 */
+    if (c.has_field) c.field = ldxy(val, val_dtype, i);
+    for (int64_t j = 0; j + 1 < nverts; j++) {    /* perform_extend_line, line.py:1250-1275 */
+      const int64_t o = i * nverts + j;
+      double x0 = ldxy(xs, xy_dtype, o), y0 = ldxy(ys, xy_dtype, o);
+      double x1 = ldxy(xs, xy_dtype, o + 1), y1 = ldxy(ys, xy_dtype, o + 1);
+      int segment_start = (j == 0) || isnan(ldxy(xs, xy_dtype, o - 1)) || isnan(ldxy(ys, xy_dtype, o - 1));
+      int segment_end = (j == nverts - 2) || isnan(ldxy(xs, xy_dtype, o + 2)) || isnan(ldxy(ys, xy_dtype, o + 2));
+      double xm = 0.0, ym = 0.0;
+      if (!segment_start) { xm = ldxy(xs, xy_dtype, o - 1); ym = ldxy(ys, xy_dtype, o - 1); }
+      draw_segment(v, &c, line_width, overwrite, segment_start, segment_end, x0, x1, y0, y1, xm, ym, xy_dtype == ORA_F32);
+    }
+  }
+}

@@ -1,0 +1,219 @@
+"""Generate golden vectors from the REAL reference (holoviz/datashader at /root/reference).
+
+Run in the build container only (the reference is not present on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference is pure Python + numba; it is imported unmodified.  `xarray`, `toolz` and
+`multipledispatch` are missing from this image, so tests/golden/_shims/ provides container-only
+stand-ins for them (containers and functional helpers only - no arithmetic).  Outputs are small
+.npz fixtures (inputs + reference outputs) committed under tests/golden/; tests/ compare both the
+C oracle and the CUDA path against them.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+import pandas as pd  # noqa: E402
+
+import datashader as ds  # noqa: E402
+from datashader.compiler import compile_components  # noqa: E402
+from datashader.glyphs import Point  # noqa: E402
+from datashader.utils import dshape_from_pandas  # noqa: E402
+
+NCAT = 5
+
+
+def make_frame(seed, n, xy_dtype):
+    rng = np.random.default_rng(seed)
+    x = rng.random(n).astype(xy_dtype) * 1.3 - 0.15      # some rows fall outside (0,1)
+    y = rng.random(n).astype(xy_dtype) * 1.3 - 0.15
+    # plant exact edge / pixel-boundary coordinates
+    edge = np.array([0.0, 1.0, 0.5, 0.25, 0.75, np.nextafter(np.float32(1), np.float32(0)),
+                     np.nextafter(np.float32(0.5), np.float32(0)), 1.0 / 3, 2.0 / 3], dtype=xy_dtype)
+    k = len(edge)
+    x[:k] = edge
+    y[:k] = edge[::-1]
+    x[k:2 * k] = edge
+    y[k:2 * k] = 0.5
+    x[rng.integers(0, n, n // 50)] = np.nan
+    y[rng.integers(0, n, n // 50)] = np.nan
+    v32 = rng.standard_normal(n).astype(np.float32)
+    v32[rng.integers(0, n, n // 20)] = np.nan
+    v32[rng.integers(0, n, n // 40)] = np.round(v32[rng.integers(0, n, n // 40)], 1)   # ties
+    v64 = rng.standard_normal(n) * 1e3
+    v64[rng.integers(0, n, n // 20)] = np.nan
+    vi = rng.integers(-50, 50, n).astype(np.int32)
+    other = rng.random(n).astype(np.float32) * 100
+    other[rng.integers(0, n, n // 30)] = np.nan
+    codes = rng.integers(0, NCAT, n).astype(np.int8)
+    return dict(x=x, y=y, v32=v32, v64=v64, vi=vi, other=other, cat=codes)
+
+
+def to_df(cols):
+    d = {k: v for k, v in cols.items() if k != "cat"}
+    d["cat"] = pd.Categorical.from_codes(cols["cat"], categories=[f"c{i}" for i in range(NCAT)])
+    return pd.DataFrame(d)
+
+
+def reductions():
+    return {
+        "count": ds.count(), "count_v32": ds.count("v32"), "any": ds.any(), "any_v32": ds.any("v32"),
+        "sum_v32": ds.sum("v32"), "sum_v64": ds.sum("v64"), "sum_vi": ds.sum("vi"),
+        "mean_v32": ds.mean("v32"), "mean_v64": ds.mean("v64"),
+        "min_v32": ds.min("v32"), "max_v32": ds.max("v32"), "min_v64": ds.min("v64"), "max_v64": ds.max("v64"),
+        "max_vi": ds.max("vi"),
+        "first_v32": ds.first("v32"), "last_v32": ds.last("v32"),
+        "where_max_v32_other": ds.where(ds.max("v32"), "other"), "where_min_v32_other": ds.where(ds.min("v32"), "other"),
+        "where_max_v32_row": ds.where(ds.max("v32")), "where_min_v32_row": ds.where(ds.min("v32")),
+        "where_first_v32_other": ds.where(ds.first("v32"), "other"), "where_last_v32_other": ds.where(ds.last("v32"), "other"),
+        "where_first_v32_row": ds.where(ds.first("v32")), "where_last_v32_row": ds.where(ds.last("v32")),
+        "where_max_vi_other": ds.where(ds.max("vi"), "other"),
+        "by_count": ds.by("cat", ds.count()), "by_count_v32": ds.by("cat", ds.count("v32")),
+        "by_sum_v32": ds.by("cat", ds.sum("v32")), "by_mean_v32": ds.by("cat", ds.mean("v32")),
+        "by_max_v32": ds.by("cat", ds.max("v32")), "by_min_v32": ds.by("cat", ds.min("v32")),
+        "by_any": ds.by("cat", ds.any()),
+    }
+
+
+def points_cases():
+    out = {}
+    canvases = {
+        "c2x2": dict(plot_width=2, plot_height=2, x_range=(0, 1), y_range=(0, 1)),
+        "c37x23": dict(plot_width=37, plot_height=23, x_range=(-0.1, 1.05), y_range=(0.1, 0.9)),
+        "c90x52": dict(plot_width=90, plot_height=52, x_range=(0, 1), y_range=(0, 1)),
+        "cauto": dict(plot_width=31, plot_height=17),
+    }
+    for xy_dtype in (np.float32, np.float64):
+        tag = "f32" if xy_dtype == np.float32 else "f64"
+        cols = make_frame(1234 if tag == "f32" else 4321, 6000, xy_dtype)
+        df = to_df(cols)
+        for k, v in cols.items():
+            out[f"in_{tag}_{k}"] = v
+        for cname, ckw in canvases.items():
+            cvs = ds.Canvas(**ckw)
+            for rname, red in reductions().items():
+                if tag == "f64" and not (rname in ("count", "mean_v32", "max_v32", "by_count", "where_max_v32_other")):
+                    continue
+                agg = cvs.points(df, "x", "y", red)
+                out[f"pts_{tag}_{cname}_{rname}"] = np.asarray(agg.data)
+                if rname == "count":
+                    out[f"pts_{tag}_{cname}_xcoords"] = np.asarray(agg.coords["x"])
+                    out[f"pts_{tag}_{cname}_ycoords"] = np.asarray(agg.coords["y"])
+                    out[f"pts_{tag}_{cname}_xrange"] = np.asarray(agg.attrs["x_range"], dtype=np.float64)
+                    out[f"pts_{tag}_{cname}_yrange"] = np.asarray(agg.attrs["y_range"], dtype=np.float64)
+    # log axes
+    cols = make_frame(99, 4000, np.float32)
+    cols["x"] = (10 ** (cols["x"].astype(np.float64) * 3)).astype(np.float32)
+    cols["y"] = (10 ** (cols["y"].astype(np.float64) * 2)).astype(np.float32)
+    df = to_df(cols)
+    for k in ("x", "y", "v32"):
+        out[f"in_log_{k}"] = cols[k]
+    cvs = ds.Canvas(plot_width=40, plot_height=30, x_range=(1, 1000), y_range=(1, 100), x_axis_type="log", y_axis_type="log")
+    out["pts_log_count"] = np.asarray(cvs.points(df, "x", "y", ds.count()).data)
+    out["pts_log_max_v32"] = np.asarray(cvs.points(df, "x", "y", ds.max("v32")).data)
+    a = cvs.points(df, "x", "y", ds.count())
+    out["pts_log_xcoords"] = np.asarray(a.coords["x"])
+    out["pts_log_ycoords"] = np.asarray(a.coords["y"])
+    return out
+
+
+def partitioned_cases():
+    """The reference's dask path without dask: compile_components(partitioned=True), create+extend per
+    row slice with _datashader_row_offset set as data_libraries/dask.py:110-113 does, combine, finalize."""
+    out = {}
+    cols = make_frame(777, 5000, np.float32)
+    df = to_df(cols)
+    for k, v in cols.items():
+        out[f"in_{k}"] = v
+    cvs = ds.Canvas(plot_width=37, plot_height=23, x_range=(-0.1, 1.05), y_range=(0.1, 0.9))
+    glyph = Point("x", "y")
+    schema = dshape_from_pandas(df)
+    x_range, y_range = cvs.x_range, cvs.y_range
+    x_st = cvs.x_axis.compute_scale_and_translate(x_range, cvs.plot_width)
+    y_st = cvs.y_axis.compute_scale_and_translate(y_range, cvs.plot_height)
+    names = ["count", "mean_v32", "sum_v32", "max_v32", "min_v32", "first_v32", "last_v32",
+             "where_max_v32_other", "where_min_v32_row", "where_first_v32_other", "where_last_v32_row",
+             "by_count", "by_max_v32", "any_v32"]
+    reds = reductions()
+    nparts = 3
+    for rname in names:
+        red = reds[rname]
+        create, info, append, combine, finalize, aa2, aa2f, _ = compile_components(
+            red, schema, glyph, antialias=False, cuda=False, partitioned=True)
+        extend = glyph._build_extend(cvs.x_axis.mapper, cvs.y_axis.mapper, info, append, aa2, aa2f)
+        parts = []
+        n = len(df)
+        for p in range(nparts):
+            lo, hi = n * p // nparts, n * (p + 1) // nparts
+            part = df.iloc[lo:hi]
+            object.__setattr__(part, "_datashader_row_offset", lo)
+            aggs = create((cvs.plot_height, cvs.plot_width))
+            extend(aggs, part, x_st + y_st, x_range + y_range)
+            parts.append(aggs)
+        res = finalize(combine(parts), cuda=False, coords={"x": None, "y": None}, dims=["y", "x"], attrs={})
+        out[f"part3_{rname}"] = np.asarray(res.data)
+    return out
+
+
+def line_frame(seed, nlines, nverts, dtype):
+    rng = np.random.default_rng(seed)
+    xs = np.tile(np.linspace(-0.2, 1.2, nverts), (nlines, 1)) + rng.normal(0, 0.02, (nlines, nverts))
+    ys = np.cumsum(rng.normal(0, 0.08, (nlines, nverts)), axis=1) + 0.5
+    xs[rng.random((nlines, nverts)) < 0.03] = np.nan
+    ys[rng.random((nlines, nverts)) < 0.03] = np.nan
+    # a few degenerate / vertical / horizontal / repeated-vertex segments
+    xs[0, :] = 0.5
+    ys[1, :] = 0.5
+    xs[2, 3] = xs[2, 2]
+    ys[2, 3] = ys[2, 2]
+    xs[3, :] = np.linspace(0.0, 1.0, nverts)
+    ys[3, :] = np.linspace(0.0, 1.0, nverts)     # exact diagonal through pixel corners
+    val = rng.random(nlines) * 10 - 3
+    val[5] = np.nan
+    return xs.astype(dtype), ys.astype(dtype), val.astype(np.float32)
+
+
+def lines_cases():
+    out = {}
+    for tag, dtype in (("f32", np.float32), ("f64", np.float64)):
+        xs, ys, val = line_frame(2024, 40, 24, dtype)
+        nverts = xs.shape[1]
+        out[f"in_{tag}_xs"], out[f"in_{tag}_ys"], out[f"in_{tag}_val"] = xs, ys, val
+        d = {f"x{j}": xs[:, j] for j in range(nverts)}
+        d.update({f"y{j}": ys[:, j] for j in range(nverts)})
+        d["val"] = val
+        df = pd.DataFrame(d)
+        xcols, ycols = [f"x{j}" for j in range(nverts)], [f"y{j}" for j in range(nverts)]
+        canvases = {
+            "c64x48": dict(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1)),
+            "c33x57": dict(plot_width=33, plot_height=57, x_range=(-0.3, 1.3), y_range=(-0.5, 1.5)),
+        }
+        for cname, ckw in canvases.items():
+            cvs = ds.Canvas(**ckw)
+            for lw in (0, 1, 2.5, 0.5):
+                aggs = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val")}
+                if lw == 0:
+                    aggs["min"] = ds.min("val")
+                if tag == "f64" and lw not in (0, 1):
+                    continue
+                for aname, agg in aggs.items():
+                    r = cvs.line(df, x=xcols, y=ycols, axis=1, agg=agg, line_width=lw)
+                    out[f"ln_{tag}_{cname}_lw{lw}_{aname}"] = np.asarray(r.data)
+    return out
+
+
+def main():
+    np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
+    np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
+    np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())
+    for f in ("points.npz", "partitioned.npz", "lines.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+"""The C oracle against the real reference: committed golden vectors (tests/golden/*.npz, produced by
+tests/golden/make_golden.py from /root/reference) and the literal known-answer tables of the
+reference's own tests (datashader/tests/test_pandas.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as ora
+from helpers import (CANVASES, LINE_CANVASES, SPECS, assert_agg_equal, columns_from_golden, load)
+
+
+def _view(cols, ckw, x="x", y="y"):
+    xr = ckw.get("x_range") or ora.compute_bounds(cols[x])
+    yr = ckw.get("y_range") or ora.compute_bounds(cols[y])
+    return ora.make_view(ckw["plot_width"], ckw["plot_height"], xr, yr), xr, yr
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("cname", list(CANVASES))
+def test_points_golden(tag, cname):
+    g = load("points.npz")
+    cols = columns_from_golden(g, f"in_{tag}_")
+    view, xr, yr = _view(cols, CANVASES[cname])
+    n = 0
+    for rname, spec in SPECS.items():
+        key = f"pts_{tag}_{cname}_{rname}"
+        if key not in g.files:
+            continue
+        assert_agg_equal(ora.points(cols, "x", "y", spec, view), g[key], key)
+        n += 1
+    assert n >= 5
+    # coords and ranges (core.py:83-99, pandas.py:61-66)
+    np.testing.assert_array_equal(ora.axis_index((view.sx, view.tx), view.width), g[f"pts_{tag}_{cname}_xcoords"])
+    np.testing.assert_array_equal(ora.axis_index((view.sy, view.ty), view.height), g[f"pts_{tag}_{cname}_ycoords"])
+    np.testing.assert_array_equal(np.asarray(xr, dtype=np.float64), g[f"pts_{tag}_{cname}_xrange"])
+    np.testing.assert_array_equal(np.asarray(yr, dtype=np.float64), g[f"pts_{tag}_{cname}_yrange"])
+
+
+def test_points_log_axes_golden():
+    g = load("points.npz")
+    cols = {k: g[f"in_log_{k}"] for k in ("x", "y", "v32")}
+    view = ora.make_view(40, 30, (1, 1000), (1, 100), "log", "log")
+    assert_agg_equal(ora.points(cols, "x", "y", ("count",), view), g["pts_log_count"], "log count")
+    assert_agg_equal(ora.points(cols, "x", "y", ("max", "v32"), view), g["pts_log_max_v32"], "log max")
+    np.testing.assert_allclose(ora.axis_index((view.sx, view.tx), 40, "log"), g["pts_log_xcoords"], rtol=1e-15)
+    np.testing.assert_allclose(ora.axis_index((view.sy, view.ty), 30, "log"), g["pts_log_ycoords"], rtol=1e-15)
+
+
+@pytest.mark.parametrize("nparts", [1, 3, 4])
+def test_partitioned_golden(nparts):
+    """dask-style partition + combine (data_libraries/dask.py:168-217) equals the single pass."""
+    g = load("partitioned.npz")
+    cols = columns_from_golden(g, "in_")
+    view = ora.make_view(37, 23, (-0.1, 1.05), (0.1, 0.9))
+    for key in g.files:
+        if not key.startswith("part3_"):
+            continue
+        rname = key[len("part3_"):]
+        got = ora.points(cols, "x", "y", SPECS[rname], view, npartitions=nparts)
+        assert_agg_equal(got, g[key], f"{key} nparts={nparts}")
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("cname", list(LINE_CANVASES))
+def test_lines_golden(tag, cname):
+    g = load("lines.npz")
+    xs, ys, val = g[f"in_{tag}_xs"], g[f"in_{tag}_ys"], g[f"in_{tag}_val"]
+    ckw = LINE_CANVASES[cname]
+    view = ora.make_view(ckw["plot_width"], ckw["plot_height"], ckw["x_range"], ckw["y_range"])
+    n = 0
+    for key in g.files:
+        pre = f"ln_{tag}_{cname}_lw"
+        if not key.startswith(pre):
+            continue
+        lw, aname = key[len(pre):].split("_")
+        lw = float(lw)
+        values = None if aname in ("any", "count") else val
+        got = ora.lines_axis1(xs, ys, view, agg=aname, values=values, line_width=lw)
+        want = g[key]
+        assert got.dtype == want.dtype and got.shape == want.shape, key
+        if lw > 0 and aname in ("count", "sum"):
+            np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True, err_msg=key)
+        else:
+            assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), key
+        n += 1
+    assert n >= 8
+
+
+# ---- the reference's own literal tables (datashader/tests/test_pandas.py:27-59, 100, 194-243, 698-738)
+def _ref_fixture():
+    nan = np.nan
+    cols = {
+        "x": np.array(([0.] * 10 + [1] * 10)),
+        "y": np.array(([0.] * 5 + [1] * 5 + [0] * 5 + [1] * 5)),
+        "log_x": np.array(([1.] * 10 + [10] * 10)),
+        "log_y": np.array(([1.] * 5 + [10] * 5 + [1] * 5 + [10] * 5)),
+        "i32": np.arange(20, dtype="i4"), "i64": np.arange(20, dtype="i8"),
+        "f32": np.arange(20, dtype="f4"), "f64": np.arange(20, dtype="f8"),
+        "reverse": np.arange(20, 0, -1, dtype="f8"),
+        "plusminus": np.arange(20, dtype="f8") * ([1, -1] * 10),
+        "cat": np.array([0] * 5 + [1] * 5 + [2] * 5 + [3] * 5, dtype=np.int8), "cat__ncat": 4,
+    }
+    for c in ("f32", "f64", "reverse", "plusminus"):
+        cols[c] = cols[c].copy()
+        cols[c][2] = nan
+    cols["f64"][2] = nan
+    return cols
+
+
+def test_reference_known_answers():
+    cols = _ref_fixture()
+    view = ora.make_view(2, 2, (0, 1), (0, 1))
+    nan = np.nan
+    pts = lambda spec: ora.points(cols, "x", "y", spec, view)   # noqa: E731
+    np.testing.assert_array_equal(pts(("count",)), np.array([[5, 5], [5, 5]], dtype="u4"))          # :194-203
+    np.testing.assert_array_equal(pts(("count", "f32")), np.array([[4, 5], [5, 5]], dtype="u4"))
+    np.testing.assert_array_equal(pts(("any", "f64")), np.array([[True, True], [True, True]]))     # :206-214
+    s = pts(("sum", "i32"))                                                                            # :217-225
+    np.testing.assert_array_equal(s, cols["i32"].reshape(2, 2, 5).sum(axis=2, dtype="f8").T)
+    np.testing.assert_array_equal(pts(("sum", "f64")), np.nansum(cols["f64"].reshape(2, 2, 5), axis=2).T)
+    np.testing.assert_array_equal(pts(("min", "f32")), np.nanmin(cols["f64"].reshape(2, 2, 5), axis=2).T)   # :228-234
+    np.testing.assert_array_equal(pts(("max", "f32")), np.nanmax(cols["f64"].reshape(2, 2, 5), axis=2).T)   # :237-243
+    np.testing.assert_allclose(pts(("mean", "f32")), np.nanmean(cols["f64"].reshape(2, 2, 5), axis=2).T)  # :698-706
+    sol = np.array([[[5, 0, 0, 0], [0, 0, 5, 0]], [[0, 5, 0, 0], [0, 0, 0, 5]]], dtype="u4")          # :731-738
+    np.testing.assert_array_equal(pts(("by", "cat", ("count",))), sol)
+    np.testing.assert_array_equal(pts(("first", "f32")), np.array([[0, 10], [5, 15]], dtype="f8"))     # :991-996
+    np.testing.assert_array_equal(pts(("last", "f32")), np.array([[4, 14], [9, 19]], dtype="f8"))      # :999-1004
+    np.testing.assert_array_equal(pts(("where", ("first", "f32"), None)), np.array([[0, 10], [5, 15]]))  # :448-462
+    np.testing.assert_array_equal(pts(("where", ("last", "f32"), None)), np.array([[4, 14], [9, 19]]))   # :465-479
+    np.testing.assert_array_equal(pts(("where", ("max", "f32"), None)), np.array([[4, 14], [9, 19]]))    # :482-494
+    np.testing.assert_array_equal(pts(("where", ("min", "f32"), None)), np.array([[0, 10], [5, 15]]))    # :497-509
+    np.testing.assert_array_equal(pts(("where", ("max", "f32"), "reverse")), np.array([[16, 6], [11, 1]], dtype="f8"))
+    np.testing.assert_array_equal(pts(("where", ("first", "f32"), "reverse")), np.array([[20, 10], [15, 5]], dtype="f8"))
+    _ = nan
+
+
+def test_reference_uniform_points_upper_edge_fold():
+    """test_pandas.py:1132-1144: 101 points over [0,100] into 10 bins -> 10,...,10,11."""
+    n = 101
+    cols = {"x": np.arange(n, dtype="f8"), "y": np.zeros(n)}
+    view = ora.make_view(10, 1, (0, 100), (-1, 1))
+    got = ora.points(cols, "x", "y", ("count",), view)
+    np.testing.assert_array_equal(got, np.array([[10] * 9 + [11]], dtype="u4"))
+
+
+def test_no_fma_contraction_in_mapping():
+    """x*sx+tx must be evaluated unfused like numba does. Find inputs where the fused
+    and unfused results truncate to different pixels and check the oracle takes the unfused one."""
+    rng = np.random.default_rng(5)
+    W = 900
+    xr = (-0.3337, 1.2771)
+    s, t = ora.scale_and_translate(xr, W)
+    x = (rng.random(2_000_000) * (xr[1] - xr[0]) + xr[0]).astype(np.float32).astype(np.float64)
+    unfused = (x * s + t).astype(np.int64)
+    import math
+    # exact fused value via integer-exact long double is not available in numpy: use fractions on candidates
+    near = np.nonzero(np.abs((x * s + t) - np.rint(x * s + t)) < 1e-12)[0]
+    from fractions import Fraction
+    diff = []
+    for i in near:
+        exact = Fraction(float(x[i])) * Fraction(s) + Fraction(t)
+        fused = int(math.floor(float(exact))) if exact >= 0 else int(float(exact))
+        if fused != unfused[i]:
+            diff.append(i)
+    xs = x[diff] if diff else x[near[:8]]
+    cols = {"x": xs.astype(np.float32), "y": np.zeros(len(xs), dtype=np.float32)}
+    view = ora.make_view(W, 1, xr, (-1, 1))
+    got = ora.points(cols, "x", "y", ("count",), view)
+    want = np.bincount(np.minimum((xs * s + t).astype(np.int64), W - 1), minlength=W).astype("u4")[None, :]
+    np.testing.assert_array_equal(got, want)
