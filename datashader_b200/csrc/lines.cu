@@ -1,0 +1,394 @@
+// Line glyph (LinesAxis1): per-segment Liang-Barsky clip + snapped Bresenham or the full antialiased
+// rasteriser, fused with the reduction.  Replaces _build_extend_line_axis1_none_constant.extend_cuda
+// (glyphs/line.py:1321-1332), _build_draw_segment (:1033-1097), _build_bresenham (:986-1031) and
+// _build_full_antialias (:826-983).  The reference has NO antialiasing on its CUDA path
+// (core.py:454-459); here the antialiased single-stage combinations run on the GPU.
+//
+// All geometry is f64 with unfused multiply/add (-fmad=false semantics via _rn intrinsics where the
+// result feeds a floor/ceil/compare), matching the numba CPU arithmetic that the oracle pins.
+#include "common.cuh"
+#include <limits.h>
+
+struct LineArgs {
+  dsb_view v;
+  const void* xs;
+  const void* ys;
+  long long nlines, nverts;
+  const void* val;
+  int val_dtype;
+  int agg;
+  double line_width;
+  void* canvas;
+  uint8_t* mask;
+  long long xxmax, yymax;   // round(mapper(xmax)*sx+tx): map_onto_pixel_snap, line.py:714-715
+  long long nx, ny;         // round((xmax-xmin)*sx): draw_segment, line.py:1087-1088
+  int overwrite;
+};
+
+__device__ __forceinline__ double fmul64(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double fadd64(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double fsub64(double a, double b) { return __dadd_rn(a, -b); }
+
+struct LineCtx {
+  int agg;
+  bool has_field;
+  double field;
+  bool field_nan;
+  long long width;
+  void* canvas;
+  uint8_t* mask;
+};
+
+// ---- appends, line_width == 0 (reductions.py _append / _append_no_field) ------------------------
+__device__ __forceinline__ void append_px(const LineCtx& c, long long x, long long y) {
+  const long long cell = y * c.width + x;
+  switch (c.agg) {
+    case DSB_LINE_ANY:
+      if (c.has_field && c.field_nan) return;
+      ((uint8_t*)c.canvas)[cell] = 1;
+      return;
+    case DSB_LINE_COUNT:
+      if (c.has_field && c.field_nan) return;
+      atomicAdd((unsigned int*)c.canvas + cell, 1u);
+      return;
+    case DSB_LINE_SUM:
+      if (c.field_nan) return;
+      atomicAdd((double*)c.canvas + cell, c.field);
+      c.mask[cell] = 1;
+      return;
+    case DSB_LINE_MAX:
+      if (c.field_nan) return;
+      atomicMax((long long*)c.canvas + cell, key64_from_f64(c.field));
+      return;
+    case DSB_LINE_MIN:
+      if (c.field_nan) return;
+      atomicMin((long long*)c.canvas + cell, key64_from_f64(c.field));
+      return;
+  }
+}
+
+// ---- appends, antialiased (reductions.py _append_antialias / _append_no_field_antialias) --------
+__device__ __forceinline__ void append_aa(const LineCtx& c, long long x, long long y, double aa, double prev_aa) {
+  const long long cell = y * c.width + x;
+  switch (c.agg) {
+    case DSB_LINE_ANY:     // max of aa_factor, stored as f32 (reductions.py:850-869)
+      if (c.has_field && c.field_nan) return;
+      atomicMax((int*)c.canvas + cell, key32_from_f32((float)aa));
+      return;
+    case DSB_LINE_COUNT:   // SUM_1AGG: += aa - prev (reductions.py:560-568, 586-592)
+      if (c.has_field && c.field_nan) return;
+      atomicAdd((float*)c.canvas + cell, (float)fsub64(aa, prev_aa));
+      c.mask[cell] = 1;
+      return;
+    case DSB_LINE_SUM: {   // reductions.py:1065-1075
+      double v = fmul64(c.field, fsub64(aa, prev_aa));
+      if (v != v) return;
+      atomicAdd((double*)c.canvas + cell, v);
+      c.mask[cell] = 1;
+      return;
+    }
+    case DSB_LINE_MAX: {   // reductions.py:1229-1236
+      double v = fmul64(c.field, aa);
+      if (v != v) return;
+      atomicMax((long long*)c.canvas + cell, key64_from_f64(v));
+      return;
+    }
+  }
+}
+
+// line.py:783-800
+__device__ __forceinline__ bool clipt(double p, double q, double& t0, double& t1) {
+  if (p < 0 && q < 0) {
+    double r = __ddiv_rn(q, p);
+    if (r > t1) return false;
+    else if (r > t0) t0 = r;
+  } else if (p > 0 && q < p) {
+    double r = __ddiv_rn(q, p);
+    if (r < t0) return false;
+    else if (r < t1) t1 = r;
+  } else if (q < 0) {
+    return false;
+  }
+  return true;
+}
+
+template <typename XY> __device__ __forceinline__ double seg_delta(double a1, double a0);
+// numba types the vertex values as float32 inside _liang_barsky, so x1 - x0 rounds to float32
+template <> __device__ __forceinline__ double seg_delta<float>(double a1, double a0) { return (double)__fsub_rn((float)a1, (float)a0); }
+template <> __device__ __forceinline__ double seg_delta<double>(double a1, double a0) { return fsub64(a1, a0); }
+
+__device__ __forceinline__ double clampd(double x, double lo, double hi) { return fmax(lo, fmin(x, hi)); }
+__device__ __forceinline__ double linearstep(double e0, double e1, double x) {
+  return clampd(__ddiv_rn(fsub64(x, e0), fsub64(e1, e0)), 0.0, 1.0);
+}
+__device__ __forceinline__ double x_intercept(double y, double cx0, double cy0, double cx1, double cy1) {
+  if (cy0 == cy1) return cx1;
+  double frac = __ddiv_rn(fsub64(y, cy0), fsub64(cy1, cy0));
+  return fadd64(cx0, fmul64(frac, fsub64(cx1, cx0)));
+}
+
+// line.py:986-1031
+__device__ void bresenham(const LineCtx& c, bool segment_start, long long x0, long long x1, long long y0, long long y1,
+                          bool clipped) {
+  long long dx = x1 - x0;
+  long long ix = (dx > 0) - (dx < 0);
+  dx = llabs(dx) * 2;
+  long long dy = y1 - y0;
+  long long iy = (dy > 0) - (dy < 0);
+  dy = llabs(dy) * 2;
+  if (!clipped && !(dx | dy)) { append_px(c, x0, y0); return; }
+  if (segment_start) append_px(c, x0, y0);
+  if (dx >= dy) {
+    long long error = 2 * dy - dx;
+    while (x0 != x1) {
+      if (error >= 0 && (error || ix > 0)) { error -= 2 * dx; y0 += iy; }
+      error += 2 * dy;
+      x0 += ix;
+      append_px(c, x0, y0);
+    }
+  } else {
+    long long error = 2 * dx - dy;
+    while (y0 != y1) {
+      if (error >= 0 && (error || iy > 0)) { error -= 2 * dy; x0 += ix; }
+      error += 2 * dx;
+      y0 += iy;
+      append_px(c, x0, y0);
+    }
+  }
+}
+
+// line.py:830-981
+__device__ void full_antialias(const LineCtx& c, double line_width, bool overwrite, double x0, double x1, double y0,
+                               double y1, bool segment_start, bool segment_end, double xm, double ym, long long nx,
+                               long long ny) {
+  if (x0 == x1 && y0 == y1) return;
+  const bool flip_xy = fabs(fsub64(x0, x1)) < fabs(fsub64(y0, y1));
+  if (flip_xy) {
+    double t;
+    t = x0; x0 = y0; y0 = t;
+    t = x1; x1 = y1; y1 = t;
+    t = xm; xm = ym; ym = t;
+  }
+  double scale = 1.0;
+  if (line_width < 1.0) { scale = fmul64(scale, line_width); line_width = 1.0; }
+  const double aa = 1.0;
+  const double halfwidth = fmul64(0.5, fadd64(line_width, aa));
+  const bool flip_order = y1 < y0 || (y1 == y0 && x1 < x0);
+  double alongx = fsub64(x1, x0), alongy = fsub64(y1, y0);
+  const double length = __dsqrt_rn(fadd64(fmul64(alongx, alongx), fmul64(alongy, alongy)));
+  alongx = __ddiv_rn(alongx, length);
+  alongy = __ddiv_rn(alongy, length);
+  const double rightx = alongy, righty = -alongx;
+  double bx[4], by[4];
+  if (flip_order) {
+    bx[0] = fsub64(x1, fmul64(halfwidth, fsub64(rightx, alongx)));
+    bx[1] = fsub64(x1, fmul64(halfwidth, fsub64(-rightx, alongx)));
+    bx[2] = fsub64(x0, fmul64(halfwidth, fadd64(-rightx, alongx)));
+    bx[3] = fsub64(x0, fmul64(halfwidth, fadd64(rightx, alongx)));
+    by[0] = fsub64(y1, fmul64(halfwidth, fsub64(righty, alongy)));
+    by[1] = fsub64(y1, fmul64(halfwidth, fsub64(-righty, alongy)));
+    by[2] = fsub64(y0, fmul64(halfwidth, fadd64(-righty, alongy)));
+    by[3] = fsub64(y0, fmul64(halfwidth, fadd64(righty, alongy)));
+  } else {
+    bx[0] = fadd64(x0, fmul64(halfwidth, fsub64(rightx, alongx)));
+    bx[1] = fadd64(x0, fmul64(halfwidth, fsub64(-rightx, alongx)));
+    bx[2] = fadd64(x1, fmul64(halfwidth, fadd64(-rightx, alongx)));
+    bx[3] = fadd64(x1, fmul64(halfwidth, fadd64(rightx, alongx)));
+    by[0] = fadd64(y0, fmul64(halfwidth, fsub64(righty, alongy)));
+    by[1] = fadd64(y0, fmul64(halfwidth, fsub64(-righty, alongy)));
+    by[2] = fadd64(y1, fmul64(halfwidth, fadd64(-righty, alongy)));
+    by[3] = fadd64(y1, fmul64(halfwidth, fadd64(righty, alongy)));
+  }
+  long long xmax = nx - 1, ymax = ny - 1;
+  if (flip_xy) { long long t = xmax; xmax = ymax; ymax = t; }
+  int lowindex;
+  if (flip_order) lowindex = x0 > x1 ? 0 : 1;
+  else lowindex = x1 > x0 ? 0 : 1;
+  double prev_alongx = 0, prev_alongy = 0, prev_length = 0, prev_rightx = 0, prev_righty = 0;
+  if (!overwrite && !segment_start) {
+    prev_alongx = fsub64(x0, xm);
+    prev_alongy = fsub64(y0, ym);
+    prev_length = __dsqrt_rn(fadd64(fmul64(prev_alongx, prev_alongx), fmul64(prev_alongy, prev_alongy)));
+    if (prev_length > 0.0) {
+      prev_alongx = __ddiv_rn(prev_alongx, prev_length);
+      prev_alongy = __ddiv_rn(prev_alongy, prev_length);
+      prev_rightx = prev_alongy;
+      prev_righty = -prev_alongx;
+    } else {
+      overwrite = true;
+    }
+  }
+  const long long ystart = (long long)clampd(ceil(by[lowindex]), 0.0, (double)ymax);
+  const long long yend = (long long)clampd(floor(by[(lowindex + 2) & 3]), 0.0, (double)ymax);
+  int ll = lowindex, lu = (ll + 1) & 3, rl = lowindex, ru = (rl + 3) & 3;
+  const double e0 = fmul64(0.5, fsub64(line_width, aa));
+  for (long long y = ystart; y <= yend; y++) {
+    const double yd = (double)y;
+    if (ll == lowindex && yd > by[lu]) { ll = lu; lu = (ll + 1) & 3; }
+    if (rl == lowindex && yd > by[ru]) { rl = ru; ru = (rl + 3) & 3; }
+    const long long xleft = (long long)clampd(ceil(x_intercept(yd, bx[ll], by[ll], bx[lu], by[lu])), 0.0, (double)xmax);
+    const long long xright = (long long)clampd(floor(x_intercept(yd, bx[rl], by[rl], bx[ru], by[ru])), 0.0, (double)xmax);
+    const double ry0 = fsub64(yd, y0), ry1 = fsub64(yd, y1);
+    for (long long x = xleft; x <= xright; x++) {
+      const double rx0 = fsub64((double)x, x0);
+      const double along = fadd64(fmul64(rx0, alongx), fmul64(ry0, alongy));
+      bool prev_correction = false;
+      double distance;
+      if (along < 0.0) {
+        if (overwrite || segment_start || fadd64(fmul64(rx0, prev_alongx), fmul64(ry0, prev_alongy)) > 0.0)
+          distance = __dsqrt_rn(fadd64(fmul64(rx0, rx0), fmul64(ry0, ry0)));
+        else continue;
+      } else if (along > length) {
+        if (overwrite || segment_end) {
+          const double rx1 = fsub64((double)x, x1);
+          distance = __dsqrt_rn(fadd64(fmul64(rx1, rx1), fmul64(ry1, ry1)));
+        } else continue;
+      } else {
+        distance = fabs(fadd64(fmul64(rx0, rightx), fmul64(ry0, righty)));
+        if (!overwrite && !segment_start) {
+          const double pa = fadd64(fmul64(rx0, prev_alongx), fmul64(ry0, prev_alongy));
+          if (-prev_length <= pa && pa <= 0.0 && fabs(fadd64(fmul64(rx0, prev_rightx), fmul64(ry0, prev_righty))) <= halfwidth)
+            prev_correction = true;
+        }
+      }
+      double value = fmul64(fsub64(1.0, linearstep(e0, halfwidth, distance)), scale);
+      double prev_value = 0.0;
+      if (prev_correction) {
+        const double prev_distance = fabs(fadd64(fmul64(rx0, prev_rightx), fmul64(ry0, prev_righty)));
+        prev_value = fmul64(fsub64(1.0, linearstep(e0, halfwidth, prev_distance)), scale);
+        if (value <= prev_value) value = 0.0;
+      }
+      if (value > 0.0) {
+        if (flip_xy) append_aa(c, y, x, value, prev_value);
+        else append_aa(c, x, y, value, prev_value);
+      }
+    }
+  }
+}
+
+template <typename XY>
+__device__ __forceinline__ double map_axis(bool is_log, double v) {
+  // after clipping the coordinate is float64 (the clipped value is computed in f64), so the log
+  // mapper sees a float64 unless the vertex is an unclipped float32 value: the reference's numba
+  // unifies x0 to float64 on return from _liang_barsky, so log10 is always the f64 one here.
+  return is_log ? log10(v) : v;
+}
+
+// line.py:1045-1097
+template <typename XY>
+__device__ void draw_segment(const LineArgs& a, const LineCtx& c, bool segment_start, bool segment_end, double x0,
+                             double x1, double y0, double y1, double xm, double ym) {
+  const dsb_view& v = a.v;
+  bool skip = (x0 != x0) || (y0 != y0) || (x1 != x1) || (y1 != y1);
+  // _liang_barsky, line.py:734-780
+  if (x0 < v.xmin && x1 < v.xmin) skip = true;
+  else if (x0 > v.xmax && x1 > v.xmax) skip = true;
+  else if (y0 < v.ymin && y1 < v.ymin) skip = true;
+  else if (y0 > v.ymax && y1 > v.ymax) skip = true;
+  double t0 = 0.0, t1 = 1.0;
+  const double dx1 = seg_delta<XY>(x1, x0);
+  if (!clipt(-dx1, fsub64(x0, v.xmin), t0, t1)) skip = true;
+  if (!clipt(dx1, fsub64(v.xmax, x0), t0, t1)) skip = true;
+  const double dy1 = seg_delta<XY>(y1, y0);
+  if (!clipt(-dy1, fsub64(y0, v.ymin), t0, t1)) skip = true;
+  if (!clipt(dy1, fsub64(v.ymax, y0), t0, t1)) skip = true;
+  if (skip) return;
+  bool clipped_start = false, clipped_end = false;
+  if (t1 < 1) { clipped_end = true; x1 = fadd64(x0, fmul64(t1, dx1)); y1 = fadd64(y0, fmul64(t1, dy1)); }
+  if (t0 > 0) { clipped_start = true; x0 = fadd64(x0, fmul64(t0, dx1)); y0 = fadd64(y0, fmul64(t0, dy1)); }
+  const bool clipped = clipped_start || clipped_end;
+  segment_start = segment_start || clipped_start;
+  if (a.line_width > 0.0) {
+    // map_onto_pixel_no_snap, line.py:722-726
+    const double x0p = fsub64(fadd64(fmul64(map_axis<XY>(v.x_log, x0), v.sx), v.tx), 0.5);
+    const double y0p = fsub64(fadd64(fmul64(map_axis<XY>(v.y_log, y0), v.sy), v.ty), 0.5);
+    const double x1p = fsub64(fadd64(fmul64(map_axis<XY>(v.x_log, x1), v.sx), v.tx), 0.5);
+    const double y1p = fsub64(fadd64(fmul64(map_axis<XY>(v.y_log, y1), v.sy), v.ty), 0.5);
+    double xmp = 0.0, ymp = 0.0;
+    if (!segment_start) {
+      xmp = fsub64(fadd64(fmul64(map_axis<XY>(v.x_log, xm), v.sx), v.tx), 0.5);
+      ymp = fsub64(fadd64(fmul64(map_axis<XY>(v.y_log, ym), v.sy), v.ty), 0.5);
+    }
+    full_antialias(c, a.line_width, a.overwrite != 0, x0p, x1p, y0p, y1p, segment_start, segment_end, xmp, ymp, a.nx, a.ny);
+  } else {
+    // map_onto_pixel_snap, line.py:689-720
+    long long x0i = (long long)__double2ll_rz(fadd64(fmul64(map_axis<XY>(v.x_log, x0), v.sx), v.tx));
+    long long y0i = (long long)__double2ll_rz(fadd64(fmul64(map_axis<XY>(v.y_log, y0), v.sy), v.ty));
+    long long x1i = (long long)__double2ll_rz(fadd64(fmul64(map_axis<XY>(v.x_log, x1), v.sx), v.tx));
+    long long y1i = (long long)__double2ll_rz(fadd64(fmul64(map_axis<XY>(v.y_log, y1), v.sy), v.ty));
+    if (x0i == a.xxmax) x0i--;
+    if (y0i == a.yymax) y0i--;
+    if (x1i == a.xxmax) x1i--;
+    if (y1i == a.yymax) y1i--;
+    bresenham(c, segment_start, x0i, x1i, y0i, y1i, clipped);
+  }
+}
+
+// one thread per (line, segment): extend_cuda, line.py:1321-1332 + perform_extend_line :1250-1275
+template <typename XY>
+__global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
+  const XY* __restrict__ xs = (const XY*)a.xs;
+  const XY* __restrict__ ys = (const XY*)a.ys;
+  const long long nseg = a.nverts - 1;
+  const long long total = a.nlines * nseg;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) {
+    const long long i = s / nseg, j = s - i * nseg;
+    const long long o = i * a.nverts + j;
+    const double x0 = (double)xs[o], y0 = (double)ys[o], x1 = (double)xs[o + 1], y1 = (double)ys[o + 1];
+    bool segment_start = (j == 0);
+    double xm = 0.0, ym = 0.0;
+    if (!segment_start) {
+      xm = (double)xs[o - 1]; ym = (double)ys[o - 1];
+      segment_start = (xm != xm) || (ym != ym);
+      if (segment_start) { xm = 0.0; ym = 0.0; }
+    }
+    bool segment_end = (j == a.nverts - 2);
+    if (!segment_end) {
+      const double xn = (double)xs[o + 2], yn = (double)ys[o + 2];
+      segment_end = (xn != xn) || (yn != yn);
+    }
+    LineCtx c;
+    c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
+    c.field = c.has_field ? load_f64(a.val, a.val_dtype, i) : 0.0;
+    c.field_nan = c.has_field && (c.field != c.field);
+    draw_segment<XY>(a, c, segment_start, segment_end, x0, x1, y0, y1, xm, ym);
+  }
+}
+
+static long long py_round(double v) { return (long long)nearbyint(v); }   // Python round(): half to even
+
+extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                               int64_t nverts, const void* val, int32_t val_dtype, int32_t agg, double line_width,
+                               void* canvas, uint8_t* mask, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0 || !canvas) { dsb_set_error("dsb_lines_axis1: bad view/canvas"); return DSB_ERR_ARG; }
+  if (agg < DSB_LINE_ANY || agg > DSB_LINE_MIN) { dsb_set_error("dsb_lines_axis1: unknown agg %d", agg); return DSB_ERR_ARG; }
+  const bool aa = line_width > 0.0;
+  if (aa && agg == DSB_LINE_MIN) { dsb_set_error("dsb_lines_axis1: antialiased min needs the 2-stage combine"); return DSB_ERR_UNSUPPORTED; }
+  if ((agg == DSB_LINE_SUM || agg == DSB_LINE_MAX || agg == DSB_LINE_MIN) && (val_dtype == DSB_NONE || !val)) {
+    dsb_set_error("dsb_lines_axis1: this reduction needs a value column"); return DSB_ERR_ARG;
+  }
+  if ((agg == DSB_LINE_SUM || (aa && agg == DSB_LINE_COUNT)) && !mask) { dsb_set_error("dsb_lines_axis1: mask canvas required"); return DSB_ERR_ARG; }
+  if (nlines <= 0 || nverts < 2) return DSB_OK;
+  if (!xs || !ys) { dsb_set_error("dsb_lines_axis1: null vertex arrays"); return DSB_ERR_ARG; }
+  LineArgs a;
+  a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
+  a.agg = agg; a.line_width = line_width; a.canvas = canvas; a.mask = mask;
+  const double mx = view->x_log ? log10(view->xmax) : view->xmax, my = view->y_log ? log10(view->ymax) : view->ymax;
+  a.xxmax = py_round(mx * view->sx + view->tx);
+  a.yymax = py_round(my * view->sy + view->ty);
+  a.nx = py_round((view->xmax - view->xmin) * view->sx);
+  a.ny = py_round((view->ymax - view->ymin) * view->sy);
+  a.overwrite = !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM);   // antialias.py:47-56
+  const long long total = nlines * (nverts - 1);
+  const int threads = 128;
+  long long want = (total + threads - 1) / threads;
+  long long cap = (long long)dsb_num_sms() * 16;
+  int grid = (int)(want < cap ? want : cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (xy_dtype == DSB_F32) k_lines_axis1<float><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F64) k_lines_axis1<double><<<grid, threads, 0, s>>>(a);
+  else { dsb_set_error("dsb_lines_axis1: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+  DSB_CUDA_CHECK_LAUNCH("dsb_lines_axis1");
+  return DSB_OK;
+}

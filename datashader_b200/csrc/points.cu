@@ -1,0 +1,167 @@
+// Fused glyph projection + reduction for points (K1: the general path, L2-resident global atomics).
+//
+// Replaces Point._build_extend.extend_cuda (glyphs/points.py:188-221) together with the generated
+// append() (compiler.py:321-475).  One pass over the x / y / value columns; every base reduction is a
+// commutative accumulator (see dsb_op in include/dsb200.h), so a row costs one RED per base and no
+// per-pixel mutex is needed (the reference spin-locks one for where/first, _cuda_utils.py:177-199).
+#include "common.cuh"
+
+struct PointsArgs {
+  dsb_view v;
+  const void* x;
+  const void* y;
+  long long n;
+  long long row_offset;
+  dsb_plan plan;
+};
+
+__device__ __forceinline__ int load_cat(const void* p, int dt, long long i) {
+  switch (dt) {
+    case DSB_I8: return (int)__ldg((const int8_t*)p + i);
+    case DSB_I16: return (int)__ldg((const int16_t*)p + i);
+    case DSB_I32: return __ldg((const int32_t*)p + i);
+    case DSB_I64: return (int)__ldg((const long long*)p + i);
+    case DSB_U8: return (int)__ldg((const uint8_t*)p + i);
+  }
+  return -1;
+}
+
+__device__ __forceinline__ void apply_base(const dsb_base& b, long long cell, long long i, long long row) {
+  // nan_check_column: skip the whole base when that column is null (compiler.py:439-446, 461-466)
+  if (b.chk_dtype != DSB_NONE && col_isnan(b.chk, b.chk_dtype, i)) return;
+  switch (b.op) {
+    case DSB_OP_COUNT:
+      if (b.val_dtype != DSB_NONE && col_isnan(b.val, b.val_dtype, i)) return;
+      atomicAdd((unsigned int*)b.agg + cell, 1u);
+      return;
+    case DSB_OP_ANY:
+      if (b.val_dtype != DSB_NONE && col_isnan(b.val, b.val_dtype, i)) return;
+      ((uint8_t*)b.agg)[cell] = 1;   // idempotent store, same as the reference (reductions.py:872-873)
+      return;
+    case DSB_OP_SUM: {
+      double f = load_f64(b.val, b.val_dtype, i);
+      if (f != f) return;
+      atomicAdd((double*)b.agg + cell, f);
+      return;
+    }
+    case DSB_OP_MAX32:
+    case DSB_OP_MIN32: {
+      bool nan;
+      int32_t k = load_key32(b.val, b.val_dtype, i, &nan);
+      if (nan) return;
+      if (b.op == DSB_OP_MAX32) atomicMax((int*)b.agg + cell, k);
+      else atomicMin((int*)b.agg + cell, k);
+      return;
+    }
+    case DSB_OP_MAX64:
+    case DSB_OP_MIN64: {
+      double f = load_f64(b.val, b.val_dtype, i);
+      if (f != f) return;
+      long long k = key64_from_f64(f);
+      if (b.op == DSB_OP_MAX64) atomicMax((long long*)b.agg + cell, k);
+      else atomicMin((long long*)b.agg + cell, k);
+      return;
+    }
+    case DSB_OP_MAXROW:
+      atomicMax((long long*)b.agg + cell, row);
+      return;
+    case DSB_OP_MINROW:
+      atomicMin((long long*)b.agg + cell, row);
+      return;
+    case DSB_OP_ARGMAX32:
+    case DSB_OP_ARGMIN32: {
+      bool nan;
+      int32_t k = load_key32(b.val, b.val_dtype, i, &nan);
+      if (nan) return;
+      // ties go to the earliest row: for max the row field is complemented so that a smaller row is larger
+      if (b.op == DSB_OP_ARGMAX32) {
+        long long p = ((long long)k << 32) | (long long)(uint32_t)(~(uint32_t)i);
+        atomicMax((long long*)b.agg + cell, p);
+      } else {
+        long long p = ((long long)k << 32) | (long long)(uint32_t)i;
+        atomicMin((long long*)b.agg + cell, p);
+      }
+      return;
+    }
+    case DSB_OP_MATCHROW64: {
+      double f = load_f64(b.val, b.val_dtype, i);
+      if (f != f) return;
+      if (key64_from_f64(f) == __ldg((const long long*)b.aux + cell)) atomicMin((long long*)b.agg + cell, row);
+      return;
+    }
+  }
+}
+
+// One point per thread per step, 4 independent steps in flight (coalesced 4-byte loads; the path is
+// bound by the RED rate, not by load issue - see profiles/r01_ubench.md).
+template <typename XY>
+__global__ void __launch_bounds__(256) k_points_generic(const PointsArgs a) {
+  const XY* __restrict__ x = (const XY*)a.x;
+  const XY* __restrict__ y = (const XY*)a.y;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int ncat = a.plan.ncat;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < a.n; i0 += 4 * stride) {
+    XY xs[4], ys[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      long long i = i0 + u * stride;
+      if (i < a.n) { xs[u] = __ldcs(x + i); ys[u] = __ldcs(y + i); }
+      else { xs[u] = (XY)NAN; ys[u] = (XY)NAN; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      long long i = i0 + u * stride;
+      long long cell = map_to_cell<XY>(a.v, xs[u], ys[u]);
+      if (cell < 0) continue;
+      if (ncat > 0) {
+        int c = load_cat(a.plan.cat, a.plan.cat_dtype, i);
+        if (c < 0) c += ncat;                 // numba wraparound for agg[:, :, -1]
+        if (c < 0 || c >= ncat) continue;
+        cell = cell * ncat + c;
+      }
+      for (int k = 0; k < a.plan.nops; k++) apply_base(a.plan.ops[k], cell, i, a.row_offset + i);
+    }
+  }
+}
+
+static int validate_plan(const dsb_plan* p) {
+  if (!p || p->nops < 1 || p->nops > DSB_MAX_OPS) { dsb_set_error("dsb_points: bad plan (nops)"); return DSB_ERR_ARG; }
+  for (int k = 0; k < p->nops; k++) {
+    const dsb_base& b = p->ops[k];
+    if (!b.agg) { dsb_set_error("dsb_points: op %d has no canvas", k); return DSB_ERR_ARG; }
+    bool needs_val = !(b.op == DSB_OP_COUNT || b.op == DSB_OP_ANY || b.op == DSB_OP_MAXROW || b.op == DSB_OP_MINROW);
+    if (needs_val && (b.val_dtype == DSB_NONE || !b.val)) { dsb_set_error("dsb_points: op %d needs a value column", k); return DSB_ERR_ARG; }
+    if (b.val_dtype != DSB_NONE && !b.val) { dsb_set_error("dsb_points: op %d value pointer is null", k); return DSB_ERR_ARG; }
+    if ((b.op == DSB_OP_MAX32 || b.op == DSB_OP_MIN32 || b.op == DSB_OP_ARGMAX32 || b.op == DSB_OP_ARGMIN32) &&
+        !(b.val_dtype == DSB_F32 || (b.val_dtype >= DSB_I8 && b.val_dtype <= DSB_U32))) {
+      dsb_set_error("dsb_points: op %d needs a <=32-bit value column", k); return DSB_ERR_ARG;
+    }
+    if (b.op == DSB_OP_MATCHROW64 && !b.aux) { dsb_set_error("dsb_points: MATCHROW64 needs aux"); return DSB_ERR_ARG; }
+    if (b.op < DSB_OP_COUNT || b.op > DSB_OP_MATCHROW64) { dsb_set_error("dsb_points: unknown op %d", b.op); return DSB_ERR_ARG; }
+  }
+  if (p->ncat < 0 || (p->ncat > 0 && (!p->cat || p->cat_dtype == DSB_NONE))) { dsb_set_error("dsb_points: bad categorical plan"); return DSB_ERR_ARG; }
+  return DSB_OK;
+}
+
+extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                          int64_t row_offset, const dsb_plan* plan, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points: bad view"); return DSB_ERR_ARG; }
+  if (n < 0 || n > (1LL << 32)) { dsb_set_error("dsb_points: n must be in [0, 2^32] per call"); return DSB_ERR_ARG; }
+  int rc = validate_plan(plan);
+  if (rc != DSB_OK) return rc;
+  if (n == 0) return DSB_OK;
+  if (!x || !y) { dsb_set_error("dsb_points: null coordinate column"); return DSB_ERR_ARG; }
+  if ((int64_t)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1) > (1LL << 40)) { dsb_set_error("dsb_points: canvas too large"); return DSB_ERR_ARG; }
+  PointsArgs a;
+  a.v = *view; a.x = x; a.y = y; a.n = n; a.row_offset = row_offset; a.plan = *plan;
+  const int threads = 256;
+  long long want = (n + (long long)threads * 4 - 1) / ((long long)threads * 4);
+  long long cap = (long long)dsb_num_sms() * 8;   // 8 CTAs of 256 threads per SM: full occupancy, whole waves
+  int grid = (int)(want < cap ? want : cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (xy_dtype == DSB_F32) k_points_generic<float><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F64) k_points_generic<double><<<grid, threads, 0, s>>>(a);
+  else { dsb_set_error("dsb_points: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+  DSB_CUDA_CHECK_LAUNCH("dsb_points");
+  return DSB_OK;
+}

@@ -1,0 +1,306 @@
+"""Host dispatch for the hot path: what data_libraries/pandas.py:26-66 (single pass) and
+data_libraries/dask.py:86-219 (partition + combine) do in the reference, with compiler.py's
+make_create / make_append / make_combine / make_finalize replaced by a plan handed to libdsb200.
+
+    view  = ranges + Axis.compute_scale_and_translate                  (pandas.py:35-46)
+    accs  = unique accumulators of all reductions                      (compiler.py:103-107)
+    launch dsb_points / dsb_lines_axis1 once per <= 8 accumulators     (make_append + extend)
+    [multi-GPU] all-reduce each accumulator canvas                     (make_combine, dask.py:175-217)
+    finalize each reduction, wrap in DataArray / Dataset               (make_finalize, pandas.py:61-66)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import reductions as rd
+from .frame import as_device_frame
+from .glyphs import LinesAxis1, Point, _column_bounds, maybe_expand_bounds
+from .xr_compat import DataArray, Dataset
+
+
+class _Ctx:
+    """Everything a reduction needs to declare accumulators and finish them."""
+
+    def __init__(self, frame, view, shape, dist=None):
+        self.frame = frame
+        self.view = view
+        self.shape = shape            # (H, W) or (H, W, ncat)
+        self.dist = dist
+        self.stream_ptr = torch.cuda.current_stream(frame.device).cuda_stream
+
+    def np_dtype(self, col):
+        return self.frame.np_dtype(col)
+
+    def dsb_dtype(self, col):
+        return _lib.dsb_dtype(self.frame.np_dtype(col))
+
+
+def _auto_range(tensors, stream_ptr, dist, device):
+    """Glyph.compute_x_bounds / compute_bounds_dask (glyphs/points.py:145-167)."""
+    lo, hi = _column_bounds(stream_ptr, tensors)
+    if dist is not None:
+        lo, hi = dist.global_bounds(lo, hi, device)
+    return maybe_expand_bounds((lo, hi))
+
+
+def make_view(canvas, x_range, y_range):
+    """pandas.py:42-46 + core.py:62-81"""
+    x_st = canvas.x_axis.compute_scale_and_translate(x_range, canvas.plot_width)
+    y_st = canvas.y_axis.compute_scale_and_translate(y_range, canvas.plot_height)
+    v = _lib.View(int(canvas.plot_width), int(canvas.plot_height), int(canvas.x_axis.is_log), int(canvas.y_axis.is_log),
+                  float(x_st[0]), float(x_st[1]), float(y_st[0]), float(y_st[1]),
+                  float(x_range[0]), float(x_range[1]), float(y_range[0]), float(y_range[1]))
+    return v, x_st, y_st
+
+
+def _alloc_canvas(acc, shape, device, stream_ptr):
+    dtype, _ = rd.ACC_INFO[acc.kind]
+    t = torch.empty(shape, dtype=dtype, device=device)
+    _lib.check(_lib.lib().dsb_init_canvas(rd.ACC_OP[acc.kind], t.data_ptr(), t.numel(), stream_ptr), "dsb_init_canvas")
+    return t
+
+
+def _xy_columns(frame, xname, yname):
+    x, y = frame[xname], frame[yname]
+    # coordinates are consumed as f32 or f64; anything else is widened the way the reference's
+    # f64 arithmetic would see it (glyphs/points.py:199-201)
+    if x.dtype != y.dtype or x.dtype not in (torch.float32, torch.float64):
+        x, y = x.to(torch.float64), y.to(torch.float64)
+    return x.contiguous(), y.contiguous(), (_lib.F32 if x.dtype == torch.float32 else _lib.F64)
+
+
+def _reductions_of(agg):
+    return list(agg.values) if isinstance(agg, rd.summary) else [agg]
+
+
+def _categorical_setup(agg, frame, schema):
+    """by(): category codes + number of categories (compiler.py:379-390)."""
+    cats = [r for r in _reductions_of(agg) if isinstance(r, rd.by)]
+    if not cats:
+        return None, 0, None
+    keys = {c._hashable_inputs()[:3] for c in cats}
+    if len(keys) > 1 or len(cats) != len(_reductions_of(agg)):
+        raise NotImplementedError("summary() mixing different categorizers / non-categorical reductions "
+                                  "is not supported by datashader_b200 yet")
+    categorizer = cats[0].categorizer
+    labels = categorizer.categories(schema)
+    codes = categorizer.codes(frame).contiguous()
+    return codes, len(labels), labels
+
+
+def _launch_points(view, x, y, xy_dtype, n, row_offset, accs, canv, ctx, codes, ncat):
+    lib = _lib.lib()
+    for i in range(0, len(accs), _lib.DSB_MAX_OPS):
+        chunk = accs[i:i + _lib.DSB_MAX_OPS]
+        plan = _lib.Plan()
+        plan.nops = len(chunk)
+        keep = []
+        for k, acc in enumerate(chunk):
+            b = plan.ops[k]
+            b.op = rd.ACC_OP[acc.kind]
+            b.agg = canv[acc.key].data_ptr()
+            if acc.col is not None:
+                t = ctx.frame[acc.col]
+                keep.append(t)
+                b.val_dtype, b.val = ctx.dsb_dtype(acc.col), t.data_ptr()
+            if acc.chk is not None:
+                t = ctx.frame[acc.chk]
+                keep.append(t)
+                b.chk_dtype, b.chk = ctx.dsb_dtype(acc.chk), t.data_ptr()
+            if acc.aux is not None:
+                b.aux = canv[acc.aux.key].data_ptr()
+        if ncat:
+            plan.cat = codes.data_ptr()
+            plan.cat_dtype = _lib.dsb_dtype(str(codes.dtype).replace("torch.", ""))
+            plan.ncat = ncat
+        # dsb_points takes at most 2^32 rows per call (32-bit local row field of the arg accumulators)
+        step = 1 << 32
+        for lo in range(0, max(n, 1), step):
+            cnt = min(step, n - lo)
+            if cnt <= 0:
+                break
+            if lo:
+                raise NotImplementedError("more than 2^32 rows per device in one call")
+            _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, cnt, row_offset + lo,
+                                      C.byref(plan), ctx.stream_ptr), "dsb_points")
+
+
+def _to_host(t, np_view=None):
+    a = t.cpu().numpy()
+    if np_view is not None:
+        a = a.view(np_view)
+    return a
+
+
+def _use_count_fast_path(agg, ncat, dist):
+    return False
+
+
+def points(source, canvas, glyph: Point, agg, dist=None):
+    """bypixel for Point glyphs."""
+    needed = list(dict.fromkeys(glyph.required_columns() + agg.columns_needed))
+    frame = as_device_frame(source, needed)
+    schema = frame.schema()
+    for c in needed:
+        if c not in schema:
+            raise ValueError("specified column not found")
+    glyph.validate(schema)
+    agg.validate(schema)
+    canvas.validate()
+
+    device = frame.device
+    with torch.cuda.device(device):
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+        x_range = canvas.x_range or _auto_range([frame[glyph.x]], stream_ptr, dist, device)
+        y_range = canvas.y_range or _auto_range([frame[glyph.y]], stream_ptr, dist, device)
+        canvas.validate_ranges(x_range, y_range)
+        view, x_st, y_st = make_view(canvas, x_range, y_range)
+
+        codes, ncat, labels = _categorical_setup(agg, frame, schema)
+        shape = (canvas.plot_height, canvas.plot_width) + ((ncat,) if ncat else ())
+        ctx = _Ctx(frame, view, shape, dist)
+
+        reds = _reductions_of(agg)
+        accs, seen = [], set()
+        for r in reds:
+            for a in r._accs(ctx):
+                if a.key not in seen:
+                    seen.add(a.key)
+                    accs.append(a)
+        canv = {a.key: _alloc_canvas(a, shape, device, stream_ptr) for a in accs}
+
+        x, y, xy_dtype = _xy_columns(frame, glyph.x, glyph.y)
+        n = len(frame)
+        stage0 = [a for a in accs if a.aux is None]
+        stage1 = [a for a in accs if a.aux is not None]
+        _launch_points(view, x, y, xy_dtype, n, frame.row_offset, stage0, canv, ctx, codes, ncat)
+        if dist is not None:
+            dist.combine(stage0, canv)
+        if stage1:
+            _launch_points(view, x, y, xy_dtype, n, frame.row_offset, stage1, canv, ctx, codes, ncat)
+            if dist is not None:
+                dist.combine(stage1, canv)
+
+        results = [r._finalize(ctx, canv) for r in reds]
+
+    x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+    y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+    return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)
+
+
+def _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels):
+    """make_finalize (compiler.py:510-536) + by._build_finalize (reductions.py:809-820)."""
+    def one(r, t):
+        coords = {glyph.y_label: y_axis, glyph.x_label: x_axis}
+        dims = [glyph.y_label, glyph.x_label]
+        if isinstance(r, rd.by):
+            dims = dims + [r.cat_column]
+            coords[r.cat_column] = labels
+        data = _to_host(t, getattr(r, "_out_np_view", None))
+        return DataArray(data, coords=coords, dims=dims, attrs=dict(x_range=x_range, y_range=y_range))
+
+    if isinstance(agg, rd.summary):
+        return Dataset({k: one(r, t) for k, r, t in zip(agg.keys, reds, results)},
+                       attrs=dict(x_range=x_range, y_range=y_range))
+    return one(reds[0], results[0])
+
+
+# ------------------------------------------------------------------------------------------ lines
+def _stack_columns(frame, names):
+    cols = [frame[c] for c in names]
+    dt = torch.float32 if all(c.dtype == torch.float32 for c in cols) else torch.float64
+    return torch.stack([c.to(dt) for c in cols], dim=1).contiguous()   # [nlines, nverts], line.py:298-299
+
+
+def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=None):
+    """bypixel for LinesAxis1 (one line per row)."""
+    needed = list(dict.fromkeys(glyph.required_columns() + agg.columns_needed))
+    frame = as_device_frame(source, needed)
+    schema = frame.schema()
+    for c in needed:
+        if c not in schema:
+            raise ValueError("specified column not found")
+    glyph.validate(schema)
+    agg.validate(schema)
+    canvas.validate()
+    if isinstance(agg, (rd.summary, rd.by)) or agg._line_agg is None:
+        raise NotImplementedError(f"{type(agg).__name__} is not implemented for datashader_b200 lines yet")
+    line_width = float(glyph._line_width)
+    if line_width > 0 and isinstance(agg, rd.min):
+        raise NotImplementedError("min() needs the 2-stage antialias combine (antialias.py:30-58): not implemented yet")
+    if line_width > 0 and isinstance(agg, (rd.count, rd.sum)) and not agg.self_intersect:
+        raise NotImplementedError("self_intersect=False needs the 2-stage antialias combine: not implemented yet")
+
+    device = frame.device
+    with torch.cuda.device(device):
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+        x_range = canvas.x_range or _auto_range([frame[c] for c in glyph.x], stream_ptr, dist, device)
+        y_range = canvas.y_range or _auto_range([frame[c] for c in glyph.y], stream_ptr, dist, device)
+        canvas.validate_ranges(x_range, y_range)
+        view, x_st, y_st = make_view(canvas, x_range, y_range)
+        xs = _stack_columns(frame, glyph.x)
+        ys = _stack_columns(frame, glyph.y)
+        if xs.dtype != ys.dtype:
+            xs, ys = xs.to(torch.float64), ys.to(torch.float64)
+        xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
+        H, W = canvas.plot_height, canvas.plot_width
+        la = agg._line_agg
+        aa = line_width > 0
+        val, val_dtype = None, _lib.NONE
+        if agg.column is not None:
+            val = frame[agg.column]
+            val_dtype = _lib.dsb_dtype(frame.np_dtype(agg.column))
+        mask = None
+        lib = _lib.lib()
+        # accumulator canvases per dsb_lines_axis1's contract (include/dsb200.h)
+        if la == _lib.LINE_ANY:
+            canvas_t = torch.empty((H, W), dtype=torch.int32 if aa else torch.uint8, device=device)
+            _lib.check(lib.dsb_init_canvas(_lib.OP_MAX32 if aa else _lib.OP_ANY, canvas_t.data_ptr(), H * W, stream_ptr))
+        elif la == _lib.LINE_COUNT:
+            canvas_t = torch.zeros((H, W), dtype=torch.float32 if aa else torch.int32, device=device)
+            mask = torch.zeros((H, W), dtype=torch.uint8, device=device) if aa else None
+        elif la == _lib.LINE_SUM:
+            canvas_t = torch.zeros((H, W), dtype=torch.float64, device=device)
+            mask = torch.zeros((H, W), dtype=torch.uint8, device=device)
+        else:
+            canvas_t = torch.empty((H, W), dtype=torch.int64, device=device)
+            _lib.check(lib.dsb_init_canvas(_lib.OP_MAX64 if la == _lib.LINE_MAX else _lib.OP_MIN64, canvas_t.data_ptr(),
+                                           H * W, stream_ptr))
+        _lib.check(lib.dsb_lines_axis1(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, xs.shape[0], xs.shape[1],
+                                       val.data_ptr() if val is not None else None, val_dtype, la, line_width,
+                                       canvas_t.data_ptr(), mask.data_ptr() if mask is not None else None, stream_ptr),
+                   "dsb_lines_axis1")
+        if dist is not None:
+            canvas_t, mask = dist.combine_lines(la, aa, canvas_t, mask)
+        # finishing (dtypes pinned by test_pandas.py:3257-3277: AA any/count -> f32, others f64)
+        if la == _lib.LINE_ANY:
+            if aa:
+                out = torch.empty((H, W), dtype=torch.float64, device=device)
+                _lib.check(lib.dsb_decode_minmax(canvas_t.data_ptr(), _lib.OP_MAX32, _lib.F32, out.data_ptr(), H * W, stream_ptr))
+                data = _to_host(out.to(torch.float32))
+            else:
+                data = _to_host(canvas_t, np.bool_)
+        elif la == _lib.LINE_COUNT:
+            if aa:
+                out = torch.where(mask.bool(), canvas_t, torch.full_like(canvas_t, float("nan")))
+                data = _to_host(out)
+            else:
+                data = _to_host(canvas_t, np.uint32)
+        elif la == _lib.LINE_SUM:
+            out = torch.empty_like(canvas_t)
+            _lib.check(lib.dsb_finalize_sum(canvas_t.data_ptr(), mask.data_ptr(), out.data_ptr(), H * W, stream_ptr))
+            data = _to_host(out)
+        else:
+            out = torch.empty((H, W), dtype=torch.float64, device=device)
+            _lib.check(lib.dsb_decode_minmax(canvas_t.data_ptr(), _lib.OP_MAX64 if la == _lib.LINE_MAX else _lib.OP_MIN64,
+                                             _lib.F64, out.data_ptr(), H * W, stream_ptr))
+            data = _to_host(out)
+
+    x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+    y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+    return DataArray(data, coords={glyph.y_label: y_axis, glyph.x_label: x_axis}, dims=[glyph.y_label, glyph.x_label],
+                     attrs=dict(x_range=x_range, y_range=y_range))

@@ -1,0 +1,139 @@
+/* dsb200 - B200-native (sm_100a) kernels for datashader's projection + aggregation hot path.
+ *
+ * C ABI of libdsb200.so.  Plain pointers and sizes only; every buffer is a DEVICE pointer owned by
+ * the caller (the library allocates nothing and never copies to the host).  All entry points are
+ * asynchronous on `stream` (a cudaStream_t passed as void*), return 0 on success or a negative
+ * dsb_status, and leave a message for dsb_last_error().
+ *
+ * Each entry point names the reference interface (holoviz/datashader 0.19.1, paths relative to
+ * datashader/) it replaces; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ */
+#ifndef DSB200_H
+#define DSB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSB_ABI_VERSION 1
+#define DSB_MAX_OPS 8
+
+typedef enum {
+  DSB_OK = 0,
+  DSB_ERR_ARG = -1,       /* bad argument (dtype, op, null pointer, size) */
+  DSB_ERR_CUDA = -2,      /* CUDA runtime error, text in dsb_last_error() */
+  DSB_ERR_UNSUPPORTED = -3
+} dsb_status;
+
+/* column dtypes (numpy kinds the reference accepts for coordinates / value columns) */
+typedef enum {
+  DSB_NONE = 0, DSB_F32 = 1, DSB_F64 = 2, DSB_I8 = 3, DSB_U8 = 4, DSB_I16 = 5, DSB_U16 = 6,
+  DSB_I32 = 7, DSB_U32 = 8, DSB_I64 = 9, DSB_U64 = 10
+} dsb_dtype;
+
+/* What data_libraries/pandas.py:35-48 computes before calling extend(): canvas shape, the
+ * Axis.compute_scale_and_translate pairs (core.py:62-81) and the inclusive data bounds. */
+typedef struct {
+  int32_t width, height;          /* canvases are row-major [height, width] (pandas.py:48) */
+  int32_t x_log, y_log;           /* 0 LinearAxis, 1 LogAxis (core.py:114-132) */
+  double sx, tx, sy, ty;
+  double xmin, xmax, ymin, ymax;
+} dsb_view;
+
+/* Accumulator ops: the device-side state of the reference's base reductions (compiler.py:103-107).
+ * Every accumulator is commutative, so partial canvases combine with a plain elementwise
+ * sum / max / min (NCCL) in any order.  Canvas element types are given per op; `row` is the global
+ * row id row_offset + i (reductions.py:87-113). */
+typedef enum {
+  DSB_OP_COUNT = 1,    /* i32/u32 canvas (init 0): += 1                      count._append[_no_field] reductions.py:552-584 */
+  DSB_OP_ANY = 2,      /* u8 canvas (init 0): = 1                            any._append              reductions.py:843-862 */
+  DSB_OP_SUM = 3,      /* f64 canvas (init 0): += val                        _sum_zero._append        reductions.py:956-963 */
+  DSB_OP_MAX32 = 4,    /* i32 key canvas (init INT32_MIN): max of key32(val) max._append              reductions.py:1222-1227 */
+  DSB_OP_MIN32 = 5,    /* i32 key canvas (init INT32_MAX): min of key32(val) min._append              reductions.py:1178-1183 */
+  DSB_OP_MAX64 = 6,    /* i64 key canvas (init INT64_MIN): max of key64((double)val) */
+  DSB_OP_MIN64 = 7,    /* i64 key canvas (init INT64_MAX) */
+  DSB_OP_MAXROW = 8,   /* i64 canvas (init -1): max of row                   _max_row_index._append   reductions.py:2263-2269 */
+  DSB_OP_MINROW = 9,   /* i64 canvas (init INT64_MAX): min of row            _min_row_index._append   reductions.py:2318-2324 */
+  DSB_OP_ARGMAX32 = 10,/* i64 canvas (init INT64_MIN): max of key32(val)<<32 | ~u32(i)  -> where(max(val)) with the
+                          reference's earliest-row tie rule (strict compare, reductions.py:1224, 2014-2016) */
+  DSB_OP_ARGMIN32 = 11,/* i64 canvas (init INT64_MAX): min of key32(val)<<32 | u32(i) */
+  DSB_OP_MATCHROW64 = 12 /* second pass for 64-bit selectors: `aux` is a finished MAX64/MIN64 key canvas; rows whose
+                          key equals it contribute min(row) into an i64 canvas (init INT64_MAX) */
+} dsb_op;
+
+/* key32: order-preserving signed 32-bit key of an f32 / (u)int8-32 value; key64: the same for the
+ * value widened to f64 (what the reference stores: agg[y, x] = field).  NaN values never reach a key. */
+
+typedef struct {
+  int32_t op;               /* dsb_op */
+  int32_t val_dtype;        /* dsb_dtype of `val`, DSB_NONE if the op has no field */
+  const void* val;          /* [n] value column (the reference's `field`); NaN rows are skipped */
+  int32_t chk_dtype;        /* optional nan_check_column (compiler.py:439-446, 461-466) */
+  const void* chk;
+  void* agg;                /* accumulator canvas [H*W] or [H*W*ncat] */
+  const void* aux;          /* DSB_OP_MATCHROW64 only */
+} dsb_base;
+
+typedef struct {
+  int32_t nops;
+  dsb_base ops[DSB_MAX_OPS];
+  const void* cat;          /* optional [n] integer category codes: by()/count_cat (compiler.py:379-390) */
+  int32_t cat_dtype;        /* DSB_I8 / DSB_I16 / DSB_I32 / DSB_I64, DSB_NONE when not categorical */
+  int32_t ncat;             /* canvases become [H, W, ncat]; negative codes wrap like numba's agg[:, :, -1] */
+} dsb_plan;
+
+int dsb_abi_version(void);
+const char* dsb_last_error(void);
+/* number of kernel-launching API calls made by this process so far (diagnostics / bench.py gpu_launches) */
+int64_t dsb_launch_count(void);
+
+/* Initialise an accumulator canvas of `ncell` elements to the op's identity (see dsb_op).
+ * Replaces Reduction._build_create / make_create (reductions.py:397-472, compiler.py:294-301). */
+int dsb_init_canvas(int32_t op, void* agg, int64_t ncell, void* stream);
+
+/* Fused projection + reduction over n points: replaces Point._build_extend.extend_cuda
+ * (glyphs/points.py:188-221) and the generated append() (compiler.py:321-475).
+ * x, y: [n] device columns of xy_dtype (DSB_F32 or DSB_F64); n <= 2^32 per call. */
+int dsb_points(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+               int64_t row_offset, const dsb_plan* plan, void* stream);
+
+/* NaN-skipping min/max of a column: Glyph._compute_bounds_numba (glyphs/glyph.py:66-78).
+ * out_minmax: 2 doubles on the device, (+inf, -inf) when no finite-or-inf value exists. */
+int dsb_bounds(const void* col, int32_t dtype, int64_t n, double* out_minmax, void* stream);
+
+/* ---- canvas-sized finishing passes (replace each reduction's _finalize, reductions.py:491-493,
+ *      1091-1098, 1292-1297, 1374-1378, 2150-2161) -------------------------------------------- */
+/* key canvas -> f64 with NaN for empty cells. val_dtype selects the key decoding. */
+int dsb_decode_minmax(const void* keys, int32_t op, int32_t val_dtype, double* out, int64_t ncell, void* stream);
+/* ARGMAX32/ARGMIN32 packed canvas -> selector value (f64, may be NULL) and global row id (i64, -1 empty). */
+int dsb_decode_arg(const void* packed, int32_t op, int32_t val_dtype, int64_t row_offset, double* out_sel,
+                   int64_t* out_row, int64_t ncell, void* stream);
+/* row canvas (i64; -1 or INT64_MAX = empty) -> f64 lookup[row - row_offset] (NaN for empty); rows outside
+ * [row_offset, row_offset + n) are left untouched in `out` (used by the multi-GPU combine). */
+int dsb_gather_rows(const int64_t* rows, int64_t row_offset, int64_t n, const void* lookup, int32_t lookup_dtype,
+                    double* out, int64_t ncell, void* stream);
+/* MINROW canvas -> reference form (-1 for empty). */
+int dsb_finish_minrow(int64_t* rows, int64_t ncell, void* stream);
+/* mean = where(count > 0, sum / count, nan)  (reductions.py:1292-1297) */
+int dsb_finalize_mean(const double* sum, const void* count_u32, double* out, int64_t ncell, void* stream);
+/* sum  = where(mask, sum, nan); mask is a u8 any-canvas (reductions.py:1091-1096) */
+int dsb_finalize_sum(const double* sum, const uint8_t* mask, double* out, int64_t ncell, void* stream);
+
+/* ---- lines ---------------------------------------------------------------------------------- */
+typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5 } dsb_line_agg;
+
+/* LinesAxis1 (glyphs/line.py:1244-1337): xs, ys are [nlines, nverts] row-major of xy_dtype, `val`
+ * one value per line.  line_width == 0 -> Liang-Barsky clip + snapped Bresenham (line.py:734-780,
+ * 986-1031); line_width > 0 -> the antialiased rasteriser (line.py:826-983) for the single-stage
+ * combinations (any, max: overwrite; count, sum: previous-segment correction; antialias.py:30-58).
+ * Canvases: line_width == 0: any u8, count i32, sum f64 (+ `mask` u8), max/min i64 key64.
+ *           line_width  > 0: any i32 key32 of f32, count f32 (+mask), sum f64 (+mask), max i64 key64. */
+int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                    int64_t nverts, const void* val, int32_t val_dtype, int32_t agg, double line_width,
+                    void* canvas, uint8_t* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

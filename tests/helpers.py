@@ -68,3 +68,23 @@ def assert_agg_equal(got, want, name, rtol=RTOL_SUM):
         np.testing.assert_allclose(got, want, rtol=rtol, atol=0, equal_nan=True, err_msg=name)
     else:
         assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), name
+
+
+def make_agg(spec):
+    """oracle spec tuple -> datashader_b200 reduction object"""
+    import datashader_b200 as ds
+    kind = spec[0]
+    if kind == "by":
+        return ds.by(spec[1], make_agg(spec[2]))
+    if kind == "where":
+        return ds.where(make_agg(spec[1]), spec[2])
+    ctor = getattr(ds, kind)
+    return ctor(*spec[1:])
+
+
+def pandas_frame(cols, ncat=NCAT):
+    import pandas as pd
+    d = {k: v for k, v in cols.items() if not k.endswith("__ncat") and k != "cat"}
+    if "cat" in cols:
+        d["cat"] = pd.Categorical.from_codes(cols["cat"], categories=[f"c{i}" for i in range(int(cols.get("cat__ncat", ncat)))])
+    return pd.DataFrame(d)

@@ -1,0 +1,64 @@
+"""LinesAxis1 on the GPU against the reference's golden vectors: Bresenham bit-exact; antialiased
+any/max bit-exact, antialiased count/sum within 1e-6 (atomic float adds change the summation order)."""
+import numpy as np
+import pytest
+
+from helpers import LINE_CANVASES, load
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(xs, ys, val):
+    import pandas as pd
+    nverts = xs.shape[1]
+    d = {f"x{j}": xs[:, j] for j in range(nverts)}
+    d.update({f"y{j}": ys[:, j] for j in range(nverts)})
+    d["val"] = val
+    return pd.DataFrame(d), [f"x{j}" for j in range(nverts)], [f"y{j}" for j in range(nverts)]
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("cname", list(LINE_CANVASES))
+def test_lines_golden(tag, cname):
+    import datashader_b200 as ds
+    g = load("lines.npz")
+    df, xc, yc = _frame(g[f"in_{tag}_xs"], g[f"in_{tag}_ys"], g[f"in_{tag}_val"])
+    cvs = ds.Canvas(**LINE_CANVASES[cname])
+    n = 0
+    for key in g.files:
+        pre = f"ln_{tag}_{cname}_lw"
+        if not key.startswith(pre):
+            continue
+        lw, aname = key[len(pre):].split("_")
+        lw = float(lw)
+        agg = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "min": ds.min("val")}[aname]
+        got = cvs.line(df, x=xc, y=yc, axis=1, agg=agg, line_width=lw).data
+        want = g[key]
+        assert got.dtype == want.dtype and got.shape == want.shape, key
+        if aname in ("count", "sum") and (lw > 0 or aname == "sum"):
+            assert np.array_equal(np.isnan(got), np.isnan(want)), key
+            np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True, err_msg=key)
+        else:
+            assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), key
+        n += 1
+    assert n >= 8
+
+
+def test_lines_vs_oracle_larger():
+    import datashader_b200 as ds
+    from oracle import oracle as ora
+    rng = np.random.default_rng(8)
+    nl, nv = 300, 64
+    xs = np.tile(np.arange(nv, dtype=np.float32), (nl, 1))
+    ys = np.cumsum(rng.standard_normal((nl, nv)), axis=1).astype(np.float32)
+    val = rng.random(nl).astype(np.float32)
+    df, xc, yc = _frame(xs, ys, val)
+    xr, yr = (0.0, float(nv - 1)), (float(ys.min()), float(ys.max()))
+    view = ora.make_view(384, 216, xr, yr)
+    cvs = ds.Canvas(384, 216, x_range=xr, y_range=yr)
+    for lw in (0, 1):
+        got = cvs.line(df, x=xc, y=yc, axis=1, agg=ds.max("val"), line_width=lw).data
+        want = ora.lines_axis1(xs, ys, view, agg="max", values=val, line_width=lw)
+        assert np.array_equal(got, want, equal_nan=True), lw
+    got = cvs.line(df, x=xc, y=yc, axis=1, agg=ds.count()).data
+    assert np.array_equal(got, ora.lines_axis1(xs, ys, view, agg="count"))

@@ -1,0 +1,166 @@
+"""Parity of the CUDA path (through Canvas.points -> ctypes -> libdsb200.so) with the reference's golden
+vectors and with the C oracle on seeded inputs.  Bit-exact for count / any / min / max / first / last /
+where / by; float sums within RTOL_SUM (f64 accumulation on both sides, only the order differs)."""
+import numpy as np
+import pytest
+
+from helpers import (CANVASES, NCAT, SPECS, assert_agg_equal, columns_from_golden, load, make_agg, pandas_frame)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ds():
+    import torch
+    assert torch.cuda.is_available()
+    import datashader_b200 as ds
+    return ds
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("cname", list(CANVASES))
+def test_points_golden(ds, tag, cname):
+    g = load("points.npz")
+    cols = columns_from_golden(g, f"in_{tag}_")
+    df = pandas_frame(cols)
+    cvs = ds.Canvas(**CANVASES[cname])
+    n = 0
+    for rname, spec in SPECS.items():
+        key = f"pts_{tag}_{cname}_{rname}"
+        if key not in g.files:
+            continue
+        agg = cvs.points(df, "x", "y", make_agg(spec))
+        assert_agg_equal(agg.data, g[key], key)
+        n += 1
+    assert n >= 5
+    agg = cvs.points(df, "x", "y")
+    np.testing.assert_array_equal(agg.coords["x"], g[f"pts_{tag}_{cname}_xcoords"])
+    np.testing.assert_array_equal(agg.coords["y"], g[f"pts_{tag}_{cname}_ycoords"])
+    np.testing.assert_array_equal(np.asarray(agg.attrs["x_range"], dtype="f8"), g[f"pts_{tag}_{cname}_xrange"])
+    np.testing.assert_array_equal(np.asarray(agg.attrs["y_range"], dtype="f8"), g[f"pts_{tag}_{cname}_yrange"])
+    assert tuple(agg.dims) == ("y", "x")
+
+
+def test_by_dims_and_labels(ds):
+    g = load("points.npz")
+    cols = columns_from_golden(g, "in_f32_")
+    df = pandas_frame(cols)
+    agg = ds.Canvas(**CANVASES["c37x23"]).points(df, "x", "y", ds.count_cat("cat"))
+    assert tuple(agg.dims) == ("y", "x", "cat")
+    assert list(agg.coords["cat"]) == [f"c{i}" for i in range(NCAT)]
+    assert agg.data.dtype == np.uint32 and agg.data.shape == (23, 37, NCAT)
+
+
+def test_partitioned_golden_single_gpu(ds):
+    """first/last/where are row-index based on the GPU, i.e. the reference's partitioned formulation."""
+    g = load("partitioned.npz")
+    cols = columns_from_golden(g, "in_")
+    df = pandas_frame(cols)
+    cvs = ds.Canvas(plot_width=37, plot_height=23, x_range=(-0.1, 1.05), y_range=(0.1, 0.9))
+    for key in g.files:
+        if key.startswith("part3_"):
+            rname = key[len("part3_"):]
+            assert_agg_equal(cvs.points(df, "x", "y", make_agg(SPECS[rname])).data, g[key], key)
+
+
+def test_log_axes(ds):
+    """Log axes: CUDA's log10f is not bit-identical to glibc's; the bar is +-1 pixel on boundary points
+    (SURVEY.md 8a A1).  Total count must match exactly (the bounds test is exact)."""
+    g = load("points.npz")
+    import pandas as pd
+    df = pd.DataFrame({k: g[f"in_log_{k}"] for k in ("x", "y", "v32")})
+    cvs = ds.Canvas(plot_width=40, plot_height=30, x_range=(1, 1000), y_range=(1, 100), x_axis_type="log", y_axis_type="log")
+    got = cvs.points(df, "x", "y", ds.count()).data
+    want = g["pts_log_count"]
+    assert got.sum() == want.sum()
+    assert np.abs(got.astype(np.int64) - want.astype(np.int64)).sum() <= 8
+    np.testing.assert_allclose(cvs.points(df, "x", "y").coords["x"], g["pts_log_xcoords"], rtol=1e-15)
+
+
+@pytest.mark.parametrize("seed,n,W,H", [(1, 300_000, 900, 525), (2, 200_000, 1920, 1080), (3, 100_000, 17, 3)])
+def test_points_vs_oracle_seeded(ds, seed, n, W, H):
+    from oracle import oracle as ora
+    rng = np.random.default_rng(seed)
+    cols = {
+        "x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+        "v32": rng.standard_normal(n).astype(np.float32), "other": rng.random(n).astype(np.float32),
+        "vi": rng.integers(-9, 9, n).astype(np.int32), "v64": rng.standard_normal(n),
+        "cat": rng.integers(0, NCAT, n).astype(np.int8), "cat__ncat": NCAT,
+    }
+    cols["v32"][rng.integers(0, n, n // 1000 + 1)] = np.nan
+    # adversarial coordinates: every pixel edge and its float32 neighbours
+    edges = (np.arange(W + 1) / W).astype(np.float32)
+    k = min(len(edges), n // 3)
+    cols["x"][:k] = edges[:k]
+    cols["x"][k:2 * k] = np.nextafter(edges[:k], np.float32(2))
+    cols["x"][2 * k:3 * k] = np.nextafter(edges[:k], np.float32(-1))
+    df = pandas_frame(cols)
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    for rname in ("count", "count_v32", "any", "mean_v32", "sum_v32", "max_v32", "min_v32", "max_vi", "max_v64",
+                  "first_v32", "last_v32", "where_max_v32_other", "where_min_v32_row", "where_max_vi_other",
+                  "where_first_v32_other", "where_last_v32_row", "by_count", "by_mean_v32", "by_max_v32"):
+        spec = SPECS[rname]
+        got = cvs.points(df, "x", "y", make_agg(spec)).data
+        want = ora.points(cols, "x", "y", spec, view, npartitions=2 if "first" in rname or "last" in rname else 1)
+        assert_agg_equal(got, want, f"{rname} seed={seed}")
+
+
+def test_where_max_f64_two_pass(ds):
+    from oracle import oracle as ora
+    rng = np.random.default_rng(11)
+    n = 50_000
+    cols = {"x": rng.random(n), "y": rng.random(n), "v64": np.round(rng.standard_normal(n), 1),
+            "other": rng.random(n).astype(np.float32)}
+    df = pandas_frame(cols)
+    view = ora.make_view(31, 29, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(31, 29, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    for spec in (("where", ("max", "v64"), "other"), ("where", ("min", "v64"), None)):
+        assert_agg_equal(cvs.points(df, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view), str(spec))
+
+
+def test_summary_and_device_frame(ds):
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(5)
+    n = 20_000
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": rng.standard_normal(n).astype(np.float32)}
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    cvs = ds.Canvas(50, 40, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    out = cvs.points(frame, "x", "y", ds.summary(n=ds.count(), m=ds.mean("v32"), hi=ds.max("v32")))
+    view = ora.make_view(50, 40, (0.0, 1.0), (0.0, 1.0))
+    assert_agg_equal(out["n"].data, ora.points(cols, "x", "y", ("count",), view), "summary count")
+    assert_agg_equal(out["m"].data, ora.points(cols, "x", "y", ("mean", "v32"), view), "summary mean")
+    assert_agg_equal(out["hi"].data, ora.points(cols, "x", "y", ("max", "v32"), view), "summary max")
+
+
+def test_empty_and_all_nan(ds):
+    import pandas as pd
+    cvs = ds.Canvas(4, 3, x_range=(0, 1), y_range=(0, 1))
+    df = pd.DataFrame({"x": np.array([], dtype="f4"), "y": np.array([], dtype="f4"), "v": np.array([], dtype="f4")})
+    assert cvs.points(df, "x", "y").data.sum() == 0
+    assert np.isnan(cvs.points(df, "x", "y", ds.max("v")).data).all()
+    df = pd.DataFrame({"x": np.full(5, np.nan, "f4"), "y": np.full(5, np.nan, "f4")})
+    agg = ds.Canvas(4, 3).points(df, "x", "y")          # auto-range on all-NaN -> (-1, 1) (glyph.py:42-49)
+    assert agg.attrs["x_range"] == (-1.0, 1.0) and agg.data.sum() == 0
+
+
+def test_errors_match_reference(ds):
+    import pandas as pd
+    df = pd.DataFrame({"x": [0.1, 0.2], "y": [0.1, 0.2], "s": ["a", "b"], "v": [1.0, 2.0]})
+    cvs = ds.Canvas(2, 2, x_range=(0, 1), y_range=(0, 1))
+    with pytest.raises(ValueError, match="specified column not found"):
+        cvs.points(df, "x", "y", ds.mean("nope"))
+    with pytest.raises(ValueError, match="input must be categorical"):
+        cvs.points(df, "x", "y", ds.count_cat("v"))
+    with pytest.raises(ValueError, match="where and its contained reduction cannot use the same column"):
+        cvs.points(df, "x", "y", ds.where(ds.max("v"), "v"))
+    with pytest.raises(TypeError, match="selector can only be"):
+        ds.where(ds.mean("v"), "x")
+    with pytest.raises(ValueError, match="Range values must be >0"):
+        ds.Canvas(2, 2, x_range=(0, 1), y_range=(0, 1), x_axis_type="log").points(df, "x", "y")
+    with pytest.raises(ValueError, match="Invalid size"):
+        ds.Canvas(0, 2, x_range=(0, 1), y_range=(0, 1)).points(df, "x", "y")
+    with pytest.raises(ValueError, match="coordinates may be specified"):
+        cvs.points(df, "x")
