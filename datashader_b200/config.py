@@ -1,0 +1,9 @@
+"""The few process-wide knobs of datashader_b200 (the reference has no flag system either)."""
+
+# Return aggregates as CUDA tensors inside the DataArray instead of copying them to the host, the way the
+# reference returns cupy-backed DataArrays for cudf sources (compiler.py:296-301).
+device_results = False
+
+# Record CUDA events around the fused aggregation launches (bench.py's roofline leg reads them).
+time_kernels = False
+kernel_events = []     # [(start_event, end_event)] appended per Canvas call when time_kernels is set

@@ -202,10 +202,10 @@ def bypixel(source, canvas, glyph, agg, *, antialias=False):
     type selects the fused kernel."""
     from . import pipeline
     from .distributed import current_group
-    from .frame import DeviceFrame
+    from .frame import DeviceFrame, HostFrame
     import pandas as pd
 
-    if not isinstance(source, (pd.DataFrame, DeviceFrame)):
+    if not isinstance(source, (pd.DataFrame, DeviceFrame, HostFrame)):
         raise ValueError("source must be a pandas or dask DataFrame")
     dist = current_group(source)
     with warnings.catch_warnings():

@@ -75,7 +75,7 @@ __global__ void k_decode_arg(const long long* packed, int op, int dt, long long 
     bool empty = (op == DSB_OP_ARGMAX32) ? (p == LLONG_MIN) : (p == LLONG_MAX);
     int k = (int)(p >> 32);
     uint32_t lo = (uint32_t)(p & 0xffffffffLL);
-    uint32_t local = (op == DSB_OP_ARGMAX32) ? ~lo : lo;
+    uint32_t local = ((op == DSB_OP_ARGMAX32) ? ~lo : lo) - (uint32_t)row_offset;   // mod 2^32
     if (out_sel) out_sel[i] = empty ? (double)NAN : value_from_key32(k, dt);
     if (out_row) out_row[i] = empty ? -1LL : row_offset + (long long)local;
   }

@@ -74,11 +74,13 @@ __device__ __forceinline__ void apply_base(const dsb_base& b, long long cell, lo
       int32_t k = load_key32(b.val, b.val_dtype, i, &nan);
       if (nan) return;
       // ties go to the earliest row: for max the row field is complemented so that a smaller row is larger
+      // the row field is the low 32 bits of the GLOBAL row id, so chunks of one frame (< 2^32 rows) can
+      // share a canvas; dsb_decode_arg rebuilds the full id from the frame's first row
       if (b.op == DSB_OP_ARGMAX32) {
-        long long p = ((long long)k << 32) | (long long)(uint32_t)(~(uint32_t)i);
+        long long p = ((long long)k << 32) | (long long)(uint32_t)(~(uint32_t)row);
         atomicMax((long long*)b.agg + cell, p);
       } else {
-        long long p = ((long long)k << 32) | (long long)(uint32_t)i;
+        long long p = ((long long)k << 32) | (long long)(uint32_t)row;
         atomicMin((long long*)b.agg + cell, p);
       }
       return;

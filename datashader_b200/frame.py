@@ -92,14 +92,127 @@ class DeviceFrame:
     def np_dtype(self, name):
         return np.dtype(str(self.columns[name].dtype).replace("torch.", ""))
 
+    def n_chunks(self):
+        return 1
 
-def as_device_frame(source, needed, device=None):
-    """pandas.DataFrame | DeviceFrame | dict of tensors/arrays -> DeviceFrame with the needed columns."""
+    def resident(self, needed):
+        return self
+
+    def chunks(self, needed):
+        yield self
+
+
+class HostFrame:
+    """Host-resident columns (numpy arrays or CPU torch tensors, ideally pinned) that are streamed to
+    the GPU in row chunks while the previous chunk is being aggregated.  This is the ingestion side
+    of the boundary: what `df[col].values` (glyphs/points.py:234-235) is for the reference.
+
+    A pandas.DataFrame passed to Canvas.points / Canvas.line is wrapped in a HostFrame without
+    copying (only the needed columns, like _bypixel_sanitise, core.py:1384-1392)."""
+
+    CHUNK_ROWS = 1 << 25     # 32 Mi rows: 128 MiB per f32 column per staging buffer
+
+    def __init__(self, columns, categories=None, row_offset=0, device=None):
+        self.columns = {}
+        for name, a in columns.items():
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    raise ValueError("HostFrame columns must live on the host; use DeviceFrame")
+                self.columns[name] = a.contiguous()
+            else:
+                a = np.ascontiguousarray(a)
+                if a.dtype == np.bool_:
+                    a = a.view(np.uint8)
+                if a.dtype not in _TORCH_OK:
+                    a = a.astype(np.int64 if a.dtype.kind in "iu" and a.dtype.itemsize < 8 else np.float64)
+                if not a.flags.writeable:
+                    a = a.copy()
+                self.columns[name] = torch.from_numpy(a)
+        self.categories = dict(categories or {})
+        self.row_offset = int(row_offset)
+        lens = {int(t.shape[0]) for t in self.columns.values()}
+        if len(lens) > 1:
+            raise ValueError("all columns must have the same length")
+        self._len = lens.pop() if lens else 0
+        self.device = torch.device(device if device is not None else "cuda")
+
+    def __len__(self):
+        return self._len
+
+    def __contains__(self, name):
+        return name in self.columns
+
+    @classmethod
+    def from_pandas(cls, df, columns=None, device=None):
+        import pandas as pd
+        cols, cats = {}, {}
+        for name in (columns if columns is not None else list(df.columns)):
+            if name not in df.columns:
+                raise ValueError("specified column not found")     # reductions.py:352-353
+            s = df[name]
+            if isinstance(s.dtype, pd.CategoricalDtype):
+                cats[name] = list(s.cat.categories)
+                cols[name] = np.asarray(s.cat.codes.values)
+            else:
+                cols[name] = s.to_numpy()
+        off = getattr(df, "_datashader_row_offset", 0)
+        return cls(cols, cats, off, device)
+
+    def schema(self):
+        out = {}
+        for name, t in self.columns.items():
+            if name in self.categories:
+                out[name] = ("categorical", list(self.categories[name]))
+            else:
+                out[name] = ("float" if t.dtype.is_floating_point else "int", None)
+        return out
+
+    def np_dtype(self, name):
+        return np.dtype(str(self.columns[name].dtype).replace("torch.", ""))
+
+    def n_chunks(self):
+        return max(1, -(-self._len // self.CHUNK_ROWS))
+
+    def resident(self, needed):
+        """The whole frame on the device (single-chunk sources and gathers)."""
+        cols = {c: self.columns[c].to(self.device, non_blocking=True) for c in needed}
+        return DeviceFrame(cols, self.categories, self.row_offset)
+
+    def chunks(self, needed):
+        """Yield DeviceFrame row chunks; H2D copies run on a side stream, double-buffered, so the copy of
+        chunk k+1 overlaps the aggregation of chunk k."""
+        if self.n_chunks() == 1:
+            yield self.resident(needed)
+            return
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        rows = self.CHUNK_ROWS
+        bufs = [{c: torch.empty(rows, dtype=self.columns[c].dtype, device=dev) for c in needed} for _ in range(2)]
+        free_ev = [None, None]
+        for k, lo in enumerate(range(0, self._len, rows)):
+            hi = min(lo + rows, self._len)
+            b = bufs[k & 1]
+            with torch.cuda.stream(copy):
+                if free_ev[k & 1] is not None:
+                    copy.wait_event(free_ev[k & 1])       # the kernel that read this buffer has finished
+                for c in needed:
+                    b[c][:hi - lo].copy_(self.columns[c][lo:hi], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            compute.wait_event(ready)
+            yield DeviceFrame({c: b[c][:hi - lo] for c in needed}, self.categories, self.row_offset + lo)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            free_ev[k & 1] = ev
+        compute.synchronize()
+
+
+def as_frame(source, needed, device=None):
+    """pandas.DataFrame | HostFrame | DeviceFrame -> a frame with the needed columns."""
     import pandas as pd
-    if isinstance(source, DeviceFrame):
+    if isinstance(source, (DeviceFrame, HostFrame)):
         return source
     if isinstance(source, pd.DataFrame):
-        # only the needed columns are staged, like _bypixel_sanitise (core.py:1384-1392)
-        off = getattr(source, "_datashader_row_offset", 0)
-        return DeviceFrame.from_pandas(source, columns=needed, device=device, row_offset=off)
-    raise ValueError("source must be a pandas DataFrame or a datashader_b200.DeviceFrame")
+        return HostFrame.from_pandas(source, columns=needed, device=device)
+    raise ValueError("source must be a pandas or dask DataFrame")

@@ -16,8 +16,9 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import config
 from . import reductions as rd
-from .frame import as_device_frame
+from .frame import DeviceFrame, as_frame
 from .glyphs import LinesAxis1, Point, _column_bounds, maybe_expand_bounds
 from .xr_compat import DataArray, Dataset
 
@@ -26,7 +27,8 @@ class _Ctx:
     """Everything a reduction needs to declare accumulators and finish them."""
 
     def __init__(self, frame, view, shape, dist=None):
-        self.frame = frame
+        self.frame = frame            # the source (DeviceFrame or HostFrame): dtypes, length, row offset
+        self.resident = frame if isinstance(frame, DeviceFrame) else None   # device columns for gathers
         self.view = view
         self.shape = shape            # (H, W) or (H, W, ncat)
         self.dist = dist
@@ -77,8 +79,8 @@ def _reductions_of(agg):
     return list(agg.values) if isinstance(agg, rd.summary) else [agg]
 
 
-def _categorical_setup(agg, frame, schema):
-    """by(): category codes + number of categories (compiler.py:379-390)."""
+def _categorical_setup(agg, schema):
+    """by(): the categorizer + number of categories (compiler.py:379-390)."""
     cats = [r for r in _reductions_of(agg) if isinstance(r, rd.by)]
     if not cats:
         return None, 0, None
@@ -88,27 +90,30 @@ def _categorical_setup(agg, frame, schema):
                                   "is not supported by datashader_b200 yet")
     categorizer = cats[0].categorizer
     labels = categorizer.categories(schema)
-    codes = categorizer.codes(frame).contiguous()
-    return codes, len(labels), labels
+    return categorizer, len(labels), labels
 
 
-def _launch_points(view, x, y, xy_dtype, n, row_offset, accs, canv, ctx, codes, ncat):
+def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
+    """One fused launch per <= DSB_MAX_OPS accumulators over one resident row chunk."""
     lib = _lib.lib()
+    x, y, xy_dtype = _xy_columns(chunk, glyph.x, glyph.y)
+    n, row_offset = len(chunk), chunk.row_offset
+    codes = categorizer.codes(chunk).contiguous() if ncat else None
     for i in range(0, len(accs), _lib.DSB_MAX_OPS):
-        chunk = accs[i:i + _lib.DSB_MAX_OPS]
+        group = accs[i:i + _lib.DSB_MAX_OPS]
         plan = _lib.Plan()
-        plan.nops = len(chunk)
+        plan.nops = len(group)
         keep = []
-        for k, acc in enumerate(chunk):
+        for k, acc in enumerate(group):
             b = plan.ops[k]
             b.op = rd.ACC_OP[acc.kind]
             b.agg = canv[acc.key].data_ptr()
             if acc.col is not None:
-                t = ctx.frame[acc.col]
+                t = chunk[acc.col]
                 keep.append(t)
                 b.val_dtype, b.val = ctx.dsb_dtype(acc.col), t.data_ptr()
             if acc.chk is not None:
-                t = ctx.frame[acc.chk]
+                t = chunk[acc.chk]
                 keep.append(t)
                 b.chk_dtype, b.chk = ctx.dsb_dtype(acc.chk), t.data_ptr()
             if acc.aux is not None:
@@ -130,6 +135,12 @@ def _launch_points(view, x, y, xy_dtype, n, row_offset, accs, canv, ctx, codes, 
 
 
 def _to_host(t, np_view=None):
+    if config.device_results:
+        if np_view is np.uint32:
+            return t.view(torch.uint32)
+        if np_view is np.bool_:
+            return t.bool()
+        return t
     a = t.cpu().numpy()
     if np_view is not None:
         a = a.view(np_view)
@@ -143,7 +154,7 @@ def _use_count_fast_path(agg, ncat, dist):
 def points(source, canvas, glyph: Point, agg, dist=None):
     """bypixel for Point glyphs."""
     needed = list(dict.fromkeys(glyph.required_columns() + agg.columns_needed))
-    frame = as_device_frame(source, needed)
+    frame = as_frame(source, needed)
     schema = frame.schema()
     for c in needed:
         if c not in schema:
@@ -155,14 +166,26 @@ def points(source, canvas, glyph: Point, agg, dist=None):
     device = frame.device
     with torch.cuda.device(device):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
-        x_range = canvas.x_range or _auto_range([frame[glyph.x]], stream_ptr, dist, device)
-        y_range = canvas.y_range or _auto_range([frame[glyph.y]], stream_ptr, dist, device)
+        single = frame.n_chunks() == 1
+        resident = frame.resident(needed) if single else None      # one H2D for small host sources
+        if canvas.x_range is None or canvas.y_range is None:
+            # the reference's separate bounds pass (pandas.py:35-36, glyph.py:66-78)
+            bx, by = [], []
+            for ch in ([resident] if single else frame.chunks([glyph.x, glyph.y])):
+                bx.append(_column_bounds(stream_ptr, [ch[glyph.x]]))
+                by.append(_column_bounds(stream_ptr, [ch[glyph.y]]))
+            x_range = canvas.x_range or _merge_bounds(bx, dist, device)
+            y_range = canvas.y_range or _merge_bounds(by, dist, device)
+        else:
+            x_range, y_range = canvas.x_range, canvas.y_range
         canvas.validate_ranges(x_range, y_range)
         view, x_st, y_st = make_view(canvas, x_range, y_range)
 
-        codes, ncat, labels = _categorical_setup(agg, frame, schema)
+        categorizer, ncat, labels = _categorical_setup(agg, schema)
         shape = (canvas.plot_height, canvas.plot_width) + ((ncat,) if ncat else ())
         ctx = _Ctx(frame, view, shape, dist)
+        if single:
+            ctx.resident = resident
 
         reds = _reductions_of(agg)
         accs, seen = [], set()
@@ -173,23 +196,35 @@ def points(source, canvas, glyph: Point, agg, dist=None):
                     accs.append(a)
         canv = {a.key: _alloc_canvas(a, shape, device, stream_ptr) for a in accs}
 
-        x, y, xy_dtype = _xy_columns(frame, glyph.x, glyph.y)
-        n = len(frame)
-        stage0 = [a for a in accs if a.aux is None]
-        stage1 = [a for a in accs if a.aux is not None]
-        _launch_points(view, x, y, xy_dtype, n, frame.row_offset, stage0, canv, ctx, codes, ncat)
-        if dist is not None:
-            dist.combine(stage0, canv)
-        if stage1:
-            _launch_points(view, x, y, xy_dtype, n, frame.row_offset, stage1, canv, ctx, codes, ncat)
+        # stage 0: everything that needs one pass; stage 1: accumulators that read a finished stage-0 canvas
+        for stage in ([a for a in accs if a.aux is None], [a for a in accs if a.aux is not None]):
+            if not stage:
+                continue
+            if config.time_kernels:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            for ch in ([resident] if single else frame.chunks(needed)):
+                _launch_points(view, ch, glyph, stage, canv, ctx, categorizer, ncat)
+            if config.time_kernels:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                config.kernel_events.append((ev0, ev1))
             if dist is not None:
-                dist.combine(stage1, canv)
+                dist.combine(stage, canv)
 
         results = [r._finalize(ctx, canv) for r in reds]
 
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)
+
+
+def _merge_bounds(parts, dist, device):
+    lo = np.min([p[0] for p in parts])
+    hi = np.max([p[1] for p in parts])
+    if dist is not None:
+        lo, hi = dist.global_bounds(float(lo), float(hi), device)
+    return maybe_expand_bounds((float(lo), float(hi)))
 
 
 def _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels):
@@ -219,7 +254,7 @@ def _stack_columns(frame, names):
 def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=None):
     """bypixel for LinesAxis1 (one line per row)."""
     needed = list(dict.fromkeys(glyph.required_columns() + agg.columns_needed))
-    frame = as_device_frame(source, needed)
+    frame = as_frame(source, needed)
     schema = frame.schema()
     for c in needed:
         if c not in schema:
@@ -227,6 +262,7 @@ def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=No
     glyph.validate(schema)
     agg.validate(schema)
     canvas.validate()
+    frame = frame.resident(needed)      # lines are staged whole ([nlines, nverts] matrices)
     if isinstance(agg, (rd.summary, rd.by)) or agg._line_agg is None:
         raise NotImplementedError(f"{type(agg).__name__} is not implemented for datashader_b200 lines yet")
     line_width = float(glyph._line_width)

@@ -310,9 +310,19 @@ class min(_MinMax):   # noqa: A001
 
 def _gather(ctx, rows, column):
     """value canvas = column[row] per pixel (NaN where empty); cross-shard aware."""
+    if ctx.resident is None:
+        # host source streamed in chunks: the canvas-sized lookup is done against the host column
+        if ctx.dist is not None:
+            raise NotImplementedError("sharded + host-streamed sources: stage the shard in a DeviceFrame")
+        r = rows.cpu()
+        empty = (r < 0) | (r == torch.iinfo(torch.int64).max)
+        idx = (r - ctx.frame.row_offset).clamp_(0, len(ctx.frame) - 1 if len(ctx.frame) else 0)
+        vals = ctx.frame.columns[column][idx.reshape(-1)].to(torch.float64).reshape(r.shape)
+        vals[empty] = float("nan")
+        return vals.to(rows.device)
     out = torch.zeros(rows.shape, dtype=torch.float64, device=rows.device)
-    col = ctx.frame[column]
-    _lib.check(_lib.lib().dsb_gather_rows(rows.data_ptr(), ctx.frame.row_offset, len(ctx.frame), col.data_ptr(),
+    col = ctx.resident[column]
+    _lib.check(_lib.lib().dsb_gather_rows(rows.data_ptr(), ctx.resident.row_offset, len(ctx.resident), col.data_ptr(),
                                           ctx.dsb_dtype(column), out.data_ptr(), rows.numel(), ctx.stream_ptr),
                "dsb_gather_rows")
     if ctx.dist is not None:

@@ -55,9 +55,9 @@ typedef enum {
   DSB_OP_MIN64 = 7,    /* i64 key canvas (init INT64_MAX) */
   DSB_OP_MAXROW = 8,   /* i64 canvas (init -1): max of row                   _max_row_index._append   reductions.py:2263-2269 */
   DSB_OP_MINROW = 9,   /* i64 canvas (init INT64_MAX): min of row            _min_row_index._append   reductions.py:2318-2324 */
-  DSB_OP_ARGMAX32 = 10,/* i64 canvas (init INT64_MIN): max of key32(val)<<32 | ~u32(i)  -> where(max(val)) with the
+  DSB_OP_ARGMAX32 = 10,/* i64 canvas (init INT64_MIN): max of key32(val)<<32 | ~u32(row)  -> where(max(val)) with the
                           reference's earliest-row tie rule (strict compare, reductions.py:1224, 2014-2016) */
-  DSB_OP_ARGMIN32 = 11,/* i64 canvas (init INT64_MAX): min of key32(val)<<32 | u32(i) */
+  DSB_OP_ARGMIN32 = 11,/* i64 canvas (init INT64_MAX): min of key32(val)<<32 | u32(row) */
   DSB_OP_MATCHROW64 = 12 /* second pass for 64-bit selectors: `aux` is a finished MAX64/MIN64 key canvas; rows whose
                           key equals it contribute min(row) into an i64 canvas (init INT64_MAX) */
 } dsb_op;
@@ -106,7 +106,8 @@ int dsb_bounds(const void* col, int32_t dtype, int64_t n, double* out_minmax, vo
  *      1091-1098, 1292-1297, 1374-1378, 2150-2161) -------------------------------------------- */
 /* key canvas -> f64 with NaN for empty cells. val_dtype selects the key decoding. */
 int dsb_decode_minmax(const void* keys, int32_t op, int32_t val_dtype, double* out, int64_t ncell, void* stream);
-/* ARGMAX32/ARGMIN32 packed canvas -> selector value (f64, may be NULL) and global row id (i64, -1 empty). */
+/* ARGMAX32/ARGMIN32 packed canvas -> selector value (f64, may be NULL) and global row id (i64, -1 empty).
+ * row_offset is the first global row that contributed (rows span < 2^32), used to widen the 32-bit row field. */
 int dsb_decode_arg(const void* packed, int32_t op, int32_t val_dtype, int64_t row_offset, double* out_sel,
                    int64_t* out_row, int64_t ncell, void* stream);
 /* row canvas (i64; -1 or INT64_MAX = empty) -> f64 lookup[row - row_offset] (NaN for empty); rows outside

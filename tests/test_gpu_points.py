@@ -164,3 +164,30 @@ def test_errors_match_reference(ds):
         ds.Canvas(0, 2, x_range=(0, 1), y_range=(0, 1)).points(df, "x", "y")
     with pytest.raises(ValueError, match="coordinates may be specified"):
         cvs.points(df, "x")
+
+
+def test_host_frame_chunk_streaming(ds, monkeypatch):
+    """Host columns streamed in several double-buffered chunks give the same aggregates as one pass
+    (global row ids keep first/last/where exact across chunk boundaries)."""
+    from oracle import oracle as ora
+    monkeypatch.setattr(ds.HostFrame, "CHUNK_ROWS", 7_000)
+    rng = np.random.default_rng(21)
+    n = 50_000
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": np.round(rng.standard_normal(n), 1).astype(np.float32), "other": rng.random(n).astype(np.float32),
+            "v64": np.round(rng.standard_normal(n), 1), "cat": rng.integers(0, NCAT, n).astype(np.int8), "cat__ncat": NCAT}
+    cols["v32"][rng.integers(0, n, 50)] = np.nan
+    df = pandas_frame(cols)
+    view = ora.make_view(64, 48, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(64, 48, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    for rname in ("count", "mean_v32", "max_v32", "first_v32", "last_v32", "where_max_v32_other", "where_min_v32_row",
+                  "where_first_v32_other", "by_count", "by_max_v32"):
+        assert_agg_equal(cvs.points(df, "x", "y", make_agg(SPECS[rname])).data,
+                         ora.points(cols, "x", "y", SPECS[rname], view, npartitions=2 if "first" in rname or "last" in rname else 1),
+                         f"chunked {rname}")
+    spec = ("where", ("max", "v64"), "other")
+    assert_agg_equal(cvs.points(df, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view), "chunked 2-pass")
+    # auto-ranging over chunks
+    got = ds.Canvas(31, 17).points(df, "x", "y")
+    v2 = ora.make_view(31, 17, ora.compute_bounds(cols["x"]), ora.compute_bounds(cols["y"]))
+    assert_agg_equal(got.data, ora.points(cols, "x", "y", ("count",), v2), "chunked auto-range")
