@@ -10,6 +10,7 @@ from . import config  # noqa: F401
 from .frame import DeviceFrame, HostFrame  # noqa: F401
 from .reductions import (any, by, category_binning, category_codes, category_modulo, count, count_cat,  # noqa: F401,A004
                          first, last, max, mean, min, sum, summary, where)
+from . import palette  # noqa: F401
 from . import transfer_functions as tf  # noqa: F401
 
 __version__ = "0.1.0"

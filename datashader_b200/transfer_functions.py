@@ -1,1 +1,265 @@
-"""shade / eq_hist on the GPU (transfer_functions/__init__.py of the reference) - filled in below."""
+"""tf.shade on the GPU (the reference's datashader/transfer_functions/__init__.py:616-745).
+
+Covered: 3-D categorical aggregates (uint32 counts, e.g. by('cat', count())) -> colour mix + alpha, and
+2-D aggregates with a list colormap or a single colour; how in {'eq_hist', 'log', 'cbrt', 'linear'},
+span=None.  The canvas-sized work (totals, histogram, scan/CDF, per-pixel lookup and colour mixing) runs
+in libdsb200 (csrc/shade.cu); the host only picks scalars (offset, histogram range) exactly the way
+_interpolate_alpha / eq_hist do.  Not covered (raise NotImplementedError): span=..., callable how/cmap,
+float categorical aggregates, discrete colour keys on 2-D aggregates, spread/dynspread/stack.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Iterator
+
+import numpy as np
+import torch
+
+from . import _lib
+from .palette import Sets1to3, rgb
+from .xr_compat import DataArray
+
+__all__ = ["shade", "Image"]
+
+_HOW = {"eq_hist": 0, "log": 1, "cbrt": 2, "linear": 3}
+_NBINS = 256 * 256
+
+_p, _i32, _i64, _f64, _u32, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_uint32, C.c_uint64
+_SIGS = {
+    "dsb_shade_cat_totals": [_p, _i64, _i32, _p, _p, _p],
+    "dsb_eqhist_hist_u64": [_p, _i64, _u64, _i32, _f64, _f64, _i32, _i32, _p, _p],
+    "dsb_eqhist_hist_f64": [_p, _i64, _f64, _f64, _f64, _i32, _i32, _p, _p],
+    "dsb_eqhist_scan": [_p, _i32, _i32, _f64, _f64, _p, _p, _p, _p],
+    "dsb_shade_norm_span": [_i32, _f64, _f64, _p, _p, _p, _i32, _p, _p],
+    "dsb_shade_cat_colorize": [_p, _p, _i64, _i32, _p, _u32, _u32, _u64, _i32, _i32, _p, _p, _p, _p, _f64, _f64, _p, _p],
+    "dsb_shade_map2d": [_p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _f64, _f64, _p, _p],
+}
+_bound = False
+
+
+def _lib_shade():
+    global _bound
+    L = _lib.lib()
+    if not _bound:
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _bound = True
+    return L
+
+
+class Image(DataArray):
+    """An RGBA image stored as uint32 (transfer_functions/__init__.py:30-78)."""
+    __slots__ = ()
+
+    def to_pil(self, origin="lower"):
+        from PIL import Image as PILImage
+        data = np.asarray(self.data)
+        arr = np.flipud(data) if origin == "lower" else data
+        return PILImage.fromarray(np.ascontiguousarray(arr).view(np.uint8).reshape(arr.shape + (4,)), "RGBA")
+
+
+def _device_tensor(data, device):
+    if isinstance(data, torch.Tensor):
+        return data.to(device)
+    a = np.ascontiguousarray(data)
+    if a.dtype == np.uint32:
+        return torch.from_numpy(a.view(np.int32)).to(device).view(torch.uint32)
+    if a.dtype == np.uint64:
+        return torch.from_numpy(a.view(np.int64)).to(device)
+    return torch.from_numpy(a).to(device)
+
+
+def _host_transform(how, d):
+    """The reference's analytic transfer functions on a scalar, evaluated with numpy like the reference."""
+    d = np.float64(d)
+    if how == "log":
+        return float(np.log1p(d))
+    if how == "cbrt":
+        return float(d ** (1 / 3.))
+    return float(d)
+
+
+def _eq_hist_tables(L, s, kind, values, npix, offset, mask_zero, dmax, integer_mode, rescale, device):
+    """histogram -> scan -> (xp, cdf, meta, span) on the device.  kind: 'u64' (totals) or 'f64'."""
+    nbins = int(dmax) + 1 if integer_mode else _NBINS
+    hist = torch.empty(nbins, dtype=torch.int32, device=device)
+    xp = torch.empty(nbins, dtype=torch.float64, device=device)
+    cdf = torch.empty(nbins, dtype=torch.float64, device=device)
+    meta = torch.zeros(2, dtype=torch.int32, device=device)
+    span = torch.empty(2, dtype=torch.float64, device=device)
+    first, last = 0.0, float(dmax)
+    if kind == "u64":
+        _lib.check(L.dsb_eqhist_hist_u64(values.data_ptr(), npix, int(offset), int(mask_zero), first, last, nbins,
+                                         int(integer_mode), hist.data_ptr(), s), "dsb_eqhist_hist_u64")
+    else:
+        _lib.check(L.dsb_eqhist_hist_f64(values.data_ptr(), npix, float(offset), first, last, nbins, int(integer_mode),
+                                         hist.data_ptr(), s), "dsb_eqhist_hist_f64")
+    _lib.check(L.dsb_eqhist_scan(hist.data_ptr(), nbins, int(integer_mode), first, last, xp.data_ptr(), cdf.data_ptr(),
+                                 meta.data_ptr(), s), "dsb_eqhist_scan")
+    _lib.check(L.dsb_shade_norm_span(0, 0.0, float(dmax), xp.data_ptr(), cdf.data_ptr(), meta.data_ptr(), int(rescale),
+                                     span.data_ptr(), s), "dsb_shade_norm_span")
+    return xp, cdf, meta, span
+
+
+def _colorize(agg, color_key, how, alpha, min_alpha, name, color_baseline, rescale_discrete_levels, device):
+    """3-D categorical path: _colorize (:359-463) + _interpolate_alpha (:466-532)."""
+    data = agg.data
+    cats = list(np.asarray(agg.coords[agg.dims[-1]]))
+    H, W = int(data.shape[0]), int(data.shape[1])
+    coords = {agg.dims[1]: agg.coords[agg.dims[1]], agg.dims[0]: agg.coords[agg.dims[0]]}
+    if not len(cats):
+        return Image(np.zeros((H, W), dtype=np.uint32), dims=agg.dims[:-1], coords=coords, name=name)
+    if color_key is None:
+        raise ValueError("Color key must be provided, with at least as many " +
+                         "colors as there are categorical fields")
+    if not isinstance(color_key, dict):
+        color_key = dict(zip(cats, color_key))
+    if len(color_key) < len(cats):
+        raise ValueError(f"Insufficient colors provided ({len(color_key)}) for the categorical "
+                         f"fields available ({len(cats)})")
+    dt = str(data.dtype).replace("torch.", "")
+    if dt != "uint32":
+        raise NotImplementedError("datashader_b200.tf.shade: categorical aggregates must be uint32 counts "
+                                  f"(got {dt})")
+    colors = [rgb(color_key[c]) for c in cats]
+    ncat = len(cats)
+    RGB = np.array(colors, dtype=np.float32)                       # (C, 3)
+    rgb2 = ((np.ones((1, ncat), np.float32) @ RGB) / np.float32(ncat)).astype(np.uint8)[0]   # :432-442
+    fallback = int(rgb2[0]) | (int(rgb2[1]) << 8) | (int(rgb2[2]) << 16)
+
+    L = _lib_shade()
+    with torch.cuda.device(device):
+        s = torch.cuda.current_stream(device).cuda_stream
+        counts = _device_tensor(data, device).contiguous()
+        npix = H * W
+        total = torch.empty(npix, dtype=torch.int64, device=device)
+        stats = torch.empty(4, dtype=torch.int64, device=device)
+        _lib.check(L.dsb_shade_cat_totals(counts.data_ptr(), npix, ncat, total.data_ptr(), stats.data_ptr(), s),
+                   "dsb_shade_cat_totals")
+        min_entry, min_total, min_nz, max_total = [int(v) & 0xFFFFFFFFFFFFFFFF for v in stats.tolist()]
+        baseline = min_entry if color_baseline is None else int(color_baseline)
+        # _interpolate_alpha, span is None (:475-487)
+        mask_zero = min_total == 0
+        all_masked = mask_zero and max_total == 0
+        offset = (min_nz if not all_masked else 0) if mask_zero else min_total
+        dmax = max_total - offset if not all_masked else 0
+        rgbt = torch.from_numpy(RGB).to(device)
+        out = torch.empty(npix, dtype=torch.int32, device=device)
+        xp = cdf = meta = None
+        if all_masked:
+            span = torch.tensor([0.0, 1.0], dtype=torch.float64, device=device)
+            how_code = 3
+        elif how == "eq_hist":
+            integer_mode = (not mask_zero) and dmax < _NBINS          # eq_hist :194-196 (totals stay uint64)
+            xp, cdf, meta, span = _eq_hist_tables(L, s, "u64", total, npix, offset, mask_zero, dmax, integer_mode,
+                                                  rescale_discrete_levels, device)
+            how_code = 0
+        else:
+            span = torch.tensor([_host_transform(how, 0), _host_transform(how, dmax)], dtype=torch.float64, device=device)
+            how_code = _HOW[how]
+        _lib.check(L.dsb_shade_cat_colorize(
+            counts.data_ptr(), total.data_ptr(), npix, ncat, rgbt.data_ptr(), fallback, baseline & 0xFFFFFFFF, offset,
+            int(mask_zero), how_code, xp.data_ptr() if xp is not None else None, cdf.data_ptr() if cdf is not None else None,
+            meta.data_ptr() if meta is not None else None, span.data_ptr(), float(min_alpha), float(alpha), out.data_ptr(), s),
+            "dsb_shade_cat_colorize")
+        img = out.cpu().numpy().view(np.uint32).reshape(H, W)
+    return Image(img, dims=agg.dims[:-1], coords=coords, name=name)
+
+
+def _interpolate(agg, cmap, how, alpha, min_alpha, name, rescale_discrete_levels, device):
+    """2-D path: _interpolate (:251-357) with span=None and a list / single-colour cmap."""
+    data = agg.data
+    if len(data.shape) != 2:
+        raise ValueError("agg must be 2D")
+    if isinstance(cmap, Iterator):
+        cmap = list(cmap)
+    if isinstance(cmap, tuple) and isinstance(cmap[0], str):
+        cmap = list(cmap)
+    if callable(cmap):
+        raise NotImplementedError("matplotlib colormaps are not supported by datashader_b200.tf.shade")
+    if not isinstance(cmap, (list, str, tuple)):
+        raise TypeError("Expected `cmap` of `matplotlib.colors.Colormap`, "
+                        f"`list`, `str`, or `tuple`; got: '{type(cmap)}'")
+    H, W = int(data.shape[0]), int(data.shape[1])
+    npix = H * W
+    L = _lib_shade()
+    with torch.cuda.device(device):
+        s = torch.cuda.current_stream(device).cuda_stream
+        t = _device_tensor(data, device).contiguous()
+        integer = not t.dtype.is_floating_point
+        if t.dtype == torch.bool:
+            mask = ~t
+            v = t.to(torch.int64)
+        elif t.dtype in (torch.uint32, torch.uint8, torch.uint16, torch.uint64):
+            v = t.view(torch.int32).to(torch.int64) & 0xFFFFFFFF if t.dtype == torch.uint32 else t.to(torch.int64)
+            mask = v == 0
+        elif integer:
+            v = t.to(torch.int64)
+            mask = torch.zeros_like(v, dtype=torch.bool)      # np.isnan of signed ints is never true
+        else:
+            v = t
+            mask = torch.isnan(t)
+        if bool(mask.all()):
+            return Image(np.zeros((H, W), dtype=np.uint32), coords=agg.coords, dims=agg.dims, attrs=agg.attrs, name=name)
+        valid = v[~mask]
+        offset = valid.min()
+        # data -= offset in the canvas dtype (f32 stays f32), then everything downstream is float64
+        d = (v - offset).to(torch.float64)
+        d = torch.where(mask, torch.full_like(d, float("nan")), d).reshape(-1).contiguous()
+        dmax = float((valid.max() - offset).item())
+        xp = cdf = meta = None
+        if how == "eq_hist":
+            integer_mode = integer and dmax < _NBINS
+            xp, cdf, meta, span = _eq_hist_tables(L, s, "f64", d, npix, 0.0, False, dmax, integer_mode,
+                                                  rescale_discrete_levels, device)
+            span_host = span.tolist()
+        else:
+            span_host = [_host_transform(how, 0), _host_transform(how, dmax)]
+            span = torch.tensor(span_host, dtype=torch.float64, device=device)
+        if isinstance(cmap, list):
+            cols = np.array([rgb(c) for c in cmap], dtype=np.float64)
+            ncolors = len(cmap)
+            cspan = torch.from_numpy(np.linspace(span_host[0], span_host[1], ncolors)).to(device)
+        else:
+            cols = np.array([rgb(cmap)], dtype=np.float64)
+            ncolors, cspan = 1, None
+        rs, gs, bs = (torch.from_numpy(np.ascontiguousarray(cols[:, k])).to(device) for k in range(3))
+        out = torch.empty(npix, dtype=torch.int32, device=device)
+        _lib.check(L.dsb_shade_map2d(
+            d.data_ptr(), npix, _HOW[how], xp.data_ptr() if xp is not None else None,
+            cdf.data_ptr() if cdf is not None else None, meta.data_ptr() if meta is not None else None, span.data_ptr(),
+            ncolors, cspan.data_ptr() if cspan is not None else None, rs.data_ptr(), gs.data_ptr(), bs.data_ptr(),
+            float(min_alpha), float(alpha), out.data_ptr(), s), "dsb_shade_map2d")
+        img = out.cpu().numpy().view(np.uint32).reshape(H, W)
+    return Image(img, coords=agg.coords, dims=agg.dims, name=name)
+
+
+def shade(agg, cmap=["lightblue", "darkblue"], color_key=Sets1to3, how='eq_hist', alpha=255, min_alpha=40, span=None,  # noqa: B006
+          name=None, color_baseline=None, rescale_discrete_levels=False):
+    """Convert a DataArray to an RGBA image (same signature as the reference's tf.shade, :616-745)."""
+    if not isinstance(agg, DataArray):
+        raise TypeError("agg must be instance of DataArray")
+    name = agg.name if name is None else name
+    if not ((0 <= min_alpha <= 255) and (0 <= alpha <= 255)):
+        raise ValueError(f"min_alpha ({min_alpha}) and alpha ({alpha}) must be between 0 and 255")
+    if callable(how):
+        raise NotImplementedError("callable `how` is not supported by datashader_b200.tf.shade")
+    if how not in _HOW:
+        raise ValueError(f"Unknown interpolation method: {how}")
+    if span is not None:
+        if how == "eq_hist":
+            raise ValueError("span is not (yet) valid to use with eq_hist")
+        raise NotImplementedError("span= is not supported by datashader_b200.tf.shade yet")
+    if rescale_discrete_levels and how != 'eq_hist':
+        rescale_discrete_levels = False
+    device = agg.data.device if isinstance(agg.data, torch.Tensor) and agg.data.is_cuda else torch.device("cuda")
+    ndim = len(agg.data.shape)
+    if ndim == 2:
+        if color_key is not None and isinstance(color_key, dict):
+            raise NotImplementedError("discrete colour keys on 2-D aggregates are not supported yet")
+        return _interpolate(agg, cmap, how, alpha, min_alpha, name, rescale_discrete_levels, device)
+    elif ndim == 3:
+        return _colorize(agg, color_key, how, alpha, min_alpha, name, color_baseline, rescale_discrete_levels, device)
+    raise ValueError("agg must use 2D or 3D coordinates")

@@ -134,6 +134,44 @@ int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_
                     int64_t nverts, const void* val, int32_t val_dtype, int32_t agg, double line_width,
                     void* canvas, uint8_t* mask, void* stream);
 
+/* ---- shade: tf.shade / eq_hist (transfer_functions/__init__.py) --------------------------------- */
+/* how codes */
+#define DSB_HOW_EQ_HIST 0
+#define DSB_HOW_LOG 1
+#define DSB_HOW_CBRT 2
+#define DSB_HOW_LINEAR 3
+
+/* Per-pixel totals of a categorical count canvas counts[npix, ncat] (u32) and global statistics:
+ * stats[0] min entry (colour baseline, __init__.py:398), [1] min total, [2] min non-zero total, [3] max total.
+ * Replaces nansum_missing (utils.py:161-181) + the nanmin scans of _colorize / _interpolate_alpha. */
+int dsb_shade_cat_totals(const uint32_t* counts, int64_t npix, int32_t ncat, uint64_t* total, uint64_t* stats, void* stream);
+
+/* eq_hist step 1 (__init__.py:194-211): histogram of d = total - offset over unmasked pixels.  integer_mode = the
+ * exact unique-value path (one bin per integer in [first, last]); otherwise numpy.histogram's uniform-bin rule with
+ * `nbins` bins over [first, last]. */
+int dsb_eqhist_hist_u64(const uint64_t* total, int64_t npix, uint64_t offset, int32_t mask_zero, double first, double last,
+                        int32_t nbins, int32_t integer_mode, uint32_t* hist, void* stream);
+int dsb_eqhist_hist_f64(const double* vals /* NaN = masked */, int64_t npix, double offset, double first, double last,
+                        int32_t nbins, int32_t integer_mode, uint32_t* hist, void* stream);
+/* eq_hist step 2 (__init__.py:205-213): drop empty bins (unless integer_mode), cumulative sum, cdf / cdf[-1].
+ * xp, cdf: [nbins] outputs; meta[0] = entries written, meta[1] = discrete_levels.  One CTA, block scan. */
+int dsb_eqhist_scan(const uint32_t* hist, int32_t nbins, int32_t integer_mode, double first, double last, double* xp,
+                    double* cdf, int32_t* meta, void* stream);
+/* norm_span = [f(dmin), f(dmax)] (+ _rescale_discrete_levels, __init__.py:232-248) written to span[2] on the device */
+int dsb_shade_norm_span(int32_t how, double dmin, double dmax, const double* xp, const double* cdf, const int32_t* meta,
+                        int32_t rescale, double* span, void* stream);
+/* _colorize + _interpolate_alpha (__init__.py:359-532): weighted colour mix over categories (f32) and alpha from the
+ * transfer function of the total; out[npix] = r | g<<8 | b<<16 | a<<24. */
+int dsb_shade_cat_colorize(const uint32_t* counts, const uint64_t* total, int64_t npix, int32_t ncat, const float* rgb,
+                           uint32_t fallback_rgb, uint32_t baseline, uint64_t offset, int32_t mask_zero, int32_t how,
+                           const double* xp, const double* cdf, const int32_t* meta, const double* span, double min_alpha,
+                           double alpha, uint32_t* out, void* stream);
+/* _interpolate (__init__.py:251-357) for list colormaps (ncolors >= 2) and single colours (ncolors == 1):
+ * data[npix] = value - offset as f64 with NaN for masked pixels. */
+int dsb_shade_map2d(const double* data, int64_t npix, int32_t how, const double* xp, const double* cdf, const int32_t* meta,
+                    const double* span, int32_t ncolors, const double* cspan, const double* rs, const double* gs,
+                    const double* bs, double min_alpha, double alpha, uint32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

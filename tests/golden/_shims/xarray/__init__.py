@@ -32,6 +32,18 @@ class DataArray:
     def __getitem__(self, key):
         return self.coords[key] if isinstance(key, str) else self.data[key]
 
+    @property
+    def indexes(self):
+        return {d: list(self.coords[d]) for d in self.dims if d in self.coords}
+
+    def transpose(self, *dims):
+        order = [self.dims.index(d) for d in dims]
+        return type(self)(np.transpose(self.data, order), coords=self.coords, dims=dims, attrs=self.attrs,
+                          name=self.name)
+
+    def copy(self):
+        return type(self)(self.data.copy(), coords=self.coords, dims=self.dims, attrs=self.attrs, name=self.name)
+
 
 class Dataset(dict):
     def __init__(self, data_vars=None, coords=None, attrs=None):

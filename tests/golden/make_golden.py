@@ -207,11 +207,69 @@ def lines_cases():
     return out
 
 
+def shade_cases():
+    """tf.shade on categorical [H,W,C] count canvases and on 2-D canvases (transfer_functions/__init__.py)."""
+    import xarray as xr
+    import datashader.transfer_functions as tf
+    out = {}
+    rng = np.random.default_rng(31)
+    H, Wd = 48, 64
+
+    def cat_agg(data):
+        C = data.shape[2]
+        return xr.DataArray(data, coords={"y": np.arange(H), "x": np.arange(Wd), "cat": [f"c{i}" for i in range(C)]},
+                            dims=["y", "x", "cat"])
+
+    def agg2(data):
+        return xr.DataArray(data, coords={"y": np.arange(H), "x": np.arange(Wd)}, dims=["y", "x"])
+
+    cats = {}
+    a = rng.poisson(2.0, (H, Wd, 5)).astype(np.uint32)
+    a[rng.random((H, Wd)) < 0.3] = 0                       # empty pixels
+    cats["poisson5"] = a
+    b = (rng.pareto(1.2, (H, Wd, 16)) * 40).astype(np.uint32)   # heavy tail: totals far apart, > 65536 levels
+    b[rng.random((H, Wd)) < 0.2] = 0
+    b[0, 0, :] = 3_000_000
+    cats["pareto16"] = b
+    c = rng.integers(1, 50, (H, Wd, 3)).astype(np.uint32)  # no empty pixel, baseline > 0
+    cats["dense3"] = c
+    d = np.zeros((H, Wd, 4), np.uint32)
+    d[5, 7, 2] = 9                                           # single non-empty pixel
+    cats["single4"] = d
+    for name, data in cats.items():
+        out[f"cat_{name}_in"] = data
+        for how in ("eq_hist", "log", "cbrt", "linear"):
+            out[f"cat_{name}_{how}"] = np.asarray(tf.shade(cat_agg(data), how=how).data)
+        out[f"cat_{name}_eq_hist_a200_m10"] = np.asarray(tf.shade(cat_agg(data), how="eq_hist", alpha=200, min_alpha=10).data)
+        out[f"cat_{name}_eq_hist_rescale"] = np.asarray(
+            tf.shade(cat_agg(data), how="eq_hist", rescale_discrete_levels=True).data)
+
+    twod = {
+        "u32": cats["poisson5"].sum(axis=2).astype(np.uint32),
+        "u32big": cats["pareto16"].sum(axis=2).astype(np.uint32),
+        "f64": np.where(rng.random((H, Wd)) < 0.25, np.nan, rng.standard_normal((H, Wd)) * 10),
+        "f32": np.where(rng.random((H, Wd)) < 0.25, np.nan, rng.random((H, Wd))).astype(np.float32),
+    }
+    for name, data in twod.items():
+        out[f"d2_{name}_in"] = data
+        for how in ("eq_hist", "log", "cbrt", "linear"):
+            out[f"d2_{name}_{how}_default"] = np.asarray(tf.shade(agg2(data), how=how).data)
+            out[f"d2_{name}_{how}_hot"] = np.asarray(
+                tf.shade(agg2(data), cmap=["black", "darkred", "red", "orange", "yellow", "white"], how=how).data)
+            out[f"d2_{name}_{how}_single"] = np.asarray(tf.shade(agg2(data), cmap="#3070c0", how=how, min_alpha=20).data)
+    return out
+
+
 def main():
+    if "--shade-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "shade.npz"), **shade_cases())
+        print("shade.npz", os.path.getsize(os.path.join(HERE, "shade.npz")) // 1024, "KiB")
+        return
+    np.savez_compressed(os.path.join(HERE, "shade.npz"), **shade_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())
-    for f in ("points.npz", "partitioned.npz", "lines.npz"):
+    for f in ("points.npz", "partitioned.npz", "lines.npz", "shade.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -1,0 +1,99 @@
+"""tf.shade on the GPU against the real reference's images (tests/golden/shade.npz).
+eq_hist and linear: bit-exact.  log / cbrt: CUDA's log1p / pow are not bit-identical to numpy's, so the
+alpha (or colour) byte may differ by one level on a handful of pixels - tolerance written below."""
+import numpy as np
+import pytest
+
+from helpers import load
+
+pytestmark = pytest.mark.gpu
+
+HOT = ["black", "darkred", "red", "orange", "yellow", "white"]
+
+
+def _channels(img):
+    return np.ascontiguousarray(img).view(np.uint8).reshape(img.shape + (4,)).astype(np.int16)
+
+
+def _check(got, want, how, key):
+    assert got.dtype == np.uint32 and got.shape == want.shape, key
+    if how in ("eq_hist", "linear"):
+        np.testing.assert_array_equal(got, want, err_msg=key)
+    else:
+        diff = np.abs(_channels(got) - _channels(want))
+        assert diff.max() <= 1, key
+        assert (diff > 0).mean() < 0.02, key
+
+
+def _cat_agg(ds, data):
+    from datashader_b200.xr_compat import DataArray
+    H, W, C = data.shape
+    return DataArray(data, coords={"y": np.arange(H), "x": np.arange(W), "cat": [f"c{i}" for i in range(C)]},
+                     dims=["y", "x", "cat"])
+
+
+def _agg2(data):
+    from datashader_b200.xr_compat import DataArray
+    H, W = data.shape
+    return DataArray(data, coords={"y": np.arange(H), "x": np.arange(W)}, dims=["y", "x"])
+
+
+@pytest.mark.parametrize("name", ["poisson5", "pareto16", "dense3", "single4"])
+def test_shade_categorical_golden(name):
+    import datashader_b200 as ds
+    g = load("shade.npz")
+    data = g[f"cat_{name}_in"]
+    agg = _cat_agg(ds, data)
+    for how in ("eq_hist", "log", "cbrt", "linear"):
+        _check(ds.tf.shade(agg, how=how).data, g[f"cat_{name}_{how}"], how, f"{name} {how}")
+    _check(ds.tf.shade(agg, how="eq_hist", alpha=200, min_alpha=10).data, g[f"cat_{name}_eq_hist_a200_m10"], "eq_hist", name)
+    _check(ds.tf.shade(agg, how="eq_hist", rescale_discrete_levels=True).data, g[f"cat_{name}_eq_hist_rescale"], "eq_hist", name)
+
+
+@pytest.mark.parametrize("name", ["u32", "u32big", "f64"])
+def test_shade_2d_golden(name):
+    import datashader_b200 as ds
+    g = load("shade.npz")
+    agg = _agg2(g[f"d2_{name}_in"])
+    for how in ("eq_hist", "log", "cbrt", "linear"):
+        _check(ds.tf.shade(agg, how=how).data, g[f"d2_{name}_{how}_default"], how, f"{name} {how} default")
+        _check(ds.tf.shade(agg, cmap=HOT, how=how).data, g[f"d2_{name}_{how}_hot"], how, f"{name} {how} hot")
+        _check(ds.tf.shade(agg, cmap="#3070c0", how=how, min_alpha=20).data, g[f"d2_{name}_{how}_single"], how,
+               f"{name} {how} single")
+
+
+def test_shade_2d_f32_linear_log():
+    """float32 canvases (antialiased any/count): offset subtraction happens in float32 like the reference."""
+    import datashader_b200 as ds
+    g = load("shade.npz")
+    agg = _agg2(g["d2_f32_in"])
+    for how in ("linear", "log", "cbrt"):
+        _check(ds.tf.shade(agg, how=how).data, g[f"d2_f32_{how}_default"], how, f"f32 {how}")
+
+
+def test_shade_reference_literal_table():
+    """datashader/tests/test_transfer_functions.py:22-37, 109-111."""
+    import datashader_b200 as ds
+    a = np.arange(10, 19, dtype="u4").reshape((3, 3))
+    a[[0, 1, 2], [0, 1, 2]] = 0
+    sol = np.array([[0, 4291543295, 4288846335], [4286149631, 0, 4283518207], [4280821503, 4278190335, 0]], dtype="u4")
+    np.testing.assert_array_equal(ds.tf.shade(_agg2(a), cmap=["pink", "red"], how="eq_hist").data, sol)
+
+
+def test_points_by_then_shade_pipeline():
+    """BASELINE config 3 in miniature: by('cat', count()) -> tf.shade(how='eq_hist') against oracle + shade oracle."""
+    import pandas as pd
+    import datashader_b200 as ds
+    from oracle import oracle as ora, shade_oracle as so
+    rng = np.random.default_rng(9)
+    n, C = 400_000, 16
+    cols = {"x": rng.normal(0.5, 0.15, n).astype(np.float32), "y": rng.normal(0.5, 0.15, n).astype(np.float32),
+            "cat": rng.integers(0, C, n).astype(np.int8), "cat__ncat": C}
+    df = pd.DataFrame({"x": cols["x"], "y": cols["y"]})
+    df["cat"] = pd.Categorical.from_codes(cols["cat"], categories=[f"c{i}" for i in range(C)])
+    agg = ds.Canvas(192, 108, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(df, "x", "y", ds.by("cat", ds.count()))
+    want_agg = ora.points(cols, "x", "y", ("by", "cat", ("count",)), ora.make_view(192, 108, (0.0, 1.0), (0.0, 1.0)))
+    np.testing.assert_array_equal(agg.data, want_agg)
+    img = ds.tf.shade(agg, how="eq_hist")
+    colors = [ds.palette.rgb(c) for c in ds.palette.Sets1to3[:C]]
+    np.testing.assert_array_equal(img.data, so.shade_categorical(want_agg, colors, how="eq_hist"))

@@ -1,0 +1,58 @@
+"""The numpy shade oracle (oracle/shade_oracle.py) against the real reference's tf.shade outputs
+(tests/golden/shade.npz) and the literal tables of datashader/tests/test_transfer_functions.py."""
+import numpy as np
+import pytest
+
+from helpers import load
+from oracle import shade_oracle as so
+
+SETS1TO3 = ['#e41a1c', '#377eb8', '#4daf4a', '#984ea3', '#ff7f00', '#ffff33', '#a65628', '#f781bf', '#999999', '#66c2a5',
+            '#fc8d62', '#8da0cb', '#a6d854', '#ffd92f', '#e5c494', '#ffffb3', '#fb8072', '#fdb462', '#fccde5', '#d9d9d9',
+            '#ccebc5', '#ffed6f']
+
+
+def _rgb(h):
+    return int(h[1:3], 16), int(h[3:5], 16), int(h[5:7], 16)
+
+
+LIGHTBLUE, DARKBLUE = (173, 216, 230), (0, 0, 139)
+HOT = [(0, 0, 0), (139, 0, 0), (255, 0, 0), (255, 165, 0), (255, 255, 0), (255, 255, 255)]
+
+
+@pytest.mark.parametrize("name", ["poisson5", "pareto16", "dense3", "single4"])
+def test_categorical_golden(name):
+    g = load("shade.npz")
+    data = g[f"cat_{name}_in"]
+    colors = [_rgb(c) for c in SETS1TO3[:data.shape[2]]]
+    for how in ("eq_hist", "log", "cbrt", "linear"):
+        np.testing.assert_array_equal(so.shade_categorical(data, colors, how=how), g[f"cat_{name}_{how}"], err_msg=how)
+    np.testing.assert_array_equal(so.shade_categorical(data, colors, how="eq_hist", alpha=200, min_alpha=10),
+                                  g[f"cat_{name}_eq_hist_a200_m10"])
+    np.testing.assert_array_equal(so.shade_categorical(data, colors, how="eq_hist", rescale_discrete_levels=True),
+                                  g[f"cat_{name}_eq_hist_rescale"])
+
+
+@pytest.mark.parametrize("name", ["u32", "u32big", "f64", "f32"])
+def test_2d_golden(name):
+    g = load("shade.npz")
+    data = g[f"d2_{name}_in"]
+    for how in ("eq_hist", "log", "cbrt", "linear"):
+        np.testing.assert_array_equal(so.shade_2d(data, [LIGHTBLUE, DARKBLUE], how=how), g[f"d2_{name}_{how}_default"], err_msg=how)
+        np.testing.assert_array_equal(so.shade_2d(data, HOT, how=how), g[f"d2_{name}_{how}_hot"], err_msg=how)
+        np.testing.assert_array_equal(so.shade_2d(data, (0x30, 0x70, 0xc0), how=how, min_alpha=20),
+                                      g[f"d2_{name}_{how}_single"], err_msg=how)
+
+
+def test_reference_literal_tables():
+    """datashader/tests/test_transfer_functions.py:22-37, 86-120 (3x3 fixture, pink->red cmap)."""
+    a = np.arange(10, 19, dtype="u4").reshape((3, 3))
+    a[[0, 1, 2], [0, 1, 2]] = 0
+    sol_eq_hist = np.array([[0, 4291543295, 4288846335], [4286149631, 0, 4283518207], [4280821503, 4278190335, 0]], dtype="u4")
+    sol_linear = np.array([[0, 4291543295, 4289306879], [4287070463, 0, 4282597631], [4280361215, 4278190335, 0]], dtype="u4")
+    sol_log = np.array([[0, 4291543295, 4286741503], [4283978751, 0, 4280492543], [4279242751, 4278190335, 0]], dtype="u4")
+    sol_cbrt = np.array([[0, 4291543295, 4284176127], [4282268415, 0, 4279834879], [4278914047, 4278190335, 0]], dtype="u4")
+    cmap = [(255, 192, 203), (255, 0, 0)]
+    np.testing.assert_array_equal(so.shade_2d(a, cmap, how="eq_hist"), sol_eq_hist)
+    np.testing.assert_array_equal(so.shade_2d(a, cmap, how="linear"), sol_linear)
+    np.testing.assert_array_equal(so.shade_2d(a, cmap, how="log"), sol_log)
+    np.testing.assert_array_equal(so.shade_2d(a, cmap, how="cbrt"), sol_cbrt)
