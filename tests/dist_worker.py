@@ -1,0 +1,66 @@
+"""Multi-rank parity worker (run under torchrun): every rank aggregates its contiguous row shard on its own
+GPU, partial canvases are combined with NCCL all-reduces, and rank 0 checks the result against the
+single-pass CPU oracle - the multi-GPU statement of tests/test_dask.py's npartitions sweep."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datashader_b200 as ds
+    from datashader_b200.distributed import shard_bounds
+    from helpers import NCAT, SPECS, assert_agg_equal, make_agg
+    from oracle import oracle as ora
+
+    rng = np.random.default_rng(1234)
+    n = 300_001
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": np.round(rng.standard_normal(n), 1).astype(np.float32), "other": rng.random(n).astype(np.float32),
+            "vi": rng.integers(-9, 9, n).astype(np.int32), "v64": np.round(rng.standard_normal(n), 1),
+            "cat": rng.integers(0, NCAT, n).astype(np.int8), "cat__ncat": NCAT}
+    cols["v32"][rng.integers(0, n, 300)] = np.nan
+    lo, hi = shard_bounds(n, rank, world)
+    frame = ds.DeviceFrame({k: torch.from_numpy(np.ascontiguousarray(v[lo:hi])).cuda() for k, v in cols.items()
+                            if k != "cat__ncat"}, categories={"cat": [f"c{i}" for i in range(NCAT)]}, row_offset=lo)
+    frame.sharded = True
+    W, H = 97, 61
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    names = ["count", "count_v32", "any", "sum_v32", "mean_v32", "max_v32", "min_v32", "max_vi", "max_v64", "first_v32",
+             "last_v32", "where_max_v32_other", "where_min_v32_row", "where_max_vi_other", "where_first_v32_other",
+             "where_last_v32_row", "by_count", "by_mean_v32", "by_max_v32"]
+    bad = []
+    for name in names + ["where_max_v64_other"]:
+        spec = SPECS.get(name, ("where", ("max", "v64"), "other"))
+        got = cvs.points(frame, "x", "y", make_agg(spec)).data
+        if rank == 0:
+            want = ora.points(cols, "x", "y", spec, view, npartitions=2 if ("first" in name or "last" in name) else 1)
+            try:
+                assert_agg_equal(got, want, f"{name} world={world}")
+            except AssertionError as e:   # noqa: PERF203
+                bad.append(f"{name}: {str(e)[:200]}")
+    # auto-ranging across shards
+    got = ds.Canvas(31, 17).points(frame, "x", "y").data
+    if rank == 0:
+        v2 = ora.make_view(31, 17, ora.compute_bounds(cols["x"]), ora.compute_bounds(cols["y"]))
+        if not np.array_equal(got, ora.points(cols, "x", "y", ("count",), v2)):
+            bad.append("auto-range count")
+        print("DIST_PARITY " + ("OK" if not bad else "FAIL " + "; ".join(bad)), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if bad:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
