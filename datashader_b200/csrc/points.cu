@@ -5,6 +5,7 @@
 // commutative accumulator (see dsb_op in include/dsb200.h), so a row costs one RED per base and no
 // per-pixel mutex is needed (the reference spin-locks one for where/first, _cuda_utils.py:177-199).
 #include "common.cuh"
+#include <stdlib.h>
 
 struct PointsArgs {
   dsb_view v;
@@ -12,6 +13,7 @@ struct PointsArgs {
   const void* y;
   long long n;
   long long row_offset;
+  long long band_lo, band_hi;   // only pixels [band_lo, band_hi) are updated in this launch (L2 banding)
   dsb_plan plan;
 };
 
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256) k_points_generic(const PointsArgs a) {
     for (int u = 0; u < 4; u++) {
       long long i = i0 + u * stride;
       long long cell = map_to_cell<XY>(a.v, xs[u], ys[u]);
-      if (cell < 0) continue;
+      if (cell < a.band_lo || cell >= a.band_hi) continue;     // also drops cell == -1 (out of bounds / NaN)
       if (ncat > 0) {
         int c = load_cat(a.plan.cat, a.plan.cat_dtype, i);
         if (c < 0) c += ncat;                 // numba wraparound for agg[:, :, -1]
@@ -124,6 +126,28 @@ __global__ void __launch_bounds__(256) k_points_generic(const PointsArgs a) {
       for (int k = 0; k < a.plan.nops; k++) apply_base(a.plan.ops[k], cell, i, a.row_offset + i);
     }
   }
+}
+
+static long long op_cell_bytes(int op) {
+  switch (op) {
+    case DSB_OP_COUNT: case DSB_OP_MAX32: case DSB_OP_MIN32: return 4;
+    case DSB_OP_ANY: return 1;
+    case DSB_OP_MATCHROW64: return 16;   // reads the finished key canvas as well
+    default: return 8;
+  }
+}
+
+// Bytes of accumulator canvas one launch may touch before banding kicks in.  Default 96 MB of the 126 MB L2
+// (swept 16..144 MB on configs 3 and 5, profiles/r01b_l2_banding.md; the streamed input is read with
+// ld.global.cs so it does not displace the canvas).  DSB_L2_BAND_MB overrides (0 disables).
+static long long l2_band_budget_bytes() {
+  static long long cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("DSB_L2_BAND_MB");
+    long long mb = e ? atoll(e) : 96;
+    cached = mb * (1LL << 20);
+  }
+  return cached;
 }
 
 static int validate_plan(const dsb_plan* p) {
@@ -154,6 +178,7 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
   if (n == 0) return DSB_OK;
   if (!x || !y) { dsb_set_error("dsb_points: null coordinate column"); return DSB_ERR_ARG; }
   if ((int64_t)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1) > (1LL << 40)) { dsb_set_error("dsb_points: canvas too large"); return DSB_ERR_ARG; }
+  if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("dsb_points: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
   PointsArgs a;
   a.v = *view; a.x = x; a.y = y; a.n = n; a.row_offset = row_offset; a.plan = *plan;
   const int threads = 256;
@@ -161,9 +186,31 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
   long long cap = (long long)dsb_num_sms() * 8;   // 8 CTAs of 256 threads per SM: full occupancy, whole waves
   int grid = (int)(want < cap ? want : cap);
   cudaStream_t s = (cudaStream_t)stream;
-  if (xy_dtype == DSB_F32) k_points_generic<float><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F64) k_points_generic<double><<<grid, threads, 0, s>>>(a);
-  else { dsb_set_error("dsb_points: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
-  DSB_CUDA_CHECK_LAUNCH("dsb_points");
+
+  // L2 banding.  REDs into an L2-resident canvas run at ~170 G/s; once the canvases outgrow L2 every RED
+  // becomes a DRAM read-modify-write (27-47 G/s measured, profiles/r01a_configs.md).  HBM read bandwidth is
+  // nearly idle on this path, so when the accumulator footprint exceeds the budget the rows are re-read once
+  // per band of canvas rows and only the points of that band are scattered: K passes, each L2-resident.
+  long long bytes_per_pixel = 0;
+  for (int k = 0; k < plan->nops; k++) bytes_per_pixel += op_cell_bytes(plan->ops[k].op);
+  bytes_per_pixel *= (plan->ncat > 0 ? plan->ncat : 1);
+  const long long npixels = (long long)view->width * view->height;
+  const long long budget = l2_band_budget_bytes();
+  long long nbands = 1;
+  if (budget > 0 && bytes_per_pixel * npixels > budget && n >= (1LL << 22)) {
+    nbands = (bytes_per_pixel * npixels + budget - 1) / budget;
+    if (nbands > view->height) nbands = view->height;
+    if (nbands > 64) nbands = 64;
+  }
+  const long long rows_per_band = (view->height + nbands - 1) / nbands;
+  for (long long b = 0; b < nbands; b++) {
+    a.band_lo = b * rows_per_band * view->width;
+    a.band_hi = (b + 1) * rows_per_band * view->width;
+    if (a.band_hi > npixels) a.band_hi = npixels;
+    if (a.band_lo >= a.band_hi) break;
+    if (xy_dtype == DSB_F32) k_points_generic<float><<<grid, threads, 0, s>>>(a);
+    else k_points_generic<double><<<grid, threads, 0, s>>>(a);
+    DSB_CUDA_CHECK_LAUNCH("dsb_points");
+  }
   return DSB_OK;
 }
