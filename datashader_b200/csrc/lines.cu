@@ -7,6 +7,7 @@
 // All geometry is f64 with unfused multiply/add (-fmad=false semantics via _rn intrinsics where the
 // result feeds a floor/ceil/compare), matching the numba CPU arithmetic that the oracle pins.
 #include "common.cuh"
+#include "accum.cuh"
 #include <limits.h>
 
 struct LineArgs {
@@ -23,6 +24,9 @@ struct LineArgs {
   long long xxmax, yymax;   // round(mapper(xmax)*sx+tx): map_onto_pixel_snap, line.py:714-715
   long long nx, ny;         // round((xmax-xmin)*sx): draw_segment, line.py:1087-1088
   int overwrite;
+  int use_plan;             // line_width == 0 with an accumulator plan (any reduction the point path supports)
+  long long row_offset;
+  dsb_plan plan;
 };
 
 __device__ __forceinline__ double fmul64(double a, double b) { return __dmul_rn(a, b); }
@@ -37,11 +41,22 @@ struct LineCtx {
   long long width;
   void* canvas;
   uint8_t* mask;
+  const dsb_plan* plan;     // non-null: run the accumulator plan for every touched pixel
+  long long line, row;      // line index within the frame / global row id
+  int cat;                  // category of this line (by()), -1 = skip
 };
 
 // ---- appends, line_width == 0 (reductions.py _append / _append_no_field) ------------------------
 __device__ __forceinline__ void append_px(const LineCtx& c, long long x, long long y) {
-  const long long cell = y * c.width + x;
+  long long cell = y * c.width + x;
+  if (c.plan) {
+    if (c.plan->ncat > 0) {
+      if (c.cat < 0) return;
+      cell = cell * c.plan->ncat + c.cat;
+    }
+    for (int k = 0; k < c.plan->nops; k++) apply_base(c.plan->ops[k], cell, c.line, c.row);
+    return;
+  }
   switch (c.agg) {
     case DSB_LINE_ANY:
       if (c.has_field && c.field_nan) return;
@@ -352,11 +367,58 @@ __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
     c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
     c.field = c.has_field ? load_f64(a.val, a.val_dtype, i) : 0.0;
     c.field_nan = c.has_field && (c.field != c.field);
+    c.plan = a.use_plan ? &a.plan : nullptr;
+    c.line = i; c.row = a.row_offset + i; c.cat = 0;
+    if (a.use_plan && a.plan.ncat > 0) {
+      int cc = load_cat(a.plan.cat, a.plan.cat_dtype, i);
+      if (cc < 0) cc += a.plan.ncat;
+      c.cat = (cc < 0 || cc >= a.plan.ncat) ? -1 : cc;
+    }
     draw_segment<XY>(a, c, segment_start, segment_end, x0, x1, y0, y1, xm, ym);
   }
 }
 
 static long long py_round(double v) { return (long long)nearbyint(v); }   // Python round(): half to even
+
+static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char* what) {
+  const dsb_view* view = &a.v;
+  const double mx = view->x_log ? log10(view->xmax) : view->xmax, my = view->y_log ? log10(view->ymax) : view->ymax;
+  a.xxmax = py_round(mx * view->sx + view->tx);
+  a.yymax = py_round(my * view->sy + view->ty);
+  a.nx = py_round((view->xmax - view->xmin) * view->sx);
+  a.ny = py_round((view->ymax - view->ymin) * view->sy);
+  const long long total = a.nlines * (a.nverts - 1);
+  const int threads = 128;
+  long long want = (total + threads - 1) / threads;
+  long long cap = (long long)dsb_num_sms() * 16;
+  int grid = (int)(want < cap ? want : cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (xy_dtype == DSB_F32) k_lines_axis1<float><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F64) k_lines_axis1<double><<<grid, threads, 0, s>>>(a);
+  else { dsb_set_error("%s: xy_dtype must be f32 or f64", what); return DSB_ERR_ARG; }
+  DSB_CUDA_CHECK_LAUNCH(what);
+  return DSB_OK;
+}
+
+// Bresenham lines with a full accumulator plan: any reduction Canvas.points supports, applied to every pixel a
+// line touches, with i = the line's row (the reference passes the row index i to append, line.py:1046-1097).
+extern "C" int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype,
+                                    int64_t nlines, int64_t nverts, int64_t row_offset, const dsb_plan* plan,
+                                    void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_lines_axis1_plan: bad view"); return DSB_ERR_ARG; }
+  if (!plan || plan->nops < 1 || plan->nops > DSB_MAX_OPS) { dsb_set_error("dsb_lines_axis1_plan: bad plan"); return DSB_ERR_ARG; }
+  for (int k = 0; k < plan->nops; k++)
+    if (!plan->ops[k].agg || plan->ops[k].op < DSB_OP_COUNT || plan->ops[k].op > DSB_OP_MATCHROW64) {
+      dsb_set_error("dsb_lines_axis1_plan: bad op %d", k); return DSB_ERR_ARG;
+    }
+  if (nlines <= 0 || nverts < 2) return DSB_OK;
+  if (!xs || !ys) { dsb_set_error("dsb_lines_axis1_plan: null vertex arrays"); return DSB_ERR_ARG; }
+  LineArgs a;
+  a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = nullptr; a.val_dtype = DSB_NONE;
+  a.agg = 0; a.line_width = 0.0; a.canvas = nullptr; a.mask = nullptr; a.overwrite = 1;
+  a.use_plan = 1; a.row_offset = row_offset; a.plan = *plan;
+  return launch_lines(a, xy_dtype, stream, "dsb_lines_axis1_plan");
+}
 
 extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
                                int64_t nverts, const void* val, int32_t val_dtype, int32_t agg, double line_width,
@@ -374,21 +436,7 @@ extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void*
   LineArgs a;
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
   a.agg = agg; a.line_width = line_width; a.canvas = canvas; a.mask = mask;
-  const double mx = view->x_log ? log10(view->xmax) : view->xmax, my = view->y_log ? log10(view->ymax) : view->ymax;
-  a.xxmax = py_round(mx * view->sx + view->tx);
-  a.yymax = py_round(my * view->sy + view->ty);
-  a.nx = py_round((view->xmax - view->xmin) * view->sx);
-  a.ny = py_round((view->ymax - view->ymin) * view->sy);
   a.overwrite = !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM);   // antialias.py:47-56
-  const long long total = nlines * (nverts - 1);
-  const int threads = 128;
-  long long want = (total + threads - 1) / threads;
-  long long cap = (long long)dsb_num_sms() * 16;
-  int grid = (int)(want < cap ? want : cap);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (xy_dtype == DSB_F32) k_lines_axis1<float><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F64) k_lines_axis1<double><<<grid, threads, 0, s>>>(a);
-  else { dsb_set_error("dsb_lines_axis1: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
-  DSB_CUDA_CHECK_LAUNCH("dsb_lines_axis1");
-  return DSB_OK;
+  a.use_plan = 0; a.row_offset = 0;
+  return launch_lines(a, xy_dtype, stream, "dsb_lines_axis1");
 }

@@ -93,17 +93,14 @@ def _categorical_setup(agg, schema):
     return categorizer, len(labels), labels
 
 
-def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
-    """One fused launch per <= DSB_MAX_OPS accumulators over one resident row chunk."""
-    lib = _lib.lib()
-    x, y, xy_dtype = _xy_columns(chunk, glyph.x, glyph.y)
-    n, row_offset = len(chunk), chunk.row_offset
+def _plans(chunk, accs, canv, ctx, categorizer, ncat):
+    """Yield (plan, keepalive) for groups of <= DSB_MAX_OPS accumulators over one resident row chunk."""
     codes = categorizer.codes(chunk).contiguous() if ncat else None
     for i in range(0, len(accs), _lib.DSB_MAX_OPS):
         group = accs[i:i + _lib.DSB_MAX_OPS]
         plan = _lib.Plan()
         plan.nops = len(group)
-        keep = []
+        keep = [codes]
         for k, acc in enumerate(group):
             b = plan.ops[k]
             b.op = rd.ACC_OP[acc.kind]
@@ -122,16 +119,28 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
             plan.cat = codes.data_ptr()
             plan.cat_dtype = _lib.dsb_dtype(str(codes.dtype).replace("torch.", ""))
             plan.ncat = ncat
-        # dsb_points takes at most 2^32 rows per call (32-bit local row field of the arg accumulators)
-        step = 1 << 32
-        for lo in range(0, max(n, 1), step):
-            cnt = min(step, n - lo)
-            if cnt <= 0:
-                break
-            if lo:
-                raise NotImplementedError("more than 2^32 rows per device in one call")
-            _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, cnt, row_offset + lo,
-                                      C.byref(plan), ctx.stream_ptr), "dsb_points")
+        yield plan, keep
+
+
+def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
+    """One fused launch per <= DSB_MAX_OPS accumulators over one resident row chunk."""
+    lib = _lib.lib()
+    x, y, xy_dtype = _xy_columns(chunk, glyph.x, glyph.y)
+    n, row_offset = len(chunk), chunk.row_offset
+    if n > (1 << 32):
+        raise NotImplementedError("more than 2^32 rows per device chunk")
+    for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
+        _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
+                                  ctx.stream_ptr), "dsb_points")
+
+
+def _launch_lines(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
+    """Bresenham lines: the same accumulator plans, one row of the frame = one line (i = line index)."""
+    lib = _lib.lib()
+    xs, ys, xy_dtype = ctx.line_vertices
+    for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
+        _lib.check(lib.dsb_lines_axis1_plan(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, xs.shape[0], xs.shape[1],
+                                            chunk.row_offset, C.byref(plan), ctx.stream_ptr), "dsb_lines_axis1_plan")
 
 
 def _to_host(t, np_view=None):
@@ -151,8 +160,7 @@ def _use_count_fast_path(agg, ncat, dist):
     return False
 
 
-def points(source, canvas, glyph: Point, agg, dist=None):
-    """bypixel for Point glyphs."""
+def _prepare(source, glyph, agg, canvas):
     needed = list(dict.fromkeys(glyph.required_columns() + agg.columns_needed))
     frame = as_frame(source, needed)
     schema = frame.schema()
@@ -162,7 +170,51 @@ def points(source, canvas, glyph: Point, agg, dist=None):
     glyph.validate(schema)
     agg.validate(schema)
     canvas.validate()
+    return needed, frame, schema
 
+
+def _accumulate_and_finalize(frame, resident, needed, schema, view, canvas, glyph, agg, dist, launch, ctx_extra=None):
+    """accumulators -> fused launches (per chunk, per stage) -> [all-reduce] -> finalize."""
+    device = frame.device
+    stream_ptr = torch.cuda.current_stream(device).cuda_stream
+    single = resident is not None
+    categorizer, ncat, labels = _categorical_setup(agg, schema)
+    shape = (canvas.plot_height, canvas.plot_width) + ((ncat,) if ncat else ())
+    ctx = _Ctx(frame, view, shape, dist)
+    if single:
+        ctx.resident = resident
+    for k, v in (ctx_extra or {}).items():
+        setattr(ctx, k, v)
+    reds = _reductions_of(agg)
+    accs, seen = [], set()
+    for r in reds:
+        for a in r._accs(ctx):
+            if a.key not in seen:
+                seen.add(a.key)
+                accs.append(a)
+    canv = {a.key: _alloc_canvas(a, shape, device, stream_ptr) for a in accs}
+    # stage 0: everything that needs one pass; stage 1: accumulators that read a finished stage-0 canvas
+    for stage in ([a for a in accs if a.aux is None], [a for a in accs if a.aux is not None]):
+        if not stage:
+            continue
+        if config.time_kernels:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        for ch in ([resident] if single else frame.chunks(needed)):
+            launch(view, ch, glyph, stage, canv, ctx, categorizer, ncat)
+        if config.time_kernels:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            config.kernel_events.append((ev0, ev1))
+        if dist is not None:
+            dist.combine(stage, canv)
+    results = [r._finalize(ctx, canv) for r in reds]
+    return reds, results, labels
+
+
+def points(source, canvas, glyph: Point, agg, dist=None):
+    """bypixel for Point glyphs."""
+    needed, frame, schema = _prepare(source, glyph, agg, canvas)
     device = frame.device
     with torch.cuda.device(device):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
@@ -180,40 +232,8 @@ def points(source, canvas, glyph: Point, agg, dist=None):
             x_range, y_range = canvas.x_range, canvas.y_range
         canvas.validate_ranges(x_range, y_range)
         view, x_st, y_st = make_view(canvas, x_range, y_range)
-
-        categorizer, ncat, labels = _categorical_setup(agg, schema)
-        shape = (canvas.plot_height, canvas.plot_width) + ((ncat,) if ncat else ())
-        ctx = _Ctx(frame, view, shape, dist)
-        if single:
-            ctx.resident = resident
-
-        reds = _reductions_of(agg)
-        accs, seen = [], set()
-        for r in reds:
-            for a in r._accs(ctx):
-                if a.key not in seen:
-                    seen.add(a.key)
-                    accs.append(a)
-        canv = {a.key: _alloc_canvas(a, shape, device, stream_ptr) for a in accs}
-
-        # stage 0: everything that needs one pass; stage 1: accumulators that read a finished stage-0 canvas
-        for stage in ([a for a in accs if a.aux is None], [a for a in accs if a.aux is not None]):
-            if not stage:
-                continue
-            if config.time_kernels:
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            for ch in ([resident] if single else frame.chunks(needed)):
-                _launch_points(view, ch, glyph, stage, canv, ctx, categorizer, ncat)
-            if config.time_kernels:
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev1.record()
-                config.kernel_events.append((ev0, ev1))
-            if dist is not None:
-                dist.combine(stage, canv)
-
-        results = [r._finalize(ctx, canv) for r in reds]
-
+        reds, results, labels = _accumulate_and_finalize(frame, resident, needed, schema, view, canvas, glyph, agg, dist,
+                                                         _launch_points)
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)
@@ -253,22 +273,16 @@ def _stack_columns(frame, names):
 
 def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=None):
     """bypixel for LinesAxis1 (one line per row)."""
-    needed = list(dict.fromkeys(glyph.required_columns() + agg.columns_needed))
-    frame = as_frame(source, needed)
-    schema = frame.schema()
-    for c in needed:
-        if c not in schema:
-            raise ValueError("specified column not found")
-    glyph.validate(schema)
-    agg.validate(schema)
-    canvas.validate()
+    needed, frame, schema = _prepare(source, glyph, agg, canvas)
     frame = frame.resident(needed)      # lines are staged whole ([nlines, nverts] matrices)
-    if isinstance(agg, (rd.summary, rd.by)) or agg._line_agg is None:
-        raise NotImplementedError(f"{type(agg).__name__} is not implemented for datashader_b200 lines yet")
     line_width = float(glyph._line_width)
-    if line_width > 0 and isinstance(agg, rd.min):
+    if line_width == 0:
+        return _lines_axis1_plan(frame, needed, schema, canvas, glyph, agg, dist)
+    if isinstance(agg, (rd.summary, rd.by)) or agg._line_agg is None:
+        raise NotImplementedError(f"{type(agg).__name__} is not implemented for antialiased datashader_b200 lines yet")
+    if isinstance(agg, rd.min):
         raise NotImplementedError("min() needs the 2-stage antialias combine (antialias.py:30-58): not implemented yet")
-    if line_width > 0 and isinstance(agg, (rd.count, rd.sum)) and not agg.self_intersect:
+    if isinstance(agg, (rd.count, rd.sum)) and not agg.self_intersect:
         raise NotImplementedError("self_intersect=False needs the 2-stage antialias combine: not implemented yet")
 
     device = frame.device
@@ -340,3 +354,24 @@ def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=No
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return DataArray(data, coords={glyph.y_label: y_axis, glyph.x_label: x_axis}, dims=[glyph.y_label, glyph.x_label],
                      attrs=dict(x_range=x_range, y_range=y_range))
+
+
+def _lines_axis1_plan(frame, needed, schema, canvas, glyph, agg, dist):
+    """line_width == 0: every reduction of the point path, applied per touched pixel with i = line row."""
+    device = frame.device
+    with torch.cuda.device(device):
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+        x_range = canvas.x_range or _auto_range([frame[c] for c in glyph.x], stream_ptr, dist, device)
+        y_range = canvas.y_range or _auto_range([frame[c] for c in glyph.y], stream_ptr, dist, device)
+        canvas.validate_ranges(x_range, y_range)
+        view, x_st, y_st = make_view(canvas, x_range, y_range)
+        xs = _stack_columns(frame, glyph.x)
+        ys = _stack_columns(frame, glyph.y)
+        if xs.dtype != ys.dtype:
+            xs, ys = xs.to(torch.float64), ys.to(torch.float64)
+        xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
+        reds, results, labels = _accumulate_and_finalize(frame, frame, needed, schema, view, canvas, glyph, agg, dist,
+                                                         _launch_lines, ctx_extra={"line_vertices": (xs, ys, xy_dtype)})
+    x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+    y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+    return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)

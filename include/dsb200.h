@@ -134,6 +134,12 @@ int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_
                     int64_t nverts, const void* val, int32_t val_dtype, int32_t agg, double line_width,
                     void* canvas, uint8_t* mask, void* stream);
 
+/* LinesAxis1 with line_width == 0 and a full accumulator plan (every reduction dsb_points supports): the plan runs
+ * for every pixel a line touches with i = the line's row, exactly how the reference hands the row index to append()
+ * from _bresenham (line.py:1006-1031).  Value / nan-check / category columns are per line ([nlines]). */
+int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                         int64_t nverts, int64_t row_offset, const dsb_plan* plan, void* stream);
+
 /* ---- shade: tf.shade / eq_hist (transfer_functions/__init__.py) --------------------------------- */
 /* how codes */
 #define DSB_HOW_EQ_HIST 0

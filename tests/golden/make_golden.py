@@ -260,12 +260,44 @@ def shade_cases():
     return out
 
 
+def lines_extra_cases():
+    """Bresenham lines with the reductions beyond any/count/sum/max/min (row-index based ones included)."""
+    out = {}
+    xs, ys, val = line_frame(2024, 40, 24, np.float32)
+    rng = np.random.default_rng(77)
+    nl, nverts = xs.shape
+    other = rng.random(nl).astype(np.float32) * 5
+    codes = rng.integers(0, 4, nl).astype(np.int8)
+    out["in_other"], out["in_cat"] = other, codes
+    d = {f"x{j}": xs[:, j] for j in range(nverts)}
+    d.update({f"y{j}": ys[:, j] for j in range(nverts)})
+    d["val"], d["other"] = val, other
+    d["cat"] = pd.Categorical.from_codes(codes, categories=["a", "b", "c", "d"])
+    df = pd.DataFrame(d)
+    xcols, ycols = [f"x{j}" for j in range(nverts)], [f"y{j}" for j in range(nverts)]
+    cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+    aggs = {
+        "count_val": ds.count("val"), "mean_val": ds.mean("val"), "first_val": ds.first("val"), "last_val": ds.last("val"),
+        "where_max_val_row": ds.where(ds.max("val")), "where_min_val_other": ds.where(ds.min("val"), "other"),
+        "where_first_val_other": ds.where(ds.first("val"), "other"), "by_count": ds.by("cat", ds.count()),
+        "by_max_val": ds.by("cat", ds.max("val")), "by_any": ds.by("cat", ds.any()),
+    }
+    for name, agg in aggs.items():
+        out[f"lnx_{name}"] = np.asarray(cvs.line(df, x=xcols, y=ycols, axis=1, agg=agg).data)
+    return out
+
+
 def main():
+    if "--lines-extra-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "lines_extra.npz"), **lines_extra_cases())
+        print("lines_extra.npz", os.path.getsize(os.path.join(HERE, "lines_extra.npz")) // 1024, "KiB")
+        return
     if "--shade-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "shade.npz"), **shade_cases())
         print("shade.npz", os.path.getsize(os.path.join(HERE, "shade.npz")) // 1024, "KiB")
         return
     np.savez_compressed(os.path.join(HERE, "shade.npz"), **shade_cases())
+    np.savez_compressed(os.path.join(HERE, "lines_extra.npz"), **lines_extra_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())

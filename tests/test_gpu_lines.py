@@ -62,3 +62,28 @@ def test_lines_vs_oracle_larger():
         assert np.array_equal(got, want, equal_nan=True), lw
     got = cvs.line(df, x=xc, y=yc, axis=1, agg=ds.count()).data
     assert np.array_equal(got, ora.lines_axis1(xs, ys, view, agg="count"))
+
+
+def test_lines_all_reductions_golden():
+    """line_width=0 runs the same accumulator plans as points: mean / first / last / where / by on lines."""
+    import pandas as pd
+    import datashader_b200 as ds
+    g, gx = load("lines.npz"), load("lines_extra.npz")
+    df, xc, yc = _frame(g["in_f32_xs"], g["in_f32_ys"], g["in_f32_val"])
+    df["other"] = gx["in_other"]
+    df["cat"] = pd.Categorical.from_codes(gx["in_cat"], categories=["a", "b", "c", "d"])
+    cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+    aggs = {
+        "count_val": ds.count("val"), "mean_val": ds.mean("val"), "first_val": ds.first("val"), "last_val": ds.last("val"),
+        "where_max_val_row": ds.where(ds.max("val")), "where_min_val_other": ds.where(ds.min("val"), "other"),
+        "where_first_val_other": ds.where(ds.first("val"), "other"), "by_count": ds.by("cat", ds.count()),
+        "by_max_val": ds.by("cat", ds.max("val")), "by_any": ds.by("cat", ds.any()),
+    }
+    for name, agg in aggs.items():
+        got = cvs.line(df, x=xc, y=yc, axis=1, agg=agg).data
+        want = gx[f"lnx_{name}"]
+        assert got.dtype == want.dtype and got.shape == want.shape, name
+        if name == "mean_val":
+            np.testing.assert_allclose(got, want, rtol=1e-12, equal_nan=True, err_msg=name)
+        else:
+            assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), name
