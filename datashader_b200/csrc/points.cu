@@ -95,9 +95,9 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
                           int64_t row_offset, const dsb_plan* plan, void* stream) {
   if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points: bad view"); return DSB_ERR_ARG; }
   if (n < 0 || n > (1LL << 32)) { dsb_set_error("dsb_points: n must be in [0, 2^32] per call"); return DSB_ERR_ARG; }
+  if (n == 0) return (plan && plan->nops >= 1 && plan->nops <= DSB_MAX_OPS) ? DSB_OK : (dsb_set_error("dsb_points: bad plan (nops)"), DSB_ERR_ARG);
   int rc = validate_plan(plan);
   if (rc != DSB_OK) return rc;
-  if (n == 0) return DSB_OK;
   if (!x || !y) { dsb_set_error("dsb_points: null coordinate column"); return DSB_ERR_ARG; }
   if ((int64_t)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1) > (1LL << 40)) { dsb_set_error("dsb_points: canvas too large"); return DSB_ERR_ARG; }
   if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("dsb_points: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
