@@ -43,6 +43,11 @@ class Plan(C.Structure):
                 ("cat_dtype", C.c_int32), ("ncat", C.c_int32)]
 
 
+class LineLayout(C.Structure):
+    _fields_ = [("x_line_stride", C.c_int64), ("y_line_stride", C.c_int64), ("value_per_vertex", C.c_int32),
+                ("plot_start", C.c_int32)]
+
+
 class Dsb200Error(RuntimeError):
     pass
 
@@ -69,8 +74,10 @@ _SIGNATURES = {
     "dsb_finish_minrow": ([_p, _i64, _p], C.c_int),
     "dsb_finalize_mean": ([_p, _p, _p, _i64, _p], C.c_int),
     "dsb_finalize_sum": ([_p, _p, _p, _i64, _p], C.c_int),
-    "dsb_lines_axis1_plan": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, _i64, C.POINTER(Plan), _p], C.c_int),
-    "dsb_lines_axis1": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, _p, _i32, _i32, _f64, _p, _p, _p], C.c_int),
+    "dsb_lines_axis1_plan": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _i64, C.POINTER(Plan), _p],
+                             C.c_int),
+    "dsb_lines_axis1": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _p, _i32, _i32, _f64, _p, _p,
+                         _p], C.c_int),
 }
 
 _lib = None

@@ -10,7 +10,8 @@ from numbers import Number
 import numpy as np
 
 from . import reductions as rd
-from .glyphs import LinesAxis1, Point
+from .glyphs import (LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1XConstant, LinesAxis1YConstant, Point,
+                     _LineGlyph)
 
 
 class Axis:
@@ -135,10 +136,11 @@ class Canvas:
         x, y = _broadcast_column_specifications(x, y)
         if axis == 0:
             if isinstance(x, (Number, str)) and isinstance(y, (Number, str)):
-                raise NotImplementedError("LineAxis0 is not implemented in datashader_b200 yet")
+                glyph = LineAxis0(x, y)
             elif isinstance(x, (list, tuple)) and isinstance(y, (list, tuple)):
-                raise NotImplementedError("LineAxis0Multi is not implemented in datashader_b200 yet")
-            raise ValueError(f"""
+                glyph = LineAxis0Multi(tuple(x), tuple(y))
+            else:
+                raise ValueError(f"""
 Invalid combination of x and y arguments to Canvas.line when axis=0.
     Received:
         x: {repr(orig_x)}
@@ -148,9 +150,9 @@ See docstring for more information on valid usage""")
             if isinstance(x, (list, tuple)) and isinstance(y, (list, tuple)):
                 glyph = LinesAxis1(tuple(x), tuple(y))
             elif isinstance(x, np.ndarray) and isinstance(y, (list, tuple)):
-                raise NotImplementedError("LinesAxis1XConstant is not implemented in datashader_b200 yet")
+                glyph = LinesAxis1XConstant(x, tuple(y))
             elif isinstance(x, (list, tuple)) and isinstance(y, np.ndarray):
-                raise NotImplementedError("LinesAxis1YConstant is not implemented in datashader_b200 yet")
+                glyph = LinesAxis1YConstant(tuple(x), y)
             elif isinstance(x, (Number, str)) and isinstance(y, (Number, str)):
                 raise NotImplementedError("LinesAxis1Ragged is outside the B200 hot path")
             else:
@@ -212,6 +214,9 @@ def bypixel(source, canvas, glyph, agg, *, antialias=False):
         warnings.filterwarnings('ignore', r'All-NaN (slice|axis) encountered')
         if isinstance(glyph, Point):
             return pipeline.points(source, canvas, glyph, agg, dist=dist)
-        if isinstance(glyph, LinesAxis1):
-            return pipeline.lines_axis1(source, canvas, glyph, agg, antialias=antialias, dist=dist)
+        if isinstance(glyph, _LineGlyph):
+            if dist is not None and glyph.value_per_vertex:
+                raise NotImplementedError("axis=0 lines cannot be sharded by rows without the previous shard's last "
+                                          "vertex (data_libraries/dask.py:244-266): not implemented")
+            return pipeline.lines(source, canvas, glyph, agg, antialias=antialias, dist=dist)
     raise NotImplementedError(f"glyph {type(glyph).__name__} is not supported")

@@ -26,6 +26,9 @@ struct LineArgs {
   int overwrite;
   int use_plan;             // line_width == 0 with an accumulator plan (any reduction the point path supports)
   long long row_offset;
+  long long x_line_stride, y_line_stride;   // elements between consecutive lines (0: one shared vertex vector)
+  int value_per_vertex;     // axis=0 layouts: append(i = row of the segment's first vertex); axis=1: i = line
+  int plot_start;           // axis=0: whether vertex 0 starts a line (False for a continued dask partition)
   dsb_plan plan;
 };
 
@@ -349,28 +352,29 @@ __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) {
     const long long i = s / nseg, j = s - i * nseg;
-    const long long o = i * a.nverts + j;
-    const double x0 = (double)xs[o], y0 = (double)ys[o], x1 = (double)xs[o + 1], y1 = (double)ys[o + 1];
-    bool segment_start = (j == 0);
+    const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+    const double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
+    bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
     double xm = 0.0, ym = 0.0;
-    if (!segment_start) {
-      xm = (double)xs[o - 1]; ym = (double)ys[o - 1];
+    if (j > 0) {
+      xm = (double)xs[ox - 1]; ym = (double)ys[oy - 1];
       segment_start = (xm != xm) || (ym != ym);
       if (segment_start) { xm = 0.0; ym = 0.0; }
     }
     bool segment_end = (j == a.nverts - 2);
     if (!segment_end) {
-      const double xn = (double)xs[o + 2], yn = (double)ys[o + 2];
+      const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
       segment_end = (xn != xn) || (yn != yn);
     }
+    const long long vi = a.value_per_vertex ? j : i;      // the index the reference hands to append()
     LineCtx c;
     c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
-    c.field = c.has_field ? load_f64(a.val, a.val_dtype, i) : 0.0;
+    c.field = c.has_field ? load_f64(a.val, a.val_dtype, vi) : 0.0;
     c.field_nan = c.has_field && (c.field != c.field);
     c.plan = a.use_plan ? &a.plan : nullptr;
-    c.line = i; c.row = a.row_offset + i; c.cat = 0;
+    c.line = vi; c.row = a.row_offset + vi; c.cat = 0;
     if (a.use_plan && a.plan.ncat > 0) {
-      int cc = load_cat(a.plan.cat, a.plan.cat_dtype, i);
+      int cc = load_cat(a.plan.cat, a.plan.cat_dtype, vi);
       if (cc < 0) cc += a.plan.ncat;
       c.cat = (cc < 0 || cc >= a.plan.ncat) ? -1 : cc;
     }
@@ -402,9 +406,20 @@ static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char*
 
 // Bresenham lines with a full accumulator plan: any reduction Canvas.points supports, applied to every pixel a
 // line touches, with i = the line's row (the reference passes the row index i to append, line.py:1046-1097).
+static int apply_layout(LineArgs& a, const dsb_line_layout* L, const char* what) {
+  if (!L) {   // LinesAxis1 default: dense [nlines, nverts]
+    a.x_line_stride = a.nverts; a.y_line_stride = a.nverts; a.value_per_vertex = 0; a.plot_start = 1;
+    return DSB_OK;
+  }
+  if (L->x_line_stride < 0 || L->y_line_stride < 0) { dsb_set_error("%s: negative line stride", what); return DSB_ERR_ARG; }
+  a.x_line_stride = L->x_line_stride; a.y_line_stride = L->y_line_stride;
+  a.value_per_vertex = L->value_per_vertex; a.plot_start = L->plot_start;
+  return DSB_OK;
+}
+
 extern "C" int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype,
-                                    int64_t nlines, int64_t nverts, int64_t row_offset, const dsb_plan* plan,
-                                    void* stream) {
+                                    int64_t nlines, int64_t nverts, const dsb_line_layout* layout, int64_t row_offset,
+                                    const dsb_plan* plan, void* stream) {
   if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_lines_axis1_plan: bad view"); return DSB_ERR_ARG; }
   if (!plan || plan->nops < 1 || plan->nops > DSB_MAX_OPS) { dsb_set_error("dsb_lines_axis1_plan: bad plan"); return DSB_ERR_ARG; }
   for (int k = 0; k < plan->nops; k++)
@@ -417,12 +432,14 @@ extern "C" int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const 
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = nullptr; a.val_dtype = DSB_NONE;
   a.agg = 0; a.line_width = 0.0; a.canvas = nullptr; a.mask = nullptr; a.overwrite = 1;
   a.use_plan = 1; a.row_offset = row_offset; a.plan = *plan;
+  int rc = apply_layout(a, layout, "dsb_lines_axis1_plan");
+  if (rc != DSB_OK) return rc;
   return launch_lines(a, xy_dtype, stream, "dsb_lines_axis1_plan");
 }
 
 extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
-                               int64_t nverts, const void* val, int32_t val_dtype, int32_t agg, double line_width,
-                               void* canvas, uint8_t* mask, void* stream) {
+                               int64_t nverts, const dsb_line_layout* layout, const void* val, int32_t val_dtype,
+                               int32_t agg, double line_width, void* canvas, uint8_t* mask, void* stream) {
   if (!view || view->width <= 0 || view->height <= 0 || !canvas) { dsb_set_error("dsb_lines_axis1: bad view/canvas"); return DSB_ERR_ARG; }
   if (agg < DSB_LINE_ANY || agg > DSB_LINE_MIN) { dsb_set_error("dsb_lines_axis1: unknown agg %d", agg); return DSB_ERR_ARG; }
   const bool aa = line_width > 0.0;
@@ -438,5 +455,7 @@ extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void*
   a.agg = agg; a.line_width = line_width; a.canvas = canvas; a.mask = mask;
   a.overwrite = !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM);   // antialias.py:47-56
   a.use_plan = 0; a.row_offset = 0;
+  int rc = apply_layout(a, layout, "dsb_lines_axis1");
+  if (rc != DSB_OK) return rc;
   return launch_lines(a, xy_dtype, stream, "dsb_lines_axis1");
 }

@@ -71,17 +71,97 @@ class Point(Glyph):
         return maybe_expand_bounds(_column_bounds(stream_ptr, [frame[self.y]]))
 
 
-class LinesAxis1(Glyph):
-    """One line per row; vertex coordinates spread over columns x[0..k), y[0..k)
-    (glyphs/line.py:198-306)."""
+def _to_float_matrix(cols):
+    dt = torch.float32 if all(c.dtype == torch.float32 for c in cols) else torch.float64
+    return torch.stack([c.to(dt) for c in cols], dim=0).contiguous()
+
+
+class _LineGlyph(Glyph):
+    """Common host side of the line layouts: every layout is presented to the kernel as vertex vectors
+    `xs, ys` of shape [nlines, nverts] (or one shared [nverts] vector), plus a dsb_line_layout."""
     antialiased = False
     _line_width = 0
+    x_label = "x"
+    y_label = "y"
+    value_per_vertex = False      # axis=0 layouts index values by vertex (row), axis=1 by line (row)
+
+    def compute_x_bounds(self, frame, stream_ptr):
+        return maybe_expand_bounds(_column_bounds(stream_ptr, self._x_tensors(frame)))
+
+    def compute_y_bounds(self, frame, stream_ptr):
+        return maybe_expand_bounds(_column_bounds(stream_ptr, self._y_tensors(frame)))
+
+
+class LineAxis0(_LineGlyph):
+    """One line through all rows: vertices (x[i], y[i]) (glyphs/line.py:59-111)."""
+    value_per_vertex = True
+
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    @property
+    def x_label(self):
+        return self.x
+
+    @property
+    def y_label(self):
+        return self.y
+
+    def required_columns(self):
+        return [self.x, self.y]
+
+    def validate(self, schema):
+        if schema[str(self.x)][0] not in ("float", "int"):
+            raise ValueError('x must be real')
+        elif schema[str(self.y)][0] not in ("float", "int"):
+            raise ValueError('y must be real')
+
+    def _x_tensors(self, frame):
+        return [frame[self.x]]
+
+    def _y_tensors(self, frame):
+        return [frame[self.y]]
+
+    def vertices(self, frame):
+        xs, ys = _to_float_matrix([frame[self.x]]), _to_float_matrix([frame[self.y]])
+        return xs, ys, (xs.shape[1], ys.shape[1])
+
+
+class LineAxis0Multi(_LineGlyph):
+    """One line per (x_k, y_k) column pair, vertices along the rows (glyphs/line.py:114-195)."""
+    value_per_vertex = True
 
     def __init__(self, x, y):
         self.x, self.y = tuple(x), tuple(y)
 
-    x_label = "x"
-    y_label = "y"
+    def required_columns(self):
+        return list(self.x) + list(self.y)
+
+    def validate(self, schema):
+        if not {schema[str(c)][0] for c in self.x} <= {"float", "int"}:
+            raise ValueError('x columns must be real')
+        elif not {schema[str(c)][0] for c in self.y} <= {"float", "int"}:
+            raise ValueError('y columns must be real')
+        if len(self.x) != len(self.y):
+            raise ValueError(f"x and y coordinate lengths do not match: {len(self.x)} != {len(self.y)}")
+
+    def _x_tensors(self, frame):
+        return [frame[c] for c in self.x]
+
+    def _y_tensors(self, frame):
+        return [frame[c] for c in self.y]
+
+    def vertices(self, frame):
+        xs, ys = _to_float_matrix(self._x_tensors(frame)), _to_float_matrix(self._y_tensors(frame))   # [ncols, nrows]
+        return xs, ys, (xs.shape[1], ys.shape[1])
+
+
+class LinesAxis1(_LineGlyph):
+    """One line per row; vertex coordinates spread over columns x[0..k), y[0..k)
+    (glyphs/line.py:198-306)."""
+
+    def __init__(self, x, y):
+        self.x, self.y = tuple(x), tuple(y)
 
     def required_columns(self):
         return list(self.x) + list(self.y)
@@ -96,8 +176,68 @@ class LinesAxis1(Glyph):
         if len(self.x) != len(self.y):
             raise ValueError(f"x and y coordinate lengths do not match: {len(self.x)} != {len(self.y)}")
 
-    def compute_x_bounds(self, frame, stream_ptr):
-        return maybe_expand_bounds(_column_bounds(stream_ptr, [frame[c] for c in self.x]))
+    def _x_tensors(self, frame):
+        return [frame[c] for c in self.x]
 
-    def compute_y_bounds(self, frame, stream_ptr):
-        return maybe_expand_bounds(_column_bounds(stream_ptr, [frame[c] for c in self.y]))
+    def _y_tensors(self, frame):
+        return [frame[c] for c in self.y]
+
+    def vertices(self, frame):
+        # [nverts, nlines] stacked then transposed to the reference's [nlines, nverts] (line.py:298-299)
+        xs = _to_float_matrix(self._x_tensors(frame)).t().contiguous()
+        ys = _to_float_matrix(self._y_tensors(frame)).t().contiguous()
+        return xs, ys, (xs.shape[1], ys.shape[1])
+
+
+class LinesAxis1XConstant(LinesAxis1):
+    """One line per row with a shared x vector (glyphs/line.py:309-381)."""
+
+    def __init__(self, x, y):
+        self.x = np.asarray(x)
+        self.y = tuple(y)
+
+    def required_columns(self):
+        return list(self.y)
+
+    def validate(self, schema):
+        if not {schema[str(c)][0] for c in self.y} <= {"float", "int"}:
+            raise ValueError('y columns must be real')
+        if len(self.x) != len(self.y):
+            raise ValueError(f"x and y coordinate lengths do not match: {len(self.x)} != {len(self.y)}")
+
+    def _x_tensors(self, frame):
+        return [torch.from_numpy(np.ascontiguousarray(self.x, dtype=np.float64)).to(frame.device)]
+
+    def vertices(self, frame):
+        ys = _to_float_matrix(self._y_tensors(frame)).t().contiguous()
+        xs = torch.from_numpy(np.ascontiguousarray(self.x)).to(frame.device)
+        if xs.dtype != ys.dtype or xs.dtype not in (torch.float32, torch.float64):
+            xs, ys = xs.to(torch.float64), ys.to(torch.float64)
+        return xs.reshape(1, -1).contiguous(), ys, (0, ys.shape[1])
+
+
+class LinesAxis1YConstant(LinesAxis1):
+    """One line per row with a shared y vector (glyphs/line.py:384-454)."""
+
+    def __init__(self, x, y):
+        self.x = tuple(x)
+        self.y = np.asarray(y)
+
+    def required_columns(self):
+        return list(self.x)
+
+    def validate(self, schema):
+        if not {schema[str(c)][0] for c in self.x} <= {"float", "int"}:
+            raise ValueError('x columns must be real')
+        if len(self.x) != len(self.y):
+            raise ValueError(f"x and y coordinate lengths do not match: {len(self.x)} != {len(self.y)}")
+
+    def _y_tensors(self, frame):
+        return [torch.from_numpy(np.ascontiguousarray(self.y, dtype=np.float64)).to(frame.device)]
+
+    def vertices(self, frame):
+        xs = _to_float_matrix(self._x_tensors(frame)).t().contiguous()
+        ys = torch.from_numpy(np.ascontiguousarray(self.y)).to(frame.device)
+        if xs.dtype != ys.dtype or ys.dtype not in (torch.float32, torch.float64):
+            xs, ys = xs.to(torch.float64), ys.to(torch.float64)
+        return xs, ys.reshape(1, -1).contiguous(), (xs.shape[1], 0)

@@ -19,7 +19,7 @@ from . import _lib
 from . import config
 from . import reductions as rd
 from .frame import DeviceFrame, as_frame
-from .glyphs import LinesAxis1, Point, _column_bounds, maybe_expand_bounds
+from .glyphs import Point, _column_bounds, maybe_expand_bounds
 from .xr_compat import DataArray, Dataset
 
 
@@ -137,10 +137,11 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
 def _launch_lines(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
     """Bresenham lines: the same accumulator plans, one row of the frame = one line (i = line index)."""
     lib = _lib.lib()
-    xs, ys, xy_dtype = ctx.line_vertices
+    xs, ys, xy_dtype, nlines, nverts, layout = ctx.line_vertices
     for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
-        _lib.check(lib.dsb_lines_axis1_plan(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, xs.shape[0], xs.shape[1],
-                                            chunk.row_offset, C.byref(plan), ctx.stream_ptr), "dsb_lines_axis1_plan")
+        _lib.check(lib.dsb_lines_axis1_plan(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, nlines, nverts,
+                                            C.byref(layout), chunk.row_offset, C.byref(plan), ctx.stream_ptr),
+                   "dsb_lines_axis1_plan")
 
 
 def _to_host(t, np_view=None):
@@ -265,19 +266,30 @@ def _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels):
 
 
 # ------------------------------------------------------------------------------------------ lines
-def _stack_columns(frame, names):
-    cols = [frame[c] for c in names]
-    dt = torch.float32 if all(c.dtype == torch.float32 for c in cols) else torch.float64
-    return torch.stack([c.to(dt) for c in cols], dim=1).contiguous()   # [nlines, nverts], line.py:298-299
+def _line_setup(frame, canvas, glyph, dist):
+    """ranges, view and the vertex matrices + dsb_line_layout of any line layout."""
+    device = frame.device
+    stream_ptr = torch.cuda.current_stream(device).cuda_stream
+    x_range = canvas.x_range or _auto_range(glyph._x_tensors(frame), stream_ptr, dist, device)
+    y_range = canvas.y_range or _auto_range(glyph._y_tensors(frame), stream_ptr, dist, device)
+    canvas.validate_ranges(x_range, y_range)
+    view, x_st, y_st = make_view(canvas, x_range, y_range)
+    xs, ys, (xls, yls) = glyph.vertices(frame)
+    if xs.dtype != ys.dtype:
+        xs, ys = xs.to(torch.float64), ys.to(torch.float64)
+    xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
+    nlines, nverts = int(max(xs.shape[0], ys.shape[0])), int(xs.shape[1])
+    layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), 1)
+    return x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout)
 
 
-def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=None):
-    """bypixel for LinesAxis1 (one line per row)."""
+def lines(source, canvas, glyph, agg, antialias=False, dist=None):
+    """bypixel for the line glyphs (LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1X/YConstant)."""
     needed, frame, schema = _prepare(source, glyph, agg, canvas)
     frame = frame.resident(needed)      # lines are staged whole ([nlines, nverts] matrices)
     line_width = float(glyph._line_width)
     if line_width == 0:
-        return _lines_axis1_plan(frame, needed, schema, canvas, glyph, agg, dist)
+        return _lines_plan(frame, needed, schema, canvas, glyph, agg, dist)
     if isinstance(agg, (rd.summary, rd.by)) or agg._line_agg is None:
         raise NotImplementedError(f"{type(agg).__name__} is not implemented for antialiased datashader_b200 lines yet")
     if isinstance(agg, rd.min):
@@ -288,15 +300,7 @@ def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=No
     device = frame.device
     with torch.cuda.device(device):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
-        x_range = canvas.x_range or _auto_range([frame[c] for c in glyph.x], stream_ptr, dist, device)
-        y_range = canvas.y_range or _auto_range([frame[c] for c in glyph.y], stream_ptr, dist, device)
-        canvas.validate_ranges(x_range, y_range)
-        view, x_st, y_st = make_view(canvas, x_range, y_range)
-        xs = _stack_columns(frame, glyph.x)
-        ys = _stack_columns(frame, glyph.y)
-        if xs.dtype != ys.dtype:
-            xs, ys = xs.to(torch.float64), ys.to(torch.float64)
-        xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
+        x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout) = _line_setup(frame, canvas, glyph, dist)
         H, W = canvas.plot_height, canvas.plot_width
         la = agg._line_agg
         aa = line_width > 0
@@ -320,7 +324,7 @@ def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=No
             canvas_t = torch.empty((H, W), dtype=torch.int64, device=device)
             _lib.check(lib.dsb_init_canvas(_lib.OP_MAX64 if la == _lib.LINE_MAX else _lib.OP_MIN64, canvas_t.data_ptr(),
                                            H * W, stream_ptr))
-        _lib.check(lib.dsb_lines_axis1(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, xs.shape[0], xs.shape[1],
+        _lib.check(lib.dsb_lines_axis1(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, nlines, nverts, C.byref(layout),
                                        val.data_ptr() if val is not None else None, val_dtype, la, line_width,
                                        canvas_t.data_ptr(), mask.data_ptr() if mask is not None else None, stream_ptr),
                    "dsb_lines_axis1")
@@ -356,22 +360,14 @@ def lines_axis1(source, canvas, glyph: LinesAxis1, agg, antialias=False, dist=No
                      attrs=dict(x_range=x_range, y_range=y_range))
 
 
-def _lines_axis1_plan(frame, needed, schema, canvas, glyph, agg, dist):
-    """line_width == 0: every reduction of the point path, applied per touched pixel with i = line row."""
+def _lines_plan(frame, needed, schema, canvas, glyph, agg, dist):
+    """line_width == 0: every reduction of the point path, applied per touched pixel with i = the row the
+    reference passes to append (the line for axis=1 layouts, the segment's first vertex for axis=0)."""
     device = frame.device
     with torch.cuda.device(device):
-        stream_ptr = torch.cuda.current_stream(device).cuda_stream
-        x_range = canvas.x_range or _auto_range([frame[c] for c in glyph.x], stream_ptr, dist, device)
-        y_range = canvas.y_range or _auto_range([frame[c] for c in glyph.y], stream_ptr, dist, device)
-        canvas.validate_ranges(x_range, y_range)
-        view, x_st, y_st = make_view(canvas, x_range, y_range)
-        xs = _stack_columns(frame, glyph.x)
-        ys = _stack_columns(frame, glyph.y)
-        if xs.dtype != ys.dtype:
-            xs, ys = xs.to(torch.float64), ys.to(torch.float64)
-        xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
+        x_range, y_range, view, x_st, y_st, verts = _line_setup(frame, canvas, glyph, dist)
         reds, results, labels = _accumulate_and_finalize(frame, frame, needed, schema, view, canvas, glyph, agg, dist,
-                                                         _launch_lines, ctx_extra={"line_vertices": (xs, ys, xy_dtype)})
+                                                         _launch_lines, ctx_extra={"line_vertices": verts})
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)

@@ -124,6 +124,17 @@ int dsb_finalize_sum(const double* sum, const uint8_t* mask, double* out, int64_
 /* ---- lines ---------------------------------------------------------------------------------- */
 typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5 } dsb_line_agg;
 
+/* Vertex addressing of the other line layouts.  NULL = LinesAxis1: dense [nlines, nverts] matrices, one value per
+ * line.  x_line_stride / y_line_stride = elements between consecutive lines (0 = one vertex vector shared by all
+ * lines: LinesAxis1XConstant / YConstant, line.py:1340-1535).  value_per_vertex = 1 for the axis=0 layouts
+ * (LineAxis0, LineAxis0Multi, line.py:1099-1242): value / category / row index are those of the segment's first
+ * vertex.  plot_start: whether vertex 0 starts a line (line.py:1112-1113). */
+typedef struct {
+  int64_t x_line_stride, y_line_stride;
+  int32_t value_per_vertex;
+  int32_t plot_start;
+} dsb_line_layout;
+
 /* LinesAxis1 (glyphs/line.py:1244-1337): xs, ys are [nlines, nverts] row-major of xy_dtype, `val`
  * one value per line.  line_width == 0 -> Liang-Barsky clip + snapped Bresenham (line.py:734-780,
  * 986-1031); line_width > 0 -> the antialiased rasteriser (line.py:826-983) for the single-stage
@@ -131,14 +142,15 @@ typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_
  * Canvases: line_width == 0: any u8, count i32, sum f64 (+ `mask` u8), max/min i64 key64.
  *           line_width  > 0: any i32 key32 of f32, count f32 (+mask), sum f64 (+mask), max i64 key64. */
 int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
-                    int64_t nverts, const void* val, int32_t val_dtype, int32_t agg, double line_width,
-                    void* canvas, uint8_t* mask, void* stream);
+                    int64_t nverts, const dsb_line_layout* layout, const void* val, int32_t val_dtype, int32_t agg,
+                    double line_width, void* canvas, uint8_t* mask, void* stream);
 
 /* LinesAxis1 with line_width == 0 and a full accumulator plan (every reduction dsb_points supports): the plan runs
  * for every pixel a line touches with i = the line's row, exactly how the reference hands the row index to append()
  * from _bresenham (line.py:1006-1031).  Value / nan-check / category columns are per line ([nlines]). */
 int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
-                         int64_t nverts, int64_t row_offset, const dsb_plan* plan, void* stream);
+                         int64_t nverts, const dsb_line_layout* layout, int64_t row_offset, const dsb_plan* plan,
+                         void* stream);
 
 /* ---- shade: tf.shade / eq_hist (transfer_functions/__init__.py) --------------------------------- */
 /* how codes */

@@ -287,7 +287,65 @@ def lines_extra_cases():
     return out
 
 
+def line_layout_cases():
+    """The other line layouts: LineAxis0, LineAxis0Multi, LinesAxis1XConstant, LinesAxis1YConstant
+    (core.py:408-452), Bresenham and antialiased."""
+    out = {}
+    rng = np.random.default_rng(404)
+    n = 60
+    x = np.linspace(-0.1, 1.1, n) + rng.normal(0, 0.01, n)
+    y = np.cumsum(rng.normal(0, 0.07, n)) + 0.5
+    x2 = x[::-1].copy() + 0.03
+    y2 = np.cumsum(rng.normal(0, 0.05, n)) + 0.4
+    y[17] = np.nan
+    x2[40] = np.nan
+    val = rng.random(n).astype(np.float32) * 4 - 1
+    val[5] = np.nan
+    df0 = pd.DataFrame({"x": x.astype(np.float32), "y": y.astype(np.float32), "x2": x2.astype(np.float32),
+                        "y2": y2.astype(np.float32), "val": val})
+    for k in df0.columns:
+        out[f"ax0_{k}"] = df0[k].to_numpy()
+    cvs = ds.Canvas(plot_width=50, plot_height=40, x_range=(0, 1), y_range=(0, 1))
+    aggs0 = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "mean": ds.mean("val"),
+             "first": ds.first("val"), "where_max_row": ds.where(ds.max("val"))}
+    for name, agg in aggs0.items():
+        out[f"ax0_lw0_{name}"] = np.asarray(cvs.line(df0, "x", "y", agg=agg).data)
+        out[f"ax0multi_lw0_{name}"] = np.asarray(cvs.line(df0, x=["x", "x2"], y=["y", "y2"], axis=0, agg=agg).data)
+    for name in ("any", "max"):
+        out[f"ax0_lw1_{name}"] = np.asarray(cvs.line(df0, "x", "y", agg=aggs0[name], line_width=1).data)
+        out[f"ax0multi_lw1_{name}"] = np.asarray(
+            cvs.line(df0, x=["x", "x2"], y=["y", "y2"], axis=0, agg=aggs0[name], line_width=1).data)
+
+    # constant-x / constant-y: 12 lines x 9 vertices
+    nl, nv = 12, 9
+    xc = np.linspace(0.0, 1.0, nv)
+    ys = rng.random((nl, nv)).astype(np.float32)
+    ys[3, 4] = np.nan
+    lval = rng.random(nl).astype(np.float32)
+    d = {f"y{j}": ys[:, j] for j in range(nv)}
+    d["val"] = lval
+    df1 = pd.DataFrame(d)
+    out["xc_x"], out["xc_ys"], out["xc_val"] = xc, ys, lval
+    ycols = [f"y{j}" for j in range(nv)]
+    aggs1 = {"any": ds.any(), "count": ds.count(), "max": ds.max("val"), "mean": ds.mean("val")}
+    for name, agg in aggs1.items():
+        out[f"xconst_lw0_{name}"] = np.asarray(cvs.line(df1, x=xc, y=ycols, axis=1, agg=agg).data)
+    out["xconst_lw1_max"] = np.asarray(cvs.line(df1, x=xc, y=ycols, axis=1, agg=ds.max("val"), line_width=1).data)
+    d2 = {f"x{j}": ys[:, j] for j in range(nv)}
+    d2["val"] = lval
+    df2 = pd.DataFrame(d2)
+    xcols = [f"x{j}" for j in range(nv)]
+    for name, agg in aggs1.items():
+        out[f"yconst_lw0_{name}"] = np.asarray(cvs.line(df2, x=xcols, y=xc, axis=1, agg=agg).data)
+    out["yconst_lw1_max"] = np.asarray(cvs.line(df2, x=xcols, y=xc, axis=1, agg=ds.max("val"), line_width=1).data)
+    return out
+
+
 def main():
+    if "--line-layouts-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
+        print("line_layouts.npz", os.path.getsize(os.path.join(HERE, "line_layouts.npz")) // 1024, "KiB")
+        return
     if "--lines-extra-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "lines_extra.npz"), **lines_extra_cases())
         print("lines_extra.npz", os.path.getsize(os.path.join(HERE, "lines_extra.npz")) // 1024, "KiB")
@@ -298,6 +356,7 @@ def main():
         return
     np.savez_compressed(os.path.join(HERE, "shade.npz"), **shade_cases())
     np.savez_compressed(os.path.join(HERE, "lines_extra.npz"), **lines_extra_cases())
+    np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())

@@ -87,3 +87,44 @@ def test_lines_all_reductions_golden():
             np.testing.assert_allclose(got, want, rtol=1e-12, equal_nan=True, err_msg=name)
         else:
             assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), name
+
+
+def _cmp(got, want, key, float_sum=False):
+    assert got.dtype == want.dtype and got.shape == want.shape, key
+    if float_sum:
+        assert np.array_equal(np.isnan(got), np.isnan(want)), key
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9, equal_nan=True, err_msg=key)
+    else:
+        assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), key
+
+
+def test_line_layouts_golden():
+    """LineAxis0, LineAxis0Multi, LinesAxis1XConstant, LinesAxis1YConstant against the real reference."""
+    import pandas as pd
+    import datashader_b200 as ds
+    g = load("line_layouts.npz")
+    df0 = pd.DataFrame({k: g[f"ax0_{k}"] for k in ("x", "y", "x2", "y2", "val")})
+    cvs = ds.Canvas(plot_width=50, plot_height=40, x_range=(0, 1), y_range=(0, 1))
+    aggs0 = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "mean": ds.mean("val"),
+             "first": ds.first("val"), "where_max_row": ds.where(ds.max("val"))}
+    for name, agg in aggs0.items():
+        r = cvs.line(df0, "x", "y", agg=agg)
+        assert tuple(r.dims) == ("y", "x")
+        _cmp(r.data, g[f"ax0_lw0_{name}"], f"ax0 {name}", name in ("sum", "mean"))
+        _cmp(cvs.line(df0, x=["x", "x2"], y=["y", "y2"], axis=0, agg=agg).data, g[f"ax0multi_lw0_{name}"],
+             f"ax0multi {name}", name in ("sum", "mean"))
+    for name in ("any", "max"):
+        _cmp(cvs.line(df0, "x", "y", agg=aggs0[name], line_width=1).data, g[f"ax0_lw1_{name}"], f"ax0 aa {name}")
+        _cmp(cvs.line(df0, x=["x", "x2"], y=["y", "y2"], axis=0, agg=aggs0[name], line_width=1).data,
+             g[f"ax0multi_lw1_{name}"], f"ax0multi aa {name}")
+    xc, ys, lval = g["xc_x"], g["xc_ys"], g["xc_val"]
+    nv = ys.shape[1]
+    df1 = pd.DataFrame({**{f"y{j}": ys[:, j] for j in range(nv)}, "val": lval})
+    df2 = pd.DataFrame({**{f"x{j}": ys[:, j] for j in range(nv)}, "val": lval})
+    ycols, xcols = [f"y{j}" for j in range(nv)], [f"x{j}" for j in range(nv)]
+    aggs1 = {"any": ds.any(), "count": ds.count(), "max": ds.max("val"), "mean": ds.mean("val")}
+    for name, agg in aggs1.items():
+        _cmp(cvs.line(df1, x=xc, y=ycols, axis=1, agg=agg).data, g[f"xconst_lw0_{name}"], f"xconst {name}", name == "mean")
+        _cmp(cvs.line(df2, x=xcols, y=xc, axis=1, agg=agg).data, g[f"yconst_lw0_{name}"], f"yconst {name}", name == "mean")
+    _cmp(cvs.line(df1, x=xc, y=ycols, axis=1, agg=ds.max("val"), line_width=1).data, g["xconst_lw1_max"], "xconst aa")
+    _cmp(cvs.line(df2, x=xcols, y=xc, axis=1, agg=ds.max("val"), line_width=1).data, g["yconst_lw1_max"], "yconst aa")
