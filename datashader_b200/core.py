@@ -10,7 +10,7 @@ from numbers import Number
 import numpy as np
 
 from . import reductions as rd
-from .glyphs import (LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1XConstant, LinesAxis1YConstant, Point,
+from .glyphs import (AreaGlyph, LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1XConstant, LinesAxis1YConstant, Point,
                      _LineGlyph)
 
 
@@ -180,8 +180,77 @@ The axis argument to Canvas.line must be 0 or 1
 
     # ---------------------------------------------------------------------------- areas
     def area(self, source, x, y, agg=None, axis=0, y_stack=None):
-        """core.py:480-709.  Areas are a "next" row of the scope table - not built yet."""
-        raise NotImplementedError("Canvas.area is not implemented in datashader_b200 yet")
+        """Compute a reduction by pixel, mapping data to pixels as a filled area region (core.py:480-709)."""
+        if agg is None:
+            agg = rd.any()
+        orig_x, orig_y, orig_y_stack = x, y, y_stack
+        x, y, y_stack = _broadcast_column_specifications(x, y, y_stack)
+        scalar, seq = (Number, str), (list, tuple)
+        if axis == 0:
+            if y_stack is None:
+                if isinstance(x, scalar) and isinstance(y, scalar):
+                    glyph = AreaGlyph(LineAxis0(x, y))
+                elif isinstance(x, seq) and isinstance(y, seq):
+                    glyph = AreaGlyph(LineAxis0Multi(tuple(x), tuple(y)))
+                else:
+                    raise ValueError(f"""
+Invalid combination of x and y arguments to Canvas.area when axis=0.
+    Received:
+        x: {repr(x)}
+        y: {repr(y)}
+See docstring for more information on valid usage""")
+            else:
+                if isinstance(x, scalar) and isinstance(y, scalar) and isinstance(y_stack, scalar):
+                    glyph = AreaGlyph(LineAxis0(x, y), LineAxis0(x, y_stack))
+                elif isinstance(x, seq) and isinstance(y, seq) and isinstance(y_stack, seq):
+                    glyph = AreaGlyph(LineAxis0Multi(tuple(x), tuple(y)), LineAxis0Multi(tuple(x), tuple(y_stack)))
+                else:
+                    raise ValueError(f"""
+Invalid combination of x, y, and y_stack arguments to Canvas.area when axis=0.
+    Received:
+        x: {repr(orig_x)}
+        y: {repr(orig_y)}
+        y_stack: {repr(orig_y_stack)}
+See docstring for more information on valid usage""")
+        elif axis == 1:
+            if y_stack is None:
+                if isinstance(x, seq) and isinstance(y, seq):
+                    glyph = AreaGlyph(LinesAxis1(tuple(x), tuple(y)))
+                elif isinstance(x, np.ndarray) and isinstance(y, seq):
+                    glyph = AreaGlyph(LinesAxis1XConstant(x, tuple(y)))
+                elif isinstance(x, seq) and isinstance(y, np.ndarray):
+                    glyph = AreaGlyph(LinesAxis1YConstant(tuple(x), y))
+                elif isinstance(x, scalar) and isinstance(y, scalar):
+                    raise NotImplementedError("AreaToZeroAxis1Ragged is outside the B200 hot path")
+                else:
+                    raise ValueError(f"""
+Invalid combination of x and y arguments to Canvas.area when axis=1.
+    Received:
+        x: {repr(x)}
+        y: {repr(y)}
+See docstring for more information on valid usage""")
+            else:
+                if isinstance(x, seq) and isinstance(y, seq) and isinstance(y_stack, seq):
+                    glyph = AreaGlyph(LinesAxis1(tuple(x), tuple(y)), LinesAxis1(tuple(x), tuple(y_stack)))
+                elif isinstance(x, np.ndarray) and isinstance(y, seq) and isinstance(y_stack, seq):
+                    glyph = AreaGlyph(LinesAxis1XConstant(x, tuple(y)), LinesAxis1XConstant(x, tuple(y_stack)))
+                elif isinstance(x, seq) and isinstance(y, np.ndarray) and isinstance(y_stack, np.ndarray):
+                    glyph = AreaGlyph(LinesAxis1YConstant(tuple(x), y), LinesAxis1YConstant(tuple(x), y_stack))
+                elif isinstance(x, scalar) and isinstance(y, scalar) and isinstance(y_stack, scalar):
+                    raise NotImplementedError("AreaToLineAxis1Ragged is outside the B200 hot path")
+                else:
+                    raise ValueError(f"""
+Invalid combination of x, y, and y_stack arguments to Canvas.area when axis=1.
+    Received:
+        x: {repr(orig_x)}
+        y: {repr(orig_y)}
+        y_stack: {repr(orig_y_stack)}
+See docstring for more information on valid usage""")
+        else:
+            raise ValueError(f"""
+The axis argument to Canvas.area must be 0 or 1
+    Received: {axis}""")
+        return bypixel(source, self, glyph, agg)
 
     # ---------------------------------------------------------------------------- validation
     def validate_ranges(self, x_range, y_range):
@@ -214,6 +283,10 @@ def bypixel(source, canvas, glyph, agg, *, antialias=False):
         warnings.filterwarnings('ignore', r'All-NaN (slice|axis) encountered')
         if isinstance(glyph, Point):
             return pipeline.points(source, canvas, glyph, agg, dist=dist)
+        if isinstance(glyph, AreaGlyph):
+            if dist is not None and glyph.value_per_vertex:
+                raise NotImplementedError("axis=0 areas cannot be sharded by rows: not implemented")
+            return pipeline.areas(source, canvas, glyph, agg, dist=dist)
         if isinstance(glyph, _LineGlyph):
             if dist is not None and glyph.value_per_vertex:
                 raise NotImplementedError("axis=0 lines cannot be sharded by rows without the previous shard's last "

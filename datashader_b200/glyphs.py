@@ -241,3 +241,55 @@ class LinesAxis1YConstant(LinesAxis1):
         if xs.dtype != ys.dtype or ys.dtype not in (torch.float32, torch.float64):
             xs, ys = xs.to(torch.float64), ys.to(torch.float64)
         return xs, ys.reshape(1, -1).contiguous(), (xs.shape[1], 0)
+
+
+class AreaGlyph(Glyph):
+    """Filled area between the curve of `line` and y = 0 (stack is None) or the curve of `stack`
+    (glyphs/area.py:60-900: AreaToZero* / AreaToLine* for the axis0, axis0-multi, axis1 and constant-x/y layouts).
+    The vertex layout is the one of the wrapped line glyph."""
+
+    def __init__(self, line, stack=None):
+        self.line, self.stack = line, stack
+        self.value_per_vertex = line.value_per_vertex
+
+    @property
+    def x_label(self):
+        return self.line.x_label
+
+    @property
+    def y_label(self):
+        return self.line.y_label
+
+    def required_columns(self):
+        cols = self.line.required_columns()
+        if self.stack is not None:
+            cols = cols + [c for c in self.stack.required_columns() if c not in cols]
+        return cols
+
+    def validate(self, schema):
+        self.line.validate(schema)
+        if self.stack is not None:
+            self.stack.validate(schema)
+
+    def _x_tensors(self, frame):
+        return self.line._x_tensors(frame)
+
+    def _y_tensors(self, frame):
+        ts = self.line._y_tensors(frame)
+        if self.stack is not None:
+            ts = ts + self.stack._y_tensors(frame)
+        return ts
+
+    def y_bounds_include_zero(self):
+        return self.stack is None      # area.py:71-79
+
+    def vertices(self, frame):
+        xs, ys0, (xls, yls) = self.line.vertices(frame)
+        ys1 = None
+        if self.stack is not None:
+            _, ys1, _ = self.stack.vertices(frame)
+        ts = [t for t in (xs, ys0, ys1) if t is not None]
+        if len({t.dtype for t in ts}) > 1:
+            xs, ys0 = xs.to(torch.float64), ys0.to(torch.float64)
+            ys1 = ys1.to(torch.float64) if ys1 is not None else None
+        return xs, ys0, ys1, (xls, yls)

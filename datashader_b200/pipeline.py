@@ -371,3 +371,44 @@ def _lines_plan(frame, needed, schema, canvas, glyph, agg, dist):
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)
+
+
+# ------------------------------------------------------------------------------------------ areas
+def _launch_areas(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
+    lib = _lib.lib()
+    xs, ys0, ys1, xy_dtype, nlines, nverts, layout = ctx.area_vertices
+    for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
+        _lib.check(lib.dsb_areas_plan(C.byref(view), xs.data_ptr(), ys0.data_ptr(), ys1.data_ptr() if ys1 is not None else None,
+                                      xy_dtype, nlines, nverts, C.byref(layout), chunk.row_offset, C.byref(plan),
+                                      ctx.stream_ptr), "dsb_areas_plan")
+
+
+def areas(source, canvas, glyph, agg, dist=None):
+    """bypixel for the area glyphs (Canvas.area, core.py:480-709)."""
+    needed, frame, schema = _prepare(source, glyph, agg, canvas)
+    frame = frame.resident(needed)
+    device = frame.device
+    with torch.cuda.device(device):
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+        x_range = canvas.x_range or _auto_range(glyph._x_tensors(frame), stream_ptr, dist, device)
+        if canvas.y_range:
+            y_range = canvas.y_range
+        else:
+            lo, hi = _column_bounds(stream_ptr, glyph._y_tensors(frame))
+            if dist is not None:
+                lo, hi = dist.global_bounds(lo, hi, device)
+            if glyph.y_bounds_include_zero():          # area.py:71-79
+                lo, hi = (lo if lo < 0 else 0), (hi if hi > 0 else 0)
+            y_range = maybe_expand_bounds((lo, hi))
+        canvas.validate_ranges(x_range, y_range)
+        view, x_st, y_st = make_view(canvas, x_range, y_range)
+        xs, ys0, ys1, (xls, yls) = glyph.vertices(frame)
+        xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
+        nlines, nverts = int(max(xs.shape[0], ys0.shape[0])), int(xs.shape[1])
+        layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), 1)
+        reds, results, labels = _accumulate_and_finalize(
+            frame, frame, needed, schema, view, canvas, glyph, agg, dist, _launch_areas,
+            ctx_extra={"area_vertices": (xs, ys0, ys1, xy_dtype, nlines, nverts, layout)})
+    x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+    y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+    return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)

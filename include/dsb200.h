@@ -152,6 +152,15 @@ int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, i
                          int64_t nverts, const dsb_line_layout* layout, int64_t row_offset, const dsb_plan* plan,
                          void* stream);
 
+/* ---- areas ----------------------------------------------------------------------------------------- */
+/* Filled areas (glyphs/area.py): one trapezoid per vertex pair, x-driven double-Bresenham scan fill
+ * (_build_draw_trapezoid_y :1076-1320, _skip_or_clip_trapezoid_y :1323-1380) with the accumulator plan applied to
+ * every filled pixel.  ys1 == NULL: fill to y = 0 (AreaToZero*, stacked = False); otherwise fill between the two
+ * curves (AreaToLine*, stacked = True).  Layouts as for lines (dsb_line_layout; y_line_stride applies to both ys). */
+int dsb_areas_plan(const dsb_view* view, const void* xs, const void* ys0, const void* ys1, int32_t xy_dtype,
+                   int64_t nlines, int64_t nverts, const dsb_line_layout* layout, int64_t row_offset,
+                   const dsb_plan* plan, void* stream);
+
 /* ---- shade: tf.shade / eq_hist (transfer_functions/__init__.py) --------------------------------- */
 /* how codes */
 #define DSB_HOW_EQ_HIST 0

@@ -341,7 +341,73 @@ def line_layout_cases():
     return out
 
 
+def area_cases():
+    """Canvas.area for the ten non-ragged layouts (core.py:480-709, glyphs/area.py)."""
+    out = {}
+    rng = np.random.default_rng(808)
+    n = 50
+    x = np.linspace(-0.1, 1.1, n) + rng.normal(0, 0.01, n)
+    y = np.cumsum(rng.normal(0, 0.12, n)) + 0.2
+    ys = y - rng.random(n) * 0.4
+    x2 = np.linspace(1.05, -0.05, n)
+    y2 = np.cumsum(rng.normal(0, 0.1, n))
+    y2s = y2 + rng.random(n) * 0.3
+    y[11] = np.nan
+    ys[30] = np.nan
+    val = (rng.random(n) * 3).astype(np.float32)
+    val[7] = np.nan
+    f32 = np.float32
+    df0 = pd.DataFrame({"x": x.astype(f32), "y": y.astype(f32), "ys": ys.astype(f32), "x2": x2.astype(f32),
+                        "y2": y2.astype(f32), "y2s": y2s.astype(f32), "val": val})
+    for k in df0.columns:
+        out[f"a0_{k}"] = df0[k].to_numpy()
+    canvases = {"fixed": ds.Canvas(plot_width=45, plot_height=35, x_range=(0, 1), y_range=(-0.5, 1.0)),
+                "auto": ds.Canvas(plot_width=33, plot_height=27)}
+    aggs = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "first": ds.first("val")}
+    for cn, cvs in canvases.items():
+        for an, agg in aggs.items():
+            out[f"a0_zero_{cn}_{an}"] = np.asarray(cvs.area(df0, "x", "y", agg=agg).data)
+            out[f"a0_line_{cn}_{an}"] = np.asarray(cvs.area(df0, "x", "y", agg=agg, y_stack="ys").data)
+            out[f"a0m_zero_{cn}_{an}"] = np.asarray(cvs.area(df0, x=["x", "x2"], y=["y", "y2"], agg=agg, axis=0).data)
+            out[f"a0m_line_{cn}_{an}"] = np.asarray(
+                cvs.area(df0, x=["x", "x2"], y=["y", "y2"], y_stack=["ys", "y2s"], agg=agg, axis=0).data)
+        r = cvs.area(df0, "x", "y")
+        out[f"a0_zero_{cn}_yrange"] = np.asarray(r.attrs["y_range"], dtype=np.float64)
+
+    nl, nv = 10, 8
+    xm = (np.tile(np.linspace(-0.1, 1.1, nv), (nl, 1)) + rng.normal(0, 0.02, (nl, nv))).astype(f32)
+    ym = (rng.random((nl, nv)) * 1.4 - 0.3).astype(f32)
+    ysm = (ym - rng.random((nl, nv)).astype(f32) * 0.5).astype(f32)
+    ym[2, 3] = np.nan
+    lval = (rng.random(nl) * 2).astype(f32)
+    out["a1_x"], out["a1_y"], out["a1_ys"], out["a1_val"] = xm, ym, ysm, lval
+    d = {f"x{j}": xm[:, j] for j in range(nv)}
+    d.update({f"y{j}": ym[:, j] for j in range(nv)})
+    d.update({f"s{j}": ysm[:, j] for j in range(nv)})
+    d["val"] = lval
+    df1 = pd.DataFrame(d)
+    xc, yc, sc = [f"x{j}" for j in range(nv)], [f"y{j}" for j in range(nv)], [f"s{j}" for j in range(nv)]
+    xconst = np.linspace(0.0, 1.0, nv)
+    yconst = np.linspace(0.9, -0.2, nv)
+    sconst = yconst - 0.25
+    out["a1_xconst"], out["a1_yconst"], out["a1_sconst"] = xconst, yconst, sconst
+    cvs = canvases["fixed"]
+    aggs1 = {"any": ds.any(), "count": ds.count(), "max": ds.max("val"), "mean": ds.mean("val")}
+    for an, agg in aggs1.items():
+        out[f"a1_zero_{an}"] = np.asarray(cvs.area(df1, x=xc, y=yc, agg=agg, axis=1).data)
+        out[f"a1_line_{an}"] = np.asarray(cvs.area(df1, x=xc, y=yc, y_stack=sc, agg=agg, axis=1).data)
+        out[f"a1xc_zero_{an}"] = np.asarray(cvs.area(df1, x=xconst, y=yc, agg=agg, axis=1).data)
+        out[f"a1xc_line_{an}"] = np.asarray(cvs.area(df1, x=xconst, y=yc, y_stack=sc, agg=agg, axis=1).data)
+        out[f"a1yc_zero_{an}"] = np.asarray(cvs.area(df1, x=xc, y=yconst, agg=agg, axis=1).data)
+        out[f"a1yc_line_{an}"] = np.asarray(cvs.area(df1, x=xc, y=yconst, y_stack=sconst, agg=agg, axis=1).data)
+    return out
+
+
 def main():
+    if "--areas-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
+        print("areas.npz", os.path.getsize(os.path.join(HERE, "areas.npz")) // 1024, "KiB")
+        return
     if "--line-layouts-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
         print("line_layouts.npz", os.path.getsize(os.path.join(HERE, "line_layouts.npz")) // 1024, "KiB")
@@ -357,6 +423,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "shade.npz"), **shade_cases())
     np.savez_compressed(os.path.join(HERE, "lines_extra.npz"), **lines_extra_cases())
     np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
+    np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())
