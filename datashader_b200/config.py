@@ -7,3 +7,8 @@ device_results = False
 # Record CUDA events around the fused aggregation launches (bench.py's roofline leg reads them).
 time_kernels = False
 kernel_events = []     # [(start_event, end_event)] appended per Canvas call when time_kernels is set
+
+# K2: count() with the canvas privatised in shared memory (csrc/points.cu).  Used for resident chunks of at least
+# `priv_min_rows` float32 points when the canvas fits (<= 786 432 cells); "off" forces the global-RED kernel.
+priv_count = True
+priv_min_rows = 100_000_000

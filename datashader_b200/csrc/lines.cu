@@ -137,7 +137,10 @@ template <> __device__ __forceinline__ double seg_delta<double>(double a1, doubl
 
 __device__ __forceinline__ double clampd(double x, double lo, double hi) { return fmax(lo, fmin(x, hi)); }
 __device__ __forceinline__ double linearstep(double e0, double e1, double x) {
-  return clampd(__ddiv_rn(fsub64(x, e0), fsub64(e1, e0)), 0.0, 1.0);
+  const double den = fsub64(e1, e0);
+  // line_width <= 1 gives den == 1.0 exactly: x / 1.0 == x, so the f64 division (a ~30-instruction sequence) is skipped
+  const double t = (den == 1.0) ? fsub64(x, e0) : __ddiv_rn(fsub64(x, e0), den);
+  return clampd(t, 0.0, 1.0);
 }
 __device__ __forceinline__ double x_intercept(double y, double cx0, double cy0, double cx1, double cy1) {
   if (cy0 == cy1) return cx1;

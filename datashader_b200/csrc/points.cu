@@ -50,6 +50,172 @@ __global__ void __launch_bounds__(256) k_points_generic(const PointsArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K2: count() with the WHOLE canvas privatised per SM in shared memory.
+//
+// Shared-memory atomics run 6x faster than global REDs (profiles/r01_ubench.md) but a 900x525 u32 canvas is
+// 1.89 MB.  Here every pixel gets a SLOT-bit field ((SLOT-1)-bit counter + 1 guard bit, 32/SLOT fields per word:
+// SLOT=3 -> 472 500 pixels in 189 KB).  A hit is one ATOMS.ADD with return; the thread that sees the counter wrap
+// into its guard bit owns the spill: it clears the guard (ATOMS) and adds 2^(SLOT-1) to the global scratch canvas
+// (one RED per 2^(SLOT-1) hits).  At the end each CTA flushes its residual counters.  The guard bit absorbs hits
+// that arrive between a wrap and its spill; a field can only be corrupted if 2^(SLOT-1) MORE hits land on the same
+// pixel of the same SM inside that window, and the thread whose add overflows an all-ones field sees it (old ==
+// all ones) and raises `flag`.  flag == 0 therefore proves exactness; otherwise the scratch is discarded and the
+// count is redone with global REDs (k_points_generic gated on the flag), so the result is always exact.
+// Other accumulators of the plan (e.g. the f64 sum of mean) run as global REDs in the same pass.
+struct PrivArgs {
+  PointsArgs p;
+  int priv_op;              // index of the COUNT op held in shared memory
+  const float* vcol;        // the float32 value column shared by the plan's ops (vector-loaded with x, y), or NULL
+  long long npriv;          // cells [0, npriv) live in shared memory; the (few) cells beyond go straight to REDs
+  unsigned int* scratch;    // [ncell] u32, zeroed: spills + flush land here
+  unsigned int* flag;       // set to 1 on a carry event
+};
+
+template <int SLOT>
+__device__ __forceinline__ void priv_hit(uint32_t* sh, long long cell, unsigned int* scratch, unsigned int& bad) {
+  constexpr uint32_t PER = 32 / SLOT;
+  constexpr uint32_t CNT_MASK = (1u << (SLOT - 1)) - 1u, GUARD = 1u << (SLOT - 1), FIELD = (1u << SLOT) - 1u;
+  const uint32_t b = (uint32_t)cell;
+  const uint32_t w = b / PER, sft = (b - w * PER) * SLOT;
+  const uint32_t old = atomicAdd(sh + w, 1u << sft);
+  const uint32_t f = (old >> sft) & FIELD;
+  if (f == CNT_MASK) {
+    atomicSub(sh + w, GUARD << sft);
+    atomicAdd(scratch + b, GUARD);
+  } else if (f == FIELD) {
+    bad = 1;
+  }
+}
+
+// apply_base for an op whose value column is the vector-loaded float32 column (value already in a register)
+__device__ __forceinline__ void apply_base_f32(const dsb_base& b, long long cell, long long i, long long row, float v) {
+  if (b.chk_dtype != DSB_NONE) { apply_base(b, cell, i, row); return; }
+  if (v != v) return;                       // every op below skips NaN fields
+  switch (b.op) {
+    case DSB_OP_COUNT: atomicAdd((unsigned int*)b.agg + cell, 1u); return;
+    case DSB_OP_ANY: ((uint8_t*)b.agg)[cell] = 1; return;
+    case DSB_OP_SUM: atomicAdd((double*)b.agg + cell, (double)v); return;
+    case DSB_OP_MAX32: atomicMax((int*)b.agg + cell, key32_from_f32(v)); return;
+    case DSB_OP_MIN32: atomicMin((int*)b.agg + cell, key32_from_f32(v)); return;
+    default: apply_base(b, cell, i, row); return;
+  }
+}
+
+template <int SLOT, bool VEC, bool HASV>
+__global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a) {
+  extern __shared__ uint32_t sh[];
+  constexpr uint32_t PER = 32 / SLOT;
+  constexpr uint32_t FIELD = (1u << SLOT) - 1u;
+  const PointsArgs& p = a.p;
+  const long long ncell = a.npriv;
+  const int nwords = (int)((ncell + PER - 1) / PER);
+  for (int j = threadIdx.x; j < nwords; j += blockDim.x) sh[j] = 0;
+  __syncthreads();
+  const float* __restrict__ x = (const float*)p.x;
+  const float* __restrict__ y = (const float*)p.y;
+  const dsb_base& cop = p.plan.ops[a.priv_op];
+  const int ncat = p.plan.ncat;
+  unsigned int bad = 0;
+
+  constexpr bool have_v = VEC && HASV;
+  auto one = [&](float xv, float yv, float vv, long long i) {
+    long long cell = map_to_cell<float>(p.v, xv, yv);
+    if (cell < 0) return;
+    if (ncat > 0) {
+      int c = load_cat(p.plan.cat, p.plan.cat_dtype, i);
+      if (c < 0) c += ncat;
+      if (c < 0 || c >= ncat) return;
+      cell = cell * ncat + c;
+    }
+    for (int k = 0; k < p.plan.nops; k++) {
+      const dsb_base& b = p.plan.ops[k];
+      const bool reg_v = have_v && b.val == (const void*)a.vcol;
+      if (k == a.priv_op) {
+        if (cop.chk_dtype != DSB_NONE && col_isnan(cop.chk, cop.chk_dtype, i)) continue;
+        if (reg_v) { if (vv != vv) continue; }
+        else if (cop.val_dtype != DSB_NONE && col_isnan(cop.val, cop.val_dtype, i)) continue;
+        if (cell < a.npriv) priv_hit<SLOT>(sh, cell, a.scratch, bad);
+        else atomicAdd(a.scratch + cell, 1u);
+      } else if (reg_v) {
+        apply_base_f32(b, cell, i, p.row_offset + i, vv);
+      } else {
+        apply_base(b, cell, i, p.row_offset + i);
+      }
+    }
+  };
+
+  if (VEC) {
+    const float4* __restrict__ x4 = (const float4*)p.x;
+    const float4* __restrict__ y4 = (const float4*)p.y;
+    const long long n4 = p.n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += 2 * stride) {
+      const bool two = i4 + stride < n4;
+      const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
+      const float4* __restrict__ v4 = (const float4*)a.vcol;
+      float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
+      float4 va = have_v ? __ldcs(v4 + i4) : nan4;
+      float4 xb = two ? __ldcs(x4 + i4 + stride) : nan4;
+      float4 yb = two ? __ldcs(y4 + i4 + stride) : nan4;
+      float4 vb = (two && have_v) ? __ldcs(v4 + i4 + stride) : nan4;
+      one(xa.x, ya.x, va.x, 4 * i4 + 0); one(xa.y, ya.y, va.y, 4 * i4 + 1);
+      one(xa.z, ya.z, va.z, 4 * i4 + 2); one(xa.w, ya.w, va.w, 4 * i4 + 3);
+      if (two) {
+        const long long j4 = i4 + stride;
+        one(xb.x, yb.x, vb.x, 4 * j4 + 0); one(xb.y, yb.y, vb.y, 4 * j4 + 1);
+        one(xb.z, yb.z, vb.z, 4 * j4 + 2); one(xb.w, yb.w, vb.w, 4 * j4 + 3);
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {           // tail rows
+      const long long i = (n4 << 2) + threadIdx.x;
+      one(x[i], y[i], have_v ? a.vcol[i] : NAN, i);
+    }
+  } else {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) one(__ldcs(x + i), __ldcs(y + i), NAN, i);
+  }
+
+  __syncthreads();
+  // flush the residual counters (guard bits are clear unless a spill was lost, which `bad` reports)
+  for (long long j = threadIdx.x; j < ncell; j += blockDim.x) {
+    const uint32_t w = (uint32_t)j / PER, sft = ((uint32_t)j - w * PER) * SLOT;
+    const uint32_t c = (sh[w] >> sft) & FIELD;
+    if (c) atomicAdd(a.scratch + j, c);
+  }
+  if (bad) atomicOr(a.flag, 1u);
+}
+
+// canvas += scratch when the privatised pass was exact (flag == 0)
+__global__ void k_priv_commit(unsigned int* __restrict__ canvas, const unsigned int* __restrict__ scratch,
+                              const unsigned int* __restrict__ flag, long long n) {
+  if (*flag) return;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { unsigned int v = scratch[i]; if (v) canvas[i] += v; }
+}
+
+// the exact redo of the privatised op with global REDs, only when the flag was raised
+template <typename XY>
+__global__ void __launch_bounds__(256) k_points_generic_if(const PointsArgs a, const unsigned int* __restrict__ flag) {
+  if (*flag == 0) return;
+  const XY* __restrict__ x = (const XY*)a.x;
+  const XY* __restrict__ y = (const XY*)a.y;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int ncat = a.plan.ncat;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    long long cell = map_to_cell<XY>(a.v, __ldcs(x + i), __ldcs(y + i));
+    if (cell < 0) continue;
+    if (ncat > 0) {
+      int c = load_cat(a.plan.cat, a.plan.cat_dtype, i);
+      if (c < 0) c += ncat;
+      if (c < 0 || c >= ncat) continue;
+      cell = cell * ncat + c;
+    }
+    for (int k = 0; k < a.plan.nops; k++) apply_base(a.plan.ops[k], cell, i, a.row_offset + i);
+  }
+}
+
 static long long op_cell_bytes(int op) {
   switch (op) {
     case DSB_OP_COUNT: case DSB_OP_MAX32: case DSB_OP_MIN32: return 4;
@@ -134,5 +300,87 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
     else k_points_generic<double><<<grid, threads, 0, s>>>(a);
     DSB_CUDA_CHECK_LAUNCH("dsb_points");
   }
+  return DSB_OK;
+}
+
+
+// ---- K2 entry point ------------------------------------------------------------------------------------
+template <int SLOT, bool VEC, bool HASV>
+static void launch_priv_one(const PrivArgs& a, size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_points_priv<SLOT, VEC, HASV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  k_points_priv<SLOT, VEC, HASV><<<dsb_num_sms(), 1024, smem, s>>>(a);
+}
+
+template <int SLOT>
+static int launch_priv(const PrivArgs& a, bool vec, size_t smem, cudaStream_t s) {
+  if (!vec) launch_priv_one<SLOT, false, false>(a, smem, s);
+  else if (a.vcol) launch_priv_one<SLOT, true, true>(a, smem, s);
+  else launch_priv_one<SLOT, true, false>(a, smem, s);
+  return 0;
+}
+
+extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                               int64_t row_offset, const dsb_plan* plan, int32_t priv_op, uint32_t* scratch,
+                               uint32_t* flag, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points_priv: bad view"); return DSB_ERR_ARG; }
+  if (!scratch || !flag) { dsb_set_error("dsb_points_priv: scratch/flag required"); return DSB_ERR_ARG; }
+  if (n < 0 || n > (1LL << 32)) { dsb_set_error("dsb_points_priv: n must be in [0, 2^32] per call"); return DSB_ERR_ARG; }
+  if (n == 0) return DSB_OK;
+  int rc = validate_plan(plan);
+  if (rc != DSB_OK) return rc;
+  if (priv_op < 0 || priv_op >= plan->nops || plan->ops[priv_op].op != DSB_OP_COUNT) { dsb_set_error("dsb_points_priv: priv_op must name a COUNT op"); return DSB_ERR_ARG; }
+  if (!x || !y) { dsb_set_error("dsb_points_priv: null coordinate column"); return DSB_ERR_ARG; }
+  const long long ncell = (long long)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1);
+  // 192 KB of the 228 KB L1/shared array: the rest must stay L1 for the streaming loads (measured: using all
+  // 227 KB drops count from 256 to 214 Gpts/s)
+  const size_t max_words = (size_t)(192 * 1024) / 4;
+  // widest slot (fewest spills) that keeps at least 97 % of the cells in shared memory; the remainder, if any,
+  // is scattered with plain REDs
+  int slot = 0;
+  const int slots[5] = {8, 5, 4, 3, 2};
+  for (int k = 0; k < 5; k++) {
+    const long long per = 32 / slots[k];
+    if ((long long)max_words * per * 100 >= ncell * 97) { slot = slots[k]; break; }
+  }
+  if (xy_dtype != DSB_F32 || slot == 0) {
+    dsb_set_error("dsb_points_priv: needs float32 coordinates and a canvas of at most %lld cells", (long long)max_words * 16);
+    return DSB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  PrivArgs a;
+  a.p.v = *view; a.p.x = x; a.p.y = y; a.p.n = n; a.p.row_offset = row_offset; a.p.band_lo = 0; a.p.band_hi = ncell; a.p.plan = *plan;
+  a.priv_op = priv_op; a.scratch = scratch; a.flag = flag;
+  a.vcol = nullptr;       // the first 16-byte aligned float32 value column of the plan rides along with x, y
+  for (int k = 0; k < plan->nops && !a.vcol; k++)
+    if (plan->ops[k].val_dtype == DSB_F32 && plan->ops[k].val && ((uintptr_t)plan->ops[k].val & 15) == 0)
+      a.vcol = (const float*)plan->ops[k].val;
+  cudaMemsetAsync(scratch, 0, (size_t)ncell * 4, s);
+  cudaMemsetAsync(flag, 0, 4, s);
+  const bool vec = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  const long long per = 32 / slot;
+  a.npriv = ncell < (long long)max_words * per ? ncell : (long long)max_words * per;
+  const size_t smem = (size_t)((a.npriv + per - 1) / per) * 4;
+  switch (slot) {
+    case 8: launch_priv<8>(a, vec, smem, s); break;
+    case 5: launch_priv<5>(a, vec, smem, s); break;
+    case 4: launch_priv<4>(a, vec, smem, s); break;
+    case 3: launch_priv<3>(a, vec, smem, s); break;
+    default: launch_priv<2>(a, vec, smem, s); break;
+  }
+  DSB_CUDA_CHECK_LAUNCH("dsb_points_priv");
+  unsigned int* canvas = (unsigned int*)plan->ops[priv_op].agg;
+  long long g = (ncell + 255) / 256, cap = (long long)dsb_num_sms() * 8;
+  k_priv_commit<<<(int)(g < cap ? g : cap), 256, 0, s>>>(canvas, scratch, flag, ncell);
+  // exact redo of the count with global REDs, executed only if a carry event was seen
+  PointsArgs r = a.p;
+  r.plan.nops = 1; r.plan.ops[0] = plan->ops[priv_op];
+  long long want = (n + 255) / 256;
+  int grid = (int)(want < cap ? want : cap);
+  k_points_generic_if<float><<<grid, 256, 0, s>>>(r, flag);
+  DSB_CUDA_CHECK_LAUNCH("dsb_points_priv(commit)");
   return DSB_OK;
 }

@@ -130,6 +130,19 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
     if n > (1 << 32):
         raise NotImplementedError("more than 2^32 rows per device chunk")
     for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
+        if config.priv_count and xy_dtype == _lib.F32 and n >= config.priv_min_rows:
+            priv = [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_COUNT]
+            ncell = int(np.prod(ctx.shape))
+            if priv and ncell <= 786_432:
+                scratch = getattr(ctx, "_priv_scratch", None)
+                if scratch is None:
+                    scratch = ctx._priv_scratch = torch.empty(ncell + 1, dtype=torch.int32, device=x.device)
+                rc = lib.dsb_points_priv(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
+                                         priv[0], scratch.data_ptr(), scratch.data_ptr() + 4 * ncell, ctx.stream_ptr)
+                if rc == 0:
+                    continue
+                if rc != -3:
+                    _lib.check(rc, "dsb_points_priv")
         _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
                                   ctx.stream_ptr), "dsb_points")
 

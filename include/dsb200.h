@@ -98,6 +98,15 @@ int dsb_init_canvas(int32_t op, void* agg, int64_t ncell, void* stream);
 int dsb_points(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
                int64_t row_offset, const dsb_plan* plan, void* stream);
 
+/* K2 - the same contract as dsb_points for a plan that contains a COUNT accumulator (`priv_op` = its index), with
+ * that accumulator's whole canvas privatised per SM in shared memory as packed guard-bit counters.
+ * Requires float32 coordinates and width*height*ncat <= ~800 000 cells; otherwise returns DSB_ERR_UNSUPPORTED and the
+ * caller uses dsb_points.  scratch: [cells] u32 work canvas, flag: 1 u32 (both device, contents ignored on entry).
+ * The result is always exact: a detected counter carry makes the library redo the count with global REDs. */
+int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                    int64_t row_offset, const dsb_plan* plan, int32_t priv_op, uint32_t* scratch, uint32_t* flag,
+                    void* stream);
+
 /* NaN-skipping min/max of a column: Glyph._compute_bounds_numba (glyphs/glyph.py:66-78).
  * out_minmax: 2 doubles on the device, (+inf, -inf) when no finite-or-inf value exists. */
 int dsb_bounds(const void* col, int32_t dtype, int64_t n, double* out_minmax, void* stream);

@@ -191,3 +191,61 @@ def test_host_frame_chunk_streaming(ds, monkeypatch):
     got = ds.Canvas(31, 17).points(df, "x", "y")
     v2 = ora.make_view(31, 17, ora.compute_bounds(cols["x"]), ora.compute_bounds(cols["y"]))
     assert_agg_equal(got.data, ora.points(cols, "x", "y", ("count",), v2), "chunked auto-range")
+
+
+@pytest.fixture
+def force_priv(ds):
+    old = ds.config.priv_min_rows
+    ds.config.priv_min_rows = 0
+    yield
+    ds.config.priv_min_rows = old
+
+
+@pytest.mark.parametrize("W,H", [(2, 2), (500, 400), (600, 500), (900, 525), (1024, 768)])
+def test_priv_count_kernel_matches_oracle(ds, force_priv, W, H):
+    """K2 (shared-memory privatised count): every slot width (8/5/4/3/2 bits), count / count(col) / mean / by."""
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(W * 1000 + H)
+    n = 400_003                                   # not a multiple of 4: exercises the vector tail
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": rng.standard_normal(n).astype(np.float32)}
+    cols["v32"][rng.integers(0, n, 400)] = np.nan
+    cols["x"][:5] = [0.0, 1.0, 0.5, np.nan, 2.0]
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    for spec in (("count",), ("count", "v32"), ("mean", "v32")):
+        assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view), f"priv {spec} {W}x{H}")
+    # unaligned column start -> scalar-load variant
+    frame2 = ds.DeviceFrame({k: torch.from_numpy(v).cuda()[1:] for k, v in cols.items()})
+    cols2 = {k: v[1:] for k, v in cols.items()}
+    assert_agg_equal(cvs.points(frame2, "x", "y", ds.count()).data, ora.points(cols2, "x", "y", ("count",), view), "priv unaligned")
+
+
+def test_priv_count_hot_pixel_falls_back_exactly(ds, force_priv):
+    """All points in a handful of pixels: guard bits overflow, the carry is detected and the count is redone
+    with global REDs - the result must still be exact."""
+    import torch
+    n = 3_000_000
+    x = torch.full((n,), 0.5, dtype=torch.float32, device="cuda")
+    y = torch.full((n,), 0.25, dtype=torch.float32, device="cuda")
+    x[::7] = 0.75
+    frame = ds.DeviceFrame({"x": x, "y": y})
+    got = ds.Canvas(900, 525, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(frame, "x", "y").data
+    assert int(got.sum()) == n
+    assert got[131, 450] == n - len(range(0, n, 7)) and got[131, 675] == len(range(0, n, 7))
+
+
+def test_priv_by_count_small_canvas(ds, force_priv):
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(77)
+    n = 200_000
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "cat": rng.integers(0, NCAT, n).astype(np.int8), "cat__ncat": NCAT}
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items() if k != "cat__ncat"},
+                           categories={"cat": [f"c{i}" for i in range(NCAT)]})
+    view = ora.make_view(300, 200, (0.0, 1.0), (0.0, 1.0))
+    got = ds.Canvas(300, 200, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(frame, "x", "y", ds.count_cat("cat")).data
+    assert_agg_equal(got, ora.points(cols, "x", "y", ("by", "cat", ("count",)), view), "priv by count")
