@@ -102,8 +102,27 @@ __device__ __forceinline__ void apply_base_f32(const dsb_base& b, long long cell
   }
 }
 
-template <int SLOT, bool VEC, bool HASV>
-__global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a) {
+// float32 fast path of the pixel mapping.  xf = fmaf(x, sx32, tx32) differs from the reference's exact value by at
+// most `ex` (host-side bound: 2^-23 * (W + 1 + max|x| * |sx| + |tx|)); whenever xf is further than that from an
+// integer its floor IS the reference's truncated f64 result, otherwise the exact f64 mapping is evaluated.  The
+// bounds test is exact: xlo/xhi are the float32 values that bracket the f64 bounds from inside.
+struct FastMap {
+  float sx, tx, sy, ty, xlo, xhi, ylo, yhi, ex, ey;
+  int enabled;
+};
+
+__device__ __forceinline__ long long map_to_cell_fast(const FastMap& f, const dsb_view& v, float x, float y) {
+  if (!(x >= f.xlo && x <= f.xhi && y >= f.ylo && y <= f.yhi)) return -1;
+  const float xf = fmaf(x, f.sx, f.tx), yf = fmaf(y, f.sy, f.ty);
+  const float xr = floorf(xf), yr = floorf(yf);
+  const float dx = xf - xr, dy = yf - yr;
+  if (dx < f.ex || dx > 1.0f - f.ex || dy < f.ey || dy > 1.0f - f.ey) return map_to_cell<float>(v, x, y);
+  return (long long)((int)yr * v.width + (int)xr);
+}
+
+// MODE 0: count() only; MODE 1: SUM + COUNT of one vector-loaded float32 column (mean); MODE 2: any plan
+template <int SLOT, int MODE, bool VEC>
+__global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a, const FastMap fm) {
   extern __shared__ uint32_t sh[];
   constexpr uint32_t PER = 32 / SLOT;
   constexpr uint32_t FIELD = (1u << SLOT) - 1u;
@@ -116,12 +135,25 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a) {
   const float* __restrict__ y = (const float*)p.y;
   const dsb_base& cop = p.plan.ops[a.priv_op];
   const int ncat = p.plan.ncat;
+  double* __restrict__ sum_canvas = (MODE == 1) ? (double*)p.plan.ops[1 - a.priv_op].agg : nullptr;
   unsigned int bad = 0;
+  constexpr bool have_v = VEC && MODE >= 1;
 
-  constexpr bool have_v = VEC && HASV;
   auto one = [&](float xv, float yv, float vv, long long i) {
-    long long cell = map_to_cell<float>(p.v, xv, yv);
+    long long cell = fm.enabled ? map_to_cell_fast(fm, p.v, xv, yv) : map_to_cell<float>(p.v, xv, yv);
     if (cell < 0) return;
+    if (MODE == 0) {
+      if (cell < a.npriv) priv_hit<SLOT>(sh, cell, a.scratch, bad);
+      else atomicAdd(a.scratch + cell, 1u);
+      return;
+    }
+    if (MODE == 1) {
+      if (vv != vv) return;
+      atomicAdd(sum_canvas + cell, (double)vv);
+      if (cell < a.npriv) priv_hit<SLOT>(sh, cell, a.scratch, bad);
+      else atomicAdd(a.scratch + cell, 1u);
+      return;
+    }
     if (ncat > 0) {
       int c = load_cat(p.plan.cat, p.plan.cat_dtype, i);
       if (c < 0) c += ncat;
@@ -130,7 +162,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a) {
     }
     for (int k = 0; k < p.plan.nops; k++) {
       const dsb_base& b = p.plan.ops[k];
-      const bool reg_v = have_v && b.val == (const void*)a.vcol;
+      const bool reg_v = have_v && a.vcol != nullptr && b.val == (const void*)a.vcol;
       if (k == a.priv_op) {
         if (cop.chk_dtype != DSB_NONE && col_isnan(cop.chk, cop.chk_dtype, i)) continue;
         if (reg_v) { if (vv != vv) continue; }
@@ -148,17 +180,18 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a) {
   if (VEC) {
     const float4* __restrict__ x4 = (const float4*)p.x;
     const float4* __restrict__ y4 = (const float4*)p.y;
+    const float4* __restrict__ v4 = (const float4*)a.vcol;
+    const bool lv = have_v && a.vcol != nullptr;
     const long long n4 = p.n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
     for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += 2 * stride) {
       const bool two = i4 + stride < n4;
-      const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
-      const float4* __restrict__ v4 = (const float4*)a.vcol;
       float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
-      float4 va = have_v ? __ldcs(v4 + i4) : nan4;
+      float4 va = lv ? __ldcs(v4 + i4) : nan4;
       float4 xb = two ? __ldcs(x4 + i4 + stride) : nan4;
       float4 yb = two ? __ldcs(y4 + i4 + stride) : nan4;
-      float4 vb = (two && have_v) ? __ldcs(v4 + i4 + stride) : nan4;
+      float4 vb = (two && lv) ? __ldcs(v4 + i4 + stride) : nan4;
       one(xa.x, ya.x, va.x, 4 * i4 + 0); one(xa.y, ya.y, va.y, 4 * i4 + 1);
       one(xa.z, ya.z, va.z, 4 * i4 + 2); one(xa.w, ya.w, va.w, 4 * i4 + 3);
       if (two) {
@@ -169,7 +202,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a) {
     }
     if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {           // tail rows
       const long long i = (n4 << 2) + threadIdx.x;
-      one(x[i], y[i], have_v ? a.vcol[i] : NAN, i);
+      one(x[i], y[i], lv ? a.vcol[i] : NAN, i);
     }
   } else {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -305,22 +338,37 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
 
 
 // ---- K2 entry point ------------------------------------------------------------------------------------
-template <int SLOT, bool VEC, bool HASV>
-static void launch_priv_one(const PrivArgs& a, size_t smem, cudaStream_t s) {
+template <int SLOT, int MODE, bool VEC>
+static void launch_priv_one(const PrivArgs& a, const FastMap& fm, size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_points_priv<SLOT, VEC, HASV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_points_priv<SLOT, MODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  k_points_priv<SLOT, VEC, HASV><<<dsb_num_sms(), 1024, smem, s>>>(a);
+  k_points_priv<SLOT, MODE, VEC><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
 }
 
 template <int SLOT>
-static int launch_priv(const PrivArgs& a, bool vec, size_t smem, cudaStream_t s) {
-  if (!vec) launch_priv_one<SLOT, false, false>(a, smem, s);
-  else if (a.vcol) launch_priv_one<SLOT, true, true>(a, smem, s);
-  else launch_priv_one<SLOT, true, false>(a, smem, s);
-  return 0;
+static void launch_priv(const PrivArgs& a, const FastMap& fm, int mode, bool vec, size_t smem, cudaStream_t s) {
+  if (!vec) launch_priv_one<SLOT, 2, false>(a, fm, smem, s);      // unaligned columns: scalar loads, generic plan
+  else if (mode == 0) launch_priv_one<SLOT, 0, true>(a, fm, smem, s);
+  else if (mode == 1) launch_priv_one<SLOT, 1, true>(a, fm, smem, s);
+  else launch_priv_one<SLOT, 2, true>(a, fm, smem, s);
+}
+
+static float f32_at_least(double v) { float f = (float)v; return ((double)f < v) ? nextafterf(f, INFINITY) : f; }
+static float f32_at_most(double v) { float f = (float)v; return ((double)f > v) ? nextafterf(f, -INFINITY) : f; }
+
+static FastMap make_fast_map(const dsb_view* v) {
+  FastMap f;
+  f.sx = (float)v->sx; f.tx = (float)v->tx; f.sy = (float)v->sy; f.ty = (float)v->ty;
+  f.xlo = f32_at_least(v->xmin); f.xhi = f32_at_most(v->xmax); f.ylo = f32_at_least(v->ymin); f.yhi = f32_at_most(v->ymax);
+  const double ax = fmax(fabs(v->xmin), fabs(v->xmax)), ay = fmax(fabs(v->ymin), fabs(v->ymax));
+  const double ex = ldexp(1.0, -23) * (v->width + 1.0 + ax * fabs(v->sx) + fabs(v->tx));
+  const double ey = ldexp(1.0, -23) * (v->height + 1.0 + ay * fabs(v->sy) + fabs(v->ty));
+  f.ex = (float)ex; f.ey = (float)ey;
+  f.enabled = !v->x_log && !v->y_log && ex < 0.125 && ey < 0.125 && isfinite(ex) && isfinite(ey) && v->sx > 0 && v->sy > 0;
+  return f;
 }
 
 extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
@@ -364,12 +412,22 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   const long long per = 32 / slot;
   a.npriv = ncell < (long long)max_words * per ? ncell : (long long)max_words * per;
   const size_t smem = (size_t)((a.npriv + per - 1) / per) * 4;
+  // compile-time specialisations of the two headline shapes
+  int mode = 2;
+  const dsb_base& c0 = plan->ops[priv_op];
+  if (plan->ncat == 0 && plan->nops == 1 && c0.val_dtype == DSB_NONE && c0.chk_dtype == DSB_NONE) mode = 0;
+  else if (plan->ncat == 0 && plan->nops == 2 && a.vcol) {
+    const dsb_base& o = plan->ops[1 - priv_op];
+    if (o.op == DSB_OP_SUM && o.val == (const void*)a.vcol && o.val_dtype == DSB_F32 && o.chk_dtype == DSB_NONE &&
+        c0.val == (const void*)a.vcol && c0.val_dtype == DSB_F32 && c0.chk_dtype == DSB_NONE) mode = 1;
+  }
+  const FastMap fm = make_fast_map(view);
   switch (slot) {
-    case 8: launch_priv<8>(a, vec, smem, s); break;
-    case 5: launch_priv<5>(a, vec, smem, s); break;
-    case 4: launch_priv<4>(a, vec, smem, s); break;
-    case 3: launch_priv<3>(a, vec, smem, s); break;
-    default: launch_priv<2>(a, vec, smem, s); break;
+    case 8: launch_priv<8>(a, fm, mode, vec, smem, s); break;
+    case 5: launch_priv<5>(a, fm, mode, vec, smem, s); break;
+    case 4: launch_priv<4>(a, fm, mode, vec, smem, s); break;
+    case 3: launch_priv<3>(a, fm, mode, vec, smem, s); break;
+    default: launch_priv<2>(a, fm, mode, vec, smem, s); break;
   }
   DSB_CUDA_CHECK_LAUNCH("dsb_points_priv");
   unsigned int* canvas = (unsigned int*)plan->ops[priv_op].agg;

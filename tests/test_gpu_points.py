@@ -249,3 +249,32 @@ def test_priv_by_count_small_canvas(ds, force_priv):
     view = ora.make_view(300, 200, (0.0, 1.0), (0.0, 1.0))
     got = ds.Canvas(300, 200, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(frame, "x", "y", ds.count_cat("cat")).data
     assert_agg_equal(got, ora.points(cols, "x", "y", ("by", "cat", ("count",)), view), "priv by count")
+
+
+@pytest.mark.parametrize("xr,yr", [((0.0, 1.0), (0.0, 1.0)), ((-0.1, 1.05), (0.1, 0.9)), ((-3.7, 12.9), (5.0, 5.5)),
+                                   ((1.0e6, 1.0e6 + 1.0), (0.0, 1.0))])
+def test_priv_fast_mapping_adversarial_edges(ds, force_priv, xr, yr):
+    """The float32 fast path of K2 must agree with the exact f64 mapping on every pixel edge and its float32
+    neighbours (and must switch itself off when the error bound is too large, last case)."""
+    import torch
+    from oracle import oracle as ora
+    W, H = 900, 525
+    rng = np.random.default_rng(3)
+    ex = xr[0] + (xr[1] - xr[0]) * np.arange(W + 1) / W
+    ey = yr[0] + (yr[1] - yr[0]) * np.arange(H + 1) / H
+    xs, ys = [], []
+    for e, other, out in ((ex, yr, xs), (ey, xr, ys)):
+        f = e.astype(np.float32)
+        cand = np.concatenate([f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf)),
+                               np.nextafter(np.nextafter(f, np.float32(np.inf)), np.float32(np.inf))])
+        out.append(cand)
+    nx, ny = len(xs[0]), len(ys[0])
+    x = np.concatenate([xs[0], (xr[0] + (xr[1] - xr[0]) * rng.random(ny)).astype(np.float32),
+                        (xr[0] + (xr[1] - xr[0]) * rng.random(200_000)).astype(np.float32)])
+    y = np.concatenate([(yr[0] + (yr[1] - yr[0]) * rng.random(nx)).astype(np.float32), ys[0],
+                        (yr[0] + (yr[1] - yr[0]) * rng.random(200_000)).astype(np.float32)])
+    cols = {"x": x, "y": y}
+    view = ora.make_view(W, H, xr, yr)
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    got = ds.Canvas(W, H, x_range=xr, y_range=yr).points(frame, "x", "y").data
+    assert_agg_equal(got, ora.points(cols, "x", "y", ("count",), view), f"fast map {xr} {yr}")
