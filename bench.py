@@ -29,6 +29,19 @@ BYTES_PER_POINT = {"mean": 12, "count": 8}
 SEED = 20240917
 
 
+def ncu_traffic_gb(workload, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (profiles/r01_traffic.json, one `ncu --set full` launch at the same n); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        e = t.get(f"{workload}:{n}")
+        return e["dram_gb"] if e else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -56,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                          "-lms", "20", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -306,9 +319,11 @@ def run_ours(args):
                        "l2": "inputs (12 GB per GPU) are far larger than the 126 MB L2; no flush needed",
                        "combine": "NCCL all-reduce of the f64 sum and u32 count canvases" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "k_points_generic<float>", "kernel_ms": kernel_ms, "peak_source": peak_src,
-                         "algorithmic_bytes_per_point": bpp},
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic_gb(args.workload, n),
+                         "kernel": ("k_points_priv<3,1,vec> (K2: count privatised in shared memory, f64 sum via global RED)"
+                                    if args.workload == "mean" else "k_points_priv<3,0,vec> (K2)"),
+                         "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_point": bpp, "traffic_unit": "GB per launch (ncu dram read+write)"},
             "cpu_baseline": cb,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -324,7 +339,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mean", choices=["mean", "count"])

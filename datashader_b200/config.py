@@ -11,4 +11,4 @@ kernel_events = []     # [(start_event, end_event)] appended per Canvas call whe
 # K2: count() with the canvas privatised in shared memory (csrc/points.cu).  Used for resident chunks of at least
 # `priv_min_rows` float32 points when the canvas fits (<= 786 432 cells); "off" forces the global-RED kernel.
 priv_count = True
-priv_min_rows = 100_000_000
+priv_min_rows = 1 << 24        # measured crossover vs global REDs: ~15-20 M rows (tools/bench_crossover.py)
