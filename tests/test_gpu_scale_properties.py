@@ -1,0 +1,69 @@
+"""Size-independent properties at sizes the CPU oracle cannot reach in seconds (2e8 points, 900x525):
+conservation (sum of counts == rows inside the ranges), K2 (shared-memory privatised) == K1 (global REDs) bit
+for bit, partition linearity (count(A) + count(B) == count(A u B)), mean within 1e-12 between the two kernels,
+max idempotent under duplication of the input."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    import torch
+    import datashader_b200 as ds
+    n = 200_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    x = torch.rand(n, generator=g, device="cuda") * 1.2 - 0.1
+    y = torch.rand(n, generator=g, device="cuda") * 1.2 - 0.1
+    v = torch.randn(n, generator=g, device="cuda")
+    v[::1009] = float("nan")
+    return ds, torch, n, x, y, v
+
+
+def _run(ds, frame, agg, priv):
+    old = ds.config.priv_min_rows
+    ds.config.priv_min_rows = 0 if priv else 1 << 62
+    try:
+        return ds.Canvas(900, 525, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(frame, "x", "y", agg).data
+    finally:
+        ds.config.priv_min_rows = old
+
+
+def test_count_conservation_and_kernel_equivalence(big):
+    ds, torch, n, x, y, v = big
+    frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
+    inside = int(((x >= 0) & (x <= 1) & (y >= 0) & (y <= 1)).sum().item())
+    k2 = _run(ds, frame, ds.count(), True)
+    k1 = _run(ds, frame, ds.count(), False)
+    assert int(k2.sum(dtype=np.int64)) == inside
+    assert np.array_equal(k1, k2)
+    # count of a column skips its NaNs
+    k2v = _run(ds, frame, ds.count("value"), True)
+    inside_v = int(((x >= 0) & (x <= 1) & (y >= 0) & (y <= 1) & ~torch.isnan(v)).sum().item())
+    assert int(k2v.sum(dtype=np.int64)) == inside_v
+    assert np.array_equal(k2v, _run(ds, frame, ds.count("value"), False))
+
+
+def test_partition_linearity(big):
+    ds, torch, n, x, y, v = big
+    h = n // 3
+    a = ds.DeviceFrame({"x": x[:h], "y": y[:h]})
+    b = ds.DeviceFrame({"x": x[h:], "y": y[h:]}, row_offset=h)
+    whole = ds.DeviceFrame({"x": x, "y": y})
+    ca, cb, cw = (_run(ds, f, ds.count(), True) for f in (a, b, whole))
+    assert np.array_equal(ca + cb, cw)
+
+
+def test_mean_k2_vs_k1_and_max_idempotence(big):
+    ds, torch, n, x, y, v = big
+    frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
+    m2 = _run(ds, frame, ds.mean("value"), True)
+    m1 = _run(ds, frame, ds.mean("value"), False)
+    assert np.array_equal(np.isnan(m1), np.isnan(m2))
+    np.testing.assert_allclose(m2, m1, rtol=1e-12, atol=1e-15, equal_nan=True)   # f64 sums, order differs only
+    half = n // 2
+    mx = _run(ds, frame, ds.max("value"), False)
+    twice = ds.DeviceFrame({"x": torch.cat([x[:half], x]), "y": torch.cat([y[:half], y]), "value": torch.cat([v[:half], v])})
+    assert np.array_equal(_run(ds, twice, ds.max("value"), False), mx, equal_nan=True)
