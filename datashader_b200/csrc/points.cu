@@ -340,11 +340,8 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
 // ---- K2 entry point ------------------------------------------------------------------------------------
 template <int SLOT, int MODE, bool VEC>
 static void launch_priv_one(const PrivArgs& a, const FastMap& fm, size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_points_priv<SLOT, MODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
-  }
+  // per launch: the attribute is per device, and one process may drive several devices
+  cudaFuncSetAttribute(k_points_priv<SLOT, MODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   k_points_priv<SLOT, MODE, VEC><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
 }
 

@@ -170,10 +170,6 @@ def _to_host(t, np_view=None):
     return a
 
 
-def _use_count_fast_path(agg, ncat, dist):
-    return False
-
-
 def _prepare(source, glyph, agg, canvas):
     needed = list(dict.fromkeys(glyph.required_columns() + agg.columns_needed))
     frame = as_frame(source, needed)

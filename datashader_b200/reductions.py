@@ -11,14 +11,12 @@ what `uses_row_index(cuda or partitioned)` arranges in the reference (reductions
 """
 from __future__ import annotations
 
-import copy
 from enum import Enum
 
 import numpy as np
 import torch
 
 from . import _lib
-from .xr_compat import DataArray, Dataset
 
 __all__ = ["count", "any", "sum", "mean", "min", "max", "first", "last", "where", "by", "count_cat", "summary",
            "category_codes", "category_modulo", "category_binning", "SpecialColumn"]
@@ -522,8 +520,3 @@ class summary:
         return False
 
 
-def _copy_kwargs(kwargs):
-    return copy.deepcopy(kwargs)
-
-
-__all_internal__ = [Acc, ACC_INFO, ACC_OP, DataArray, Dataset]
