@@ -271,6 +271,30 @@ static long long l2_band_budget_bytes() {
   return cached;
 }
 
+// Optional L2 persistence window for banded passes (DSB_L2_PERSIST=1 enables; off by default: measured gains were
+// marginal and inconsistent - 10.8 -> 10.6 ms on config 3, profiles/r01b_l2_banding.md - because a banded pass is
+// bound by K1's per-point issue cost and the RED rate, not by L2 misses).  The carve-out is set once per device.
+static size_t g_l2_window = 0;
+static bool l2_persist_enabled() {
+  static thread_local int state = -1, state_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (state < 0 || state_dev != dev) {
+    const char* e = getenv("DSB_L2_PERSIST");
+    state = (e && atoi(e) == 1) ? 1 : 0;
+    state_dev = dev;
+    if (state) {
+      int maxp = 0, maxw = 0;
+      cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      if (maxp <= 0 || maxw <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp) != cudaSuccess) { state = 0; cudaGetLastError(); }
+      else g_l2_window = (size_t)maxw;
+    }
+  }
+  return state == 1;
+}
+static size_t l2_max_window_bytes() { return g_l2_window; }
+
 static int validate_plan(const dsb_plan* p) {
   if (!p || p->nops < 1 || p->nops > DSB_MAX_OPS) { dsb_set_error("dsb_points: bad plan (nops)"); return DSB_ERR_ARG; }
   for (int k = 0; k < p->nops; k++) {
@@ -324,13 +348,36 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
     if (nbands > 64) nbands = 64;
   }
   const long long rows_per_band = (view->height + nbands - 1) / nbands;
+  int biggest_op = 0;
+  for (int k = 1; k < plan->nops; k++) if (op_cell_bytes(plan->ops[k].op) > op_cell_bytes(plan->ops[biggest_op].op)) biggest_op = k;
   for (long long b = 0; b < nbands; b++) {
     a.band_lo = b * rows_per_band * view->width;
     a.band_hi = (b + 1) * rows_per_band * view->width;
     if (a.band_hi > npixels) a.band_hi = npixels;
     if (a.band_lo >= a.band_hi) break;
-    if (xy_dtype == DSB_F32) k_points_generic<float><<<grid, threads, 0, s>>>(a);
-    else k_points_generic<double><<<grid, threads, 0, s>>>(a);
+    if (nbands > 1 && l2_persist_enabled()) {
+      // pin this band of the (largest) accumulator canvas in L2: the launch carries an access-policy window whose
+      // hits persist while everything else (the streamed columns) is treated as streaming
+      const dsb_base& big = plan->ops[biggest_op];
+      const long long cb = op_cell_bytes(big.op) * (plan->ncat > 0 ? plan->ncat : 1);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+      at[0].val.accessPolicyWindow.base_ptr = (char*)big.agg + a.band_lo * cb;
+      size_t nb = (size_t)((a.band_hi - a.band_lo) * cb);
+      const size_t maxw = l2_max_window_bytes();
+      at[0].val.accessPolicyWindow.num_bytes = nb < maxw ? nb : maxw;
+      at[0].val.accessPolicyWindow.hitRatio = 1.0f;
+      at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (xy_dtype == DSB_F32) cudaLaunchKernelEx(&cfg, k_points_generic<float>, a);
+      else cudaLaunchKernelEx(&cfg, k_points_generic<double>, a);
+    } else {
+      if (xy_dtype == DSB_F32) k_points_generic<float><<<grid, threads, 0, s>>>(a);
+      else k_points_generic<double><<<grid, threads, 0, s>>>(a);
+    }
     DSB_CUDA_CHECK_LAUNCH("dsb_points");
   }
   return DSB_OK;
