@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "accum.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 struct PointsArgs {
   dsb_view v;
@@ -261,14 +262,24 @@ static long long op_cell_bytes(int op) {
 // Bytes of accumulator canvas one launch may touch before banding kicks in.  Default 96 MB of the 126 MB L2
 // (swept 16..144 MB on configs 3 and 5, profiles/r01b_l2_banding.md; the streamed input is read with
 // ld.global.cs so it does not displace the canvas).  DSB_L2_BAND_MB overrides (0 disables).
+static long long g_band_budget = -1;        // bytes; -1 = not initialised
+static long long g_band_min_rows = 1LL << 22;
 static long long l2_band_budget_bytes() {
-  static long long cached = -1;
-  if (cached < 0) {
+  if (g_band_budget < 0) {
     const char* e = getenv("DSB_L2_BAND_MB");
     long long mb = e ? atoll(e) : 96;
-    cached = mb * (1LL << 20);
+    g_band_budget = mb * (1LL << 20);
   }
-  return cached;
+  return g_band_budget;
+}
+
+// runtime knobs (tests and tuning): "l2_band_bytes" (0 disables banding), "band_min_rows"
+extern "C" int dsb_configure(const char* key, int64_t value) {
+  if (!key) { dsb_set_error("dsb_configure: null key"); return DSB_ERR_ARG; }
+  if (!strcmp(key, "l2_band_bytes")) { g_band_budget = value; return DSB_OK; }
+  if (!strcmp(key, "band_min_rows")) { g_band_min_rows = value; return DSB_OK; }
+  dsb_set_error("dsb_configure: unknown key %s", key);
+  return DSB_ERR_ARG;
 }
 
 // Optional L2 persistence window for banded passes (DSB_L2_PERSIST=1 enables; off by default: measured gains were
@@ -342,7 +353,7 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
   const long long npixels = (long long)view->width * view->height;
   const long long budget = l2_band_budget_bytes();
   long long nbands = 1;
-  if (budget > 0 && bytes_per_pixel * npixels > budget && n >= (1LL << 22)) {
+  if (budget > 0 && bytes_per_pixel * npixels > budget && n >= g_band_min_rows) {
     nbands = (bytes_per_pixel * npixels + budget - 1) / budget;
     if (nbands > view->height) nbands = view->height;
     if (nbands > 64) nbands = 64;

@@ -88,6 +88,10 @@ const char* dsb_last_error(void);
 /* number of kernel-launching API calls made by this process so far (diagnostics / bench.py gpu_launches) */
 int64_t dsb_launch_count(void);
 
+/* Runtime knobs: "l2_band_bytes" - accumulator bytes one dsb_points launch may touch before the rows are re-read
+ * once per band of canvas rows (default 96 MiB, 0 disables); "band_min_rows" - smallest n that is banded. */
+int dsb_configure(const char* key, int64_t value);
+
 /* Initialise an accumulator canvas of `ncell` elements to the op's identity (see dsb_op).
  * Replaces Reduction._build_create / make_create (reductions.py:397-472, compiler.py:294-301). */
 int dsb_init_canvas(int32_t op, void* agg, int64_t ncell, void* stream);

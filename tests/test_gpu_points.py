@@ -278,3 +278,39 @@ def test_priv_fast_mapping_adversarial_edges(ds, force_priv, xr, yr):
     frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
     got = ds.Canvas(W, H, x_range=xr, y_range=yr).points(frame, "x", "y").data
     assert_agg_equal(got, ora.points(cols, "x", "y", ("count",), view), f"fast map {xr} {yr}")
+
+
+def test_l2_banded_passes_match_oracle(ds):
+    """Canvases beyond the L2 budget are filled in several passes over bands of canvas rows (with a float32 y
+    pre-filter); force tiny bands and compare every kind of accumulator with the oracle."""
+    import torch
+    from datashader_b200 import _lib
+    from oracle import oracle as ora
+    L = _lib.lib()
+    rng = np.random.default_rng(12)
+    n = 150_000
+    cols = {"x": rng.random(n, dtype=np.float32) * 1.1 - 0.05, "y": rng.random(n, dtype=np.float32) * 1.1 - 0.05,
+            "v32": np.round(rng.standard_normal(n), 1).astype(np.float32), "other": rng.random(n).astype(np.float32),
+            "v64": np.round(rng.standard_normal(n), 1), "cat": rng.integers(0, NCAT, n).astype(np.int8), "cat__ncat": NCAT}
+    cols["y"][:4] = [0.0, 1.0, np.nan, 0.5]
+    df = pandas_frame(cols)
+    W, H = 301, 257
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    old_priv = ds.config.priv_count
+    try:
+        _lib.check(L.dsb_configure(b"l2_band_bytes", 64 * 1024))
+        _lib.check(L.dsb_configure(b"band_min_rows", 0))
+        ds.config.priv_count = False
+        for rname in ("count", "mean_v32", "max_v32", "max_v64", "first_v32", "last_v32", "where_max_v32_other",
+                      "where_min_v32_row", "by_count", "by_max_v32"):
+            spec = SPECS[rname]
+            got = cvs.points(df, "x", "y", make_agg(spec)).data
+            want = ora.points(cols, "x", "y", spec, view, npartitions=2 if "first" in rname or "last" in rname else 1)
+            assert_agg_equal(got, want, f"banded {rname}")
+        spec = ("where", ("max", "v64"), "other")
+        assert_agg_equal(cvs.points(df, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view), "banded 2-pass")
+    finally:
+        ds.config.priv_count = old_priv
+        _lib.check(L.dsb_configure(b"l2_band_bytes", 96 << 20))
+        _lib.check(L.dsb_configure(b"band_min_rows", 1 << 22))
