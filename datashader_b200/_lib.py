@@ -76,6 +76,7 @@ _SIGNATURES = {
     "dsb_finish_minrow": ([_p, _i64, _p], C.c_int),
     "dsb_finalize_mean": ([_p, _p, _p, _i64, _p], C.c_int),
     "dsb_finalize_sum": ([_p, _p, _p, _i64, _p], C.c_int),
+    "dsb_finalize_sum_counted": ([_p, _p, _p, _i64, _p], C.c_int),
     "dsb_lines_axis1_plan": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _i64, C.POINTER(Plan), _p],
                              C.c_int),
     "dsb_areas_plan": ([C.POINTER(View), _p, _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _i64, C.POINTER(Plan), _p],

@@ -159,6 +159,20 @@ extern "C" int dsb_finalize_sum(const double* sum, const uint8_t* mask, double* 
   return DSB_OK;
 }
 
+__global__ void k_finalize_sum_counted(const double* sum, const uint32_t* count, double* out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = count[i] ? sum[i] : (double)NAN;
+}
+
+extern "C" int dsb_finalize_sum_counted(const double* sum, const void* count_u32, double* out, int64_t ncell, void* stream) {
+  if (!sum || !count_u32 || !out) { dsb_set_error("dsb_finalize_sum_counted: null pointer"); return DSB_ERR_ARG; }
+  if (ncell == 0) return DSB_OK;
+  k_finalize_sum_counted<<<grid_for(ncell, 256), 256, 0, (cudaStream_t)stream>>>(sum, (const uint32_t*)count_u32, out, ncell);
+  DSB_CUDA_CHECK_LAUNCH("dsb_finalize_sum_counted");
+  return DSB_OK;
+}
+
 // ---- column bounds: Glyph._compute_bounds_numba (glyphs/glyph.py:66-78) ----------------------------
 __device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
   // monotone CAS; NaNs never reach here

@@ -229,6 +229,15 @@ __global__ void k_priv_commit(unsigned int* __restrict__ canvas, const unsigned 
   for (; i < n; i += stride) { unsigned int v = scratch[i]; if (v) canvas[i] += v; }
 }
 
+// any(): the privatised pass counted hits (fewer than 2^32 per call, so no wrap); canvas |= (scratch > 0)
+__global__ void k_priv_commit_any(uint8_t* __restrict__ canvas, const unsigned int* __restrict__ scratch,
+                                  const unsigned int* __restrict__ flag, long long n) {
+  if (*flag) return;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) if (scratch[i]) canvas[i] = 1;
+}
+
 // the exact redo of the privatised op with global REDs, only when the flag was raised
 template <typename XY>
 __global__ void __launch_bounds__(256) k_points_generic_if(const PointsArgs a, const unsigned int* __restrict__ flag) {
@@ -435,7 +444,11 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   if (n == 0) return DSB_OK;
   int rc = validate_plan(plan);
   if (rc != DSB_OK) return rc;
-  if (priv_op < 0 || priv_op >= plan->nops || plan->ops[priv_op].op != DSB_OP_COUNT) { dsb_set_error("dsb_points_priv: priv_op must name a COUNT op"); return DSB_ERR_ARG; }
+  if (priv_op < 0 || priv_op >= plan->nops || !(plan->ops[priv_op].op == DSB_OP_COUNT || plan->ops[priv_op].op == DSB_OP_ANY)) {
+    dsb_set_error("dsb_points_priv: priv_op must name a COUNT or ANY op"); return DSB_ERR_ARG;
+  }
+  const bool priv_any = plan->ops[priv_op].op == DSB_OP_ANY;
+  if (priv_any && n == (1LL << 32)) { dsb_set_error("dsb_points_priv: an ANY op takes fewer than 2^32 rows per call"); return DSB_ERR_ARG; }
   if (!x || !y) { dsb_set_error("dsb_points_priv: null coordinate column"); return DSB_ERR_ARG; }
   const long long ncell = (long long)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1);
   // 192 KB of the 228 KB L1/shared array: the rest must stay L1 for the streaming loads (measured: using all
@@ -485,10 +498,10 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
     default: launch_priv<2>(a, fm, mode, vec, smem, s); break;
   }
   DSB_CUDA_CHECK_LAUNCH("dsb_points_priv");
-  unsigned int* canvas = (unsigned int*)plan->ops[priv_op].agg;
   long long g = (ncell + 255) / 256, cap = (long long)dsb_num_sms() * 8;
-  k_priv_commit<<<(int)(g < cap ? g : cap), 256, 0, s>>>(canvas, scratch, flag, ncell);
-  // exact redo of the count with global REDs, executed only if a carry event was seen
+  if (priv_any) k_priv_commit_any<<<(int)(g < cap ? g : cap), 256, 0, s>>>((uint8_t*)plan->ops[priv_op].agg, scratch, flag, ncell);
+  else k_priv_commit<<<(int)(g < cap ? g : cap), 256, 0, s>>>((unsigned int*)plan->ops[priv_op].agg, scratch, flag, ncell);
+  // exact redo of the count / any with global REDs / stores, executed only if a carry event was seen
   PointsArgs r = a.p;
   r.plan.nops = 1; r.plan.ops[0] = plan->ops[priv_op];
   long long want = (n + 255) / 256;

@@ -131,7 +131,8 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
         raise NotImplementedError("more than 2^32 rows per device chunk")
     for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
         if config.priv_count and xy_dtype == _lib.F32 and n >= config.priv_min_rows:
-            priv = [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_COUNT]
+            priv = [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_COUNT] or \
+                   [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_ANY and n < (1 << 32)]
             ncell = int(np.prod(ctx.shape))
             if priv and ncell <= 786_432:
                 scratch = getattr(ctx, "_priv_scratch", None)

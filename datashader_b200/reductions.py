@@ -240,7 +240,8 @@ class _FloatingReduction(Reduction):
 
 class sum(_FloatingReduction):   # noqa: A001
     """Sum of `column` (NaN where nothing was added) -> float64. reductions.py:1030-1098.
-    Built, like the reference's CUDA path (:1047-1051), from a zero-initialised sum and an any-mask."""
+    Built, like the reference's CUDA path (:1047-1051), from a zero-initialised sum and a "was anything added" mask;
+    the mask here is the non-null count of the column, which mean() shares and the privatised count kernel serves."""
     _line_agg = _lib.LINE_SUM
 
     def __init__(self, column=None, self_intersect=True):
@@ -251,13 +252,13 @@ class sum(_FloatingReduction):   # noqa: A001
         return super()._hashable_inputs() + (self.self_intersect,)
 
     def _accs(self, ctx):
-        return [Acc("sum", self.column), Acc("any", self.column)]
+        return [Acc("sum", self.column), Acc("count", self.column)]
 
     def _finalize(self, ctx, canv):
-        s, m = canv[Acc("sum", self.column).key], canv[Acc("any", self.column).key]
+        s, m = canv[Acc("sum", self.column).key], canv[Acc("count", self.column).key]
         out = torch.empty_like(s)
-        _lib.check(_lib.lib().dsb_finalize_sum(s.data_ptr(), m.data_ptr(), out.data_ptr(), s.numel(), ctx.stream_ptr),
-                   "dsb_finalize_sum")
+        _lib.check(_lib.lib().dsb_finalize_sum_counted(s.data_ptr(), m.data_ptr(), out.data_ptr(), s.numel(), ctx.stream_ptr),
+                   "dsb_finalize_sum_counted")
         return out
 
 

@@ -102,11 +102,12 @@ int dsb_init_canvas(int32_t op, void* agg, int64_t ncell, void* stream);
 int dsb_points(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
                int64_t row_offset, const dsb_plan* plan, void* stream);
 
-/* K2 - the same contract as dsb_points for a plan that contains a COUNT accumulator (`priv_op` = its index), with
+/* K2 - the same contract as dsb_points for a plan that contains a COUNT or ANY accumulator (`priv_op` = its index), with
  * that accumulator's whole canvas privatised per SM in shared memory as packed guard-bit counters.
  * Requires float32 coordinates and width*height*ncat <= ~800 000 cells; otherwise returns DSB_ERR_UNSUPPORTED and the
  * caller uses dsb_points.  scratch: [cells] u32 work canvas, flag: 1 u32 (both device, contents ignored on entry).
- * The result is always exact: a detected counter carry makes the library redo the count with global REDs. */
+ * The result is always exact: a detected counter carry makes the library redo the count with global REDs.
+ * An ANY accumulator is counted in `scratch` and committed as canvas |= (scratch > 0); it takes n < 2^32 rows per call. */
 int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
                     int64_t row_offset, const dsb_plan* plan, int32_t priv_op, uint32_t* scratch, uint32_t* flag,
                     void* stream);
@@ -133,6 +134,9 @@ int dsb_finish_minrow(int64_t* rows, int64_t ncell, void* stream);
 int dsb_finalize_mean(const double* sum, const void* count_u32, double* out, int64_t ncell, void* stream);
 /* sum  = where(mask, sum, nan); mask is a u8 any-canvas (reductions.py:1091-1096) */
 int dsb_finalize_sum(const double* sum, const uint8_t* mask, double* out, int64_t ncell, void* stream);
+/* the same with the non-null count of the column as the mask: sum = where(count > 0, sum, nan).  Lets sum() share
+ * its two accumulators with mean() and ride the privatised count kernel (dsb_points_priv). */
+int dsb_finalize_sum_counted(const double* sum, const void* count_u32, double* out, int64_t ncell, void* stream);
 
 /* ---- lines ---------------------------------------------------------------------------------- */
 typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5 } dsb_line_agg;

@@ -98,6 +98,16 @@ void ora_lines_axis1(const ora_view* v, const void* xs, const void* ys, int32_t 
                      int64_t nlines, int64_t nverts, const void* val, int32_t val_dtype,
                      int32_t agg_op, double line_width, void* agg);
 
+/* Every line layout (LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1XConstant/YConstant): see ds_oracle_lines.c. */
+void ora_lines(const ora_view* v, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines, int64_t nverts,
+               int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
+               int32_t val_dtype, int32_t agg_op, double line_width, void* agg);
+
+/* Area glyphs, the ten non-ragged layouts (glyphs/area.py:1076-2083). ys1 == NULL: fill to y = 0. */
+void ora_areas(const ora_view* v, const void* xs, const void* ys0, const void* ys1, int32_t xy_dtype, int64_t nlines,
+               int64_t nverts, int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
+               int32_t val_dtype, int32_t agg_op, void* agg);
+
 #ifdef __cplusplus
 }
 #endif

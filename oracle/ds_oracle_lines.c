@@ -298,24 +298,135 @@ static inline double ldxy(const void* p, int32_t dt, int64_t i) {
   return dt == ORA_F32 ? (double)((const float*)p)[i] : ((const double*)p)[i];
 }
 
-void ora_lines_axis1(const ora_view* v, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
-                     int64_t nverts, const void* val, int32_t val_dtype, int32_t agg_op, double line_width, void* agg) {
+/* All line layouts through one driver: vertex (line i, vertex j) = xs[i * x_line_stride + j], ys[i * y_line_stride + j]
+ * (stride 0 = a vertex vector shared by every line: LinesAxis1XConstant / YConstant, line.py:1340-1535).
+ * value_per_vertex = 1 for the axis=0 layouts (LineAxis0, LineAxis0Multi, line.py:1099-1242), where append() receives
+ * the row of the segment's first vertex; otherwise the line index (LinesAxis1, line.py:1244-1337). */
+void ora_lines(const ora_view* v, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines, int64_t nverts,
+               int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
+               int32_t val_dtype, int32_t agg_op, double line_width, void* agg) {
   line_ctx c;
   c.agg_op = agg_op; c.antialias = line_width > 0.0; c.has_field = val_dtype != ORA_NONE;
   c.width = v->width; c.agg = agg; c.field = 0.0;
   /* antialias.py:30-58: overwrite unless a SUM_1AGG combination (count / sum) is present */
   int overwrite = !(agg_op == ORA_COUNT || agg_op == ORA_SUM);
-  for (int64_t i = 0; i < nlines; i++) {          /* extend_cpu, line.py:1277-1289 */
-    if (c.has_field) c.field = ldxy(val, val_dtype, i);
-    for (int64_t j = 0; j + 1 < nverts; j++) {    /* perform_extend_line, line.py:1250-1275 */
-      const int64_t o = i * nverts + j;
-      double x0 = ldxy(xs, xy_dtype, o), y0 = ldxy(ys, xy_dtype, o);
-      double x1 = ldxy(xs, xy_dtype, o + 1), y1 = ldxy(ys, xy_dtype, o + 1);
-      int segment_start = (j == 0) || isnan(ldxy(xs, xy_dtype, o - 1)) || isnan(ldxy(ys, xy_dtype, o - 1));
-      int segment_end = (j == nverts - 2) || isnan(ldxy(xs, xy_dtype, o + 2)) || isnan(ldxy(ys, xy_dtype, o + 2));
+  for (int64_t i = 0; i < nlines; i++) {          /* extend_cpu, line.py:1277-1289 / 1127-1136 / 1200-1210 */
+    for (int64_t j = 0; j + 1 < nverts; j++) {    /* perform_extend_line, line.py:1250-1275 / 1104-1125 */
+      const int64_t ox = i * x_line_stride + j, oy = i * y_line_stride + j;
+      if (c.has_field) c.field = ldxy(val, val_dtype, value_per_vertex ? j : i);
+      double x0 = ldxy(xs, xy_dtype, ox), y0 = ldxy(ys, xy_dtype, oy);
+      double x1 = ldxy(xs, xy_dtype, ox + 1), y1 = ldxy(ys, xy_dtype, oy + 1);
+      int segment_start = (j == 0) || isnan(ldxy(xs, xy_dtype, ox - 1)) || isnan(ldxy(ys, xy_dtype, oy - 1));
+      int segment_end = (j == nverts - 2) || isnan(ldxy(xs, xy_dtype, ox + 2)) || isnan(ldxy(ys, xy_dtype, oy + 2));
       double xm = 0.0, ym = 0.0;
-      if (!segment_start) { xm = ldxy(xs, xy_dtype, o - 1); ym = ldxy(ys, xy_dtype, o - 1); }
+      if (!segment_start) { xm = ldxy(xs, xy_dtype, ox - 1); ym = ldxy(ys, xy_dtype, oy - 1); }
       draw_segment(v, &c, line_width, overwrite, segment_start, segment_end, x0, x1, y0, y1, xm, ym, xy_dtype == ORA_F32);
+    }
+  }
+}
+
+void ora_lines_axis1(const ora_view* v, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                     int64_t nverts, const void* val, int32_t val_dtype, int32_t agg_op, double line_width, void* agg) {
+  ora_lines(v, xs, ys, xy_dtype, nlines, nverts, nverts, nverts, 0, val, val_dtype, agg_op, line_width, agg);
+}
+
+/* ---- areas (glyphs/area.py) ------------------------------------------------------------------------------- */
+/* clamp_y_indices, area.py:1083-1100 */
+static inline int clamp_y_indices(int64_t ystarti, int64_t ystopi, int64_t ymaxi, int64_t* cs, int64_t* ce) {
+  int oob = (ystarti < 0 && ystopi <= 0) || (ystarti > ymaxi && ystopi >= ymaxi);
+  int64_t a = ystarti < ymaxi ? ystarti : ymaxi;
+  *cs = a > 0 ? a : 0;
+  int64_t b = ystopi < ymaxi + 1 ? ystopi : ymaxi + 1;
+  *ce = b > -1 ? b : -1;
+  return oob;
+}
+
+/* one pixel column of the scan fill, area.py:1205-1222 (repeated at :1236-1253 and :1300-1318) */
+static void fill_column(const line_ctx* c, int64_t x, int64_t y_start, int64_t y_stop, int stacked, int64_t ymaxi) {
+  if (y_start == y_stop && !stacked) { append_px(c, x, y_start); return; }
+  int64_t y = y_start;
+  int64_t iy = (y_start < y_stop) - (y_stop < y_start);
+  if (!stacked && -1 <= y_stop + iy && y_stop + iy <= ymaxi + 1) y_stop += iy;
+  while (y != y_stop) { append_px(c, x, y); y += iy; }
+}
+
+static inline int64_t snap(const ora_view* v, int is_y, double val) {   /* map_onto_pixel_snap, line.py:689-720 */
+  double s = is_y ? v->sy : v->sx, t = is_y ? v->ty : v->tx, mx = is_y ? v->ymax : v->xmax;
+  int lg = is_y ? v->y_log : v->x_log;
+  int64_t p = (int64_t)(axmap(lg, val) * s + t);
+  int64_t pmax = (int64_t)nearbyint(axmap(lg, mx) * s + t);
+  return p == pmax ? p - 1 : p;
+}
+
+/* draw_trapezoid_y, area.py:1102-1320 with _skip_or_clip_trapezoid_y, area.py:1323-1380.  f32: the coordinate
+ * differences of float32 columns are rounded to float32 by numba (the "to zero" curve is a float64 0.0). */
+static void draw_trapezoid_y(const ora_view* v, const line_ctx* c, double x0, double x1, double y0, double y1, double y2,
+                             double y3, int trapezoid_start, int stacked, int is_f32, int second_is_f32) {
+  int skip = isnan(x0) || isnan(x1) || isnan(y0) || isnan(y1) || isnan(y2) || isnan(y3);
+  if ((y0 > v->ymax && y1 > v->ymax && y2 > v->ymax && y3 > v->ymax) ||
+      (y0 < v->ymin && y1 < v->ymin && y2 < v->ymin && y3 < v->ymin)) return;
+  double t0 = 0, t1 = 1;
+  double dx = is_f32 ? (double)((float)x1 - (float)x0) : x1 - x0;
+  double dy0 = is_f32 ? (double)((float)y3 - (float)y0) : y3 - y0;
+  double dy1 = second_is_f32 ? (double)((float)y2 - (float)y1) : y2 - y1;
+  if (!clipt(-dx, x0 - v->xmin, &t0, &t1)) skip = 1;
+  if (!clipt(dx, v->xmax - x0, &t0, &t1)) skip = 1;
+  int clipped_start = 0, clipped_end = 0;
+  if (t1 < 1) { clipped_end = 1; x1 = x0 + t1 * dx; y2 = y1 + t1 * dy1; y3 = y0 + t1 * dy0; }
+  if (t0 > 0) { clipped_start = 1; x0 = x0 + t0 * dx; y0 = y0 + t0 * dy0; y1 = y1 + t0 * dy1; }
+  if (skip) return;
+  int64_t x0i = snap(v, 0, x0), y0i = snap(v, 1, y0), y1i = snap(v, 1, y1);
+  int64_t x1i = snap(v, 0, x1), y2i = snap(v, 1, y2), y3i = snap(v, 1, y3);
+  int64_t xmaxi = snap(v, 0, v->xmax), ymaxi = snap(v, 1, v->ymax);
+  int64_t dxi = x1i - x0i, ix = (dxi > 0) - (dxi < 0);
+  int64_t dy0i = y3i - y0i, iy0 = (dy0i > 0) - (dy0i < 0);
+  int64_t dy1i = y2i - y1i, iy1 = (dy1i > 0) - (dy1i < 0);
+  trapezoid_start = trapezoid_start || clipped_start;
+  int64_t ys, ye;
+  if (trapezoid_start) {
+    int y_oob = clamp_y_indices(y0i, y1i, ymaxi, &ys, &ye);
+    int x_oob = x0i < 0 || x0i > xmaxi;
+    if (!(y_oob || x_oob)) fill_column(c, x0i, ys, ye, stacked, ymaxi);
+  }
+  int clipped = clipped_start || clipped_end;
+  if (dxi == 0 && !clipped) {
+    int y_oob = clamp_y_indices(y3i, y2i, ymaxi, &ys, &ye);
+    int x_oob = x1i < 0 || x1i > xmaxi;
+    if (!(y_oob || x_oob)) fill_column(c, x1i, ys, ye, stacked, ymaxi);
+    return;
+  }
+  dxi = llabs(dxi) * 2; dy0i = llabs(dy0i) * 2; dy1i = llabs(dy1i) * 2;
+  int64_t error0 = 2 * dy0i - dxi, error1 = 2 * dy1i - dxi;
+  while (x0i != x1i) {
+    while (error0 >= 0 && (error0 || ix > 0)) { error0 -= 2 * dxi; y0i += iy0; }
+    error0 += 2 * dy0i;
+    while (error1 >= 0 && (error1 || ix > 0)) { error1 -= 2 * dxi; y1i += iy1; }
+    error1 += 2 * dy1i;
+    x0i += ix;
+    if (x0i < 0 || x0i > xmaxi) continue;
+    if (!clamp_y_indices(y0i, y1i, ymaxi, &ys, &ye)) fill_column(c, x0i, ys, ye, stacked, ymaxi);
+  }
+}
+
+/* The ten non-ragged area layouts (area.py:1383-2083): ys1 == NULL fills to y = 0 (AreaToZero*, stacked = False),
+ * otherwise between the curves (AreaToLine*, stacked = True).  Layout parameters as for ora_lines. */
+void ora_areas(const ora_view* v, const void* xs, const void* ys0, const void* ys1, int32_t xy_dtype, int64_t nlines,
+               int64_t nverts, int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
+               int32_t val_dtype, int32_t agg_op, void* agg) {
+  line_ctx c;
+  c.agg_op = agg_op; c.antialias = 0; c.has_field = val_dtype != ORA_NONE; c.width = v->width; c.agg = agg; c.field = 0.0;
+  const int to_line = ys1 != NULL;
+  for (int64_t i = 0; i < nlines; i++) {
+    for (int64_t j = 0; j + 1 < nverts; j++) {
+      const int64_t ox = i * x_line_stride + j, oy = i * y_line_stride + j;
+      if (c.has_field) c.field = ldxy(val, val_dtype, value_per_vertex ? j : i);
+      double x0 = ldxy(xs, xy_dtype, ox), x1 = ldxy(xs, xy_dtype, ox + 1);
+      double y0 = ldxy(ys0, xy_dtype, oy), y3 = ldxy(ys0, xy_dtype, oy + 1);
+      double y1 = to_line ? ldxy(ys1, xy_dtype, oy) : 0.0, y2 = to_line ? ldxy(ys1, xy_dtype, oy + 1) : 0.0;
+      int trapezoid_start = (j == 0) || isnan(ldxy(xs, xy_dtype, ox - 1)) || isnan(ldxy(ys0, xy_dtype, oy - 1)) ||
+                            (to_line && isnan(ldxy(ys1, xy_dtype, oy - 1)));
+      draw_trapezoid_y(v, &c, x0, x1, y0, y1, y2, y3, trapezoid_start, to_line, xy_dtype == ORA_F32,
+                       to_line && xy_dtype == ORA_F32);
     }
   }
 }

@@ -49,6 +49,31 @@ def main():
                 assert_agg_equal(got, want, f"{name} world={world}")
             except AssertionError as e:   # noqa: PERF203
                 bad.append(f"{name}: {str(e)[:200]}")
+    # LinesAxis1 sharded by line: each rank rasterises its lines, canvases all-reduced (sum / max / min per accumulator)
+    nl, nv = 2001, 9
+    lx = np.cumsum(rng.normal(0, 0.05, (nl, nv)), axis=1).astype(np.float32) + np.float32(0.5)
+    ly = np.cumsum(rng.normal(0, 0.05, (nl, nv)), axis=1).astype(np.float32) + np.float32(0.5)
+    lval = rng.normal(size=nl)
+    llo, lhi = shard_bounds(nl, rank, world)
+    lcols = {f"x{j}": lx[llo:lhi, j] for j in range(nv)}
+    lcols.update({f"y{j}": ly[llo:lhi, j] for j in range(nv)})
+    lcols["val"] = lval[llo:lhi]
+    lframe = ds.DeviceFrame({k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in lcols.items()}, row_offset=llo)
+    lframe.sharded = True
+    xc, yc = [f"x{j}" for j in range(nv)], [f"y{j}" for j in range(nv)]
+    lview = ora.make_view(W, H, (0.2, 0.9), (0.1, 0.8))
+    lcvs = ds.Canvas(W, H, x_range=(0.2, 0.9), y_range=(0.1, 0.8))
+    for name, agg, lw in [("any", ds.any(), 0), ("count", ds.count(), 0), ("sum", ds.sum("val"), 0), ("max", ds.max("val"), 0),
+                          ("min", ds.min("val"), 0), ("max", ds.max("val"), 2.0), ("count", ds.count(), 1.0)]:
+        got = lcvs.line(lframe, x=xc, y=yc, agg=agg, axis=1, line_width=lw).data
+        if rank == 0:
+            want = ora.lines_axis1(lx, ly, lview, name, None if name in ("any", "count") else lval, lw)
+            ok = got.dtype == want.dtype and np.array_equal(np.isnan(got.astype("f8")), np.isnan(want.astype("f8")))
+            ok = ok and np.allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True)
+            if lw == 0 and name != "sum":
+                ok = ok and np.array_equal(got, want, equal_nan=got.dtype.kind == "f")
+            if not ok:
+                bad.append(f"lines {name} lw={lw}")
     # auto-ranging across shards
     got = ds.Canvas(31, 17).points(frame, "x", "y").data
     if rank == 0:

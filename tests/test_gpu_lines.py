@@ -128,3 +128,37 @@ def test_line_layouts_golden():
         _cmp(cvs.line(df2, x=xcols, y=xc, axis=1, agg=agg).data, g[f"yconst_lw0_{name}"], f"yconst {name}", name == "mean")
     _cmp(cvs.line(df1, x=xc, y=ycols, axis=1, agg=ds.max("val"), line_width=1).data, g["xconst_lw1_max"], "xconst aa")
     _cmp(cvs.line(df2, x=xcols, y=xc, axis=1, agg=ds.max("val"), line_width=1).data, g["yconst_lw1_max"], "yconst aa")
+
+
+@pytest.mark.parametrize("dtype", ["f4", "f8"])
+def test_line_axis0_vs_oracle_random(dtype):
+    """LineAxis0 / LineAxis0Multi at a few thousand vertices with NaN breaks on a clipping canvas vs the C oracle
+    (ora_lines with value_per_vertex): Bresenham bit-exact, antialiased to 1e-6 relative (fp contraction only)."""
+    import pandas as pd
+    import datashader_b200 as ds
+    from oracle import oracle as ora
+    rng = np.random.default_rng(5)
+    n = 5000
+    x = np.cumsum(rng.normal(0, 0.01, n)).astype(dtype) + np.asarray(0.5, dtype)
+    y = np.cumsum(rng.normal(0, 0.01, n)).astype(dtype) + np.asarray(0.5, dtype)
+    x2 = rng.uniform(-0.2, 1.2, n).astype(dtype)
+    y2 = rng.uniform(-0.2, 1.2, n).astype(dtype)
+    for a in (x, y2):
+        a[rng.integers(0, n, 20)] = np.nan
+    val = rng.normal(size=n)
+    df = pd.DataFrame({"x": x, "y": y, "x2": x2, "y2": y2, "val": val})
+    W, H = 240, 180
+    cvs = ds.Canvas(plot_width=W, plot_height=H, x_range=(0.2, 0.8), y_range=(0.3, 0.9))
+    view = ora.make_view(W, H, (0.2, 0.8), (0.3, 0.9))
+    for name, agg in {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "min": ds.min("val")}.items():
+        vals = None if name in ("any", "count") else val
+        _cmp(cvs.line(df, "x", "y", agg=agg).data, ora.lines(x[None], y[None], view, name, vals, 0, per_vertex=True), f"ax0 {name}", name == "sum")
+        _cmp(cvs.line(df, x=["x", "x2"], y=["y", "y2"], agg=agg, axis=0).data,
+             ora.lines(np.stack([x, x2]), np.stack([y, y2]), view, name, vals, 0, per_vertex=True), f"ax0multi {name}", name == "sum")
+    for name, agg in {"any": ds.any(), "max": ds.max("val"), "count": ds.count(), "sum": ds.sum("val")}.items():
+        vals = None if name in ("any", "count") else val
+        got = cvs.line(df, "x", "y", agg=agg, line_width=2.5).data
+        want = ora.lines(x[None], y[None], view, name, vals, 2.5, per_vertex=True)
+        assert got.dtype == want.dtype
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True, err_msg=name)

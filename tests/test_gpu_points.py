@@ -215,7 +215,7 @@ def test_priv_count_kernel_matches_oracle(ds, force_priv, W, H):
     view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
     cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
     frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
-    for spec in (("count",), ("count", "v32"), ("mean", "v32")):
+    for spec in (("count",), ("count", "v32"), ("mean", "v32"), ("sum", "v32"), ("any",), ("any", "v32")):
         assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view), f"priv {spec} {W}x{H}")
     # unaligned column start -> scalar-load variant
     frame2 = ds.DeviceFrame({k: torch.from_numpy(v).cuda()[1:] for k, v in cols.items()})
@@ -235,6 +235,8 @@ def test_priv_count_hot_pixel_falls_back_exactly(ds, force_priv):
     got = ds.Canvas(900, 525, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(frame, "x", "y").data
     assert int(got.sum()) == n
     assert got[131, 450] == n - len(range(0, n, 7)) and got[131, 675] == len(range(0, n, 7))
+    hit = ds.Canvas(900, 525, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(frame, "x", "y", ds.any()).data
+    assert hit.dtype == np.bool_ and int(hit.sum()) == 2 and hit[131, 450] and hit[131, 675]
 
 
 def test_priv_by_count_small_canvas(ds, force_priv):

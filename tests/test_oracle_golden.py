@@ -167,3 +167,66 @@ def test_no_fma_contraction_in_mapping():
     got = ora.points(cols, "x", "y", ("count",), view)
     want = np.bincount(np.minimum((xs * s + t).astype(np.int64), W - 1), minlength=W).astype("u4")[None, :]
     np.testing.assert_array_equal(got, want)
+
+
+def _eq(got, want, key, tol=False):
+    assert got.dtype == want.dtype and got.shape == want.shape, key
+    if tol:
+        np.testing.assert_allclose(got, want, rtol=1e-12, equal_nan=True, err_msg=key)
+    else:
+        assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), key
+
+
+def test_line_layouts_golden():
+    """LineAxis0 / LineAxis0Multi / LinesAxis1XConstant / YConstant restated in the oracle vs the real reference."""
+    g = load("line_layouts.npz")
+    view = ora.make_view(50, 40, (0, 1), (0, 1))
+    x, y, x2, y2, val = (g[f"ax0_{k}"] for k in ("x", "y", "x2", "y2", "val"))
+    for name in ("any", "count", "sum", "max"):
+        vals = None if name in ("any", "count") else val
+        _eq(ora.lines(x[None, :], y[None, :], view, name, vals, 0, per_vertex=True), g[f"ax0_lw0_{name}"], f"ax0 {name}", name == "sum")
+        _eq(ora.lines(np.stack([x, x2]), np.stack([y, y2]), view, name, vals, 0, per_vertex=True), g[f"ax0multi_lw0_{name}"],
+            f"ax0multi {name}", name == "sum")
+    for name in ("any", "max"):
+        vals = None if name == "any" else val
+        _eq(ora.lines(x[None, :], y[None, :], view, name, vals, 1.0, per_vertex=True), g[f"ax0_lw1_{name}"], f"ax0 aa {name}")
+        _eq(ora.lines(np.stack([x, x2]), np.stack([y, y2]), view, name, vals, 1.0, per_vertex=True), g[f"ax0multi_lw1_{name}"],
+            f"ax0multi aa {name}")
+    xc, ys, lval = g["xc_x"], g["xc_ys"], g["xc_val"]
+    for name in ("any", "count", "max"):
+        vals = None if name in ("any", "count") else lval
+        _eq(ora.lines(xc, ys, view, name, vals, 0), g[f"xconst_lw0_{name}"], f"xconst {name}")
+        _eq(ora.lines(ys, xc, view, name, vals, 0), g[f"yconst_lw0_{name}"], f"yconst {name}")
+    _eq(ora.lines(xc, ys, view, "max", lval, 1.0), g["xconst_lw1_max"], "xconst aa")
+    _eq(ora.lines(ys, xc, view, "max", lval, 1.0), g["yconst_lw1_max"], "yconst aa")
+
+
+def test_areas_golden():
+    """The area layouts restated in the oracle (ds_oracle_lines.c: draw_trapezoid_y) vs the real reference."""
+    g = load("areas.npz")
+    x, y, ys, x2, y2, y2s, val = (g[f"a0_{k}"] for k in ("x", "y", "ys", "x2", "y2", "y2s", "val"))
+    fixed = ora.make_view(45, 35, (0, 1), (-0.5, 1.0))
+    xr = ora.compute_bounds(x)
+    b = ora.compute_bounds(y)
+    auto = ora.make_view(33, 27, xr, (min(b[0], 0), max(b[1], 0)))          # area.py:71-79: bounds include zero
+    np.testing.assert_array_equal(np.array([min(b[0], 0), max(b[1], 0)]), g["a0_zero_auto_yrange"])
+    for name in ("any", "count", "sum", "max"):
+        vals = None if name in ("any", "count") else val
+        tol = name == "sum"
+        _eq(ora.areas(x[None, :], y[None, :], fixed, None, name, vals, per_vertex=True), g[f"a0_zero_fixed_{name}"], f"a0 zero {name}", tol)
+        _eq(ora.areas(x[None, :], y[None, :], auto, None, name, vals, per_vertex=True), g[f"a0_zero_auto_{name}"], f"a0 zero auto {name}", tol)
+        _eq(ora.areas(x[None, :], y[None, :], fixed, ys[None, :], name, vals, per_vertex=True), g[f"a0_line_fixed_{name}"], f"a0 line {name}", tol)
+        _eq(ora.areas(np.stack([x, x2]), np.stack([y, y2]), fixed, None, name, vals, per_vertex=True), g[f"a0m_zero_fixed_{name}"],
+            f"a0m zero {name}", tol)
+        _eq(ora.areas(np.stack([x, x2]), np.stack([y, y2]), fixed, np.stack([ys, y2s]), name, vals, per_vertex=True),
+            g[f"a0m_line_fixed_{name}"], f"a0m line {name}", tol)
+    xm, ym, ysm, lval = g["a1_x"], g["a1_y"], g["a1_ys"], g["a1_val"]
+    xconst, yconst, sconst = g["a1_xconst"], g["a1_yconst"], g["a1_sconst"]
+    for name in ("any", "count", "max"):
+        vals = None if name in ("any", "count") else lval
+        _eq(ora.areas(xm, ym, fixed, None, name, vals), g[f"a1_zero_{name}"], f"a1 zero {name}")
+        _eq(ora.areas(xm, ym, fixed, ysm, name, vals), g[f"a1_line_{name}"], f"a1 line {name}")
+        _eq(ora.areas(xconst, ym, fixed, None, name, vals), g[f"a1xc_zero_{name}"], f"a1xc zero {name}")
+        _eq(ora.areas(xconst, ym, fixed, ysm, name, vals), g[f"a1xc_line_{name}"], f"a1xc line {name}")
+        _eq(ora.areas(xm, yconst, fixed, None, name, vals), g[f"a1yc_zero_{name}"], f"a1yc zero {name}")
+        _eq(ora.areas(xm, yconst, fixed, sconst, name, vals), g[f"a1yc_line_{name}"], f"a1yc line {name}")
