@@ -108,7 +108,7 @@ __device__ __forceinline__ void apply_base_f32(const dsb_base& b, long long cell
 // integer its floor IS the reference's truncated f64 result, otherwise the exact f64 mapping is evaluated.  The
 // bounds test is exact: xlo/xhi are the float32 values that bracket the f64 bounds from inside.
 struct FastMap {
-  float sx, tx, sy, ty, xlo, xhi, ylo, yhi, ex, ey;
+  float sx, tx, sy, ty, xlo, xhi, ylo, yhi, ex, ey, omex, omey;   // omex = 1 - ex
   int enabled;
 };
 
@@ -220,6 +220,102 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a, const
   if (bad) atomicOr(a.flag, 1u);
 }
 
+// ---- K2 "tight": the two headline shapes (count(), mean(f32 column)) when the float32 fast mapping applies, there is
+// no category axis and the whole canvas fits the packed shared-memory fields.  Same algorithm as k_points_priv with the
+// per-point instruction stream cut down: 32-bit cell arithmetic, shared-window address formed once, the exact f64
+// mapping kept out of line (taken by ~0.1 % of the points), no plan interpretation.
+__device__ __noinline__ int map_exact_linear(const dsb_view& v, float xr, float yr) {
+  return (int)map_to_cell<float>(v, xr, yr);      // the reference mapping, bounds test included; -1 = not on the canvas
+}
+
+template <int SLOT>
+__device__ __forceinline__ void priv_hit_tight(uint32_t sh_addr, uint32_t b, unsigned int* scratch, unsigned int* flag) {
+  constexpr uint32_t PER = 32 / SLOT;
+  constexpr uint32_t CNT_MASK = (1u << (SLOT - 1)) - 1u, GUARD = 1u << (SLOT - 1), FIELD = (1u << SLOT) - 1u;
+  const uint32_t w = b / PER, sft = (b - w * PER) * SLOT;
+  const uint32_t addr = sh_addr + 4u * w;
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(1u << sft) : "memory");
+  const uint32_t f = old >> sft;
+  if ((f & CNT_MASK) == CNT_MASK) {                // counter full: either this hit wraps it (spill) or the field is all ones
+    if ((f & GUARD) == 0) {
+      asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(0u - (GUARD << sft)) : "memory");
+      asm volatile("red.global.add.u32 [%0], %1;" :: "l"(scratch + b), "r"(GUARD) : "memory");
+    } else {
+      atomicOr(flag, 1u);                          // carry into the neighbouring field: the pass is redone exactly
+    }
+  }
+}
+
+template <int SLOT, bool MEAN>
+__global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_constant__ PrivArgs a, const __grid_constant__ FastMap fm) {
+  extern __shared__ uint32_t sh[];
+  constexpr uint32_t PER = 32 / SLOT;
+  constexpr uint32_t FIELD = (1u << SLOT) - 1u;
+  const PointsArgs& p = a.p;
+  const int ncell = (int)a.npriv;
+  const int nwords = (ncell + (int)PER - 1) / (int)PER;
+  for (int j = threadIdx.x; j < nwords; j += blockDim.x) sh[j] = 0;
+  __syncthreads();
+  uint32_t sh_addr;                                // opaque to the compiler so that it is formed once, not per hit
+  asm volatile("mov.u32 %0, %1;" : "=r"(sh_addr) : "r"((uint32_t)__cvta_generic_to_shared(sh)));
+  const float* __restrict__ x = (const float*)p.x;
+  const float* __restrict__ y = (const float*)p.y;
+  double* __restrict__ sum_canvas = MEAN ? (double*)p.plan.ops[1 - a.priv_op].agg : nullptr;
+  const uint32_t W = (uint32_t)p.v.width, H = (uint32_t)p.v.height;
+
+  // xf is within fm.ex of the real-number value of the reference mapping for every point whose xf lands in [-1, W + 1]
+  // (make_fast_map).  If its fractional part is in [ex, 1 - ex], floor(xf) is therefore the reference's pixel column
+  // when 0 <= floor(xf) < W - and the point is strictly inside (xmin, xmax) - and the point is outside [xmin, xmax]
+  // otherwise.  Everything else (near a pixel edge, NaN, inf) takes the exact f64 path.
+  auto one = [&](float xv, float yv, float vv) {
+    const float xf = fmaf(xv, fm.sx, fm.tx), yf = fmaf(yv, fm.sy, fm.ty);
+    const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+    const float dx = xf - (float)xi, dy = yf - (float)yi;
+    int cell;
+    if (dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey) {
+      if ((uint32_t)xi >= W || (uint32_t)yi >= H) return;
+      cell = yi * (int)W + xi;
+    } else {
+      cell = map_exact_linear(p.v, xv, yv);
+      if (cell < 0) return;
+    }
+    if (MEAN) {
+      if (vv != vv) return;
+      atomicAdd(sum_canvas + cell, (double)vv);
+    }
+    priv_hit_tight<SLOT>(sh_addr, (uint32_t)cell, a.scratch, a.flag);
+  };
+
+  const float4* __restrict__ x4 = (const float4*)p.x;
+  const float4* __restrict__ y4 = (const float4*)p.y;
+  const float4* __restrict__ v4 = (const float4*)a.vcol;
+  const long long n4 = p.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += 2 * stride) {
+    const bool two = i4 + stride < n4;
+    float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
+    float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
+    float4 xb = two ? __ldcs(x4 + i4 + stride) : nan4;
+    float4 yb = two ? __ldcs(y4 + i4 + stride) : nan4;
+    float4 vb = (two && MEAN) ? __ldcs(v4 + i4 + stride) : nan4;
+    one(xa.x, ya.x, va.x); one(xa.y, ya.y, va.y); one(xa.z, ya.z, va.z); one(xa.w, ya.w, va.w);
+    one(xb.x, yb.x, vb.x); one(xb.y, yb.y, vb.y); one(xb.z, yb.z, vb.z); one(xb.w, yb.w, vb.w);   // NaN coordinates: no-ops
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {           // tail rows
+    const long long i = (n4 << 2) + threadIdx.x;
+    one(x[i], y[i], MEAN ? a.vcol[i] : NAN);
+  }
+
+  __syncthreads();
+  for (int j = threadIdx.x; j < ncell; j += blockDim.x) {
+    const uint32_t w = (uint32_t)j / PER, sft = ((uint32_t)j - w * PER) * SLOT;
+    const uint32_t c = (sh[w] >> sft) & FIELD;
+    if (c) atomicAdd(a.scratch + j, c);
+  }
+}
+
 // canvas += scratch when the privatised pass was exact (flag == 0)
 __global__ void k_priv_commit(unsigned int* __restrict__ canvas, const unsigned int* __restrict__ scratch,
                               const unsigned int* __restrict__ flag, long long n) {
@@ -273,6 +369,7 @@ static long long op_cell_bytes(int op) {
 // ld.global.cs so it does not displace the canvas).  DSB_L2_BAND_MB overrides (0 disables).
 static long long g_band_budget = -1;        // bytes; -1 = not initialised
 static long long g_band_min_rows = 1LL << 22;
+static int g_priv_tight = 1;                 // use k_points_priv_tight for the count() / mean(f32) shapes
 static long long l2_band_budget_bytes() {
   if (g_band_budget < 0) {
     const char* e = getenv("DSB_L2_BAND_MB");
@@ -287,6 +384,7 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!key) { dsb_set_error("dsb_configure: null key"); return DSB_ERR_ARG; }
   if (!strcmp(key, "l2_band_bytes")) { g_band_budget = value; return DSB_OK; }
   if (!strcmp(key, "band_min_rows")) { g_band_min_rows = value; return DSB_OK; }
+  if (!strcmp(key, "priv_tight")) { g_priv_tight = value != 0; return DSB_OK; }
   dsb_set_error("dsb_configure: unknown key %s", key);
   return DSB_ERR_ARG;
 }
@@ -412,9 +510,17 @@ static void launch_priv_one(const PrivArgs& a, const FastMap& fm, size_t smem, c
   k_points_priv<SLOT, MODE, VEC><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
 }
 
+template <int SLOT, bool MEAN>
+static void launch_priv_tight(const PrivArgs& a, const FastMap& fm, size_t smem, cudaStream_t s) {
+  cudaFuncSetAttribute(k_points_priv_tight<SLOT, MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  k_points_priv_tight<SLOT, MEAN><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
+}
+
 template <int SLOT>
-static void launch_priv(const PrivArgs& a, const FastMap& fm, int mode, bool vec, size_t smem, cudaStream_t s) {
-  if (!vec) launch_priv_one<SLOT, 2, false>(a, fm, smem, s);      // unaligned columns: scalar loads, generic plan
+static void launch_priv(const PrivArgs& a, const FastMap& fm, int mode, bool vec, bool tight, size_t smem, cudaStream_t s) {
+  if (tight && mode == 0) launch_priv_tight<SLOT, false>(a, fm, smem, s);
+  else if (tight && mode == 1) launch_priv_tight<SLOT, true>(a, fm, smem, s);
+  else if (!vec) launch_priv_one<SLOT, 2, false>(a, fm, smem, s);      // unaligned columns: scalar loads, generic plan
   else if (mode == 0) launch_priv_one<SLOT, 0, true>(a, fm, smem, s);
   else if (mode == 1) launch_priv_one<SLOT, 1, true>(a, fm, smem, s);
   else launch_priv_one<SLOT, 2, true>(a, fm, smem, s);
@@ -428,9 +534,12 @@ static FastMap make_fast_map(const dsb_view* v) {
   f.sx = (float)v->sx; f.tx = (float)v->tx; f.sy = (float)v->sy; f.ty = (float)v->ty;
   f.xlo = f32_at_least(v->xmin); f.xhi = f32_at_most(v->xmax); f.ylo = f32_at_least(v->ymin); f.yhi = f32_at_most(v->ymax);
   const double ax = fmax(fabs(v->xmin), fabs(v->xmax)), ay = fmax(fabs(v->ymin), fabs(v->ymax));
-  const double ex = ldexp(1.0, -23) * (v->width + 1.0 + ax * fabs(v->sx) + fabs(v->tx));
-  const double ey = ldexp(1.0, -23) * (v->height + 1.0 + ay * fabs(v->sy) + fabs(v->ty));
-  f.ex = (float)ex; f.ey = (float)ey;
+  // |x * sx| is at most max(ax * |sx|, |tx| + W + 2) for any point, in or out of bounds, whose fast image lands in
+  // [-1, W + 1]; the bound covers the float32 roundings of sx, tx and of the fused multiply-add.
+  const double mx = fmax(ax * fabs(v->sx), fabs(v->tx) + v->width + 2.0), my = fmax(ay * fabs(v->sy), fabs(v->ty) + v->height + 2.0);
+  const double ex = ldexp(1.0, -23) * (v->width + 1.0 + mx + fabs(v->tx));
+  const double ey = ldexp(1.0, -23) * (v->height + 1.0 + my + fabs(v->ty));
+  f.ex = (float)ex; f.ey = (float)ey; f.omex = 1.0f - f.ex; f.omey = 1.0f - f.ey;
   f.enabled = !v->x_log && !v->y_log && ex < 0.125 && ey < 0.125 && isfinite(ex) && isfinite(ey) && v->sx > 0 && v->sy > 0;
   return f;
 }
@@ -490,12 +599,14 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
         c0.val == (const void*)a.vcol && c0.val_dtype == DSB_F32 && c0.chk_dtype == DSB_NONE) mode = 1;
   }
   const FastMap fm = make_fast_map(view);
+  const bool vvec = mode != 1 || ((uintptr_t)a.vcol & 15) == 0;
+  const bool tight = g_priv_tight && vec && vvec && mode <= 1 && fm.enabled && a.npriv == ncell && ncell < (1LL << 31);
   switch (slot) {
-    case 8: launch_priv<8>(a, fm, mode, vec, smem, s); break;
-    case 5: launch_priv<5>(a, fm, mode, vec, smem, s); break;
-    case 4: launch_priv<4>(a, fm, mode, vec, smem, s); break;
-    case 3: launch_priv<3>(a, fm, mode, vec, smem, s); break;
-    default: launch_priv<2>(a, fm, mode, vec, smem, s); break;
+    case 8: launch_priv<8>(a, fm, mode, vec, tight, smem, s); break;
+    case 5: launch_priv<5>(a, fm, mode, vec, tight, smem, s); break;
+    case 4: launch_priv<4>(a, fm, mode, vec, tight, smem, s); break;
+    case 3: launch_priv<3>(a, fm, mode, vec, tight, smem, s); break;
+    default: launch_priv<2>(a, fm, mode, vec, tight, smem, s); break;
   }
   DSB_CUDA_CHECK_LAUNCH("dsb_points_priv");
   long long g = (ncell + 255) / 256, cap = (long long)dsb_num_sms() * 8;
