@@ -320,8 +320,8 @@ def run_ours(args):
                        "combine": "NCCL all-reduce of the f64 sum and u32 count canvases" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic_gb(args.workload, n),
-                         "kernel": ("k_points_priv<3,1,vec> (K2: count privatised in shared memory, f64 sum via global RED)"
-                                    if args.workload == "mean" else "k_points_priv<3,0,vec> (K2)"),
+                         "kernel": ("k_points_priv_tight<4,mean> (K2: count privatised in shared memory, f64 sum via global RED)"
+                                    if args.workload == "mean" else "k_points_priv_tight<3,count> (K2)"),
                          "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_point": bpp, "traffic_unit": "GB per launch (ncu dram read+write)"},
             "cpu_baseline": cb,

@@ -228,26 +228,35 @@ __device__ __noinline__ int map_exact_linear(const dsb_view& v, float xr, float 
   return (int)map_to_cell<float>(v, xr, yr);      // the reference mapping, bounds test included; -1 = not on the canvas
 }
 
-template <int SLOT>
-__device__ __forceinline__ void priv_hit_tight(uint32_t sh_addr, uint32_t b, unsigned int* scratch, unsigned int* flag) {
+// One hit.  `ok` (0 / 1) gates it without a branch: the shared-memory add is unconditional, of ok << shift at a clamped
+// address.  The every-2^(SLOT-1)-th-hit spill is the only branch; with 32 lanes some lane of nearly every warp takes
+// it, so its operands are formed outside and it holds just the two memory instructions.
+template <int SLOT, bool ALLP>
+__device__ __forceinline__ void priv_hit_tight(uint32_t sh_addr, uint32_t cell, bool ok, uint32_t npriv, unsigned int* scratch,
+                                               uint32_t& bad) {
   constexpr uint32_t PER = 32 / SLOT;
   constexpr uint32_t CNT_MASK = (1u << (SLOT - 1)) - 1u, GUARD = 1u << (SLOT - 1), FIELD = (1u << SLOT) - 1u;
-  const uint32_t w = b / PER, sft = (b - w * PER) * SLOT;
+  if (ALLP) {
+    cell = min(cell, npriv - 1u);                  // only matters when !ok
+  } else if (cell >= npriv) {                      // the few cells that did not fit shared memory: plain REDs
+    if (ok) atomicAdd(scratch + cell, 1u);
+    return;
+  }
+  const uint32_t w = cell / PER, sft = (cell - w * PER) * SLOT;
   const uint32_t addr = sh_addr + 4u * w;
   uint32_t old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(1u << sft) : "memory");
-  const uint32_t f = old >> sft;
-  if ((f & CNT_MASK) == CNT_MASK) {                // counter full: either this hit wraps it (spill) or the field is all ones
-    if ((f & GUARD) == 0) {
-      asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(0u - (GUARD << sft)) : "memory");
-      asm volatile("red.global.add.u32 [%0], %1;" :: "l"(scratch + b), "r"(GUARD) : "memory");
-    } else {
-      atomicOr(flag, 1u);                          // carry into the neighbouring field: the pass is redone exactly
-    }
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"((uint32_t)ok << sft) : "memory");
+  const uint32_t f = (old >> sft) & FIELD;
+  const uint32_t unguard = 0u - (GUARD << sft);
+  unsigned int* const spill_to = scratch + cell;
+  if (ok && f == CNT_MASK) {                       // this hit wrapped the counter into its guard bit
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(unguard) : "memory");
+    asm volatile("red.global.add.u32 [%0], %1;" :: "l"(spill_to), "r"(GUARD) : "memory");
   }
+  bad |= (uint32_t)(ok && f == FIELD);             // the add carried into the neighbouring field: redo exactly
 }
 
-template <int SLOT, bool MEAN>
+template <int SLOT, bool MEAN, bool ALLP>
 __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_constant__ PrivArgs a, const __grid_constant__ FastMap fm) {
   extern __shared__ uint32_t sh[];
   constexpr uint32_t PER = 32 / SLOT;
@@ -263,28 +272,32 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
   const float* __restrict__ y = (const float*)p.y;
   double* __restrict__ sum_canvas = MEAN ? (double*)p.plan.ops[1 - a.priv_op].agg : nullptr;
   const uint32_t W = (uint32_t)p.v.width, H = (uint32_t)p.v.height;
+  uint32_t bad = 0;
+
+  auto hit = [&](uint32_t cell, bool ok, float vv) {
+    if (MEAN) {
+      ok = ok && vv == vv;
+      if (ok) atomicAdd(sum_canvas + cell, (double)vv);
+    }
+    priv_hit_tight<SLOT, ALLP>(sh_addr, cell, ok, (uint32_t)ncell, a.scratch, bad);
+  };
 
   // xf is within fm.ex of the real-number value of the reference mapping for every point whose xf lands in [-1, W + 1]
   // (make_fast_map).  If its fractional part is in [ex, 1 - ex], floor(xf) is therefore the reference's pixel column
   // when 0 <= floor(xf) < W - and the point is strictly inside (xmin, xmax) - and the point is outside [xmin, xmax]
-  // otherwise.  Everything else (near a pixel edge, NaN, inf) takes the exact f64 path.
-  auto one = [&](float xv, float yv, float vv) {
+  // otherwise.  Everything else (near a pixel edge, NaN, inf) is deferred to the exact f64 mapping: returns 1.
+  auto one = [&](float xv, float yv, float vv) -> uint32_t {
     const float xf = fmaf(xv, fm.sx, fm.tx), yf = fmaf(yv, fm.sy, fm.ty);
     const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
     const float dx = xf - (float)xi, dy = yf - (float)yi;
-    int cell;
-    if (dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey) {
-      if ((uint32_t)xi >= W || (uint32_t)yi >= H) return;
-      cell = yi * (int)W + xi;
-    } else {
-      cell = map_exact_linear(p.v, xv, yv);
-      if (cell < 0) return;
-    }
-    if (MEAN) {
-      if (vv != vv) return;
-      atomicAdd(sum_canvas + cell, (double)vv);
-    }
-    priv_hit_tight<SLOT>(sh_addr, (uint32_t)cell, a.scratch, a.flag);
+    const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
+    const bool inside = (uint32_t)xi < W && (uint32_t)yi < H;
+    hit((uint32_t)(yi * (int)W + xi), sure && inside, vv);
+    return (uint32_t)!sure;
+  };
+  auto exact = [&](float xv, float yv, float vv) {
+    const int cell = map_exact_linear(p.v, xv, yv);
+    hit((uint32_t)cell, cell >= 0, vv);
   };
 
   const float4* __restrict__ x4 = (const float4*)p.x;
@@ -300,12 +313,22 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
     float4 xb = two ? __ldcs(x4 + i4 + stride) : nan4;
     float4 yb = two ? __ldcs(y4 + i4 + stride) : nan4;
     float4 vb = (two && MEAN) ? __ldcs(v4 + i4 + stride) : nan4;
-    one(xa.x, ya.x, va.x); one(xa.y, ya.y, va.y); one(xa.z, ya.z, va.z); one(xa.w, ya.w, va.w);
-    one(xb.x, yb.x, vb.x); one(xb.y, yb.y, vb.y); one(xb.z, yb.z, vb.z); one(xb.w, yb.w, vb.w);   // NaN coordinates: no-ops
+    uint32_t slow = one(xa.x, ya.x, va.x) | one(xa.y, ya.y, va.y) << 1 | one(xa.z, ya.z, va.z) << 2 | one(xa.w, ya.w, va.w) << 3 |
+                    one(xb.x, yb.x, vb.x) << 4 | one(xb.y, yb.y, vb.y) << 5 | one(xb.z, yb.z, vb.z) << 6 | one(xb.w, yb.w, vb.w) << 7;
+    if (slow) {                                    // ~0.07 % of the points (and the NaN padding of a missing second vector)
+      if (slow & 1) exact(xa.x, ya.x, va.x);
+      if (slow & 2) exact(xa.y, ya.y, va.y);
+      if (slow & 4) exact(xa.z, ya.z, va.z);
+      if (slow & 8) exact(xa.w, ya.w, va.w);
+      if (slow & 16) exact(xb.x, yb.x, vb.x);
+      if (slow & 32) exact(xb.y, yb.y, vb.y);
+      if (slow & 64) exact(xb.z, yb.z, vb.z);
+      if (slow & 128) exact(xb.w, yb.w, vb.w);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {           // tail rows
     const long long i = (n4 << 2) + threadIdx.x;
-    one(x[i], y[i], MEAN ? a.vcol[i] : NAN);
+    exact(x[i], y[i], MEAN ? a.vcol[i] : 0.0f);
   }
 
   __syncthreads();
@@ -314,6 +337,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
     const uint32_t c = (sh[w] >> sft) & FIELD;
     if (c) atomicAdd(a.scratch + j, c);
   }
+  if (bad) atomicOr(a.flag, 1u);
 }
 
 // canvas += scratch when the privatised pass was exact (flag == 0)
@@ -369,6 +393,8 @@ static long long op_cell_bytes(int op) {
 // ld.global.cs so it does not displace the canvas).  DSB_L2_BAND_MB overrides (0 disables).
 static long long g_band_budget = -1;        // bytes; -1 = not initialised
 static long long g_band_min_rows = 1LL << 22;
+static long long g_priv_smem_kb = 192;        // shared memory the privatised canvas may take (see dsb_points_priv)
+static long long g_priv_smem_kb_mean = 226;   // the same for the mean() shape
 static int g_priv_tight = 1;                 // use k_points_priv_tight for the count() / mean(f32) shapes
 static long long l2_band_budget_bytes() {
   if (g_band_budget < 0) {
@@ -385,6 +411,8 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "l2_band_bytes")) { g_band_budget = value; return DSB_OK; }
   if (!strcmp(key, "band_min_rows")) { g_band_min_rows = value; return DSB_OK; }
   if (!strcmp(key, "priv_tight")) { g_priv_tight = value != 0; return DSB_OK; }
+  if (!strcmp(key, "priv_smem_kb")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb = value; return DSB_OK; }
+  if (!strcmp(key, "priv_smem_kb_mean")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb_mean must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb_mean = value; return DSB_OK; }
   dsb_set_error("dsb_configure: unknown key %s", key);
   return DSB_ERR_ARG;
 }
@@ -511,15 +539,21 @@ static void launch_priv_one(const PrivArgs& a, const FastMap& fm, size_t smem, c
 }
 
 template <int SLOT, bool MEAN>
-static void launch_priv_tight(const PrivArgs& a, const FastMap& fm, size_t smem, cudaStream_t s) {
-  cudaFuncSetAttribute(k_points_priv_tight<SLOT, MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  k_points_priv_tight<SLOT, MEAN><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
+static void launch_priv_tight(const PrivArgs& a, const FastMap& fm, bool allp, size_t smem, cudaStream_t s) {
+  if (allp) {
+    cudaFuncSetAttribute(k_points_priv_tight<SLOT, MEAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    k_points_priv_tight<SLOT, MEAN, true><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
+  } else {
+    cudaFuncSetAttribute(k_points_priv_tight<SLOT, MEAN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    k_points_priv_tight<SLOT, MEAN, false><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
+  }
 }
 
 template <int SLOT>
 static void launch_priv(const PrivArgs& a, const FastMap& fm, int mode, bool vec, bool tight, size_t smem, cudaStream_t s) {
-  if (tight && mode == 0) launch_priv_tight<SLOT, false>(a, fm, smem, s);
-  else if (tight && mode == 1) launch_priv_tight<SLOT, true>(a, fm, smem, s);
+  const bool allp = a.npriv == a.p.band_hi;          // band_hi = number of cells
+  if (tight && mode == 0) launch_priv_tight<SLOT, false>(a, fm, allp, smem, s);
+  else if (tight && mode == 1) launch_priv_tight<SLOT, true>(a, fm, allp, smem, s);
   else if (!vec) launch_priv_one<SLOT, 2, false>(a, fm, smem, s);      // unaligned columns: scalar loads, generic plan
   else if (mode == 0) launch_priv_one<SLOT, 0, true>(a, fm, smem, s);
   else if (mode == 1) launch_priv_one<SLOT, 1, true>(a, fm, smem, s);
@@ -560,21 +594,7 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   if (priv_any && n == (1LL << 32)) { dsb_set_error("dsb_points_priv: an ANY op takes fewer than 2^32 rows per call"); return DSB_ERR_ARG; }
   if (!x || !y) { dsb_set_error("dsb_points_priv: null coordinate column"); return DSB_ERR_ARG; }
   const long long ncell = (long long)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1);
-  // 192 KB of the 228 KB L1/shared array: the rest must stay L1 for the streaming loads (measured: using all
-  // 227 KB drops count from 256 to 214 Gpts/s)
-  const size_t max_words = (size_t)(192 * 1024) / 4;
-  // widest slot (fewest spills) that keeps at least 97 % of the cells in shared memory; the remainder, if any,
-  // is scattered with plain REDs
-  int slot = 0;
-  const int slots[5] = {8, 5, 4, 3, 2};
-  for (int k = 0; k < 5; k++) {
-    const long long per = 32 / slots[k];
-    if ((long long)max_words * per * 100 >= ncell * 97) { slot = slots[k]; break; }
-  }
-  if (xy_dtype != DSB_F32 || slot == 0) {
-    dsb_set_error("dsb_points_priv: needs float32 coordinates and a canvas of at most %lld cells", (long long)max_words * 16);
-    return DSB_ERR_UNSUPPORTED;
-  }
+  if (xy_dtype != DSB_F32) { dsb_set_error("dsb_points_priv: needs float32 coordinates"); return DSB_ERR_UNSUPPORTED; }
   cudaStream_t s = (cudaStream_t)stream;
   PrivArgs a;
   a.p.v = *view; a.p.x = x; a.p.y = y; a.p.n = n; a.p.row_offset = row_offset; a.p.band_lo = 0; a.p.band_hi = ncell; a.p.plan = *plan;
@@ -583,12 +603,6 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   for (int k = 0; k < plan->nops && !a.vcol; k++)
     if (plan->ops[k].val_dtype == DSB_F32 && plan->ops[k].val && ((uintptr_t)plan->ops[k].val & 15) == 0)
       a.vcol = (const float*)plan->ops[k].val;
-  cudaMemsetAsync(scratch, 0, (size_t)ncell * 4, s);
-  cudaMemsetAsync(flag, 0, 4, s);
-  const bool vec = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-  const long long per = 32 / slot;
-  a.npriv = ncell < (long long)max_words * per ? ncell : (long long)max_words * per;
-  const size_t smem = (size_t)((a.npriv + per - 1) / per) * 4;
   // compile-time specialisations of the two headline shapes
   int mode = 2;
   const dsb_base& c0 = plan->ops[priv_op];
@@ -598,9 +612,33 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
     if (o.op == DSB_OP_SUM && o.val == (const void*)a.vcol && o.val_dtype == DSB_F32 && o.chk_dtype == DSB_NONE &&
         c0.val == (const void*)a.vcol && c0.val_dtype == DSB_F32 && c0.chk_dtype == DSB_NONE) mode = 1;
   }
+  // Shared-memory budget.  count() streams 8 B / point and needs the rest of the 228 KB L1/shared array as L1 for its
+  // loads in flight: 192 KB (measured: 226 KB drops count from 484 to 438 Gpts/s).  mean() is bound by the global REDs
+  // instead (one f64 sum RED per point + one spill RED per 2^(SLOT-1) points), so a wider slot is worth more than
+  // the L1: 226 KB (900x525: SLOT 3 -> 4, mean 134 -> 144 Gpts/s).
+  const long long kb = (mode == 1 && g_priv_smem_kb_mean > g_priv_smem_kb) ? g_priv_smem_kb_mean : g_priv_smem_kb;
+  const size_t max_words = (size_t)(kb * 1024) / 4;
+  // widest slot (fewest spills) that keeps at least 97 % of the cells in shared memory; the remainder, if any,
+  // is scattered with plain REDs
+  int slot = 0;
+  const int slots[5] = {8, 5, 4, 3, 2};
+  for (int k = 0; k < 5; k++) {
+    const long long per = 32 / slots[k];
+    if ((long long)max_words * per * 100 >= ncell * 97) { slot = slots[k]; break; }
+  }
+  if (slot == 0) {
+    dsb_set_error("dsb_points_priv: needs a canvas of at most %lld cells", (long long)max_words * 16);
+    return DSB_ERR_UNSUPPORTED;
+  }
+  cudaMemsetAsync(scratch, 0, (size_t)ncell * 4, s);
+  cudaMemsetAsync(flag, 0, 4, s);
+  const bool vec = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  const long long per = 32 / slot;
+  a.npriv = ncell < (long long)max_words * per ? ncell : (long long)max_words * per;
+  const size_t smem = (size_t)((a.npriv + per - 1) / per) * 4;
   const FastMap fm = make_fast_map(view);
   const bool vvec = mode != 1 || ((uintptr_t)a.vcol & 15) == 0;
-  const bool tight = g_priv_tight && vec && vvec && mode <= 1 && fm.enabled && a.npriv == ncell && ncell < (1LL << 31);
+  const bool tight = g_priv_tight && vec && vvec && mode <= 1 && fm.enabled && ncell < (1LL << 31);
   switch (slot) {
     case 8: launch_priv<8>(a, fm, mode, vec, tight, smem, s); break;
     case 5: launch_priv<5>(a, fm, mode, vec, tight, smem, s); break;

@@ -34,8 +34,14 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000_000)
     ap.add_argument("--width", type=int, default=900)
     ap.add_argument("--height", type=int, default=525)
+    ap.add_argument("--only", default="", help="comma-separated subset of the reductions")
+    ap.add_argument("--configure", action="append", default=[], help="key=value passed to dsb_configure")
     a = ap.parse_args()
     n = a.n
+    from datashader_b200 import _lib
+    for kv in a.configure:
+        k, v = kv.split("=")
+        _lib.check(_lib.lib().dsb_configure(k.encode(), int(v)), "dsb_configure")
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     x = torch.rand(n, generator=g, device="cuda"); y = torch.rand(n, generator=g, device="cuda")
     v = torch.randn(n, generator=g, device="cuda")
@@ -49,6 +55,8 @@ def main():
             "by_count": ds.by("cat", ds.count()), "by_mean": ds.by("cat", ds.mean("value")),
             "summary(count,mean,max)": ds.summary(c=ds.count(), m=ds.mean("value"), mx=ds.max("value"))}
     out = {}
+    if a.only:
+        aggs = {k: v for k, v in aggs.items() if k in a.only.split(",")}
     for name, agg in aggs.items():
         ms = timed(lambda: cvs.points(frame, "x", "y", agg))
         out[name] = {"ms": round(ms, 3), "gpts": round(n / ms / 1e6, 1)}
