@@ -25,6 +25,7 @@ OP_COUNT, OP_ANY, OP_SUM, OP_MAX32, OP_MIN32, OP_MAX64, OP_MIN64 = 1, 2, 3, 4, 5
 OP_MAXROW, OP_MINROW, OP_ARGMAX32, OP_ARGMIN32, OP_MATCHROW64 = 8, 9, 10, 11, 12
 
 LINE_ANY, LINE_COUNT, LINE_SUM, LINE_MAX, LINE_MIN = 1, 2, 3, 4, 5
+AA2_SUM, AA2_COUNT, AA2_MIN, AA2_FIRST, AA2_LAST = 1, 2, 3, 4, 5
 
 
 class View(C.Structure):
@@ -77,6 +78,7 @@ _SIGNATURES = {
     "dsb_finalize_mean": ([_p, _p, _p, _i64, _p], C.c_int),
     "dsb_finalize_sum": ([_p, _p, _p, _i64, _p], C.c_int),
     "dsb_finalize_sum_counted": ([_p, _p, _p, _i64, _p], C.c_int),
+    "dsb_lines_aa2": ([_p, _p, _p, _i32, _i64, _i64, _p, _i64, _p, _i32, _i32, _i32, C.c_double, _p, _p, _p, _i64, _p], C.c_int),
     "dsb_lines_axis1_plan": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _i64, C.POINTER(Plan), _p],
                              C.c_int),
     "dsb_areas_plan": ([C.POINTER(View), _p, _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _i64, C.POINTER(Plan), _p],

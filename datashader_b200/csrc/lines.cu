@@ -47,7 +47,13 @@ struct LineCtx {
   const dsb_plan* plan;     // non-null: run the accumulator plan for every touched pixel
   long long line, row;      // line index within the frame / global row id
   int cat;                  // category of this line (by()), -1 = skip
+  unsigned int* touched_n;  // 2-stage antialiasing: the CTA's count of / list of cells its current line has touched
+  uint32_t* touched;
 };
+
+// internal agg codes of the 2-stage path (stage 1 = per-line max of field * aa_factor / of aa_factor)
+#define DSB_LINE_AA2_VALUE 101
+#define DSB_LINE_AA2_COVER 102
 
 // ---- appends, line_width == 0 (reductions.py _append / _append_no_field) ------------------------
 __device__ __forceinline__ void append_px(const LineCtx& c, long long x, long long y) {
@@ -109,6 +115,20 @@ __device__ __forceinline__ void append_aa(const LineCtx& c, long long x, long lo
       double v = fmul64(c.field, aa);
       if (v != v) return;
       atomicMax((long long*)c.canvas + cell, key64_from_f64(v));
+      return;
+    }
+    case DSB_LINE_AA2_VALUE:   // stage 1 of min / first / last / sum(self_intersect=False): reductions.py:1186-1191,
+    case DSB_LINE_AA2_COVER: { // 1408-1413, 1446-1451, 1079-1085; of count(self_intersect=False): :570-578, 594-600
+      double v;
+      if (c.agg == DSB_LINE_AA2_COVER) {
+        if (c.has_field && c.field_nan) return;
+        v = (double)(float)aa;             // the reference's stage-1 canvas is float32; rounding is monotone, so max commutes
+      } else {
+        v = fmul64(c.field, aa);
+        if (v != v) return;
+      }
+      const long long old = atomicMax((long long*)c.canvas + cell, key64_from_f64(v));
+      if (old == LLONG_MIN) c.touched[atomicAdd(c.touched_n, 1u)] = (uint32_t)cell;   // first touch by this line
       return;
     }
   }
@@ -385,6 +405,98 @@ __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
   }
 }
 
+
+// ---- 2-stage antialiased lines -------------------------------------------------------------------------------------
+// compiler.py:198-268 + line.py:1291-1319: for min / first / last and count / sum with self_intersect=False the
+// reference renders every line on its own into a cleared canvas with a max() combination (stage 1) and folds that
+// canvas into the result with nansum / nanmin / nanfirst / nanlast (stage 2), one line after the other.
+// Here: one CTA per line.  Stage 1 goes into the CTA's private full-size key64 canvas (`temp`, all EMPTY between
+// lines) with atomicMax; the first touch of a cell appends it to the CTA's touched list.  Stage 2 walks that list: it
+// resets the cell and applies the line's value to the shared result with the commutative form of the combine
+// (sum: atomic add; min: atomicMin on key64; first / last: atomicMin / atomicMax of the global line index in phase 1,
+// and in phase 2 - after every line has voted - the winning line alone stores its value).
+struct Aa2Args {
+  int combo, phase;
+  void* out;
+  void* aux;              // sum / count: u8 mask; first / last: i64 line-index canvas
+  long long* temp;        // [nctas][ncell]
+  uint32_t* touched;      // [nctas][ncell]
+};
+
+template <typename XY>
+__global__ void __launch_bounds__(256) k_lines_aa2(const LineArgs a, const Aa2Args b) {
+  __shared__ unsigned int s_touched;
+  const XY* __restrict__ xs = (const XY*)a.xs;
+  const XY* __restrict__ ys = (const XY*)a.ys;
+  const long long ncell = (long long)a.v.width * a.v.height;
+  long long* temp = b.temp + (long long)blockIdx.x * ncell;
+  uint32_t* touched = b.touched + (long long)blockIdx.x * ncell;
+  const long long nseg = a.nverts - 1;
+  for (long long i = blockIdx.x; i < a.nlines; i += gridDim.x) {
+    if (threadIdx.x == 0) s_touched = 0;
+    __syncthreads();
+    for (long long j = threadIdx.x; j < nseg; j += blockDim.x) {
+      const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+      const double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
+      bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
+      if (j > 0) {
+        const double xm = (double)xs[ox - 1], ym = (double)ys[oy - 1];
+        segment_start = (xm != xm) || (ym != ym);
+      }
+      bool segment_end = (j == a.nverts - 2);
+      if (!segment_end) {
+        const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
+        segment_end = (xn != xn) || (yn != yn);
+      }
+      const long long vi = a.value_per_vertex ? j : i;
+      LineCtx c;
+      c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = temp; c.mask = nullptr;
+      c.field = c.has_field ? load_f64(a.val, a.val_dtype, vi) : 0.0;
+      c.field_nan = c.has_field && (c.field != c.field);
+      c.plan = nullptr; c.line = vi; c.row = a.row_offset + vi; c.cat = 0;
+      c.touched_n = &s_touched; c.touched = touched;
+      // xm = ym = 0 in 2-stage mode (line.py:1266-1268); unused because overwrite is True
+      draw_segment<XY>(a, c, segment_start, segment_end, x0, x1, y0, y1, 0.0, 0.0);
+    }
+    __syncthreads();
+    const unsigned int n = s_touched;
+    const long long line = a.row_offset + i;          // global line index: what "first" / "last" order by
+    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
+      const uint32_t cell = touched[k];
+      const long long key = __ldcg(temp + cell);    // written by L2 atomics: do not trust a stale L1 line
+      temp[cell] = LLONG_MIN;
+      switch (b.combo) {
+        case DSB_AA2_SUM:
+          atomicAdd((double*)b.out + cell, f64_from_key64(key));
+          ((uint8_t*)b.aux)[cell] = 1;
+          break;
+        case DSB_AA2_COUNT:
+          atomicAdd((float*)b.out + cell, (float)f64_from_key64(key));
+          ((uint8_t*)b.aux)[cell] = 1;
+          break;
+        case DSB_AA2_MIN:
+          atomicMin((long long*)b.out + cell, key);
+          break;
+        case DSB_AA2_FIRST:
+          if (b.phase == 1) atomicMin((long long*)b.aux + cell, line);
+          else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
+          break;
+        case DSB_AA2_LAST:
+          if (b.phase == 1) atomicMax((long long*)b.aux + cell, line);
+          else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
+          break;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_fill_i64(long long* p, long long v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
 static long long py_round(double v) { return (long long)nearbyint(v); }   // Python round(): half to even
 
 static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char* what) {
@@ -461,4 +573,48 @@ extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void*
   int rc = apply_layout(a, layout, "dsb_lines_axis1");
   if (rc != DSB_OK) return rc;
   return launch_lines(a, xy_dtype, stream, "dsb_lines_axis1");
+}
+
+extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                             int64_t nverts, const dsb_line_layout* layout, int64_t row_offset, const void* val,
+                             int32_t val_dtype, int32_t combo, int32_t phase, double line_width, void* out, void* aux,
+                             void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0 || !out) { dsb_set_error("dsb_lines_aa2: bad view/canvas"); return DSB_ERR_ARG; }
+  if (combo < DSB_AA2_SUM || combo > DSB_AA2_LAST) { dsb_set_error("dsb_lines_aa2: unknown combination %d", combo); return DSB_ERR_ARG; }
+  if (!(line_width > 0.0)) { dsb_set_error("dsb_lines_aa2: line_width must be > 0"); return DSB_ERR_ARG; }
+  if (combo != DSB_AA2_COUNT && (val_dtype == DSB_NONE || !val)) { dsb_set_error("dsb_lines_aa2: this reduction needs a value column"); return DSB_ERR_ARG; }
+  if (combo != DSB_AA2_MIN && !aux) { dsb_set_error("dsb_lines_aa2: aux canvas required"); return DSB_ERR_ARG; }
+  if ((combo == DSB_AA2_FIRST || combo == DSB_AA2_LAST) && phase != 1 && phase != 2) { dsb_set_error("dsb_lines_aa2: phase must be 1 or 2"); return DSB_ERR_ARG; }
+  if (nlines <= 0 || nverts < 2) return DSB_OK;
+  if (!xs || !ys) { dsb_set_error("dsb_lines_aa2: null vertex arrays"); return DSB_ERR_ARG; }
+  const long long ncell = (long long)view->width * view->height;
+  if (ncell >= (1LL << 32)) { dsb_set_error("dsb_lines_aa2: canvas too large"); return DSB_ERR_UNSUPPORTED; }
+  const long long per_cta = ncell * 12;
+  long long nctas = scratch ? scratch_bytes / per_cta : 0;
+  if (nctas < 1) { dsb_set_error("dsb_lines_aa2: scratch must hold at least %lld bytes (12 per pixel per CTA)", per_cta); return DSB_ERR_ARG; }
+  const long long cap = (long long)dsb_num_sms() * 4;
+  if (nctas > cap) nctas = cap;
+  if (nctas > nlines) nctas = nlines;
+  LineArgs a;
+  a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
+  a.agg = combo == DSB_AA2_COUNT ? DSB_LINE_AA2_COVER : DSB_LINE_AA2_VALUE;
+  a.line_width = line_width; a.canvas = nullptr; a.mask = nullptr; a.overwrite = 1; a.use_plan = 0; a.row_offset = row_offset;
+  int rc = apply_layout(a, layout, "dsb_lines_aa2");
+  if (rc != DSB_OK) return rc;
+  const double mx = view->x_log ? log10(view->xmax) : view->xmax, my = view->y_log ? log10(view->ymax) : view->ymax;
+  a.xxmax = py_round(mx * view->sx + view->tx);
+  a.yymax = py_round(my * view->sy + view->ty);
+  a.nx = py_round((view->xmax - view->xmin) * view->sx);
+  a.ny = py_round((view->ymax - view->ymin) * view->sy);
+  Aa2Args b;
+  b.combo = combo; b.phase = phase; b.out = out; b.aux = aux;
+  b.temp = (long long*)scratch;                               // [nctas][ncell] i64, then [nctas][ncell] u32
+  b.touched = (uint32_t*)((char*)scratch + nctas * ncell * 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  k_fill_i64<<<dsb_num_sms() * 8, 256, 0, s>>>(b.temp, LLONG_MIN, nctas * ncell);
+  if (xy_dtype == DSB_F32) k_lines_aa2<float><<<(int)nctas, 256, 0, s>>>(a, b);
+  else if (xy_dtype == DSB_F64) k_lines_aa2<double><<<(int)nctas, 256, 0, s>>>(a, b);
+  else { dsb_set_error("dsb_lines_aa2: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+  DSB_CUDA_CHECK_LAUNCH("dsb_lines_aa2");
+  return DSB_OK;
 }

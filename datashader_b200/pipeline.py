@@ -300,12 +300,11 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
     line_width = float(glyph._line_width)
     if line_width == 0:
         return _lines_plan(frame, needed, schema, canvas, glyph, agg, dist)
+    combo = _aa2_combo(agg)
+    if combo is not None:
+        return _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist)
     if isinstance(agg, (rd.summary, rd.by)) or agg._line_agg is None:
         raise NotImplementedError(f"{type(agg).__name__} is not implemented for antialiased datashader_b200 lines yet")
-    if isinstance(agg, rd.min):
-        raise NotImplementedError("min() needs the 2-stage antialias combine (antialias.py:30-58): not implemented yet")
-    if isinstance(agg, (rd.count, rd.sum)) and not agg.self_intersect:
-        raise NotImplementedError("self_intersect=False needs the 2-stage antialias combine: not implemented yet")
 
     device = frame.device
     with torch.cuda.device(device):
@@ -368,6 +367,88 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return DataArray(data, coords={glyph.y_label: y_axis, glyph.x_label: x_axis}, dims=[glyph.y_label, glyph.x_label],
                      attrs=dict(x_range=x_range, y_range=y_range))
+
+
+def _aa2_combo(agg):
+    """The reductions whose antialiased form needs the 2-stage combine (each reduction's _antialias_stage_2,
+    reductions.py:545-549, 1041-1045, 1172-1173, 1395-1396, 1433-1434; antialias.py:30-58)."""
+    if isinstance(agg, rd.min):
+        return _lib.AA2_MIN
+    if isinstance(agg, rd.first):
+        return _lib.AA2_FIRST
+    if isinstance(agg, rd.last):
+        return _lib.AA2_LAST
+    if isinstance(agg, rd.sum) and not agg.self_intersect:
+        return _lib.AA2_SUM
+    if isinstance(agg, rd.count) and not agg.self_intersect:
+        return _lib.AA2_COUNT
+    return None
+
+
+def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist):
+    """Antialiased lines, 2-stage reductions: dsb_lines_aa2 (one CTA per line, per-line max then the stage-2 fold)."""
+    device = frame.device
+    with torch.cuda.device(device):
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+        x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout) = _line_setup(frame, canvas, glyph, dist)
+        H, W = canvas.plot_height, canvas.plot_width
+        lib = _lib.lib()
+        val, val_dtype = None, _lib.NONE
+        if agg.column is not None:
+            val = frame[agg.column]
+            val_dtype = _lib.dsb_dtype(frame.np_dtype(agg.column))
+        # scratch: 12 bytes per pixel per CTA; as many CTAs as a budget of 1/8 of the free memory (<= 16 GiB) allows
+        free, _total = torch.cuda.mem_get_info(device)
+        per_cta = 12 * H * W
+        nctas = int(max(1, min(4 * torch.cuda.get_device_properties(device).multi_processor_count, max(nlines, 1),
+                               min(free // 8, 16 << 30) // per_cta)))
+        scratch = torch.empty(nctas * per_cta, dtype=torch.uint8, device=device)
+        row_offset = frame.row_offset if not glyph_per_vertex(glyph) else 0
+
+        def launch(phase, out, aux):
+            _lib.check(lib.dsb_lines_aa2(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, nlines, nverts, C.byref(layout),
+                                         row_offset, val.data_ptr() if val is not None else None, val_dtype, combo, phase,
+                                         line_width, out.data_ptr(), aux.data_ptr() if aux is not None else None,
+                                         scratch.data_ptr(), scratch.numel(), stream_ptr), "dsb_lines_aa2")
+
+        if combo in (_lib.AA2_SUM, _lib.AA2_COUNT):
+            acc = torch.zeros((H, W), dtype=torch.float64 if combo == _lib.AA2_SUM else torch.float32, device=device)
+            mask = torch.zeros((H, W), dtype=torch.uint8, device=device)
+            launch(1, acc, mask)
+            if dist is not None:
+                dist._all_reduce(acc, "sum")
+                dist._all_reduce(mask, "max")
+            out = torch.where(mask.bool(), acc, torch.full_like(acc, float("nan")))
+        elif combo == _lib.AA2_MIN:
+            keys = torch.empty((H, W), dtype=torch.int64, device=device)
+            _lib.check(lib.dsb_init_canvas(_lib.OP_MIN64, keys.data_ptr(), H * W, stream_ptr))
+            launch(1, keys, None)
+            if dist is not None:
+                dist._all_reduce(keys, "min")
+            out = torch.empty((H, W), dtype=torch.float64, device=device)
+            _lib.check(lib.dsb_decode_minmax(keys.data_ptr(), _lib.OP_MIN64, _lib.F64, out.data_ptr(), H * W, stream_ptr))
+        else:
+            first = combo == _lib.AA2_FIRST
+            rows = torch.empty((H, W), dtype=torch.int64, device=device)
+            _lib.check(lib.dsb_init_canvas(_lib.OP_MINROW if first else _lib.OP_MAXROW, rows.data_ptr(), H * W, stream_ptr))
+            out = torch.full((H, W), float("nan"), dtype=torch.float64, device=device)
+            launch(1, out, rows)
+            if dist is not None:
+                dist._all_reduce(rows, "min" if first else "max")
+            launch(2, out, rows)
+            if dist is not None:      # exactly one rank owns each winning line: the others contribute 0 bits
+                out = dist.sum_bits_f64(torch.nan_to_num(out, nan=0.0), rows)
+        data = _to_host(out)
+    x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+    y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+    return DataArray(data, coords={glyph.y_label: y_axis, glyph.x_label: x_axis}, dims=[glyph.y_label, glyph.x_label],
+                     attrs=dict(x_range=x_range, y_range=y_range))
+
+
+def glyph_per_vertex(glyph):
+    """axis=0 layouts hand append() the vertex row, not the line index (line.py:1104-1125, 1157-1180)."""
+    from .glyphs import LineAxis0, LineAxis0Multi
+    return isinstance(glyph, (LineAxis0, LineAxis0Multi))
 
 
 def _lines_plan(frame, needed, schema, canvas, glyph, agg, dist):

@@ -171,6 +171,22 @@ int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, i
                          int64_t nverts, const dsb_line_layout* layout, int64_t row_offset, const dsb_plan* plan,
                          void* stream);
 
+/* Antialiased lines whose reduction needs the reference's 2-stage combine (compiler.py:198-268, line.py:1291-1319,
+ * antialias.py:30-58): every line is rendered on its own with a max() combination (stage 1) and folded into the result
+ * with nansum / nanmin / nanfirst / nanlast (stage 2).  One CTA per line; `scratch` holds each CTA's private stage-1
+ * canvas + touched list (12 bytes per pixel per CTA; the library uses as many CTAs as fit, at most 4 per SM).
+ *   DSB_AA2_SUM   sum(self_intersect=False):   out f64 zero-initialised, aux u8 mask (zeroed)
+ *   DSB_AA2_COUNT count(self_intersect=False): out f32 zero-initialised, aux u8 mask (zeroed); val optional (NaN check)
+ *   DSB_AA2_MIN   min:                         out i64 key64 canvas (dsb_init_canvas(DSB_OP_MIN64)), aux unused
+ *   DSB_AA2_FIRST / DSB_AA2_LAST:              aux i64 line-index canvas (DSB_OP_MINROW / DSB_OP_MAXROW init); call
+ *                 with phase = 1 (votes the global line index row_offset + i into aux; all-reduce aux across GPUs
+ *                 here), then phase = 2 (the winning line stores its value into out, f64, NaN-initialised). */
+typedef enum { DSB_AA2_SUM = 1, DSB_AA2_COUNT = 2, DSB_AA2_MIN = 3, DSB_AA2_FIRST = 4, DSB_AA2_LAST = 5 } dsb_aa2_combo;
+int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                  int64_t nverts, const dsb_line_layout* layout, int64_t row_offset, const void* val,
+                  int32_t val_dtype, int32_t combo, int32_t phase, double line_width, void* out, void* aux,
+                  void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ---- areas ----------------------------------------------------------------------------------------- */
 /* Filled areas (glyphs/area.py): one trapezoid per vertex pair, x-driven double-Bresenham scan fill
  * (_build_draw_trapezoid_y :1076-1320, _skip_or_clip_trapezoid_y :1323-1380) with the accumulator plan applied to

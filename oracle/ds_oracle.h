@@ -108,6 +108,12 @@ void ora_areas(const ora_view* v, const void* xs, const void* ys0, const void* y
                int64_t nverts, int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
                int32_t val_dtype, int32_t agg_op, void* agg);
 
+/* Antialiased lines whose reduction needs the 2-stage combine (compiler.py:198-268): combo = ORA_SUM / ORA_COUNT
+ * (self_intersect=False; f64 / f32 canvas), ORA_MIN, ORA_FIRST, ORA_LAST (f64).  agg must be NaN-initialised. */
+void ora_lines_aa2(const ora_view* v, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines, int64_t nverts,
+                   int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
+                   int32_t val_dtype, int32_t combo, double line_width, void* agg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+enum { ORA_AA2_VALUE = 101, ORA_AA2_COVER = 102 };   /* internal: stage-1 appends of the 2-stage antialias path */
+
 typedef struct {
   int32_t agg_op;     /* ORA_ANY / ORA_COUNT / ORA_SUM / ORA_MAX / ORA_MIN */
   int antialias;
@@ -70,10 +72,19 @@ static inline void append_aa(const line_ctx* c, int64_t x, int64_t y, double aa,
       if (isnan(*a)) *a = v; else *a += v;
       return;
     }
-    case ORA_MAX: { /* reductions.py:1229-1236 */
+    case ORA_MAX:   /* reductions.py:1229-1236 */
+    case ORA_AA2_VALUE: { /* stage 1 of min / first / last / sum(self_intersect=False): the same max of field * aa_factor
+                             (reductions.py:1186-1191, 1408-1413, 1446-1451, 1079-1085) */
       double v = f * aa;
       double* a = (double*)c->agg + cell;
       if (!isnan(v) && (isnan(*a) || v > *a)) *a = v;
+      return;
+    }
+    case ORA_AA2_COVER: { /* stage 1 of count(self_intersect=False): max of aa_factor in a float32 canvas
+                             (reductions.py:570-578, 594-600) */
+      if (c->has_field && isnan(f)) return;
+      float* a = (float*)c->agg + cell;
+      if (isnan(*a) || aa > *a) *a = (float)aa;
       return;
     }
   }
@@ -429,4 +440,52 @@ void ora_areas(const ora_view* v, const void* xs, const void* ys0, const void* y
                        to_line && xy_dtype == ORA_F32);
     }
   }
+}
+
+/* ---- 2-stage antialiased lines (compiler.py:198-268; line.py:1291-1319 and its per-layout twins) ------------------
+ * For min / first / last and count / sum with self_intersect=False every line is first rendered on its own into a
+ * cleared canvas with a max() combination (stage 1: overlapping segments of ONE line do not accumulate), then that
+ * canvas is folded into the running result with the reduction's stage-2 combine: nansum_in_place, nanmin_in_place,
+ * nanfirst_in_place, nanlast_in_place (utils.py:615-668, 885-897).  A single line returns after stage 1.
+ * combo: ORA_SUM (f64 canvas), ORA_COUNT (f32 canvas), ORA_MIN, ORA_FIRST, ORA_LAST (f64).  agg: NaN-initialised. */
+void ora_lines_aa2(const ora_view* v, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines, int64_t nverts,
+                   int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
+                   int32_t val_dtype, int32_t combo, double line_width, void* agg) {
+  const int64_t ncell = (int64_t)v->width * v->height;
+  const int is_f32_canvas = combo == ORA_COUNT;
+  void* stage1 = malloc((size_t)ncell * (is_f32_canvas ? 4 : 8));
+  line_ctx c;
+  c.agg_op = is_f32_canvas ? ORA_AA2_COVER : ORA_AA2_VALUE;
+  c.antialias = 1; c.has_field = val_dtype != ORA_NONE; c.width = v->width; c.agg = stage1; c.field = 0.0;
+  for (int64_t i = 0; i < nlines; i++) {
+    if (is_f32_canvas) for (int64_t k = 0; k < ncell; k++) ((float*)stage1)[k] = NAN;      /* aa_stage_2_clear */
+    else for (int64_t k = 0; k < ncell; k++) ((double*)stage1)[k] = NAN;
+    for (int64_t j = 0; j + 1 < nverts; j++) {
+      const int64_t ox = i * x_line_stride + j, oy = i * y_line_stride + j;
+      if (c.has_field) c.field = ldxy(val, val_dtype, value_per_vertex ? j : i);
+      double x0 = ldxy(xs, xy_dtype, ox), y0 = ldxy(ys, xy_dtype, oy);
+      double x1 = ldxy(xs, xy_dtype, ox + 1), y1 = ldxy(ys, xy_dtype, oy + 1);
+      int segment_start = (j == 0) || isnan(ldxy(xs, xy_dtype, ox - 1)) || isnan(ldxy(ys, xy_dtype, oy - 1));
+      int segment_end = (j == nverts - 2) || isnan(ldxy(xs, xy_dtype, ox + 2)) || isnan(ldxy(ys, xy_dtype, oy + 2));
+      /* xm = ym = 0 in 2-stage mode (line.py:1266-1268); unused because overwrite is True (antialias.py:47-56) */
+      draw_segment(v, &c, line_width, 1, segment_start, segment_end, x0, x1, y0, y1, 0.0, 0.0, xy_dtype == ORA_F32);
+    }
+    for (int64_t k = 0; k < ncell; k++) {          /* aa_stage_2_accumulate; the first pass is a copy */
+      if (is_f32_canvas) {
+        float* r = (float*)agg + k; const float o = ((float*)stage1)[k];
+        if (i == 0) { *r = o; continue; }
+        if (isnan(*r)) { if (!isnan(o)) *r = o; } else if (!isnan(o)) *r += o;             /* nansum_in_place */
+        continue;
+      }
+      double* r = (double*)agg + k; const double o = ((double*)stage1)[k];
+      if (i == 0) { *r = o; continue; }
+      switch (combo) {
+        case ORA_SUM: if (isnan(*r)) { if (!isnan(o)) *r = o; } else if (!isnan(o)) *r += o; break;
+        case ORA_MIN: if (isnan(*r)) { if (!isnan(o)) *r = o; } else if (!isnan(o) && o < *r) *r = o; break;
+        case ORA_FIRST: if (isnan(*r) && !isnan(o)) *r = o; break;
+        case ORA_LAST: if (!isnan(o)) *r = o; break;
+      }
+    }
+  }
+  free(stage1);
 }

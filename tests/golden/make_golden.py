@@ -341,6 +341,37 @@ def line_layout_cases():
     return out
 
 
+def lines_aa2_cases():
+    """Antialiased lines whose reduction needs the 2-stage combine (antialias.py:30-58; compiler.py:198-268;
+    line.py:1291-1319): min, first, last and count/sum with self_intersect=False - LinesAxis1 (40 lines, the
+    lines.npz inputs), LineAxis0Multi (2 lines) and LineAxis0 (1 line: stage 1 only)."""
+    out = {}
+    aggs = {"min": ds.min("val"), "first": ds.first("val"), "last": ds.last("val"),
+            "sum_nsi": ds.sum("val", self_intersect=False), "count_nsi": ds.count(self_intersect=False),
+            "count_val_nsi": ds.count("val", self_intersect=False)}
+    for tag, dtype in (("f32", np.float32), ("f64", np.float64)):
+        xs, ys, val = line_frame(2024, 40, 24, dtype)       # identical to lines.npz in_{tag}_*
+        nverts = xs.shape[1]
+        d = {f"x{j}": xs[:, j] for j in range(nverts)}
+        d.update({f"y{j}": ys[:, j] for j in range(nverts)})
+        d["val"] = val
+        df = pd.DataFrame(d)
+        xcols, ycols = [f"x{j}" for j in range(nverts)], [f"y{j}" for j in range(nverts)]
+        cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+        for lw in ((1, 2.5) if tag == "f32" else (1,)):
+            for aname, agg in aggs.items():
+                out[f"aa2_{tag}_lw{lw}_{aname}"] = np.asarray(cvs.line(df, x=xcols, y=ycols, axis=1, agg=agg, line_width=lw).data)
+    # axis=0 layouts: the line_layouts.npz inputs (ax0_x, ax0_y, ax0_x2, ax0_y2, ax0_val)
+    g = np.load(os.path.join(HERE, "line_layouts.npz"))
+    df0 = pd.DataFrame({k: g[f"ax0_{k}"] for k in ("x", "y", "x2", "y2", "val")})
+    cvs = ds.Canvas(plot_width=50, plot_height=40, x_range=(0, 1), y_range=(0, 1))
+    for aname, agg in aggs.items():
+        out[f"aa2_ax0_lw2_{aname}"] = np.asarray(cvs.line(df0, "x", "y", agg=agg, line_width=2).data)
+        out[f"aa2_ax0multi_lw2_{aname}"] = np.asarray(
+            cvs.line(df0, x=["x", "x2"], y=["y", "y2"], axis=0, agg=agg, line_width=2).data)
+    return out
+
+
 def area_cases():
     """Canvas.area for the ten non-ragged layouts (core.py:480-709, glyphs/area.py)."""
     out = {}
@@ -404,6 +435,10 @@ def area_cases():
 
 
 def main():
+    if "--lines-aa2-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
+        print("lines_aa2.npz", os.path.getsize(os.path.join(HERE, "lines_aa2.npz")) // 1024, "KiB")
+        return
     if "--areas-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
         print("areas.npz", os.path.getsize(os.path.join(HERE, "areas.npz")) // 1024, "KiB")
@@ -424,6 +459,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "lines_extra.npz"), **lines_extra_cases())
     np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
     np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
+    np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())

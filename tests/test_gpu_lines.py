@@ -162,3 +162,57 @@ def test_line_axis0_vs_oracle_random(dtype):
         assert got.dtype == want.dtype
         assert np.array_equal(np.isnan(got), np.isnan(want)), name
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True, err_msg=name)
+
+
+AA2 = {"min": ("min", lambda ds: ds.min("val")), "first": ("first", lambda ds: ds.first("val")),
+       "last": ("last", lambda ds: ds.last("val")), "sum_nsi": ("sum", lambda ds: ds.sum("val", self_intersect=False)),
+       "count_nsi": ("count", lambda ds: ds.count(self_intersect=False)),
+       "count_val_nsi": ("count", lambda ds: ds.count("val", self_intersect=False))}
+
+
+def _cmp_aa(got, want, key, rtol=1e-6):
+    assert got.dtype == want.dtype and got.shape == want.shape, key
+    assert np.array_equal(np.isnan(got), np.isnan(want)), key
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-7, equal_nan=True, err_msg=key)
+
+
+def test_lines_aa2_golden():
+    """2-stage antialiased reductions (L7: compiler.py:198-268) vs the real reference: LinesAxis1 (40 lines), LineAxis0Multi
+    and LineAxis0.  Tolerance 1e-6: the GPU contracts a few f64 expressions of the coverage computation differently."""
+    import pandas as pd
+    import datashader_b200 as ds
+    g, gl, gx = load("lines_aa2.npz"), load("lines.npz"), load("line_layouts.npz")
+    for tag in ("f32", "f64"):
+        frame, xcols, ycols = _frame(gl[f"in_{tag}_xs"], gl[f"in_{tag}_ys"], gl[f"in_{tag}_val"])
+        cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+        for lw in ((1, 2.5) if tag == "f32" else (1,)):
+            for gname, (_o, mk) in AA2.items():
+                got = cvs.line(frame, x=xcols, y=ycols, axis=1, agg=mk(ds), line_width=lw).data
+                _cmp_aa(got, g[f"aa2_{tag}_lw{lw}_{gname}"], f"{tag} lw{lw} {gname}")
+    df0 = pd.DataFrame({k: gx[f"ax0_{k}"] for k in ("x", "y", "x2", "y2", "val")})
+    cvs = ds.Canvas(plot_width=50, plot_height=40, x_range=(0, 1), y_range=(0, 1))
+    for gname, (_o, mk) in AA2.items():
+        _cmp_aa(cvs.line(df0, "x", "y", agg=mk(ds), line_width=2).data, g[f"aa2_ax0_lw2_{gname}"], f"ax0 {gname}")
+        _cmp_aa(cvs.line(df0, x=["x", "x2"], y=["y", "y2"], axis=0, agg=mk(ds), line_width=2).data, g[f"aa2_ax0multi_lw2_{gname}"],
+                f"ax0multi {gname}")
+
+
+def test_lines_aa2_vs_oracle_larger():
+    """3000 lines x 16 vertices on a clipping 300x200 canvas: many lines per CTA, heavy overlap."""
+    import datashader_b200 as ds
+    from oracle import oracle as ora
+    rng = np.random.default_rng(99)
+    nl, nv = 3000, 16
+    xs = (np.cumsum(rng.normal(0, 0.04, (nl, nv)), axis=1) + rng.random((nl, 1))).astype(np.float32)
+    ys = (np.cumsum(rng.normal(0, 0.04, (nl, nv)), axis=1) + rng.random((nl, 1))).astype(np.float32)
+    xs[rng.random((nl, nv)) < 0.02] = np.nan
+    val = (rng.random(nl) * 6 - 2).astype(np.float32)
+    val[rng.integers(0, nl, 30)] = np.nan
+    frame, xcols, ycols = _frame(xs, ys, val)
+    W, H = 300, 200
+    cvs = ds.Canvas(plot_width=W, plot_height=H, x_range=(0.1, 0.9), y_range=(0.2, 0.8))
+    view = ora.make_view(W, H, (0.1, 0.9), (0.2, 0.8))
+    for gname, (oname, mk) in AA2.items():
+        got = cvs.line(frame, x=xcols, y=ycols, axis=1, agg=mk(ds), line_width=1.5).data
+        want = ora.lines_aa2(xs, ys, view, oname, None if gname == "count_nsi" else val, 1.5)
+        _cmp_aa(got, want, gname, rtol=2e-6 if oname in ("sum", "count") else 1e-6)

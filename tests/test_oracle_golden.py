@@ -230,3 +230,29 @@ def test_areas_golden():
         _eq(ora.areas(xconst, ym, fixed, ysm, name, vals), g[f"a1xc_line_{name}"], f"a1xc line {name}")
         _eq(ora.areas(xm, yconst, fixed, None, name, vals), g[f"a1yc_zero_{name}"], f"a1yc zero {name}")
         _eq(ora.areas(xm, yconst, fixed, sconst, name, vals), g[f"a1yc_line_{name}"], f"a1yc line {name}")
+
+
+def test_lines_aa2_golden():
+    """2-stage antialiased reductions (min / first / last / count, sum with self_intersect=False) vs the reference."""
+    g, gl, gx = load("lines_aa2.npz"), load("lines.npz"), load("line_layouts.npz")
+    view = ora.make_view(64, 48, (0, 1), (0, 1))
+    names = {"min": "min", "first": "first", "last": "last", "sum_nsi": "sum", "count_nsi": "count", "count_val_nsi": "count"}
+    for tag in ("f32", "f64"):
+        xs, ys, val = gl[f"in_{tag}_xs"], gl[f"in_{tag}_ys"], gl[f"in_{tag}_val"]
+        for lw in ((1, 2.5) if tag == "f32" else (1,)):
+            for gname, oname in names.items():
+                vals = None if gname == "count_nsi" else val
+                got = ora.lines_aa2(xs, ys, view, oname, vals, lw)
+                want = g[f"aa2_{tag}_lw{lw}_{gname}"]
+                assert got.dtype == want.dtype, gname
+                assert np.array_equal(np.isnan(got), np.isnan(want)), (tag, lw, gname)
+                np.testing.assert_allclose(got, want, rtol=1e-6 if oname == "count" else 1e-12, equal_nan=True, err_msg=f"{tag} {lw} {gname}")
+    view0 = ora.make_view(50, 40, (0, 1), (0, 1))
+    x, y, x2, y2, val = (gx[f"ax0_{k}"] for k in ("x", "y", "x2", "y2", "val"))
+    for gname, oname in names.items():
+        vals = None if gname == "count_nsi" else val
+        for key, xa, ya in (("ax0", x[None], y[None]), ("ax0multi", np.stack([x, x2]), np.stack([y, y2]))):
+            got = ora.lines_aa2(xa, ya, view0, oname, vals, 2, per_vertex=True)
+            want = g[f"aa2_{key}_lw2_{gname}"]
+            assert got.dtype == want.dtype and np.array_equal(np.isnan(got), np.isnan(want)), (key, gname)
+            np.testing.assert_allclose(got, want, rtol=1e-6 if oname == "count" else 1e-12, equal_nan=True, err_msg=f"{key} {gname}")
