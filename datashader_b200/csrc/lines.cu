@@ -47,8 +47,13 @@ struct LineCtx {
   const dsb_plan* plan;     // non-null: run the accumulator plan for every touched pixel
   long long line, row;      // line index within the frame / global row id
   int cat;                  // category of this line (by()), -1 = skip
-  unsigned int* touched_n;  // 2-stage antialiasing: the CTA's count of / list of cells its current line has touched
-  uint32_t* touched;
+  unsigned int* touched_n;  // 2-stage antialiasing, global stage-1 canvas: `touched` = the CTA's bitmap of touched cells,
+  uint32_t* touched;        //   bbox = this thread's {ymin, ymax} of touched rows; or, when hkeys != nullptr, the
+  int* bbox;                //   shared-memory hash table:
+  uint32_t* hkeys;          //   [cap] cell ids (0xffffffff = free), hvals [cap] key64 maxima, touched_n = entries in use
+  long long* hvals;
+  uint32_t hmask;           //   cap - 1
+  uint32_t hgroup;          //   (index of the line within its group) << 27, or-ed into the table key
 };
 
 // internal agg codes of the 2-stage path (stage 1 = per-line max of field * aa_factor / of aa_factor)
@@ -127,8 +132,24 @@ __device__ __forceinline__ void append_aa(const LineCtx& c, long long x, long lo
         v = fmul64(c.field, aa);
         if (v != v) return;
       }
-      const long long old = atomicMax((long long*)c.canvas + cell, key64_from_f64(v));
-      if (old == LLONG_MIN) c.touched[atomicAdd(c.touched_n, 1u)] = (uint32_t)cell;   // first touch by this line
+      const long long key = key64_from_f64(v);
+      if (c.hkeys) {                        // open addressing, linear probing; at most 3/4 full, else the line is redone
+        const uint32_t id = c.hgroup | (uint32_t)cell;
+        uint32_t h = (id * 2654435761u) >> 7 & c.hmask;
+        for (;;) {
+          uint32_t k = c.hkeys[h];
+          if (k == 0xffffffffu) {
+            if (*(volatile unsigned int*)c.touched_n > (c.hmask >> 2) * 3u) { atomicOr(c.touched_n, 0x80000000u); return; }
+            k = atomicCAS(c.hkeys + h, 0xffffffffu, id);
+            if (k == 0xffffffffu) { atomicAdd(c.touched_n, 1u); k = id; }
+          }
+          if (k == id) { atomicMax((long long*)c.hvals + h, key); return; }
+          h = (h + 1) & c.hmask;
+        }
+      }
+      atomicMax((long long*)c.canvas + cell, key);                 // both fire-and-forget REDs
+      atomicOr(c.touched + (cell >> 5), 1u << (cell & 31));
+      c.bbox[0] = min(c.bbox[0], (int)y); c.bbox[1] = max(c.bbox[1], (int)y);
       return;
     }
   }
@@ -419,23 +440,84 @@ struct Aa2Args {
   int combo, phase;
   void* out;
   void* aux;              // sum / count: u8 mask; first / last: i64 line-index canvas
-  long long* temp;        // [nctas][ncell]
-  uint32_t* touched;      // [nctas][ncell]
+  long long* temp;        // [nctas][ncell]  (global stage-1 canvases, used for the lines that overflow the hash table)
+  uint32_t* touched;      // [nctas][nwords] bitmaps of the cells the CTA's current line has touched (nwords = ceil(ncell / 32))
+  unsigned int* stats;    // [2] groups tried / groups overflowed by the hash pass (it gives up when most overflow)
+  unsigned int* redo_n;   // number of / indices of the lines whose touched-pixel set overflowed the shared-memory table
+  unsigned int* redo;     // [nlines]
 };
 
-template <typename XY>
-__global__ void __launch_bounds__(256) k_lines_aa2(const LineArgs a, const Aa2Args b) {
+#define AA2_HASH_CAP 16384   // 16384 x (4 + 8) B = 192 KB of shared memory: one 512-thread CTA per SM
+#define AA2_THREADS 512
+#define AA2_CELL_BITS 27      // table key = (line within its group) << 27 | cell: canvases below 2^27 pixels, groups <= 32
+
+__device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long long key, long long line) {
+  switch (b.combo) {
+    case DSB_AA2_SUM:      // nansum_in_place, utils.py:885-897 (the NaN start is restored from the mask afterwards)
+      atomicAdd((double*)b.out + cell, f64_from_key64(key));
+      ((uint8_t*)b.aux)[cell] = 1;
+      break;
+    case DSB_AA2_COUNT:
+      atomicAdd((float*)b.out + cell, (float)f64_from_key64(key));
+      ((uint8_t*)b.aux)[cell] = 1;
+      break;
+    case DSB_AA2_MIN:      // nanmin_in_place, utils.py:655-668
+      atomicMin((long long*)b.out + cell, key);
+      break;
+    case DSB_AA2_FIRST:    // nanfirst_in_place, utils.py:615-623: the lowest line index that touches the pixel wins
+      if (b.phase == 1) atomicMin((long long*)b.aux + cell, line);
+      else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
+      break;
+    case DSB_AA2_LAST:     // nanlast_in_place, utils.py:627-635
+      if (b.phase == 1) atomicMax((long long*)b.aux + cell, line);
+      else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
+      break;
+  }
+}
+
+// HASH: stage 1 in a shared-memory hash table ((line, cell) -> max key64).  A CTA takes a group of G consecutive lines
+// at a time (G = 1 for long lines; short lines are batched so that all threads have a segment) and flushes the table
+// after each group.  Groups that fill more than 3/4 of the table are queued in b.redo and handled, line by line, by a
+// second launch with HASH = false, whose stage 1 is the CTA's private full-size global canvas.
+template <typename XY, bool HASH>
+__global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, const Aa2Args b, const int G) {
+  extern __shared__ long long aa2_smem[];
   __shared__ unsigned int s_touched;
+  long long* hvals = aa2_smem;
+  uint32_t* hkeys = (uint32_t*)(aa2_smem + AA2_HASH_CAP);
   const XY* __restrict__ xs = (const XY*)a.xs;
   const XY* __restrict__ ys = (const XY*)a.ys;
   const long long ncell = (long long)a.v.width * a.v.height;
-  long long* temp = b.temp + (long long)blockIdx.x * ncell;
-  uint32_t* touched = b.touched + (long long)blockIdx.x * ncell;
+  const long long nwords = (ncell + 31) >> 5;
+  long long* temp = HASH ? nullptr : b.temp + (long long)blockIdx.x * ncell;
+  uint32_t* touched = HASH ? nullptr : b.touched + (long long)blockIdx.x * nwords;
+  __shared__ int s_bbox[2];
+  __shared__ int s_skip;
   const long long nseg = a.nverts - 1;
-  for (long long i = blockIdx.x; i < a.nlines; i += gridDim.x) {
-    if (threadIdx.x == 0) s_touched = 0;
+  const long long nwork = HASH ? (a.nlines + G - 1) / G : (long long)*b.redo_n;
+  if (HASH) {
+    for (int k = threadIdx.x; k < AA2_HASH_CAP; k += blockDim.x) { hkeys[k] = 0xffffffffu; hvals[k] = LLONG_MIN; }
+  }
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const long long i0 = HASH ? w * G : (long long)b.redo[w];
+    const long long glines = HASH ? (a.nlines - i0 < G ? a.nlines - i0 : (long long)G) : 1;
+    if (threadIdx.x == 0) {
+      s_touched = 0; s_bbox[0] = INT_MAX; s_bbox[1] = -1;
+      if (HASH) {
+        const unsigned int tried = *(volatile unsigned int*)b.stats, failed = *(volatile unsigned int*)(b.stats + 1);
+        s_skip = tried >= 64u && failed * 2u > tried;
+      }
+    }
     __syncthreads();
-    for (long long j = threadIdx.x; j < nseg; j += blockDim.x) {
+    if (HASH && s_skip) {
+      // most groups so far did not fit the table (long lines): stop trying, hand the rest to the global path
+      if (threadIdx.x < glines) b.redo[atomicAdd(b.redo_n, 1u)] = (unsigned int)(i0 + threadIdx.x);
+      __syncthreads();
+      continue;
+    }
+    int bbox[2] = {INT_MAX, -1};
+    for (long long t = threadIdx.x; t < glines * nseg; t += blockDim.x) {
+      const long long g = t / nseg, j = t - g * nseg, i = i0 + g;
       const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
       const double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
       bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
@@ -454,41 +536,53 @@ __global__ void __launch_bounds__(256) k_lines_aa2(const LineArgs a, const Aa2Ar
       c.field = c.has_field ? load_f64(a.val, a.val_dtype, vi) : 0.0;
       c.field_nan = c.has_field && (c.field != c.field);
       c.plan = nullptr; c.line = vi; c.row = a.row_offset + vi; c.cat = 0;
-      c.touched_n = &s_touched; c.touched = touched;
+      c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox;
+      c.hkeys = HASH ? hkeys : nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = (uint32_t)g << AA2_CELL_BITS;
       // xm = ym = 0 in 2-stage mode (line.py:1266-1268); unused because overwrite is True
       draw_segment<XY>(a, c, segment_start, segment_end, x0, x1, y0, y1, 0.0, 0.0);
     }
+    if (!HASH && bbox[1] >= 0) { atomicMin(&s_bbox[0], bbox[0]); atomicMax(&s_bbox[1], bbox[1]); }
     __syncthreads();
     const unsigned int n = s_touched;
-    const long long line = a.row_offset + i;          // global line index: what "first" / "last" order by
-    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
-      const uint32_t cell = touched[k];
-      const long long key = __ldcg(temp + cell);    // written by L2 atomics: do not trust a stale L1 line
-      temp[cell] = LLONG_MIN;
-      switch (b.combo) {
-        case DSB_AA2_SUM:
-          atomicAdd((double*)b.out + cell, f64_from_key64(key));
-          ((uint8_t*)b.aux)[cell] = 1;
-          break;
-        case DSB_AA2_COUNT:
-          atomicAdd((float*)b.out + cell, (float)f64_from_key64(key));
-          ((uint8_t*)b.aux)[cell] = 1;
-          break;
-        case DSB_AA2_MIN:
-          atomicMin((long long*)b.out + cell, key);
-          break;
-        case DSB_AA2_FIRST:
-          if (b.phase == 1) atomicMin((long long*)b.aux + cell, line);
-          else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
-          break;
-        case DSB_AA2_LAST:
-          if (b.phase == 1) atomicMax((long long*)b.aux + cell, line);
-          else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
-          break;
+    if (HASH) {
+      const bool overflow = (n & 0x80000000u) != 0;
+      if (overflow && threadIdx.x < glines) b.redo[atomicAdd(b.redo_n, 1u)] = (unsigned int)(i0 + threadIdx.x);
+      if (threadIdx.x == 0) { atomicAdd(b.stats, 1u); if (overflow) atomicAdd(b.stats + 1, 1u); }
+      if (n != 0) {
+        for (int k = threadIdx.x; k < AA2_HASH_CAP; k += blockDim.x) {
+          const uint32_t id = hkeys[k];
+          if (id == 0xffffffffu) continue;
+          const long long key = hvals[k];
+          hkeys[k] = 0xffffffffu; hvals[k] = LLONG_MIN;
+          // global line index: what "first" / "last" order by
+          if (!overflow) aa2_stage2(b, id & ((1u << AA2_CELL_BITS) - 1u), key, a.row_offset + i0 + (id >> AA2_CELL_BITS));
+        }
+      }
+    } else if (s_bbox[1] >= 0) {
+      // walk the bitmap words of the touched rows; every set bit is a cell of this line: fold it in and clear it
+      const long long w0 = ((long long)s_bbox[0] * a.v.width) >> 5, w1 = (((long long)s_bbox[1] + 1) * a.v.width - 1) >> 5;
+      for (long long wi = w0 + threadIdx.x; wi <= w1; wi += blockDim.x) {
+        uint32_t bits = __ldcg(touched + wi);          // written by L2 REDs: do not trust a stale L1 line
+        if (!bits) continue;
+        touched[wi] = 0;
+        while (bits) {
+          const int bit = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const uint32_t cell = (uint32_t)(wi << 5) + bit;
+          const long long key = __ldcg(temp + cell);
+          temp[cell] = LLONG_MIN;
+          aa2_stage2(b, cell, key, a.row_offset + i0);
+        }
       }
     }
     __syncthreads();
   }
+}
+
+// canvases of 2^27 pixels and more do not fit the table key: every line is queued for the global stage-1 path
+__global__ void k_aa2_queue_all(unsigned int* redo_n, unsigned int* redo, unsigned int nlines) {
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlines; i += gridDim.x * blockDim.x) redo[i] = i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *redo_n = nlines;
 }
 
 __global__ void k_fill_i64(long long* p, long long v, long long n) {
@@ -589,12 +683,10 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   if (!xs || !ys) { dsb_set_error("dsb_lines_aa2: null vertex arrays"); return DSB_ERR_ARG; }
   const long long ncell = (long long)view->width * view->height;
   if (ncell >= (1LL << 32)) { dsb_set_error("dsb_lines_aa2: canvas too large"); return DSB_ERR_UNSUPPORTED; }
-  const long long per_cta = ncell * 12;
-  long long nctas = scratch ? scratch_bytes / per_cta : 0;
-  if (nctas < 1) { dsb_set_error("dsb_lines_aa2: scratch must hold at least %lld bytes (12 per pixel per CTA)", per_cta); return DSB_ERR_ARG; }
-  const long long cap = (long long)dsb_num_sms() * 4;
-  if (nctas > cap) nctas = cap;
-  if (nctas > nlines) nctas = nlines;
+  if (!scratch) { dsb_set_error("dsb_lines_aa2: scratch required"); return DSB_ERR_ARG; }
+  const long long per_cta = ncell * 8 + ((ncell + 31) >> 5) * 4;
+  const long long cap = (long long)dsb_num_sms();
+  long long nctas;
   LineArgs a;
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
   a.agg = combo == DSB_AA2_COUNT ? DSB_LINE_AA2_COVER : DSB_LINE_AA2_VALUE;
@@ -606,15 +698,43 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   a.yymax = py_round(my * view->sy + view->ty);
   a.nx = py_round((view->xmax - view->xmin) * view->sx);
   a.ny = py_round((view->ymax - view->ymin) * view->sy);
+  if (nlines >= (1LL << 31)) { dsb_set_error("dsb_lines_aa2: too many lines"); return DSB_ERR_UNSUPPORTED; }
   Aa2Args b;
   b.combo = combo; b.phase = phase; b.out = out; b.aux = aux;
-  b.temp = (long long*)scratch;                               // [nctas][ncell] i64, then [nctas][ncell] u32
+  // scratch layout: [nctas][ncell] i64 stage-1 canvases, [nctas][nwords] u32 touched bitmaps, [4 + nlines] u32 queue
+  const long long nwords = (ncell + 31) >> 5;
+  const long long redo_bytes = 4 * (4 + nlines);
+  nctas = (scratch_bytes - redo_bytes) / per_cta;
+  if (nctas < 1) { dsb_set_error("dsb_lines_aa2: scratch must hold at least %lld bytes", per_cta + redo_bytes); return DSB_ERR_ARG; }
+  if (nctas > cap) nctas = cap;
+  if (nctas > nlines) nctas = nlines;
+  b.temp = (long long*)scratch;
   b.touched = (uint32_t*)((char*)scratch + nctas * ncell * 8);
+  b.redo_n = (unsigned int*)((char*)scratch + nctas * (ncell * 8 + nwords * 4));
+  b.stats = b.redo_n + 1;
+  b.redo = b.redo_n + 4;
   cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(b.touched, 0, (size_t)(nctas * nwords * 4 + 16), s);     // bitmaps + queue header
   k_fill_i64<<<dsb_num_sms() * 8, 256, 0, s>>>(b.temp, LLONG_MIN, nctas * ncell);
-  if (xy_dtype == DSB_F32) k_lines_aa2<float><<<(int)nctas, 256, 0, s>>>(a, b);
-  else if (xy_dtype == DSB_F64) k_lines_aa2<double><<<(int)nctas, 256, 0, s>>>(a, b);
-  else { dsb_set_error("dsb_lines_aa2: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+  const size_t smem = (size_t)AA2_HASH_CAP * 12;
+  // short lines are batched G to a group so that every thread of the CTA has a segment (at most 32 lines per group)
+  long long G = AA2_THREADS / (nverts - 1);
+  G = G < 1 ? 1 : (G > 32 ? 32 : G);
+  const bool use_hash = ncell < (1LL << AA2_CELL_BITS) - 1;
+  if (!use_hash) G = 1;
+  long long hgrid = (long long)dsb_num_sms();
+  if (hgrid > (nlines + G - 1) / G) hgrid = (nlines + G - 1) / G;
+  if (xy_dtype == DSB_F32) {
+    cudaFuncSetAttribute(k_lines_aa2<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (use_hash) k_lines_aa2<float, true><<<(int)hgrid, AA2_THREADS, smem, s>>>(a, b, (int)G);
+    else k_aa2_queue_all<<<dsb_num_sms(), 256, 0, s>>>(b.redo_n, b.redo, (unsigned int)nlines);
+    k_lines_aa2<float, false><<<(int)nctas, AA2_THREADS, 0, s>>>(a, b, 1);
+  } else if (xy_dtype == DSB_F64) {
+    cudaFuncSetAttribute(k_lines_aa2<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (use_hash) k_lines_aa2<double, true><<<(int)hgrid, AA2_THREADS, smem, s>>>(a, b, (int)G);
+    else k_aa2_queue_all<<<dsb_num_sms(), 256, 0, s>>>(b.redo_n, b.redo, (unsigned int)nlines);
+    k_lines_aa2<double, false><<<(int)nctas, AA2_THREADS, 0, s>>>(a, b, 1);
+  } else { dsb_set_error("dsb_lines_aa2: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
   DSB_CUDA_CHECK_LAUNCH("dsb_lines_aa2");
   return DSB_OK;
 }

@@ -397,12 +397,13 @@ def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist):
         if agg.column is not None:
             val = frame[agg.column]
             val_dtype = _lib.dsb_dtype(frame.np_dtype(agg.column))
-        # scratch: 12 bytes per pixel per CTA; as many CTAs as a budget of 1/8 of the free memory (<= 16 GiB) allows
+        # scratch for the lines that overflow the shared-memory stage-1 table: a key64 canvas + a touched bitmap per CTA
+        # (8.125 bytes per pixel), one CTA per SM if 1/4 of the free memory (<= 16 GiB) allows, plus the redo queue
         free, _total = torch.cuda.mem_get_info(device)
-        per_cta = 12 * H * W
-        nctas = int(max(1, min(4 * torch.cuda.get_device_properties(device).multi_processor_count, max(nlines, 1),
-                               min(free // 8, 16 << 30) // per_cta)))
-        scratch = torch.empty(nctas * per_cta, dtype=torch.uint8, device=device)
+        per_cta = 8 * H * W + 4 * ((H * W + 31) // 32)
+        nctas = int(max(1, min(torch.cuda.get_device_properties(device).multi_processor_count, max(nlines, 1),
+                               min(free // 4, 16 << 30) // per_cta)))
+        scratch = torch.empty(nctas * per_cta + 4 * (nlines + 4), dtype=torch.uint8, device=device)
         row_offset = frame.row_offset if not glyph_per_vertex(glyph) else 0
 
         def launch(phase, out, aux):

@@ -216,3 +216,25 @@ def test_lines_aa2_vs_oracle_larger():
         got = cvs.line(frame, x=xcols, y=ycols, axis=1, agg=mk(ds), line_width=1.5).data
         want = ora.lines_aa2(xs, ys, view, oname, None if gname == "count_nsi" else val, 1.5)
         _cmp_aa(got, want, gname, rtol=2e-6 if oname in ("sum", "count") else 1e-6)
+
+
+def test_lines_aa2_long_lines_overflow_the_stage1_table():
+    """Lines that touch far more than 6144 pixels (wide line_width on a 1200x900 canvas) take the global stage-1 canvas;
+    the result must match the oracle either way."""
+    import datashader_b200 as ds
+    from oracle import oracle as ora
+    rng = np.random.default_rng(3)
+    nl, nv = 24, 40
+    xs = np.sort(rng.random((nl, nv)), axis=1).astype(np.float32)
+    ys = rng.random((nl, nv)).astype(np.float32)
+    xs[:4] = rng.random((4, nv)).astype(np.float32) * 0.02 + 0.5      # 4 short lines stay in the table
+    ys[:4] = rng.random((4, nv)).astype(np.float32) * 0.02 + 0.5
+    val = (rng.random(nl) * 5 + 1).astype(np.float32)
+    frame, xcols, ycols = _frame(xs, ys, val)
+    W, H = 1200, 900
+    cvs = ds.Canvas(plot_width=W, plot_height=H, x_range=(0, 1), y_range=(0, 1))
+    view = ora.make_view(W, H, (0, 1), (0, 1))
+    for gname in ("min", "first", "last", "sum_nsi"):
+        oname, mk = AA2[gname]
+        got = cvs.line(frame, x=xcols, y=ycols, axis=1, agg=mk(ds), line_width=4).data
+        _cmp_aa(got, ora.lines_aa2(xs, ys, view, oname, val, 4), gname, rtol=2e-6)

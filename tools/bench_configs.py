@@ -71,6 +71,11 @@ def config4(scale):
         out[f"{tag}_ms"] = ms
         out[f"{tag}_msegments_per_s"] = nl * (nv - 1) / ms / 1e3
         out[f"{tag}_covered_pixels"] = int((~torch.isnan(torch.as_tensor(agg.data))).sum())
+    # the 2-stage antialiased reductions (one CTA per line, per-line stage-1 canvases in scratch memory)
+    for name, a2 in (("aa2_min", ds.min("value")), ("aa2_first", ds.first("value")), ("aa2_sum_nsi", ds.sum("value", self_intersect=False))):
+        ms, agg = timed(lambda: cvs.line(frame, x=xc, y=yc, axis=1, agg=a2, line_width=1), warmup=1, steps=2)
+        out[f"{name}_ms"] = ms
+        out[f"{name}_msegments_per_s"] = nl * (nv - 1) / ms / 1e3
     return out
 
 
