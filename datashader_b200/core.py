@@ -273,10 +273,10 @@ def bypixel(source, canvas, glyph, agg, *, antialias=False):
     type selects the fused kernel."""
     from . import pipeline
     from .distributed import current_group
-    from .frame import DeviceFrame, HostFrame
+    from .frame import DeviceFrame, HostFrame, _is_arrow
     import pandas as pd
 
-    if not isinstance(source, (pd.DataFrame, DeviceFrame, HostFrame)):
+    if not (isinstance(source, (pd.DataFrame, DeviceFrame, HostFrame, dict)) or _is_arrow(source)):
         raise ValueError("source must be a pandas or dask DataFrame")
     dist = current_group(source)
     with warnings.catch_warnings():

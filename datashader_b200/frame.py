@@ -40,7 +40,14 @@ class DeviceFrame:
     """
 
     def __init__(self, columns, categories=None, row_offset=0, n_global=None):
-        self.columns = dict(columns)
+        self.columns = {}
+        for name, t in dict(columns).items():
+            if not isinstance(t, torch.Tensor):
+                # cupy / numba / cudf-column style device arrays (__cuda_array_interface__, DLPack): borrowed, not copied
+                t = torch.as_tensor(t, device="cuda")
+            if not t.is_cuda:
+                raise ValueError("DeviceFrame columns must live on the GPU; use HostFrame for host arrays")
+            self.columns[name] = t.contiguous()
         self.categories = dict(categories or {})
         self.row_offset = int(row_offset)
         lens = {int(t.shape[0]) for t in self.columns.values()}
@@ -158,6 +165,44 @@ class HostFrame:
         off = getattr(df, "_datashader_row_offset", 0)
         return cls(cols, cats, off, device)
 
+    @classmethod
+    def from_arrow(cls, table, columns=None, device=None, row_offset=0):
+        """pyarrow.Table / RecordBatch -> HostFrame.  Numeric columns are taken zero-copy when they are a single chunk
+        without nulls; float nulls become NaN (what pandas hands the reference), integer columns with nulls are
+        widened to float64 with NaN, dictionary columns become category codes + labels (null -> -1, pandas' code)."""
+        import pyarrow as pa
+        if isinstance(table, pa.RecordBatch):
+            table = pa.Table.from_batches([table])
+        cols, cats = {}, {}
+        for name in (columns if columns is not None else table.column_names):
+            if name not in table.column_names:
+                raise ValueError("specified column not found")     # reductions.py:352-353
+            col = table.column(name)
+            arr = col.chunk(0) if col.num_chunks == 1 else col.combine_chunks()
+            if isinstance(arr, pa.ChunkedArray):
+                arr = arr.combine_chunks()
+            if pa.types.is_dictionary(arr.type):
+                cats[name] = arr.dictionary.to_pylist()
+                idx = arr.indices
+                codes = idx.to_numpy(zero_copy_only=False)
+                if idx.null_count:
+                    codes = np.where(np.asarray(idx.is_null()), -1, np.nan_to_num(codes, nan=0)).astype(np.int64)
+                small = np.int8 if len(cats[name]) <= 127 else (np.int16 if len(cats[name]) <= 32767 else np.int32)
+                cols[name] = np.asarray(codes).astype(small)
+            elif pa.types.is_floating(arr.type) or pa.types.is_integer(arr.type) or pa.types.is_boolean(arr.type):
+                cols[name] = arr.to_numpy(zero_copy_only=False)     # nulls: float NaN (ints are promoted to float64)
+            else:
+                raise ValueError(f"input '{name}' must be a numeric or dictionary column")
+        return cls(cols, cats, row_offset, device)
+
+    @classmethod
+    def from_parquet(cls, path, columns=None, device=None, row_offset=0):
+        """Read only the needed columns of a Parquet file (the reference's performance guidance,
+        examples/user_guide/10_Performance.ipynb) straight into a HostFrame."""
+        import pyarrow.parquet as pq
+        return cls.from_arrow(pq.read_table(path, columns=list(columns) if columns is not None else None),
+                              columns=columns, device=device, row_offset=row_offset)
+
     def schema(self):
         out = {}
         for name, t in self.columns.items():
@@ -208,11 +253,30 @@ class HostFrame:
         compute.synchronize()
 
 
+def _is_arrow(source):
+    mod = type(source).__module__ or ""
+    return mod.startswith("pyarrow") and type(source).__name__ in ("Table", "RecordBatch")
+
+
 def as_frame(source, needed, device=None):
-    """pandas.DataFrame | HostFrame | DeviceFrame -> a frame with the needed columns."""
+    """pandas.DataFrame | pyarrow.Table / RecordBatch | dict of columns | HostFrame | DeviceFrame -> a frame holding
+    the needed columns.  Only those columns are touched (like _bypixel_sanitise, core.py:1384-1392)."""
     import pandas as pd
     if isinstance(source, (DeviceFrame, HostFrame)):
         return source
     if isinstance(source, pd.DataFrame):
         return HostFrame.from_pandas(source, columns=needed, device=device)
+    if _is_arrow(source):
+        return HostFrame.from_arrow(source, columns=needed, device=device)
+    if isinstance(source, dict):
+        missing = [c for c in needed if c not in source]
+        if missing:
+            raise ValueError("specified column not found")
+        cols = {c: source[c] for c in needed}
+        on_gpu = [hasattr(v, "__cuda_array_interface__") or (isinstance(v, torch.Tensor) and v.is_cuda) for v in cols.values()]
+        if cols and all(on_gpu):
+            return DeviceFrame(cols)
+        if any(on_gpu):
+            raise ValueError("columns of a dict source must be all on the host or all on the GPU")
+        return HostFrame(cols, device=device)
     raise ValueError("source must be a pandas or dask DataFrame")

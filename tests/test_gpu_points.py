@@ -316,3 +316,27 @@ def test_l2_banded_passes_match_oracle(ds):
         ds.config.priv_count = old_priv
         _lib.check(L.dsb_configure(b"l2_band_bytes", 96 << 20))
         _lib.check(L.dsb_configure(b"band_min_rows", 1 << 22))
+
+
+def test_arrow_and_dict_sources_match_pandas(ds):
+    """The same rows through a pandas.DataFrame, a pyarrow.Table, a dict of host arrays and a dict of device arrays."""
+    import pandas as pd
+    import torch
+    pa = pytest.importorskip("pyarrow")
+    rng = np.random.default_rng(8)
+    n = 50_000
+    df = pd.DataFrame({"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32), "v": rng.normal(size=n),
+                       "cat": pd.Categorical.from_codes(rng.integers(0, 4, n), categories=list("abcd"))})
+    df.loc[rng.integers(0, n, 50), "v"] = np.nan
+    cvs = ds.Canvas(120, 80, x_range=(0, 1), y_range=(0, 1))
+    table = pa.Table.from_pandas(df)
+    host = {"x": df.x.to_numpy(), "y": df.y.to_numpy(), "v": df.v.to_numpy()}
+    dev = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+    for agg in (ds.count(), ds.mean("v"), ds.max("v"), ds.where(ds.max("v"))):
+        want = cvs.points(df, "x", "y", agg).data
+        for src in (table, host, dev):
+            got = cvs.points(src, "x", "y", agg).data
+            assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), (type(src), agg)
+    want = cvs.points(df, "x", "y", ds.by("cat", ds.count()))
+    got = cvs.points(table, "x", "y", ds.by("cat", ds.count()))
+    assert np.array_equal(got.data, want.data) and list(got.coords["cat"]) == list(want.coords["cat"])
