@@ -284,12 +284,7 @@ def bypixel(source, canvas, glyph, agg, *, antialias=False):
         if isinstance(glyph, Point):
             return pipeline.points(source, canvas, glyph, agg, dist=dist)
         if isinstance(glyph, AreaGlyph):
-            if dist is not None and glyph.value_per_vertex:
-                raise NotImplementedError("axis=0 areas cannot be sharded by rows: not implemented")
             return pipeline.areas(source, canvas, glyph, agg, dist=dist)
         if isinstance(glyph, _LineGlyph):
-            if dist is not None and glyph.value_per_vertex:
-                raise NotImplementedError("axis=0 lines cannot be sharded by rows without the previous shard's last "
-                                          "vertex (data_libraries/dask.py:244-266): not implemented")
             return pipeline.lines(source, canvas, glyph, agg, antialias=antialias, dist=dist)
     raise NotImplementedError(f"glyph {type(glyph).__name__} is not supported")

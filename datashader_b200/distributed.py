@@ -77,6 +77,35 @@ class ShardGroup:
         out = bits.view(torch.float64)
         return torch.where(empty, torch.full_like(out, float("nan")), out)
 
+    # ---- axis=0 glyphs sharded by rows (data_libraries/dask.py:244-266) ------------------------------
+    def carry_last_row(self, frame, needed):
+        """LineAxis0 / area axis=0 shards: the segment from the previous shard's last vertex to this shard's first
+        vertex belongs to this shard.  The reference prepends the previous partition's last row and clears
+        plot_start; here every rank all-gathers its last row (needed columns only, as f64) and does the same.
+        Returns (frame, plot_start)."""
+        from .frame import DeviceFrame
+        dev = frame.device
+        cols = list(needed)
+        last = torch.zeros(len(cols) + 1, dtype=torch.float64, device=dev)
+        if len(frame) > 0:
+            last[0] = 1.0                                             # "this rank has rows"
+            for k, c in enumerate(cols):
+                last[k + 1] = frame[c][-1].to(torch.float64)
+        gathered = [torch.empty_like(last) for _ in range(self.world)]
+        dist.all_gather(gathered, last, group=self.group)
+        prev = None
+        for r in range(self.rank - 1, -1, -1):                         # nearest previous rank that has rows
+            if float(gathered[r][0]) != 0.0:
+                prev = gathered[r]
+                break
+        if prev is None or len(frame) == 0:
+            return frame, prev is None
+        new_cols = {c: torch.cat([prev[k + 1:k + 2].to(frame[c].dtype), frame[c]]) for k, c in enumerate(cols)}
+        out = DeviceFrame(new_cols, frame.categories, frame.row_offset - 1, frame.n_global)
+        out.sharded = True
+        out.group = getattr(frame, "group", None)
+        return out, False
+
     # ---- auto-ranging (compute_bounds_dask, glyphs/points.py:153-167) -----------------------------
     def global_bounds(self, lo, hi, device):
         t = torch.tensor([lo, -hi], dtype=torch.float64, device=device)

@@ -289,7 +289,7 @@ def _line_setup(frame, canvas, glyph, dist):
         xs, ys = xs.to(torch.float64), ys.to(torch.float64)
     xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
     nlines, nverts = int(max(xs.shape[0], ys.shape[0])), int(xs.shape[1])
-    layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), 1)
+    layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), int(getattr(frame, "plot_start", True)))
     return x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout)
 
 
@@ -297,6 +297,8 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
     """bypixel for the line glyphs (LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1X/YConstant)."""
     needed, frame, schema = _prepare(source, glyph, agg, canvas)
     frame = frame.resident(needed)      # lines are staged whole ([nlines, nverts] matrices)
+    if dist is not None and glyph.value_per_vertex:
+        frame, frame.plot_start = dist.carry_last_row(frame, needed)     # row shards of one long line (dask.py:244-266)
     line_width = float(glyph._line_width)
     if line_width == 0:
         return _lines_plan(frame, needed, schema, canvas, glyph, agg, dist)
@@ -479,6 +481,8 @@ def areas(source, canvas, glyph, agg, dist=None):
     """bypixel for the area glyphs (Canvas.area, core.py:480-709)."""
     needed, frame, schema = _prepare(source, glyph, agg, canvas)
     frame = frame.resident(needed)
+    if dist is not None and glyph.value_per_vertex:
+        frame, frame.plot_start = dist.carry_last_row(frame, needed)     # row shards of one long curve (dask.py:244-266)
     device = frame.device
     with torch.cuda.device(device):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
@@ -497,7 +501,7 @@ def areas(source, canvas, glyph, agg, dist=None):
         xs, ys0, ys1, (xls, yls) = glyph.vertices(frame)
         xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
         nlines, nverts = int(max(xs.shape[0], ys0.shape[0])), int(xs.shape[1])
-        layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), 1)
+        layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), int(getattr(frame, "plot_start", True)))
         reds, results, labels = _accumulate_and_finalize(
             frame, frame, needed, schema, view, canvas, glyph, agg, dist, _launch_areas,
             ctx_extra={"area_vertices": (xs, ys0, ys1, xy_dtype, nlines, nverts, layout)})

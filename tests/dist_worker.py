@@ -74,6 +74,41 @@ def main():
                 ok = ok and np.array_equal(got, want, equal_nan=got.dtype.kind == "f")
             if not ok:
                 bad.append(f"lines {name} lw={lw}")
+    # LineAxis0 / AreaToZeroAxis0: ONE long curve sharded by rows; each rank receives the previous shard's last vertex
+    # (data_libraries/dask.py:244-266) so that the segment across the shard boundary is drawn exactly once
+    nv0 = 4001
+    x0 = np.cumsum(rng.normal(0, 0.01, nv0)).astype(np.float32) + np.float32(0.5)
+    y0 = np.cumsum(rng.normal(0, 0.01, nv0)).astype(np.float32) + np.float32(0.5)
+    y0[rng.integers(0, nv0, 15)] = np.nan
+    y0[nv0 // 2 - 1] = np.nan                      # a break right at the 2-rank shard boundary
+    v0 = rng.normal(size=nv0)
+    alo, ahi = shard_bounds(nv0, rank, world)
+    aframe = ds.DeviceFrame({"x": torch.from_numpy(x0[alo:ahi].copy()).cuda(), "y": torch.from_numpy(y0[alo:ahi].copy()).cuda(),
+                             "val": torch.from_numpy(v0[alo:ahi].copy()).cuda()}, row_offset=alo)
+    aframe.sharded = True
+    for name, agg, lw in [("any", ds.any(), 0), ("count", ds.count(), 0), ("sum", ds.sum("val"), 0), ("max", ds.max("val"), 0),
+                          ("max", ds.max("val"), 2.0)]:
+        got = lcvs.line(aframe, "x", "y", agg=agg, line_width=lw).data
+        if rank == 0:
+            want = ora.lines(x0[None], y0[None], lview, name, None if name in ("any", "count") else v0, lw, per_vertex=True)
+            ok = got.dtype == want.dtype and np.array_equal(np.isnan(got.astype("f8")), np.isnan(want.astype("f8")))
+            ok = ok and np.allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True)
+            if lw == 0 and name != "sum":
+                ok = ok and np.array_equal(got, want, equal_nan=got.dtype.kind == "f")
+            if not ok:
+                bad.append(f"line axis0 sharded {name} lw={lw}")
+    for name, agg in [("any", ds.any()), ("count", ds.count()), ("max", ds.max("val"))]:
+        got = lcvs.area(aframe, "x", "y", agg=agg).data
+        if rank == 0:
+            want = ora.areas(x0[None], y0[None], lview, None, name, None if name in ("any", "count") else v0, per_vertex=True)
+            if not (got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f")):
+                bad.append(f"area axis0 sharded {name}")
+    got = lcvs.line(aframe, "x", "y", agg=ds.first("val")).data      # global row ids survive the prepended vertex
+    if rank == 0:
+        full = ds.DeviceFrame({"x": torch.from_numpy(x0).cuda(), "y": torch.from_numpy(y0).cuda(), "val": torch.from_numpy(v0).cuda()})
+    whole = lcvs.line(full, "x", "y", agg=ds.first("val")).data if rank == 0 else None
+    if rank == 0 and not np.array_equal(got, whole, equal_nan=True):
+        bad.append("line axis0 sharded first")
     # auto-ranging across shards
     got = ds.Canvas(31, 17).points(frame, "x", "y").data
     if rank == 0:

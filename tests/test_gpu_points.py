@@ -336,7 +336,11 @@ def test_arrow_and_dict_sources_match_pandas(ds):
         want = cvs.points(df, "x", "y", agg).data
         for src in (table, host, dev):
             got = cvs.points(src, "x", "y", agg).data
-            assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), (type(src), agg)
+            assert got.dtype == want.dtype, (type(src), agg)
+            if isinstance(agg, ds.mean):      # f64 atomic adds: the summation order differs from run to run
+                np.testing.assert_allclose(got, want, rtol=1e-12, equal_nan=True)
+            else:
+                assert np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), (type(src), agg)
     want = cvs.points(df, "x", "y", ds.by("cat", ds.count()))
     got = cvs.points(table, "x", "y", ds.by("cat", ds.count()))
     assert np.array_equal(got.data, want.data) and list(got.coords["cat"]) == list(want.coords["cat"])
