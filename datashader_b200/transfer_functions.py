@@ -19,7 +19,7 @@ from . import _lib
 from .palette import Sets1to3, rgb
 from .xr_compat import DataArray
 
-__all__ = ["shade", "Image"]
+__all__ = ["shade", "Image", "spread", "dynspread", "stack", "set_background"]
 
 _HOW = {"eq_hist": 0, "log": 1, "cbrt": 2, "linear": 3}
 _NBINS = 256 * 256
@@ -263,3 +263,194 @@ def shade(agg, cmap=["lightblue", "darkblue"], color_key=Sets1to3, how='eq_hist'
     elif ndim == 3:
         return _colorize(agg, color_key, how, alpha, min_alpha, name, color_baseline, rescale_discrete_levels, device)
     raise ValueError("agg must use 2D or 3D coordinates")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Post-shade image operations (transfer_functions/__init__.py:115-145, 748-1051; composite.py): the step after
+# shade() in every real pipeline (pipeline.py:43-72 defaults to spread_fn=tf.dynspread).
+# ---------------------------------------------------------------------------------------------------------------
+_IMAGE_OPS = {"over": 0, "add": 1, "saturate": 2, "source": 3}
+_ARRAY_OPS = {"add": 0, "max": 1, "min": 2, "source": 3}
+_NP_DSB = {"float32": _lib.F32, "float64": _lib.F64, "int32": _lib.I32, "int64": _lib.I64, "uint32": _lib.U32}
+
+
+def _validate_operator(how, is_image):
+    """composite.py:18-29"""
+    if is_image:
+        if how not in _IMAGE_OPS:
+            image_repr = ', '.join(repr(el) for el in _IMAGE_OPS)
+            raise ValueError(f'Operator {how!r} not one of the supported image operators: {image_repr}')
+    elif how not in _ARRAY_OPS:
+        array_repr = ', '.join(repr(el) for el in _ARRAY_OPS)
+        raise ValueError(f'Operator {how!r} not one of the supported array operators: {array_repr}')
+
+
+def _np_dtype_of(data):
+    return np.dtype(str(data.dtype).replace("torch.", ""))
+
+
+def _result_like(data, out_t, np_dtype):
+    """Same residency as the input: torch in -> torch out (device results), numpy in -> numpy out."""
+    if isinstance(data, torch.Tensor):
+        return out_t
+    a = out_t.cpu().numpy()
+    return a.view(np_dtype) if a.dtype != np_dtype else a
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _square_mask(px):
+    """transfer_functions/__init__.py:918-922"""
+    w = 2 * int(px) + 1
+    return np.ones((w, w), dtype='bool')
+
+
+def _circle_mask(r):
+    """transfer_functions/__init__.py:925-928"""
+    x = np.arange(-r, r + 1, dtype='i4')
+    return np.where(np.sqrt(x**2 + x[:, None]**2) <= r+0.5, True, False)
+
+
+_mask_lookup = {'square': _square_mask, 'circle': _circle_mask}
+
+
+def set_background(img, color=None, name=None):
+    """Return a new image, with the background set to `color` (transfer_functions/__init__.py:748-768)."""
+    if not isinstance(img, Image):
+        raise TypeError(f"Expected `Image`, got: `{type(img)}`")
+    name = img.name if name is None else name
+    if color is None:
+        return img
+    background = int(np.uint8(rgb(color) + (255,)).view('uint32')[0])
+    dev = _device()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        src = _device_tensor(img.data, dev).contiguous()
+        out = torch.empty_like(src)
+        _lib.check(L.dsb_composite(src.data_ptr(), None, background, src.numel(), _IMAGE_OPS["over"], out.data_ptr(),
+                                   torch.cuda.current_stream(dev).cuda_stream), "dsb_composite")
+        data = _result_like(img.data, out, np.dtype("uint32"))
+    return Image(data, coords=img.coords, dims=img.dims, name=name)
+
+
+def stack(*imgs, **kwargs):
+    """Combine images together, overlaying later images onto earlier ones (transfer_functions/__init__.py:115-145)."""
+    if not imgs:
+        raise ValueError("No images passed in")
+    shapes = []
+    for i in imgs:
+        if not isinstance(i, Image):
+            raise TypeError(f"Expected `Image`, got: `{type(i)}`")
+        elif not shapes:
+            shapes.append(tuple(i.shape))
+        elif shapes and tuple(i.shape) not in shapes:
+            raise ValueError("The stacked images must have the same shape.")
+    name = kwargs.get('name', None)
+    how = kwargs.get('how', 'over')
+    if how not in _IMAGE_OPS:
+        raise KeyError(how)
+    if len(imgs) == 1:
+        return imgs[0]
+    dev = _device()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        s = torch.cuda.current_stream(dev).cuda_stream
+        acc = _device_tensor(imgs[0].data, dev).contiguous()
+        for nxt in imgs[1:]:                          # reduce(flip(op)): op(next, accumulated)
+            src = _device_tensor(nxt.data, dev).contiguous()
+            out = torch.empty_like(acc)
+            _lib.check(L.dsb_composite(src.data_ptr(), acc.data_ptr(), 0, acc.numel(), _IMAGE_OPS[how], out.data_ptr(), s),
+                       "dsb_composite")
+            acc = out
+        data = _result_like(imgs[0].data, acc, np.dtype("uint32"))
+    return Image(data, coords=imgs[0].coords, dims=imgs[0].dims, name=name)
+
+
+def spread(img, px=1, shape='circle', how=None, mask=None, name=None):
+    """Spread pixels in an image or aggregate (transfer_functions/__init__.py:771-822): each pixel is expanded `px` pixels
+    on all sides according to `shape` ('circle' or 'square') or an explicit odd square `mask`, merging with the
+    compositing operator `how` ('over' for Images, 'add' otherwise by default)."""
+    if not isinstance(img, DataArray):
+        raise TypeError(f"Expected `xr.DataArray`, got: `{type(img)}`")
+    is_image = isinstance(img, Image)
+    name = img.name if name is None else name
+    if mask is None:
+        if not isinstance(px, int) or px < 0:
+            raise ValueError("``px`` must be an integer >= 0")
+        if px == 0:
+            return img
+        mask = _mask_lookup[shape](px)
+    elif not (isinstance(mask, np.ndarray) and mask.ndim == 2 and
+              mask.shape[0] == mask.shape[1] and mask.shape[0] % 2 == 1):
+        raise ValueError("mask must be a square 2 dimensional ndarray with "
+                         "odd dimensions.")
+    if how is None:
+        how = 'over' if is_image else 'add'
+    _validate_operator(how, is_image)
+    np_dtype = _np_dtype_of(img.data)
+    if not is_image and np_dtype.name not in _NP_DSB:
+        raise TypeError(f"spread: unsupported aggregate dtype {np_dtype}")
+    dev = _device()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        s = torch.cuda.current_stream(dev).cuda_stream
+        src = _device_tensor(img.data, dev).contiguous()
+        m = torch.from_numpy(np.ascontiguousarray(mask != 0).view(np.uint8)).to(dev)
+        out = torch.empty_like(src)
+        H, W = int(src.shape[0]), int(src.shape[1])
+        if is_image:
+            _lib.check(L.dsb_spread_image(src.data_ptr(), H, W, m.data_ptr(), int(mask.shape[0]), _IMAGE_OPS[how], out.data_ptr(), s),
+                       "dsb_spread_image")
+        else:
+            ncat = int(src.shape[2]) if src.ndim == 3 else 1
+            _lib.check(L.dsb_spread_array(src.data_ptr(), _NP_DSB[np_dtype.name], H, W, ncat, m.data_ptr(), int(mask.shape[0]),
+                                          _ARRAY_OPS[how], out.data_ptr(), s), "dsb_spread_array")
+        data = _result_like(img.data, out, np_dtype)
+    return img.__class__(data, dims=img.dims, coords=img.coords, name=name)
+
+
+def _density(data, is_image, px):
+    """_rgb_density / _array_density (transfer_functions/__init__.py:1004-1051) on the device."""
+    dev = _device()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        src = _device_tensor(data, dev).contiguous()
+        out2 = torch.zeros(2, dtype=torch.int64, device=dev)
+        np_dtype = _np_dtype_of(src) if not isinstance(data, np.ndarray) else data.dtype
+        _lib.check(L.dsb_density(src.data_ptr(), _NP_DSB[np.dtype(np_dtype).name], int(is_image), int(src.shape[0]), int(src.shape[1]),
+                                 int(px), out2.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "dsb_density")
+        cnt, has = (int(v) for v in out2.tolist())
+    return has / cnt if cnt else np.inf
+
+
+def dynspread(img, threshold=0.5, max_px=3, shape='circle', how=None, name=None):
+    """Spread pixels dynamically based on the image density (transfer_functions/__init__.py:931-1001): spreading starts
+    at 1 pixel and stops when the fraction of non-empty pixels with a non-empty neighbour exceeds `threshold`, or at
+    `max_px`."""
+    is_image = isinstance(img, Image)
+    if not 0 <= threshold <= 1:
+        raise ValueError("threshold must be in [0, 1]")
+    if not isinstance(max_px, int) or max_px < 0:
+        raise ValueError("max_px must be >= 0")
+    np_dtype = _np_dtype_of(img.data)
+    float_type = np_dtype in (np.float32, np.float64)
+    flat = None
+    px_ = 0
+    for px in range(1, max_px + 1):
+        px_ = px
+        if is_image or len(img.shape) == 2:
+            density = _density(img.data, is_image, px * 2)
+        else:
+            if flat is None:           # number of non-empty categories per pixel
+                d = _device_tensor(img.data, _device())
+                flat = ((~torch.isnan(d)) if float_type else (d != 0)).sum(dim=2).to(torch.int32)
+            density = _density(flat, False, px * 2)
+        if density > threshold:
+            px_ = px_ - 1
+            break
+    if px_ >= 1:
+        return spread(img, px_, shape=shape, how=how, name=name)
+    else:
+        return img

@@ -236,6 +236,27 @@ int dsb_shade_map2d(const double* data, int64_t npix, int32_t how, const double*
                     const double* span, int32_t ncolors, const double* cspan, const double* rs, const double* gs,
                     const double* bs, double min_alpha, double alpha, uint32_t* out, void* stream);
 
+/* ---- post-shade image operations ------------------------------------------------------------------- */
+/* Binary compositing operators on uint32 RGBA (datashader/composite.py:72-125) and on plain arrays (:150-168). */
+typedef enum { DSB_COMP_OVER = 0, DSB_COMP_ADD = 1, DSB_COMP_SATURATE = 2, DSB_COMP_SOURCE = 3 } dsb_composite_op;
+typedef enum { DSB_ARR_ADD = 0, DSB_ARR_MAX = 1, DSB_ARR_MIN = 2, DSB_ARR_SOURCE = 3 } dsb_array_op;
+/* out[i] = op(src[i], dst ? dst[i] : dst_scalar): tf.stack (transfer_functions/__init__.py:139-144) and
+ * tf.set_background (:766, over(img, background)). */
+int dsb_composite(const uint32_t* src, const uint32_t* dst, uint32_t dst_scalar, int64_t n, int32_t how, uint32_t* out,
+                  void* stream);
+/* tf.spread of an Image (transfer_functions/__init__.py:771-915): mask is [w, w] u8, w odd.  Each output pixel folds
+ * its sources in the reference's raster order, so non-commutative operators give bit-identical results. */
+int dsb_spread_image(const uint32_t* img, int32_t H, int32_t W, const uint8_t* mask, int32_t w, int32_t how, uint32_t* out,
+                     void* stream);
+/* tf.spread of an aggregate [H, W] or [H, W, C] (every category layer on its own): the float kernel (NaN = empty)
+ * for f32 / f64, the int kernel for i32 / i64, the zero-ignoring kernel for u32 (:825-877). */
+int dsb_spread_array(const void* arr, int32_t dtype, int32_t H, int32_t W, int32_t C, const uint8_t* mask, int32_t w,
+                     int32_t how, void* out, void* stream);
+/* dynspread's density heuristic (_rgb_density / _array_density, :1004-1051): out2[0] = non-empty pixels, out2[1] =
+ * those with another non-empty pixel within px; density = out2[1] / out2[0] (inf when out2[0] == 0). */
+int dsb_density(const void* arr, int32_t dtype, int32_t is_image, int32_t H, int32_t W, int32_t px, uint64_t* out2,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

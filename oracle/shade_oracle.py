@@ -167,3 +167,171 @@ def shade_2d(data, cmap, how="eq_hist", alpha=255, min_alpha=40, rescale_discret
             a = np.nan_to_num(np.interp(data, span, aspan, left=0, right=255), copy=False).astype(np.uint8)
     rgba = np.dstack([r, g, b, a])
     return rgba.view(np.uint32).reshape(data.shape)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Post-shade image operations: composite operators, spread, dynspread's density heuristic, stack, set_background.
+# TEST INFRASTRUCTURE ONLY - restates datashader/composite.py and transfer_functions/__init__.py:115-145, 748-1060.
+# Pinned by tests/golden/spread.npz (generated from the reference's own kernels) in tests/test_shade_oracle.py.
+# ---------------------------------------------------------------------------------------------------------------
+def _extract_scaled(x):
+    """composite.py:32-38"""
+    x = np.asarray(x, dtype=np.uint32)
+    return tuple(((x >> s) & 255).astype(np.float64) / 255 for s in (0, 8, 16, 24))
+
+
+def _combine_scaled(r, g, b, a):
+    """composite.py:43-49: truncating uint32 casts, clamped at 255"""
+    with np.errstate(invalid="ignore"):
+        ch = [np.minimum(255, (np.nan_to_num(c) * 255).astype(np.uint32)) for c in (r, g, b, a)]
+    return (ch[3] << 24) | (ch[2] << 16) | (ch[1] << 8) | ch[0]
+
+
+def composite(how, src, dst):
+    """The image operators of composite.py:72-125 on uint32 RGBA arrays (broadcasting): op(src, dst)."""
+    src, dst = np.broadcast_arrays(np.asarray(src, np.uint32), np.asarray(dst, np.uint32))
+    if how == "source":
+        return np.where(src & np.uint32(0xff000000), src, dst).astype(np.uint32)
+    sr, sg, sb, sa = _extract_scaled(src)
+    dr, dg, db, da = _extract_scaled(dst)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if how == "over":
+            factor = 1 - sa
+            a = sa + da * factor
+            r, g, b = ((s * sa + d * da * factor) / a for s, d in ((sr, dr), (sg, dg), (sb, db)))
+        elif how == "add":
+            a = np.minimum(1, sa + da)
+            r, g, b = ((s * sa + d * da) / a for s, d in ((sr, dr), (sg, dg), (sb, db)))
+        elif how == "saturate":
+            a = np.minimum(1, sa + da)
+            factor = np.minimum(sa, 1 - da)
+            r, g, b = ((factor * s + d * da) / a for s, d in ((sr, dr), (sg, dg), (sb, db)))
+        else:
+            raise ValueError(how)
+    out = _combine_scaled(r, g, b, a)
+    return np.where(a == 0, np.uint32(0), out).astype(np.uint32)
+
+
+def circle_mask(r):
+    """transfer_functions/__init__.py:925-928"""
+    x = np.arange(-r, r + 1, dtype="i4")
+    return np.where(np.sqrt(x ** 2 + x[:, None] ** 2) <= r + 0.5, True, False)
+
+
+def square_mask(px):
+    """transfer_functions/__init__.py:918-922"""
+    w = 2 * int(px) + 1
+    return np.ones((w, w), dtype=bool)
+
+
+def _arr_op(how, el, out):
+    """composite.py:150-168 (scalars)"""
+    if how == "add":
+        return el + out
+    if how == "max":
+        return max(el, out)
+    if how == "min":
+        return min(el, out)
+    if how == "source":
+        return el if el else out
+    raise ValueError(how)
+
+
+def spread_plane(arr, mask, how, is_image):
+    """One 2-D layer of tf.spread (transfer_functions/__init__.py:771-915): the reference's serial scatter, pixel by
+    pixel in raster order, through the image / float / int kernel that spread() would pick.  Small inputs only."""
+    arr = np.asarray(arr)
+    w = mask.shape[0]
+    extra = w // 2
+    M, N = arr.shape
+    float_type = arr.dtype in (np.float32, np.float64)
+    out = np.full((M + 2 * extra, N + 2 * extra), np.nan if float_type else 0, dtype=arr.dtype)
+    ignore_zeros = (not is_image) and (not float_type) and arr.dtype == np.uint32
+    for y in range(M):
+        for x in range(N):
+            el = arr[y, x]
+            if is_image:                                     # _build_spread_kernel :880-915
+                if not ((int(el) >> 24) & 255):
+                    continue
+            for i in range(w):
+                for j in range(w):
+                    if not mask[i, j]:
+                        continue
+                    o = out[i + y, j + x]
+                    if is_image:
+                        res = el if o == 0 else composite(how, el, o)[()]
+                    elif float_type:                         # _build_float_kernel :852-877
+                        if np.isnan(el):
+                            res = o
+                        elif np.isnan(o):
+                            res = el
+                        else:
+                            res = _arr_op(how, el, o)
+                    else:                                    # _build_int_kernel :825-849
+                        if ignore_zeros and el == 0:
+                            res = o
+                        elif ignore_zeros and o == 0:
+                            res = el
+                        else:
+                            res = _arr_op(how, el, o)
+                    out[i + y, j + x] = res
+    return out[extra:extra + M, extra:extra + N].copy()
+
+
+def spread(arr, px=1, shape="circle", how=None, is_image=False, mask=None):
+    """tf.spread on a 2-D or 3-D ([H, W, C], per category plane) array."""
+    arr = np.asarray(arr)
+    if mask is None:
+        if px == 0:
+            return arr
+        mask = circle_mask(px) if shape == "circle" else square_mask(px)
+    how = how or ("over" if is_image else "add")
+    if arr.ndim == 2:
+        return spread_plane(arr, mask, how, is_image)
+    return np.dstack([spread_plane(arr[:, :, c], mask, how, is_image) for c in range(arr.shape[2])])
+
+
+def density(arr, px, is_image):
+    """_rgb_density / _array_density (transfer_functions/__init__.py:1004-1051)."""
+    arr = np.asarray(arr)
+    if is_image:
+        occ = ((arr >> 24) & 255) != 0
+    elif arr.dtype in (np.float32, np.float64):
+        occ = ~np.isnan(arr)
+    else:
+        occ = arr != 0
+    M, N = occ.shape
+    cnt = has = 0
+    for y in range(M):
+        for x in range(N):
+            if occ[y, x]:
+                cnt += 1
+                if occ[max(0, y - px):min(y + px + 1, M), max(0, x - px):min(x + px + 1, N)].sum() > 1:
+                    has += 1
+    return has / cnt if cnt else np.inf
+
+
+def dynspread_px(arr, threshold=0.5, max_px=3, is_image=False):
+    """The radius dynspread settles on (transfer_functions/__init__.py:972-994)."""
+    arr = np.asarray(arr)
+    float_type = arr.dtype in (np.float32, np.float64)
+    px_ = 0
+    for px in range(1, max_px + 1):
+        px_ = px
+        if is_image or arr.ndim == 2:
+            d = density(arr, px * 2, is_image)
+        else:
+            masked = ~np.isnan(arr) if float_type else (arr != 0)
+            d = density(np.sum(masked, axis=2, dtype="uint32"), px * 2, False)
+        if d > threshold:
+            px_ -= 1
+            break
+    return px_
+
+
+def stack(imgs, how="over"):
+    """tf.stack: later images over earlier ones, reduce(flip(op)) (transfer_functions/__init__.py:139-144)."""
+    out = np.asarray(imgs[0], np.uint32)
+    for nxt in imgs[1:]:
+        out = composite(how, nxt, out)
+    return out

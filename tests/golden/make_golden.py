@@ -372,6 +372,68 @@ def lines_aa2_cases():
     return out
 
 
+def spread_cases():
+    """Post-shade image ops straight from the reference's kernels (composite.py; transfer_functions/__init__.py:748-1051)."""
+    from datashader import composite as comp
+    from datashader import transfer_functions as tf
+    out = {}
+    rng = np.random.default_rng(31)
+    H, W = 23, 31
+    img = rng.integers(0, 2 ** 32, (H, W), dtype=np.uint64).astype(np.uint32)
+    img[rng.random((H, W)) < 0.6] = 0
+    img[2, 3] = 0x00ffffff                       # colour but alpha 0
+    img2 = rng.integers(0, 2 ** 32, (H, W), dtype=np.uint64).astype(np.uint32)
+    img2[rng.random((H, W)) < 0.4] = 0
+    out["img"], out["img2"] = img, img2
+    for how in ("over", "add", "saturate", "source"):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out[f"comp_{how}"] = comp.composite_op_lookup[how](img, img2)
+            out[f"comp_bg_{how}"] = comp.composite_op_lookup[how](img, np.uint32(0xff204060))
+    f64 = rng.normal(size=(H, W))
+    f64[rng.random((H, W)) < 0.7] = np.nan
+    f32 = f64.astype(np.float32)
+    i32 = rng.integers(-5, 9, (H, W)).astype(np.int32)
+    i32[rng.random((H, W)) < 0.7] = 0
+    u32 = rng.integers(0, 9, (H, W)).astype(np.uint32)
+    u32[rng.random((H, W)) < 0.7] = 0
+    cat = rng.integers(0, 5, (H, W, 3)).astype(np.uint32)
+    cat[rng.random((H, W, 3)) < 0.8] = 0
+    out.update(f64=f64, f32=f32, i32=i32, u32=u32, cat=cat)
+    masks = {"c1": tf._circle_mask(1), "c2": tf._circle_mask(2), "c3": tf._circle_mask(3), "s1": tf._square_mask(1), "s2": tf._square_mask(2)}
+    for mname, mask in masks.items():
+        out[f"mask_{mname}"] = mask
+        w = mask.shape[0]
+        extra = w // 2
+
+        def run(kernel, layer, fill):
+            buf = np.full((layer.shape[0] + 2 * extra, layer.shape[1] + 2 * extra), fill, dtype=layer.dtype)
+            kernel(layer, mask, buf)
+            return buf[extra:-extra, extra:-extra].copy()
+
+        for how in ("over", "add", "saturate", "source"):
+            if mname in ("c1", "c2", "s1"):
+                out[f"spread_img_{mname}_{how}"] = run(tf._build_spread_kernel(how, True), img, 0)
+        for how in ("add", "max", "min", "source"):
+            if mname in ("c1", "c3", "s2"):
+                out[f"spread_f64_{mname}_{how}"] = run(tf._build_float_kernel(how, w), f64, np.nan)
+                out[f"spread_f32_{mname}_{how}"] = run(tf._build_float_kernel(how, w), f32, np.nan)
+                out[f"spread_i32_{mname}_{how}"] = run(tf._build_int_kernel(how, w, False), i32, 0)
+                out[f"spread_u32_{mname}_{how}"] = run(tf._build_int_kernel(how, w, True), u32, 0)
+        if mname == "c2":
+            out["spread_cat_c2_add"] = np.dstack([run(tf._build_int_kernel("add", w, True), np.ascontiguousarray(cat[:, :, c]), 0)
+                                                  for c in range(3)])
+    for px in (1, 2, 4, 6):
+        out[f"density_img_{px}"] = np.float64(tf._rgb_density(img, px))
+        out[f"density_f64_{px}"] = np.float64(tf._array_density(f64, True, px))
+        out[f"density_u32_{px}"] = np.float64(tf._array_density(u32, False, px))
+    sparse = np.zeros((40, 50), np.uint32)
+    sparse[rng.integers(0, 40, 25), rng.integers(0, 50, 25)] = 0xff0000ff
+    out["sparse"] = sparse
+    for px in (2, 4, 6):
+        out[f"density_sparse_{px}"] = np.float64(tf._rgb_density(sparse, px))
+    return out
+
+
 def area_cases():
     """Canvas.area for the ten non-ragged layouts (core.py:480-709, glyphs/area.py)."""
     out = {}
@@ -439,6 +501,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
         print("lines_aa2.npz", os.path.getsize(os.path.join(HERE, "lines_aa2.npz")) // 1024, "KiB")
         return
+    if "--spread-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
+        print("spread.npz", os.path.getsize(os.path.join(HERE, "spread.npz")) // 1024, "KiB")
+        return
     if "--areas-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
         print("areas.npz", os.path.getsize(os.path.join(HERE, "areas.npz")) // 1024, "KiB")
@@ -460,6 +526,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
     np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
     np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
+    np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())

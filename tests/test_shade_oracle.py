@@ -56,3 +56,29 @@ def test_reference_literal_tables():
     np.testing.assert_array_equal(so.shade_2d(a, cmap, how="linear"), sol_linear)
     np.testing.assert_array_equal(so.shade_2d(a, cmap, how="log"), sol_log)
     np.testing.assert_array_equal(so.shade_2d(a, cmap, how="cbrt"), sol_cbrt)
+
+
+def test_post_shade_ops_golden():
+    """composite operators, spread (image / float / int / uint32 kernels), density: oracle vs the reference's kernels."""
+    g = load("spread.npz")
+    img, img2 = g["img"], g["img2"]
+    for how in ("over", "add", "saturate", "source"):
+        np.testing.assert_array_equal(so.composite(how, img, img2), g[f"comp_{how}"], err_msg=how)
+        np.testing.assert_array_equal(so.composite(how, img, np.uint32(0xff204060)), g[f"comp_bg_{how}"], err_msg=how)
+    np.testing.assert_array_equal(so.circle_mask(2), g["mask_c2"])
+    np.testing.assert_array_equal(so.square_mask(2), g["mask_s2"])
+    for key in g.files:
+        if not key.startswith("spread_"):
+            continue
+        _, kind, mname, how = key.split("_")
+        mask = g[f"mask_{mname}"]
+        src = {"img": img, "f64": g["f64"], "f32": g["f32"], "i32": g["i32"], "u32": g["u32"], "cat": g["cat"]}[kind]
+        got = so.spread(src, how=how, is_image=(kind == "img"), mask=mask)
+        assert got.dtype == g[key].dtype, key
+        np.testing.assert_array_equal(got, g[key], err_msg=key)
+    for px in (1, 2, 4, 6):
+        assert so.density(img, px, True) == float(g[f"density_img_{px}"])
+        assert so.density(g["f64"], px, False) == float(g[f"density_f64_{px}"])
+        assert so.density(g["u32"], px, False) == float(g[f"density_u32_{px}"])
+    for px in (2, 4, 6):
+        assert so.density(g["sparse"], px, True) == float(g[f"density_sparse_{px}"])
