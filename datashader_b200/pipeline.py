@@ -134,7 +134,7 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
             priv = [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_COUNT] or \
                    [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_ANY and n < (1 << 32)]
             ncell = int(np.prod(ctx.shape))
-            if priv and ncell <= 786_432:
+            if priv and ncell <= 954_000:      # 226 KB of 2-bit fields / 0.97; beyond, dsb_points_priv returns UNSUPPORTED
                 scratch = getattr(ctx, "_priv_scratch", None)
                 if scratch is None:
                     scratch = ctx._priv_scratch = torch.empty(ncell + 1, dtype=torch.int32, device=x.device)
