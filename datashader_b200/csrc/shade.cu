@@ -258,11 +258,14 @@ __device__ __forceinline__ double np_interp(double x, const double* __restrict__
 }
 
 // a_scaled for one pixel: eq_hist -> CDF lookup, otherwise the analytic transfer functions
+// DSB_HOW_F32: the canvas is float32, so numpy evaluates log1p / ** (1/3.) in float32 (the python-float exponent is
+// cast to float32); the correctly rounded float32 result is obtained by rounding the float64 function value.
 __device__ __forceinline__ double transfer(int how, double d, const double* xp, const double* cdf, int L) {
-  switch (how) {
+  const bool f32 = (how & DSB_HOW_F32) != 0;
+  switch (how & 0xff) {
     case DSB_HOW_EQ_HIST: return np_interp(d, xp, cdf, L, cdf[0], cdf[L - 1]);
-    case DSB_HOW_LOG: return log1p(d);
-    case DSB_HOW_CBRT: return pow(d, 1.0 / 3.0);
+    case DSB_HOW_LOG: return f32 ? (double)(float)log1p(d) : log1p(d);
+    case DSB_HOW_CBRT: return f32 ? (double)(float)pow(d, (double)(float)(1.0 / 3.0)) : pow(d, 1.0 / 3.0);
     default: return d;
   }
 }
@@ -315,6 +318,8 @@ struct CatColorArgs {
   int how;
   const double* xp; const double* cdf; const int* meta; const double* span;
   double min_alpha, alpha;
+  int clip_mode;             // explicit span (:507-514): 0 none, 1 the totals became float64 (zeros masked), 2 stay uint64
+  double clip_lo, clip_hi;
   uint32_t* out;
 };
 
@@ -344,7 +349,17 @@ __global__ void __launch_bounds__(256) k_cat_colorize(const CatColorArgs a) {
     unsigned long long t = a.total[i];
     uint32_t al = 0;
     if (!(a.mask_zero && t == 0)) {
-      double d = s64((double)t, (double)a.offset);
+      double d;
+      if (a.clip_mode == 1) {            // masked_clip_2d on float64 totals, then total - offset
+        double tv = (double)t;
+        if (tv < a.clip_lo) tv = a.clip_lo; else if (tv > a.clip_hi) tv = a.clip_hi;
+        d = s64(tv, (double)a.offset);
+      } else if (a.clip_mode == 2) {     // on uint64 totals: the bound is truncated to an integer when it is stored
+        if ((double)t < a.clip_lo) t = (unsigned long long)a.clip_lo; else if ((double)t > a.clip_hi) t = (unsigned long long)a.clip_hi;
+        d = (double)(t - a.offset);
+      } else {
+        d = s64((double)t, (double)a.offset);
+      }
       al = alpha_u8(transfer(a.how, d, a.xp, a.cdf, L), lo, hi, a.min_alpha, a.alpha);
     }
     a.out[i] = rgb | (al << 24);
@@ -355,7 +370,7 @@ extern "C" int dsb_shade_cat_colorize(const uint32_t* counts, const uint64_t* to
                                       const float* rgb, uint32_t fallback_rgb, uint32_t baseline, uint64_t offset,
                                       int32_t mask_zero, int32_t how, const double* xp, const double* cdf,
                                       const int32_t* meta, const double* span, double min_alpha, double alpha,
-                                      uint32_t* out, void* stream) {
+                                      int32_t clip_mode, double clip_lo, double clip_hi, uint32_t* out, void* stream) {
   if (!counts || !total || !rgb || !span || !out || ncat < 1) { dsb_set_error("dsb_shade_cat_colorize: bad arguments"); return DSB_ERR_ARG; }
   if (how == DSB_HOW_EQ_HIST && (!xp || !cdf || !meta)) { dsb_set_error("dsb_shade_cat_colorize: eq_hist needs xp/cdf/meta"); return DSB_ERR_ARG; }
   if (npix == 0) return DSB_OK;
@@ -363,6 +378,7 @@ extern "C" int dsb_shade_cat_colorize(const uint32_t* counts, const uint64_t* to
   a.counts = counts; a.total = (const unsigned long long*)total; a.npix = npix; a.ncat = ncat; a.rgb = rgb;
   a.fallback_rgb = fallback_rgb; a.baseline = baseline; a.offset = offset; a.mask_zero = mask_zero; a.how = how;
   a.xp = xp; a.cdf = cdf; a.meta = meta; a.span = span; a.min_alpha = min_alpha; a.alpha = alpha; a.out = out;
+  a.clip_mode = clip_mode; a.clip_lo = clip_lo; a.clip_hi = clip_hi;
   k_cat_colorize<<<sgrid(npix, 256), 256, 0, (cudaStream_t)stream>>>(a);
   DSB_CUDA_CHECK_LAUNCH("dsb_shade_cat_colorize");
   return DSB_OK;
@@ -442,7 +458,7 @@ extern "C" int dsb_shade_map2d(const double* data, int64_t npix, int32_t how, co
                                uint32_t* out, void* stream) {
   if (!data || !span || !rs || !gs || !bs || !out || ncolors < 1) { dsb_set_error("dsb_shade_map2d: bad arguments"); return DSB_ERR_ARG; }
   if (ncolors >= 2 && !cspan) { dsb_set_error("dsb_shade_map2d: list cmap needs cspan"); return DSB_ERR_ARG; }
-  if (how == DSB_HOW_EQ_HIST && (!xp || !cdf || !meta)) { dsb_set_error("dsb_shade_map2d: eq_hist needs xp/cdf/meta"); return DSB_ERR_ARG; }
+  if ((how & 0xff) == DSB_HOW_EQ_HIST && (!xp || !cdf || !meta)) { dsb_set_error("dsb_shade_map2d: eq_hist needs xp/cdf/meta"); return DSB_ERR_ARG; }
   if (npix == 0) return DSB_OK;
   MapArgs a;
   a.data = data; a.npix = npix; a.how = how; a.xp = xp; a.cdf = cdf; a.meta = meta; a.span = span; a.ncolors = ncolors;

@@ -31,7 +31,8 @@ _SIGS = {
     "dsb_eqhist_hist_f64": [_p, _i64, _f64, _f64, _f64, _i32, _i32, _p, _p],
     "dsb_eqhist_scan": [_p, _i32, _i32, _f64, _f64, _p, _p, _p, _p],
     "dsb_shade_norm_span": [_i32, _f64, _f64, _p, _p, _p, _i32, _p, _p],
-    "dsb_shade_cat_colorize": [_p, _p, _i64, _i32, _p, _u32, _u32, _u64, _i32, _i32, _p, _p, _p, _p, _f64, _f64, _p, _p],
+    "dsb_shade_cat_colorize": [_p, _p, _i64, _i32, _p, _u32, _u32, _u64, _i32, _i32, _p, _p, _p, _p, _f64, _f64, _i32, _f64, _f64,
+                               _p, _p],
     "dsb_shade_map2d": [_p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _f64, _f64, _p, _p],
 }
 _bound = False
@@ -71,13 +72,14 @@ def _device_tensor(data, device):
     return torch.from_numpy(a).to(device)
 
 
-def _host_transform(how, d):
-    """The reference's analytic transfer functions on a scalar, evaluated with numpy like the reference."""
-    d = np.float64(d)
+def _host_transform(how, d, f32=False):
+    """The reference's analytic transfer functions on a scalar, evaluated with numpy like the reference (in float32
+    for a float32 canvas: `data ** (1/3.)` keeps the array dtype)."""
+    d = np.float32(d) if f32 else np.float64(d)
     if how == "log":
         return float(np.log1p(d))
     if how == "cbrt":
-        return float(d ** (1 / 3.))
+        return float(d ** (np.float32(1 / 3.) if f32 else (1 / 3.)))
     return float(d)
 
 
@@ -103,7 +105,7 @@ def _eq_hist_tables(L, s, kind, values, npix, offset, mask_zero, dmax, integer_m
     return xp, cdf, meta, span
 
 
-def _colorize(agg, color_key, how, alpha, min_alpha, name, color_baseline, rescale_discrete_levels, device):
+def _colorize(agg, color_key, how, alpha, span, min_alpha, name, color_baseline, rescale_discrete_levels, device):
     """3-D categorical path: _colorize (:359-463) + _interpolate_alpha (:466-532)."""
     data = agg.data
     cats = list(np.asarray(agg.coords[agg.dims[-1]]))
@@ -140,36 +142,42 @@ def _colorize(agg, color_key, how, alpha, min_alpha, name, color_baseline, resca
                    "dsb_shade_cat_totals")
         min_entry, min_total, min_nz, max_total = [int(v) & 0xFFFFFFFFFFFFFFFF for v in stats.tolist()]
         baseline = min_entry if color_baseline is None else int(color_baseline)
-        # _interpolate_alpha, span is None (:475-487)
+        # _interpolate_alpha (:475-522)
         mask_zero = min_total == 0
         all_masked = mask_zero and max_total == 0
-        offset = (min_nz if not all_masked else 0) if mask_zero else min_total
-        dmax = max_total - offset if not all_masked else 0
+        clip_mode, clip_lo, clip_hi = 0, 0.0, 0.0
+        if span is None:
+            offset = (min_nz if not all_masked else 0) if mask_zero else min_total
+            dmax = max_total - offset if not all_masked else 0
+        else:       # explicit span: clip the totals, fixed normalisation range (:507-522)
+            offset = int(np.array(span, dtype=np.uint32)[0])
+            clip_mode, clip_lo, clip_hi = (1 if mask_zero else 2), float(span[0]), float(span[1])
+            dmax = span[1] - span[0]
         rgbt = torch.from_numpy(RGB).to(device)
         out = torch.empty(npix, dtype=torch.int32, device=device)
         xp = cdf = meta = None
         if all_masked:
-            span = torch.tensor([0.0, 1.0], dtype=torch.float64, device=device)
+            span_t = torch.tensor([0.0, 1.0], dtype=torch.float64, device=device)
             how_code = 3
         elif how == "eq_hist":
             integer_mode = (not mask_zero) and dmax < _NBINS          # eq_hist :194-196 (totals stay uint64)
-            xp, cdf, meta, span = _eq_hist_tables(L, s, "u64", total, npix, offset, mask_zero, dmax, integer_mode,
+            xp, cdf, meta, span_t = _eq_hist_tables(L, s, "u64", total, npix, offset, mask_zero, dmax, integer_mode,
                                                   rescale_discrete_levels, device)
             how_code = 0
         else:
-            span = torch.tensor([_host_transform(how, 0), _host_transform(how, dmax)], dtype=torch.float64, device=device)
+            span_t = torch.tensor([_host_transform(how, 0), _host_transform(how, dmax)], dtype=torch.float64, device=device)
             how_code = _HOW[how]
         _lib.check(L.dsb_shade_cat_colorize(
             counts.data_ptr(), total.data_ptr(), npix, ncat, rgbt.data_ptr(), fallback, baseline & 0xFFFFFFFF, offset,
             int(mask_zero), how_code, xp.data_ptr() if xp is not None else None, cdf.data_ptr() if cdf is not None else None,
-            meta.data_ptr() if meta is not None else None, span.data_ptr(), float(min_alpha), float(alpha), out.data_ptr(), s),
-            "dsb_shade_cat_colorize")
+            meta.data_ptr() if meta is not None else None, span_t.data_ptr(), float(min_alpha), float(alpha), clip_mode, clip_lo,
+            clip_hi, out.data_ptr(), s), "dsb_shade_cat_colorize")
         img = out.cpu().numpy().view(np.uint32).reshape(H, W)
     return Image(img, dims=agg.dims[:-1], coords=coords, name=name)
 
 
-def _interpolate(agg, cmap, how, alpha, min_alpha, name, rescale_discrete_levels, device):
-    """2-D path: _interpolate (:251-357) with span=None and a list / single-colour cmap."""
+def _interpolate(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_levels, device):
+    """2-D path: _interpolate (:251-357) with a list / single-colour cmap."""
     data = agg.data
     if len(data.shape) != 2:
         raise ValueError("agg must be 2D")
@@ -189,6 +197,7 @@ def _interpolate(agg, cmap, how, alpha, min_alpha, name, rescale_discrete_levels
         s = torch.cuda.current_stream(device).cuda_stream
         t = _device_tensor(data, device).contiguous()
         integer = not t.dtype.is_floating_point
+        is_f32 = t.dtype == torch.float32
         if t.dtype == torch.bool:
             mask = ~t
             v = t.to(torch.int64)
@@ -203,21 +212,36 @@ def _interpolate(agg, cmap, how, alpha, min_alpha, name, rescale_discrete_levels
             mask = torch.isnan(t)
         if bool(mask.all()):
             return Image(np.zeros((H, W), dtype=np.uint32), coords=agg.coords, dims=agg.dims, attrs=agg.attrs, name=name)
-        valid = v[~mask]
-        offset = valid.min()
+        if span is None:
+            valid = v[~mask]
+            offset = valid.min()
+            dmax = float((valid.max() - offset).item())
+        else:
+            # explicit span (:287-289, 310-315): clip the unmasked data to it (the bound is cast to the canvas dtype when
+            # stored, masked_clip_2d), offset = span[0] in the canvas dtype, fixed normalisation range
+            np_dt = np.dtype(np.int8) if t.dtype == torch.bool else _np_dtype_of(t)
+            lo_c, hi_c = (x.item() for x in np.array(span).astype(np_dt)) if np_dt.kind in "iu" else (float(span[0]), float(span[1]))
+            offset = np.array(span, dtype=np_dt)[0].item()
+            below, above = (~mask) & (v < span[0]), (~mask) & ~(v < span[0]) & (v > span[1])
+            v = torch.where(below, torch.full_like(v, lo_c), torch.where(above, torch.full_like(v, hi_c), v))
+            dmax = span[1] - span[0]
         # data -= offset in the canvas dtype (f32 stays f32), then everything downstream is float64
         d = (v - offset).to(torch.float64)
         d = torch.where(mask, torch.full_like(d, float("nan")), d).reshape(-1).contiguous()
-        dmax = float((valid.max() - offset).item())
         xp = cdf = meta = None
         if how == "eq_hist":
             integer_mode = integer and dmax < _NBINS
-            xp, cdf, meta, span = _eq_hist_tables(L, s, "f64", d, npix, 0.0, False, dmax, integer_mode,
+            xp, cdf, meta, span_t = _eq_hist_tables(L, s, "f64", d, npix, 0.0, False, dmax, integer_mode,
                                                   rescale_discrete_levels, device)
-            span_host = span.tolist()
+            span_host = span_t.tolist()
+        elif span is None:
+            # span = nanmin / nanmax of the transformed data: evaluated in the canvas dtype
+            span_host = [_host_transform(how, 0, is_f32), _host_transform(how, dmax, is_f32)]
+            span_t = torch.tensor(span_host, dtype=torch.float64, device=device)
         else:
+            # span = interpolater([0, span[1] - span[0]], 0): a python list, hence float64 (:315)
             span_host = [_host_transform(how, 0), _host_transform(how, dmax)]
-            span = torch.tensor(span_host, dtype=torch.float64, device=device)
+            span_t = torch.tensor(span_host, dtype=torch.float64, device=device)
         if isinstance(cmap, list):
             cols = np.array([rgb(c) for c in cmap], dtype=np.float64)
             ncolors = len(cmap)
@@ -228,8 +252,8 @@ def _interpolate(agg, cmap, how, alpha, min_alpha, name, rescale_discrete_levels
         rs, gs, bs = (torch.from_numpy(np.ascontiguousarray(cols[:, k])).to(device) for k in range(3))
         out = torch.empty(npix, dtype=torch.int32, device=device)
         _lib.check(L.dsb_shade_map2d(
-            d.data_ptr(), npix, _HOW[how], xp.data_ptr() if xp is not None else None,
-            cdf.data_ptr() if cdf is not None else None, meta.data_ptr() if meta is not None else None, span.data_ptr(),
+            d.data_ptr(), npix, _HOW[how] | (0x100 if is_f32 else 0), xp.data_ptr() if xp is not None else None,
+            cdf.data_ptr() if cdf is not None else None, meta.data_ptr() if meta is not None else None, span_t.data_ptr(),
             ncolors, cspan.data_ptr() if cspan is not None else None, rs.data_ptr(), gs.data_ptr(), bs.data_ptr(),
             float(min_alpha), float(alpha), out.data_ptr(), s), "dsb_shade_map2d")
         img = out.cpu().numpy().view(np.uint32).reshape(H, W)
@@ -251,7 +275,7 @@ def shade(agg, cmap=["lightblue", "darkblue"], color_key=Sets1to3, how='eq_hist'
     if span is not None:
         if how == "eq_hist":
             raise ValueError("span is not (yet) valid to use with eq_hist")
-        raise NotImplementedError("span= is not supported by datashader_b200.tf.shade yet")
+        span = (span[0], span[1])
     if rescale_discrete_levels and how != 'eq_hist':
         rescale_discrete_levels = False
     device = agg.data.device if isinstance(agg.data, torch.Tensor) and agg.data.is_cuda else torch.device("cuda")
@@ -259,9 +283,9 @@ def shade(agg, cmap=["lightblue", "darkblue"], color_key=Sets1to3, how='eq_hist'
     if ndim == 2:
         if color_key is not None and isinstance(color_key, dict):
             raise NotImplementedError("discrete colour keys on 2-D aggregates are not supported yet")
-        return _interpolate(agg, cmap, how, alpha, min_alpha, name, rescale_discrete_levels, device)
+        return _interpolate(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_levels, device)
     elif ndim == 3:
-        return _colorize(agg, color_key, how, alpha, min_alpha, name, color_baseline, rescale_discrete_levels, device)
+        return _colorize(agg, color_key, how, alpha, span, min_alpha, name, color_baseline, rescale_discrete_levels, device)
     raise ValueError("agg must use 2D or 3D coordinates")
 
 

@@ -204,6 +204,8 @@ int dsb_areas_plan(const dsb_view* view, const void* xs, const void* ys0, const 
 #define DSB_HOW_LOG 1
 #define DSB_HOW_CBRT 2
 #define DSB_HOW_LINEAR 3
+/* or-ed into `how` of dsb_shade_map2d for float32 canvases: numpy evaluates log1p / ** (1/3.) in float32 there */
+#define DSB_HOW_F32 0x100
 
 /* Per-pixel totals of a categorical count canvas counts[npix, ncat] (u32) and global statistics:
  * stats[0] min entry (colour baseline, __init__.py:398), [1] min total, [2] min non-zero total, [3] max total.
@@ -225,11 +227,12 @@ int dsb_eqhist_scan(const uint32_t* hist, int32_t nbins, int32_t integer_mode, d
 int dsb_shade_norm_span(int32_t how, double dmin, double dmax, const double* xp, const double* cdf, const int32_t* meta,
                         int32_t rescale, double* span, void* stream);
 /* _colorize + _interpolate_alpha (__init__.py:359-532): weighted colour mix over categories (f32) and alpha from the
- * transfer function of the total; out[npix] = r | g<<8 | b<<16 | a<<24. */
+ * transfer function of the total; out[npix] = r | g<<8 | b<<16 | a<<24.  clip_mode != 0: an explicit span - the totals
+ * are clipped to [clip_lo, clip_hi] first (masked_clip_2d, :507-514), as float64 (1: zeros were masked) or uint64 (2). */
 int dsb_shade_cat_colorize(const uint32_t* counts, const uint64_t* total, int64_t npix, int32_t ncat, const float* rgb,
                            uint32_t fallback_rgb, uint32_t baseline, uint64_t offset, int32_t mask_zero, int32_t how,
                            const double* xp, const double* cdf, const int32_t* meta, const double* span, double min_alpha,
-                           double alpha, uint32_t* out, void* stream);
+                           double alpha, int32_t clip_mode, double clip_lo, double clip_hi, uint32_t* out, void* stream);
 /* _interpolate (__init__.py:251-357) for list colormaps (ncolors >= 2) and single colours (ncolors == 1):
  * data[npix] = value - offset as f64 with NaN for masked pixels. */
 int dsb_shade_map2d(const double* data, int64_t npix, int32_t how, const double* xp, const double* cdf, const int32_t* meta,

@@ -57,8 +57,30 @@ def _rescale_discrete_levels(discrete_levels, span):
     return span
 
 
-def interpolate_alpha(data, total, mask, how, alpha, min_alpha, rescale_discrete_levels=False):
-    """_interpolate_alpha with span=None, :466-532"""
+def _masked_clip_2d(data, mask, lower, upper):
+    """_cpu_utils.masked_clip_2d: in place, the bound is cast to the array dtype on assignment"""
+    lo_sel = (~mask) & (data < lower)
+    hi_sel = (~mask) & ~(data < lower) & (data > upper)
+    data[lo_sel] = np.array(lower).astype(data.dtype)
+    data[hi_sel] = np.array(upper).astype(data.dtype)
+
+
+def interpolate_alpha(data, total, mask, how, alpha, min_alpha, rescale_discrete_levels=False, span=None):
+    """_interpolate_alpha, :466-532"""
+    if span is not None:
+        if how == "eq_hist":
+            raise ValueError("span is not (yet) valid to use with eq_hist")
+        with np.errstate(invalid="ignore", divide="ignore"):
+            offset = np.array(span, dtype=data.dtype)[0]
+            if total.dtype.kind == "u" and np.nanmin(total) == 0:
+                mask = mask | (total <= 0)
+                total = np.where(~mask, total, np.nan)
+            total = total.copy()
+            _masked_clip_2d(total, mask, *span)
+            a_scaled = _HOW[how](total - offset, mask)
+            norm_span = np.hstack(_HOW[how]([0, span[1] - span[0]], 0))
+            a_float = np.interp(a_scaled, norm_span, np.array([min_alpha, alpha]), left=0, right=255)
+            return np.nan_to_num(a_float, copy=False).astype(np.uint8)
     with np.errstate(invalid="ignore", divide="ignore"):
         offset = np.nanmin(total)
         if total.dtype.kind == "u" and offset == 0:
@@ -82,7 +104,7 @@ def interpolate_alpha(data, total, mask, how, alpha, min_alpha, rescale_discrete
 
 
 def shade_categorical(data, colors, how="eq_hist", alpha=255, min_alpha=40, color_baseline=None,
-                      rescale_discrete_levels=False):
+                      rescale_discrete_levels=False, span=None):
     """_colorize for a [H, W, C] aggregate, :359-463.  colors: list of (r, g, b)."""
     rs, gs, bs = map(np.array, zip(*colors))
     color_data = np.array(data, order="C", copy=True)
@@ -120,15 +142,15 @@ def shade_categorical(data, colors, how="eq_hist", alpha=255, min_alpha=40, colo
         else:
             total = data.sum(axis=2)
         mask = np.isnan(total) if total.dtype.kind == "f" else np.zeros(total.shape, bool)
-        a = interpolate_alpha(data, total, mask, how, alpha, min_alpha, rescale_discrete_levels)
+        a = interpolate_alpha(data, total, mask, how, alpha, min_alpha, rescale_discrete_levels, span)
     rgba = np.empty((a.shape[0], a.shape[1], 4), dtype=np.uint8)
     rgba[..., :3] = rgb_array
     rgba[..., 3] = a
     return rgba.view(np.uint32).reshape(a.shape)
 
 
-def shade_2d(data, cmap, how="eq_hist", alpha=255, min_alpha=40, rescale_discrete_levels=False):
-    """_interpolate with span=None, :251-357.  cmap: list of (r, g, b) tuples, or one (r, g, b) tuple."""
+def shade_2d(data, cmap, how="eq_hist", alpha=255, min_alpha=40, rescale_discrete_levels=False, span=None):
+    """_interpolate, :251-357.  cmap: list of (r, g, b) tuples, or one (r, g, b) tuple."""
     data = data.copy()
     if np.issubdtype(data.dtype, np.bool_):
         mask = ~data
@@ -139,17 +161,26 @@ def shade_2d(data, cmap, how="eq_hist", alpha=255, min_alpha=40, rescale_discret
         mask = np.isnan(data)
     if mask.all():
         return np.zeros(data.shape, dtype=np.uint32)
-    offset = np.nanmin(data[~mask])
+    if span is None:
+        offset = np.nanmin(data[~mask])
+    else:
+        offset = np.array(span, dtype=data.dtype)[0]
+        _masked_clip_2d(data, mask, *span)
     data -= offset
     with np.errstate(invalid="ignore", divide="ignore"):
         data = _HOW[how](data, mask)
         discrete_levels = None
         if isinstance(data, (list, tuple)):
             data, discrete_levels = data
-        masked_data = np.where(~mask, data, np.nan)
-        span = np.nanmin(masked_data), np.nanmax(masked_data)
-        if rescale_discrete_levels and discrete_levels is not None:
-            span = _rescale_discrete_levels(discrete_levels, span)
+        if span is None:
+            masked_data = np.where(~mask, data, np.nan)
+            span = np.nanmin(masked_data), np.nanmax(masked_data)
+            if rescale_discrete_levels and discrete_levels is not None:
+                span = _rescale_discrete_levels(discrete_levels, span)
+        else:
+            if how == "eq_hist":
+                raise ValueError("span is not (yet) valid to use with eq_hist")
+            span = _HOW[how]([0, span[1] - span[0]], 0)
         if isinstance(cmap, list):
             rspan, gspan, bspan = np.array(list(zip(*cmap)))
             span = np.linspace(span[0], span[1], len(cmap))

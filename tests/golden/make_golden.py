@@ -260,6 +260,35 @@ def shade_cases():
     return out
 
 
+SPAN_CASES_2D = {"u32": [(2, 9), (0.5, 7.5)], "f64": [(-5.0, 12.5)], "f32": [(0.2, 0.7)]}
+SPAN_CASES_CAT = {"poisson5": [(3, 20), (2.5, 15.5)], "dense3": [(40, 90), (30.5, 100.25)]}
+
+
+def shade_span_cases():
+    """tf.shade with an explicit span (clip + fixed normalisation range), on the shade.npz inputs."""
+    import xarray as xr
+    import datashader.transfer_functions as tf
+    g = np.load(os.path.join(HERE, "shade.npz"))
+    out = {}
+    for name, spans in SPAN_CASES_2D.items():
+        data = g[f"d2_{name}_in"]
+        H, Wd = data.shape
+        for k, span in enumerate(spans):
+            for how in ("log", "cbrt", "linear"):
+                agg = xr.DataArray(data.copy(), coords={"y": np.arange(H), "x": np.arange(Wd)}, dims=["y", "x"])
+                out[f"d2_{name}_s{k}_{how}_default"] = np.asarray(tf.shade(agg, how=how, span=span).data)
+                out[f"d2_{name}_s{k}_{how}_single"] = np.asarray(tf.shade(agg, cmap="#3070c0", how=how, span=span, min_alpha=20).data)
+    for name, spans in SPAN_CASES_CAT.items():
+        data = g[f"cat_{name}_in"]
+        H, Wd, C = data.shape
+        for k, span in enumerate(spans):
+            for how in ("log", "cbrt", "linear"):
+                agg = xr.DataArray(data.copy(), coords={"y": np.arange(H), "x": np.arange(Wd), "cat": [f"c{i}" for i in range(C)]},
+                                   dims=["y", "x", "cat"])
+                out[f"cat_{name}_s{k}_{how}"] = np.asarray(tf.shade(agg, how=how, span=span).data)
+    return out
+
+
 def lines_extra_cases():
     """Bresenham lines with the reductions beyond any/count/sum/max/min (row-index based ones included)."""
     out = {}
@@ -505,6 +534,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
         print("spread.npz", os.path.getsize(os.path.join(HERE, "spread.npz")) // 1024, "KiB")
         return
+    if "--shade-span-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "shade_span.npz"), **shade_span_cases())
+        print("shade_span.npz", os.path.getsize(os.path.join(HERE, "shade_span.npz")) // 1024, "KiB")
+        return
     if "--areas-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
         print("areas.npz", os.path.getsize(os.path.join(HERE, "areas.npz")) // 1024, "KiB")
@@ -527,6 +560,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
     np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
     np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
+    np.savez_compressed(os.path.join(HERE, "shade_span.npz"), **shade_span_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())

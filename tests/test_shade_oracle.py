@@ -82,3 +82,29 @@ def test_post_shade_ops_golden():
         assert so.density(g["u32"], px, False) == float(g[f"density_u32_{px}"])
     for px in (2, 4, 6):
         assert so.density(g["sparse"], px, True) == float(g[f"density_sparse_{px}"])
+
+
+SPAN_CASES_2D = {"u32": [(2, 9), (0.5, 7.5)], "f64": [(-5.0, 12.5)], "f32": [(0.2, 0.7)]}
+SPAN_CASES_CAT = {"poisson5": [(3, 20), (2.5, 15.5)], "dense3": [(40, 90), (30.5, 100.25)]}
+
+
+def test_span_golden():
+    """tf.shade(span=...) (clip to the span, fixed normalisation range) vs the reference; eq_hist + span raises."""
+    g, gs = load("shade.npz"), load("shade_span.npz")
+    for name, spans in SPAN_CASES_2D.items():
+        data = g[f"d2_{name}_in"]
+        for k, span in enumerate(spans):
+            for how in ("log", "cbrt", "linear"):
+                np.testing.assert_array_equal(so.shade_2d(data, [LIGHTBLUE, DARKBLUE], how=how, span=span),
+                                              gs[f"d2_{name}_s{k}_{how}_default"], err_msg=f"{name} {span} {how}")
+                np.testing.assert_array_equal(so.shade_2d(data, (0x30, 0x70, 0xc0), how=how, min_alpha=20, span=span),
+                                              gs[f"d2_{name}_s{k}_{how}_single"], err_msg=f"{name} {span} {how} single")
+    for name, spans in SPAN_CASES_CAT.items():
+        data = g[f"cat_{name}_in"]
+        colors = [_rgb(c) for c in SETS1TO3[:data.shape[2]]]
+        for k, span in enumerate(spans):
+            for how in ("log", "cbrt", "linear"):
+                np.testing.assert_array_equal(so.shade_categorical(data, colors, how=how, span=span), gs[f"cat_{name}_s{k}_{how}"],
+                                              err_msg=f"{name} {span} {how}")
+    with pytest.raises(ValueError, match="span is not"):
+        so.shade_2d(g["d2_u32_in"], [LIGHTBLUE, DARKBLUE], how="eq_hist", span=(1, 5))

@@ -91,7 +91,7 @@ def config5(scale):
     out = {"config": 5, "points": n}
     for name, agg in (("max", ds.max("value")), ("first", ds.first("value")), ("where_max_row", ds.where(ds.max("value"))),
                       ("count", ds.count())):
-        ms, res = timed(lambda: cvs.points(frame, "x", "y", agg), warmup=1, steps=3)
+        ms, res = timed(lambda: cvs.points(frame, "x", "y", agg), warmup=3, steps=5)   # the first passes run at ramping clocks
         out[f"{name}_ms"] = ms
         out[f"{name}_gpts"] = n / ms / 1e6
     config.device_results = False
