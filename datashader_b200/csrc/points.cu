@@ -21,7 +21,7 @@ struct PointsArgs {
 
 // One point per thread per step, 4 independent steps in flight (coalesced 4-byte loads; the path is
 // bound by the RED rate, not by load issue - see profiles/r01_ubench.md).
-template <typename XY>
+template <typename XY, bool FILTER>
 __global__ void __launch_bounds__(256) k_points_generic(const PointsArgs a) {
   const XY* __restrict__ x = (const XY*)a.x;
   const XY* __restrict__ y = (const XY*)a.y;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_points_generic(const PointsArgs a) {
         if (c < 0 || c >= ncat) continue;
         cell = cell * ncat + c;
       }
-      for (int k = 0; k < a.plan.nops; k++) apply_base(a.plan.ops[k], cell, i, a.row_offset + i);
+      for (int k = 0; k < a.plan.nops; k++) apply_base<FILTER>(a.plan.ops[k], cell, i, a.row_offset + i);
     }
   }
 }
@@ -91,15 +91,16 @@ __device__ __forceinline__ void priv_hit(uint32_t* sh, long long cell, unsigned 
 
 // apply_base for an op whose value column is the vector-loaded float32 column (value already in a register)
 __device__ __forceinline__ void apply_base_f32(const dsb_base& b, long long cell, long long i, long long row, float v) {
-  if (b.chk_dtype != DSB_NONE) { apply_base(b, cell, i, row); return; }
+  if (b.chk_dtype != DSB_NONE) { apply_base<false>(b, cell, i, row); return; }
   if (v != v) return;                       // every op below skips NaN fields
   switch (b.op) {
     case DSB_OP_COUNT: atomicAdd((unsigned int*)b.agg + cell, 1u); return;
     case DSB_OP_ANY: ((uint8_t*)b.agg)[cell] = 1; return;
     case DSB_OP_SUM: atomicAdd((double*)b.agg + cell, (double)v); return;
+    // no load-before-RED filter here: with 32 warps per SM and 36 KB of L1 the dependent load costs K2 4x (measured)
     case DSB_OP_MAX32: atomicMax((int*)b.agg + cell, key32_from_f32(v)); return;
     case DSB_OP_MIN32: atomicMin((int*)b.agg + cell, key32_from_f32(v)); return;
-    default: apply_base(b, cell, i, row); return;
+    default: apply_base<false>(b, cell, i, row); return;
   }
 }
 
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a, const
       } else if (reg_v) {
         apply_base_f32(b, cell, i, p.row_offset + i, vv);
       } else {
-        apply_base(b, cell, i, p.row_offset + i);
+        apply_base<false>(b, cell, i, p.row_offset + i);
       }
     }
   };
@@ -518,11 +519,13 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
       at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       cfg.attrs = at; cfg.numAttrs = 1;
-      if (xy_dtype == DSB_F32) cudaLaunchKernelEx(&cfg, k_points_generic<float>, a);
-      else cudaLaunchKernelEx(&cfg, k_points_generic<double>, a);
+      if (xy_dtype == DSB_F32) cudaLaunchKernelEx(&cfg, k_points_generic<float, false>, a);
+      else cudaLaunchKernelEx(&cfg, k_points_generic<double, false>, a);
     } else {
-      if (xy_dtype == DSB_F32) k_points_generic<float><<<grid, threads, 0, s>>>(a);
-      else k_points_generic<double><<<grid, threads, 0, s>>>(a);
+      // the load-before-RED filter of the monotone accumulators pays only while the canvases are L2-resident
+      const bool filter = nbands == 1 && bytes_per_pixel * npixels <= (96LL << 20);
+      if (xy_dtype == DSB_F32) { if (filter) k_points_generic<float, true><<<grid, threads, 0, s>>>(a); else k_points_generic<float, false><<<grid, threads, 0, s>>>(a); }
+      else { if (filter) k_points_generic<double, true><<<grid, threads, 0, s>>>(a); else k_points_generic<double, false><<<grid, threads, 0, s>>>(a); }
     }
     DSB_CUDA_CHECK_LAUNCH("dsb_points");
   }
