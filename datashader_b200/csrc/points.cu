@@ -341,6 +341,140 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
   if (bad) atomicOr(a.flag, 1u);
 }
 
+// ---- K1 "mono": single monotone accumulator (max / min of a float32 column, first / last, where(max / min)) ----------
+// The plans of max(col), min(col), first(col), last(col) and where(max / min (col), ...) hold ONE accumulator.  With
+// float32 coordinates on linear axes and an L2-resident canvas this kernel replaces the plan interpreter of
+// k_points_generic by the K2-tight front end (vector loads, float32 fast mapping with the exact f64 mapping deferred
+// to the ~0.1 % of points near a pixel edge) and batches the load-before-RED filter: the eight current values of a
+// batch are fetched first (eight independent L2 loads in flight), then compared, and only winners issue a RED.
+enum { MONO_MAX32 = 0, MONO_MIN32 = 1, MONO_MINROW = 2, MONO_MAXROW = 3, MONO_ARGMAX32 = 4, MONO_ARGMIN32 = 5 };
+
+template <int OP> struct MonoT { typedef long long cell_t; };
+template <> struct MonoT<MONO_MAX32> { typedef int cell_t; };
+template <> struct MonoT<MONO_MIN32> { typedef int cell_t; };
+
+template <int OP>
+__global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ PointsArgs a, const __grid_constant__ FastMap fm,
+                                                        const float* __restrict__ vcol) {
+  typedef typename MonoT<OP>::cell_t T;
+  T* __restrict__ canvas = (T*)a.plan.ops[0].agg;
+  const float* __restrict__ x = (const float*)a.x;
+  const float* __restrict__ y = (const float*)a.y;
+  const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
+  constexpr bool IS_MAX = OP == MONO_MAX32 || OP == MONO_MAXROW || OP == MONO_ARGMAX32;
+  constexpr bool FILTERED = true;
+  // "last" = the largest row id: walking the rows forwards every hit wins and pays a RED; walked BACKWARDS the first
+  // hit of a pixel is final and the filter removes the rest, as for "first"
+  constexpr bool REVERSE = OP == MONO_MAXROW;
+
+  auto key_of = [&](float vv, long long i) -> T {
+    const long long row = a.row_offset + i;
+    if (OP == MONO_MAX32 || OP == MONO_MIN32) return (T)key32_from_f32(vv);
+    if (OP == MONO_MINROW || OP == MONO_MAXROW) return (T)row;
+    const long long k = (long long)key32_from_f32(vv) << 32;          // see apply_base: value first, earliest row on ties
+    return (T)(OP == MONO_ARGMAX32 ? (k | (long long)(uint32_t)(~(uint32_t)row)) : (k | (long long)(uint32_t)row));
+  };
+  auto commit = [&](int cell, T key, T cur) {
+    if (IS_MAX) { if (!FILTERED || key > cur) atomicMax(canvas + cell, key); }
+    else { if (key < cur) atomicMin(canvas + cell, key); }
+  };
+  auto exact = [&](float xv, float yv, float vv, long long i) {
+    if (vv != vv) return;
+    const int cell = map_exact_linear(a.v, xv, yv);
+    if (cell < 0) return;
+    commit(cell, key_of(vv, i), FILTERED ? __ldcg(canvas + cell) : (T)0);
+  };
+
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const float4* __restrict__ v4 = (const float4*)vcol;
+  const long long n4 = a.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
+  for (long long t4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t4 < n4; t4 += 2 * stride) {
+    const bool two = t4 + stride < n4;
+    const long long i4 = REVERSE ? n4 - 1 - t4 : t4;
+    const long long j4 = REVERSE ? i4 - stride : i4 + stride;
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = __ldcs(v4 + i4);
+    const float4 xb = two ? __ldcs(x4 + j4) : nan4, yb = two ? __ldcs(y4 + j4) : nan4, vb = two ? __ldcs(v4 + j4) : nan4;
+    const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const float ys[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+    const float vs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    int cell[8];
+    bool ok[8];
+    uint32_t slow = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                     // the K2-tight mapping: see k_points_priv_tight
+      const float xf = fmaf(xs[k], fm.sx, fm.tx), yf = fmaf(ys[k], fm.sy, fm.ty);
+      const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+      const float dx = xf - (float)xi, dy = yf - (float)yi;
+      const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
+      ok[k] = sure && (uint32_t)xi < W && (uint32_t)yi < H && vs[k] == vs[k];
+      cell[k] = ok[k] ? yi * (int)W + xi : 0;
+      slow |= (uint32_t)(!sure && vs[k] == vs[k]) << k;
+    }
+    T cur[8];
+    if (FILTERED) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) cur[k] = __ldcg(canvas + cell[k]);   // eight independent L2 loads in flight
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (ok[k]) commit(cell[k], key_of(vs[k], 4 * (k < 4 ? i4 : j4) + (k & 3)), FILTERED ? cur[k] : (T)0);
+    if (slow) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (slow & (1u << k)) exact(xs[k], ys[k], vs[k], 4 * (k < 4 ? i4 : j4) + (k & 3));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {           // tail rows
+    const long long i = (n4 << 2) + threadIdx.x;
+    exact(x[i], y[i], vcol[i], i);
+  }
+}
+
+static FastMap make_fast_map(const dsb_view* v);
+
+// Returns true when the launch was taken by k_points_mono.
+static bool try_launch_mono(const PointsArgs& a, int32_t xy_dtype, cudaStream_t s) {
+  const dsb_plan& p = a.plan;
+  if (xy_dtype != DSB_F32 || p.nops != 1 || p.ncat != 0 || a.n < (1LL << 20)) return false;
+  const dsb_base& b = p.ops[0];
+  int op = -1;
+  const float* vcol = nullptr;
+  switch (b.op) {
+    case DSB_OP_MAX32: op = MONO_MAX32; break;
+    case DSB_OP_MIN32: op = MONO_MIN32; break;
+    case DSB_OP_ARGMAX32: op = MONO_ARGMAX32; break;
+    case DSB_OP_ARGMIN32: op = MONO_ARGMIN32; break;
+    case DSB_OP_MINROW: op = MONO_MINROW; break;
+    case DSB_OP_MAXROW: op = MONO_MAXROW; break;
+    default: return false;
+  }
+  if (op == MONO_MINROW || op == MONO_MAXROW) {            // first / last: the row id, gated by the nan-check column
+    if (b.chk_dtype != DSB_F32 || !b.chk || b.val_dtype != DSB_NONE) return false;
+    vcol = (const float*)b.chk;
+  } else {
+    if (b.val_dtype != DSB_F32 || !b.val || b.chk_dtype != DSB_NONE) return false;
+    vcol = (const float*)b.val;
+  }
+  if ((((uintptr_t)a.x | (uintptr_t)a.y | (uintptr_t)vcol) & 15) != 0) return false;
+  if ((long long)a.v.width * a.v.height >= (1LL << 31)) return false;
+  const FastMap fm = make_fast_map(&a.v);
+  if (!fm.enabled) return false;
+  const int grid = dsb_num_sms() * 3;
+  switch (op) {
+    case MONO_MAX32: k_points_mono<MONO_MAX32><<<grid, 256, 0, s>>>(a, fm, vcol); break;
+    case MONO_MIN32: k_points_mono<MONO_MIN32><<<grid, 256, 0, s>>>(a, fm, vcol); break;
+    case MONO_MINROW: k_points_mono<MONO_MINROW><<<grid, 256, 0, s>>>(a, fm, vcol); break;
+    case MONO_MAXROW: k_points_mono<MONO_MAXROW><<<grid, 256, 0, s>>>(a, fm, vcol); break;
+    case MONO_ARGMAX32: k_points_mono<MONO_ARGMAX32><<<grid, 256, 0, s>>>(a, fm, vcol); break;
+    default: k_points_mono<MONO_ARGMIN32><<<grid, 256, 0, s>>>(a, fm, vcol); break;
+  }
+  return true;
+}
+
+
 // canvas += scratch when the privatised pass was exact (flag == 0)
 __global__ void k_priv_commit(unsigned int* __restrict__ canvas, const unsigned int* __restrict__ scratch,
                               const unsigned int* __restrict__ flag, long long n) {
@@ -396,6 +530,7 @@ static long long g_band_budget = -1;        // bytes; -1 = not initialised
 static long long g_band_min_rows = 1LL << 22;
 static long long g_priv_smem_kb = 192;        // shared memory the privatised canvas may take (see dsb_points_priv)
 static long long g_priv_smem_kb_mean = 226;   // the same for the mean() shape
+static int g_mono = 1;                       // use k_points_mono for single monotone accumulators
 static int g_priv_tight = 1;                 // use k_points_priv_tight for the count() / mean(f32) shapes
 static long long l2_band_budget_bytes() {
   if (g_band_budget < 0) {
@@ -412,6 +547,7 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "l2_band_bytes")) { g_band_budget = value; return DSB_OK; }
   if (!strcmp(key, "band_min_rows")) { g_band_min_rows = value; return DSB_OK; }
   if (!strcmp(key, "priv_tight")) { g_priv_tight = value != 0; return DSB_OK; }
+  if (!strcmp(key, "mono")) { g_mono = value != 0; return DSB_OK; }
   if (!strcmp(key, "priv_smem_kb")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb = value; return DSB_OK; }
   if (!strcmp(key, "priv_smem_kb_mean")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb_mean must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb_mean = value; return DSB_OK; }
   dsb_set_error("dsb_configure: unknown key %s", key);
@@ -524,6 +660,7 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
     } else {
       // the load-before-RED filter of the monotone accumulators pays only while the canvases are L2-resident
       const bool filter = nbands == 1 && bytes_per_pixel * npixels <= (96LL << 20);
+      if (filter && g_mono && try_launch_mono(a, xy_dtype, s)) { DSB_CUDA_CHECK_LAUNCH("dsb_points(mono)"); continue; }
       if (xy_dtype == DSB_F32) { if (filter) k_points_generic<float, true><<<grid, threads, 0, s>>>(a); else k_points_generic<float, false><<<grid, threads, 0, s>>>(a); }
       else { if (filter) k_points_generic<double, true><<<grid, threads, 0, s>>>(a); else k_points_generic<double, false><<<grid, threads, 0, s>>>(a); }
     }

@@ -344,3 +344,35 @@ def test_arrow_and_dict_sources_match_pandas(ds):
     want = cvs.points(df, "x", "y", ds.by("cat", ds.count()))
     got = cvs.points(table, "x", "y", ds.by("cat", ds.count()))
     assert np.array_equal(got.data, want.data) and list(got.coords["cat"]) == list(want.coords["cat"])
+
+
+def test_mono_kernel_matches_oracle(ds):
+    """k_points_mono (single monotone accumulator, >= 2^20 float32 rows, L2-resident canvas): max / min / first / last /
+    where(max | min) with NaN values, NaN coordinates, points on pixel edges and outside the ranges - bit-exact."""
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(4242)
+    n = (1 << 20) + 4099
+    x = (rng.random(n, dtype=np.float32) * 1.2 - 0.1).astype(np.float32)      # ~17 % out of range
+    y = (rng.random(n, dtype=np.float32) * 1.2 - 0.1).astype(np.float32)
+    x[:2000] = (rng.integers(0, 301, 2000) / 300).astype(np.float32)            # exactly on pixel edges (W = 300)
+    y[2000:4000] = (rng.integers(0, 201, 2000) / 200).astype(np.float32)
+    x[5000:5010] = np.nan
+    cols = {"x": x, "y": y, "v32": np.round(rng.standard_normal(n), 2).astype(np.float32),     # rounded: many ties
+            "other": rng.random(n).astype(np.float32)}
+    cols["v32"][rng.integers(0, n, 3000)] = np.nan
+    W, H = 300, 200
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    specs = [("max", "v32"), ("min", "v32"), ("first", "v32"), ("last", "v32"), ("where", ("max", "v32"), "other"),
+             ("where", ("min", "v32"), None), ("where", ("max", "v32"), None), ("where", ("first", "v32"), "other")]
+    lib = ds._lib.lib()
+    for spec in specs:
+        want = ora.points(cols, "x", "y", spec, view, npartitions=2 if ("first" in str(spec) or "last" in str(spec)) else 1)
+        for mono in (1, 0):        # the specialised kernel and the generic one must agree with the oracle
+            ds._lib.check(lib.dsb_configure(b"mono", mono), "dsb_configure")
+            try:
+                assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, want, f"mono={mono} {spec}")
+            finally:
+                ds._lib.check(lib.dsb_configure(b"mono", 1), "dsb_configure")
