@@ -78,6 +78,7 @@ _SIGNATURES = {
     "dsb_finalize_mean": ([_p, _p, _p, _i64, _p], C.c_int),
     "dsb_finalize_sum": ([_p, _p, _p, _i64, _p], C.c_int),
     "dsb_finalize_sum_counted": ([_p, _p, _p, _i64, _p], C.c_int),
+    "dsb_points_count16": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(Plan), _p, _i64, _p], C.c_int),
     "dsb_composite": ([_p, _p, C.c_uint32, _i64, _i32, _p, _p], C.c_int),
     "dsb_spread_image": ([_p, _i32, _i32, _p, _i32, _i32, _p, _p], C.c_int),
     "dsb_spread_array": ([_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p, _p], C.c_int),

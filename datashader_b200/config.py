@@ -12,3 +12,9 @@ kernel_events = []     # [(start_event, end_event)] appended per Canvas call whe
 # `priv_min_rows` float32 points when the canvas fits (<= 786 432 cells); "off" forces the global-RED kernel.
 priv_count = True
 priv_min_rows = 1 << 24        # measured crossover vs global REDs: ~15-20 M rows (tools/bench_crossover.py)
+
+# count() / by(cat, count()) on a u32 canvas of 1x..2x the L2 budget: one pass into 16-bit packed counters
+# (dsb_points_count16) instead of two L2-banded passes.  l2_budget_bytes mirrors the library's default band budget.
+count16 = True
+count16_min_rows = 1 << 22
+l2_budget_bytes = 96 << 20

@@ -815,3 +815,104 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   DSB_CUDA_CHECK_LAUNCH("dsb_points_priv(commit)");
   return DSB_OK;
 }
+
+// ---- count() on canvases between 1x and 2x the L2 budget: 16-bit packed counters ------------------------------------
+// A u32 count canvas of 96..192 MB (config 3: by('cat', count()) with 16 categories at 1920x1080 = 133 MB) does not
+// stay in L2, so dsb_points bands it and reads the rows twice.  Here the pass counts into 16-bit halves of a u32
+// scratch canvas (half the footprint: L2-resident, ONE pass) with plain REDs of 1 or 1 << 16.  A half that wraps
+// loses 65 536 (low half: carries into its neighbour) or 65 536 (high half: carries out), so the sum of all halves
+// falls short of the number of accepted hits - which the pass counts on the side.  Equal sums prove that no half
+// wrapped; then the halves are added into the real canvas.  Otherwise the scratch is discarded and the pass is redone
+// with u32 REDs on the real canvas (flag-gated launch, no host round trip).  Always exact.
+template <typename XY>
+__global__ void __launch_bounds__(256) k_points_count16(const PointsArgs a, unsigned int* __restrict__ packed,
+                                                        unsigned long long* __restrict__ accepted) {
+  const XY* __restrict__ x = (const XY*)a.x;
+  const XY* __restrict__ y = (const XY*)a.y;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int ncat = a.plan.ncat;
+  const dsb_base& b = a.plan.ops[0];
+  unsigned long long mine = 0;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < a.n; i0 += 4 * stride) {
+    XY xs[4], ys[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long i = i0 + u * stride;
+      if (i < a.n) { xs[u] = __ldcs(x + i); ys[u] = __ldcs(y + i); } else { xs[u] = (XY)NAN; ys[u] = (XY)NAN; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long i = i0 + u * stride;
+      long long cell = map_to_cell<XY>(a.v, xs[u], ys[u]);
+      if (cell < 0) continue;
+      if (ncat > 0) {
+        int c = load_cat(a.plan.cat, a.plan.cat_dtype, i);
+        if (c < 0) c += ncat;
+        if (c < 0 || c >= ncat) continue;
+        cell = cell * ncat + c;
+      }
+      if (b.chk_dtype != DSB_NONE && col_isnan(b.chk, b.chk_dtype, i)) continue;
+      if (b.val_dtype != DSB_NONE && col_isnan(b.val, b.val_dtype, i)) continue;
+      atomicAdd(packed + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
+      mine++;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(accepted, mine);
+}
+
+__global__ void k_sum16(const unsigned int* __restrict__ packed, long long nwords, unsigned long long* __restrict__ total) {
+  unsigned long long t = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned int w = packed[i];
+    t += (w & 0xffffu) + (w >> 16);
+  }
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0 && t) atomicAdd(total, t);
+}
+
+// st[0] = accepted hits, st[1] = sum of the halves, st[2] = flag (1: a half wrapped, redo)
+__global__ void k_unpack16_if(unsigned int* __restrict__ canvas, const unsigned int* __restrict__ packed, long long ncell,
+                              unsigned long long* __restrict__ st) {
+  if (st[0] != st[1]) { if (blockIdx.x == 0 && threadIdx.x == 0) *(unsigned int*)(st + 2) = 1u; return; }
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+    const unsigned int w = packed[c >> 1];
+    const unsigned int h = (c & 1) ? (w >> 16) : (w & 0xffffu);
+    if (h) canvas[c] += h;
+  }
+}
+
+extern "C" int dsb_points_count16(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                                  int64_t row_offset, const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points_count16: bad view"); return DSB_ERR_ARG; }
+  if (n < 0 || n > (1LL << 32)) { dsb_set_error("dsb_points_count16: n must be in [0, 2^32] per call"); return DSB_ERR_ARG; }
+  int rc = validate_plan(plan);
+  if (rc != DSB_OK) return rc;
+  if (plan->nops != 1 || plan->ops[0].op != DSB_OP_COUNT) { dsb_set_error("dsb_points_count16: the plan must be one COUNT accumulator"); return DSB_ERR_UNSUPPORTED; }
+  if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("dsb_points_count16: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+  if (n == 0) return DSB_OK;
+  if (!x || !y) { dsb_set_error("dsb_points_count16: null coordinate column"); return DSB_ERR_ARG; }
+  const long long ncell = (long long)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1);
+  const long long nwords = (ncell + 1) >> 1;
+  if (!scratch || scratch_bytes < nwords * 4 + 24) { dsb_set_error("dsb_points_count16: scratch must hold %lld bytes", nwords * 4 + 24); return DSB_ERR_ARG; }
+  unsigned long long* st = (unsigned long long*)scratch;               // [3] u64 header, then the packed canvas
+  unsigned int* packed = (unsigned int*)(st + 3);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, (size_t)(nwords * 4 + 24), s);
+  PointsArgs a;
+  a.v = *view; a.x = x; a.y = y; a.n = n; a.row_offset = row_offset; a.plan = *plan; a.band_lo = 0; a.band_hi = ncell;
+  const int threads = 256;
+  long long want = (n + (long long)threads * 4 - 1) / ((long long)threads * 4);
+  const long long cap = (long long)dsb_num_sms() * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  if (xy_dtype == DSB_F32) k_points_count16<float><<<grid, threads, 0, s>>>(a, packed, st);
+  else k_points_count16<double><<<grid, threads, 0, s>>>(a, packed, st);
+  k_sum16<<<(int)cap, 256, 0, s>>>(packed, nwords, st + 1);
+  k_unpack16_if<<<(int)cap, 256, 0, s>>>((unsigned int*)plan->ops[0].agg, packed, ncell, st);
+  want = (n + 255) / 256;
+  const int g2 = (int)(want < cap ? want : cap);
+  if (xy_dtype == DSB_F32) k_points_generic_if<float><<<g2, 256, 0, s>>>(a, (const unsigned int*)(st + 2));
+  else k_points_generic_if<double><<<g2, 256, 0, s>>>(a, (const unsigned int*)(st + 2));
+  DSB_CUDA_CHECK_LAUNCH("dsb_points_count16");
+  return DSB_OK;
+}

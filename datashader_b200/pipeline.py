@@ -144,6 +144,19 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
                     continue
                 if rc != -3:
                     _lib.check(rc, "dsb_points_priv")
+        ncell = int(np.prod(ctx.shape))
+        if (config.count16 and plan.nops == 1 and plan.ops[0].op == _lib.OP_COUNT and n >= config.count16_min_rows
+                and 4 * ncell > config.l2_budget_bytes >= 2 * ncell):
+            # u32 canvas beyond L2 but its 16-bit packed form fits: one L2-resident pass instead of two banded ones
+            scratch = getattr(ctx, "_count16_scratch", None)
+            if scratch is None:
+                scratch = ctx._count16_scratch = torch.empty(4 * ((ncell + 1) // 2) + 24, dtype=torch.uint8, device=x.device)
+            rc = lib.dsb_points_count16(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
+                                        scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
+            if rc == 0:
+                continue
+            if rc != -3:
+                _lib.check(rc, "dsb_points_count16")
         _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
                                   ctx.stream_ptr), "dsb_points")
 

@@ -239,6 +239,14 @@ int dsb_shade_map2d(const double* data, int64_t npix, int32_t how, const double*
                     const double* span, int32_t ncolors, const double* cspan, const double* rs, const double* gs,
                     const double* bs, double min_alpha, double alpha, uint32_t* out, void* stream);
 
+/* count() / by(cat, count()) on a u32 canvas of 1x..2x the L2 budget (config 3: 133 MB): one pass into 16-bit packed
+ * counters in `scratch` (2 bytes per cell + 24: L2-resident), verified by a checksum (sum of the halves == accepted hits)
+ * and then added into the canvas; on a mismatch (some cell took more than 65 535 hits) the pass is redone with u32
+ * REDs by a flag-gated launch.  Same contract as dsb_points for a plan of exactly one COUNT accumulator; otherwise
+ * DSB_ERR_UNSUPPORTED. */
+int dsb_points_count16(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                       const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ---- post-shade image operations ------------------------------------------------------------------- */
 /* Binary compositing operators on uint32 RGBA (datashader/composite.py:72-125) and on plain arrays (:150-168). */
 typedef enum { DSB_COMP_OVER = 0, DSB_COMP_ADD = 1, DSB_COMP_SATURATE = 2, DSB_COMP_SOURCE = 3 } dsb_composite_op;

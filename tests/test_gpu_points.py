@@ -376,3 +376,41 @@ def test_mono_kernel_matches_oracle(ds):
                 assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, want, f"mono={mono} {spec}")
             finally:
                 ds._lib.check(lib.dsb_configure(b"mono", 1), "dsb_configure")
+
+
+def test_count16_packed_path_matches_oracle(ds):
+    """dsb_points_count16 (16-bit packed counters + checksum) on a by-count canvas: the normal case, and a hot cell with
+    more than 65 535 hits that must trip the checksum and fall back to the exact u32 pass."""
+    import torch
+    from oracle import oracle as ora
+    old = (ds.config.count16_min_rows, ds.config.l2_budget_bytes)
+    ds.config.count16_min_rows = 0
+    W, H, NC = 64, 48, 4
+    ds.config.l2_budget_bytes = 3 * W * H * NC          # makes 4*cells > budget >= 2*cells: the packed path is chosen
+    try:
+        rng = np.random.default_rng(16)
+        n = 400_000
+        cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+                "v32": rng.standard_normal(n).astype(np.float32), "cat": rng.integers(0, NC, n).astype(np.int8), "cat__ncat": NC}
+        cols["v32"][rng.integers(0, n, 500)] = np.nan
+        view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+        cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+        frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items() if k != "cat__ncat"},
+                               categories={"cat": [f"c{i}" for i in range(NC)]})
+        before = ds._lib.lib().dsb_launch_count()
+        got = cvs.points(frame, "x", "y", ds.by("cat", ds.count())).data
+        assert_agg_equal(got, ora.points(cols, "x", "y", ("by", "cat", ("count",)), view), "count16 by count")
+        got = cvs.points(frame, "x", "y", ds.by("cat", ds.count("v32"))).data
+        assert_agg_equal(got, ora.points(cols, "x", "y", ("by", "cat", ("count", "v32")), view), "count16 by count(v32)")
+        assert ds._lib.lib().dsb_launch_count() > before
+        # hot cell: 200 000 hits on one (pixel, category) -> a 16-bit half wraps -> checksum mismatch -> exact redo
+        cols["x"][:200_000] = 0.51
+        cols["y"][:200_000] = 0.52
+        cols["cat"][:200_000] = 1
+        frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items() if k != "cat__ncat"},
+                               categories={"cat": [f"c{i}" for i in range(NC)]})
+        got = cvs.points(frame, "x", "y", ds.by("cat", ds.count())).data
+        assert_agg_equal(got, ora.points(cols, "x", "y", ("by", "cat", ("count",)), view), "count16 hot cell")
+        assert got.max() >= 200_000
+    finally:
+        ds.config.count16_min_rows, ds.config.l2_budget_bytes = old
