@@ -905,7 +905,22 @@ extern "C" int dsb_points_count16(const dsb_view* view, const void* x, const voi
   long long want = (n + (long long)threads * 4 - 1) / ((long long)threads * 4);
   const long long cap = (long long)dsb_num_sms() * 8;
   const int grid = (int)(want < cap ? want : cap);
-  if (xy_dtype == DSB_F32) k_points_count16<float><<<grid, threads, 0, s>>>(a, packed, st);
+  if (l2_persist_enabled()) {
+    // opt-in (DSB_L2_PERSIST=1): pin the packed canvas in L2, everything else streams
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[0].val.accessPolicyWindow.base_ptr = (void*)packed;
+    const size_t nb = (size_t)nwords * 4, maxw = l2_max_window_bytes();
+    at[0].val.accessPolicyWindow.num_bytes = nb < maxw ? nb : maxw;
+    at[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (xy_dtype == DSB_F32) cudaLaunchKernelEx(&cfg, k_points_count16<float>, a, packed, st);
+    else cudaLaunchKernelEx(&cfg, k_points_count16<double>, a, packed, st);
+  } else if (xy_dtype == DSB_F32) k_points_count16<float><<<grid, threads, 0, s>>>(a, packed, st);
   else k_points_count16<double><<<grid, threads, 0, s>>>(a, packed, st);
   k_sum16<<<(int)cap, 256, 0, s>>>(packed, nwords, st + 1);
   k_unpack16_if<<<(int)cap, 256, 0, s>>>((unsigned int*)plan->ops[0].agg, packed, ncell, st);
