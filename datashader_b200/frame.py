@@ -12,6 +12,65 @@ import torch
 _TORCH_OK = {np.dtype(t) for t in ("float32", "float64", "int8", "uint8", "int16", "int32", "int64", "bool")}
 
 
+def _from_numpy(a):
+    """torch view of a numpy array without copying it: pandas hands out read-only (copy-on-write) views, which torch
+    only warns about - the columns are never written to."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(a)
+
+
+class _PinnedRing:
+    """Pageable host memory -> device through a small ring of pinned staging buffers.
+
+    A pageable-source cudaMemcpy is staged by the driver through one internal buffer, synchronously (measured here:
+    3.6 GB/s for a pandas frame against 54 GB/s from pinned memory).  The ring does the staging explicitly: a
+    multi-threaded CPU copy into a pinned slot, then an asynchronous H2D copy of that slot on the copy stream, so the
+    CPU copy of sub-chunk k+1 overlaps the DMA of sub-chunk k (and the kernels of the previous chunk)."""
+    SLOT_BYTES = 16 << 20
+    NSLOTS = 4
+    _rings = {}
+
+    def __init__(self):
+        self.slots = [torch.empty(self.SLOT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.NSLOTS)]
+        self.events = [None] * self.NSLOTS
+        self.next = 0
+
+    @classmethod
+    def get(cls, device):
+        key = str(device)
+        if key not in cls._rings:
+            cls._rings[key] = cls()
+        return cls._rings[key]
+
+    def copy(self, dst, src, stream):
+        """dst: 1-D CUDA tensor, src: 1-D contiguous CPU tensor of the same dtype and length; enqueued on `stream`."""
+        d8, s8 = dst.view(torch.uint8), src.view(torch.uint8)
+        n = s8.numel()
+        for off in range(0, n, self.SLOT_BYTES):
+            m = min(self.SLOT_BYTES, n - off)
+            k = self.next
+            self.next = (k + 1) % self.NSLOTS
+            if self.events[k] is not None:
+                self.events[k].synchronize()              # the DMA that last read this slot has finished
+            self.slots[k][:m].copy_(s8[off:off + m])      # pageable -> pinned, torch's parallel CPU copy
+            with torch.cuda.stream(stream):
+                d8[off:off + m].copy_(self.slots[k][:m], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            self.events[k] = ev
+
+
+def _h2d(dst, src, stream):
+    """Asynchronous host -> device copy on `stream`: direct DMA from pinned memory, the staging ring otherwise."""
+    if src.is_pinned() or src.numel() * src.element_size() < (1 << 20):
+        with torch.cuda.stream(stream):
+            dst.copy_(src, non_blocking=True)
+    else:
+        _PinnedRing.get(dst.device).copy(dst, src, stream)
+
+
 def _to_tensor(arr: np.ndarray, device, pin=False, stream=None):
     arr = np.ascontiguousarray(arr)
     if not arr.flags.writeable:
@@ -132,9 +191,7 @@ class HostFrame:
                     a = a.view(np.uint8)
                 if a.dtype not in _TORCH_OK:
                     a = a.astype(np.int64 if a.dtype.kind in "iu" and a.dtype.itemsize < 8 else np.float64)
-                if not a.flags.writeable:
-                    a = a.copy()
-                self.columns[name] = torch.from_numpy(a)
+                self.columns[name] = _from_numpy(a)
         self.categories = dict(categories or {})
         self.row_offset = int(row_offset)
         lens = {int(t.shape[0]) for t in self.columns.values()}
@@ -220,7 +277,13 @@ class HostFrame:
 
     def resident(self, needed):
         """The whole frame on the device (single-chunk sources and gathers)."""
-        cols = {c: self.columns[c].to(self.device, non_blocking=True) for c in needed}
+        stream = torch.cuda.current_stream(self.device)
+        cols = {}
+        for c in needed:
+            src = self.columns[c]
+            dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+            _h2d(dst, src, stream)
+            cols[c] = dst
         return DeviceFrame(cols, self.categories, self.row_offset)
 
     def chunks(self, needed):
@@ -238,11 +301,11 @@ class HostFrame:
         for k, lo in enumerate(range(0, self._len, rows)):
             hi = min(lo + rows, self._len)
             b = bufs[k & 1]
+            if free_ev[k & 1] is not None:
+                copy.wait_event(free_ev[k & 1])           # the kernel that read this buffer has finished
+            for c in needed:
+                _h2d(b[c][:hi - lo], self.columns[c][lo:hi], copy)
             with torch.cuda.stream(copy):
-                if free_ev[k & 1] is not None:
-                    copy.wait_event(free_ev[k & 1])       # the kernel that read this buffer has finished
-                for c in needed:
-                    b[c][:hi - lo].copy_(self.columns[c][lo:hi], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy)
             compute.wait_event(ready)
