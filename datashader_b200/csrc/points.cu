@@ -541,6 +541,7 @@ static long long g_band_budget = -1;        // bytes; -1 = not initialised
 static long long g_band_min_rows = 1LL << 22;
 static long long g_priv_smem_kb = 192;        // shared memory the privatised canvas may take (see dsb_points_priv)
 static long long g_priv_smem_kb_mean = 226;   // the same for the mean() shape
+static long long g_split_bytes = 48LL << 20;  // plans whose canvases total more than this run one pass per accumulator
 static int g_mono = 1;                       // use k_points_mono for single monotone accumulators
 static int g_mono_banded = 0;                //   ... for the L2-banded passes of big canvases too: measured slower (8192^2,
                                              //   1e9 points: max 20.7 -> 29.5 ms, first 32.7 -> 49.6 ms: ~15 hits per pixel
@@ -562,6 +563,7 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "band_min_rows")) { g_band_min_rows = value; return DSB_OK; }
   if (!strcmp(key, "priv_tight")) { g_priv_tight = value != 0; return DSB_OK; }
   if (!strcmp(key, "mono")) { g_mono = value != 0; return DSB_OK; }
+  if (!strcmp(key, "split_bytes")) { g_split_bytes = value; return DSB_OK; }
   if (!strcmp(key, "mono_banded")) { g_mono_banded = value != 0; return DSB_OK; }
   if (!strcmp(key, "priv_smem_kb")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb = value; return DSB_OK; }
   if (!strcmp(key, "priv_smem_kb_mean")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb_mean must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb_mean = value; return DSB_OK; }
@@ -622,6 +624,28 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
   if (!x || !y) { dsb_set_error("dsb_points: null coordinate column"); return DSB_ERR_ARG; }
   if ((int64_t)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1) > (1LL << 40)) { dsb_set_error("dsb_points: canvas too large"); return DSB_ERR_ARG; }
   if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("dsb_points: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+  // Accumulator splitting.  Several canvases that together outgrow what stays resident in L2 (by('cat', mean()): 60 MB
+  // of f64 sums + 30 MB of counts) thrash it when they are updated in one pass.  The input columns are cheap to read
+  // again (HBM idles on this path), so such a plan runs as one pass per accumulator, each with its canvas L2-resident.
+  // MATCHROW64 reads another op's finished canvas and is already planned on its own by the host.
+  if (plan->nops > 1 && g_split_bytes > 0 && n >= g_band_min_rows) {
+    long long total = 0, biggest = 0;
+    for (int k = 0; k < plan->nops; k++) {
+      const long long b = op_cell_bytes(plan->ops[k].op) * (long long)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1);
+      total += b;
+      if (b > biggest) biggest = b;
+    }
+    if (total > g_split_bytes && biggest < total) {
+      for (int k = 0; k < plan->nops; k++) {
+        dsb_plan one = *plan;
+        one.nops = 1;
+        one.ops[0] = plan->ops[k];
+        rc = dsb_points(view, x, y, xy_dtype, n, row_offset, &one, stream);
+        if (rc != DSB_OK) return rc;
+      }
+      return DSB_OK;
+    }
+  }
   PointsArgs a;
   a.v = *view; a.x = x; a.y = y; a.n = n; a.row_offset = row_offset; a.plan = *plan;
   const int threads = 256;
