@@ -24,7 +24,7 @@ _NP_TO_DSB = {
 OP_COUNT, OP_ANY, OP_SUM, OP_MAX32, OP_MIN32, OP_MAX64, OP_MIN64 = 1, 2, 3, 4, 5, 6, 7
 OP_MAXROW, OP_MINROW, OP_ARGMAX32, OP_ARGMIN32, OP_MATCHROW64 = 8, 9, 10, 11, 12
 
-LINE_ANY, LINE_COUNT, LINE_SUM, LINE_MAX, LINE_MIN = 1, 2, 3, 4, 5
+LINE_ANY, LINE_COUNT, LINE_SUM, LINE_MAX, LINE_MIN, LINE_MEAN = 1, 2, 3, 4, 5, 6
 AA2_SUM, AA2_COUNT, AA2_MIN, AA2_FIRST, AA2_LAST = 1, 2, 3, 4, 5
 
 

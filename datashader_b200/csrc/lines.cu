@@ -122,6 +122,13 @@ __device__ __forceinline__ void append_aa(const LineCtx& c, long long x, long lo
       atomicMax((long long*)c.canvas + cell, key64_from_f64(v));
       return;
     }
+    case DSB_LINE_MEAN: {  // mean = _sum_zero / _count_ignore_antialiasing (reductions.py:967-975, 681-686, 1289-1297);
+                           // `mask` is the u32 count canvas here
+      double v = fmul64(c.field, fsub64(aa, prev_aa));
+      if (v == v) atomicAdd((double*)c.canvas + cell, v);
+      if (!c.field_nan && prev_aa == 0.0) atomicAdd((unsigned int*)c.mask + cell, 1u);
+      return;
+    }
     case DSB_LINE_AA2_VALUE:   // stage 1 of min / first / last / sum(self_intersect=False): reductions.py:1186-1191,
     case DSB_LINE_AA2_COVER: { // 1408-1413, 1446-1451, 1079-1085; of count(self_intersect=False): :570-578, 594-600
       double v;
@@ -650,19 +657,20 @@ extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void*
                                int64_t nverts, const dsb_line_layout* layout, const void* val, int32_t val_dtype,
                                int32_t agg, double line_width, void* canvas, uint8_t* mask, void* stream) {
   if (!view || view->width <= 0 || view->height <= 0 || !canvas) { dsb_set_error("dsb_lines_axis1: bad view/canvas"); return DSB_ERR_ARG; }
-  if (agg < DSB_LINE_ANY || agg > DSB_LINE_MIN) { dsb_set_error("dsb_lines_axis1: unknown agg %d", agg); return DSB_ERR_ARG; }
+  if (agg < DSB_LINE_ANY || agg > DSB_LINE_MEAN) { dsb_set_error("dsb_lines_axis1: unknown agg %d", agg); return DSB_ERR_ARG; }
   const bool aa = line_width > 0.0;
   if (aa && agg == DSB_LINE_MIN) { dsb_set_error("dsb_lines_axis1: antialiased min needs the 2-stage combine"); return DSB_ERR_UNSUPPORTED; }
-  if ((agg == DSB_LINE_SUM || agg == DSB_LINE_MAX || agg == DSB_LINE_MIN) && (val_dtype == DSB_NONE || !val)) {
+  if (agg == DSB_LINE_MEAN && !aa) { dsb_set_error("dsb_lines_axis1: mean is the antialiased form only (use dsb_lines_axis1_plan)"); return DSB_ERR_UNSUPPORTED; }
+  if ((agg == DSB_LINE_SUM || agg == DSB_LINE_MAX || agg == DSB_LINE_MIN || agg == DSB_LINE_MEAN) && (val_dtype == DSB_NONE || !val)) {
     dsb_set_error("dsb_lines_axis1: this reduction needs a value column"); return DSB_ERR_ARG;
   }
-  if ((agg == DSB_LINE_SUM || (aa && agg == DSB_LINE_COUNT)) && !mask) { dsb_set_error("dsb_lines_axis1: mask canvas required"); return DSB_ERR_ARG; }
+  if ((agg == DSB_LINE_SUM || agg == DSB_LINE_MEAN || (aa && agg == DSB_LINE_COUNT)) && !mask) { dsb_set_error("dsb_lines_axis1: mask canvas required"); return DSB_ERR_ARG; }
   if (nlines <= 0 || nverts < 2) return DSB_OK;
   if (!xs || !ys) { dsb_set_error("dsb_lines_axis1: null vertex arrays"); return DSB_ERR_ARG; }
   LineArgs a;
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
   a.agg = agg; a.line_width = line_width; a.canvas = canvas; a.mask = mask;
-  a.overwrite = !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM);   // antialias.py:47-56
+  a.overwrite = !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM || agg == DSB_LINE_MEAN);   // antialias.py:47-56
   a.use_plan = 0; a.row_offset = 0;
   int rc = apply_layout(a, layout, "dsb_lines_axis1");
   if (rc != DSB_OK) return rc;

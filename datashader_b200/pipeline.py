@@ -344,6 +344,9 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
         elif la == _lib.LINE_SUM:
             canvas_t = torch.zeros((H, W), dtype=torch.float64, device=device)
             mask = torch.zeros((H, W), dtype=torch.uint8, device=device)
+        elif la == _lib.LINE_MEAN:
+            canvas_t = torch.zeros((H, W), dtype=torch.float64, device=device)
+            mask = torch.zeros((H, W), dtype=torch.int32, device=device)        # the count canvas
         else:
             canvas_t = torch.empty((H, W), dtype=torch.int64, device=device)
             _lib.check(lib.dsb_init_canvas(_lib.OP_MAX64 if la == _lib.LINE_MAX else _lib.OP_MIN64, canvas_t.data_ptr(),
@@ -353,7 +356,11 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
                                        canvas_t.data_ptr(), mask.data_ptr() if mask is not None else None, stream_ptr),
                    "dsb_lines_axis1")
         if dist is not None:
-            canvas_t, mask = dist.combine_lines(la, aa, canvas_t, mask)
+            if la == _lib.LINE_MEAN:
+                dist._all_reduce(canvas_t, "sum")
+                dist._all_reduce(mask, "sum")
+            else:
+                canvas_t, mask = dist.combine_lines(la, aa, canvas_t, mask)
         # finishing (dtypes pinned by test_pandas.py:3257-3277: AA any/count -> f32, others f64)
         if la == _lib.LINE_ANY:
             if aa:
@@ -371,6 +378,10 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
         elif la == _lib.LINE_SUM:
             out = torch.empty_like(canvas_t)
             _lib.check(lib.dsb_finalize_sum(canvas_t.data_ptr(), mask.data_ptr(), out.data_ptr(), H * W, stream_ptr))
+            data = _to_host(out)
+        elif la == _lib.LINE_MEAN:
+            out = torch.empty_like(canvas_t)
+            _lib.check(lib.dsb_finalize_mean(canvas_t.data_ptr(), mask.data_ptr(), out.data_ptr(), H * W, stream_ptr))
             data = _to_host(out)
         else:
             out = torch.empty((H, W), dtype=torch.float64, device=device)

@@ -265,6 +265,8 @@ class sum(_FloatingReduction):   # noqa: A001
 class mean(Reduction):
     """Mean of `column` -> float64. reductions.py:1280-1297"""
 
+    _line_agg = _lib.LINE_MEAN      # antialiased lines: _sum_zero / _count_ignore_antialiasing (reductions.py:667-693, 967-975)
+
     def _accs(self, ctx):
         return [Acc("sum", self.column), Acc("count", self.column)]
 

@@ -141,7 +141,8 @@ int dsb_finalize_sum(const double* sum, const uint8_t* mask, double* out, int64_
 int dsb_finalize_sum_counted(const double* sum, const void* count_u32, double* out, int64_t ncell, void* stream);
 
 /* ---- lines ---------------------------------------------------------------------------------- */
-typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5 } dsb_line_agg;
+typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5,
+               DSB_LINE_MEAN = 6 /* antialiased only: canvas f64 sum (zeroed), `mask` = u32 count canvas (zeroed) */ } dsb_line_agg;
 
 /* Vertex addressing of the other line layouts.  NULL = LinesAxis1: dense [nlines, nverts] matrices, one value per
  * line.  x_line_stride / y_line_stride = elements between consecutive lines (0 = one vertex vector shared by all

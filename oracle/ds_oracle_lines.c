@@ -7,7 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { ORA_AA2_VALUE = 101, ORA_AA2_COVER = 102 };   /* internal: stage-1 appends of the 2-stage antialias path */
+enum { ORA_AA2_VALUE = 101, ORA_AA2_COVER = 102,     /* internal: stage-1 appends of the 2-stage antialias path */
+       ORA_AA_COUNT_IGNORE = 103 };                  /* _count_ignore_antialiasing (mean's denominator) */
 
 typedef struct {
   int32_t agg_op;     /* ORA_ANY / ORA_COUNT / ORA_SUM / ORA_MAX / ORA_MIN */
@@ -78,6 +79,10 @@ static inline void append_aa(const line_ctx* c, int64_t x, int64_t y, double aa,
       double v = f * aa;
       double* a = (double*)c->agg + cell;
       if (!isnan(v) && (isnan(*a) || v > *a)) *a = v;
+      return;
+    }
+    case ORA_AA_COUNT_IGNORE: { /* reductions.py:681-686: u32, += 1 where this segment is the first of its line to touch */
+      if (!isnan(f) && prev_aa == 0.0) ((uint32_t*)c->agg)[cell] += 1u;
       return;
     }
     case ORA_AA2_COVER: { /* stage 1 of count(self_intersect=False): max of aa_factor in a float32 canvas
@@ -320,7 +325,7 @@ void ora_lines(const ora_view* v, const void* xs, const void* ys, int32_t xy_dty
   c.agg_op = agg_op; c.antialias = line_width > 0.0; c.has_field = val_dtype != ORA_NONE;
   c.width = v->width; c.agg = agg; c.field = 0.0;
   /* antialias.py:30-58: overwrite unless a SUM_1AGG combination (count / sum) is present */
-  int overwrite = !(agg_op == ORA_COUNT || agg_op == ORA_SUM);
+  int overwrite = !(agg_op == ORA_COUNT || agg_op == ORA_SUM || agg_op == ORA_AA_COUNT_IGNORE);
   for (int64_t i = 0; i < nlines; i++) {          /* extend_cpu, line.py:1277-1289 / 1127-1136 / 1200-1210 */
     for (int64_t j = 0; j + 1 < nverts; j++) {    /* perform_extend_line, line.py:1250-1275 / 1104-1125 */
       const int64_t ox = i * x_line_stride + j, oy = i * y_line_stride + j;

@@ -377,7 +377,7 @@ def lines_aa2_cases():
     out = {}
     aggs = {"min": ds.min("val"), "first": ds.first("val"), "last": ds.last("val"),
             "sum_nsi": ds.sum("val", self_intersect=False), "count_nsi": ds.count(self_intersect=False),
-            "count_val_nsi": ds.count("val", self_intersect=False)}
+            "count_val_nsi": ds.count("val", self_intersect=False), "mean": ds.mean("val")}   # mean: single stage
     for tag, dtype in (("f32", np.float32), ("f64", np.float64)):
         xs, ys, val = line_frame(2024, 40, 24, dtype)       # identical to lines.npz in_{tag}_*
         nverts = xs.shape[1]

@@ -167,7 +167,8 @@ def test_line_axis0_vs_oracle_random(dtype):
 AA2 = {"min": ("min", lambda ds: ds.min("val")), "first": ("first", lambda ds: ds.first("val")),
        "last": ("last", lambda ds: ds.last("val")), "sum_nsi": ("sum", lambda ds: ds.sum("val", self_intersect=False)),
        "count_nsi": ("count", lambda ds: ds.count(self_intersect=False)),
-       "count_val_nsi": ("count", lambda ds: ds.count("val", self_intersect=False))}
+       "count_val_nsi": ("count", lambda ds: ds.count("val", self_intersect=False)),
+       "mean": ("mean", lambda ds: ds.mean("val"))}      # single-stage, rides along with the same goldens
 
 
 def _cmp_aa(got, want, key, rtol=1e-6):
@@ -214,7 +215,10 @@ def test_lines_aa2_vs_oracle_larger():
     view = ora.make_view(W, H, (0.1, 0.9), (0.2, 0.8))
     for gname, (oname, mk) in AA2.items():
         got = cvs.line(frame, x=xcols, y=ycols, axis=1, agg=mk(ds), line_width=1.5).data
-        want = ora.lines_aa2(xs, ys, view, oname, None if gname == "count_nsi" else val, 1.5)
+        if oname == "mean":
+            want = ora.lines(xs, ys, view, "mean", val, 1.5)
+        else:
+            want = ora.lines_aa2(xs, ys, view, oname, None if gname == "count_nsi" else val, 1.5)
         _cmp_aa(got, want, gname, rtol=2e-6 if oname in ("sum", "count") else 1e-6)
 
 

@@ -236,13 +236,14 @@ def test_lines_aa2_golden():
     """2-stage antialiased reductions (min / first / last / count, sum with self_intersect=False) vs the reference."""
     g, gl, gx = load("lines_aa2.npz"), load("lines.npz"), load("line_layouts.npz")
     view = ora.make_view(64, 48, (0, 1), (0, 1))
-    names = {"min": "min", "first": "first", "last": "last", "sum_nsi": "sum", "count_nsi": "count", "count_val_nsi": "count"}
+    names = {"min": "min", "first": "first", "last": "last", "sum_nsi": "sum", "count_nsi": "count", "count_val_nsi": "count",
+             "mean": "mean"}
     for tag in ("f32", "f64"):
         xs, ys, val = gl[f"in_{tag}_xs"], gl[f"in_{tag}_ys"], gl[f"in_{tag}_val"]
         for lw in ((1, 2.5) if tag == "f32" else (1,)):
             for gname, oname in names.items():
                 vals = None if gname == "count_nsi" else val
-                got = ora.lines_aa2(xs, ys, view, oname, vals, lw)
+                got = ora.lines(xs, ys, view, "mean", val, lw) if oname == "mean" else ora.lines_aa2(xs, ys, view, oname, vals, lw)
                 want = g[f"aa2_{tag}_lw{lw}_{gname}"]
                 assert got.dtype == want.dtype, gname
                 assert np.array_equal(np.isnan(got), np.isnan(want)), (tag, lw, gname)
@@ -252,7 +253,8 @@ def test_lines_aa2_golden():
     for gname, oname in names.items():
         vals = None if gname == "count_nsi" else val
         for key, xa, ya in (("ax0", x[None], y[None]), ("ax0multi", np.stack([x, x2]), np.stack([y, y2]))):
-            got = ora.lines_aa2(xa, ya, view0, oname, vals, 2, per_vertex=True)
+            got = (ora.lines(xa, ya, view0, "mean", val, 2, per_vertex=True) if oname == "mean"
+                   else ora.lines_aa2(xa, ya, view0, oname, vals, 2, per_vertex=True))
             want = g[f"aa2_{key}_lw2_{gname}"]
             assert got.dtype == want.dtype and np.array_equal(np.isnan(got), np.isnan(want)), (key, gname)
             np.testing.assert_allclose(got, want, rtol=1e-6 if oname == "count" else 1e-12, equal_nan=True, err_msg=f"{key} {gname}")
