@@ -307,16 +307,17 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
   const long long n4 = p.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
-  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += 2 * stride) {
-    const bool two = i4 + stride < n4;
-    float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
-    float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
-    float4 xb = two ? __ldcs(x4 + i4 + stride) : nan4;
-    float4 yb = two ? __ldcs(y4 + i4 + stride) : nan4;
-    float4 vb = (two && MEAN) ? __ldcs(v4 + i4 + stride) : nan4;
+  // two vectors (8 points) per thread per step, both loads issued before the first use; the loop carries no
+  // predicates - the odd vector left at the end is handled after it
+  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i4 + stride < n4; i4 += 2 * stride) {
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
+    const float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
+    const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride);
+    const float4 vb = MEAN ? __ldcs(v4 + i4 + stride) : nan4;
     uint32_t slow = one(xa.x, ya.x, va.x) | one(xa.y, ya.y, va.y) << 1 | one(xa.z, ya.z, va.z) << 2 | one(xa.w, ya.w, va.w) << 3 |
                     one(xb.x, yb.x, vb.x) << 4 | one(xb.y, yb.y, vb.y) << 5 | one(xb.z, yb.z, vb.z) << 6 | one(xb.w, yb.w, vb.w) << 7;
-    if (slow) {                                    // ~0.07 % of the points (and the NaN padding of a missing second vector)
+    if (slow) {                                    // ~0.07 % of the points
       if (slow & 1) exact(xa.x, ya.x, va.x);
       if (slow & 2) exact(xa.y, ya.y, va.y);
       if (slow & 4) exact(xa.z, ya.z, va.z);
@@ -326,6 +327,11 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
       if (slow & 64) exact(xb.z, yb.z, vb.z);
       if (slow & 128) exact(xb.w, yb.w, vb.w);
     }
+  }
+  if (i4 < n4) {
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
+    const float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
+    exact(xa.x, ya.x, va.x); exact(xa.y, ya.y, va.y); exact(xa.z, ya.z, va.z); exact(xa.w, ya.w, va.w);
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {           // tail rows
     const long long i = (n4 << 2) + threadIdx.x;
