@@ -90,6 +90,8 @@ _SIGNATURES = {
                        C.c_int),
     "dsb_lines_axis1": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _p, _i32, _i32, _f64, _p, _p,
                          _p], C.c_int),
+    "dsb_lines_axis1_cat": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(LineLayout), _p, _i32, _i32, _f64, _p, _p,
+                             _p, _i32, _i32, _p], C.c_int),
 }
 
 _lib = None

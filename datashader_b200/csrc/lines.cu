@@ -29,6 +29,8 @@ struct LineArgs {
   long long x_line_stride, y_line_stride;   // elements between consecutive lines (0: one shared vertex vector)
   int value_per_vertex;     // axis=0 layouts: append(i = row of the segment's first vertex); axis=1: i = line
   int plot_start;           // axis=0: whether vertex 0 starts a line (False for a continued dask partition)
+  const void* cat;          // antialiased by(): category code per line / vertex row, canvases are [H, W, ncat]
+  int cat_dtype, ncat;
   dsb_plan plan;
 };
 
@@ -54,6 +56,7 @@ struct LineCtx {
   long long* hvals;
   uint32_t hmask;           //   cap - 1
   uint32_t hgroup;          //   (index of the line within its group) << 27, or-ed into the table key
+  int ncat;                 // antialiased by(): cell = (y * W + x) * ncat + cat
 };
 
 // internal agg codes of the 2-stage path (stage 1 = per-line max of field * aa_factor / of aa_factor)
@@ -98,7 +101,11 @@ __device__ __forceinline__ void append_px(const LineCtx& c, long long x, long lo
 
 // ---- appends, antialiased (reductions.py _append_antialias / _append_no_field_antialias) --------
 __device__ __forceinline__ void append_aa(const LineCtx& c, long long x, long long y, double aa, double prev_aa) {
-  const long long cell = y * c.width + x;
+  long long cell = y * c.width + x;
+  if (c.ncat > 0) {                      // by(): the reduction runs on agg[:, :, cat] (compiler.py:379-390)
+    if (c.cat < 0) return;
+    cell = cell * c.ncat + c.cat;
+  }
   switch (c.agg) {
     case DSB_LINE_ANY:     // max of aa_factor, stored as f32 (reductions.py:850-869)
       if (c.has_field && c.field_nan) return;
@@ -423,7 +430,14 @@ __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
     c.field = c.has_field ? load_f64(a.val, a.val_dtype, vi) : 0.0;
     c.field_nan = c.has_field && (c.field != c.field);
     c.plan = a.use_plan ? &a.plan : nullptr;
-    c.line = vi; c.row = a.row_offset + vi; c.cat = 0;
+    c.line = vi; c.row = a.row_offset + vi; c.cat = 0; c.ncat = 0;
+    c.hkeys = nullptr; c.touched = nullptr;
+    if (!a.use_plan && a.ncat > 0) {
+      int cc = load_cat(a.cat, a.cat_dtype, vi);
+      if (cc < 0) cc += a.ncat;
+      c.cat = (cc < 0 || cc >= a.ncat) ? -1 : cc;
+      c.ncat = a.ncat;
+    }
     if (a.use_plan && a.plan.ncat > 0) {
       int cc = load_cat(a.plan.cat, a.plan.cat_dtype, vi);
       if (cc < 0) cc += a.plan.ncat;
@@ -542,7 +556,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
       c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = temp; c.mask = nullptr;
       c.field = c.has_field ? load_f64(a.val, a.val_dtype, vi) : 0.0;
       c.field_nan = c.has_field && (c.field != c.field);
-      c.plan = nullptr; c.line = vi; c.row = a.row_offset + vi; c.cat = 0;
+      c.plan = nullptr; c.line = vi; c.row = a.row_offset + vi; c.cat = 0; c.ncat = 0;
       c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox;
       c.hkeys = HASH ? hkeys : nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = (uint32_t)g << AA2_CELL_BITS;
       // xm = ym = 0 in 2-stage mode (line.py:1266-1268); unused because overwrite is True
@@ -647,7 +661,7 @@ extern "C" int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const 
   LineArgs a;
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = nullptr; a.val_dtype = DSB_NONE;
   a.agg = 0; a.line_width = 0.0; a.canvas = nullptr; a.mask = nullptr; a.overwrite = 1;
-  a.use_plan = 1; a.row_offset = row_offset; a.plan = *plan;
+  a.use_plan = 1; a.row_offset = row_offset; a.plan = *plan; a.cat = nullptr; a.cat_dtype = DSB_NONE; a.ncat = 0;
   int rc = apply_layout(a, layout, "dsb_lines_axis1_plan");
   if (rc != DSB_OK) return rc;
   return launch_lines(a, xy_dtype, stream, "dsb_lines_axis1_plan");
@@ -656,6 +670,16 @@ extern "C" int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const 
 extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
                                int64_t nverts, const dsb_line_layout* layout, const void* val, int32_t val_dtype,
                                int32_t agg, double line_width, void* canvas, uint8_t* mask, void* stream) {
+  return dsb_lines_axis1_cat(view, xs, ys, xy_dtype, nlines, nverts, layout, val, val_dtype, agg, line_width, canvas, mask,
+                             nullptr, DSB_NONE, 0, stream);
+}
+
+extern "C" int dsb_lines_axis1_cat(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                                   int64_t nverts, const dsb_line_layout* layout, const void* val, int32_t val_dtype,
+                                   int32_t agg, double line_width, void* canvas, uint8_t* mask, const void* cat,
+                                   int32_t cat_dtype, int32_t ncat, void* stream) {
+  if (ncat < 0 || (ncat > 0 && (!cat || cat_dtype == DSB_NONE))) { dsb_set_error("dsb_lines_axis1_cat: bad category column"); return DSB_ERR_ARG; }
+  if (ncat > 0 && !(line_width > 0.0)) { dsb_set_error("dsb_lines_axis1_cat: categories are for the antialiased form (use dsb_lines_axis1_plan)"); return DSB_ERR_UNSUPPORTED; }
   if (!view || view->width <= 0 || view->height <= 0 || !canvas) { dsb_set_error("dsb_lines_axis1: bad view/canvas"); return DSB_ERR_ARG; }
   if (agg < DSB_LINE_ANY || agg > DSB_LINE_MEAN) { dsb_set_error("dsb_lines_axis1: unknown agg %d", agg); return DSB_ERR_ARG; }
   const bool aa = line_width > 0.0;
@@ -671,7 +695,7 @@ extern "C" int dsb_lines_axis1(const dsb_view* view, const void* xs, const void*
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
   a.agg = agg; a.line_width = line_width; a.canvas = canvas; a.mask = mask;
   a.overwrite = !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM || agg == DSB_LINE_MEAN);   // antialias.py:47-56
-  a.use_plan = 0; a.row_offset = 0;
+  a.use_plan = 0; a.row_offset = 0; a.cat = cat; a.cat_dtype = cat_dtype; a.ncat = ncat;
   int rc = apply_layout(a, layout, "dsb_lines_axis1");
   if (rc != DSB_OK) return rc;
   return launch_lines(a, xy_dtype, stream, "dsb_lines_axis1");
@@ -699,6 +723,7 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
   a.agg = combo == DSB_AA2_COUNT ? DSB_LINE_AA2_COVER : DSB_LINE_AA2_VALUE;
   a.line_width = line_width; a.canvas = nullptr; a.mask = nullptr; a.overwrite = 1; a.use_plan = 0; a.row_offset = row_offset;
+  a.cat = nullptr; a.cat_dtype = DSB_NONE; a.ncat = 0;
   int rc = apply_layout(a, layout, "dsb_lines_aa2");
   if (rc != DSB_OK) return rc;
   const double mx = view->x_log ? log10(view->xmax) : view->xmax, my = view->y_log ? log10(view->ymax) : view->ymax;

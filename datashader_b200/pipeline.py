@@ -318,7 +318,9 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
     combo = _aa2_combo(agg)
     if combo is not None:
         return _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist)
-    if isinstance(agg, (rd.summary, rd.by)) or agg._line_agg is None:
+    # single-stage antialiased reductions: any / count / sum / max / mean, optionally per category (by)
+    red = agg.reduction if isinstance(agg, rd.by) else agg
+    if isinstance(red, (rd.summary, rd.by)) or getattr(red, "_line_agg", None) is None or _aa2_combo(red) is not None:
         raise NotImplementedError(f"{type(agg).__name__} is not implemented for antialiased datashader_b200 lines yet")
 
     device = frame.device
@@ -326,35 +328,41 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
         x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout) = _line_setup(frame, canvas, glyph, dist)
         H, W = canvas.plot_height, canvas.plot_width
-        la = agg._line_agg
+        categorizer, ncat, labels = _categorical_setup(agg, schema)
+        codes = categorizer.codes(frame).contiguous() if ncat else None
+        shape = (H, W) + ((ncat,) if ncat else ())
+        ncell = int(np.prod(shape))
+        la = red._line_agg
         aa = line_width > 0
         val, val_dtype = None, _lib.NONE
-        if agg.column is not None:
-            val = frame[agg.column]
-            val_dtype = _lib.dsb_dtype(frame.np_dtype(agg.column))
+        if red.column is not None:
+            val = frame[red.column]
+            val_dtype = _lib.dsb_dtype(frame.np_dtype(red.column))
         mask = None
         lib = _lib.lib()
         # accumulator canvases per dsb_lines_axis1's contract (include/dsb200.h)
         if la == _lib.LINE_ANY:
-            canvas_t = torch.empty((H, W), dtype=torch.int32 if aa else torch.uint8, device=device)
-            _lib.check(lib.dsb_init_canvas(_lib.OP_MAX32 if aa else _lib.OP_ANY, canvas_t.data_ptr(), H * W, stream_ptr))
+            canvas_t = torch.empty(shape, dtype=torch.int32 if aa else torch.uint8, device=device)
+            _lib.check(lib.dsb_init_canvas(_lib.OP_MAX32 if aa else _lib.OP_ANY, canvas_t.data_ptr(), ncell, stream_ptr))
         elif la == _lib.LINE_COUNT:
-            canvas_t = torch.zeros((H, W), dtype=torch.float32 if aa else torch.int32, device=device)
-            mask = torch.zeros((H, W), dtype=torch.uint8, device=device) if aa else None
+            canvas_t = torch.zeros(shape, dtype=torch.float32 if aa else torch.int32, device=device)
+            mask = torch.zeros(shape, dtype=torch.uint8, device=device) if aa else None
         elif la == _lib.LINE_SUM:
-            canvas_t = torch.zeros((H, W), dtype=torch.float64, device=device)
-            mask = torch.zeros((H, W), dtype=torch.uint8, device=device)
+            canvas_t = torch.zeros(shape, dtype=torch.float64, device=device)
+            mask = torch.zeros(shape, dtype=torch.uint8, device=device)
         elif la == _lib.LINE_MEAN:
-            canvas_t = torch.zeros((H, W), dtype=torch.float64, device=device)
-            mask = torch.zeros((H, W), dtype=torch.int32, device=device)        # the count canvas
+            canvas_t = torch.zeros(shape, dtype=torch.float64, device=device)
+            mask = torch.zeros(shape, dtype=torch.int32, device=device)        # the count canvas
         else:
-            canvas_t = torch.empty((H, W), dtype=torch.int64, device=device)
+            canvas_t = torch.empty(shape, dtype=torch.int64, device=device)
             _lib.check(lib.dsb_init_canvas(_lib.OP_MAX64 if la == _lib.LINE_MAX else _lib.OP_MIN64, canvas_t.data_ptr(),
-                                           H * W, stream_ptr))
-        _lib.check(lib.dsb_lines_axis1(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, nlines, nverts, C.byref(layout),
-                                       val.data_ptr() if val is not None else None, val_dtype, la, line_width,
-                                       canvas_t.data_ptr(), mask.data_ptr() if mask is not None else None, stream_ptr),
-                   "dsb_lines_axis1")
+                                           ncell, stream_ptr))
+        _lib.check(lib.dsb_lines_axis1_cat(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, nlines, nverts, C.byref(layout),
+                                           val.data_ptr() if val is not None else None, val_dtype, la, line_width,
+                                           canvas_t.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                           codes.data_ptr() if ncat else None,
+                                           _lib.dsb_dtype(str(codes.dtype).replace("torch.", "")) if ncat else _lib.NONE, ncat,
+                                           stream_ptr), "dsb_lines_axis1_cat")
         if dist is not None:
             if la == _lib.LINE_MEAN:
                 dist._all_reduce(canvas_t, "sum")
@@ -364,8 +372,8 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
         # finishing (dtypes pinned by test_pandas.py:3257-3277: AA any/count -> f32, others f64)
         if la == _lib.LINE_ANY:
             if aa:
-                out = torch.empty((H, W), dtype=torch.float64, device=device)
-                _lib.check(lib.dsb_decode_minmax(canvas_t.data_ptr(), _lib.OP_MAX32, _lib.F32, out.data_ptr(), H * W, stream_ptr))
+                out = torch.empty(shape, dtype=torch.float64, device=device)
+                _lib.check(lib.dsb_decode_minmax(canvas_t.data_ptr(), _lib.OP_MAX32, _lib.F32, out.data_ptr(), ncell, stream_ptr))
                 data = _to_host(out.to(torch.float32))
             else:
                 data = _to_host(canvas_t, np.bool_)
@@ -377,22 +385,26 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
                 data = _to_host(canvas_t, np.uint32)
         elif la == _lib.LINE_SUM:
             out = torch.empty_like(canvas_t)
-            _lib.check(lib.dsb_finalize_sum(canvas_t.data_ptr(), mask.data_ptr(), out.data_ptr(), H * W, stream_ptr))
+            _lib.check(lib.dsb_finalize_sum(canvas_t.data_ptr(), mask.data_ptr(), out.data_ptr(), ncell, stream_ptr))
             data = _to_host(out)
         elif la == _lib.LINE_MEAN:
             out = torch.empty_like(canvas_t)
-            _lib.check(lib.dsb_finalize_mean(canvas_t.data_ptr(), mask.data_ptr(), out.data_ptr(), H * W, stream_ptr))
+            _lib.check(lib.dsb_finalize_mean(canvas_t.data_ptr(), mask.data_ptr(), out.data_ptr(), ncell, stream_ptr))
             data = _to_host(out)
         else:
-            out = torch.empty((H, W), dtype=torch.float64, device=device)
+            out = torch.empty(shape, dtype=torch.float64, device=device)
             _lib.check(lib.dsb_decode_minmax(canvas_t.data_ptr(), _lib.OP_MAX64 if la == _lib.LINE_MAX else _lib.OP_MIN64,
-                                             _lib.F64, out.data_ptr(), H * W, stream_ptr))
+                                             _lib.F64, out.data_ptr(), ncell, stream_ptr))
             data = _to_host(out)
 
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
-    return DataArray(data, coords={glyph.y_label: y_axis, glyph.x_label: x_axis}, dims=[glyph.y_label, glyph.x_label],
-                     attrs=dict(x_range=x_range, y_range=y_range))
+    coords = {glyph.y_label: y_axis, glyph.x_label: x_axis}
+    dims = [glyph.y_label, glyph.x_label]
+    if ncat:                          # by._build_finalize, reductions.py:809-820
+        coords[agg.cat_column] = list(labels)
+        dims.append(agg.cat_column)
+    return DataArray(data, coords=coords, dims=dims, attrs=dict(x_range=x_range, y_range=y_range))
 
 
 def _aa2_combo(agg):

@@ -165,6 +165,14 @@ int dsb_lines_axis1(const dsb_view* view, const void* xs, const void* ys, int32_
                     int64_t nverts, const dsb_line_layout* layout, const void* val, int32_t val_dtype, int32_t agg,
                     double line_width, void* canvas, uint8_t* mask, void* stream);
 
+/* The same with a category column (antialiased by(cat, any | count | sum | max | mean), compiler.py:379-390): canvases
+ * are [H, W, ncat], every line (or vertex row, axis=0 layouts) updates the plane of its category; negative codes wrap
+ * like numba's agg[:, :, -1].  ncat == 0: identical to dsb_lines_axis1. */
+int dsb_lines_axis1_cat(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
+                        int64_t nverts, const dsb_line_layout* layout, const void* val, int32_t val_dtype, int32_t agg,
+                        double line_width, void* canvas, uint8_t* mask, const void* cat, int32_t cat_dtype, int32_t ncat,
+                        void* stream);
+
 /* LinesAxis1 with line_width == 0 and a full accumulator plan (every reduction dsb_points supports): the plan runs
  * for every pixel a line touches with i = the line's row, exactly how the reference hands the row index to append()
  * from _bresenham (line.py:1006-1031).  Value / nan-check / category columns are per line ([nlines]). */

@@ -390,6 +390,19 @@ def lines_aa2_cases():
         for lw in ((1, 2.5) if tag == "f32" else (1,)):
             for aname, agg in aggs.items():
                 out[f"aa2_{tag}_lw{lw}_{aname}"] = np.asarray(cvs.line(df, x=xcols, y=ycols, axis=1, agg=agg, line_width=lw).data)
+    # antialiased by(cat, r) on the 40-line f32 frame (categories from lines_extra.npz: in_cat)
+    xs, ys, val = line_frame(2024, 40, 24, np.float32)
+    nverts = xs.shape[1]
+    codes = np.load(os.path.join(HERE, "lines_extra.npz"))["in_cat"]
+    d = {f"x{j}": xs[:, j] for j in range(nverts)}
+    d.update({f"y{j}": ys[:, j] for j in range(nverts)})
+    d["val"] = val
+    d["cat"] = pd.Categorical.from_codes(codes, categories=["a", "b", "c", "d"])
+    df = pd.DataFrame(d)
+    xcols, ycols = [f"x{j}" for j in range(nverts)], [f"y{j}" for j in range(nverts)]
+    cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+    for aname, inner in {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "mean": ds.mean("val")}.items():
+        out[f"aaby_lw2_{aname}"] = np.asarray(cvs.line(df, x=xcols, y=ycols, axis=1, agg=ds.by("cat", inner), line_width=2).data)
     # axis=0 layouts: the line_layouts.npz inputs (ax0_x, ax0_y, ax0_x2, ax0_y2, ax0_val)
     g = np.load(os.path.join(HERE, "line_layouts.npz"))
     df0 = pd.DataFrame({k: g[f"ax0_{k}"] for k in ("x", "y", "x2", "y2", "val")})

@@ -242,3 +242,21 @@ def test_lines_aa2_long_lines_overflow_the_stage1_table():
         oname, mk = AA2[gname]
         got = cvs.line(frame, x=xcols, y=ycols, axis=1, agg=mk(ds), line_width=4).data
         _cmp_aa(got, ora.lines_aa2(xs, ys, view, oname, val, 4), gname, rtol=2e-6)
+
+
+def test_lines_aa_by_category_golden():
+    """Antialiased by('cat', any | count | sum | max | mean): every line updates the [H, W] plane of its category."""
+    import pandas as pd
+    import datashader_b200 as ds
+    g, gl, ge = load("lines_aa2.npz"), load("lines.npz"), load("lines_extra.npz")
+    frame, xcols, ycols = _frame(gl["in_f32_xs"], gl["in_f32_ys"], gl["in_f32_val"])
+    frame["cat"] = pd.Categorical.from_codes(ge["in_cat"], categories=["a", "b", "c", "d"])
+    cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+    inner = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "mean": ds.mean("val")}
+    for aname, red in inner.items():
+        r = cvs.line(frame, x=xcols, y=ycols, axis=1, agg=ds.by("cat", red), line_width=2)
+        want = g[f"aaby_lw2_{aname}"]
+        assert tuple(r.dims) == ("y", "x", "cat") and list(r.coords["cat"]) == ["a", "b", "c", "d"], aname
+        _cmp_aa(r.data, want, f"aa by {aname}")
+    with pytest.raises(NotImplementedError):
+        cvs.line(frame, x=xcols, y=ycols, axis=1, agg=ds.by("cat", ds.min("val")), line_width=2)

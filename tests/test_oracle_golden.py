@@ -258,3 +258,16 @@ def test_lines_aa2_golden():
             want = g[f"aa2_{key}_lw2_{gname}"]
             assert got.dtype == want.dtype and np.array_equal(np.isnan(got), np.isnan(want)), (key, gname)
             np.testing.assert_allclose(got, want, rtol=1e-6 if oname == "count" else 1e-12, equal_nan=True, err_msg=f"{key} {gname}")
+
+
+def test_lines_aa_by_category_golden():
+    """Antialiased by('cat', r): the oracle's per-category restatement vs the reference."""
+    g, gl, ge = load("lines_aa2.npz"), load("lines.npz"), load("lines_extra.npz")
+    view = ora.make_view(64, 48, (0, 1), (0, 1))
+    xs, ys, val, codes = gl["in_f32_xs"], gl["in_f32_ys"], gl["in_f32_val"], ge["in_cat"]
+    for aname in ("any", "count", "sum", "max", "mean"):
+        got = ora.lines_by(xs, ys, view, codes, 4, aname, None if aname in ("any", "count") else val, 2)
+        want = g[f"aaby_lw2_{aname}"]
+        assert got.dtype == want.dtype and got.shape == want.shape, aname
+        assert np.array_equal(np.isnan(got), np.isnan(want)), aname
+        np.testing.assert_allclose(got, want, rtol=1e-6 if aname == "count" else 1e-12, equal_nan=True, err_msg=aname)
