@@ -18,3 +18,7 @@ priv_min_rows = 1 << 24        # measured crossover vs global REDs: ~15-20 M row
 count16 = True
 count16_min_rows = 1 << 22
 l2_budget_bytes = 96 << 20
+
+# summary()-style plans (>= 3 accumulators) on small canvases: one specialised launch per accumulator group instead of
+# one interpreted pass (pipeline._specialised_groups).
+split_summary = True

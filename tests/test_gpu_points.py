@@ -414,3 +414,32 @@ def test_count16_packed_path_matches_oracle(ds):
         assert got.max() >= 200_000
     finally:
         ds.config.count16_min_rows, ds.config.l2_budget_bytes = old
+
+
+def test_summary_split_into_specialised_groups_matches_oracle(ds, force_priv):
+    """summary() with >= 3 accumulators on a small canvas is routed group by group to the specialised kernels
+    (pipeline._specialised_groups); every member must still equal the oracle, with and without the split."""
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(77)
+    n = (1 << 20) + 123
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": np.round(rng.standard_normal(n), 2).astype(np.float32)}
+    cols["v32"][rng.integers(0, n, 2000)] = np.nan
+    W, H = 200, 150
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    specs = {"c": ("count",), "m": ("mean", "v32"), "mx": ("max", "v32"), "mn": ("min", "v32"), "f": ("first", "v32"),
+             "s": ("sum", "v32")}
+    agg = ds.summary(**{k: make_agg(v) for k, v in specs.items()})
+    old = ds.config.split_summary
+    try:
+        for split in (True, False):
+            ds.config.split_summary = split
+            got = cvs.points(frame, "x", "y", agg)
+            for k, spec in specs.items():
+                want = ora.points(cols, "x", "y", spec, view, npartitions=2 if spec[0] == "first" else 1)
+                assert_agg_equal(np.asarray(got[k].data), want, f"summary split={split} {k}")
+    finally:
+        ds.config.split_summary = old

@@ -53,7 +53,7 @@ def main():
             "min": ds.min("value"), "first": ds.first("value"), "last": ds.last("value"),
             "where_max": ds.where(ds.max("value"), "x"), "where_max_row": ds.where(ds.max("value")),
             "by_count": ds.by("cat", ds.count()), "by_mean": ds.by("cat", ds.mean("value")),
-            "summary(count,mean,max)": ds.summary(c=ds.count(), m=ds.mean("value"), mx=ds.max("value"))}
+            "summary3": ds.summary(c=ds.count(), m=ds.mean("value"), mx=ds.max("value"))}
     out = {}
     if a.only:
         aggs = {k: v for k, v in aggs.items() if k in a.only.split(",")}
