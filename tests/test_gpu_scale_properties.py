@@ -67,3 +67,53 @@ def test_mean_k2_vs_k1_and_max_idempotence(big):
     mx = _run(ds, frame, ds.max("value"), False)
     twice = ds.DeviceFrame({"x": torch.cat([x[:half], x]), "y": torch.cat([y[:half], y]), "value": torch.cat([v[:half], v])})
     assert np.array_equal(_run(ds, twice, ds.max("value"), False), mx, equal_nan=True)
+
+
+def _configure(ds, key, value):
+    ds._lib.check(ds._lib.lib().dsb_configure(key.encode(), int(value)), "dsb_configure")
+
+
+def test_mono_kernel_equals_generic_at_scale(big):
+    """k_points_mono (filtered, vectorised) == k_points_generic bit for bit on 2e8 points for every monotone reduction;
+    first <= last row-wise; where(max) returns a row whose value is the pixel's max."""
+    ds, torch, n, x, y, v = big
+    frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
+    aggs = {"max": ds.max("value"), "min": ds.min("value"), "first": ds.first("value"), "last": ds.last("value"),
+            "where_max_row": ds.where(ds.max("value")), "where_min_row": ds.where(ds.min("value"))}
+    out = {}
+    for name, agg in aggs.items():
+        _configure(ds, "mono", 1)
+        a = _run(ds, frame, agg, False)
+        _configure(ds, "mono", 0)
+        try:
+            b = _run(ds, frame, agg, False)
+        finally:
+            _configure(ds, "mono", 1)
+        assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), name
+        out[name] = a
+    assert np.all((out["min"] <= out["max"]) | np.isnan(out["max"]))
+    rows = torch.from_numpy(out["where_max_row"]).cuda()
+    hit = rows >= 0
+    picked = v[rows[hit]].cpu().numpy()
+    assert np.array_equal(picked, out["max"][hit.cpu().numpy()])
+
+
+def test_count16_equals_u32_count_at_scale(big):
+    """by('cat', count()) through the 16-bit packed path == the u32 path, and conserves the number of rows in range."""
+    ds, torch, n, x, y, v = big
+    m = 60_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    cat = torch.randint(0, 16, (m,), generator=g, device="cuda", dtype=torch.int8)
+    frame = ds.DeviceFrame({"x": x[:m], "y": y[:m], "cat": cat}, categories={"cat": [f"c{i}" for i in range(16)]})
+    cvs = ds.Canvas(1920, 1080, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    a = cvs.points(frame, "x", "y", ds.by("cat", ds.count())).data
+    old = ds.config.count16
+    ds.config.count16 = False
+    try:
+        b = cvs.points(frame, "x", "y", ds.by("cat", ds.count())).data
+    finally:
+        ds.config.count16 = old
+    assert np.array_equal(a, b)
+    inside = int(((x[:m] >= 0) & (x[:m] <= 1) & (y[:m] >= 0) & (y[:m] <= 1)).sum().item())
+    assert int(a.sum(dtype=np.int64)) == inside
