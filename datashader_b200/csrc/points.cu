@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
   const float* __restrict__ y = (const float*)a.y;
   const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
   constexpr bool IS_MAX = OP == MONO_MAX32 || OP == MONO_MAXROW || OP == MONO_ARGMAX32;
-  constexpr bool FILTERED = true;
+  constexpr bool FILTERED = !BANDED;     // banded passes of big canvases: ~15 hits per pixel leave the filter little to remove
   // "last" = the largest row id: walking the rows forwards every hit wins and pays a RED; walked BACKWARDS the first
   // hit of a pixel is final and the filter removes the rest, as for "first"
   constexpr bool REVERSE = OP == MONO_MAXROW;
@@ -549,9 +549,7 @@ static long long g_priv_smem_kb = 192;        // shared memory the privatised ca
 static long long g_priv_smem_kb_mean = 226;   // the same for the mean() shape
 static long long g_split_bytes = 48LL << 20;  // plans whose canvases total more than this run one pass per accumulator
 static int g_mono = 1;                       // use k_points_mono for single monotone accumulators
-static int g_mono_banded = 0;                //   ... for the L2-banded passes of big canvases too: measured slower (8192^2,
-                                             //   1e9 points: max 20.7 -> 29.5 ms, first 32.7 -> 49.6 ms: ~15 hits per pixel
-                                             //   leave the filter little to remove), kept as a knob
+static int g_mono_banded = 1;                //   ... also for the L2-banded passes of big canvases (without the filter)
 static int g_priv_tight = 1;                 // use k_points_priv_tight for the count() / mean(f32) shapes
 static long long l2_band_budget_bytes() {
   if (g_band_budget < 0) {
@@ -668,7 +666,17 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
   for (int k = 0; k < plan->nops; k++) bytes_per_pixel += op_cell_bytes(plan->ops[k].op);
   bytes_per_pixel *= (plan->ncat > 0 ? plan->ncat : 1);
   const long long npixels = (long long)view->width * view->height;
-  const long long budget = l2_band_budget_bytes();
+  long long budget = l2_band_budget_bytes();
+  // Measured on 8192^2 canvases, 1e9 points (profiles/r01b_l2_banding.md, sweep of 48..160 MB): 4-byte accumulators
+  // (count, max / min keys) are fastest with bands of 2/3 of the budget (64 MB: 14.8 / 16.6 ms vs 19.4 / 18.8 at 96),
+  // first / last row-index canvases with 4/3 (128 MB: 12.7 vs 18.8 ms - a min/max RED that does not change the value
+  // leaves its sector clean, so larger bands do not pay write-backs); the packed where() keys stay at the budget.
+  {
+    bool all4 = true, rowonly = plan->nops == 1 && (plan->ops[0].op == DSB_OP_MINROW || plan->ops[0].op == DSB_OP_MAXROW);
+    for (int k = 0; k < plan->nops; k++) all4 = all4 && op_cell_bytes(plan->ops[k].op) == 4;
+    if (all4) budget = budget * 2 / 3;
+    else if (rowonly) budget = budget * 4 / 3;
+  }
   long long nbands = 1;
   if (budget > 0 && bytes_per_pixel * npixels > budget && n >= g_band_min_rows) {
     nbands = (bytes_per_pixel * npixels + budget - 1) / budget;
