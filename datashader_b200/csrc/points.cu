@@ -353,11 +353,13 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
 // k_points_generic by the K2-tight front end (vector loads, float32 fast mapping with the exact f64 mapping deferred
 // to the ~0.1 % of points near a pixel edge) and batches the load-before-RED filter: the eight current values of a
 // batch are fetched first (eight independent L2 loads in flight), then compared, and only winners issue a RED.
-enum { MONO_MAX32 = 0, MONO_MIN32 = 1, MONO_MINROW = 2, MONO_MAXROW = 3, MONO_ARGMAX32 = 4, MONO_ARGMIN32 = 5 };
+enum { MONO_MAX32 = 0, MONO_MIN32 = 1, MONO_MINROW = 2, MONO_MAXROW = 3, MONO_ARGMAX32 = 4, MONO_ARGMIN32 = 5,
+       MONO_COUNT = 6 };   // count([col]) rides along for the banded passes of big canvases (plain RED, no filter)
 
 template <int OP> struct MonoT { typedef long long cell_t; };
 template <> struct MonoT<MONO_MAX32> { typedef int cell_t; };
 template <> struct MonoT<MONO_MIN32> { typedef int cell_t; };
+template <> struct MonoT<MONO_COUNT> { typedef unsigned int cell_t; };
 
 template <int OP, bool BANDED>
 __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ PointsArgs a, const __grid_constant__ FastMap fm,
@@ -368,20 +370,22 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
   const float* __restrict__ y = (const float*)a.y;
   const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
   constexpr bool IS_MAX = OP == MONO_MAX32 || OP == MONO_MAXROW || OP == MONO_ARGMAX32;
-  constexpr bool FILTERED = !BANDED;     // banded passes of big canvases: ~15 hits per pixel leave the filter little to remove
+  constexpr bool FILTERED = !BANDED && OP != MONO_COUNT;   // banded passes of big canvases: ~15 hits per pixel leave the filter little to remove
   // "last" = the largest row id: walking the rows forwards every hit wins and pays a RED; walked BACKWARDS the first
   // hit of a pixel is final and the filter removes the rest, as for "first"
   constexpr bool REVERSE = OP == MONO_MAXROW;
 
   auto key_of = [&](float vv, long long i) -> T {
     const long long row = a.row_offset + i;
+    if (OP == MONO_COUNT) return (T)1;
     if (OP == MONO_MAX32 || OP == MONO_MIN32) return (T)key32_from_f32(vv);
     if (OP == MONO_MINROW || OP == MONO_MAXROW) return (T)row;
     const long long k = (long long)key32_from_f32(vv) << 32;          // see apply_base: value first, earliest row on ties
     return (T)(OP == MONO_ARGMAX32 ? (k | (long long)(uint32_t)(~(uint32_t)row)) : (k | (long long)(uint32_t)row));
   };
   auto commit = [&](int cell, T key, T cur) {
-    if (IS_MAX) { if (!FILTERED || key > cur) atomicMax(canvas + cell, key); }
+    if constexpr (OP == MONO_COUNT) { atomicAdd(canvas + cell, (T)1); return; }
+    else if (IS_MAX) { if (!FILTERED || key > cur) atomicMax(canvas + cell, key); }
     else { if (key < cur) atomicMin(canvas + cell, key); }
   };
   auto exact = [&](float xv, float yv, float vv, long long i) {
@@ -402,8 +406,11 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
     const bool two = t4 + stride < n4;
     const long long i4 = REVERSE ? n4 - 1 - t4 : t4;
     const long long j4 = REVERSE ? i4 - stride : i4 + stride;
-    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = __ldcs(v4 + i4);
-    const float4 xb = two ? __ldcs(x4 + j4) : nan4, yb = two ? __ldcs(y4 + j4) : nan4, vb = two ? __ldcs(v4 + j4) : nan4;
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);      // count() without a column: nothing to NaN-check
+    const bool hasv = OP != MONO_COUNT || vcol != nullptr;      // compile-time true for everything but count()
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = hasv ? __ldcs(v4 + i4) : one4;
+    const float4 xb = two ? __ldcs(x4 + j4) : nan4, yb = two ? __ldcs(y4 + j4) : nan4;
+    const float4 vb = two ? (hasv ? __ldcs(v4 + j4) : one4) : nan4;
     const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
     const float ys[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
     const float vs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
   }
   if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {           // tail rows
     const long long i = (n4 << 2) + threadIdx.x;
-    exact(x[i], y[i], vcol[i], i);
+    exact(x[i], y[i], vcol ? vcol[i] : 1.f, i);
   }
 }
 
@@ -467,9 +474,13 @@ static bool try_launch_mono(const PointsArgs& a, int32_t xy_dtype, bool banded, 
     case DSB_OP_ARGMIN32: op = MONO_ARGMIN32; break;
     case DSB_OP_MINROW: op = MONO_MINROW; break;
     case DSB_OP_MAXROW: op = MONO_MAXROW; break;
+    case DSB_OP_COUNT: if (!banded) return false; op = MONO_COUNT; break;   // unbanded counts are RED-bound either way
     default: return false;
   }
-  if (op == MONO_MINROW || op == MONO_MAXROW) {            // first / last: the row id, gated by the nan-check column
+  if (op == MONO_COUNT) {                                  // count(): optional float32 column to NaN-check
+    if (b.chk_dtype != DSB_NONE || (b.val_dtype != DSB_NONE && b.val_dtype != DSB_F32)) return false;
+    vcol = b.val_dtype == DSB_F32 ? (const float*)b.val : nullptr;
+  } else if (op == MONO_MINROW || op == MONO_MAXROW) {     // first / last: the row id, gated by the nan-check column
     if (b.chk_dtype != DSB_F32 || !b.chk || b.val_dtype != DSB_NONE) return false;
     vcol = (const float*)b.chk;
   } else {
@@ -486,6 +497,7 @@ static bool try_launch_mono(const PointsArgs& a, int32_t xy_dtype, bool banded, 
     case MONO_MINROW: launch_mono<MONO_MINROW>(a, fm, vcol, banded, s); break;
     case MONO_MAXROW: launch_mono<MONO_MAXROW>(a, fm, vcol, banded, s); break;
     case MONO_ARGMAX32: launch_mono<MONO_ARGMAX32>(a, fm, vcol, banded, s); break;
+    case MONO_COUNT: launch_mono<MONO_COUNT>(a, fm, vcol, banded, s); break;
     default: launch_mono<MONO_ARGMIN32>(a, fm, vcol, banded, s); break;
   }
   return true;
