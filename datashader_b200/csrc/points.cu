@@ -915,6 +915,76 @@ __global__ void __launch_bounds__(256) k_points_count16(const PointsArgs a, unsi
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(accepted, mine);
 }
 
+
+// count16 with the tight front end: float32 coordinates on linear axes, optional 1-byte category codes (by('cat',
+// count()): four codes per 32-bit load beside the float4 of x and y), optional float32 column to NaN-check.  Same
+// contract as k_points_count16.
+template <bool CAT>
+__global__ void __launch_bounds__(256, 3) k_points_count16_tight(const __grid_constant__ PointsArgs a, const __grid_constant__ FastMap fm,
+                                                                 const float* __restrict__ vcol, unsigned int* __restrict__ packed,
+                                                                 unsigned long long* __restrict__ accepted) {
+  const float* __restrict__ x = (const float*)a.x;
+  const float* __restrict__ y = (const float*)a.y;
+  const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
+  const int ncat = a.plan.ncat;
+  const bool cat_signed = a.plan.cat_dtype == DSB_I8;
+  const uint8_t* __restrict__ cat = (const uint8_t*)a.plan.cat;
+  unsigned long long mine = 0;
+  auto code_of = [&](uint32_t byte) -> int {
+    int c = cat_signed ? (int)(int8_t)byte : (int)byte;
+    if (c < 0) c += ncat;                                 // numba wraparound for agg[:, :, -1]
+    return (c < 0 || c >= ncat) ? -1 : c;
+  };
+  auto put = [&](long long cell) {
+    atomicAdd(packed + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
+    mine++;
+  };
+  auto exact = [&](float xv, float yv, float vv, int code) {
+    if (vv != vv || (CAT && code < 0)) return;
+    const int cell = map_exact_linear(a.v, xv, yv);
+    if (cell < 0) return;
+    put(CAT ? (long long)cell * ncat + code : (long long)cell);
+  };
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const float4* __restrict__ v4 = (const float4*)vcol;
+  const uint32_t* __restrict__ c4 = (const uint32_t*)a.plan.cat;
+  const long long n4 = a.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = vcol ? __ldcs(v4 + i4) : one4;
+    const uint32_t cw = CAT ? __ldcs(c4 + i4) : 0u;
+    const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w}, vs[4] = {va.x, va.y, va.z, va.w};
+    uint32_t slow = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float xf = fmaf(xs[k], fm.sx, fm.tx), yf = fmaf(ys[k], fm.sy, fm.ty);
+      const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+      const float dx = xf - (float)xi, dy = yf - (float)yi;
+      const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
+      const int code = CAT ? code_of((cw >> (8 * k)) & 255u) : 0;
+      const bool ok = sure && (uint32_t)xi < W && (uint32_t)yi < H && vs[k] == vs[k] && code >= 0;
+      if (ok) {
+        const long long cell = (long long)(yi * (int)W + xi);
+        put(CAT ? cell * ncat + code : cell);
+      }
+      slow |= (uint32_t)(!sure) << k;
+    }
+    if (slow) {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (slow & (1u << k)) exact(xs[k], ys[k], vs[k], CAT ? code_of((cw >> (8 * k)) & 255u) : 0);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {           // tail rows
+    const long long i = (n4 << 2) + threadIdx.x;
+    exact(x[i], y[i], vcol ? vcol[i] : 1.f, CAT ? code_of(cat[i]) : 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(accepted, mine);
+}
+
 __global__ void k_sum16(const unsigned int* __restrict__ packed, long long nwords, unsigned long long* __restrict__ total) {
   unsigned long long t = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
@@ -959,7 +1029,20 @@ extern "C" int dsb_points_count16(const dsb_view* view, const void* x, const voi
   long long want = (n + (long long)threads * 4 - 1) / ((long long)threads * 4);
   const long long cap = (long long)dsb_num_sms() * 8;
   const int grid = (int)(want < cap ? want : cap);
-  if (l2_persist_enabled()) {
+  // the tight front end when it applies: float32 coordinates on linear axes, 1-byte category codes (or none), an optional
+  // float32 NaN-check column, everything 16-byte (codes: 4-byte) aligned
+  const dsb_base& cb = plan->ops[0];
+  const FastMap fm = make_fast_map(view);
+  const bool cat1 = plan->ncat > 0 && (plan->cat_dtype == DSB_I8 || plan->cat_dtype == DSB_U8) && (((uintptr_t)plan->cat) & 3) == 0;
+  const bool tight_ok = g_priv_tight && xy_dtype == DSB_F32 && fm.enabled && ncell < (1LL << 31) && (plan->ncat == 0 || cat1) &&
+                        cb.chk_dtype == DSB_NONE && (cb.val_dtype == DSB_NONE || (cb.val_dtype == DSB_F32 && (((uintptr_t)cb.val) & 15) == 0)) &&
+                        ((((uintptr_t)x | (uintptr_t)y)) & 15) == 0 && g_count16_band_bytes == 0 && !l2_persist_enabled();
+  if (tight_ok) {
+    const float* vcol = cb.val_dtype == DSB_F32 ? (const float*)cb.val : nullptr;
+    const int g3 = dsb_num_sms() * 3;
+    if (plan->ncat > 0) k_points_count16_tight<true><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st);
+    else k_points_count16_tight<false><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st);
+  } else if (l2_persist_enabled()) {
     // opt-in (DSB_L2_PERSIST=1): pin the packed canvas in L2, everything else streams
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
