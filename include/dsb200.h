@@ -91,7 +91,10 @@ int64_t dsb_launch_count(void);
 /* Runtime knobs: "l2_band_bytes" - accumulator bytes one dsb_points launch may touch before the rows are re-read
  * once per band of canvas rows (default 96 MiB, 0 disables); "band_min_rows" - smallest n that is banded;
  * "priv_smem_kb" / "priv_smem_kb_mean" - shared memory dsb_points_priv may take for the privatised canvas (defaults
- * 192 / 226 KB, see points.cu); "priv_tight" - 0 disables the specialised count()/mean() kernels (A/B testing). */
+ * 192 / 226 KB, see points.cu); "priv_tight" - 0 disables the specialised count()/mean() kernels (A/B testing);
+ * "mono" / "mono_banded" - 0 disables k_points_mono (single monotone accumulator) / its use in banded passes;
+ * "split_bytes" - plans whose canvases total more than this run one pass per accumulator (default 48 MiB, 0 = never);
+ * "count16_band_bytes" - optional banding of dsb_points_count16's packed canvas (default 0 = off). */
 int dsb_configure(const char* key, int64_t value);
 
 /* Initialise an accumulator canvas of `ncell` elements to the op's identity (see dsb_op).
