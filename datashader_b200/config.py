@@ -22,3 +22,7 @@ l2_budget_bytes = 96 << 20
 # summary()-style plans (>= 3 accumulators) on small canvases: one specialised launch per accumulator group instead of
 # one interpreted pass (pipeline._specialised_groups).
 split_summary = True
+
+# Bresenham lines with any / count / sum / max / min: the line kernel's own appends (the line's value held in a register)
+# instead of the accumulator-plan interpreter, which re-reads the value column for every pixel.
+lines_simple_path = True

@@ -358,14 +358,16 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
     if dist is not None and glyph.value_per_vertex:
         frame, frame.plot_start = dist.carry_last_row(frame, needed)     # row shards of one long line (dask.py:244-266)
     line_width = float(glyph._line_width)
-    if line_width == 0:
+    simple = config.lines_simple_path and type(agg) in (rd.any, rd.count, rd.sum, rd.max, rd.min)
+    if line_width == 0 and not simple:
         return _lines_plan(frame, needed, schema, canvas, glyph, agg, dist)
-    combo = _aa2_combo(agg)
+    combo = _aa2_combo(agg) if line_width > 0 else None
     if combo is not None:
         return _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist)
     # single-stage antialiased reductions: any / count / sum / max / mean, optionally per category (by)
     red = agg.reduction if isinstance(agg, rd.by) else agg
-    if isinstance(red, (rd.summary, rd.by)) or getattr(red, "_line_agg", None) is None or _aa2_combo(red) is not None:
+    if (isinstance(red, (rd.summary, rd.by)) or getattr(red, "_line_agg", None) is None
+            or (line_width > 0 and _aa2_combo(red) is not None)):
         raise NotImplementedError(f"{type(agg).__name__} is not implemented for antialiased datashader_b200 lines yet")
 
     device = frame.device
