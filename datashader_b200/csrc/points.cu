@@ -461,9 +461,11 @@ static void launch_mono(const PointsArgs& a, const FastMap& fm, const float* vco
   else k_points_mono<OP, false><<<grid, 256, 0, s>>>(a, fm, vcol);
 }
 
+static long long g_mono_min_rows = 1LL << 20;   // below this the generic kernel's launch is as fast
+
 static bool try_launch_mono(const PointsArgs& a, int32_t xy_dtype, bool banded, cudaStream_t s) {
   const dsb_plan& p = a.plan;
-  if (xy_dtype != DSB_F32 || p.nops != 1 || p.ncat != 0 || a.n < (1LL << 20)) return false;
+  if (xy_dtype != DSB_F32 || p.nops != 1 || p.ncat != 0 || a.n < g_mono_min_rows) return false;
   const dsb_base& b = p.ops[0];
   int op = -1;
   const float* vcol = nullptr;
@@ -584,6 +586,7 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "split_bytes")) { g_split_bytes = value; return DSB_OK; }
   if (!strcmp(key, "count16_band_bytes")) { g_count16_band_bytes = value; return DSB_OK; }
   if (!strcmp(key, "mono_banded")) { g_mono_banded = value != 0; return DSB_OK; }
+  if (!strcmp(key, "mono_min_rows")) { g_mono_min_rows = value; return DSB_OK; }
   if (!strcmp(key, "priv_smem_kb")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb = value; return DSB_OK; }
   if (!strcmp(key, "priv_smem_kb_mean")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb_mean must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb_mean = value; return DSB_OK; }
   dsb_set_error("dsb_configure: unknown key %s", key);

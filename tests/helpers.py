@@ -59,13 +59,15 @@ def columns_from_golden(g, prefix):
     return cols
 
 
-def assert_agg_equal(got, want, name, rtol=RTOL_SUM):
+def assert_agg_equal(got, want, name, rtol=RTOL_SUM, atol=0):
+    """Bit-exact except for float sums / means, whose f64 atomic adds run in a different order than the reference's
+    loop: rtol (1e-12), plus `atol` where the values of a pixel may cancel to ~0 (stated by the caller)."""
     got, want = np.asarray(got), np.asarray(want)
     assert got.shape == want.shape, (name, got.shape, want.shape)
     assert got.dtype == want.dtype, (name, got.dtype, want.dtype)
     if is_float_sum(name):
         assert np.array_equal(np.isnan(got), np.isnan(want)), name
-        np.testing.assert_allclose(got, want, rtol=rtol, atol=0, equal_nan=True, err_msg=name)
+        np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, equal_nan=True, err_msg=name)
     else:
         assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), name
 

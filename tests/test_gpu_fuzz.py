@@ -1,0 +1,63 @@
+"""Differential fuzz of Canvas.points against the C oracle: random canvas sizes, ranges (including ranges far from the
+origin, where the float32 fast mapping must hand over to the exact one), coordinate dtypes, reductions and NaN patterns,
+with every specialised kernel forced on at small n (K2 privatised count, K1 mono, 16-bit packed count)."""
+import numpy as np
+import pytest
+
+from helpers import assert_agg_equal, make_agg
+
+pytestmark = pytest.mark.gpu
+
+SPECS = [("count",), ("count", "v32"), ("any",), ("sum", "v32"), ("mean", "v32"), ("max", "v32"), ("min", "v32"),
+         ("first", "v32"), ("last", "v32"), ("where", ("max", "v32"), "other"), ("where", ("min", "v32"), None),
+         ("max", "vi"), ("mean", "v64"), ("by", "cat", ("count",)), ("by", "cat", ("mean", "v32"))]
+
+
+@pytest.fixture()
+def forced(monkeypatch):
+    import datashader_b200 as ds
+    lib = ds._lib.lib()
+    monkeypatch.setattr(ds.config, "priv_min_rows", 0)
+    monkeypatch.setattr(ds.config, "count16_min_rows", 0)
+    ds._lib.check(lib.dsb_configure(b"mono_min_rows", 0), "cfg")
+    ds._lib.check(lib.dsb_configure(b"band_min_rows", 0), "cfg")
+    yield ds
+    ds._lib.check(lib.dsb_configure(b"mono_min_rows", 1 << 20), "cfg")
+    ds._lib.check(lib.dsb_configure(b"band_min_rows", 1 << 22), "cfg")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_points_fuzz_vs_oracle(forced, seed):
+    import torch
+    from oracle import oracle as ora
+    ds = forced
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(20_000, 60_000))
+    W, H = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+    centre = float(rng.choice([0.0, 0.5, -3.0, 1e3, 2.5e5, -7e6]))      # big offsets: the fast mapping's error bound grows
+    span = float(rng.choice([1.0, 0.01, 37.5, 1e4]))
+    xdt = np.float32 if seed % 3 else np.float64
+    x = (centre + span * (rng.random(n) * 1.3 - 0.15)).astype(xdt)
+    y = (centre + span * (rng.random(n) * 1.3 - 0.15)).astype(xdt)
+    xr = (float(np.float64(centre)), float(np.float64(centre + span)))
+    yr = (float(np.float64(centre + 0.1 * span)), float(np.float64(centre + 0.9 * span)))
+    # points exactly on pixel edges and on the range bounds
+    k = min(n, 500)
+    x[:k] = (xr[0] + (xr[1] - xr[0]) * rng.integers(0, W + 1, k) / W).astype(xdt)
+    y[k:2 * k] = (yr[0] + (yr[1] - yr[0]) * rng.integers(0, H + 1, k) / H).astype(xdt)
+    x[2 * k:2 * k + 5] = np.nan
+    ncat = int(rng.integers(2, 6))
+    cols = {"x": x, "y": y, "v32": np.round(rng.standard_normal(n), 1).astype(np.float32), "other": rng.random(n).astype(np.float32),
+            "vi": rng.integers(-9, 9, n).astype(np.int32), "v64": np.round(rng.standard_normal(n), 1),
+            "cat": rng.integers(0, ncat, n).astype(np.int8), "cat__ncat": ncat}
+    cols["v32"][rng.integers(0, n, n // 50)] = np.nan
+    view = ora.make_view(W, H, xr, yr)
+    cvs = ds.Canvas(W, H, x_range=xr, y_range=yr)
+    frame = ds.DeviceFrame({k_: torch.from_numpy(v).cuda() for k_, v in cols.items() if k_ != "cat__ncat"},
+                           categories={"cat": [f"c{i}" for i in range(ncat)]})
+    picks = [SPECS[i] for i in rng.choice(len(SPECS), 6, replace=False)]
+    for spec in picks:
+        want = ora.points(cols, "x", "y", spec, view, npartitions=2 if ("first" in str(spec) or "last" in str(spec)) else 1)
+        got = cvs.points(frame, "x", "y", make_agg(spec)).data
+        # values are multiples of 0.1 that may cancel exactly in the reference's order: 1e-13 absolute on sums / means
+        assert_agg_equal(got, want, f"seed {seed} {W}x{H} centre {centre} span {span} {xdt.__name__} {spec}", atol=1e-13)
