@@ -61,3 +61,55 @@ def test_points_fuzz_vs_oracle(forced, seed):
         got = cvs.points(frame, "x", "y", make_agg(spec)).data
         # values are multiples of 0.1 that may cancel exactly in the reference's order: 1e-13 absolute on sums / means
         assert_agg_equal(got, want, f"seed {seed} {W}x{H} centre {centre} span {span} {xdt.__name__} {spec}", atol=1e-13)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_lines_and_areas_fuzz_vs_oracle(seed):
+    """Random LinesAxis1 frames (float32 / float64, NaN breaks, clipping canvases, ranges away from the origin): Bresenham
+    bit-exact, antialiased single-stage and 2-stage reductions to 1e-6; areas (to zero / to line) bit-exact."""
+    import pandas as pd
+    import datashader_b200 as ds
+    from oracle import oracle as ora
+    rng = np.random.default_rng(500 + seed)
+    nl, nv = int(rng.integers(30, 400)), int(rng.integers(2, 20))
+    dt = np.float32 if seed % 2 else np.float64
+    centre = float(rng.choice([0.0, 10.0, -250.0]))
+    xs = (centre + np.cumsum(rng.normal(0, 0.06, (nl, nv)), axis=1) + rng.random((nl, 1))).astype(dt)
+    ys = (centre + np.cumsum(rng.normal(0, 0.06, (nl, nv)), axis=1) + rng.random((nl, 1))).astype(dt)
+    ys2 = (ys - np.abs(rng.normal(0.1, 0.05, (nl, nv)))).astype(dt)
+    xs[rng.random((nl, nv)) < 0.03] = np.nan
+    val = (rng.random(nl) * 6 - 2).astype(np.float32)
+    val[rng.integers(0, nl, max(1, nl // 20))] = np.nan
+    d = {f"x{j}": xs[:, j] for j in range(nv)}
+    d.update({f"y{j}": ys[:, j] for j in range(nv)})
+    d.update({f"s{j}": ys2[:, j] for j in range(nv)})
+    d["val"] = val
+    df = pd.DataFrame(d)
+    xc, yc, sc = ([f"{p}{j}" for j in range(nv)] for p in "xys")
+    W, H = int(rng.integers(20, 300)), int(rng.integers(20, 200))
+    xr, yr = (centre + 0.1, centre + 0.9), (centre + 0.2, centre + 1.1)
+    cvs = ds.Canvas(W, H, x_range=xr, y_range=yr)
+    view = ora.make_view(W, H, xr, yr)
+    key = f"seed {seed} {nl}x{nv} {dt.__name__} {W}x{H} centre {centre}"
+    for name, agg in (("any", ds.any()), ("count", ds.count()), ("max", ds.max("val")), ("min", ds.min("val"))):
+        got = cvs.line(df, x=xc, y=yc, axis=1, agg=agg).data
+        want = ora.lines(xs, ys, view, name, None if name in ("any", "count") else val, 0)
+        assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), f"{key} bresenham {name}"
+    lw = float(rng.choice([0.5, 1.0, 2.0, 3.5]))
+    for name, agg in (("any", ds.any()), ("max", ds.max("val")), ("sum", ds.sum("val")), ("mean", ds.mean("val"))):
+        got = cvs.line(df, x=xc, y=yc, axis=1, agg=agg, line_width=lw).data
+        want = ora.lines(xs, ys, view, name, None if name == "any" else val, lw)
+        assert got.dtype == want.dtype and np.array_equal(np.isnan(got), np.isnan(want)), f"{key} aa {name} lw {lw}"
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6, equal_nan=True, err_msg=f"{key} aa {name} lw {lw}")
+    for name, agg in (("min", ds.min("val")), ("first", ds.first("val")), ("last", ds.last("val")),
+                      ("sum", ds.sum("val", self_intersect=False))):
+        got = cvs.line(df, x=xc, y=yc, axis=1, agg=agg, line_width=lw).data
+        want = ora.lines_aa2(xs, ys, view, name, val, lw)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), f"{key} aa2 {name} lw {lw}"
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6, equal_nan=True, err_msg=f"{key} aa2 {name} lw {lw}")
+    for name, agg in (("any", ds.any()), ("count", ds.count()), ("max", ds.max("val"))):
+        vals = None if name in ("any", "count") else val
+        got = cvs.area(df, x=xc, y=yc, agg=agg, axis=1).data
+        assert np.array_equal(got, ora.areas(xs, ys, view, None, name, vals), equal_nan=got.dtype.kind == "f"), f"{key} area zero {name}"
+        got = cvs.area(df, x=xc, y=yc, y_stack=sc, agg=agg, axis=1).data
+        assert np.array_equal(got, ora.areas(xs, ys, view, ys2, name, vals), equal_nan=got.dtype.kind == "f"), f"{key} area line {name}"
