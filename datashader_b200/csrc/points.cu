@@ -566,6 +566,7 @@ static long long g_count16_band_bytes = 0;   // dsb_points_count16: optional ban
                                              // config 3: 1 pass 8.5 ms, 2 bands 9.0 ms, 3 bands 13.4 ms - each pass pays the generic front end)
 static int g_mono = 1;                       // use k_points_mono for single monotone accumulators
 static int g_mono_banded = 1;                //   ... also for the L2-banded passes of big canvases (without the filter)
+static int g_priv_threads = 1024;            // threads per CTA of the tight K2 kernels (one CTA per SM)
 static int g_priv_tight = 1;                 // use k_points_priv_tight for the count() / mean(f32) shapes
 static long long l2_band_budget_bytes() {
   if (g_band_budget < 0) {
@@ -582,6 +583,7 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "l2_band_bytes")) { g_band_budget = value; return DSB_OK; }
   if (!strcmp(key, "band_min_rows")) { g_band_min_rows = value; return DSB_OK; }
   if (!strcmp(key, "priv_tight")) { g_priv_tight = value != 0; return DSB_OK; }
+  if (!strcmp(key, "priv_threads")) { if (value < 128 || value > 1024 || (value & 31)) { dsb_set_error("dsb_configure: priv_threads must be a multiple of 32 in [128, 1024]"); return DSB_ERR_ARG; } g_priv_threads = (int)value; return DSB_OK; }
   if (!strcmp(key, "mono")) { g_mono = value != 0; return DSB_OK; }
   if (!strcmp(key, "split_bytes")) { g_split_bytes = value; return DSB_OK; }
   if (!strcmp(key, "count16_band_bytes")) { g_count16_band_bytes = value; return DSB_OK; }
@@ -754,10 +756,10 @@ template <int SLOT, bool MEAN>
 static void launch_priv_tight(const PrivArgs& a, const FastMap& fm, bool allp, size_t smem, cudaStream_t s) {
   if (allp) {
     cudaFuncSetAttribute(k_points_priv_tight<SLOT, MEAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    k_points_priv_tight<SLOT, MEAN, true><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
+    k_points_priv_tight<SLOT, MEAN, true><<<dsb_num_sms(), g_priv_threads, smem, s>>>(a, fm);
   } else {
     cudaFuncSetAttribute(k_points_priv_tight<SLOT, MEAN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    k_points_priv_tight<SLOT, MEAN, false><<<dsb_num_sms(), 1024, smem, s>>>(a, fm);
+    k_points_priv_tight<SLOT, MEAN, false><<<dsb_num_sms(), g_priv_threads, smem, s>>>(a, fm);
   }
 }
 
