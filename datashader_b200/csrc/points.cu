@@ -763,6 +763,71 @@ static void launch_priv_tight(const PrivArgs& a, const FastMap& fm, bool allp, s
   }
 }
 
+
+// ---- K2 for float64 coordinates (pandas' default dtype): count() and mean(float64 column) ----------------------------
+// Same privatised counters; the mapping is the exact f64 one (there is no cheaper form for doubles), two points per
+// 16-byte load, four loads in flight per column.  Streams 16 B / point (count) or 24 B / point (mean).
+template <int SLOT, bool MEAN, bool ALLP>
+__global__ void __launch_bounds__(1024, 1) k_points_priv_f64(const __grid_constant__ PrivArgs a, const double* __restrict__ vcol) {
+  extern __shared__ uint32_t sh[];
+  constexpr uint32_t PER = 32 / SLOT;
+  constexpr uint32_t FIELD = (1u << SLOT) - 1u;
+  const PointsArgs& p = a.p;
+  const int ncell = (int)a.npriv;
+  const int nwords = (ncell + (int)PER - 1) / (int)PER;
+  for (int j = threadIdx.x; j < nwords; j += blockDim.x) sh[j] = 0;
+  __syncthreads();
+  uint32_t sh_addr;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sh_addr) : "r"((uint32_t)__cvta_generic_to_shared(sh)));
+  const double* __restrict__ x = (const double*)p.x;
+  const double* __restrict__ y = (const double*)p.y;
+  double* __restrict__ sum_canvas = MEAN ? (double*)p.plan.ops[1 - a.priv_op].agg : nullptr;
+  uint32_t bad = 0;
+  auto one = [&](double xv, double yv, double vv) {
+    const long long c = map_to_cell<double>(p.v, xv, yv);
+    bool ok = c >= 0;
+    if (MEAN) {
+      ok = ok && vv == vv;
+      if (ok) atomicAdd(sum_canvas + c, vv);
+    }
+    priv_hit_tight<SLOT, ALLP>(sh_addr, (uint32_t)c, ok, (uint32_t)ncell, a.scratch, bad);
+  };
+  const double2* __restrict__ x2 = (const double2*)p.x;
+  const double2* __restrict__ y2 = (const double2*)p.y;
+  const double2* __restrict__ v2 = (const double2*)vcol;
+  const long long n2 = p.n >> 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double2 nan2 = make_double2(NAN, NAN);
+  long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i2 + stride < n2; i2 += 2 * stride) {
+    const double2 xa = __ldcs(x2 + i2), ya = __ldcs(y2 + i2), va = MEAN ? __ldcs(v2 + i2) : nan2;
+    const double2 xb = __ldcs(x2 + i2 + stride), yb = __ldcs(y2 + i2 + stride), vb = MEAN ? __ldcs(v2 + i2 + stride) : nan2;
+    one(xa.x, ya.x, va.x); one(xa.y, ya.y, va.y); one(xb.x, yb.x, vb.x); one(xb.y, yb.y, vb.y);
+  }
+  if (i2 < n2) {
+    const double2 xa = __ldcs(x2 + i2), ya = __ldcs(y2 + i2), va = MEAN ? __ldcs(v2 + i2) : nan2;
+    one(xa.x, ya.x, va.x); one(xa.y, ya.y, va.y);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (p.n & 1)) one(x[p.n - 1], y[p.n - 1], MEAN ? vcol[p.n - 1] : 0.0);
+  __syncthreads();
+  for (int j = threadIdx.x; j < ncell; j += blockDim.x) {
+    const uint32_t w = (uint32_t)j / PER, sft = ((uint32_t)j - w * PER) * SLOT;
+    const uint32_t c = (sh[w] >> sft) & FIELD;
+    if (c) atomicAdd(a.scratch + j, c);
+  }
+  if (bad) atomicOr(a.flag, 1u);
+}
+
+template <int SLOT>
+static void launch_priv_f64(const PrivArgs& a, bool mean, const double* vcol, size_t smem, cudaStream_t s) {
+  const bool allp = a.npriv == a.p.band_hi;
+#define DSB_F64_LAUNCH(M, A) do { cudaFuncSetAttribute(k_points_priv_f64<SLOT, M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    k_points_priv_f64<SLOT, M, A><<<dsb_num_sms(), 1024, smem, s>>>(a, vcol); } while (0)
+  if (mean) { if (allp) DSB_F64_LAUNCH(true, true); else DSB_F64_LAUNCH(true, false); }
+  else { if (allp) DSB_F64_LAUNCH(false, true); else DSB_F64_LAUNCH(false, false); }
+#undef DSB_F64_LAUNCH
+}
+
 template <int SLOT>
 static void launch_priv(const PrivArgs& a, const FastMap& fm, int mode, bool vec, bool tight, size_t smem, cudaStream_t s) {
   const bool allp = a.npriv == a.p.band_hi;          // band_hi = number of cells
@@ -808,7 +873,8 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   if (priv_any && n == (1LL << 32)) { dsb_set_error("dsb_points_priv: an ANY op takes fewer than 2^32 rows per call"); return DSB_ERR_ARG; }
   if (!x || !y) { dsb_set_error("dsb_points_priv: null coordinate column"); return DSB_ERR_ARG; }
   const long long ncell = (long long)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1);
-  if (xy_dtype != DSB_F32) { dsb_set_error("dsb_points_priv: needs float32 coordinates"); return DSB_ERR_UNSUPPORTED; }
+  if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("dsb_points_priv: needs float32 or float64 coordinates"); return DSB_ERR_UNSUPPORTED; }
+  const bool f64 = xy_dtype == DSB_F64;
   cudaStream_t s = (cudaStream_t)stream;
   PrivArgs a;
   a.p.v = *view; a.p.x = x; a.p.y = y; a.p.n = n; a.p.row_offset = row_offset; a.p.band_lo = 0; a.p.band_hi = ncell; a.p.plan = *plan;
@@ -825,6 +891,19 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
     const dsb_base& o = plan->ops[1 - priv_op];
     if (o.op == DSB_OP_SUM && o.val == (const void*)a.vcol && o.val_dtype == DSB_F32 && o.chk_dtype == DSB_NONE &&
         c0.val == (const void*)a.vcol && c0.val_dtype == DSB_F32 && c0.chk_dtype == DSB_NONE) mode = 1;
+  }
+  const double* vcol64 = nullptr;
+  if (f64) {                  // float64 coordinates: count(), or SUM + COUNT of one aligned float64 column; nothing else
+    if (plan->ncat != 0 || ((((uintptr_t)x | (uintptr_t)y)) & 15) != 0) { dsb_set_error("dsb_points_priv: float64 path needs aligned columns and no categories"); return DSB_ERR_UNSUPPORTED; }
+    if (mode != 0) {
+      mode = 2;
+      if (plan->nops == 2) {
+        const dsb_base& o = plan->ops[1 - priv_op];
+        if (o.op == DSB_OP_SUM && o.val_dtype == DSB_F64 && o.val && o.chk_dtype == DSB_NONE && c0.val == o.val && c0.val_dtype == DSB_F64 &&
+            c0.chk_dtype == DSB_NONE && (((uintptr_t)o.val) & 15) == 0) { mode = 1; vcol64 = (const double*)o.val; }
+      }
+      if (mode != 1) { dsb_set_error("dsb_points_priv: float64 path serves count() and mean(float64 column) only"); return DSB_ERR_UNSUPPORTED; }
+    }
   }
   // Shared-memory budget.  count() streams 8 B / point and needs the rest of the 228 KB L1/shared array as L1 for its
   // loads in flight: 192 KB (measured: 226 KB drops count from 484 to 438 Gpts/s).  mean() is bound by the global REDs
@@ -853,6 +932,16 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   const FastMap fm = make_fast_map(view);
   const bool vvec = mode != 1 || ((uintptr_t)a.vcol & 15) == 0;
   const bool tight = g_priv_tight && vec && vvec && mode <= 1 && fm.enabled && ncell < (1LL << 31);
+  if (f64) {
+    if (ncell >= (1LL << 31)) { dsb_set_error("dsb_points_priv: canvas too large"); return DSB_ERR_UNSUPPORTED; }
+    switch (slot) {
+      case 8: launch_priv_f64<8>(a, mode == 1, vcol64, smem, s); break;
+      case 5: launch_priv_f64<5>(a, mode == 1, vcol64, smem, s); break;
+      case 4: launch_priv_f64<4>(a, mode == 1, vcol64, smem, s); break;
+      case 3: launch_priv_f64<3>(a, mode == 1, vcol64, smem, s); break;
+      default: launch_priv_f64<2>(a, mode == 1, vcol64, smem, s); break;
+    }
+  } else
   switch (slot) {
     case 8: launch_priv<8>(a, fm, mode, vec, tight, smem, s); break;
     case 5: launch_priv<5>(a, fm, mode, vec, tight, smem, s); break;
@@ -869,7 +958,8 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   r.plan.nops = 1; r.plan.ops[0] = plan->ops[priv_op];
   long long want = (n + 255) / 256;
   int grid = (int)(want < cap ? want : cap);
-  k_points_generic_if<float><<<grid, 256, 0, s>>>(r, flag);
+  if (f64) k_points_generic_if<double><<<grid, 256, 0, s>>>(r, flag);
+  else k_points_generic_if<float><<<grid, 256, 0, s>>>(r, flag);
   DSB_CUDA_CHECK_LAUNCH("dsb_points_priv(commit)");
   return DSB_OK;
 }

@@ -177,7 +177,7 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
     of 1-2x the L2 budget, otherwise dsb_points (which picks the mono / generic / banded / split forms itself)."""
     lib = _lib.lib()
     ncell = int(np.prod(ctx.shape))
-    if config.priv_count and xy_dtype == _lib.F32 and n >= config.priv_min_rows:
+    if config.priv_count and xy_dtype in (_lib.F32, _lib.F64) and n >= config.priv_min_rows:
         priv = [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_COUNT] or \
                [k for k in range(plan.nops) if plan.ops[k].op == _lib.OP_ANY and n < (1 << 32)]
         if priv and ncell <= 954_000:      # 226 KB of 2-bit fields / 0.97; beyond, dsb_points_priv returns UNSUPPORTED

@@ -109,8 +109,9 @@ int dsb_points(const dsb_view* view, const void* x, const void* y, int32_t xy_dt
 
 /* K2 - the same contract as dsb_points for a plan that contains a COUNT or ANY accumulator (`priv_op` = its index), with
  * that accumulator's whole canvas privatised per SM in shared memory as packed guard-bit counters.
- * Requires float32 coordinates and width*height*ncat <= ~800 000 cells; otherwise returns DSB_ERR_UNSUPPORTED and the
- * caller uses dsb_points.  scratch: [cells] u32 work canvas, flag: 1 u32 (both device, contents ignored on entry).
+ * Requires float32 coordinates (any plan) or float64 coordinates (count / any, or SUM + COUNT of one float64 column;
+ * 16-byte aligned columns, no categories) and width*height*ncat <= ~950 000 cells; otherwise returns
+ * DSB_ERR_UNSUPPORTED and the caller uses dsb_points.  scratch: [cells] u32 work canvas, flag: 1 u32 (both device, contents ignored on entry).
  * The result is always exact: a detected counter carry makes the library redo the count with global REDs.
  * An ANY accumulator is counted in `scratch` and committed as canvas |= (scratch > 0); it takes n < 2^32 rows per call. */
 int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,

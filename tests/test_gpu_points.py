@@ -443,3 +443,31 @@ def test_summary_split_into_specialised_groups_matches_oracle(ds, force_priv):
                 assert_agg_equal(np.asarray(got[k].data), want, f"summary split={split} {k}")
     finally:
         ds.config.split_summary = old
+
+
+@pytest.mark.parametrize("W,H", [(300, 200), (900, 525), (1024, 768)])
+def test_priv_kernel_float64_coordinates(ds, force_priv, W, H):
+    """K2 with float64 coordinates (pandas' default dtype): count / count(col) / mean / sum of a float64 column, linear
+    and log axes, odd row count; anything else must fall back to the generic kernel and still match."""
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(W + H)
+    n = 300_001
+    cols = {"x": rng.random(n) * 1.2 - 0.1, "y": rng.random(n) * 1.2 - 0.1, "v64": np.round(rng.standard_normal(n), 2),
+            "v32": rng.standard_normal(n).astype(np.float32)}
+    cols["v64"][rng.integers(0, n, 300)] = np.nan
+    cols["x"][:4] = [0.0, 1.0, np.nan, 0.5]
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    for spec in (("count",), ("count", "v64"), ("mean", "v64"), ("sum", "v64"), ("any",), ("mean", "v32"), ("max", "v64")):
+        assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view),
+                         f"f64 priv {spec} {W}x{H}", atol=1e-13)
+    lcols = dict(cols, x=np.abs(cols["x"]) + 0.01, y=np.abs(cols["y"]) + 0.01)
+    lview = ora.make_view(W, H, (0.01, 1.0), (0.01, 1.0), "log", "log")
+    lcvs = ds.Canvas(W, H, x_range=(0.01, 1.0), y_range=(0.01, 1.0), x_axis_type="log", y_axis_type="log")
+    lframe = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in lcols.items()})
+    got = lcvs.points(lframe, "x", "y", ds.count()).data
+    want = ora.points(lcols, "x", "y", ("count",), lview)
+    assert int(got.sum()) == int(want.sum())
+    assert np.abs(got.astype(np.int64) - want.astype(np.int64)).sum() <= 2 * max(1, n // 20000)   # log10 rounding on pixel edges
