@@ -113,3 +113,27 @@ def test_lines_and_areas_fuzz_vs_oracle(seed):
         assert np.array_equal(got, ora.areas(xs, ys, view, None, name, vals), equal_nan=got.dtype.kind == "f"), f"{key} area zero {name}"
         got = cvs.area(df, x=xc, y=yc, y_stack=sc, agg=agg, axis=1).data
         assert np.array_equal(got, ora.areas(xs, ys, view, ys2, name, vals), equal_nan=got.dtype.kind == "f"), f"{key} area line {name}"
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 15, 17, 1023, 1025])
+def test_tiny_inputs_through_the_specialised_kernels(forced, n):
+    """Row counts around the vector widths (float4 / double2 loads, 8-point batches, tail rows) with every specialised
+    kernel forced on."""
+    import torch
+    from oracle import oracle as ora
+    ds = forced
+    rng = np.random.default_rng(n)
+    W, H = 37, 23
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    for dt in (np.float32, np.float64):
+        cols = {"x": rng.random(n).astype(dt), "y": rng.random(n).astype(dt), "v32": rng.standard_normal(n).astype(np.float32),
+                "v64": rng.standard_normal(n)}
+        if n > 2:
+            cols["v32"][1] = np.nan
+            cols["v64"][1] = np.nan
+        frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+        for spec in (("count",), ("any",), ("mean", "v32"), ("mean", "v64"), ("sum", "v64"), ("max", "v32"), ("first", "v32"),
+                     ("last", "v32"), ("where", ("max", "v32"), None)):
+            want = ora.points(cols, "x", "y", spec, view, npartitions=2 if spec[0] in ("first", "last") else 1)
+            assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, want, f"n={n} {dt.__name__} {spec}", atol=1e-13)
