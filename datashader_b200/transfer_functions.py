@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from .palette import Sets1to3, rgb
+from .frame import to_host_array
 from .xr_compat import DataArray
 
 __all__ = ["shade", "Image", "spread", "dynspread", "stack", "set_background"]
@@ -172,7 +173,7 @@ def _colorize(agg, color_key, how, alpha, span, min_alpha, name, color_baseline,
             int(mask_zero), how_code, xp.data_ptr() if xp is not None else None, cdf.data_ptr() if cdf is not None else None,
             meta.data_ptr() if meta is not None else None, span_t.data_ptr(), float(min_alpha), float(alpha), clip_mode, clip_lo,
             clip_hi, out.data_ptr(), s), "dsb_shade_cat_colorize")
-        img = out.cpu().numpy().view(np.uint32).reshape(H, W)
+        img = to_host_array(out).view(np.uint32).reshape(H, W)
     return Image(img, dims=agg.dims[:-1], coords=coords, name=name)
 
 
@@ -256,7 +257,7 @@ def _interpolate(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_
             cdf.data_ptr() if cdf is not None else None, meta.data_ptr() if meta is not None else None, span_t.data_ptr(),
             ncolors, cspan.data_ptr() if cspan is not None else None, rs.data_ptr(), gs.data_ptr(), bs.data_ptr(),
             float(min_alpha), float(alpha), out.data_ptr(), s), "dsb_shade_map2d")
-        img = out.cpu().numpy().view(np.uint32).reshape(H, W)
+        img = to_host_array(out).view(np.uint32).reshape(H, W)
     return Image(img, coords=agg.coords, dims=agg.dims, name=name)
 
 
@@ -317,7 +318,7 @@ def _result_like(data, out_t, np_dtype):
     """Same residency as the input: torch in -> torch out (device results), numpy in -> numpy out."""
     if isinstance(data, torch.Tensor):
         return out_t
-    a = out_t.cpu().numpy()
+    a = to_host_array(out_t)
     return a.view(np_dtype) if a.dtype != np_dtype else a
 
 
