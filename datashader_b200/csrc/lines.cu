@@ -51,6 +51,8 @@ struct LineCtx {
   int cat;                  // category of this line (by()), -1 = skip
   unsigned int* touched_n;  // 2-stage antialiasing, global stage-1 canvas: `touched` = the CTA's bitmap of touched cells,
   uint32_t* touched;        //   bbox = this thread's {ymin, ymax} of touched rows; or, when hkeys != nullptr, the
+  uint32_t* tlist;          //   tlist / tn: this thread's own list of touched cells (entry k at tlist[k * AA2_THREADS + tid]);
+  int* tn;                  //   the bitmap is only used once that list is full
   int* bbox;                //   shared-memory hash table:
   uint32_t* hkeys;          //   [cap] cell ids (0xffffffff = free), hvals [cap] key64 maxima, touched_n = entries in use
   long long* hvals;
@@ -60,6 +62,8 @@ struct LineCtx {
 };
 
 // internal agg codes of the 2-stage path (stage 1 = per-line max of field * aa_factor / of aa_factor)
+#define AA2_THREADS 512
+#define AA2_LIST_CAP 512       // touched cells a thread can remember per line before it falls back to the bitmap
 #define DSB_LINE_AA2_VALUE 101
 #define DSB_LINE_AA2_COVER 102
 
@@ -161,9 +165,14 @@ __device__ __forceinline__ void append_aa(const LineCtx& c, long long x, long lo
           h = (h + 1) & c.hmask;
         }
       }
-      atomicMax((long long*)c.canvas + cell, key);                 // both fire-and-forget REDs
-      atomicOr(c.touched + (cell >> 5), 1u << (cell & 31));
-      c.bbox[0] = min(c.bbox[0], (int)y); c.bbox[1] = max(c.bbox[1], (int)y);
+      atomicMax((long long*)c.canvas + cell, key);                 // fire-and-forget RED
+      if (*c.tn < AA2_LIST_CAP) {           // remember the cell in this thread's own list: no atomics, no shared state
+        c.tlist[(long long)(*c.tn) * AA2_THREADS + threadIdx.x] = (uint32_t)cell;
+        (*c.tn)++;
+      } else {                              // list full (very long / wide segments): fall back to the CTA's bitmap
+        atomicOr(c.touched + (cell >> 5), 1u << (cell & 31));
+        c.bbox[0] = min(c.bbox[0], (int)y); c.bbox[1] = max(c.bbox[1], (int)y);
+      }
       return;
     }
   }
@@ -463,13 +472,13 @@ struct Aa2Args {
   void* aux;              // sum / count: u8 mask; first / last: i64 line-index canvas
   long long* temp;        // [nctas][ncell]  (global stage-1 canvases, used for the lines that overflow the hash table)
   uint32_t* touched;      // [nctas][nwords] bitmaps of the cells the CTA's current line has touched (nwords = ceil(ncell / 32))
+  uint32_t* tlists;       // [nctas][AA2_LIST_CAP][AA2_THREADS] per-thread lists of touched cells
   unsigned int* stats;    // [2] groups tried / groups overflowed by the hash pass (it gives up when most overflow)
   unsigned int* redo_n;   // number of / indices of the lines whose touched-pixel set overflowed the shared-memory table
   unsigned int* redo;     // [nlines]
 };
 
 #define AA2_HASH_CAP 16384   // 16384 x (4 + 8) B = 192 KB of shared memory: one 512-thread CTA per SM
-#define AA2_THREADS 512
 #define AA2_CELL_BITS 27      // table key = (line within its group) << 27 | cell: canvases below 2^27 pixels, groups <= 32
 
 __device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long long key, long long line) {
@@ -512,6 +521,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
   const long long nwords = (ncell + 31) >> 5;
   long long* temp = HASH ? nullptr : b.temp + (long long)blockIdx.x * ncell;
   uint32_t* touched = HASH ? nullptr : b.touched + (long long)blockIdx.x * nwords;
+  uint32_t* tlist = HASH ? nullptr : b.tlists + (long long)blockIdx.x * AA2_LIST_CAP * AA2_THREADS;
   __shared__ int s_bbox[2];
   __shared__ int s_skip;
   const long long nseg = a.nverts - 1;
@@ -537,6 +547,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
       continue;
     }
     int bbox[2] = {INT_MAX, -1};
+    int tn = 0;
     for (long long t = threadIdx.x; t < glines * nseg; t += blockDim.x) {
       const long long g = t / nseg, j = t - g * nseg, i = i0 + g;
       const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
@@ -557,7 +568,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
       c.field = c.has_field ? load_f64(a.val, a.val_dtype, vi) : 0.0;
       c.field_nan = c.has_field && (c.field != c.field);
       c.plan = nullptr; c.line = vi; c.row = a.row_offset + vi; c.cat = 0; c.ncat = 0;
-      c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox;
+      c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox; c.tlist = tlist; c.tn = &tn;
       c.hkeys = HASH ? hkeys : nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = (uint32_t)g << AA2_CELL_BITS;
       // xm = ym = 0 in 2-stage mode (line.py:1266-1268); unused because overwrite is True
       draw_segment<XY>(a, c, segment_start, segment_end, x0, x1, y0, y1, 0.0, 0.0);
@@ -579,8 +590,25 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
           if (!overflow) aa2_stage2(b, id & ((1u << AA2_CELL_BITS) - 1u), key, a.row_offset + i0 + (id >> AA2_CELL_BITS));
         }
       }
-    } else if (s_bbox[1] >= 0) {
-      // walk the bitmap words of the touched rows; every set bit is a cell of this line: fold it in and clear it
+    } else {
+      // this thread's own touched cells: whoever exchanges a cell's stage-1 value out first folds it in (adjacent segments of
+      // a line share pixels, so a cell can sit in several lists); four exchanges in flight
+      for (int k = 0; k < tn; k += 4) {
+        uint32_t cells[4];
+        long long keys[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) cells[u] = (k + u < tn) ? tlist[(long long)(k + u) * AA2_THREADS + threadIdx.x] : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          keys[u] = cells[u] != 0xffffffffu ? (long long)atomicExch((unsigned long long*)(temp + cells[u]), (unsigned long long)LLONG_MIN) : LLONG_MIN;
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (keys[u] != LLONG_MIN) aa2_stage2(b, cells[u], keys[u], a.row_offset + i0);
+      }
+      __syncthreads();
+    }
+    if (!HASH && s_bbox[1] >= 0) {
+      // some thread's list overflowed: walk the bitmap words of those rows; a set bit is a cell of this line unless a
+      // list already took its value
       const long long w0 = ((long long)s_bbox[0] * a.v.width) >> 5, w1 = (((long long)s_bbox[1] + 1) * a.v.width - 1) >> 5;
       for (long long wi = w0 + threadIdx.x; wi <= w1; wi += blockDim.x) {
         uint32_t bits = __ldcg(touched + wi);          // written by L2 REDs: do not trust a stale L1 line
@@ -591,6 +619,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
           bits &= bits - 1;
           const uint32_t cell = (uint32_t)(wi << 5) + bit;
           const long long key = __ldcg(temp + cell);
+          if (key == LLONG_MIN) continue;
           temp[cell] = LLONG_MIN;
           aa2_stage2(b, cell, key, a.row_offset + i0);
         }
@@ -716,7 +745,7 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   const long long ncell = (long long)view->width * view->height;
   if (ncell >= (1LL << 32)) { dsb_set_error("dsb_lines_aa2: canvas too large"); return DSB_ERR_UNSUPPORTED; }
   if (!scratch) { dsb_set_error("dsb_lines_aa2: scratch required"); return DSB_ERR_ARG; }
-  const long long per_cta = ncell * 8 + ((ncell + 31) >> 5) * 4;
+  const long long per_cta = ncell * 8 + ((ncell + 31) >> 5) * 4 + (long long)AA2_LIST_CAP * AA2_THREADS * 4;
   const long long cap = (long long)dsb_num_sms();
   long long nctas;
   LineArgs a;
@@ -734,7 +763,8 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   if (nlines >= (1LL << 31)) { dsb_set_error("dsb_lines_aa2: too many lines"); return DSB_ERR_UNSUPPORTED; }
   Aa2Args b;
   b.combo = combo; b.phase = phase; b.out = out; b.aux = aux;
-  // scratch layout: [nctas][ncell] i64 stage-1 canvases, [nctas][nwords] u32 touched bitmaps, [4 + nlines] u32 queue
+  // scratch layout: [nctas][ncell] i64 stage-1 canvases, [nctas][nwords] u32 touched bitmaps, [nctas][512][512] u32
+  // per-thread touched lists, [4 + nlines] u32 queue
   const long long nwords = (ncell + 31) >> 5;
   const long long redo_bytes = 4 * (4 + nlines);
   nctas = (scratch_bytes - redo_bytes) / per_cta;
@@ -743,11 +773,13 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   if (nctas > nlines) nctas = nlines;
   b.temp = (long long*)scratch;
   b.touched = (uint32_t*)((char*)scratch + nctas * ncell * 8);
-  b.redo_n = (unsigned int*)((char*)scratch + nctas * (ncell * 8 + nwords * 4));
+  b.tlists = b.touched + nctas * nwords;
+  b.redo_n = (unsigned int*)((char*)scratch + nctas * (ncell * 8 + nwords * 4 + (long long)AA2_LIST_CAP * AA2_THREADS * 4));
   b.stats = b.redo_n + 1;
   b.redo = b.redo_n + 4;
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(b.touched, 0, (size_t)(nctas * nwords * 4 + 16), s);     // bitmaps + queue header
+  cudaMemsetAsync(b.touched, 0, (size_t)(nctas * nwords * 4), s);           // bitmaps
+  cudaMemsetAsync(b.redo_n, 0, 16, s);                                        // queue header
   k_fill_i64<<<dsb_num_sms() * 8, 256, 0, s>>>(b.temp, LLONG_MIN, nctas * ncell);
   const size_t smem = (size_t)AA2_HASH_CAP * 12;
   // short lines are batched G to a group so that every thread of the CTA has a segment (at most 32 lines per group)

@@ -485,7 +485,7 @@ def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist):
         # scratch for the lines that overflow the shared-memory stage-1 table: a key64 canvas + a touched bitmap per CTA
         # (8.125 bytes per pixel), one CTA per SM if 1/4 of the free memory (<= 16 GiB) allows, plus the redo queue
         free, _total = torch.cuda.mem_get_info(device)
-        per_cta = 8 * H * W + 4 * ((H * W + 31) // 32)
+        per_cta = 8 * H * W + 4 * ((H * W + 31) // 32) + 512 * 512 * 4     # stage-1 canvas + bitmap + per-thread lists
         nctas = int(max(1, min(torch.cuda.get_device_properties(device).multi_processor_count, max(nlines, 1),
                                min(free // 4, 16 << 30) // per_cta)))
         scratch = torch.empty(nctas * per_cta + 4 * (nlines + 4), dtype=torch.uint8, device=device)

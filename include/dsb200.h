@@ -188,7 +188,7 @@ int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, i
  * antialias.py:30-58): every line is rendered on its own with a max() combination (stage 1) and folded into the result
  * with nansum / nanmin / nanfirst / nanlast (stage 2).  One CTA per line; stage 1 lives in a shared-memory hash table
  * (12288 touched pixels per group of lines); longer lines are queued and redone with a private full-size stage-1
- * canvas + touched bitmap per CTA in `scratch`: 8 * pixels + 4 * ceil(pixels / 32) bytes per CTA (as many CTAs as fit,
+ * canvas + touched bitmap per CTA in `scratch`: 8 * pixels + 4 * ceil(pixels / 32) + 1 MiB bytes per CTA (as many CTAs as fit,
  * at most one per SM) + 4 * (nlines + 4) bytes of queue.
  *   DSB_AA2_SUM   sum(self_intersect=False):   out f64 zero-initialised, aux u8 mask (zeroed)
  *   DSB_AA2_COUNT count(self_intersect=False): out f32 zero-initialised, aux u8 mask (zeroed); val optional (NaN check)
