@@ -471,3 +471,24 @@ def test_priv_kernel_float64_coordinates(ds, force_priv, W, H):
     want = ora.points(lcols, "x", "y", ("count",), lview)
     assert int(got.sum()) == int(want.sum())
     assert np.abs(got.astype(np.int64) - want.astype(np.int64)).sum() <= 2 * max(1, n // 20000)   # log10 rounding on pixel edges
+
+
+def test_large_result_leaves_through_the_staging_ring(ds):
+    """Aggregates above 128 MiB (here 4200x4100 f64 = 138 MB) are copied to ordinary host memory through the pinned ring;
+    the values must equal the device-resident result."""
+    import torch
+    rng = np.random.default_rng(1)
+    n = 200_000
+    frame = ds.DeviceFrame({"x": torch.from_numpy(rng.random(n, dtype=np.float32)).cuda(),
+                            "y": torch.from_numpy(rng.random(n, dtype=np.float32)).cuda(),
+                            "v": torch.from_numpy(rng.standard_normal(n).astype(np.float32)).cuda()})
+    cvs = ds.Canvas(4200, 4100, x_range=(0, 1), y_range=(0, 1))
+    host = cvs.points(frame, "x", "y", ds.max("v")).data
+    ds.config.device_results = True
+    try:
+        dev = cvs.points(frame, "x", "y", ds.max("v")).data
+    finally:
+        ds.config.device_results = False
+    assert isinstance(host, np.ndarray) and host.dtype == np.float64 and host.shape == (4100, 4200)
+    assert np.array_equal(host, dev.cpu().numpy(), equal_nan=True)
+    assert int((~np.isnan(host)).sum()) > 0
