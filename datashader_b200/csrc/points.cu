@@ -506,6 +506,83 @@ static bool try_launch_mono(const PointsArgs& a, int32_t xy_dtype, bool banded, 
 }
 
 
+// ---- K1 mono for float64 frames (pandas' default dtype): max / min of a float64 column, first / last gated by one ----------
+// Exact f64 mapping (linear or log axes), two points per 16-byte load, four points per batch with their four filter
+// loads in flight; key64 canvases (MAX64 / MIN64) or row-index canvases (MINROW / MAXROW; last walks the rows backwards).
+enum { M64_MAX = 0, M64_MIN = 1, M64_MINROW = 2, M64_MAXROW = 3 };
+
+template <int OP>
+__global__ void __launch_bounds__(256, 3) k_points_mono_f64(const __grid_constant__ PointsArgs a, const double* __restrict__ vcol) {
+  long long* __restrict__ canvas = (long long*)a.plan.ops[0].agg;
+  constexpr bool IS_MAX = OP == M64_MAX || OP == M64_MAXROW;
+  constexpr bool REVERSE = OP == M64_MAXROW;
+  const double* __restrict__ x = (const double*)a.x;
+  const double* __restrict__ y = (const double*)a.y;
+  auto key_of = [&](double vv, long long i) -> long long {
+    return (OP == M64_MAX || OP == M64_MIN) ? (long long)key64_from_f64(vv) : a.row_offset + i;
+  };
+  auto commit = [&](long long cell, long long key, long long cur) {
+    if (IS_MAX) { if (key > cur) atomicMax(canvas + cell, key); }
+    else { if (key < cur) atomicMin(canvas + cell, key); }
+  };
+  const double2* __restrict__ x2 = (const double2*)a.x;
+  const double2* __restrict__ y2 = (const double2*)a.y;
+  const double2* __restrict__ v2 = (const double2*)vcol;
+  const long long n2 = a.n >> 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double2 nan2 = make_double2(NAN, NAN);
+  for (long long t2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t2 < n2; t2 += 2 * stride) {
+    const bool two = t2 + stride < n2;
+    const long long i2 = REVERSE ? n2 - 1 - t2 : t2;
+    const long long j2 = REVERSE ? i2 - stride : i2 + stride;
+    const double2 xa = __ldcs(x2 + i2), ya = __ldcs(y2 + i2), va = __ldcs(v2 + i2);
+    const double2 xb = two ? __ldcs(x2 + j2) : nan2, yb = two ? __ldcs(y2 + j2) : nan2, vb = two ? __ldcs(v2 + j2) : nan2;
+    const double xs[4] = {xa.x, xa.y, xb.x, xb.y}, ys[4] = {ya.x, ya.y, yb.x, yb.y}, vs[4] = {va.x, va.y, vb.x, vb.y};
+    long long cell[4], cur[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      cell[k] = (vs[k] == vs[k]) ? map_to_cell<double>(a.v, xs[k], ys[k]) : -1;
+      if (cell[k] >= 0 && (cell[k] < a.band_lo || cell[k] >= a.band_hi)) cell[k] = -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = cell[k] >= 0 ? __ldcg(canvas + cell[k]) : 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (cell[k] >= 0) commit(cell[k], key_of(vs[k], 2 * (k < 2 ? i2 : j2) + (k & 1)), cur[k]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (a.n & 1)) {
+    const long long i = a.n - 1;
+    const double vv = vcol[i];
+    const long long c = (vv == vv) ? map_to_cell<double>(a.v, x[i], y[i]) : -1;
+    if (c >= 0 && c >= a.band_lo && c < a.band_hi) commit(c, key_of(vv, i), __ldcg(canvas + c));
+  }
+}
+
+static bool try_launch_mono_f64(const PointsArgs& a, int32_t xy_dtype, cudaStream_t s) {
+  const dsb_plan& p = a.plan;
+  if (xy_dtype != DSB_F64 || p.nops != 1 || p.ncat != 0 || a.n < g_mono_min_rows) return false;
+  const dsb_base& b = p.ops[0];
+  const double* vcol = nullptr;
+  int op;
+  if (b.op == DSB_OP_MAX64 || b.op == DSB_OP_MIN64) {
+    if (b.val_dtype != DSB_F64 || !b.val || b.chk_dtype != DSB_NONE) return false;
+    vcol = (const double*)b.val; op = b.op == DSB_OP_MAX64 ? M64_MAX : M64_MIN;
+  } else if (b.op == DSB_OP_MINROW || b.op == DSB_OP_MAXROW) {
+    if (b.chk_dtype != DSB_F64 || !b.chk || b.val_dtype != DSB_NONE) return false;
+    vcol = (const double*)b.chk; op = b.op == DSB_OP_MINROW ? M64_MINROW : M64_MAXROW;
+  } else return false;
+  if ((((uintptr_t)a.x | (uintptr_t)a.y | (uintptr_t)vcol) & 15) != 0) return false;
+  const int grid = dsb_num_sms() * 3;
+  switch (op) {
+    case M64_MAX: k_points_mono_f64<M64_MAX><<<grid, 256, 0, s>>>(a, vcol); break;
+    case M64_MIN: k_points_mono_f64<M64_MIN><<<grid, 256, 0, s>>>(a, vcol); break;
+    case M64_MINROW: k_points_mono_f64<M64_MINROW><<<grid, 256, 0, s>>>(a, vcol); break;
+    default: k_points_mono_f64<M64_MAXROW><<<grid, 256, 0, s>>>(a, vcol); break;
+  }
+  return true;
+}
+
+
 // canvas += scratch when the privatised pass was exact (flag == 0)
 __global__ void k_priv_commit(unsigned int* __restrict__ canvas, const unsigned int* __restrict__ scratch,
                               const unsigned int* __restrict__ flag, long long n) {
@@ -735,6 +812,7 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
       // the load-before-RED filter of the monotone accumulators pays only while the canvases are L2-resident
       const bool filter = nbands == 1 && bytes_per_pixel * npixels <= (96LL << 20);
       if (filter && g_mono && try_launch_mono(a, xy_dtype, false, s)) { DSB_CUDA_CHECK_LAUNCH("dsb_points(mono)"); continue; }
+      if (filter && g_mono && try_launch_mono_f64(a, xy_dtype, s)) { DSB_CUDA_CHECK_LAUNCH("dsb_points(mono f64)"); continue; }
       if (xy_dtype == DSB_F32) { if (filter) k_points_generic<float, true><<<grid, threads, 0, s>>>(a); else k_points_generic<float, false><<<grid, threads, 0, s>>>(a); }
       else { if (filter) k_points_generic<double, true><<<grid, threads, 0, s>>>(a); else k_points_generic<double, false><<<grid, threads, 0, s>>>(a); }
     }

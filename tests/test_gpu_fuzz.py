@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 SPECS = [("count",), ("count", "v32"), ("any",), ("sum", "v32"), ("mean", "v32"), ("max", "v32"), ("min", "v32"),
          ("first", "v32"), ("last", "v32"), ("where", ("max", "v32"), "other"), ("where", ("min", "v32"), None),
-         ("max", "vi"), ("mean", "v64"), ("by", "cat", ("count",)), ("by", "cat", ("mean", "v32"))]
+         ("max", "vi"), ("mean", "v64"), ("by", "cat", ("count",)), ("by", "cat", ("mean", "v32")),
+         ("max", "v64"), ("min", "v64"), ("first", "v64"), ("last", "v64")]
 
 
 @pytest.fixture()
@@ -55,7 +56,7 @@ def test_points_fuzz_vs_oracle(forced, seed):
     cvs = ds.Canvas(W, H, x_range=xr, y_range=yr)
     frame = ds.DeviceFrame({k_: torch.from_numpy(v).cuda() for k_, v in cols.items() if k_ != "cat__ncat"},
                            categories={"cat": [f"c{i}" for i in range(ncat)]})
-    picks = [SPECS[i] for i in rng.choice(len(SPECS), 6, replace=False)]
+    picks = [SPECS[i] for i in rng.choice(len(SPECS), 8, replace=False)]
     for spec in picks:
         want = ora.points(cols, "x", "y", spec, view, npartitions=2 if ("first" in str(spec) or "last" in str(spec)) else 1)
         got = cvs.points(frame, "x", "y", make_agg(spec)).data
@@ -134,6 +135,7 @@ def test_tiny_inputs_through_the_specialised_kernels(forced, n):
             cols["v64"][1] = np.nan
         frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
         for spec in (("count",), ("any",), ("mean", "v32"), ("mean", "v64"), ("sum", "v64"), ("max", "v32"), ("first", "v32"),
-                     ("last", "v32"), ("where", ("max", "v32"), None)):
+                     ("last", "v32"), ("where", ("max", "v32"), None), ("max", "v64"), ("min", "v64"), ("first", "v64"),
+                     ("last", "v64")):
             want = ora.points(cols, "x", "y", spec, view, npartitions=2 if spec[0] in ("first", "last") else 1)
             assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, want, f"n={n} {dt.__name__} {spec}", atol=1e-13)
