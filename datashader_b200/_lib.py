@@ -11,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdsb200.so")
 
 DSB_MAX_OPS = 8
+ABI_VERSION = 2
+NOTE_NEGZERO = 1
 
 # dsb_dtype
 NONE, F32, F64, I8, U8, I16, U16, I32, U32, I64, U64 = range(11)
@@ -41,7 +43,7 @@ class Base(C.Structure):
 
 class Plan(C.Structure):
     _fields_ = [("nops", C.c_int32), ("ops", Base * DSB_MAX_OPS), ("cat", C.c_void_p),
-                ("cat_dtype", C.c_int32), ("ncat", C.c_int32)]
+                ("cat_dtype", C.c_int32), ("ncat", C.c_int32), ("notes", C.c_void_p)]
 
 
 class LineLayout(C.Structure):
@@ -121,7 +123,7 @@ def lib():
                 continue
             fn.argtypes = argtypes
             fn.restype = restype
-        if L.dsb_abi_version() != 1:
+        if L.dsb_abi_version() != ABI_VERSION:
             raise Dsb200Error("libdsb200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -9,7 +9,7 @@ time_kernels = False
 kernel_events = []     # [(start_event, end_event)] appended per Canvas call when time_kernels is set
 
 # K2: count() with the canvas privatised in shared memory (csrc/points.cu).  Used for resident chunks of at least
-# `priv_min_rows` float32 points when the canvas fits (<= 786 432 cells); "off" forces the global-RED kernel.
+# `priv_min_rows` float32 or float64 points when the canvas fits (<= 954 000 cells: 226 KB of 2-bit fields, 97 % private); "off" forces the global-RED kernel.
 priv_count = True
 priv_min_rows = 1 << 24        # measured crossover vs global REDs: ~15-20 M rows (tools/bench_crossover.py)
 

@@ -29,7 +29,7 @@ template <bool FILTER, typename T> __device__ __forceinline__ void red_min(T* p,
 }
 
 template <bool FILTER = true>
-__device__ __forceinline__ void apply_base(const dsb_base& b, long long cell, long long i, long long row) {
+__device__ __forceinline__ void apply_base(const dsb_base& b, long long cell, long long i, long long row, unsigned int* notes = nullptr) {
   // nan_check_column: skip the whole base when that column is null (compiler.py:439-446, 461-466)
   if (b.chk_dtype != DSB_NONE && col_isnan(b.chk, b.chk_dtype, i)) return;
   switch (b.op) {
@@ -49,9 +49,10 @@ __device__ __forceinline__ void apply_base(const dsb_base& b, long long cell, lo
     }
     case DSB_OP_MAX32:
     case DSB_OP_MIN32: {
-      bool nan;
-      int32_t k = load_key32(b.val, b.val_dtype, i, &nan);
+      bool nan, nz;
+      int32_t k = load_key32(b.val, b.val_dtype, i, &nan, &nz);
       if (nan) return;
+      if (nz && notes) *notes = DSB_NOTE_NEGZERO;      // idempotent store; rare (the data holds a -0.0)
       if (b.op == DSB_OP_MAX32) red_max<FILTER>((int*)b.agg + cell, k);
       else red_min<FILTER>((int*)b.agg + cell, k);
       return;
@@ -60,6 +61,7 @@ __device__ __forceinline__ void apply_base(const dsb_base& b, long long cell, lo
     case DSB_OP_MIN64: {
       double f = load_f64(b.val, b.val_dtype, i);
       if (f != f) return;
+      if (notes && is_negzero(f)) *notes = DSB_NOTE_NEGZERO;
       long long k = key64_from_f64(f);
       if (b.op == DSB_OP_MAX64) red_max<FILTER>((long long*)b.agg + cell, k);
       else red_min<FILTER>((long long*)b.agg + cell, k);
@@ -73,8 +75,8 @@ __device__ __forceinline__ void apply_base(const dsb_base& b, long long cell, lo
       return;
     case DSB_OP_ARGMAX32:
     case DSB_OP_ARGMIN32: {
-      bool nan;
-      int32_t k = load_key32(b.val, b.val_dtype, i, &nan);
+      bool nan, nz;
+      int32_t k = load_key32(b.val, b.val_dtype, i, &nan, &nz);
       if (nan) return;
       // ties go to the earliest row: for max the row field is complemented so that a smaller row is larger
       // the row field is the low 32 bits of the GLOBAL row id, so chunks of one frame (< 2^32 rows) can

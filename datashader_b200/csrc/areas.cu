@@ -31,7 +31,7 @@ __device__ __forceinline__ void area_append(const AreaCtx& c, long long x, long 
     if (c.cat < 0) return;
     cell = cell * c.plan->ncat + c.cat;
   }
-  for (int k = 0; k < c.plan->nops; k++) apply_base(c.plan->ops[k], cell, c.idx, c.row);
+  for (int k = 0; k < c.plan->nops; k++) apply_base(c.plan->ops[k], cell, c.idx, c.row, c.plan->notes);
 }
 
 __device__ __forceinline__ double mul64(double a, double b) { return __dmul_rn(a, b); }

@@ -65,11 +65,15 @@ __device__ __forceinline__ bool col_isnan(const void* p, int dt, int64_t i) {
   return false;
 }
 
-// key32 of a <=32-bit value column; *isnan set for float NaN
-__device__ __forceinline__ int32_t load_key32(const void* p, int dt, int64_t i, bool* nan) {
+__device__ __forceinline__ bool is_negzero(float f) { return __float_as_uint(f) == 0x80000000u; }
+__device__ __forceinline__ bool is_negzero(double d) { return (unsigned long long)__double_as_longlong(d) == 0x8000000000000000ULL; }
+
+// key32 of a <=32-bit value column; *isnan set for float NaN, *negzero for a float -0.0 (see DSB_NOTE_NEGZERO)
+__device__ __forceinline__ int32_t load_key32(const void* p, int dt, int64_t i, bool* nan, bool* negzero) {
   *nan = false;
+  *negzero = false;
   switch (dt) {
-    case DSB_F32: { float f = __ldg((const float*)p + i); *nan = (f != f); return key32_from_f32(f); }
+    case DSB_F32: { float f = __ldg((const float*)p + i); *nan = (f != f); *negzero = is_negzero(f); return key32_from_f32(f); }
     case DSB_I8: return (int32_t)__ldg((const int8_t*)p + i);
     case DSB_U8: return (int32_t)__ldg((const uint8_t*)p + i);
     case DSB_I16: return (int32_t)__ldg((const int16_t*)p + i);

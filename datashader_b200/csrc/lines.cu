@@ -75,7 +75,7 @@ __device__ __forceinline__ void append_px(const LineCtx& c, long long x, long lo
       if (c.cat < 0) return;
       cell = cell * c.plan->ncat + c.cat;
     }
-    for (int k = 0; k < c.plan->nops; k++) apply_base(c.plan->ops[k], cell, c.line, c.row);
+    for (int k = 0; k < c.plan->nops; k++) apply_base(c.plan->ops[k], cell, c.line, c.row, c.plan->notes);
     return;
   }
   switch (c.agg) {

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_points_generic(const PointsArgs a) {
         if (c < 0 || c >= ncat) continue;
         cell = cell * ncat + c;
       }
-      for (int k = 0; k < a.plan.nops; k++) apply_base<FILTER>(a.plan.ops[k], cell, i, a.row_offset + i);
+      for (int k = 0; k < a.plan.nops; k++) apply_base<FILTER>(a.plan.ops[k], cell, i, a.row_offset + i, a.plan.notes);
     }
   }
 }
@@ -90,17 +90,17 @@ __device__ __forceinline__ void priv_hit(uint32_t* sh, long long cell, unsigned 
 }
 
 // apply_base for an op whose value column is the vector-loaded float32 column (value already in a register)
-__device__ __forceinline__ void apply_base_f32(const dsb_base& b, long long cell, long long i, long long row, float v) {
-  if (b.chk_dtype != DSB_NONE) { apply_base<false>(b, cell, i, row); return; }
+__device__ __forceinline__ void apply_base_f32(const dsb_base& b, long long cell, long long i, long long row, float v, unsigned int* notes) {
+  if (b.chk_dtype != DSB_NONE) { apply_base<false>(b, cell, i, row, notes); return; }
   if (v != v) return;                       // every op below skips NaN fields
   switch (b.op) {
     case DSB_OP_COUNT: atomicAdd((unsigned int*)b.agg + cell, 1u); return;
     case DSB_OP_ANY: ((uint8_t*)b.agg)[cell] = 1; return;
     case DSB_OP_SUM: atomicAdd((double*)b.agg + cell, (double)v); return;
     // no load-before-RED filter here: with 32 warps per SM and 36 KB of L1 the dependent load costs K2 4x (measured)
-    case DSB_OP_MAX32: atomicMax((int*)b.agg + cell, key32_from_f32(v)); return;
-    case DSB_OP_MIN32: atomicMin((int*)b.agg + cell, key32_from_f32(v)); return;
-    default: apply_base<false>(b, cell, i, row); return;
+    case DSB_OP_MAX32: if (notes && is_negzero(v)) *notes = DSB_NOTE_NEGZERO; atomicMax((int*)b.agg + cell, key32_from_f32(v)); return;
+    case DSB_OP_MIN32: if (notes && is_negzero(v)) *notes = DSB_NOTE_NEGZERO; atomicMin((int*)b.agg + cell, key32_from_f32(v)); return;
+    default: apply_base<false>(b, cell, i, row, notes); return;
   }
 }
 
@@ -172,9 +172,9 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a, const
         if (cell < a.npriv) priv_hit<SLOT>(sh, cell, a.scratch, bad);
         else atomicAdd(a.scratch + cell, 1u);
       } else if (reg_v) {
-        apply_base_f32(b, cell, i, p.row_offset + i, vv);
+        apply_base_f32(b, cell, i, p.row_offset + i, vv, p.plan.notes);
       } else {
-        apply_base<false>(b, cell, i, p.row_offset + i);
+        apply_base<false>(b, cell, i, p.row_offset + i, p.plan.notes);
       }
     }
   };
@@ -375,10 +375,11 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
   // hit of a pixel is final and the filter removes the rest, as for "first"
   constexpr bool REVERSE = OP == MONO_MAXROW;
 
+  bool negzero = false;          // a max / min candidate was -0.0: see DSB_NOTE_NEGZERO
   auto key_of = [&](float vv, long long i) -> T {
     const long long row = a.row_offset + i;
     if (OP == MONO_COUNT) return (T)1;
-    if (OP == MONO_MAX32 || OP == MONO_MIN32) return (T)key32_from_f32(vv);
+    if (OP == MONO_MAX32 || OP == MONO_MIN32) { negzero |= is_negzero(vv); return (T)key32_from_f32(vv); }
     if (OP == MONO_MINROW || OP == MONO_MAXROW) return (T)row;
     const long long k = (long long)key32_from_f32(vv) << 32;          // see apply_base: value first, earliest row on ties
     return (T)(OP == MONO_ARGMAX32 ? (k | (long long)(uint32_t)(~(uint32_t)row)) : (k | (long long)(uint32_t)row));
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
   auto commit = [&](int cell, T key, T cur) {
     if constexpr (OP == MONO_COUNT) { atomicAdd(canvas + cell, (T)1); return; }
     else if (IS_MAX) { if (!FILTERED || key > cur) atomicMax(canvas + cell, key); }
-    else { if (key < cur) atomicMin(canvas + cell, key); }
+    else { if (!FILTERED || key < cur) atomicMin(canvas + cell, key); }
   };
   auto exact = [&](float xv, float yv, float vv, long long i) {
     if (vv != vv) return;
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
     const long long i = (n4 << 2) + threadIdx.x;
     exact(x[i], y[i], vcol ? vcol[i] : 1.f, i);
   }
+  if ((OP == MONO_MAX32 || OP == MONO_MIN32) && negzero && a.plan.notes) *a.plan.notes = DSB_NOTE_NEGZERO;
 }
 
 static FastMap make_fast_map(const dsb_view* v);
@@ -518,8 +520,10 @@ __global__ void __launch_bounds__(256, 3) k_points_mono_f64(const __grid_constan
   constexpr bool REVERSE = OP == M64_MAXROW;
   const double* __restrict__ x = (const double*)a.x;
   const double* __restrict__ y = (const double*)a.y;
+  bool negzero = false;
   auto key_of = [&](double vv, long long i) -> long long {
-    return (OP == M64_MAX || OP == M64_MIN) ? (long long)key64_from_f64(vv) : a.row_offset + i;
+    if (OP == M64_MAX || OP == M64_MIN) { negzero |= is_negzero(vv); return (long long)key64_from_f64(vv); }
+    return a.row_offset + i;
   };
   auto commit = [&](long long cell, long long key, long long cur) {
     if (IS_MAX) { if (key > cur) atomicMax(canvas + cell, key); }
@@ -556,6 +560,7 @@ __global__ void __launch_bounds__(256, 3) k_points_mono_f64(const __grid_constan
     const long long c = (vv == vv) ? map_to_cell<double>(a.v, x[i], y[i]) : -1;
     if (c >= 0 && c >= a.band_lo && c < a.band_hi) commit(c, key_of(vv, i), __ldcg(canvas + c));
   }
+  if ((OP == M64_MAX || OP == M64_MIN) && negzero && a.plan.notes) *a.plan.notes = DSB_NOTE_NEGZERO;
 }
 
 static bool try_launch_mono_f64(const PointsArgs& a, int32_t xy_dtype, cudaStream_t s) {
@@ -618,7 +623,7 @@ __global__ void __launch_bounds__(256) k_points_generic_if(const PointsArgs a, c
       if (c < 0 || c >= ncat) continue;
       cell = cell * ncat + c;
     }
-    for (int k = 0; k < a.plan.nops; k++) apply_base(a.plan.ops[k], cell, i, a.row_offset + i);
+    for (int k = 0; k < a.plan.nops; k++) apply_base(a.plan.ops[k], cell, i, a.row_offset + i, a.plan.notes);
   }
 }
 

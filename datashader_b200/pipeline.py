@@ -119,6 +119,9 @@ def _plans(chunk, accs, canv, ctx, categorizer, ncat):
             plan.cat = codes.data_ptr()
             plan.cat_dtype = _lib.dsb_dtype(str(codes.dtype).replace("torch.", ""))
             plan.ncat = ncat
+        notes = getattr(ctx, "notes", None)
+        if notes is not None:
+            plan.notes = notes.data_ptr()
         yield plan, keep
 
 
@@ -130,7 +133,7 @@ def _sub_plan(plan, idx):
     sub.nops = len(idx)
     for j, k in enumerate(idx):
         sub.ops[j] = plan.ops[k]
-    sub.cat, sub.cat_dtype, sub.ncat = plan.cat, plan.cat_dtype, plan.ncat
+    sub.cat, sub.cat_dtype, sub.ncat, sub.notes = plan.cat, plan.cat_dtype, plan.ncat, plan.notes
     return sub
 
 
@@ -255,28 +258,53 @@ def _accumulate_and_finalize(frame, resident, needed, schema, view, canvas, glyp
     for k, v in (ctx_extra or {}).items():
         setattr(ctx, k, v)
     reds = _reductions_of(agg)
-    accs, seen = [], set()
-    for r in reds:
-        for a in r._accs(ctx):
+
+    def unique_accs(lists):
+        out, seen = [], set()
+        for a in lists:
             if a.key not in seen:
                 seen.add(a.key)
-                accs.append(a)
-    canv = {a.key: _alloc_canvas(a, shape, device, stream_ptr) for a in accs}
-    # stage 0: everything that needs one pass; stage 1: accumulators that read a finished stage-0 canvas
-    for stage in ([a for a in accs if a.aux is None], [a for a in accs if a.aux is not None]):
-        if not stage:
-            continue
-        if config.time_kernels:
-            ev0 = torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        for ch in ([resident] if single else frame.chunks(needed)):
-            launch(view, ch, glyph, stage, canv, ctx, categorizer, ncat)
-        if config.time_kernels:
-            ev1 = torch.cuda.Event(enable_timing=True)
-            ev1.record()
-            config.kernel_events.append((ev0, ev1))
+                out.append(a)
+        return out
+
+    canv = {}
+
+    def run(accs):
+        """allocate the canvases of `accs`, launch them (stage 0, then the accumulators that read a finished stage-0
+        canvas) over every chunk and combine them across ranks"""
+        accs = [a for a in accs if a.key not in canv]
+        canv.update({a.key: _alloc_canvas(a, shape, device, stream_ptr) for a in accs})
+        for stage in ([a for a in accs if a.aux is None], [a for a in accs if a.aux is not None]):
+            if not stage:
+                continue
+            if config.time_kernels:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            for ch in ([resident] if single else frame.chunks(needed)):
+                launch(view, ch, glyph, stage, canv, ctx, categorizer, ncat)
+            if config.time_kernels:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                config.kernel_events.append((ev0, ev1))
+            if dist is not None:
+                dist.combine(stage, canv)
+
+    accs = unique_accs([a for r in reds for a in r._accs(ctx)])
+    # max / min of a float column: the keys fold -0.0 onto +0.0, so the pass reports whether it met a -0.0 at all
+    # (DSB_NOTE_NEGZERO, include/dsb200.h); only then is the sign of a zero extreme in doubt
+    zero_keyed = [a for a in accs if a.kind in ("max32", "min32", "max64", "min64") and a.col is not None
+                  and np.dtype(ctx.np_dtype(a.col)).kind == "f"]
+    ctx.notes = torch.zeros(1, dtype=torch.int32, device=device) if zero_keyed else None
+    run(accs)
+    if ctx.notes is not None:
         if dist is not None:
-            dist.combine(stage, canv)
+            dist._all_reduce(ctx.notes, "max")
+        if int(ctx.notes.item()) & _lib.NOTE_NEGZERO:
+            # rare: redo those reductions through the row-exact accumulators (the earliest row among the extreme's
+            # ties, exactly the reference's strict compare) and gather that row's own bit pattern
+            ctx.exact_zero = True
+            ctx.notes = None
+            run(unique_accs([a for r in reds for a in r._exact_accs(ctx)]))
     results = [r._finalize(ctx, canv) for r in reds]
     return reds, results, labels
 
@@ -359,6 +387,10 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
         frame, frame.plot_start = dist.carry_last_row(frame, needed)     # row shards of one long line (dask.py:244-266)
     line_width = float(glyph._line_width)
     simple = config.lines_simple_path and type(agg) in (rd.any, rd.count, rd.sum, rd.max, rd.min)
+    if simple and line_width == 0 and type(agg) in (rd.max, rd.min) and frame.np_dtype(agg.column).kind == "f":
+        v = frame[agg.column]
+        if bool(((v == 0) & torch.signbit(v)).any()):
+            simple = False       # a -0.0 value: the plan path resolves which zero arrived first (DSB_NOTE_NEGZERO)
     if line_width == 0 and not simple:
         return _lines_plan(frame, needed, schema, canvas, glyph, agg, dist)
     combo = _aa2_combo(agg) if line_width > 0 else None

@@ -59,8 +59,11 @@ ACC_OP = {
 
 
 def _is_key32(np_dtype):
+    """Columns whose max / min run on 32-bit order-preserving keys.  32-bit integers are excluded: their keys can
+    equal the INT_MIN / INT_MAX "empty" sentinels of the key32 canvases (uint32 0, int32 INT32_MIN / INT32_MAX),
+    so they take the 64-bit key path, where every value is far from the sentinels."""
     d = np.dtype(np_dtype)
-    return d == np.float32 or (d.kind in "iub" and d.itemsize <= 4)
+    return d == np.float32 or (d.kind in "iub" and d.itemsize <= 2)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -187,6 +190,10 @@ class Reduction:
         """-> torch tensor on the device, already in the reference's output dtype/layout."""
         raise NotImplementedError
 
+    def _exact_accs(self, ctx):
+        """accumulators of the row-exact redo after DSB_NOTE_NEGZERO (max / min only)"""
+        return []
+
     # antialiased-line support: (dsb_line_agg, needs value column)
     _line_agg = None
 
@@ -288,7 +295,19 @@ class _MinMax(_FloatingReduction):
     def _accs(self, ctx):
         return [self._acc(ctx)]
 
+    def _as_where(self):
+        """where(self, self.column): the selected row per pixel - the earliest row among the ties of the extreme, which
+        is the row whose value the reference's strict compare keeps (reductions.py:1178-1183, 1222-1227)"""
+        w = where.__new__(where)
+        w.column, w.selector, w.columns = self.column, self, (self.column, self.column)
+        return w
+
+    def _exact_accs(self, ctx):
+        return self._as_where()._row_accs(ctx)
+
     def _finalize(self, ctx, canv):
+        if getattr(ctx, "exact_zero", False) and np.dtype(ctx.np_dtype(self.column)).kind == "f":
+            return _gather(ctx, self._as_where()._rows(ctx, canv), self.column)
         acc = self._acc(ctx)
         k = canv[acc.key]
         out = torch.empty(k.shape, dtype=torch.float64, device=k.device)
@@ -475,6 +494,9 @@ class by(Reduction):
 
     def _accs(self, ctx):
         return self.reduction._accs(ctx)
+
+    def _exact_accs(self, ctx):
+        return self.reduction._exact_accs(ctx)
 
     def _finalize(self, ctx, canv):
         return self.reduction._finalize(ctx, canv)

@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define DSB_ABI_VERSION 1
+#define DSB_ABI_VERSION 2
 #define DSB_MAX_OPS 8
 
 typedef enum {
@@ -81,7 +81,15 @@ typedef struct {
   const void* cat;          /* optional [n] integer category codes: by()/count_cat (compiler.py:379-390) */
   int32_t cat_dtype;        /* DSB_I8 / DSB_I16 / DSB_I32 / DSB_I64, DSB_NONE when not categorical */
   int32_t ncat;             /* canvases become [H, W, ncat]; negative codes wrap like numba's agg[:, :, -1] */
+  uint32_t* notes;          /* optional device word (may be NULL), OR-ed with DSB_NOTE_* bits by the pass */
 } dsb_plan;
+
+/* dsb_plan.notes bits.  DSB_NOTE_NEGZERO: a MAX32/MIN32/MAX64/MIN64 accumulator consumed a float -0.0.  The keys fold
+ * -0.0 onto +0.0 (the reference compares with < / >, for which the zeros tie), so a pixel whose extreme is a zero
+ * decodes as +0.0 while the reference keeps whichever zero ARRIVED FIRST (strict compare, reductions.py:1178-1183,
+ * 1222-1227).  When the bit is set the caller re-runs those reductions through the row-exact accumulators
+ * (ARGMAX32 / ARGMIN32, or MAX64 / MIN64 + MATCHROW64) and gathers the winning row's own bit pattern. */
+#define DSB_NOTE_NEGZERO 1u
 
 int dsb_abi_version(void);
 const char* dsb_last_error(void);

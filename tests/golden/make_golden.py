@@ -538,7 +538,37 @@ def area_cases():
     return out
 
 
+def negzero_cases():
+    """max / min keep whichever zero ARRIVED FIRST when the extreme of a pixel is a zero (strict compare,
+    reductions.py:1178-1183, 1222-1227): columns mixing -0.0 and +0.0 with values on one side of zero only."""
+    out = {}
+    rng = np.random.default_rng(606)
+    n = 4000
+    x = rng.random(n).astype(np.float32)
+    y = rng.random(n).astype(np.float32)
+    zeros = np.where(rng.random(n) < 0.5, np.float32(-0.0), np.float32(0.0))
+    neg = -rng.random(n).astype(np.float32) - 0.1
+    vmax32 = np.where(rng.random(n) < 0.4, zeros, neg).astype(np.float32)          # the max of most pixels is a zero
+    vmin32 = np.where(rng.random(n) < 0.4, zeros, -neg).astype(np.float32)         # the min of most pixels is a zero
+    vmax32[rng.integers(0, n, n // 30)] = np.nan
+    cols = dict(x=x, y=y, vmax32=vmax32, vmin32=vmin32, vmax64=vmax32.astype(np.float64), vmin64=vmin32.astype(np.float64),
+                cat=rng.integers(0, NCAT, n).astype(np.int8))
+    for k, v in cols.items():
+        out[f"in_{k}"] = v
+    df = to_df(cols)
+    cvs = ds.Canvas(plot_width=9, plot_height=7, x_range=(0, 1), y_range=(0, 1))
+    for name, red in (("max_vmax32", ds.max("vmax32")), ("min_vmin32", ds.min("vmin32")), ("max_vmax64", ds.max("vmax64")),
+                      ("min_vmin64", ds.min("vmin64")), ("by_max_vmax32", ds.by("cat", ds.max("vmax32"))),
+                      ("max_vmin32", ds.max("vmin32")), ("min_vmax32", ds.min("vmax32"))):
+        out[f"nz_{name}"] = np.asarray(cvs.points(df, "x", "y", red).data)
+    return out
+
+
 def main():
+    if "--negzero-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "points_negzero.npz"), **negzero_cases())
+        print("points_negzero.npz", os.path.getsize(os.path.join(HERE, "points_negzero.npz")) // 1024, "KiB")
+        return
     if "--lines-aa2-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
         print("lines_aa2.npz", os.path.getsize(os.path.join(HERE, "lines_aa2.npz")) // 1024, "KiB")
@@ -575,6 +605,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
     np.savez_compressed(os.path.join(HERE, "shade_span.npz"), **shade_span_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
+    np.savez_compressed(os.path.join(HERE, "points_negzero.npz"), **negzero_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())
     np.savez_compressed(os.path.join(HERE, "lines.npz"), **lines_cases())
     for f in ("points.npz", "partitioned.npz", "lines.npz", "shade.npz"):

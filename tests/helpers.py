@@ -70,6 +70,13 @@ def assert_agg_equal(got, want, name, rtol=RTOL_SUM, atol=0):
         np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, equal_nan=True, err_msg=name)
     else:
         assert np.array_equal(got, want, equal_nan=(got.dtype.kind == "f")), name
+        if got.dtype.kind == "f":
+            # bit patterns, not just values: np.array_equal treats -0.0 == +0.0, the reference keeps the zero that
+            # arrived first (NaN payloads are not compared)
+            ok = ~np.isnan(want)
+            bits = {4: np.uint32, 8: np.uint64}[got.dtype.itemsize]
+            assert np.array_equal(np.ascontiguousarray(got)[ok].view(bits), np.ascontiguousarray(want)[ok].view(bits)), \
+                f"{name}: sign of zero differs"
 
 
 def make_agg(spec):

@@ -16,14 +16,14 @@ def test_library_exports_every_declared_symbol():
     assert len(declared) >= 12
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
-    assert L.dsb_abi_version() == 1
+    assert L.dsb_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header():
     # dsb_view: 4 x i32 + 8 x f64; dsb_base: 2 ints+ptr ... natural alignment
     assert ctypes.sizeof(_lib.View) == 16 + 64
     assert ctypes.sizeof(_lib.Base) == 48
-    assert ctypes.sizeof(_lib.Plan) == 8 + 48 * 8 + 8 + 8
+    assert ctypes.sizeof(_lib.Plan) == 8 + 48 * 8 + 8 + 8 + 8
 
 
 def test_argument_errors_do_not_need_a_gpu():

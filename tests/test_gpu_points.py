@@ -41,6 +41,36 @@ def test_points_golden(ds, tag, cname):
     assert tuple(agg.dims) == ("y", "x")
 
 
+@pytest.mark.parametrize("source", ["pandas", "device_mono", "host_chunks"])
+def test_points_negzero_golden(ds, source):
+    """A pixel whose max / min is a zero keeps the sign of the zero that arrived first (reductions.py:1178-1183,
+    1222-1227): the keys fold -0.0 onto +0.0, the pass raises DSB_NOTE_NEGZERO and the host redoes the reduction through
+    the row-exact accumulators.  Bit patterns compared (helpers.assert_agg_equal)."""
+    import torch
+    from datashader_b200 import _lib
+    from test_oracle_golden import NEGZERO
+    g = load("points_negzero.npz")
+    cols = columns_from_golden(g, "in_")
+    cvs = ds.Canvas(plot_width=9, plot_height=7, x_range=(0, 1), y_range=(0, 1))
+    L = _lib.lib()
+    try:
+        if source == "pandas":
+            src = pandas_frame(cols)
+        elif source == "device_mono":         # the single-accumulator kernels (k_points_mono, k_points_mono_f64)
+            _lib.check(L.dsb_configure(b"mono_min_rows", 0))
+            src = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items() if k not in ("cat__ncat",)},
+                                 categories={"cat": [f"c{i}" for i in range(NCAT)]})
+        else:                                  # host columns streamed in chunks: the gather runs against the host column
+            src = ds.HostFrame({k: torch.from_numpy(v) for k, v in cols.items() if k not in ("cat__ncat", "cat")},
+                               chunk_rows=1024)
+        for name, spec in NEGZERO.items():
+            if source == "host_chunks" and spec[0] == "by":
+                continue
+            assert_agg_equal(cvs.points(src, "x", "y", make_agg(spec)).data, g[f"nz_{name}"], f"negzero {source} {name}")
+    finally:
+        _lib.check(L.dsb_configure(b"mono_min_rows", 1 << 20))
+
+
 def test_by_dims_and_labels(ds):
     g = load("points.npz")
     cols = columns_from_golden(g, "in_f32_")
@@ -304,18 +334,24 @@ def test_l2_banded_passes_match_oracle(ds):
         _lib.check(L.dsb_configure(b"l2_band_bytes", 64 * 1024))
         _lib.check(L.dsb_configure(b"band_min_rows", 0))
         ds.config.priv_count = False
-        for rname in ("count", "mean_v32", "max_v32", "max_v64", "first_v32", "last_v32", "where_max_v32_other",
-                      "where_min_v32_row", "by_count", "by_max_v32"):
-            spec = SPECS[rname]
-            got = cvs.points(df, "x", "y", make_agg(spec)).data
-            want = ora.points(cols, "x", "y", spec, view, npartitions=2 if "first" in rname or "last" in rname else 1)
-            assert_agg_equal(got, want, f"banded {rname}")
+        # mono_min_rows = 0 sends the single-accumulator plans through the BANDED k_points_mono (the production path of
+        # 8192^2 canvases); the default leaves them to the banded generic kernel - both must agree with the oracle
+        for mono_rows in (0, 1 << 20):
+            _lib.check(L.dsb_configure(b"mono_min_rows", mono_rows))
+            for rname in ("count", "count_v32", "mean_v32", "max_v32", "min_v32", "max_v64", "first_v32", "last_v32",
+                          "where_max_v32_other", "where_min_v32_other", "where_min_v32_row", "where_first_v32_other",
+                          "by_count", "by_max_v32"):
+                spec = SPECS[rname]
+                got = cvs.points(df, "x", "y", make_agg(spec)).data
+                want = ora.points(cols, "x", "y", spec, view, npartitions=2 if "first" in rname or "last" in rname else 1)
+                assert_agg_equal(got, want, f"banded {rname} mono_min_rows={mono_rows}")
         spec = ("where", ("max", "v64"), "other")
         assert_agg_equal(cvs.points(df, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view), "banded 2-pass")
     finally:
         ds.config.priv_count = old_priv
         _lib.check(L.dsb_configure(b"l2_band_bytes", 96 << 20))
         _lib.check(L.dsb_configure(b"band_min_rows", 1 << 22))
+        _lib.check(L.dsb_configure(b"mono_min_rows", 1 << 20))
 
 
 def test_arrow_and_dict_sources_match_pandas(ds):

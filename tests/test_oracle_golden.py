@@ -45,6 +45,22 @@ def test_points_log_axes_golden():
     np.testing.assert_allclose(ora.axis_index((view.sy, view.ty), 30, "log"), g["pts_log_ycoords"], rtol=1e-15)
 
 
+NEGZERO = {"max_vmax32": ("max", "vmax32"), "min_vmin32": ("min", "vmin32"), "max_vmax64": ("max", "vmax64"),
+           "min_vmin64": ("min", "vmin64"), "by_max_vmax32": ("by", "cat", ("max", "vmax32")),
+           "max_vmin32": ("max", "vmin32"), "min_vmax32": ("min", "vmax32")}
+
+
+def test_points_negzero_golden():
+    """max / min keep the zero that arrived first (-0.0 or +0.0): compared as bit patterns (helpers.assert_agg_equal)."""
+    g = load("points_negzero.npz")
+    cols = columns_from_golden(g, "in_")
+    view = ora.make_view(9, 7, (0, 1), (0, 1))
+    for name, spec in NEGZERO.items():
+        want = g[f"nz_{name}"]
+        assert np.signbit(want[want == 0]).any() or "vmin32" in name and "max" in name or "vmax32" in name and "min" in name
+        assert_agg_equal(ora.points(cols, "x", "y", spec, view), want, f"negzero {name}")
+
+
 @pytest.mark.parametrize("nparts", [1, 3, 4])
 def test_partitioned_golden(nparts):
     """dask-style partition + combine (data_libraries/dask.py:168-217) equals the single pass."""
