@@ -1,16 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: Canvas(900x525).points over 1e9 float32 points per GPU, agg=mean('value')
-(BASELINE.json configs[1]), plus the count() variant of the same pass.
+"""Benchmark of the hot path, on BASELINE.json's metric: Canvas.points count Gpoints/s at 1/2/4/8 B200 and the
+fraction of the HBM-read roofline, on BASELINE.json configs[1]'s data (900x525, 1e9 float32 points per GPU).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
-    python bench.py --impl reference ...                      # the reference's CPU algorithm (oracle port,
-                                                              #   all host threads) on a bounded sample
+    python bench.py --impl reference ...                      # the reference's own CPU path (numba, from oracle/_ref
+                                                              #   when present, else the C oracle port), all host threads
 
-Prints ONE JSON line (rank 0).  `value` = Gpoints/s with the columns resident in HBM; `e2e` = the same
-call fed from pinned HOST columns (H2D of every column + D2H of the aggregate inside the timed
-region); `roofline` = algorithmic bytes (12 B/point for mean) / CUDA-event time of the
-fused aggregation kernel against the measured HBM peak; `cpu_baseline` = the oracle port timed on
-this box's host cores on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0):
+  value / ms_per_step   count() over the resident columns, whole job (weak scaling: 1e9 points per GPU)
+  roofline              the count kernel: algorithmic bytes (8 B/point) / CUDA-event time of the fused
+                        aggregation launch against the measured HBM peak; the kernel's name comes from the library
+  mean                  the same pass with agg=mean('value') (configs[1] as written), with its own roofline (12 B/point)
+  strong                configs[1] read as strong scaling: 1e9 points IN TOTAL sharded over the N GPUs (count and mean)
+  configs               BASELINE.json configs[2..4]: by('cat', count()) + shade at 1920x1080; antialiased LinesAxis1 max at
+                        3840x2160; max / first at 8192x8192 over 4e9 points (sharded over the N GPUs, all-reduced)
+  parity_ok             count / mean / first / where(max) of a 1e7-row sample, sharded over the N GPUs, against the
+                        single-pass CPU oracle - checked before anything is timed
+  e2e                   the headline call fed from pinned HOST columns (H2D of x, y + D2H of the aggregate in the timed region)
+  cpu_baseline          the reference's CPU path timed on this box's host cores on a bounded sample
 """
 import argparse
 import json
@@ -25,21 +32,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 W, H = 900, 525
-BYTES_PER_POINT = {"mean": 12, "count": 8}
 SEED = 20240917
-
-
-def ncu_traffic_gb(workload, n):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
-    (profiles/r01_traffic.json, one `ncu --set full` launch at the same n); None when no capture matches."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(p) as f:
-            t = json.load(f)
-        e = t.get(f"{workload}:{n}")
-        return e["dram_gb"] if e else None
-    except Exception:  # noqa: BLE001
-        return None
+METRIC = "Canvas.points count Gpoints/s at 1/2/4/8 B200; % of HBM-read roofline"
 
 
 def measured_hbm_peak():
@@ -51,6 +45,20 @@ def measured_hbm_peak():
         except Exception:  # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_gb(kernel, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed `ncu --set full` capture at the same
+    n (profiles/r02_traffic.json: {kernel name: {n: GB per launch}}); None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            t = json.load(f)
+        for name, by_n in t.items():
+            if kernel and kernel.startswith(name) and str(n) in by_n:
+                return by_n[str(n)]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -105,235 +113,439 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def make_device_columns(n, rank, device):
-    """uniform x, y in [0,1) f32; value ~ N(0,1) f32 with 0.1 % NaN, generated on the device."""
+def host_sample(n, seed=SEED):
+    """uniform x, y in [0,1) f32; value ~ N(0,1) f32 with 0.1 % NaN - the CPU-side twin of
+    make_device_columns (same distribution; the device generator is torch's)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32)}
+    v = rng.standard_normal(n, dtype=np.float32)
+    v[rng.integers(0, n, max(1, n // 1000))] = np.nan
+    cols["value"] = v
+    return cols
+
+
+def make_device_columns(n, rank, device, value=True):
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(SEED + rank)
-    x = torch.rand(n, generator=g, device=device, dtype=torch.float32)
-    y = torch.rand(n, generator=g, device=device, dtype=torch.float32)
-    v = torch.empty(n, device=device, dtype=torch.float32)
     step = 1 << 27
-    for lo in range(0, n, step):      # chunked: randn + mask temporaries stay small
+    x = torch.empty(n, device=device, dtype=torch.float32)
+    y = torch.empty(n, device=device, dtype=torch.float32)
+    v = torch.empty(n, device=device, dtype=torch.float32) if value else None
+    for lo in range(0, n, step):      # chunked: the generator's temporaries stay small
         hi = min(n, lo + step)
-        v[lo:hi].normal_(generator=g)
-        m = torch.rand(hi - lo, generator=g, device=device) < 1e-3
-        v[lo:hi].masked_fill_(m, float("nan"))
-        del m
+        x[lo:hi].uniform_(generator=g)
+        y[lo:hi].uniform_(generator=g)
+        if value:
+            v[lo:hi].normal_(generator=g)
+            m = torch.rand(hi - lo, generator=g, device=device) < 1e-3
+            v[lo:hi].masked_fill_(m, float("nan"))
+            del m
     return x, y, v
 
 
-def cpu_baseline(sample_n, workload, threads=None):
-    """The oracle port (the reference's numba algorithm restated in C) on the host cores: `threads` row
-    partitions aggregated into private canvases and combined, like dask's threaded scheduler."""
-    import numpy as np
-    from oracle import oracle as ora
-    threads = threads or os.cpu_count() or 1
-    rng = np.random.default_rng(SEED)
-    cols = {"x": rng.random(sample_n, dtype=np.float32), "y": rng.random(sample_n, dtype=np.float32)}
-    v = rng.standard_normal(sample_n, dtype=np.float32)
-    v[rng.integers(0, sample_n, sample_n // 1000)] = np.nan
-    cols["value"] = v
-    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
-    spec = ("mean", "value") if workload == "mean" else ("count",)
-    ora.points_mt(cols, "x", "y", spec, view, threads)      # warm-up (page faults, thread start)
-    best = float("inf")
-    for _ in range(3):
-        t0 = time.perf_counter()
-        ora.points_mt(cols, "x", "y", spec, view, threads)
-        best = min(best, time.perf_counter() - t0)
-    return sample_n / best / 1e9, best, threads
+# ------------------------------------------------------------------------------------------------ CPU arms
+def _ref_module():
+    """The reference itself (numba CPU path), vendored by oracle/make_ref.py into oracle/_ref (git-ignored; travels
+    with gpurun).  None when it is absent or does not import on this box."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "datashader")):
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ref, "_shims"))
+        sys.path.insert(0, ref)
+        import datashader  # noqa: F401
+        return datashader
+    except Exception:  # noqa: BLE001
+        for p in (ref, os.path.join(ref, "_shims")):
+            if p in sys.path:
+                sys.path.remove(p)
+        return None
+
+
+class CpuArm:
+    """count() / mean('value') over `threads` row partitions aggregated into private canvases and combined - what dask's
+    threaded scheduler does with the reference's nogil numba kernels (data_libraries/dask.py:168-217)."""
+
+    def __init__(self, cols, threads):
+        self.cols, self.threads = cols, threads
+        self.n = len(cols["x"])
+        self.ref = _ref_module()
+        self.kind = "reference" if self.ref is not None else "port"
+        if self.ref is not None:
+            self._setup_ref()
+        else:
+            from oracle import oracle as ora
+            self.ora = ora
+            self.view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+
+    def _setup_ref(self):
+        import pandas as pd
+        from concurrent.futures import ThreadPoolExecutor
+        ds = self.ref
+        self.df = pd.DataFrame(self.cols, copy=False)
+        self.cvs = ds.Canvas(plot_width=W, plot_height=H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+        self.pool = ThreadPoolExecutor(self.threads)
+        n, t = self.n, self.threads
+        self.parts = []
+        for p in range(t):
+            part = self.df.iloc[n * p // t:n * (p + 1) // t]
+            object.__setattr__(part, "_datashader_row_offset", n * p // t)
+            self.parts.append(part)
+
+    def _run_ref(self, workload):
+        from datashader.compiler import compile_components
+        from datashader.glyphs import Point
+        from datashader.utils import dshape_from_pandas
+        ds, cvs = self.ref, self.cvs
+        red = ds.count() if workload == "count" else ds.mean("value")
+        glyph = Point("x", "y")
+        schema = dshape_from_pandas(self.df)
+        create, info, append, combine, finalize, aa2, aa2f, _ = compile_components(
+            red, schema, glyph, antialias=False, cuda=False, partitioned=True)
+        extend = glyph._build_extend(cvs.x_axis.mapper, cvs.y_axis.mapper, info, append, aa2, aa2f)
+        x_st = cvs.x_axis.compute_scale_and_translate(cvs.x_range, cvs.plot_width)
+        y_st = cvs.y_axis.compute_scale_and_translate(cvs.y_range, cvs.plot_height)
+
+        def chunk(part):
+            aggs = create((H, W))
+            extend(aggs, part, x_st + y_st, cvs.x_range + cvs.y_range)
+            return aggs
+
+        return combine(list(self.pool.map(chunk, self.parts)))
+
+    def run(self, workload):
+        if self.ref is not None:
+            return self._run_ref(workload)
+        spec = ("mean", "value") if workload == "mean" else ("count",)
+        return self.ora.points_mt(self.cols, "x", "y", spec, self.view, self.threads)
+
+    def best_of(self, workload, reps=3):
+        self.run(workload)                       # warm-up (numba JIT / page faults / thread start)
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            self.run(workload)
+            best = min(best, time.perf_counter() - t0)
+        return self.n / best / 1e9, best
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm for this path (oracle port; the reference is pure
-    Python + numba and cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, all threads, each
+    step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from oracle import oracle as ora
     threads = os.cpu_count() or 1
     sample_n = args.cpu_sample
-    rng = np.random.default_rng(SEED)
-    cols = {"x": rng.random(sample_n, dtype=np.float32), "y": rng.random(sample_n, dtype=np.float32)}
-    v = rng.standard_normal(sample_n, dtype=np.float32)
-    v[rng.integers(0, sample_n, sample_n // 1000)] = np.nan
-    cols["value"] = v
-    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
-    spec = ("mean", "value") if args.workload == "mean" else ("count",)
-    for _ in range(args.warmup):
-        ora.points_mt(cols, "x", "y", spec, view, threads)
+    arm = CpuArm(host_sample(sample_n), threads)
+    for _ in range(max(1, args.warmup)):
+        arm.run("count")
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ora.points_mt(cols, "x", "y", spec, view, threads)
+        arm.run("count")
     dt = time.perf_counter() - t0
     val = sample_n * args.steps / dt / 1e9
-    sample = f"{sample_n:.0e} of the {args.n:.0e} points per step (same generator), {threads} threads"
+    mean_val, _ = arm.best_of("mean", reps=1)
+    sample = (f"{sample_n:.0e} of the {args.n:.0e} points per step (same distribution), {threads} threads, "
+              + ("the reference's numba kernels (oracle/_ref)" if arm.kind == "reference" else "C port of the numba loops"))
     line = {
-        "impl": "reference", "metric": f"Canvas.points Gpoints/s ({args.workload}('value'), 900x525)", "value": val,
-        "unit": "Gpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Canvas(900x525).points, agg={args.workload}('value'), float32 x/y/value, "
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gpoints/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Canvas(900x525).points, agg=count(), float32 x/y (BASELINE.json configs[1] data), "
                                f"bounded CPU sample of {sample_n} rows per step", "points_per_gpu": args.n},
-        "cpu_baseline": {"value": val, "unit": "Gpoints/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Gpoints/s", "cores": threads, "kind": arm.kind, "sample": sample},
+        "mean": {"value": mean_val, "unit": "Gpoints/s"},
         "e2e": {"value": val, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (datashader_b200 has no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.device)
+        import datashader_b200 as ds
+        from datashader_b200 import _lib, config
+        self.ds, self.lib, self.config = ds, _lib.lib(), config
+        self.peak, self.peak_src = measured_hbm_peak()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (datashader_b200 has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    import datashader_b200 as ds
-    from datashader_b200 import _lib, config
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), device=self.device, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
 
-    n = args.n
-    x, y, v = make_device_columns(n, rank, device)
-    frame = ds.DeviceFrame({"x": x, "y": y, "value": v}, row_offset=rank * n)
-    frame.sharded = world > 1
-    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
-    agg = ds.mean("value") if args.workload == "mean" else ds.count()
-    config.device_results = True
+    def last_kernel(self):
+        fn = getattr(self.lib, "dsb_last_kernel", None)
+        if fn is None:
+            return None
+        s = fn()
+        return s.decode() if s else None
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def timed(self, fn, steps, warmup):
+        """W untimed + K timed calls bracketed by barrier + synchronize; CUDA events on the launching stream; the fused
+        aggregation launches carry their own events (config.kernel_events); max over ranks."""
+        torch, config = self.torch, self.config
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        config.time_kernels = True
+        config.kernel_events.clear()
+        l0 = self.lib.dsb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        config.time_kernels = False
+        ms = e0.elapsed_time(e1) / steps
+        kms = sum(a.elapsed_time(b) for a, b in config.kernel_events) / max(1, steps)
+        ms, kms = self.max_over_ranks(ms, kms)
+        return {"ms": ms, "kernel_ms": kms, "out": out, "launches": int(self.lib.dsb_launch_count() - l0),
+                "kernel": self.last_kernel()}
 
-    def step():
-        return cvs.points(frame, "x", "y", agg)
+    def roofline(self, r, units, bytes_per_unit, n_for_traffic=None):
+        ach = units * bytes_per_unit / (r["kernel_ms"] * 1e-3) / 1e9 if r["kernel_ms"] > 0 else None
+        return {"bound": "hbm", "achieved": ach, "peak": self.peak, "unit": "GB/s", "frac": ach / self.peak if ach else None,
+                "traffic": ncu_traffic_gb(r["kernel"], n_for_traffic or units), "kernel": r["kernel"],
+                "kernel_ms": r["kernel_ms"], "peak_source": self.peak_src, "algorithmic_bytes_per_unit": bytes_per_unit,
+                "traffic_unit": "GB per launch (ncu dram read+write)"}
 
-    for _ in range(args.warmup):
-        out = step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    config.time_kernels = True
-    config.kernel_events.clear()
-    launches0 = _lib.lib().dsb_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        out = step()
-    ev1.record()
-    barrier()
-    config.time_kernels = False
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    launches = _lib.lib().dsb_launch_count() - launches0
-    kernel_ms = sum(a.elapsed_time(b) for a, b in config.kernel_events) / max(1, len(config.kernel_events))
-    t = torch.tensor([ms, kernel_ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, kernel_ms = t.tolist()
-    value = world * n * args.steps / (ms * 1e-3) / 1e9
-    def total_u32(t):
-        return int(t.view(torch.int32).to(torch.int64).sum().item())
+    # ---- parity of the sharded path on a sample, before anything is timed ------------------------------------------
+    def parity(self):
+        import numpy as np
+        torch, ds = self.torch, self.ds
+        from datashader_b200.distributed import shard_bounds
+        m = self.args.parity_n
+        cols = host_sample(m, SEED + 7)
+        lo, hi = shard_bounds(m, self.rank, self.world)
+        frame = ds.DeviceFrame({k: torch.from_numpy(np.ascontiguousarray(v[lo:hi])).to(self.device) for k, v in cols.items()},
+                               row_offset=lo)
+        frame.sharded = self.world > 1
+        cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+        old = self.config.priv_min_rows
+        self.config.priv_min_rows = 0          # the timed kernels (K2) also at this size
+        specs = {"count": (ds.count(), ("count",)), "mean": (ds.mean("value"), ("mean", "value")),
+                 "first": (ds.first("value"), ("first", "value")),
+                 "where_max": (ds.where(ds.max("value")), ("where", ("max", "value"), None))}
+        bad = []
+        try:
+            got = {k: np.asarray(cvs.points(frame, "x", "y", a).data) for k, (a, _) in specs.items()}
+        finally:
+            self.config.priv_min_rows = old
+        if self.rank == 0:
+            from oracle import oracle as ora          # the checker; never on the measured path
+            view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+            for k, (_, spec) in specs.items():
+                want = ora.points(cols, "x", "y", spec, view, npartitions=2 if k == "first" else 1)
+                if k == "mean":
+                    ok = np.array_equal(np.isnan(got[k]), np.isnan(want)) and np.allclose(got[k], want, rtol=1e-12, atol=0, equal_nan=True)
+                else:
+                    ok = got[k].dtype == want.dtype and np.array_equal(got[k], want, equal_nan=got[k].dtype.kind == "f")
+                if not ok:
+                    bad.append(k)
+        return {"parity_ok": not bad, "parity_failed": bad, "parity_sample_rows": m,
+                "parity_checked": "count (bit-exact), mean (rtol 1e-12), first, where(max) row ids (bit-exact) vs the CPU oracle"}
 
-    checksum = float(torch.nan_to_num(out.data.double()).sum().item()) if args.workload == "mean" else total_u32(out.data)
+    # ---- BASELINE.json configs[2..4] --------------------------------------------------------------------------------
+    def config3(self, x, y):
+        torch, ds = self.torch, self.ds
+        n = len(x)
+        g = torch.Generator(device=self.device)
+        g.manual_seed(3)
+        cat = torch.randint(0, 16, (n,), generator=g, device=self.device, dtype=torch.int8)
+        frame = ds.DeviceFrame({"x": x, "y": y, "cat": cat}, categories={"cat": [f"c{i}" for i in range(16)]})
+        cvs = ds.Canvas(1920, 1080, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+        r = self.timed(lambda: cvs.points(frame, "x", "y", ds.by("cat", ds.count())), 5, 3)
+        total = int(r["out"].data.view(torch.int32).to(torch.int64).sum().item())
+        agg = r["out"]
+        s = self.timed(lambda: ds.tf.shade(agg, how="eq_hist"), 5, 3)
+        return {"workload": "Canvas(1920x1080).points, by('cat', count()) 16 categories (int8 codes), then tf.shade(eq_hist)",
+                "points": n, "agg_ms": r["ms"], "agg_gpoints_per_s": n / r["ms"] / 1e6, "shade_ms": s["ms"],
+                "roofline": self.roofline(r, n, 9), "count_total_ok": total == n}
 
-    # ---- the count() variant of the same pass (the other half of the north-star target), device-resident
-    also = {}
-    if args.also_count and args.workload == "mean":
-        cagg = ds.count()
-        for _ in range(2):
-            cvs.points(frame, "x", "y", cagg)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(args.steps):
-            cout = cvs.points(frame, "x", "y", cagg)
-        c1.record()
-        barrier()
-        cms = torch.tensor([c0.elapsed_time(c1)], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(cms, op=dist.ReduceOp.MAX)
-        cg = world * n * args.steps / (cms.item() * 1e-3) / 1e9
-        peak, _ = measured_hbm_peak()
-        also = {"count_gpoints_per_s": cg, "count_ms_per_step": cms.item() / args.steps,
-                "count_hbm_frac": cg / world * 8 / peak, "count_total": total_u32(cout.data)}
+    def config4(self):
+        torch, ds = self.torch, self.ds
+        nl, nv = 100_000, 1000
+        g = torch.Generator(device=self.device)
+        g.manual_seed(4)
+        xs = torch.arange(nv, device=self.device, dtype=torch.float32).repeat(nl, 1)
+        ys = torch.randn(nl, nv, generator=g, device=self.device).cumsum(dim=1)
+        cols = {f"x{j}": xs[:, j].contiguous() for j in range(nv)}
+        cols.update({f"y{j}": ys[:, j].contiguous() for j in range(nv)})
+        cols["value"] = torch.rand(nl, generator=g, device=self.device)
+        frame = ds.DeviceFrame(cols)
+        xr, yr = (0.0, float(nv - 1)), (float(ys.min()), float(ys.max()))
+        del xs, ys
+        cvs = ds.Canvas(3840, 2160, x_range=xr, y_range=yr)
+        xc, yc = [f"x{j}" for j in range(nv)], [f"y{j}" for j in range(nv)]
+        nseg = nl * (nv - 1)
+        out = {"workload": "Canvas(3840x2160).line LinesAxis1 100k lines x 1000 samples, max('value')", "segments": nseg}
+        for lw, tag in ((1, "antialiased"), (0, "bresenham")):
+            r = self.timed(lambda: cvs.line(frame, x=xc, y=yc, axis=1, agg=ds.max("value"), line_width=lw), 3, 2)
+            out[tag] = {"ms": r["ms"], "gsegments_per_s": nseg / r["ms"] / 1e6, "kernel": r["kernel"], "kernel_ms": r["kernel_ms"],
+                        "hbm_frac_of_8B_per_vertex": nl * nv * 8 / (r["ms"] * 1e-3) / 1e9 / self.peak,
+                        "covered_pixels": int((~torch.isnan(torch.as_tensor(r["out"].data))).sum())}
+        return out
 
-    # ---- e2e: the same call fed from pinned host columns (H2D + D2H inside the timed region)
-    config.device_results = False
-    e2e = None
-    if not args.no_e2e:
-        n_e2e = min(n, args.e2e_n)
-        host = {}
-        for name, t_ in (("x", x), ("y", y), ("value", v)):
-            h = torch.empty(n_e2e, dtype=torch.float32, pin_memory=True)
-            h.copy_(t_[:n_e2e])
-            host[name] = h
-        torch.cuda.synchronize()
-        hframe = ds.HostFrame(host, row_offset=rank * n_e2e, device=device)
-        hframe.sharded = world > 1
-        cvs.points(hframe, "x", "y", agg)     # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            res = cvs.points(hframe, "x", "y", agg)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n_e2e * args.e2e_steps / dt.item() / 1e9, "unit": "Gpoints/s",
-               "h2d_bytes_per_step": int(n_e2e * BYTES_PER_POINT[args.workload]),
-               "d2h_bytes_per_step": int(res.data.nbytes), "points_per_gpu_per_step": n_e2e,
-               "ms_per_step": dt.item() / args.e2e_steps * 1e3}
-        del host, hframe
+    def config5(self):
+        """8192x8192, 4e9 points IN TOTAL: rows sharded over the ranks, key / row canvases all-reduced (268 / 537 MB)."""
+        torch, ds = self.torch, self.ds
+        n_total = int(self.args.c5_n)
+        n = n_total // self.world
+        x, y, v = make_device_columns(n, 100 + self.rank, self.device)
+        frame = ds.DeviceFrame({"x": x, "y": y, "value": v}, row_offset=self.rank * n)
+        frame.sharded = self.world > 1
+        cvs = ds.Canvas(8192, 8192, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+        out = {"workload": f"Canvas(8192x8192).points, {n_total:.0e} float32 points in total over {self.world} GPU(s)",
+               "points_total": n_total}
+        for name, agg in (("max", ds.max("value")), ("first", ds.first("value")), ("where_max", ds.where(ds.max("value")))):
+            r = self.timed(lambda: cvs.points(frame, "x", "y", agg), 4, 3)
+            out[name] = {"ms": r["ms"], "gpoints_per_s": n_total / r["ms"] / 1e6, "roofline": self.roofline(r, n, 12)}
+        return out
 
-    if rank == 0:
-        peak, peak_src = measured_hbm_peak()
-        bpp = BYTES_PER_POINT[args.workload]
-        achieved = n * bpp / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    # ---- the run -----------------------------------------------------------------------------------------------------
+    def run(self):
+        torch, ds, config, args = self.torch, self.ds, self.config, self.args
+        world, rank, device = self.world, self.rank, self.device
+        n = args.n
+        extra = {}
+        if not args.no_parity:
+            extra.update(self.parity())
+        x, y, v = make_device_columns(n, rank, device)
+        frame = ds.DeviceFrame({"x": x, "y": y, "value": v}, row_offset=rank * n)
+        frame.sharded = world > 1
+        cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+        config.device_results = True
+
+        sampler = ClockSampler(self.local_rank)
+        if rank == 0:
+            sampler.start()
+        head = self.timed(lambda: cvs.points(frame, "x", "y", ds.count()), args.steps, args.warmup)
+        clocks = sampler.stop() if rank == 0 else None
+        count_total = int(head["out"].data.view(torch.int32).to(torch.int64).sum().item())
+        mean = self.timed(lambda: cvs.points(frame, "x", "y", ds.mean("value")), args.steps, args.warmup)
+        mean_checksum = float(torch.nan_to_num(mean["out"].data.double()).sum().item())
+
+        strong = None
+        if not args.no_strong:
+            ns = n // world                        # configs[1] as written: 1e9 points in total, sharded
+            sframe = ds.DeviceFrame({"x": x[:ns], "y": y[:ns], "value": v[:ns]}, row_offset=rank * ns)
+            sframe.sharded = world > 1
+            sc = self.timed(lambda: cvs.points(sframe, "x", "y", ds.count()), args.steps, args.warmup)
+            sm = self.timed(lambda: cvs.points(sframe, "x", "y", ds.mean("value")), args.steps, args.warmup)
+            strong = {"points_total": ns * world,
+                      "count": {"value": ns * world / sc["ms"] / 1e6, "ms_per_step": sc["ms"], "kernel": sc["kernel"]},
+                      "mean": {"value": ns * world / sm["ms"] / 1e6, "ms_per_step": sm["ms"], "kernel": sm["kernel"]},
+                      "unit": "Gpoints/s", "note": "rows sharded contiguously; canvases all-reduced (NCCL) inside the timed step"}
+
+        # ---- e2e: the headline call fed from pinned host columns (H2D + D2H inside the timed region)
+        config.device_results = False
+        e2e = None
+        if not args.no_e2e:
+            n_e2e = min(n, args.e2e_n)
+            host = {}
+            for name, t_ in (("x", x), ("y", y)):
+                h = torch.empty(n_e2e, dtype=torch.float32, pin_memory=True)
+                h.copy_(t_[:n_e2e])
+                host[name] = h
+            torch.cuda.synchronize()
+            hframe = ds.HostFrame(host, row_offset=rank * n_e2e, device=device)
+            hframe.sharded = world > 1
+            cvs.points(hframe, "x", "y", ds.count())     # warm-up
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                res = cvs.points(hframe, "x", "y", ds.count())
+            torch.cuda.synchronize()
+            (dt,) = self.max_over_ranks(time.perf_counter() - t0)
+            e2e = {"value": world * n_e2e * args.e2e_steps / dt / 1e9, "unit": "Gpoints/s",
+                   "h2d_bytes_per_step": int(n_e2e * 8), "d2h_bytes_per_step": int(res.data.nbytes),
+                   "points_per_gpu_per_step": n_e2e, "ms_per_step": dt / args.e2e_steps * 1e3,
+                   "h2d_gbs_per_gpu": n_e2e * 8 * args.e2e_steps / dt / 1e9}
+            del host, hframe
+        config.device_results = True
+
+        configs = None
+        if not args.no_configs:
+            configs = {}
+            want = [c.strip() for c in args.configs.split(",") if c.strip()]
+            if "3" in want and world == 1:
+                configs["c3"] = self.config3(x, y)
+            del frame, x, y, v
+            torch.cuda.empty_cache()
+            if "4" in want and world == 1:
+                configs["c4"] = self.config4()
+                torch.cuda.empty_cache()
+            if "5" in want:
+                configs["c5"] = self.config5()
+                torch.cuda.empty_cache()
+            if world > 1:
+                configs["note"] = "configs 3 and 4 are single-GPU workloads: measured at --gpus 1 only"
+        config.device_results = False
+
+        if rank != 0:
+            return
         cb = None
         if not args.no_cpu:
-            cv, csec, cthreads = cpu_baseline(args.cpu_sample, args.workload)
-            cb = {"value": cv, "unit": "Gpoints/s", "cores": cthreads, "kind": "port",
-                  "sample": f"{args.cpu_sample:.0e} of the {n:.0e} points (same distribution), best of 3, {csec:.2f} s per pass"}
+            arm = CpuArm(host_sample(args.cpu_sample), os.cpu_count() or 1)
+            cv, csec = arm.best_of("count")
+            cb = {"value": cv, "unit": "Gpoints/s", "cores": arm.threads, "kind": arm.kind,
+                  "sample": f"{args.cpu_sample:.0e} of the {n:.0e} points (same distribution), best of 3, {csec:.2f} s per pass, "
+                            + ("the reference's numba kernels" if arm.kind == "reference" else "C port of the numba loops")}
+        value = world * n / head["ms"] / 1e6
         line = {
-            "metric": f"Canvas.points Gpoints/s ({args.workload}('value'), 900x525)" if args.workload == "mean"
-                      else "Canvas.points count Gpoints/s (900x525)",
-            "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Canvas(900x525).points, {n:.0e} float32 points per GPU, agg={args.workload}"
-                                   + ("('value')" if args.workload == "mean" else "()")
-                                   + " (BASELINE.json configs[1]), uniform x/y in [0,1), 0.1% NaN values",
+            "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": f"Canvas(900x525).points, {n:.0e} float32 points per GPU, agg=count() on the data of "
+                                   "BASELINE.json configs[1] (uniform x/y in [0,1), value ~ N(0,1) with 0.1% NaN); "
+                                   "agg=mean('value') of the same pass in `mean`",
                        "points_per_gpu": n, "canvas": [W, H],
-                       "l2": "inputs (12 GB per GPU) are far larger than the 126 MB L2; no flush needed",
-                       "combine": "NCCL all-reduce of the f64 sum and u32 count canvases" if world > 1 else "none (1 GPU)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic_gb(args.workload, n),
-                         "kernel": ("k_points_priv_tight<4,mean> (K2: count privatised in shared memory, f64 sum via global RED)"
-                                    if args.workload == "mean" else "k_points_priv_tight<3,count> (K2)"),
-                         "kernel_ms": kernel_ms, "peak_source": peak_src,
-                         "algorithmic_bytes_per_point": bpp, "traffic_unit": "GB per launch (ncu dram read+write)"},
+                       "l2": "inputs (8-12 GB per GPU) are far larger than the 126 MB L2; no flush needed",
+                       "combine": "NCCL all-reduce of the canvases inside the timed step" if world > 1 else "none (1 GPU)"},
+            "roofline": self.roofline(head, n, 8),
+            "hbm_frac_per_gpu": value / world * 8 / self.peak,
+            "mean": {"value": world * n / mean["ms"] / 1e6, "unit": "Gpoints/s", "ms_per_step": mean["ms"], "dtype": "f64",
+                     "roofline": self.roofline(mean, n, 12), "checksum": mean_checksum,
+                     "gpu_launches": mean["launches"]},
+            "strong": strong,
+            "configs": configs,
             "cpu_baseline": cb,
             "e2e": e2e,
-            "gpu_launches": int(launches),
+            "gpu_launches": head["launches"],
             "clocks": clocks,
-            "checksum": checksum,
-            "also": also,
+            "checksum": count_total,
+            "count_total_ok": count_total == world * n,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
 def main():
@@ -342,21 +554,30 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mean", choices=["mean", "count"])
-    ap.add_argument("--n", type=float, default=1e9, help="points per GPU")
+    ap.add_argument("--n", type=float, default=1e9, help="points per GPU (weak scaling)")
     ap.add_argument("--cpu-sample", type=float, default=1e8, help="rows of the CPU baseline sample")
     ap.add_argument("--e2e-n", type=float, default=1e9)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--parity-n", type=float, default=1e7)
+    ap.add_argument("--c5-n", type=float, default=4e9, help="config 5: points in total (sharded over the GPUs)")
+    ap.add_argument("--configs", default="3,4,5")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-also-count", dest="also_count", action="store_false")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
-    args.n, args.cpu_sample, args.e2e_n = int(args.n), int(args.cpu_sample), int(args.e2e_n)
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    for k in ("n", "cpu_sample", "e2e_n", "parity_n", "c5_n"):
+        setattr(args, k, int(getattr(args, k)))
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    args.warmup = max(args.warmup, 3)
+    b = Bench(args)
+    try:
+        b.run()
+    finally:
+        b.close()
 
 
 if __name__ == "__main__":

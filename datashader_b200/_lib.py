@@ -68,6 +68,7 @@ _SIGNATURES = {
     "dsb_abi_version": ([], C.c_int),
     "dsb_last_error": ([], C.c_char_p),
     "dsb_launch_count": ([], C.c_int64),
+    "dsb_last_kernel": ([], C.c_char_p),
     "dsb_configure": ([C.c_char_p, _i64], C.c_int),
     "dsb_init_canvas": ([_i32, _p, _i64, _p], C.c_int),
     "dsb_points": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, C.POINTER(Plan), _p], C.c_int),

@@ -31,3 +31,14 @@ int dsb_num_sms() {
 static unsigned long long g_launches = 0;
 void dsb_count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 extern "C" int64_t dsb_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+// name of the aggregation kernel the most recent entry point chose (bench.py's roofline.kernel: read back from the
+// library, so a silent change of route cannot be mislabelled)
+static thread_local char g_kernel[160] = "";
+void dsb_note_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* dsb_last_kernel(void) { return g_kernel; }

@@ -210,6 +210,7 @@ extern "C" int dsb_areas_plan(const dsb_view* view, const void* xs, const void* 
   long long want = (total + threads - 1) / threads, cap = (long long)dsb_num_sms() * 16;
   int grid = (int)(want < cap ? want : cap);
   cudaStream_t s = (cudaStream_t)stream;
+  dsb_note_kernel("k_areas<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
   if (xy_dtype == DSB_F32) k_areas<float><<<grid, threads, 0, s>>>(a);
   else k_areas<double><<<grid, threads, 0, s>>>(a);
   DSB_CUDA_CHECK_LAUNCH("dsb_areas_plan");

@@ -10,6 +10,7 @@
 extern "C" void dsb_set_error(const char* fmt, ...);
 int dsb_num_sms();
 void dsb_count_launch();
+void dsb_note_kernel(const char* fmt, ...);
 
 #define DSB_CUDA_CHECK_LAUNCH(what)                                              \
   do {                                                                           \

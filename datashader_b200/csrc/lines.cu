@@ -656,6 +656,7 @@ static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char*
   long long cap = (long long)dsb_num_sms() * 16;
   int grid = (int)(want < cap ? want : cap);
   cudaStream_t s = (cudaStream_t)stream;
+  dsb_note_kernel("k_lines_axis1<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
   if (xy_dtype == DSB_F32) k_lines_axis1<float><<<grid, threads, 0, s>>>(a);
   else if (xy_dtype == DSB_F64) k_lines_axis1<double><<<grid, threads, 0, s>>>(a);
   else { dsb_set_error("%s: xy_dtype must be f32 or f64", what); return DSB_ERR_ARG; }
@@ -780,6 +781,7 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(b.touched, 0, (size_t)(nctas * nwords * 4), s);           // bitmaps
   cudaMemsetAsync(b.redo_n, 0, 16, s);                                        // queue header
+  dsb_note_kernel("k_lines_aa2<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
   k_fill_i64<<<dsb_num_sms() * 8, 256, 0, s>>>(b.temp, LLONG_MIN, nctas * ncell);
   const size_t smem = (size_t)AA2_HASH_CAP * 12;
   // short lines are batched G to a group so that every thread of the CTA has a segment (at most 32 lines per group)

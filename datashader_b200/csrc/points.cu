@@ -495,6 +495,8 @@ static bool try_launch_mono(const PointsArgs& a, int32_t xy_dtype, bool banded, 
   if ((long long)a.v.width * a.v.height >= (1LL << 31)) return false;
   const FastMap fm = make_fast_map(&a.v);
   if (!fm.enabled) return false;
+  static const char* const names[] = {"max32", "min32", "minrow", "maxrow", "argmax32", "argmin32", "count"};
+  dsb_note_kernel("k_points_mono<%s,%s>", names[op], banded ? "banded" : "filtered");
   switch (op) {
     case MONO_MAX32: launch_mono<MONO_MAX32>(a, fm, vcol, banded, s); break;
     case MONO_MIN32: launch_mono<MONO_MIN32>(a, fm, vcol, banded, s); break;
@@ -578,6 +580,8 @@ static bool try_launch_mono_f64(const PointsArgs& a, int32_t xy_dtype, cudaStrea
   } else return false;
   if ((((uintptr_t)a.x | (uintptr_t)a.y | (uintptr_t)vcol) & 15) != 0) return false;
   const int grid = dsb_num_sms() * 3;
+  static const char* const names64[] = {"max64", "min64", "minrow", "maxrow"};
+  dsb_note_kernel("k_points_mono_f64<%s>", names64[op]);
   switch (op) {
     case M64_MAX: k_points_mono_f64<M64_MAX><<<grid, 256, 0, s>>>(a, vcol); break;
     case M64_MIN: k_points_mono_f64<M64_MIN><<<grid, 256, 0, s>>>(a, vcol); break;
@@ -816,6 +820,8 @@ extern "C" int dsb_points(const dsb_view* view, const void* x, const void* y, in
     } else {
       // the load-before-RED filter of the monotone accumulators pays only while the canvases are L2-resident
       const bool filter = nbands == 1 && bytes_per_pixel * npixels <= (96LL << 20);
+      dsb_note_kernel("k_points_generic<%s,%s> nops=%d bands=%lld", xy_dtype == DSB_F32 ? "f32" : "f64", filter ? "filtered" : "plain",
+                      plan->nops, nbands);
       if (filter && g_mono && try_launch_mono(a, xy_dtype, false, s)) { DSB_CUDA_CHECK_LAUNCH("dsb_points(mono)"); continue; }
       if (filter && g_mono && try_launch_mono_f64(a, xy_dtype, s)) { DSB_CUDA_CHECK_LAUNCH("dsb_points(mono f64)"); continue; }
       if (xy_dtype == DSB_F32) { if (filter) k_points_generic<float, true><<<grid, threads, 0, s>>>(a); else k_points_generic<float, false><<<grid, threads, 0, s>>>(a); }
@@ -1015,6 +1021,9 @@ extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* 
   const FastMap fm = make_fast_map(view);
   const bool vvec = mode != 1 || ((uintptr_t)a.vcol & 15) == 0;
   const bool tight = g_priv_tight && vec && vvec && mode <= 1 && fm.enabled && ncell < (1LL << 31);
+  if (f64) dsb_note_kernel("k_points_priv_f64<%d,%s>", slot, mode == 1 ? "mean" : "count");
+  else if (tight) dsb_note_kernel("k_points_priv_tight<%d,%s>", slot, mode == 1 ? "mean" : "count");
+  else dsb_note_kernel("k_points_priv<%d,mode%d,%s>", slot, mode, vec ? "vec" : "scalar");
   if (f64) {
     if (ncell >= (1LL << 31)) { dsb_set_error("dsb_points_priv: canvas too large"); return DSB_ERR_UNSUPPORTED; }
     switch (slot) {
@@ -1215,6 +1224,7 @@ extern "C" int dsb_points_count16(const dsb_view* view, const void* x, const voi
   const bool tight_ok = g_priv_tight && xy_dtype == DSB_F32 && fm.enabled && ncell < (1LL << 31) && (plan->ncat == 0 || cat1) &&
                         cb.chk_dtype == DSB_NONE && (cb.val_dtype == DSB_NONE || (cb.val_dtype == DSB_F32 && (((uintptr_t)cb.val) & 15) == 0)) &&
                         ((((uintptr_t)x | (uintptr_t)y)) & 15) == 0 && g_count16_band_bytes == 0 && !l2_persist_enabled();
+  dsb_note_kernel(tight_ok ? "k_points_count16_tight<%s>" : "k_points_count16<%s>", tight_ok ? (plan->ncat > 0 ? "cat" : "nocat") : (xy_dtype == DSB_F32 ? "f32" : "f64"));
   if (tight_ok) {
     const float* vcol = cb.val_dtype == DSB_F32 ? (const float*)cb.val : nullptr;
     const int g3 = dsb_num_sms() * 3;

@@ -95,6 +95,9 @@ int dsb_abi_version(void);
 const char* dsb_last_error(void);
 /* number of kernel-launching API calls made by this process so far (diagnostics / bench.py gpu_launches) */
 int64_t dsb_launch_count(void);
+/* name (template arguments included) of the aggregation kernel the most recent dsb_points* / dsb_lines* / dsb_areas* call
+ * of this thread launched - diagnostics: bench.py labels its roofline with it */
+const char* dsb_last_kernel(void);
 
 /* Runtime knobs: "l2_band_bytes" - accumulator bytes one dsb_points launch may touch before the rows are re-read
  * once per band of canvas rows (default 96 MiB, 0 disables); "band_min_rows" - smallest n that is banded;
