@@ -61,8 +61,8 @@ def test_points_negzero_golden(ds, source):
             src = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items() if k not in ("cat__ncat",)},
                                  categories={"cat": [f"c{i}" for i in range(NCAT)]})
         else:                                  # host columns streamed in chunks: the gather runs against the host column
-            src = ds.HostFrame({k: torch.from_numpy(v) for k, v in cols.items() if k not in ("cat__ncat", "cat")},
-                               chunk_rows=1024)
+            src = ds.HostFrame({k: torch.from_numpy(v) for k, v in cols.items() if k not in ("cat__ncat", "cat")})
+            src.CHUNK_ROWS = 1024
         for name, spec in NEGZERO.items():
             if source == "host_chunks" and spec[0] == "by":
                 continue
