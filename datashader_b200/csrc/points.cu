@@ -360,8 +360,10 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
 //  * word index by a multiply-high with a magic constant that is exact for every cell < 2^26.
 struct FastMap2 { float sx, sy, txl, txh, tyl, tyh; int enabled; };
 
-template <int SLOT, bool MEAN, bool ALLP>
-__global__ void __launch_bounds__(1024, 1) k_points_priv_v2(const __grid_constant__ PrivArgs a, const __grid_constant__ FastMap2 fm) {
+// NT = 1024: two vectors per thread per step, loaded at the top of the step.  NT = 768 (up to 85 registers per thread):
+// the loads of step k + 1 are issued before step k is processed, so twice the bytes stay in flight.
+template <int SLOT, bool MEAN, bool ALLP, int NT>
+__global__ void __launch_bounds__(NT, 1) k_points_priv_v2(const __grid_constant__ PrivArgs a, const __grid_constant__ FastMap2 fm) {
   extern __shared__ uint32_t sh[];
   constexpr uint32_t PER = 32 / SLOT;
   constexpr uint32_t CNT_MASK = (1u << (SLOT - 1)) - 1u, GUARD = 1u << (SLOT - 1), FIELD = (1u << SLOT) - 1u;
@@ -422,12 +424,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_v2(const __grid_constan
   const long long n4 = p.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
-  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i4 + stride < n4; i4 += 2 * stride) {
-    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
-    const float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
-    const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride);
-    const float4 vb = MEAN ? __ldcs(v4 + i4 + stride) : nan4;
+  auto batch = [&](const float4& xa, const float4& ya, const float4& va, const float4& xb, const float4& yb, const float4& vb) {
     uint32_t slow = one(xa.x, ya.x, va.x);
     slow |= one(xa.y, ya.y, va.y) << 1;
     slow |= one(xa.z, ya.z, va.z) << 2;
@@ -445,6 +442,32 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_v2(const __grid_constan
       if (slow & 32) exact(xb.y, yb.y, vb.y);
       if (slow & 64) exact(xb.z, yb.z, vb.z);
       if (slow & 128) exact(xb.w, yb.w, vb.w);
+    }
+  };
+  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (NT == 1024) {
+    for (; i4 + stride < n4; i4 += 2 * stride) {
+      const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
+      const float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
+      const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride);
+      const float4 vb = MEAN ? __ldcs(v4 + i4 + stride) : nan4;
+      batch(xa, ya, va, xb, yb, vb);
+    }
+  } else if (i4 + stride < n4) {
+    float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = MEAN ? __ldcs(v4 + i4) : nan4;
+    float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride), vb = MEAN ? __ldcs(v4 + i4 + stride) : nan4;
+    for (;;) {
+      const long long j4 = i4 + 2 * stride;
+      const bool more = j4 + stride < n4;
+      float4 nxa = nan4, nya = nan4, nva = nan4, nxb = nan4, nyb = nan4, nvb = nan4;
+      if (more) {
+        nxa = __ldcs(x4 + j4); nya = __ldcs(y4 + j4); nxb = __ldcs(x4 + j4 + stride); nyb = __ldcs(y4 + j4 + stride);
+        if (MEAN) { nva = __ldcs(v4 + j4); nvb = __ldcs(v4 + j4 + stride); }
+      }
+      batch(xa, ya, va, xb, yb, vb);
+      i4 = j4;
+      if (!more) break;
+      xa = nxa; ya = nya; va = nva; xb = nxb; yb = nyb; vb = nvb;
     }
   }
   if (i4 < n4) {
@@ -964,13 +987,11 @@ static void launch_priv_one(const PrivArgs& a, const FastMap& fm, size_t smem, c
 
 template <int SLOT, bool MEAN>
 static void launch_priv_v2(const PrivArgs& a, const FastMap2& fm, bool allp, size_t smem, cudaStream_t s) {
-  if (allp) {
-    cudaFuncSetAttribute(k_points_priv_v2<SLOT, MEAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    k_points_priv_v2<SLOT, MEAN, true><<<dsb_num_sms(), g_priv_threads, smem, s>>>(a, fm);
-  } else {
-    cudaFuncSetAttribute(k_points_priv_v2<SLOT, MEAN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    k_points_priv_v2<SLOT, MEAN, false><<<dsb_num_sms(), g_priv_threads, smem, s>>>(a, fm);
-  }
+#define DSB_V2_LAUNCH(A, NT) do { cudaFuncSetAttribute(k_points_priv_v2<SLOT, MEAN, A, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    k_points_priv_v2<SLOT, MEAN, A, NT><<<dsb_num_sms(), NT == 1024 ? g_priv_threads : NT, smem, s>>>(a, fm); } while (0)
+  if (g_priv_threads == 768) { if (allp) DSB_V2_LAUNCH(true, 768); else DSB_V2_LAUNCH(false, 768); }
+  else { if (allp) DSB_V2_LAUNCH(true, 1024); else DSB_V2_LAUNCH(false, 1024); }
+#undef DSB_V2_LAUNCH
 }
 
 template <int SLOT, bool MEAN>

@@ -113,19 +113,28 @@ __device__ __forceinline__ void issue_tile(const BinJob& j, const BinSmem& s, in
 }
 
 // one tile whose x / y are (about to be) in stage `st`; next_t0 >= 0: prefetch that tile into the same stage once the stage is free
+// the value column of one tile, straight into registers (issued one tile ahead of its use)
+template <int PPT>
+__device__ __forceinline__ void load_values(const BinJob& j, long long t0, float4 (&va)[PPT / 4]) {
+  constexpr int TILE = BT * PPT;
+  const long long left = j.n - t0;
+  const uint32_t pts = t0 < 0 ? 0u : (uint32_t)(left < TILE ? left : TILE);
+#pragma unroll
+  for (int u = 0; u < PPT / 4; u++) {
+    const uint32_t p = (u * BT + threadIdx.x) * 4;
+    va[u] = p < pts ? __ldcs((const float4*)(j.v + t0) + u * BT + threadIdx.x) : make_float4(NAN, NAN, NAN, NAN);
+  }
+}
+
+// va: this tile's values on entry, the values of the tile after it (vnext_t0, -1 = none) on exit
 template <int PPT>
 __device__ __forceinline__ void bin_tile2(const BinJob& j, const BinSmem& s, int st, uint32_t parity, long long t0, long long next_t0,
+                                          long long vnext_t0, float4 (&va)[PPT / 4],
                                           uint32_t region0 /* = cta * cap_sub */, uint32_t region_stride /* = nctas * cap_sub */) {
   constexpr int TILE = BT * PPT;
   const int tid = threadIdx.x;
   const long long left = j.n - t0;
   const uint32_t pts = (uint32_t)(left < TILE ? left : TILE);
-  float4 va[PPT / 4];
-#pragma unroll
-  for (int u = 0; u < PPT / 4; u++) {
-    const uint32_t p = (u * BT + tid) * 4;
-    va[u] = p < pts ? __ldcs((const float4*)(j.v + t0) + u * BT + tid) : make_float4(NAN, NAN, NAN, NAN);
-  }
   mbar_wait(s.bar0 + 8 * st, parity);
   const float4* sx4 = (const float4*)(s.in + st * TILE);
   const float4* sy4 = (const float4*)(s.in + (2 + st) * TILE);
@@ -148,6 +157,7 @@ __device__ __forceinline__ void bin_tile2(const BinJob& j, const BinSmem& s, int
   }
   __syncthreads();                                            // B1: hist complete, the stage has been read
   if (tid == 0 && next_t0 >= 0) issue_tile(j, s, st, next_t0, TILE);
+  load_values<PPT>(j, vnext_t0, va);                          // lands while this tile is sorted and written out
   // block-wide exclusive scan of hist (2 entries per thread)
   const uint32_t nb = j.r.nb;
   const uint32_t e0 = 2 * tid, e1 = 2 * tid + 1;
@@ -186,9 +196,16 @@ __device__ __forceinline__ void bin_tile2(const BinJob& j, const BinSmem& s, int
   }
   __syncthreads();                                            // B5
   const uint32_t total = s.wsum[31];
-  for (uint32_t q = tid; q < total; q += BT) {
-    const unsigned long long rr = s.rec[q];
-    j.out[(size_t)s.gdel[((uint32_t)rr) >> 16] + q] = rr;
+#pragma unroll
+  for (int u = 0; u < PPT; u += 4) {                          // four records in flight per thread
+    unsigned long long rr[4];
+    uint32_t gd[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const uint32_t q = (u + k) * BT + tid; rr[k] = q < total ? s.rec[q] : 0ull; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) gd[k] = s.gdel[((uint32_t)rr[k]) >> 16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const uint32_t q = (u + k) * BT + tid; if (q < total) j.out[(size_t)gd[k] + q] = rr[k]; }
   }
 }
 
@@ -212,9 +229,11 @@ __global__ void __launch_bounds__(BT, 1) k_bin2(const BinJob j, uint32_t* __rest
     if (t0 + stride < j.n) issue_tile(j, s, 1, t0 + stride, TILE);
   }
   const uint32_t region0 = blockIdx.x * j.cap_sub, region_stride = gridDim.x * j.cap_sub;
+  float4 va[PPT / 4];
+  load_values<PPT>(j, t0 < j.n ? t0 : -1, va);
   for (uint32_t k = 0; t0 < j.n; k++, t0 += stride) {
-    const long long nx = t0 + 2 * stride;
-    bin_tile2<PPT>(j, s, k & 1, (k >> 1) & 1, t0, nx < j.n ? nx : -1, region0, region_stride);
+    const long long nx = t0 + 2 * stride, nv = t0 + stride;
+    bin_tile2<PPT>(j, s, k & 1, (k >> 1) & 1, t0, nx < j.n ? nx : -1, nv < j.n ? nv : -1, va, region0, region_stride);
   }
   __syncthreads();
   for (uint32_t b = tid; b < j.r.nb; b += BT) cnt[(size_t)b * gridDim.x + blockIdx.x] = s.scur[b];
@@ -282,13 +301,16 @@ __global__ void __launch_bounds__(BT, 1) k_routed_mean2(BinJob j, int tiles_per_
     if (my_tiles > 1) issue_tile(j, s, 1, tile_start(1), TILE);
   }
   const uint32_t region0 = blockIdx.x * j.cap_sub, region_stride = G * j.cap_sub;
+  float4 va[PPT / 4];
+  load_values<PPT>(j, (my_tiles > 0 && (mode & 1)) ? tile_start(0) : -1, va);
   long long k = 0;
   for (int ph = 0; ph <= nchunks; ph++) {
     if (ph < nchunks && (mode & 1)) {
       BinJob jj = j;
       jj.out = (ph & 1) ? buf1 : buf0;
       for (int t = 0; t < tiles_per_cta && k < my_tiles; t++, k++)
-        bin_tile2<PPT>(jj, s, (int)(k & 1), (uint32_t)((k >> 1) & 1), tile_start(k), k + 2 < my_tiles ? tile_start(k + 2) : -1, region0, region_stride);
+        bin_tile2<PPT>(jj, s, (int)(k & 1), (uint32_t)((k >> 1) & 1), tile_start(k), k + 2 < my_tiles ? tile_start(k + 2) : -1,
+                       k + 1 < my_tiles ? tile_start(k + 1) : -1, va, region0, region_stride);
       __syncthreads();
       uint32_t* cnt = (ph & 1) ? cnt1 : cnt0;
       for (uint32_t b = tid; b < j.r.nb; b += BT) { cnt[(size_t)b * G + blockIdx.x] = s.scur[b]; s.scur[b] = 0; }
