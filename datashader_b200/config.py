@@ -26,3 +26,10 @@ split_summary = True
 # Bresenham lines with any / count / sum / max / min: the line kernel's own appends (the line's value held in a register)
 # instead of the accumulator-plan interpreter, which re-reads the value column for every pixel.
 lines_simple_path = True
+
+# Single-accumulator plans (max / min / first / last of a float32 column, count) on canvases whose accumulator outgrows the
+# L2 budget: bin the points into shared-memory-sized buckets and accumulate bucket by bucket (dsb_points_routed) instead of
+# L2-banded passes with a global RED per hit.  routed_max_scratch_bytes bounds the record buffer (~8.8 bytes per point).
+routed = True
+routed_min_rows = 1 << 24
+routed_max_scratch_bytes = 64 << 30

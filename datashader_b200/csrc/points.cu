@@ -6,6 +6,7 @@
 // per-pixel mutex is needed (the reference spin-locks one for where/first, _cuda_utils.py:177-199).
 #include "common.cuh"
 #include "accum.cuh"
+#include "fastmap.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -103,15 +104,6 @@ __device__ __forceinline__ void apply_base_f32(const dsb_base& b, long long cell
     default: apply_base<false>(b, cell, i, row, notes); return;
   }
 }
-
-// float32 fast path of the pixel mapping.  xf = fmaf(x, sx32, tx32) differs from the reference's exact value by at
-// most `ex` (host-side bound: 2^-23 * (W + 1 + max|x| * |sx| + |tx|)); whenever xf is further than that from an
-// integer its floor IS the reference's truncated f64 result, otherwise the exact f64 mapping is evaluated.  The
-// bounds test is exact: xlo/xhi are the float32 values that bracket the f64 bounds from inside.
-struct FastMap {
-  float sx, tx, sy, ty, xlo, xhi, ylo, yhi, ex, ey, omex, omey;   // omex = 1 - ex
-  int enabled;
-};
 
 __device__ __forceinline__ long long map_to_cell_fast(const FastMap& f, const dsb_view& v, float x, float y) {
   if (!(x >= f.xlo && x <= f.xhi && y >= f.ylo && y <= f.yhi)) return -1;
@@ -225,9 +217,6 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv(const PrivArgs a, const
 // no category axis and the whole canvas fits the packed shared-memory fields.  Same algorithm as k_points_priv with the
 // per-point instruction stream cut down: 32-bit cell arithmetic, shared-window address formed once, the exact f64
 // mapping kept out of line (taken by ~0.1 % of the points), no plan interpretation.
-__device__ __noinline__ int map_exact_linear(const dsb_view& v, float xr, float yr) {
-  return (int)map_to_cell<float>(v, xr, yr);      // the reference mapping, bounds test included; -1 = not on the canvas
-}
 
 // One hit.  `ok` (0 / 1) gates it without a branch: the shared-memory add is unconditional, of ok << shift at a clamped
 // address.  The every-2^(SLOT-1)-th-hit spill is the only branch; with 32 lanes some lane of nearly every warp takes
@@ -347,148 +336,6 @@ __global__ void __launch_bounds__(1024, 1) k_points_priv_tight(const __grid_cons
   if (bad) atomicOr(a.flag, 1u);
 }
 
-// ---- K2 "v2": the tight kernel with the per-point instruction stream cut again (51 -> ~37 SASS instructions) ---------------
-// ncu on k_points_priv_tight (profiles/r01n_k2_tight_final.md): 51 instructions per point at 70 % issue utilisation,
-// math_pipe_throttle 1.5 (the F2I / I2F pairs run on the quarter-rate pipe), a BSSY / BRA / BSYNC region per point around
-// a spill that some lane of nearly every warp takes.  Here:
-//  * floor and the "sure" test come from the FP32 pipe alone: xl = fma(x, sx, tx - 2ex), xh = fma(x, sx, tx + 2ex) bracket
-//    the reference's value (make_fast_map2), RD(xl + 2^23) and RD(xh + 2^23) hold their floors in the mantissa, equal
-//    results prove the pixel and bits - bits(2^23) IS the pixel index (negative / huge / NaN images land outside [0, W));
-//  * (tried: predicated atom / red in inline PTX for a branch-free spill - ptxas turns every predicated atomic back into a
-//    BSSY / BRA / BSYNC region and keeps the undefined `old` in local memory, so the hit keeps round 1's form: an
-//    unconditional add of ok << shift and one branch around the two spill instructions);
-//  * word index by a multiply-high with a magic constant that is exact for every cell < 2^26.
-struct FastMap2 { float sx, sy, txl, txh, tyl, tyh; int enabled; };
-
-// NT = 1024: two vectors per thread per step, loaded at the top of the step.  NT = 768 (up to 85 registers per thread):
-// the loads of step k + 1 are issued before step k is processed, so twice the bytes stay in flight.
-template <int SLOT, bool MEAN, bool ALLP, int NT>
-__global__ void __launch_bounds__(NT, 1) k_points_priv_v2(const __grid_constant__ PrivArgs a, const __grid_constant__ FastMap2 fm) {
-  extern __shared__ uint32_t sh[];
-  constexpr uint32_t PER = 32 / SLOT;
-  constexpr uint32_t CNT_MASK = (1u << (SLOT - 1)) - 1u, GUARD = 1u << (SLOT - 1), FIELD = (1u << SLOT) - 1u;
-  constexpr uint32_t MAGIC = (uint32_t)((1ull << 32) / PER + 1);      // __umulhi(c, MAGIC) == c / PER for c < 2^26
-  const PointsArgs& p = a.p;
-  const int ncell = (int)a.npriv;
-  const int nwords = (ncell + (int)PER - 1) / (int)PER;
-  for (int j = threadIdx.x; j < nwords; j += blockDim.x) sh[j] = 0;
-  __syncthreads();
-  uint32_t sh_addr;
-  asm volatile("mov.u32 %0, %1;" : "=r"(sh_addr) : "r"((uint32_t)__cvta_generic_to_shared(sh)));
-  const float* __restrict__ x = (const float*)p.x;
-  const float* __restrict__ y = (const float*)p.y;
-  double* __restrict__ sum_canvas = MEAN ? (double*)p.plan.ops[1 - a.priv_op].agg : nullptr;
-  unsigned int* const scratch = a.scratch;
-  const uint32_t W = (uint32_t)p.v.width, H = (uint32_t)p.v.height;
-  uint32_t bad = 0;
-
-  auto hit = [&](uint32_t cell, bool ok, float vv) {
-    if (MEAN) {
-      ok = ok && vv == vv;
-      if (ok) atomicAdd(sum_canvas + cell, (double)vv);
-    }
-    if (!ALLP && cell >= (uint32_t)ncell) {          // the few cells that did not fit shared memory: plain REDs
-      if (ok) atomicAdd(scratch + cell, 1u);
-      return;
-    }
-    if (ALLP) cell = min(cell, (uint32_t)ncell - 1u);      // only matters when !ok (the add below is then of 0)
-    const uint32_t w = __umulhi(cell, MAGIC), sft = (cell - w * PER) * SLOT;
-    const uint32_t addr = sh_addr + 4u * w;
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"((uint32_t)ok << sft) : "memory");
-    const uint32_t f = (old >> sft) & FIELD;
-    if (ok && f == CNT_MASK) {                       // this hit wrapped the counter into its guard bit: spill
-      asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(0u - (GUARD << sft)) : "memory");
-      asm volatile("red.global.add.u32 [%0], %1;" :: "l"(scratch + cell), "r"(GUARD) : "memory");
-    }
-    bad |= (uint32_t)(ok && f == FIELD);             // the add carried into the neighbouring field: redo exactly
-  };
-
-  constexpr float M23 = 8388608.0f;
-  auto one = [&](float xv, float yv, float vv) -> uint32_t {
-    const float axl = __fadd_rd(fmaf(xv, fm.sx, fm.txl), M23), axh = __fadd_rd(fmaf(xv, fm.sx, fm.txh), M23);
-    const float ayl = __fadd_rd(fmaf(yv, fm.sy, fm.tyl), M23), ayh = __fadd_rd(fmaf(yv, fm.sy, fm.tyh), M23);
-    const bool sure = axl == axh && ayl == ayh;                 // NaN compares false: deferred to the exact mapping
-    const uint32_t xi = __float_as_uint(axl) - 0x4B000000u, yi = __float_as_uint(ayl) - 0x4B000000u;
-    hit(yi * W + xi, sure && xi < W && yi < H, vv);
-    return (uint32_t)!sure;
-  };
-  auto exact = [&](float xv, float yv, float vv) {
-    const int cell = map_exact_linear(p.v, xv, yv);
-    hit((uint32_t)cell, cell >= 0, vv);
-  };
-
-  const float4* __restrict__ x4 = (const float4*)p.x;
-  const float4* __restrict__ y4 = (const float4*)p.y;
-  const float4* __restrict__ v4 = (const float4*)a.vcol;
-  const long long n4 = p.n >> 2;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
-  auto batch = [&](const float4& xa, const float4& ya, const float4& va, const float4& xb, const float4& yb, const float4& vb) {
-    uint32_t slow = one(xa.x, ya.x, va.x);
-    slow |= one(xa.y, ya.y, va.y) << 1;
-    slow |= one(xa.z, ya.z, va.z) << 2;
-    slow |= one(xa.w, ya.w, va.w) << 3;
-    slow |= one(xb.x, yb.x, vb.x) << 4;
-    slow |= one(xb.y, yb.y, vb.y) << 5;
-    slow |= one(xb.z, yb.z, vb.z) << 6;
-    slow |= one(xb.w, yb.w, vb.w) << 7;
-    if (slow) {                                    // ~0.15 % of the points
-      if (slow & 1) exact(xa.x, ya.x, va.x);
-      if (slow & 2) exact(xa.y, ya.y, va.y);
-      if (slow & 4) exact(xa.z, ya.z, va.z);
-      if (slow & 8) exact(xa.w, ya.w, va.w);
-      if (slow & 16) exact(xb.x, yb.x, vb.x);
-      if (slow & 32) exact(xb.y, yb.y, vb.y);
-      if (slow & 64) exact(xb.z, yb.z, vb.z);
-      if (slow & 128) exact(xb.w, yb.w, vb.w);
-    }
-  };
-  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (NT == 1024) {
-    for (; i4 + stride < n4; i4 += 2 * stride) {
-      const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
-      const float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
-      const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride);
-      const float4 vb = MEAN ? __ldcs(v4 + i4 + stride) : nan4;
-      batch(xa, ya, va, xb, yb, vb);
-    }
-  } else if (i4 + stride < n4) {
-    float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = MEAN ? __ldcs(v4 + i4) : nan4;
-    float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride), vb = MEAN ? __ldcs(v4 + i4 + stride) : nan4;
-    for (;;) {
-      const long long j4 = i4 + 2 * stride;
-      const bool more = j4 + stride < n4;
-      float4 nxa = nan4, nya = nan4, nva = nan4, nxb = nan4, nyb = nan4, nvb = nan4;
-      if (more) {
-        nxa = __ldcs(x4 + j4); nya = __ldcs(y4 + j4); nxb = __ldcs(x4 + j4 + stride); nyb = __ldcs(y4 + j4 + stride);
-        if (MEAN) { nva = __ldcs(v4 + j4); nvb = __ldcs(v4 + j4 + stride); }
-      }
-      batch(xa, ya, va, xb, yb, vb);
-      i4 = j4;
-      if (!more) break;
-      xa = nxa; ya = nya; va = nva; xb = nxb; yb = nyb; vb = nvb;
-    }
-  }
-  if (i4 < n4) {
-    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
-    const float4 va = MEAN ? __ldcs(v4 + i4) : nan4;
-    exact(xa.x, ya.x, va.x); exact(xa.y, ya.y, va.y); exact(xa.z, ya.z, va.z); exact(xa.w, ya.w, va.w);
-  }
-  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {           // tail rows
-    const long long i = (n4 << 2) + threadIdx.x;
-    exact(x[i], y[i], MEAN ? a.vcol[i] : 0.0f);
-  }
-
-  __syncthreads();
-  for (int j = threadIdx.x; j < ncell; j += blockDim.x) {
-    const uint32_t w = (uint32_t)j / PER, sft = ((uint32_t)j - w * PER) * SLOT;
-    const uint32_t c = (sh[w] >> sft) & FIELD;
-    if (c) atomicAdd(scratch + j, c);
-  }
-  if (bad) atomicOr(a.flag, 1u);
-}
-
 // ---- K1 "mono": single monotone accumulator (max / min of a float32 column, first / last, where(max / min)) ----------
 // The plans of max(col), min(col), first(col), last(col) and where(max / min (col), ...) hold ONE accumulator.  With
 // float32 coordinates on linear axes and an L2-resident canvas this kernel replaces the plan interpreter of
@@ -595,7 +442,6 @@ __global__ void __launch_bounds__(256, 3) k_points_mono(const __grid_constant__ 
   if ((OP == MONO_MAX32 || OP == MONO_MIN32) && negzero && a.plan.notes) *a.plan.notes = DSB_NOTE_NEGZERO;
 }
 
-static FastMap make_fast_map(const dsb_view* v);
 
 // Returns true when the launch was taken by k_points_mono.
 template <int OP>
@@ -796,7 +642,6 @@ static int g_mono = 1;                       // use k_points_mono for single mon
 static int g_mono_banded = 1;                //   ... also for the L2-banded passes of big canvases (without the filter)
 static int g_priv_threads = 1024;            // threads per CTA of the tight K2 kernels (one CTA per SM)
 static int g_priv_tight = 1;                 // use k_points_priv_tight for the count() / mean(f32) shapes
-static int g_priv_v2 = 1;                    //   ... in its v2 form (directed-rounding floor, predicated spill)
 static long long l2_band_budget_bytes() {
   if (g_band_budget < 0) {
     const char* e = getenv("DSB_L2_BAND_MB");
@@ -812,7 +657,6 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "l2_band_bytes")) { g_band_budget = value; return DSB_OK; }
   if (!strcmp(key, "band_min_rows")) { g_band_min_rows = value; return DSB_OK; }
   if (!strcmp(key, "priv_tight")) { g_priv_tight = value != 0; return DSB_OK; }
-  if (!strcmp(key, "priv_v2")) { g_priv_v2 = value != 0; return DSB_OK; }
   if (!strcmp(key, "priv_threads")) { if (value < 128 || value > 1024 || (value & 31)) { dsb_set_error("dsb_configure: priv_threads must be a multiple of 32 in [128, 1024]"); return DSB_ERR_ARG; } g_priv_threads = (int)value; return DSB_OK; }
   if (!strcmp(key, "mono")) { g_mono = value != 0; return DSB_OK; }
   if (!strcmp(key, "split_bytes")) { g_split_bytes = value; return DSB_OK; }
@@ -986,15 +830,6 @@ static void launch_priv_one(const PrivArgs& a, const FastMap& fm, size_t smem, c
 }
 
 template <int SLOT, bool MEAN>
-static void launch_priv_v2(const PrivArgs& a, const FastMap2& fm, bool allp, size_t smem, cudaStream_t s) {
-#define DSB_V2_LAUNCH(A, NT) do { cudaFuncSetAttribute(k_points_priv_v2<SLOT, MEAN, A, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-    k_points_priv_v2<SLOT, MEAN, A, NT><<<dsb_num_sms(), NT == 1024 ? g_priv_threads : NT, smem, s>>>(a, fm); } while (0)
-  if (g_priv_threads == 768) { if (allp) DSB_V2_LAUNCH(true, 768); else DSB_V2_LAUNCH(false, 768); }
-  else { if (allp) DSB_V2_LAUNCH(true, 1024); else DSB_V2_LAUNCH(false, 1024); }
-#undef DSB_V2_LAUNCH
-}
-
-template <int SLOT, bool MEAN>
 static void launch_priv_tight(const PrivArgs& a, const FastMap& fm, bool allp, size_t smem, cudaStream_t s) {
   if (allp) {
     cudaFuncSetAttribute(k_points_priv_tight<SLOT, MEAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1070,57 +905,15 @@ static void launch_priv_f64(const PrivArgs& a, bool mean, const double* vcol, si
 #undef DSB_F64_LAUNCH
 }
 
-static FastMap2 make_fast_map2(const dsb_view* v, const FastMap& f);
-
 template <int SLOT>
 static void launch_priv(const PrivArgs& a, const FastMap& fm, int mode, bool vec, bool tight, size_t smem, cudaStream_t s) {
   const bool allp = a.npriv == a.p.band_hi;          // band_hi = number of cells
-  if (tight && g_priv_v2) {
-    const FastMap2 f2 = make_fast_map2(&a.p.v, fm);
-    if (f2.enabled) {
-      if (mode == 0) launch_priv_v2<SLOT, false>(a, f2, allp, smem, s);
-      else launch_priv_v2<SLOT, true>(a, f2, allp, smem, s);
-      dsb_note_kernel("k_points_priv_v2<%d,%s>", SLOT, mode == 1 ? "mean" : "count");
-      return;
-    }
-  }
   if (tight && mode == 0) launch_priv_tight<SLOT, false>(a, fm, allp, smem, s);
   else if (tight && mode == 1) launch_priv_tight<SLOT, true>(a, fm, allp, smem, s);
   else if (!vec) launch_priv_one<SLOT, 2, false>(a, fm, smem, s);      // unaligned columns: scalar loads, generic plan
   else if (mode == 0) launch_priv_one<SLOT, 0, true>(a, fm, smem, s);
   else if (mode == 1) launch_priv_one<SLOT, 1, true>(a, fm, smem, s);
   else launch_priv_one<SLOT, 2, true>(a, fm, smem, s);
-}
-
-static float f32_at_least(double v) { float f = (float)v; return ((double)f < v) ? nextafterf(f, INFINITY) : f; }
-static float f32_at_most(double v) { float f = (float)v; return ((double)f > v) ? nextafterf(f, -INFINITY) : f; }
-
-static FastMap make_fast_map(const dsb_view* v) {
-  FastMap f;
-  f.sx = (float)v->sx; f.tx = (float)v->tx; f.sy = (float)v->sy; f.ty = (float)v->ty;
-  f.xlo = f32_at_least(v->xmin); f.xhi = f32_at_most(v->xmax); f.ylo = f32_at_least(v->ymin); f.yhi = f32_at_most(v->ymax);
-  const double ax = fmax(fabs(v->xmin), fabs(v->xmax)), ay = fmax(fabs(v->ymin), fabs(v->ymax));
-  // |x * sx| is at most max(ax * |sx|, |tx| + W + 2) for any point, in or out of bounds, whose fast image lands in
-  // [-1, W + 1]; the bound covers the float32 roundings of sx, tx and of the fused multiply-add.
-  const double mx = fmax(ax * fabs(v->sx), fabs(v->tx) + v->width + 2.0), my = fmax(ay * fabs(v->sy), fabs(v->ty) + v->height + 2.0);
-  const double ex = ldexp(1.0, -23) * (v->width + 1.0 + mx + fabs(v->tx));
-  const double ey = ldexp(1.0, -23) * (v->height + 1.0 + my + fabs(v->ty));
-  f.ex = (float)ex; f.ey = (float)ey; f.omex = 1.0f - f.ex; f.omey = 1.0f - f.ey;
-  f.enabled = !v->x_log && !v->y_log && ex < 0.125 && ey < 0.125 && isfinite(ex) && isfinite(ey) && v->sx > 0 && v->sy > 0;
-  return f;
-}
-
-// v2: the bracket constants.  |fma(x, sx, tx) - R| <= ex for the reference's value R (make_fast_map); with the offsets
-// tx -+ 2 ex rounded outwards and the rounding of the shifted fma (<= ex / 2), xl < R < xh holds for every point whose
-// image lands in [-1, W + 1].  Equal floors of xl and xh therefore prove floor(R); everything else takes the exact path.
-static FastMap2 make_fast_map2(const dsb_view* v, const FastMap& f) {
-  FastMap2 g;
-  g.sx = f.sx; g.sy = f.sy;
-  g.txl = f32_at_most((double)f.tx - 2.0 * (double)f.ex); g.txh = f32_at_least((double)f.tx + 2.0 * (double)f.ex);
-  g.tyl = f32_at_most((double)f.ty - 2.0 * (double)f.ey); g.tyh = f32_at_least((double)f.ty + 2.0 * (double)f.ey);
-  g.enabled = f.enabled && f.ex < 0.03f && f.ey < 0.03f && v->width < (1 << 22) && v->height < (1 << 22) &&
-              (long long)v->width * v->height < (1LL << 26);
-  return g;
 }
 
 extern "C" int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,

@@ -1,0 +1,379 @@
+// Routed aggregation ("bin, then accumulate in shared memory") for single-accumulator plans on canvases that fit neither
+// shared memory nor L2 (BASELINE config 5: 8192 x 8192).
+//
+// dsb_points L2-bands such canvases: the columns are re-read once per band (5 passes = 60 B / point at 8192^2) and every
+// hit is still a global RED.  Here the points are routed instead (profiles/r02_routed.md):
+//
+//   sample   every 64th vector of x / y is mapped and histogrammed per BUCKET (a contiguous range of <= 45 056 canvas
+//            cells); a one-CTA planning kernel turns the estimate into per-bucket record capacities and offsets
+//   pass 1   every CTA maps a tile of points (float32 fast mapping, exact f64 mapping for points near a pixel edge),
+//            counting-sorts the tile by bucket in shared memory and appends each bucket's run to its region as coalesced
+//            8-byte records (bucket << 16 | cell in bucket, payload); one global atomic per bucket per tile reserves the space
+//   pass 2   a CTA takes one bucket at a time, keeps the bucket's cells in shared memory (u32 keys / rows / counts:
+//            shared-memory atomics, ~500 Gpts/s) and folds the finished tile into the canvas with plain loads and stores
+//
+// Traffic 12 + 8 + 8 B / point, no global atomics at all on the fast path.  Records that do not fit their bucket's region
+// (the sample underestimated it) are applied to the canvas directly with the same atomics dsb_points would use, so the
+// result is exact for any distribution; pass 2 hands out buckets dynamically, largest shares first come first served.
+#include "common.cuh"
+#include "fastmap.cuh"
+#include <limits.h>
+
+enum { R_MAX32 = 0, R_MIN32 = 1, R_MINROW = 2, R_MAXROW = 3, R_COUNT = 4 };
+
+constexpr int RT = 512;                 // threads per CTA of pass 1 (two CTAs per SM)
+constexpr int RPPT = 16;                // points per thread per tile
+constexpr int RTILE = RT * RPPT;        // 8192 points per tile
+constexpr uint32_t R_CPB_MAX = 45056;   // cells per bucket: 176 KB of u32 in pass 2
+
+struct RouteArgs {
+  dsb_view v;
+  FastMap fm;
+  const float* x; const float* y; const float* vcol;
+  long long n, row_offset;
+  uint32_t cpb, inv, nb, ncell;
+  unsigned long long* recs;             // records; bucket b owns [off[b], off[b] + cap[b])
+  const unsigned long long* off;        // [nb]
+  const uint32_t* cap;                  // [nb]
+  uint32_t* cursor;                     // [nb] records offered so far (beyond cap: applied to the canvas directly)
+  uint32_t* queue;                      // pass 2: next bucket to hand out
+  void* canvas;
+  unsigned int* notes;
+};
+
+__device__ __forceinline__ uint32_t route_key(const RouteArgs& a, uint32_t cell) {
+  uint32_t b = __umulhi(cell, a.inv);
+  uint32_t l = cell - b * a.cpb;
+  if (l >= a.cpb) { b++; l -= a.cpb; }
+  return (b << 16) | l;
+}
+
+// the accumulator op on the canvas itself (overflow records of pass 1)
+template <int OP>
+__device__ __forceinline__ void route_direct(const RouteArgs& a, uint32_t cell, uint32_t payload) {
+  if (OP == R_MAX32) atomicMax((int*)a.canvas + cell, key32_from_f32(__uint_as_float(payload)));
+  else if (OP == R_MIN32) atomicMin((int*)a.canvas + cell, key32_from_f32(__uint_as_float(payload)));
+  else if (OP == R_MINROW) atomicMin((long long*)a.canvas + cell, a.row_offset + (long long)payload);
+  else if (OP == R_MAXROW) atomicMax((long long*)a.canvas + cell, a.row_offset + (long long)payload);
+  else atomicAdd((unsigned int*)a.canvas + cell, 1u);
+}
+
+// ---- sample + plan ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_route_sample(const RouteArgs a, long long stride4, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh[];
+  for (uint32_t b = threadIdx.x; b < a.nb; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const long long n4 = a.n >> 2;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s * stride4 < n4; s += (long long)gridDim.x * blockDim.x) {
+    const float4 xa = __ldg(x4 + s * stride4), ya = __ldg(y4 + s * stride4);
+    const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float xf = fmaf(xs[k], a.fm.sx, a.fm.tx), yf = fmaf(ys[k], a.fm.sy, a.fm.ty);
+      const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+      if ((uint32_t)xi < (uint32_t)a.v.width && (uint32_t)yi < (uint32_t)a.v.height)
+        atomicAdd(sh + (route_key(a, (uint32_t)(yi * a.v.width + xi)) >> 16), 1u);      // an estimate: the fast pixel is enough
+    }
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < a.nb; b += blockDim.x) if (sh[b]) atomicAdd(hist + b, sh[b]);
+}
+
+// capacities from the sampled histogram (estimate + 8 standard deviations + slack, scaled down if the scratch is too
+// small - the overflow path keeps the result exact), exclusive scan -> offsets; cursors and the queue are cleared
+__global__ void __launch_bounds__(1024) k_route_plan(const uint32_t* __restrict__ hist, uint32_t nb, uint32_t stride_pts, unsigned long long capacity,
+                                                     unsigned long long* __restrict__ off, uint32_t* __restrict__ cap,
+                                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ queue) {
+  __shared__ unsigned long long part[1024];
+  __shared__ double scale_sh;
+  const int tid = threadIdx.x;
+  const uint32_t per = (nb + 1023) / 1024;
+  const uint32_t lo = tid * per, hi = min(lo + per, nb);
+  auto want = [&](uint32_t b) -> unsigned long long {
+    const double est = (double)hist[b] * stride_pts;
+    return (unsigned long long)(est + 8.0 * sqrt(est * stride_pts) + 2048.0) & ~1ull;
+  };
+  unsigned long long mine = 0;
+  for (uint32_t b = lo; b < hi; b++) mine += want(b);
+  part[tid] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 1024; i++) { const unsigned long long t = part[i]; part[i] = run; run += t; }
+    scale_sh = run > capacity ? (double)capacity / (double)run : 1.0;
+  }
+  __syncthreads();
+  const double scale = scale_sh;
+  unsigned long long run = (unsigned long long)((double)part[tid] * scale) & ~1ull;
+  for (uint32_t b = lo; b < hi; b++) {
+    unsigned long long c = want(b);
+    if (scale < 1.0) c = (unsigned long long)((double)c * scale) & ~1ull;
+    if (c > 0xfffffff0ull) c = 0xfffffff0ull;
+    off[b] = run; cap[b] = (uint32_t)c; cursor[b] = 0;
+    run += c;
+  }
+  if (tid == 0) *queue = 0;
+}
+
+// ---- pass 1 ----------------------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ RouteArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t nbp = (a.nb + 1) & ~1u;
+  unsigned long long* rec = (unsigned long long*)smem;                 // [RTILE]
+  unsigned long long* s_off = rec + RTILE;                             // [nbp] global offset of this tile's run minus base
+  uint32_t* hist = (uint32_t*)(s_off + nbp);                           // [nbp]
+  uint32_t* base = hist + nbp;                                         // [nbp]
+  uint32_t* room = base + nbp;                                         // [nbp] records of this tile's run that fit the region
+  uint32_t* wsum = room + nbp;                                         // [64]
+  const int tid = threadIdx.x;
+  const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const float4* __restrict__ v4 = (const float4*)a.vcol;
+  const long long n4 = a.n >> 2;
+  constexpr long long TILE4 = RTILE / 4;
+  bool negzero = false;
+  for (uint32_t b = tid; b < nbp; b += RT) hist[b] = 0;
+  __syncthreads();
+
+  for (long long t4 = (long long)blockIdx.x * TILE4; t4 < n4; t4 += (long long)gridDim.x * TILE4) {
+    uint32_t key[RPPT], rank[RPPT], pay[RPPT];
+#pragma unroll
+    for (int u = 0; u < RPPT / 4; u++) {
+      const long long i4 = t4 + (long long)u * RT + tid;
+      float4 xa, ya, va;
+      const float4 nan4 = make_float4(NAN, NAN, NAN, NAN), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (i4 < n4) { xa = __ldcs(x4 + i4); ya = __ldcs(y4 + i4); va = v4 ? __ldcs(v4 + i4) : one4; }
+      else { xa = ya = va = nan4; }
+      const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w}, vs[4] = {va.x, va.y, va.z, va.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        // the K2-tight mapping (k_points_priv_tight): a sure fractional part proves the pixel and the bounds decision
+        const float xf = fmaf(xs[k], a.fm.sx, a.fm.tx), yf = fmaf(ys[k], a.fm.sy, a.fm.ty);
+        const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+        const float dx = xf - (float)xi, dy = yf - (float)yi;
+        const bool sure = dx >= a.fm.ex && dx <= a.fm.omex && dy >= a.fm.ey && dy <= a.fm.omey;
+        int cell = (sure && (uint32_t)xi < W && (uint32_t)yi < H) ? yi * (int)W + xi : -1;
+        const bool live = vs[k] == vs[k];                      // NaN rows are skipped by every op
+        if (!sure && live) cell = map_exact_linear(a.v, xs[k], ys[k]);
+        const bool ok = live && cell >= 0;
+        const uint32_t kk = ok ? route_key(a, (uint32_t)cell) : 0xffffffffu;
+        key[u * 4 + k] = kk;
+        if (OP == R_MAX32 || OP == R_MIN32) { pay[u * 4 + k] = __float_as_uint(vs[k]); negzero |= ok && is_negzero(vs[k]); }
+        else pay[u * 4 + k] = (uint32_t)(4 * i4 + k);          // the row within this call (n < 2^32)
+        rank[u * 4 + k] = ok ? atomicAdd(hist + (kk >> 16), 1u) : 0u;
+      }
+    }
+    __syncthreads();
+    // block-wide exclusive scan of hist; every thread owns the entries [tid * per, tid * per + per)
+    const uint32_t per = (a.nb + RT - 1) / RT;
+    const uint32_t lo = tid * per, hi = min(lo + per, a.nb);
+    uint32_t mine = 0;
+    for (uint32_t b = lo; b < hi; b++) mine += hist[b];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t w = tid < RT / 32 ? wsum[tid] : 0u;
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += t; }
+      wsum[32 + tid] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = wsum[32 + (tid >> 5)] + incl - mine;
+    for (uint32_t b = lo; b < hi; b++) {
+      const uint32_t h = hist[b];
+      base[b] = run;
+      if (h) {
+        const uint32_t g = atomicAdd(a.cursor + b, h);         // one global atomic per non-empty bucket per tile
+        const uint32_t c = a.cap[b];
+        room[b] = g >= c ? 0u : min(h, c - g);
+        s_off[b] = a.off[b] + g - run;
+      } else room[b] = 0;
+      hist[b] = 0;                                             // ready for the next tile
+      run += h;
+    }
+    if (tid == RT - 1) wsum[31] = run;                         // records of the tile
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RPPT; k++)
+      if (key[k] != 0xffffffffu) rec[base[key[k] >> 16] + rank[k]] = ((unsigned long long)pay[k] << 32) | key[k];
+    __syncthreads();
+    const uint32_t total = wsum[31];
+#pragma unroll
+    for (int u = 0; u < RPPT; u += 4) {                        // four records in flight per thread
+      unsigned long long rr[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const uint32_t q = (u + k) * RT + tid; rr[k] = q < total ? rec[q] : 0ull; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t q = (u + k) * RT + tid;
+        if (q >= total) continue;
+        const uint32_t b = ((uint32_t)rr[k]) >> 16;
+        if (q - base[b] < room[b]) a.recs[s_off[b] + q] = rr[k];
+        else route_direct<OP>(a, b * a.cpb + ((uint32_t)rr[k] & 0xffffu), (uint32_t)(rr[k] >> 32));   // the region is full
+      }
+    }
+    __syncthreads();
+  }
+  // the last n & 3 rows: straight to the canvas
+  if (blockIdx.x == 0 && tid < (int)(a.n & 3)) {
+    const long long i = (n4 << 2) + tid;
+    const float vv = a.vcol ? a.vcol[i] : 1.f;
+    const int cell = vv == vv ? map_exact_linear(a.v, a.x[i], a.y[i]) : -1;
+    if (cell >= 0) {
+      if (OP == R_MAX32 || OP == R_MIN32) { negzero |= is_negzero(vv); route_direct<OP>(a, (uint32_t)cell, __float_as_uint(vv)); }
+      else route_direct<OP>(a, (uint32_t)cell, (uint32_t)i);
+    }
+  }
+  if ((OP == R_MAX32 || OP == R_MIN32) && negzero && a.notes) *a.notes = DSB_NOTE_NEGZERO;
+}
+
+// ---- pass 2 ----------------------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) k_route_eat(const __grid_constant__ RouteArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t* tile = (uint32_t*)smem;
+  __shared__ uint32_t next;
+  constexpr uint32_t IDENT = OP == R_MAX32 ? (uint32_t)INT_MIN : OP == R_MIN32 ? (uint32_t)INT_MAX : OP == R_MINROW ? 0xffffffffu : 0u;
+  auto eat = [&](uint32_t key, uint32_t pay) {
+    const uint32_t l = key & 0xffffu;
+    if (OP == R_MAX32) atomicMax((int*)tile + l, key32_from_f32(__uint_as_float(pay)));
+    else if (OP == R_MIN32) atomicMin((int*)tile + l, key32_from_f32(__uint_as_float(pay)));
+    else if (OP == R_MINROW) atomicMin(tile + l, pay);
+    else if (OP == R_MAXROW) atomicMax(tile + l, pay + 1u);          // 0 = no row yet
+    else atomicAdd(tile + l, 1u);
+  };
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) next = atomicAdd(a.queue, 1u);
+    __syncthreads();
+    const uint32_t b = next;
+    if (b >= a.nb) break;
+    for (uint32_t q = threadIdx.x; q < a.cpb; q += 1024) tile[q] = IDENT;
+    __syncthreads();
+    const uint32_t nrec = min(a.cursor[b], a.cap[b]);
+    const unsigned long long* base = a.recs + a.off[b];              // off and cap are even: 16-byte aligned
+    const uint4* r4 = (const uint4*)base;
+    const uint32_t n2 = nrec >> 1;
+    for (uint32_t i = threadIdx.x; i < n2; i += 1024) {
+      const uint4 q = __ldcs(r4 + i);
+      eat(q.x, q.y);
+      eat(q.z, q.w);
+    }
+    if ((nrec & 1) && threadIdx.x == 0) { const unsigned long long q = base[nrec - 1]; eat((uint32_t)q, (uint32_t)(q >> 32)); }
+    __syncthreads();
+    // fold the tile into the canvas: this CTA is the only writer of these cells now (pass 1 has finished)
+    const uint32_t c0 = b * a.cpb;
+    for (uint32_t q = threadIdx.x; q < a.cpb && c0 + q < a.ncell; q += 1024) {
+      const uint32_t t = tile[q];
+      if (t == IDENT) continue;
+      if (OP == R_MAX32) { int* c = (int*)a.canvas + c0 + q; if ((int)t > *c) *c = (int)t; }
+      else if (OP == R_MIN32) { int* c = (int*)a.canvas + c0 + q; if ((int)t < *c) *c = (int)t; }
+      else if (OP == R_MINROW) { long long* c = (long long*)a.canvas + c0 + q; const long long r = a.row_offset + (long long)t; if (r < *c) *c = r; }
+      else if (OP == R_MAXROW) { long long* c = (long long*)a.canvas + c0 + q; const long long r = a.row_offset + (long long)t - 1; if (r > *c) *c = r; }
+      else ((unsigned int*)a.canvas)[c0 + q] += t;
+    }
+  }
+}
+
+// ---- entry points ------------------------------------------------------------------------------------------------------
+static long long g_routed_min_rows = 1LL << 24;
+
+extern "C" int dsb_routed_configure(int64_t min_rows) { g_routed_min_rows = min_rows; return DSB_OK; }
+
+static uint32_t route_nb(long long ncell, uint32_t* cpb) {
+  const long long nb = (ncell + R_CPB_MAX - 1) / R_CPB_MAX;
+  *cpb = (uint32_t)((ncell + nb - 1) / nb);
+  return (uint32_t)nb;
+}
+static size_t route_header_bytes(uint32_t nb) { return (((size_t)nb * (8 + 4 + 4 + 4) + 64) + 255) & ~(size_t)255; }
+
+extern "C" int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t n) {
+  if (!view || view->width <= 0 || view->height <= 0 || n < 0) return 0;
+  uint32_t cpb;
+  const uint32_t nb = route_nb((long long)view->width * view->height, &cpb);
+  // records: 1.10 n + 4096 per bucket (k_route_plan scales the capacities down to whatever it is given)
+  return (int64_t)(route_header_bytes(nb) + ((size_t)((double)n * 1.10) + (size_t)nb * 4096) * 8);
+}
+
+template <int OP>
+static void route_launch(const RouteArgs& a, size_t smem1, size_t smem2, cudaStream_t s) {
+  cudaFuncSetAttribute(k_route_bin<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  cudaFuncSetAttribute(k_route_eat<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  k_route_bin<OP><<<dsb_num_sms() * 2, RT, smem1, s>>>(a);
+  k_route_eat<OP><<<dsb_num_sms(), 1024, smem2, s>>>(a);
+}
+
+extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                                 const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points_routed: bad view"); return DSB_ERR_ARG; }
+  if (!plan || plan->nops != 1 || plan->ncat != 0) { dsb_set_error("dsb_points_routed: one accumulator, no categories"); return DSB_ERR_UNSUPPORTED; }
+  if (n < g_routed_min_rows || n >= (1LL << 32) - 1) { dsb_set_error("dsb_points_routed: n out of range"); return DSB_ERR_UNSUPPORTED; }
+  if (!x || !y || !scratch) { dsb_set_error("dsb_points_routed: null pointer"); return DSB_ERR_ARG; }
+  const dsb_base& b = plan->ops[0];
+  if (!b.agg) { dsb_set_error("dsb_points_routed: op has no canvas"); return DSB_ERR_ARG; }
+  int op = -1;
+  const float* vcol = nullptr;
+  switch (b.op) {
+    case DSB_OP_MAX32: case DSB_OP_MIN32:
+      if (b.val_dtype != DSB_F32 || !b.val || b.chk_dtype != DSB_NONE) break;
+      vcol = (const float*)b.val; op = b.op == DSB_OP_MAX32 ? R_MAX32 : R_MIN32; break;
+    case DSB_OP_MINROW: case DSB_OP_MAXROW:
+      if (b.chk_dtype != DSB_F32 || !b.chk || b.val_dtype != DSB_NONE) break;
+      vcol = (const float*)b.chk; op = b.op == DSB_OP_MINROW ? R_MINROW : R_MAXROW; break;
+    case DSB_OP_COUNT:
+      if (b.chk_dtype != DSB_NONE || (b.val_dtype != DSB_NONE && b.val_dtype != DSB_F32)) break;
+      vcol = b.val_dtype == DSB_F32 ? (const float*)b.val : nullptr; op = R_COUNT; break;
+    default: break;
+  }
+  if (op < 0) { dsb_set_error("dsb_points_routed: serves max / min / first / last of a float32 column and count"); return DSB_ERR_UNSUPPORTED; }
+  const long long ncell = (long long)view->width * view->height;
+  if (xy_dtype != DSB_F32 || ncell >= (1LL << 31) || ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)vcol) & 15) != 0)) {
+    dsb_set_error("dsb_points_routed: needs aligned float32 columns and fewer than 2^31 cells"); return DSB_ERR_UNSUPPORTED;
+  }
+  RouteArgs a;
+  a.v = *view;
+  a.fm = make_fast_map(view);
+  if (!a.fm.enabled) { dsb_set_error("dsb_points_routed: needs linear axes within the float32 fast mapping's error bound"); return DSB_ERR_UNSUPPORTED; }
+  a.x = (const float*)x; a.y = (const float*)y; a.vcol = vcol; a.n = n; a.row_offset = row_offset;
+  a.nb = route_nb(ncell, &a.cpb);
+  a.inv = (uint32_t)((1ull << 32) / a.cpb);
+  a.ncell = (uint32_t)ncell;
+  const size_t hdr = route_header_bytes(a.nb);
+  if (a.nb > 65535 || scratch_bytes < (int64_t)(hdr + ((size_t)a.nb * 4096 + 1024) * 8)) { dsb_set_error("dsb_points_routed: scratch too small"); return DSB_ERR_ARG; }
+  unsigned char* p = (unsigned char*)scratch;
+  unsigned long long* off = (unsigned long long*)p;
+  uint32_t* cap = (uint32_t*)(off + a.nb);
+  uint32_t* cursor = cap + a.nb;
+  uint32_t* hist = cursor + a.nb;
+  uint32_t* queue = hist + a.nb;
+  a.recs = (unsigned long long*)(p + hdr);
+  a.off = off; a.cap = cap; a.cursor = cursor; a.queue = queue; a.canvas = b.agg; a.notes = plan->notes;
+  const unsigned long long capacity = ((unsigned long long)scratch_bytes - hdr) / 8;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(hist, 0, (size_t)a.nb * 4, s);
+  const long long stride4 = n >= (1LL << 28) ? 16 : 4;          // every 64th (16th) point is sampled
+  k_route_sample<<<dsb_num_sms() * 4, 256, (size_t)a.nb * 4, s>>>(a, stride4, hist);
+  k_route_plan<<<1, 1024, 0, s>>>(hist, a.nb, (uint32_t)stride4, capacity, off, cap, cursor, queue);
+  const uint32_t nbp = (a.nb + 1) & ~1u;
+  const size_t smem1 = (size_t)RTILE * 8 + (size_t)nbp * (8 + 4 + 4 + 4) + 64 * 4;
+  const size_t smem2 = (size_t)a.cpb * 4;
+  static const char* const names[] = {"max32", "min32", "minrow", "maxrow", "count"};
+  dsb_note_kernel("k_route_bin<%s> + k_route_eat<%s> buckets=%u", names[op], names[op], a.nb);
+  switch (op) {
+    case R_MAX32: route_launch<R_MAX32>(a, smem1, smem2, s); break;
+    case R_MIN32: route_launch<R_MIN32>(a, smem1, smem2, s); break;
+    case R_MINROW: route_launch<R_MINROW>(a, smem1, smem2, s); break;
+    case R_MAXROW: route_launch<R_MAXROW>(a, smem1, smem2, s); break;
+    default: route_launch<R_COUNT>(a, smem1, smem2, s); break;
+  }
+  DSB_CUDA_CHECK_LAUNCH("dsb_points_routed");
+  return DSB_OK;
+}

@@ -125,6 +125,8 @@ def _plans(chunk, accs, canv, ctx, categorizer, ncat):
         yield plan, keep
 
 
+# accumulators dsb_points_routed serves -> bytes per canvas cell
+_ROUTED_OPS = {_lib.OP_MAX32: 4, _lib.OP_MIN32: 4, _lib.OP_MINROW: 8, _lib.OP_MAXROW: 8, _lib.OP_COUNT: 4}
 _MONO_OPS = (_lib.OP_MAX32, _lib.OP_MIN32, _lib.OP_MINROW, _lib.OP_MAXROW, _lib.OP_ARGMAX32, _lib.OP_ARGMIN32)
 
 
@@ -205,6 +207,20 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
             return
         if rc != -3:
             _lib.check(rc, "dsb_points_count16")
+    if (config.routed and plan.nops == 1 and plan.ncat == 0 and xy_dtype == _lib.F32 and n >= config.routed_min_rows
+            and plan.ops[0].op in _ROUTED_OPS and ncell * _ROUTED_OPS[plan.ops[0].op] > config.l2_budget_bytes):
+        # the accumulator canvas is beyond L2: route the points to shared-memory-sized buckets instead of banding
+        need = int(lib.dsb_points_routed_scratch_bytes(C.byref(view), n))
+        if 0 < need <= config.routed_max_scratch_bytes:
+            scratch = getattr(ctx, "_routed_scratch", None)
+            if scratch is None or scratch.numel() < need:
+                scratch = ctx._routed_scratch = torch.empty(need, dtype=torch.uint8, device=x.device)
+            rc = lib.dsb_points_routed(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
+                                       scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
+            if rc == 0:
+                return
+            if rc != -3:
+                _lib.check(rc, "dsb_points_routed")
     _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
                               ctx.stream_ptr), "dsb_points")
 

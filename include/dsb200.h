@@ -129,6 +129,21 @@ int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t 
                     int64_t row_offset, const dsb_plan* plan, int32_t priv_op, uint32_t* scratch, uint32_t* flag,
                     void* stream);
 
+/* Routed aggregation for a single-accumulator plan on a canvas that fits neither shared memory nor L2 (BASELINE config 5,
+ * 8192 x 8192): the points are binned into buckets of <= 45 056 canvas cells as 8-byte records (pass 1) and every bucket
+ * is then accumulated with its cells in shared memory and folded into the canvas with plain loads and stores (pass 2) -
+ * instead of dsb_points' L2-banded re-reads with a global RED per hit.  Same contract and result as dsb_points for
+ * MAX32 / MIN32 (float32 value column), MINROW / MAXROW (float32 nan-check column) and COUNT (optional float32 column)
+ * with float32 coordinates on linear axes, 16-byte aligned columns, no categories, n in [2^24, 2^32 - 1); anything else
+ * returns DSB_ERR_UNSUPPORTED and the caller uses dsb_points.  Exact for every distribution: records that do not fit the
+ * sampled capacity of their bucket are applied to the canvas directly with atomics.
+ * scratch: device memory of at least dsb_points_routed_scratch_bytes(view, n) bytes (contents ignored on entry). */
+int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t n);
+int dsb_points_routed(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                      const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream);
+/* smallest n dsb_points_routed accepts (default 2^24; tests lower it) */
+int dsb_routed_configure(int64_t min_rows);
+
 /* NaN-skipping min/max of a column: Glyph._compute_bounds_numba (glyphs/glyph.py:66-78).
  * out_minmax: 2 doubles on the device, (+inf, -inf) when no finite-or-inf value exists. */
 int dsb_bounds(const void* col, int32_t dtype, int64_t n, double* out_minmax, void* stream);

@@ -1,0 +1,155 @@
+"""dsb_points_routed ("bin, then accumulate in shared memory", csrc/routed.cu) against the C oracle and against dsb_points:
+forced on at small n, several buckets, clustered data, records overflowing their bucket's region (direct-atomic fallback),
+-0.0 values, and - at BASELINE config 5's production geometry (8192 x 8192, 1e8 points) - against the L2-banded kernels."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import SPECS, assert_agg_equal, make_agg
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["max_v32", "min_v32", "first_v32", "last_v32", "count", "count_v32", "where_first_v32_other", "where_last_v32_row"]
+
+
+@pytest.fixture()
+def routed():
+    import datashader_b200 as ds
+    from datashader_b200 import _lib
+    L = _lib.lib()
+    old = (ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16)
+    ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16 = 0, 1, False, False
+    _lib.check(L.dsb_routed_configure(0))
+    yield ds
+    ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16 = old
+    _lib.check(L.dsb_routed_configure(1 << 24))
+
+
+def _cols(rng, n, clustered=False):
+    if clustered:
+        c = rng.integers(0, 3, n)
+        cx, cy = np.array([0.2, 0.7, 0.71])[c], np.array([0.3, 0.3, 0.8])[c]
+        x = (cx + rng.normal(0, 0.01, n)).astype(np.float32)
+        y = (cy + rng.normal(0, 0.01, n)).astype(np.float32)
+    else:
+        x = (rng.random(n) * 1.2 - 0.1).astype(np.float32)
+        y = (rng.random(n) * 1.2 - 0.1).astype(np.float32)
+    cols = {"x": x, "y": y, "v32": np.round(rng.standard_normal(n), 1).astype(np.float32), "other": rng.random(n).astype(np.float32)}
+    cols["v32"][rng.integers(0, n, n // 40)] = np.nan
+    cols["x"][:3] = [0.0, 1.0, np.nan]
+    cols["y"][:3] = [1.0, 0.0, 0.5]
+    return cols
+
+
+@pytest.mark.parametrize("shape,n,clustered", [((301, 257), 200_003, False), ((640, 480), 300_001, False), ((640, 480), 250_000, True)])
+def test_routed_matches_oracle(routed, shape, n, clustered):
+    import torch
+    from datashader_b200 import _lib
+    from oracle import oracle as ora
+    ds = routed
+    W, H = shape
+    cols = _cols(np.random.default_rng(n), n, clustered)
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    for name in NAMES:
+        spec = SPECS[name]
+        got = cvs.points(frame, "x", "y", make_agg(spec)).data
+        assert b"k_route" in _lib.lib().dsb_last_kernel(), (name, _lib.lib().dsb_last_kernel())
+        want = ora.points(cols, "x", "y", spec, view, npartitions=2 if ("first" in name or "last" in name) else 1)
+        assert_agg_equal(got, want, f"routed {name} {shape} clustered={clustered}")
+
+
+def test_routed_overflow_falls_back_to_canvas_atomics(routed):
+    """A scratch buffer far smaller than the records: almost every record overflows its bucket's region and is applied to
+    the canvas directly; the result must equal dsb_points' bit for bit."""
+    import torch
+    from datashader_b200 import _lib
+    ds = routed
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    n, W, H = 400_000, 640, 480
+    cols = _cols(rng, n)
+    x, y, v = (torch.from_numpy(cols[k]).cuda() for k in ("x", "y", "v32"))
+    from datashader_b200 import pipeline
+    view, _, _ = pipeline.make_view(ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0)), (0.0, 1.0), (0.0, 1.0))
+    stream = torch.cuda.current_stream().cuda_stream
+    nb = -(-W * H // 45056)
+    small = (((nb * 20 + 64) + 255) & ~255) + (nb * 4096 + 1024) * 8        # the minimum dsb_points_routed accepts
+    for op, dtype, use_chk in ((_lib.OP_MAX32, torch.int32, False), (_lib.OP_MINROW, torch.int64, True), (_lib.OP_MAXROW, torch.int64, True),
+                               (_lib.OP_COUNT, torch.int32, False)):
+        outs = []
+        for routed_call in (True, False):
+            canvas = torch.empty(H * W, dtype=dtype, device="cuda")
+            _lib.check(L.dsb_init_canvas(op, canvas.data_ptr(), canvas.numel(), stream))
+            plan = _lib.Plan()
+            plan.nops = 1
+            plan.ops[0].op, plan.ops[0].agg = op, canvas.data_ptr()
+            if use_chk:
+                plan.ops[0].chk_dtype, plan.ops[0].chk = _lib.F32, v.data_ptr()
+            else:
+                plan.ops[0].val_dtype, plan.ops[0].val = _lib.F32, v.data_ptr()
+            if routed_call:
+                scratch = torch.empty(small, dtype=torch.uint8, device="cuda")
+                _lib.check(L.dsb_points_routed(C.byref(view), x.data_ptr(), y.data_ptr(), _lib.F32, n, 7, C.byref(plan), scratch.data_ptr(),
+                                               small, stream), "dsb_points_routed")
+            else:
+                _lib.check(L.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), _lib.F32, n, 7, C.byref(plan), stream), "dsb_points")
+            outs.append(canvas.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1]), f"op {op}"
+
+
+def test_routed_negzero(routed):
+    import torch
+    from oracle import oracle as ora
+    ds = routed
+    rng = np.random.default_rng(11)
+    n, W, H = 150_000, 301, 257
+    zeros = np.where(rng.random(n) < 0.5, np.float32(-0.0), np.float32(0.0))
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": np.where(rng.random(n) < 0.5, zeros, -rng.random(n).astype(np.float32) - 0.1).astype(np.float32)}
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    got = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(frame, "x", "y", ds.max("v32")).data
+    want = ora.points(cols, "x", "y", ("max", "v32"), ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0)))
+    assert np.signbit(want[want == 0]).any()
+    assert_agg_equal(got, want, "routed negzero max")
+
+
+def test_routed_equals_banded_at_production_geometry():
+    """8192 x 8192, 1e8 points, real budgets: the routed path, the L2-banded mono kernels and the unbanded generic kernel
+    agree bit for bit on max / first / count (BASELINE config 5's geometry)."""
+    import torch
+    import datashader_b200 as ds
+    from datashader_b200 import _lib
+    L = _lib.lib()
+    n = 100_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.rand(n, generator=g, device="cuda") * 1.02 - 0.01
+    y = torch.rand(n, generator=g, device="cuda") * 1.02 - 0.01
+    v = torch.randn(n, generator=g, device="cuda")
+    v[::997] = float("nan")
+    frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
+    cvs = ds.Canvas(8192, 8192, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    ds.config.device_results = True
+    try:
+        for agg in (ds.max("value"), ds.first("value"), ds.count()):
+            res = {}
+            for mode in ("routed", "banded", "generic"):
+                ds.config.routed = mode == "routed"
+                _lib.check(L.dsb_configure(b"l2_band_bytes", 0 if mode == "generic" else 96 << 20))
+                _lib.check(L.dsb_configure(b"mono", 0 if mode == "generic" else 1))
+                res[mode] = cvs.points(frame, "x", "y", agg).data.clone()
+                kern = L.dsb_last_kernel()
+                assert (b"k_route" in kern) == (mode == "routed"), (mode, kern)
+            for mode in ("banded", "generic"):
+                a, b = res["routed"], res[mode]
+                same = torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)) if a.dtype.is_floating_point else torch.equal(a, b)
+                assert same, f"{agg} routed vs {mode}"
+            del res
+    finally:
+        ds.config.device_results = False
+        ds.config.routed = True
+        _lib.check(L.dsb_configure(b"l2_band_bytes", 96 << 20))
+        _lib.check(L.dsb_configure(b"mono", 1))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""A/B timing of the K2 kernels at the headline geometry (900x525, n uniform float32 points, device-resident):
+"""Timing of the K2 kernels at the headline geometry (900x525, n uniform float32 points, device-resident):
     python tools/bench_k2.py [n] [key=value ...]     # key=value pairs go to dsb_configure before timing
-Prints ms / Gpts/s of count() and mean('value') for priv_v2 = 0 and 1, and checks that the two agree."""
+Prints ms / Gpts/s of count() and mean('value') and the kernel the library chose."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,29 +23,15 @@ frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
 cvs = ds.Canvas(900, 525, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
 config.device_results = True
 config.priv_min_rows = 0
-
-
-def timed(agg, steps=10):
+for name, agg in (("count", ds.count()), ("mean", ds.mean("value"))):
     for _ in range(3):
         out = cvs.points(frame, "x", "y", agg)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
+    for _ in range(10):
         out = cvs.points(frame, "x", "y", agg)
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps, out.data.clone(), L.dsb_last_kernel().decode()
-
-
-res = {}
-for v2 in (0, 1):
-    _lib.check(L.dsb_configure(b"priv_v2", v2), "priv_v2")
-    for name, agg in (("count", ds.count()), ("mean", ds.mean("value"))):
-        ms, out, kern = timed(agg)
-        res[(name, v2)] = out
-        print(f"priv_v2={v2} {name:5s} {ms:7.3f} ms  {n / ms / 1e6:7.1f} Gpts/s   {kern}", flush=True)
-same_c = torch.equal(res[("count", 0)], res[("count", 1)])
-a, b = res[("mean", 0)], res[("mean", 1)]
-same_m = torch.equal(torch.isnan(a), torch.isnan(b)) and torch.allclose(torch.nan_to_num(a), torch.nan_to_num(b), rtol=1e-12, atol=0)
-print("count v2 == v1:", same_c, " mean v2 ~ v1:", same_m, " total:", int(res[("count", 1)].view(torch.int32).to(torch.int64).sum()))
+    ms = e0.elapsed_time(e1) / 10
+    print(f"{name:5s} {ms:7.3f} ms  {n / ms / 1e6:7.1f} Gpts/s   {L.dsb_last_kernel().decode()}", flush=True)
