@@ -11,6 +11,7 @@ make_create / make_append / make_combine / make_finalize replaced by a plan hand
 from __future__ import annotations
 
 import ctypes as C
+from builtins import any as builtins_any
 
 import numpy as np
 import torch
@@ -79,15 +80,17 @@ def _reductions_of(agg):
     return list(agg.values) if isinstance(agg, rd.summary) else [agg]
 
 
-def _categorical_setup(agg, schema):
-    """by(): the categorizer + number of categories (compiler.py:379-390)."""
-    cats = [r for r in _reductions_of(agg) if isinstance(r, rd.by)]
+def _group_key(r):
+    """Reductions that can share one pass share a canvas shape: every plain reduction -> None, by() -> its categorizer."""
+    return r._hashable_inputs()[:3] if isinstance(r, rd.by) else None
+
+
+def _categorical_setup(reds, schema):
+    """by(): the categorizer + number of categories (compiler.py:379-390) of one group of reductions (_group_key)."""
+    cats = [r for r in reds if isinstance(r, rd.by)]
     if not cats:
         return None, 0, None
-    keys = {c._hashable_inputs()[:3] for c in cats}
-    if len(keys) > 1 or len(cats) != len(_reductions_of(agg)):
-        raise NotImplementedError("summary() mixing different categorizers / non-categorical reductions "
-                                  "is not supported by datashader_b200 yet")
+    assert len(cats) == len(reds) and len({_group_key(c) for c in cats}) == 1
     categorizer = cats[0].categorizer
     labels = categorizer.categories(schema)
     return categorizer, len(labels), labels
@@ -262,18 +265,34 @@ def _prepare(source, glyph, agg, canvas):
 
 
 def _accumulate_and_finalize(frame, resident, needed, schema, view, canvas, glyph, agg, dist, launch, ctx_extra=None):
-    """accumulators -> fused launches (per chunk, per stage) -> [all-reduce] -> finalize."""
+    """summary() composes any bases (compiler.py:103-107, reductions.py:2169-2246): reductions are grouped by canvas shape -
+    the plain ones [H, W], every categorizer its own [H, W, C] - and each group runs as one accumulate-and-finalize.
+    Returns (reductions, results, category labels per reduction)."""
+    reds = _reductions_of(agg)
+    groups = {}
+    for i, r in enumerate(reds):
+        groups.setdefault(_group_key(r), []).append(i)
+    results, labels = [None] * len(reds), [None] * len(reds)
+    for idx in groups.values():
+        res, lab = _accumulate_group(frame, resident, needed, schema, view, canvas, glyph, [reds[i] for i in idx], dist, launch,
+                                     ctx_extra)
+        for i, t in zip(idx, res):
+            results[i], labels[i] = t, lab
+    return reds, results, labels
+
+
+def _accumulate_group(frame, resident, needed, schema, view, canvas, glyph, reds, dist, launch, ctx_extra=None):
+    """accumulators -> fused launches (per chunk, per stage) -> [all-reduce] -> finalize, for reductions of one shape."""
     device = frame.device
     stream_ptr = torch.cuda.current_stream(device).cuda_stream
     single = resident is not None
-    categorizer, ncat, labels = _categorical_setup(agg, schema)
+    categorizer, ncat, labels = _categorical_setup(reds, schema)
     shape = (canvas.plot_height, canvas.plot_width) + ((ncat,) if ncat else ())
     ctx = _Ctx(frame, view, shape, dist)
     if single:
         ctx.resident = resident
     for k, v in (ctx_extra or {}).items():
         setattr(ctx, k, v)
-    reds = _reductions_of(agg)
 
     def unique_accs(lists):
         out, seen = [], set()
@@ -321,8 +340,7 @@ def _accumulate_and_finalize(frame, resident, needed, schema, view, canvas, glyp
             ctx.exact_zero = True
             ctx.notes = None
             run(unique_accs([a for r in reds for a in r._exact_accs(ctx)]))
-    results = [r._finalize(ctx, canv) for r in reds]
-    return reds, results, labels
+    return [r._finalize(ctx, canv) for r in reds], labels
 
 
 def points(source, canvas, glyph: Point, agg, dist=None):
@@ -362,19 +380,19 @@ def _merge_bounds(parts, dist, device):
 
 def _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels):
     """make_finalize (compiler.py:510-536) + by._build_finalize (reductions.py:809-820)."""
-    def one(r, t):
+    def one(r, t, lab):
         coords = {glyph.y_label: y_axis, glyph.x_label: x_axis}
         dims = [glyph.y_label, glyph.x_label]
         if isinstance(r, rd.by):
             dims = dims + [r.cat_column]
-            coords[r.cat_column] = labels
+            coords[r.cat_column] = lab
         data = _to_host(t, getattr(r, "_out_np_view", None))
         return DataArray(data, coords=coords, dims=dims, attrs=dict(x_range=x_range, y_range=y_range))
 
     if isinstance(agg, rd.summary):
-        return Dataset({k: one(r, t) for k, r, t in zip(agg.keys, reds, results)},
+        return Dataset({k: one(r, t, lab) for k, r, t, lab in zip(agg.keys, reds, results, labels)},
                        attrs=dict(x_range=x_range, y_range=y_range))
-    return one(reds[0], results[0])
+    return one(reds[0], results[0], labels[0])
 
 
 # ------------------------------------------------------------------------------------------ lines
@@ -409,10 +427,116 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
             simple = False       # a -0.0 value: the plan path resolves which zero arrived first (DSB_NOTE_NEGZERO)
     if line_width == 0 and not simple:
         return _lines_plan(frame, needed, schema, canvas, glyph, agg, dist)
-    combo = _aa2_combo(agg) if line_width > 0 else None
-    if combo is not None:
-        return _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist)
-    # single-stage antialiased reductions: any / count / sum / max / mean, optionally per category (by)
+    if line_width > 0:
+        return _lines_antialiased(frame, schema, canvas, glyph, agg, line_width, dist)
+    return _lines_single_stage(frame, schema, canvas, glyph, agg, line_width, dist)
+
+
+def _aa_inner(r):
+    return r.reduction if isinstance(r, rd.by) else r
+
+
+def _aa_requires_2_stages(r):
+    """Reduction._antialias_requires_2_stages (reductions.py:370-374, 506-507, 779-780, 1009-1010, 1169-1170, 1349-1350)."""
+    r = _aa_inner(r)
+    if isinstance(r, (rd.count, rd.sum)):
+        return not r.self_intersect
+    return isinstance(r, (rd.min, rd.first, rd.last))
+
+
+def _lines_antialiased(frame, schema, canvas, glyph, agg, line_width, dist):
+    """Antialiased lines.  make_antialias_stage_2 (compiler.py:539-554): if ANY requested reduction needs the 2-stage
+    procedure, every count / sum of the call is computed without self-intersection; each reduction then runs through the
+    kernel that implements its stage-2 combination (antialias.py:30-58) and a summary() is the Dataset of those."""
+    reds = _reductions_of(agg)
+    force = builtins_any(_aa_requires_2_stages(r) for r in reds)
+    outs = []
+    for r in reds:
+        inner = _aa_inner(r)
+        if force and isinstance(inner, (rd.count, rd.sum)) and inner.self_intersect:
+            inner = type(inner)(inner.column, self_intersect=False)
+            r = rd.by(r.categorizer, inner) if isinstance(r, rd.by) else inner
+        if force and isinstance(inner, rd.mean):
+            raise NotImplementedError("mean() next to a 2-stage antialiased reduction is not implemented in datashader_b200")
+        if isinstance(inner, rd.where):
+            if isinstance(r, rd.by):
+                raise NotImplementedError("by(where(...)) is not implemented for antialiased datashader_b200 lines")
+            outs.append(_lines_aa_where(frame, canvas, glyph, inner, line_width, dist))
+        elif _aa2_combo(inner) is None:
+            if getattr(inner, "_line_agg", None) is None:
+                raise NotImplementedError(f"{type(inner).__name__} is not implemented for antialiased datashader_b200 lines yet")
+            outs.append(_lines_single_stage(frame, schema, canvas, glyph, r, line_width, dist))
+        elif isinstance(r, rd.by):
+            outs.append(_lines_aa2_by(frame, schema, canvas, glyph, r, line_width, dist))
+        else:
+            outs.append(_lines_aa2(frame, canvas, glyph, inner, _aa2_combo(inner), line_width, dist))
+    if isinstance(agg, rd.summary):
+        return Dataset(dict(zip(agg.keys, outs)), attrs=dict(outs[0].attrs))
+    return outs[0]
+
+
+def _lines_aa2_by(frame, schema, canvas, glyph, agg, line_width, dist):
+    """by(cat, <2-stage reduction>) on antialiased lines: the stage-2 combination is per category plane (categorical=True,
+    reductions.py:782-787), i.e. each category's lines are folded on their own - one dsb_lines_aa2 run per category over
+    that category's lines (line order, hence first / last, is preserved inside a category)."""
+    if glyph_per_vertex(glyph):
+        raise NotImplementedError("by() over per-vertex line glyphs is not implemented for 2-stage antialiasing")
+    categorizer, ncat, labels = _categorical_setup([agg], schema)
+    codes = categorizer.codes(frame)
+    inner = agg.reduction
+    # ranges must be those of the whole frame, not of a category's subset
+    x_range, y_range = _line_setup(frame, canvas, glyph, dist)[:2]
+    import copy
+    sub_canvas = copy.copy(canvas)
+    sub_canvas.x_range, sub_canvas.y_range = tuple(x_range), tuple(y_range)
+    planes, first = [], None
+    for c in range(ncat):
+        sel = (codes == c) | (codes == c - ncat)            # negative codes wrap like numba's agg[:, :, -1]
+        sub = DeviceFrame({k: frame[k][sel].contiguous() for k in frame.columns}, frame.categories, 0, None)
+        sub.sharded, sub.group = getattr(frame, "sharded", False), getattr(frame, "group", None)
+        part = _lines_aa2(sub, sub_canvas, glyph, inner, _aa2_combo(inner), line_width, dist)
+        first = first or part
+        planes.append(torch.as_tensor(part.data))
+    data = torch.stack(planes, dim=-1)
+    data = data if config.device_results else data.cpu().numpy()
+    coords = dict(first.coords)
+    coords[agg.cat_column] = list(labels)
+    return DataArray(data, coords=coords, dims=list(first.dims) + [agg.cat_column], attrs=dict(first.attrs))
+
+
+def _lines_aa_where(frame, canvas, glyph, agg, line_width, dist):
+    """where(first(col) | last(col)[, other]) on antialiased lines: the selector's 2-stage combination keeps, per pixel,
+    the first / last LINE that covers it with a non-null value (nanfirst / nanlast over whole lines, compiler.py:198-268,
+    reductions.py:1906-1914, 1992-2027) - exactly the line dsb_lines_aa2's first phase votes for."""
+    sel = agg.selector
+    if not isinstance(sel, (rd.first, rd.last)):
+        raise NotImplementedError("where(max | min) is not implemented for antialiased datashader_b200 lines yet")
+    device = frame.device
+    with torch.cuda.device(device):
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+        rows, (x_range, y_range, x_st, y_st) = _lines_aa2(frame, canvas, glyph, sel, _aa2_combo(sel), line_width, dist, rows_only=True)
+        _lib.check(_lib.lib().dsb_finish_minrow(rows.data_ptr(), rows.numel(), stream_ptr), "dsb_finish_minrow")
+        if agg.column == rd.SpecialColumn.RowIndex:
+            out = rows
+        else:
+            col = frame[agg.column]
+            local = rows - frame.row_offset
+            mine = (local >= 0) & (local < len(frame)) & (rows >= 0)
+            out = torch.where(mine, col[local.clamp(0, max(len(frame) - 1, 0))].to(torch.float64), torch.zeros((), dtype=torch.float64, device=device))
+            if dist is not None:
+                out = dist.sum_bits_f64(out, rows)
+            else:
+                out = torch.where(rows >= 0, out, torch.full_like(out, float("nan")))
+        data = _to_host(out)
+    x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+    y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+    return DataArray(data, coords={glyph.y_label: y_axis, glyph.x_label: x_axis}, dims=[glyph.y_label, glyph.x_label],
+                     attrs=dict(x_range=x_range, y_range=y_range))
+
+
+def _lines_single_stage(frame, schema, canvas, glyph, agg, line_width, dist):
+    """dsb_lines_axis1[_cat]: Bresenham any / count / sum / max / min and the single-stage antialiased reductions
+    (any / count / sum / max / mean), optionally per category (by)."""
     red = agg.reduction if isinstance(agg, rd.by) else agg
     if (isinstance(red, (rd.summary, rd.by)) or getattr(red, "_line_agg", None) is None
             or (line_width > 0 and _aa2_combo(red) is not None)):
@@ -423,7 +547,7 @@ def lines(source, canvas, glyph, agg, antialias=False, dist=None):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
         x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout) = _line_setup(frame, canvas, glyph, dist)
         H, W = canvas.plot_height, canvas.plot_width
-        categorizer, ncat, labels = _categorical_setup(agg, schema)
+        categorizer, ncat, labels = _categorical_setup([agg], schema)
         codes = categorizer.codes(frame).contiguous() if ncat else None
         shape = (H, W) + ((ncat,) if ncat else ())
         ncell = int(np.prod(shape))
@@ -518,8 +642,13 @@ def _aa2_combo(agg):
     return None
 
 
-def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist):
-    """Antialiased lines, 2-stage reductions: dsb_lines_aa2 (one CTA per line, per-line max then the stage-2 fold)."""
+def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist, rows_only=False):
+    """Antialiased lines, 2-stage reductions: dsb_lines_aa2 (one CTA per line, per-line max then the stage-2 fold).
+    rows_only (first / last): return the voted global row canvas (+ ranges and scale / translate) instead of the values."""
+    if dist is not None and glyph_per_vertex(glyph):
+        # every rank holds a row shard of the SAME line(s): stage 1 (the per-line maximum coverage) would have to be
+        # combined across ranks before stage 2, which the per-rank fold cannot do
+        raise NotImplementedError("2-stage antialiased reductions over row-sharded per-vertex line glyphs (axis=0)")
     device = frame.device
     with torch.cuda.device(device):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
@@ -569,6 +698,8 @@ def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist):
             launch(1, out, rows)
             if dist is not None:
                 dist._all_reduce(rows, "min" if first else "max")
+            if rows_only:
+                return rows, (x_range, y_range, x_st, y_st)
             launch(2, out, rows)
             if dist is not None:      # exactly one rank owns each winning line: the others contribute 0 bits
                 out = dist.sum_bits_f64(torch.nan_to_num(out, nan=0.0), rows)

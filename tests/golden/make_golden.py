@@ -414,6 +414,44 @@ def lines_aa2_cases():
     return out
 
 
+def lines_aa3_cases():
+    """Antialiased lines, composite aggregations (compiler.py:539-554: one 2-stage reduction forces count / sum of the
+    whole summary to self_intersect=False; reductions.py:782-787: by() over a 2-stage reduction; :1906-1914: where())
+    on the 40-line f32 frame of lines.npz with the categories of lines_extra.npz."""
+    out = {}
+    xs, ys, val = line_frame(2024, 40, 24, np.float32)
+    nverts = xs.shape[1]
+    codes = np.load(os.path.join(HERE, "lines_extra.npz"))["in_cat"]
+    other = np.random.default_rng(77).random(len(val)).astype(np.float32) * 50 - 10
+    other[7] = np.nan
+    out["in_other"] = other
+    d = {f"x{j}": xs[:, j] for j in range(nverts)}
+    d.update({f"y{j}": ys[:, j] for j in range(nverts)})
+    d["val"], d["other"] = val, other
+    d["cat"] = pd.Categorical.from_codes(codes, categories=["a", "b", "c", "d"])
+    df = pd.DataFrame(d)
+    xcols, ycols = [f"x{j}" for j in range(nverts)], [f"y{j}" for j in range(nverts)]
+    cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+    kw = dict(x=xcols, y=ycols, axis=1, line_width=2)
+    summaries = {
+        "s1": ds.summary(count=ds.count("val"), min=ds.min("val")),                       # min forces count to self_intersect=False
+        "s2": ds.summary(count=ds.count("val", self_intersect=True), sum=ds.sum("val", self_intersect=True)),
+        "s3": ds.summary(cnt=ds.count(), mx=ds.max("val"), first=ds.first("val"), anyv=ds.any()),
+        "s4": ds.summary(count=ds.count(self_intersect=True), sum=ds.sum("val", self_intersect=False)),
+    }
+    for sname, agg in summaries.items():
+        res = cvs.line(df, agg=agg, **kw)
+        for k in agg.keys:
+            out[f"aa3_{sname}_{k}"] = np.asarray(res[k].data)
+    for aname, inner in {"min": ds.min("val"), "first": ds.first("val"), "last": ds.last("val"),
+                         "sum_nsi": ds.sum("val", self_intersect=False), "count_nsi": ds.count(self_intersect=False)}.items():
+        out[f"aa3_by_{aname}"] = np.asarray(cvs.line(df, agg=ds.by("cat", inner), **kw).data)
+    for aname, agg in {"where_first_row": ds.where(ds.first("val")), "where_first_other": ds.where(ds.first("val"), "other"),
+                       "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other")}.items():
+        out[f"aa3_{aname}"] = np.asarray(cvs.line(df, agg=agg, **kw).data)
+    return out
+
+
 def spread_cases():
     """Post-shade image ops straight from the reference's kernels (composite.py; transfer_functions/__init__.py:748-1051)."""
     from datashader import composite as comp
@@ -565,6 +603,10 @@ def negzero_cases():
 
 
 def main():
+    if "--lines-aa3-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "lines_aa3.npz"), **lines_aa3_cases())
+        print("lines_aa3.npz", os.path.getsize(os.path.join(HERE, "lines_aa3.npz")) // 1024, "KiB")
+        return
     if "--negzero-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "points_negzero.npz"), **negzero_cases())
         print("points_negzero.npz", os.path.getsize(os.path.join(HERE, "points_negzero.npz")) // 1024, "KiB")
@@ -602,6 +644,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
     np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
     np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
+    np.savez_compressed(os.path.join(HERE, "lines_aa3.npz"), **lines_aa3_cases())
     np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
     np.savez_compressed(os.path.join(HERE, "shade_span.npz"), **shade_span_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())

@@ -259,4 +259,38 @@ def test_lines_aa_by_category_golden():
         assert tuple(r.dims) == ("y", "x", "cat") and list(r.coords["cat"]) == ["a", "b", "c", "d"], aname
         _cmp_aa(r.data, want, f"aa by {aname}")
     with pytest.raises(NotImplementedError):
-        cvs.line(frame, x=xcols, y=ycols, axis=1, agg=ds.by("cat", ds.min("val")), line_width=2)
+        cvs.line(frame, x=xcols, y=ycols, axis=1, agg=ds.by("cat", ds.where(ds.first("val"))), line_width=2)
+
+
+def test_lines_antialiased_summary_by_where_golden():
+    """Composite antialiased aggregations vs the real reference (tests/golden/lines_aa3.npz): summary() where one 2-stage
+    reduction forces every count / sum to self_intersect=False (compiler.py:539-554, test_pandas.py:2803
+    TestLineAntialiasSummary), by() over 2-stage reductions (reductions.py:782-787) and where(first | last)
+    (test_pandas.py:3079 TestLineAntialiasWhere)."""
+    import pandas as pd
+    import datashader_b200 as ds
+    g, gl, ge = load("lines_aa3.npz"), load("lines.npz"), load("lines_extra.npz")
+    frame, xcols, ycols = _frame(gl["in_f32_xs"], gl["in_f32_ys"], gl["in_f32_val"])
+    frame["other"] = g["in_other"]
+    frame["cat"] = pd.Categorical.from_codes(ge["in_cat"], categories=["a", "b", "c", "d"])
+    cvs = ds.Canvas(plot_width=64, plot_height=48, x_range=(0, 1), y_range=(0, 1))
+    kw = dict(x=xcols, y=ycols, axis=1, line_width=2)
+    summaries = {
+        "s1": ds.summary(count=ds.count("val"), min=ds.min("val")),
+        "s2": ds.summary(count=ds.count("val", self_intersect=True), sum=ds.sum("val", self_intersect=True)),
+        "s3": ds.summary(cnt=ds.count(), mx=ds.max("val"), first=ds.first("val"), anyv=ds.any()),
+        "s4": ds.summary(count=ds.count(self_intersect=True), sum=ds.sum("val", self_intersect=False)),
+    }
+    for sname, agg in summaries.items():
+        res = cvs.line(frame, agg=agg, **kw)
+        for k in agg.keys:
+            _cmp_aa(res[k].data, g[f"aa3_{sname}_{k}"], f"summary {sname}.{k}")
+    for aname, inner in {"min": ds.min("val"), "first": ds.first("val"), "last": ds.last("val"),
+                         "sum_nsi": ds.sum("val", self_intersect=False), "count_nsi": ds.count(self_intersect=False)}.items():
+        r = cvs.line(frame, agg=ds.by("cat", inner), **kw)
+        assert tuple(r.dims) == ("y", "x", "cat") and list(r.coords["cat"]) == ["a", "b", "c", "d"], aname
+        _cmp_aa(r.data, g[f"aa3_by_{aname}"], f"aa by {aname}")
+    for aname, agg in {"where_first_row": ds.where(ds.first("val")), "where_first_other": ds.where(ds.first("val"), "other"),
+                       "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other")}.items():
+        got, want = cvs.line(frame, agg=agg, **kw).data, g[f"aa3_{aname}"]
+        assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), aname

@@ -528,3 +528,20 @@ def test_large_result_leaves_through_the_staging_ring(ds):
     assert isinstance(host, np.ndarray) and host.dtype == np.float64 and host.shape == (4100, 4200)
     assert np.array_equal(host, dev.cpu().numpy(), equal_nan=True)
     assert int((~np.isnan(host)).sum()) > 0
+
+
+def test_summary_mixes_categorical_and_plain_reductions(ds):
+    """summary() composes any bases (compiler.py:103-107, reductions.py:2169-2246): by() and plain reductions in one call."""
+    from oracle import oracle as ora
+    g = load("points.npz")
+    cols = columns_from_golden(g, "in_f32_")
+    df = pandas_frame(cols)
+    ckw = CANVASES["c37x23"]
+    cvs = ds.Canvas(**ckw)
+    agg = cvs.points(df, "x", "y", ds.summary(cats=ds.by("cat", ds.count()), n=ds.count(), m=ds.mean("v32"),
+                                              catmax=ds.by("cat", ds.max("v32"))))
+    assert_agg_equal(agg["cats"].data, g["pts_f32_c37x23_by_count"], "summary by_count")
+    assert_agg_equal(agg["n"].data, g["pts_f32_c37x23_count"], "summary count")
+    assert_agg_equal(agg["m"].data, g["pts_f32_c37x23_mean_v32"], "summary mean_v32")
+    assert_agg_equal(agg["catmax"].data, g["pts_f32_c37x23_by_max_v32"], "summary by_max_v32")
+    assert tuple(agg["cats"].dims) == ("y", "x", "cat") and tuple(agg["n"].dims) == ("y", "x")

@@ -35,7 +35,8 @@ def _cols(rng, n, clustered=False):
     else:
         x = (rng.random(n) * 1.2 - 0.1).astype(np.float32)
         y = (rng.random(n) * 1.2 - 0.1).astype(np.float32)
-    cols = {"x": x, "y": y, "v32": np.round(rng.standard_normal(n), 1).astype(np.float32), "other": rng.random(n).astype(np.float32)}
+    cols = {"x": x, "y": y, "v32": (np.round(rng.standard_normal(n), 1) + 0.0).astype(np.float32), "other": rng.random(n).astype(np.float32)}
+    assert not np.signbit(cols["v32"][cols["v32"] == 0]).any()     # no -0.0: the routed pass is the last aggregation kernel
     cols["v32"][rng.integers(0, n, n // 40)] = np.nan
     cols["x"][:3] = [0.0, 1.0, np.nan]
     cols["y"][:3] = [1.0, 0.0, 0.5]
