@@ -442,11 +442,11 @@ class Bench:
 
         sampler = ClockSampler(self.local_rank)
         if rank == 0:
-            sampler.start()
+            sampler.start()                        # clocks / throttle reasons over both timed regions (count, then mean)
         head = self.timed(lambda: cvs.points(frame, "x", "y", ds.count()), args.steps, args.warmup)
+        mean = self.timed(lambda: cvs.points(frame, "x", "y", ds.mean("value")), args.steps, args.warmup)
         clocks = sampler.stop() if rank == 0 else None
         count_total = int(head["out"].data.view(torch.int32).to(torch.int64).sum().item())
-        mean = self.timed(lambda: cvs.points(frame, "x", "y", ds.mean("value")), args.steps, args.warmup)
         mean_checksum = float(torch.nan_to_num(mean["out"].data.double()).sum().item())
 
         strong = None

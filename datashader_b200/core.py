@@ -116,6 +116,18 @@ class Canvas:
         glyph = Point(x, y)
         return bypixel(source, self, glyph, agg)
 
+    def points_batch(self, source, x, y, agg=None, views=(), grid=None):
+        """Canvas.points for many views of this canvas' size in ONE pass over the data: the batched-viewport form of the
+        re-aggregation loops above the hot path (tiles.py:70-131 renders every zoom level tile by tile, pipeline.py:55-72
+        re-aggregates on every zoom / pan).  views: [(x_range, y_range), ...]; grid=(nx, ny) when they form a row-major
+        tile grid.  Returns a list with, per view, exactly what Canvas(w, h, x_range, y_range).points(...) returns."""
+        from . import pipeline
+        from .distributed import current_group
+        validate_xy_or_geometry('Point', x, y, None)
+        if agg is None:
+            agg = rd.count()
+        return pipeline.points_batch(source, self, Point(x, y), agg, views, grid=grid, dist=current_group(source))
+
     # ---------------------------------------------------------------------------- lines
     def line(self, source, x=None, y=None, agg=None, axis=0, geometry=None, line_width=0, antialias=False):
         """Compute a reduction by pixel, mapping data to pixels as one or more lines (core.py:234-478)."""

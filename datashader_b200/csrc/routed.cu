@@ -4,7 +4,7 @@
 // dsb_points L2-bands such canvases: the columns are re-read once per band (5 passes = 60 B / point at 8192^2) and every
 // hit is still a global RED.  Here the points are routed instead (profiles/r02_routed.md):
 //
-//   sample   every 64th vector of x / y is mapped and histogrammed per BUCKET (a contiguous range of <= 45 056 canvas
+//   sample   every 64th block of 1024 points is mapped and histogrammed per BUCKET (a contiguous range of <= 45 056 canvas
 //            cells); a one-CTA planning kernel turns the estimate into per-bucket record capacities and offsets
 //   pass 1   every CTA maps a tile of points (float32 fast mapping, exact f64 mapping for points near a pixel edge),
 //            counting-sorts the tile by bucket in shared memory and appends each bucket's run to its region as coalesced
@@ -37,6 +37,8 @@ struct RouteArgs {
   const uint32_t* cap;                  // [nb]
   uint32_t* cursor;                     // [nb] records offered so far (beyond cap: applied to the canvas directly)
   uint32_t* queue;                      // pass 2: next bucket to hand out
+  uint32_t* slow; uint32_t* slow_n;     // rows whose fast pixel is not certain (near a pixel edge): mapped exactly by k_route_slow
+  uint32_t slow_cap;
   void* canvas;
   unsigned int* notes;
 };
@@ -59,15 +61,18 @@ __device__ __forceinline__ void route_direct(const RouteArgs& a, uint32_t cell, 
 }
 
 // ---- sample + plan ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_route_sample(const RouteArgs a, long long stride4, uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(256) k_route_sample(const RouteArgs a, long long stride_blocks, uint32_t* __restrict__ hist) {
+  // every stride_blocks-th block of 256 vectors (4 KB per column, fully used sectors) is mapped and histogrammed
   extern __shared__ uint32_t sh[];
   for (uint32_t b = threadIdx.x; b < a.nb; b += blockDim.x) sh[b] = 0;
   __syncthreads();
   const float4* __restrict__ x4 = (const float4*)a.x;
   const float4* __restrict__ y4 = (const float4*)a.y;
   const long long n4 = a.n >> 2;
-  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s * stride4 < n4; s += (long long)gridDim.x * blockDim.x) {
-    const float4 xa = __ldg(x4 + s * stride4), ya = __ldg(y4 + s * stride4);
+  for (long long blk = blockIdx.x; blk * stride_blocks * 256 < n4; blk += gridDim.x) {
+    const long long i4 = blk * stride_blocks * 256 + threadIdx.x;
+    if (i4 >= n4) continue;
+    const float4 xa = __ldg(x4 + i4), ya = __ldg(y4 + i4);
     const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(256) k_route_sample(const RouteArgs a, long lo
 // small - the overflow path keeps the result exact), exclusive scan -> offsets; cursors and the queue are cleared
 __global__ void __launch_bounds__(1024) k_route_plan(const uint32_t* __restrict__ hist, uint32_t nb, uint32_t stride_pts, unsigned long long capacity,
                                                      unsigned long long* __restrict__ off, uint32_t* __restrict__ cap,
-                                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ queue) {
+                                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ queue, uint32_t* __restrict__ slow_n) {
   __shared__ unsigned long long part[1024];
   __shared__ double scale_sh;
   const int tid = threadIdx.x;
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(1024) k_route_plan(const uint32_t* __restrict_
   }
   __syncthreads();
   const double scale = scale_sh;
-  unsigned long long run = (unsigned long long)((double)part[tid] * scale) & ~1ull;
+  unsigned long long run = ((unsigned long long)((double)part[tid] * scale) + 3) & ~1ull;     // rounded UP: regions never overlap
   for (uint32_t b = lo; b < hi; b++) {
     unsigned long long c = want(b);
     if (scale < 1.0) c = (unsigned long long)((double)c * scale) & ~1ull;
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(1024) k_route_plan(const uint32_t* __restrict_
     off[b] = run; cap[b] = (uint32_t)c; cursor[b] = 0;
     run += c;
   }
-  if (tid == 0) *queue = 0;
+  if (tid == 0) { *queue = 0; *slow_n = 0; }
 }
 
 // ---- pass 1 ----------------------------------------------------------------------------------------------------------
@@ -158,7 +163,11 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
         const bool sure = dx >= a.fm.ex && dx <= a.fm.omex && dy >= a.fm.ey && dy <= a.fm.omey;
         int cell = (sure && (uint32_t)xi < W && (uint32_t)yi < H) ? yi * (int)W + xi : -1;
         const bool live = vs[k] == vs[k];                      // NaN rows are skipped by every op
-        if (!sure && live) cell = map_exact_linear(a.v, xs[k], ys[k]);
+        if (!sure && live && i4 < n4) {                        // ~0.1 % of the points: left to k_route_slow
+          const uint32_t pos = atomicAdd(a.slow_n, 1u);
+          if (pos < a.slow_cap) a.slow[pos] = (uint32_t)(4 * i4 + k);
+          else cell = map_exact_linear(a.v, xs[k], ys[k]);    // list full (adversarial data): map it here
+        }
         const bool ok = live && cell >= 0;
         const uint32_t kk = ok ? route_key(a, (uint32_t)cell) : 0xffffffffu;
         key[u * 4 + k] = kk;
@@ -235,6 +244,22 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
   if ((OP == R_MAX32 || OP == R_MIN32) && negzero && a.notes) *a.notes = DSB_NOTE_NEGZERO;
 }
 
+// the rows pass 1 could not place with the float32 mapping: exact f64 mapping, straight to the canvas
+template <int OP>
+__global__ void __launch_bounds__(256) k_route_slow(const __grid_constant__ RouteArgs a) {
+  const uint32_t n = min(*a.slow_n, a.slow_cap);
+  bool negzero = false;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t i = a.slow[j];
+    const float vv = a.vcol ? a.vcol[i] : 1.f;
+    const int cell = map_exact_linear(a.v, a.x[i], a.y[i]);
+    if (cell < 0) continue;
+    if (OP == R_MAX32 || OP == R_MIN32) { negzero |= is_negzero(vv); route_direct<OP>(a, (uint32_t)cell, __float_as_uint(vv)); }
+    else route_direct<OP>(a, (uint32_t)cell, i);
+  }
+  if ((OP == R_MAX32 || OP == R_MIN32) && negzero && a.notes) *a.notes = DSB_NOTE_NEGZERO;
+}
+
 // ---- pass 2 ----------------------------------------------------------------------------------------------------------
 template <int OP>
 __global__ void __launch_bounds__(1024, 1) k_route_eat(const __grid_constant__ RouteArgs a) {
@@ -294,13 +319,15 @@ static uint32_t route_nb(long long ncell, uint32_t* cpb) {
   return (uint32_t)nb;
 }
 static size_t route_header_bytes(uint32_t nb) { return (((size_t)nb * (8 + 4 + 4 + 4) + 64) + 255) & ~(size_t)255; }
+static size_t route_slow_entries(int64_t n) { return (size_t)(n / 16) + 65536; }        // ~6 % of the rows (typical: 0.1 %)
+static size_t route_fixed_bytes(uint32_t nb, int64_t n) { return route_header_bytes(nb) + ((route_slow_entries(n) * 4 + 255) & ~(size_t)255); }
 
 extern "C" int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t n) {
   if (!view || view->width <= 0 || view->height <= 0 || n < 0) return 0;
   uint32_t cpb;
   const uint32_t nb = route_nb((long long)view->width * view->height, &cpb);
   // records: 1.10 n + 4096 per bucket (k_route_plan scales the capacities down to whatever it is given)
-  return (int64_t)(route_header_bytes(nb) + ((size_t)((double)n * 1.10) + (size_t)nb * 4096) * 8);
+  return (int64_t)(route_fixed_bytes(nb, n) + ((size_t)((double)n * 1.10) + (size_t)nb * 4096) * 8);
 }
 
 template <int OP>
@@ -308,6 +335,7 @@ static void route_launch(const RouteArgs& a, size_t smem1, size_t smem2, cudaStr
   cudaFuncSetAttribute(k_route_bin<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   cudaFuncSetAttribute(k_route_eat<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   k_route_bin<OP><<<dsb_num_sms() * 2, RT, smem1, s>>>(a);
+  k_route_slow<OP><<<dsb_num_sms() * 2, 256, 0, s>>>(a);
   k_route_eat<OP><<<dsb_num_sms(), 1024, smem2, s>>>(a);
 }
 
@@ -346,7 +374,7 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   a.nb = route_nb(ncell, &a.cpb);
   a.inv = (uint32_t)((1ull << 32) / a.cpb);
   a.ncell = (uint32_t)ncell;
-  const size_t hdr = route_header_bytes(a.nb);
+  const size_t hdr = route_fixed_bytes(a.nb, n);
   if (a.nb > 65535 || scratch_bytes < (int64_t)(hdr + ((size_t)a.nb * 4096 + 1024) * 8)) { dsb_set_error("dsb_points_routed: scratch too small"); return DSB_ERR_ARG; }
   unsigned char* p = (unsigned char*)scratch;
   unsigned long long* off = (unsigned long long*)p;
@@ -354,14 +382,17 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   uint32_t* cursor = cap + a.nb;
   uint32_t* hist = cursor + a.nb;
   uint32_t* queue = hist + a.nb;
+  a.slow_n = queue + 1;
+  a.slow = (uint32_t*)(p + route_header_bytes(a.nb));
+  a.slow_cap = (uint32_t)route_slow_entries(n);
   a.recs = (unsigned long long*)(p + hdr);
   a.off = off; a.cap = cap; a.cursor = cursor; a.queue = queue; a.canvas = b.agg; a.notes = plan->notes;
-  const unsigned long long capacity = ((unsigned long long)scratch_bytes - hdr) / 8;
+  const unsigned long long capacity = ((unsigned long long)scratch_bytes - hdr) / 8 - 4096;   // k_route_plan rounds every thread's start up
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(hist, 0, (size_t)a.nb * 4, s);
-  const long long stride4 = n >= (1LL << 28) ? 16 : 4;          // every 64th (16th) point is sampled
-  k_route_sample<<<dsb_num_sms() * 4, 256, (size_t)a.nb * 4, s>>>(a, stride4, hist);
-  k_route_plan<<<1, 1024, 0, s>>>(hist, a.nb, (uint32_t)stride4, capacity, off, cap, cursor, queue);
+  const long long stride_blocks = n >= (1LL << 28) ? 64 : 16;   // every 64th (16th) block of 1024 points is sampled
+  k_route_sample<<<dsb_num_sms() * 4, 256, (size_t)a.nb * 4, s>>>(a, stride_blocks, hist);
+  k_route_plan<<<1, 1024, 0, s>>>(hist, a.nb, (uint32_t)stride_blocks, capacity, off, cap, cursor, queue, a.slow_n);
   const uint32_t nbp = (a.nb + 1) & ~1u;
   const size_t smem1 = (size_t)RTILE * 8 + (size_t)nbp * (8 + 4 + 4 + 4) + 64 * 4;
   const size_t smem2 = (size_t)a.cpb * 4;

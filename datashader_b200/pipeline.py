@@ -287,7 +287,8 @@ def _accumulate_group(frame, resident, needed, schema, view, canvas, glyph, reds
     stream_ptr = torch.cuda.current_stream(device).cuda_stream
     single = resident is not None
     categorizer, ncat, labels = _categorical_setup(reds, schema)
-    shape = (canvas.plot_height, canvas.plot_width) + ((ncat,) if ncat else ())
+    nviews = (ctx_extra or {}).get("nviews")          # points_batch: canvases stacked [V, H, W(, C)]
+    shape = ((nviews,) if nviews else ()) + (canvas.plot_height, canvas.plot_width) + ((ncat,) if ncat else ())
     ctx = _Ctx(frame, view, shape, dist)
     if single:
         ctx.resident = resident
@@ -368,6 +369,56 @@ def points(source, canvas, glyph: Point, agg, dist=None):
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)
+
+
+def points_batch(source, canvas, glyph: Point, agg, views, grid=None, dist=None):
+    """Canvas.points for several views at once: ONE pass over the columns fills a canvas per view (dsb_points_views).
+    views: [(x_range, y_range), ...]; grid=(nx, ny) declares them a row-major nx x ny grid of equal extents (a tile level),
+    otherwise at most 64 arbitrary views.  Returns one DataArray / Dataset per view, each identical to what
+    Canvas(..., x_range, y_range).points(source, ...) returns for that view."""
+    needed, frame, schema = _prepare(source, glyph, agg, canvas)
+    views = [(tuple(map(float, xr)), tuple(map(float, yr))) for xr, yr in views]
+    nv = len(views)
+    if nv == 0:
+        return []
+    gx = (0, 0, 0.0, 0.0, 1.0, 1.0)
+    if grid is not None:
+        nx, ny = int(grid[0]), int(grid[1])
+        if nx * ny != nv:
+            raise ValueError("grid=(nx, ny) must describe len(views) views")
+        (x0, x1), (y0, y1) = views[0]
+        gx = (nx, ny, x0, y0, x1 - x0, y1 - y0)
+    elif nv > 64:
+        raise ValueError("more than 64 views need grid=(nx, ny)")
+    device = frame.device
+    with torch.cuda.device(device):
+        single = frame.n_chunks() == 1
+        resident = frame.resident(needed) if single else None
+        vstructs, sts = [], []
+        for xr, yr in views:
+            canvas.validate_ranges(xr, yr)
+            v, x_st, y_st = make_view(canvas, xr, yr)
+            vstructs.append(v)
+            sts.append((x_st, y_st))
+        varr = (_lib.View * nv)(*vstructs)
+        dev_views = torch.frombuffer(bytearray(bytes(varr)), dtype=torch.uint8).to(device)
+
+        def launch(view, chunk, glyph_, accs, canv, ctx, categorizer, ncat):
+            x, y, xy_dtype = _xy_columns(chunk, glyph_.x, glyph_.y)
+            cells = int(canvas.plot_height) * int(canvas.plot_width) * max(ncat, 1)
+            for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
+                _lib.check(_lib.lib().dsb_points_views(dev_views.data_ptr(), nv, gx[0], gx[1], gx[2], gx[3], gx[4], gx[5],
+                                                       x.data_ptr(), y.data_ptr(), xy_dtype, len(chunk), chunk.row_offset,
+                                                       C.byref(plan), cells, ctx.stream_ptr), "dsb_points_views")
+
+        reds, results, labels = _accumulate_and_finalize(frame, resident, needed, schema, vstructs[0], canvas, glyph, agg, dist,
+                                                         launch, ctx_extra={"nviews": nv})
+    out = []
+    for k, ((xr, yr), (x_st, y_st)) in enumerate(zip(views, sts)):
+        x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+        y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+        out.append(_wrap(agg, reds, [t[k] for t in results], glyph, x_axis, y_axis, xr, yr, labels))
+    return out
 
 
 def _merge_bounds(parts, dist, device):
@@ -576,12 +627,19 @@ def _lines_single_stage(frame, schema, canvas, glyph, agg, line_width, dist):
             canvas_t = torch.empty(shape, dtype=torch.int64, device=device)
             _lib.check(lib.dsb_init_canvas(_lib.OP_MAX64 if la == _lib.LINE_MAX else _lib.OP_MIN64, canvas_t.data_ptr(),
                                            ncell, stream_ptr))
+        if config.time_kernels:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         _lib.check(lib.dsb_lines_axis1_cat(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, nlines, nverts, C.byref(layout),
                                            val.data_ptr() if val is not None else None, val_dtype, la, line_width,
                                            canvas_t.data_ptr(), mask.data_ptr() if mask is not None else None,
                                            codes.data_ptr() if ncat else None,
                                            _lib.dsb_dtype(str(codes.dtype).replace("torch.", "")) if ncat else _lib.NONE, ncat,
                                            stream_ptr), "dsb_lines_axis1_cat")
+        if config.time_kernels:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            config.kernel_events.append((ev0, ev1))
         if dist is not None:
             if la == _lib.LINE_MEAN:
                 dist._all_reduce(canvas_t, "sum")

@@ -144,6 +144,16 @@ int dsb_points_routed(const dsb_view* view, const void* x, const void* y, int32_
 /* smallest n dsb_points_routed accepts (default 2^24; tests lower it) */
 int dsb_routed_configure(int64_t min_rows);
 
+/* Batched viewports: the same contract as dsb_points for `nviews` views of identical canvas size at once, in ONE pass
+ * over the columns (a zoom level of a tile pyramid, tiles.py:70-131; the viewports of an interaction, pipeline.py:55-72).
+ * views: DEVICE array of dsb_view.  The plan's canvases are stacked [nviews, H, W(, ncat)], view_cells = H * W * max(ncat, 1);
+ * every view keeps its own scale / translate / bounds, so each canvas equals the one dsb_points produces for that view.
+ * grid_nx > 0: the views form a row-major grid_nx x grid_ny grid of equal extents (gtw x gth) starting at (gx0, gy0) and a
+ * point is tested against its grid cell and the eight neighbours only; grid_nx == 0: at most 64 arbitrary views, all tested. */
+int dsb_points_views(const dsb_view* views, int32_t nviews, int32_t grid_nx, int32_t grid_ny, double gx0, double gy0,
+                     double gtw, double gth, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                     const dsb_plan* plan, int64_t view_cells, void* stream);
+
 /* NaN-skipping min/max of a column: Glyph._compute_bounds_numba (glyphs/glyph.py:66-78).
  * out_minmax: 2 doubles on the device, (+inf, -inf) when no finite-or-inf value exists. */
 int dsb_bounds(const void* col, int32_t dtype, int64_t n, double* out_minmax, void* stream);

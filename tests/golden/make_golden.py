@@ -452,6 +452,28 @@ def lines_aa3_cases():
     return out
 
 
+def tiles_cases():
+    """Tile arithmetic of the reference's pyramid driver (tiles.py:99-117, 138-300): super tiles and 256-pixel tiles of a
+    few extents and zoom levels, flattened to (tx, ty, level, xmin, ymin, xmax, ymax) rows."""
+    from datashader.tiles import MercatorTileDefinition, gen_super_tiles
+    out = {}
+    extents = {"world": (-20037508.34, -20037508.34, 20037508.34, 20037508.34),
+               "nyc": (-8242000.0, 4965000.0, -8210000.0, 4990000.0),
+               "odd": (-1234567.8, 2345678.9, 3456789.1, 4567890.2)}
+    for name, ext in extents.items():
+        out[f"extent_{name}"] = np.array(ext)
+        for level in (0, 1, 3, 5, 9):
+            if name == "world" and level > 5:
+                continue
+            td = MercatorTileDefinition(x_range=(ext[0], ext[2]), y_range=(ext[1], ext[3]), tile_size=256)
+            tiles = td.get_tiles_by_extent(ext, level)
+            out[f"tiles_{name}_{level}"] = np.array([[t[0], t[1], t[2], *t[3]] for t in tiles], dtype=np.float64).reshape(-1, 7)
+            sup = list(gen_super_tiles(ext, level))
+            out[f"super_{name}_{level}"] = np.array([[s["level"], s["tile_size"], *s["x_range"], *s["y_range"]] for s in sup],
+                                                    dtype=np.float64).reshape(-1, 6)
+    return out
+
+
 def spread_cases():
     """Post-shade image ops straight from the reference's kernels (composite.py; transfer_functions/__init__.py:748-1051)."""
     from datashader import composite as comp
@@ -607,6 +629,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "lines_aa3.npz"), **lines_aa3_cases())
         print("lines_aa3.npz", os.path.getsize(os.path.join(HERE, "lines_aa3.npz")) // 1024, "KiB")
         return
+    if "--tiles-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "tiles.npz"), **tiles_cases())
+        print("tiles.npz", os.path.getsize(os.path.join(HERE, "tiles.npz")) // 1024, "KiB")
+        return
     if "--negzero-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "points_negzero.npz"), **negzero_cases())
         print("points_negzero.npz", os.path.getsize(os.path.join(HERE, "points_negzero.npz")) // 1024, "KiB")
@@ -645,6 +671,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
     np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
     np.savez_compressed(os.path.join(HERE, "lines_aa3.npz"), **lines_aa3_cases())
+    np.savez_compressed(os.path.join(HERE, "tiles.npz"), **tiles_cases())
     np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
     np.savez_compressed(os.path.join(HERE, "shade_span.npz"), **shade_span_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
