@@ -128,11 +128,10 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t nbp = (a.nb + 1) & ~1u;
   unsigned long long* rec = (unsigned long long*)smem;                 // [RTILE]
-  unsigned long long* s_off = rec + RTILE;                             // [nbp] global offset of this tile's run minus base
-  uint32_t* hist = (uint32_t*)(s_off + nbp);                           // [nbp]
-  uint32_t* base = hist + nbp;                                         // [nbp]
-  uint32_t* room = base + nbp;                                         // [nbp] records of this tile's run that fit the region
-  uint32_t* wsum = room + nbp;                                         // [64]
+  uint4* run_of = (uint4*)(rec + RTILE);                               // [nbp] per bucket: {global offset of this tile's run
+                                                                       //   minus base (lo, hi), base, records that fit}
+  uint32_t* hist = (uint32_t*)(run_of + nbp);                          // [nbp]
+  uint32_t* wsum = hist + nbp;                                         // [64]
   const int tid = threadIdx.x;
   const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
   const float4* __restrict__ x4 = (const float4*)a.x;
@@ -146,6 +145,7 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
 
   for (long long t4 = (long long)blockIdx.x * TILE4; t4 < n4; t4 += (long long)gridDim.x * TILE4) {
     uint32_t key[RPPT], rank[RPPT], pay[RPPT];
+    uint32_t unsure = 0;                                         // bit u * 4 + k: that point is left to k_route_slow
 #pragma unroll
     for (int u = 0; u < RPPT / 4; u++) {
       const long long i4 = t4 + (long long)u * RT + tid;
@@ -161,19 +161,29 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
         const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
         const float dx = xf - (float)xi, dy = yf - (float)yi;
         const bool sure = dx >= a.fm.ex && dx <= a.fm.omex && dy >= a.fm.ey && dy <= a.fm.omey;
-        int cell = (sure && (uint32_t)xi < W && (uint32_t)yi < H) ? yi * (int)W + xi : -1;
+        const int cell = (sure && (uint32_t)xi < W && (uint32_t)yi < H) ? yi * (int)W + xi : -1;
         const bool live = vs[k] == vs[k];                      // NaN rows are skipped by every op
-        if (!sure && live && i4 < n4) {                        // ~0.1 % of the points: left to k_route_slow
-          const uint32_t pos = atomicAdd(a.slow_n, 1u);
-          if (pos < a.slow_cap) a.slow[pos] = (uint32_t)(4 * i4 + k);
-          else cell = map_exact_linear(a.v, xs[k], ys[k]);    // list full (adversarial data): map it here
-        }
+        unsure |= (uint32_t)(!sure && live && i4 < n4) << (u * 4 + k);      // ~0.1 % of the points
         const bool ok = live && cell >= 0;
         const uint32_t kk = ok ? route_key(a, (uint32_t)cell) : 0xffffffffu;
         key[u * 4 + k] = kk;
         if (OP == R_MAX32 || OP == R_MIN32) { pay[u * 4 + k] = __float_as_uint(vs[k]); negzero |= ok && is_negzero(vs[k]); }
         else pay[u * 4 + k] = (uint32_t)(4 * i4 + k);          // the row within this call (n < 2^32)
         rank[u * 4 + k] = ok ? atomicAdd(hist + (kk >> 16), 1u) : 0u;
+      }
+    }
+    if (unsure) {                                              // out of the unrolled body: queue the rows for k_route_slow
+      for (int j = 0; j < RPPT; j++) {
+        if (!(unsure >> j & 1)) continue;
+        const uint32_t row = (uint32_t)(4 * (t4 + (long long)(j >> 2) * RT + tid) + (j & 3));
+        const uint32_t pos = atomicAdd(a.slow_n, 1u);
+        if (pos < a.slow_cap) a.slow[pos] = row;
+        else {                                                 // list full (adversarial data): map it here, straight to the canvas
+          const float vv = a.vcol ? a.vcol[row] : 1.f;
+          const int cell = map_exact_linear(a.v, a.x[row], a.y[row]);
+          if (cell >= 0) route_direct<OP>(a, (uint32_t)cell, (OP == R_MAX32 || OP == R_MIN32) ? __float_as_uint(vv) : row);
+          if (OP == R_MAX32 || OP == R_MIN32) negzero |= cell >= 0 && is_negzero(vv);
+        }
       }
     }
     __syncthreads();
@@ -198,13 +208,14 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
     uint32_t run = wsum[32 + (tid >> 5)] + incl - mine;
     for (uint32_t b = lo; b < hi; b++) {
       const uint32_t h = hist[b];
-      base[b] = run;
+      uint4 r = make_uint4(0u, 0u, run, 0u);
       if (h) {
         const uint32_t g = atomicAdd(a.cursor + b, h);         // one global atomic per non-empty bucket per tile
         const uint32_t c = a.cap[b];
-        room[b] = g >= c ? 0u : min(h, c - g);
-        s_off[b] = a.off[b] + g - run;
-      } else room[b] = 0;
+        const unsigned long long o = a.off[b] + g - run;
+        r.x = (uint32_t)o; r.y = (uint32_t)(o >> 32); r.w = g >= c ? 0u : min(h, c - g);
+      }
+      run_of[b] = r;
       hist[b] = 0;                                             // ready for the next tile
       run += h;
     }
@@ -212,7 +223,7 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < RPPT; k++)
-      if (key[k] != 0xffffffffu) rec[base[key[k] >> 16] + rank[k]] = ((unsigned long long)pay[k] << 32) | key[k];
+      if (key[k] != 0xffffffffu) rec[run_of[key[k] >> 16].z + rank[k]] = ((unsigned long long)pay[k] << 32) | key[k];
     __syncthreads();
     const uint32_t total = wsum[31];
 #pragma unroll
@@ -225,7 +236,8 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
         const uint32_t q = (u + k) * RT + tid;
         if (q >= total) continue;
         const uint32_t b = ((uint32_t)rr[k]) >> 16;
-        if (q - base[b] < room[b]) a.recs[s_off[b] + q] = rr[k];
+        const uint4 r = run_of[b];
+        if (q - r.z < r.w) a.recs[(((unsigned long long)r.y << 32) | r.x) + q] = rr[k];
         else route_direct<OP>(a, b * a.cpb + ((uint32_t)rr[k] & 0xffffu), (uint32_t)(rr[k] >> 32));   // the region is full
       }
     }
@@ -394,7 +406,7 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   k_route_sample<<<dsb_num_sms() * 4, 256, (size_t)a.nb * 4, s>>>(a, stride_blocks, hist);
   k_route_plan<<<1, 1024, 0, s>>>(hist, a.nb, (uint32_t)stride_blocks, capacity, off, cap, cursor, queue, a.slow_n);
   const uint32_t nbp = (a.nb + 1) & ~1u;
-  const size_t smem1 = (size_t)RTILE * 8 + (size_t)nbp * (8 + 4 + 4 + 4) + 64 * 4;
+  const size_t smem1 = (size_t)RTILE * 8 + (size_t)nbp * (16 + 4) + 64 * 4;
   const size_t smem2 = (size_t)a.cpb * 4;
   static const char* const names[] = {"max32", "min32", "minrow", "maxrow", "count"};
   dsb_note_kernel("k_route_bin<%s> + k_route_eat<%s> buckets=%u", names[op], names[op], a.nb);
