@@ -100,8 +100,23 @@ __device__ __forceinline__ bool dtype_is_key32(int dt) {
 // FMA for x*sx+tx; nvcc would contract it, hence the explicit _rn intrinsics), truncating cast,
 // and the upper-edge fold.  LogAxis.mapper = log10(float(val)) (core.py:129-132): under numba a
 // float32 coordinate stays float32 through log10 and is widened afterwards.
+// float32 coordinates: the C library's log10f of the reference's host, instruction for instruction (glibc 2.39, the FMA
+// build of its logf) - csrc/log10f_glibc.h, proven equal to the library for every positive finite float by
+// oracle/log10f_check.c.  CUDA's log10f is a different algorithm: last-bit differences moved points that sit on a pixel
+// boundary by one pixel (round 1).  float64 coordinates still go through CUDA's log10 (not bit-identical to glibc's).
+#define DSB_LG_FN __device__ __forceinline__
+#define DSB_LG_FMA(a, b, c) fma((a), (b), (c))
+#define DSB_LG_FMULF(a, b) __fmul_rn((a), (b))
+#define DSB_LG_FADDF(a, b) __fadd_rn((a), (b))
+#define DSB_LG_ASUINT(f) __float_as_uint(f)
+#define DSB_LG_ASFLOAT(u) __uint_as_float(u)
+#define DSB_LG_TABLE static __device__ const double
+#include "log10f_glibc.h"
+
 template <typename XY> __device__ __forceinline__ double axis_log(XY v);
-template <> __device__ __forceinline__ double axis_log<float>(float v) { return (double)log10f(v); }
+template <> __device__ __forceinline__ double axis_log<float>(float v) {
+  return (v > 0.0f && v < INFINITY) ? (double)lg_log10f(v) : (double)log10f(v);
+}
 template <> __device__ __forceinline__ double axis_log<double>(double v) { return log10(v); }
 
 template <typename XY>

@@ -94,17 +94,54 @@ def test_partitioned_golden_single_gpu(ds):
 
 
 def test_log_axes(ds):
-    """Log axes: CUDA's log10f is not bit-identical to glibc's; the bar is +-1 pixel on boundary points
-    (SURVEY.md 8a A1).  Total count must match exactly (the bounds test is exact)."""
+    """Log axes, float32 coordinates: bit-exact with the reference (test_pandas.py:1171-1187).  The device evaluates glibc's
+    log10f instruction for instruction (csrc/log10f_glibc.h, proven against the C library for every positive float by
+    oracle/log10f_check.c), so boundary points land in the reference's pixel."""
     g = load("points.npz")
     import pandas as pd
     df = pd.DataFrame({k: g[f"in_log_{k}"] for k in ("x", "y", "v32")})
     cvs = ds.Canvas(plot_width=40, plot_height=30, x_range=(1, 1000), y_range=(1, 100), x_axis_type="log", y_axis_type="log")
-    got = cvs.points(df, "x", "y", ds.count()).data
-    want = g["pts_log_count"]
-    assert got.sum() == want.sum()
-    assert np.abs(got.astype(np.int64) - want.astype(np.int64)).sum() <= 8
+    assert_agg_equal(cvs.points(df, "x", "y", ds.count()).data, g["pts_log_count"], "log count")
+    assert_agg_equal(cvs.points(df, "x", "y", ds.max("v32")).data, g["pts_log_max_v32"], "log max")
     np.testing.assert_allclose(cvs.points(df, "x", "y").coords["x"], g["pts_log_xcoords"], rtol=1e-15)
+
+
+def test_log_axes_vs_oracle_with_points_on_pixel_edges(ds):
+    """2e5 float32 points on log axes, a third of them the float32 values nearest to the pixel edges (and their float32
+    neighbours): count, by-count and K2 (forced) are bit-equal to the oracle, which calls the C library's log10f."""
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(41)
+    n, W, H = 200_000, 300, 200
+    xr, yr = (0.5, 2.0e4), (1.0e-3, 7.0)
+    x = (10 ** (np.log10(xr[0]) + rng.random(n) * (np.log10(xr[1]) - np.log10(xr[0])))).astype(np.float32)
+    y = (10 ** (np.log10(yr[0]) + rng.random(n) * (np.log10(yr[1]) - np.log10(yr[0])))).astype(np.float32)
+    ex = (10 ** (np.log10(xr[0]) + np.arange(W + 1) / W * (np.log10(xr[1]) - np.log10(xr[0])))).astype(np.float32)
+    ey = (10 ** (np.log10(yr[0]) + np.arange(H + 1) / H * (np.log10(yr[1]) - np.log10(yr[0])))).astype(np.float32)
+    k = n // 6
+    for arr, e in ((x, ex), (y, ey)):
+        pick = e[rng.integers(0, len(e), k)]
+        step = rng.integers(-2, 3, k)
+        for s_ in (-2, -1, 1, 2):
+            m = step == s_
+            for _ in range(abs(s_)):
+                pick[m] = np.nextafter(pick[m], np.float32(np.inf if s_ > 0 else -np.inf))
+        arr[:k] = pick
+        rng.shuffle(arr)
+    cols = {"x": x, "y": y, "cat": rng.integers(0, NCAT, n).astype(np.int8), "cat__ncat": NCAT}
+    view = ora.make_view(W, H, xr, yr, "log", "log")
+    cvs = ds.Canvas(W, H, x_range=xr, y_range=yr, x_axis_type="log", y_axis_type="log")
+    frame = ds.DeviceFrame({k_: torch.from_numpy(v).cuda() for k_, v in cols.items() if k_ != "cat__ncat"},
+                           categories={"cat": [f"c{i}" for i in range(NCAT)]})
+    assert_agg_equal(cvs.points(frame, "x", "y", ds.count()).data, ora.points(cols, "x", "y", ("count",), view), "log count vs oracle")
+    assert_agg_equal(cvs.points(frame, "x", "y", ds.count_cat("cat")).data, ora.points(cols, "x", "y", ("by", "cat", ("count",)), view),
+                     "log by-count vs oracle")
+    old = ds.config.priv_min_rows
+    ds.config.priv_min_rows = 0
+    try:
+        assert_agg_equal(cvs.points(frame, "x", "y", ds.count()).data, ora.points(cols, "x", "y", ("count",), view), "log K2 count")
+    finally:
+        ds.config.priv_min_rows = old
 
 
 @pytest.mark.parametrize("seed,n,W,H", [(1, 300_000, 900, 525), (2, 200_000, 1920, 1080), (3, 100_000, 17, 3)])

@@ -287,3 +287,16 @@ def test_lines_aa_by_category_golden():
         assert got.dtype == want.dtype and got.shape == want.shape, aname
         assert np.array_equal(np.isnan(got), np.isnan(want)), aname
         np.testing.assert_allclose(got, want, rtol=1e-6 if aname == "count" else 1e-12, equal_nan=True, err_msg=aname)
+
+
+def test_device_log10f_restatement_equals_the_c_library():
+    """datashader_b200/csrc/log10f_glibc.h (what the device evaluates for LogAxis on float32 coordinates) against this box's
+    libm, every 61st positive finite float (the full sweep, `oracle/_build/log10f_check 1`, takes 10 s on 8 cores: 0 of
+    2 139 095 039 differ on glibc 2.39)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_build", "log10f_check")
+    if not os.path.exists(exe):
+        ora.build()
+    r = subprocess.run([exe, "61"], capture_output=True, text=True)
+    assert r.returncode == 0 and " 0 differ" in r.stdout, r.stdout + r.stderr
