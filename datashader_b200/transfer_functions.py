@@ -123,10 +123,10 @@ def _colorize(agg, color_key, how, alpha, span, min_alpha, name, color_baseline,
         raise ValueError(f"Insufficient colors provided ({len(color_key)}) for the categorical "
                          f"fields available ({len(cats)})")
     dt = str(data.dtype).replace("torch.", "")
-    if dt != "uint32":
-        raise NotImplementedError("datashader_b200.tf.shade: categorical aggregates must be uint32 counts "
-                                  f"(got {dt})")
     colors = [rgb(color_key[c]) for c in cats]
+    if dt != "uint32":
+        return _colorize_float(agg, colors, how, alpha, span, min_alpha, name, color_baseline, rescale_discrete_levels, device,
+                               coords)
     ncat = len(cats)
     RGB = np.array(colors, dtype=np.float32)                       # (C, 3)
     rgb2 = ((np.ones((1, ncat), np.float32) @ RGB) / np.float32(ncat)).astype(np.uint8)[0]   # :432-442
@@ -175,6 +175,62 @@ def _colorize(agg, color_key, how, alpha, span, min_alpha, name, color_baseline,
             clip_hi, out.data_ptr(), s), "dsb_shade_cat_colorize")
         img = to_host_array(out).view(np.uint32).reshape(H, W)
     return Image(img, dims=agg.dims[:-1], coords=coords, name=name)
+
+
+def _colorize_float(agg, colors, how, alpha, span, min_alpha, name, color_baseline, rescale_discrete_levels, device, coords):
+    """Categorical aggregates that are not uint32 counts - by(cat, mean | sum | max | min ...) -> float64 [H, W, C] with
+    NaN for empty cells, or signed integers (_colorize :382-452).  Canvas-sized float32 arithmetic in the reference's
+    order of operations: baseline subtraction on the present cells, NaN -> 0, colour = (data @ RGB) / total with the
+    average colour of the present categories where the total is 0; alpha from the per-pixel nansum through the same
+    transfer function as a 2-D aggregate (_interpolate_alpha :466-532).  The float32 sums over the category axis run in
+    torch's order, not numpy's: colour bytes may differ from the reference's by 1 level where a quotient sits on an
+    integer (tests state the bar); the alpha channel is exact."""
+    t = _device_tensor(agg.data, device)
+    if t.dtype == torch.bool:
+        t = t.to(torch.uint8)
+    H, W, ncat = (int(v) for v in t.shape)
+    is_float = t.dtype.is_floating_point
+    signed = is_float or t.dtype in (torch.int8, torch.int16, torch.int32, torch.int64)
+    with torch.cuda.device(device):
+        nan_mask = torch.isnan(t) if is_float else torch.zeros_like(t, dtype=torch.bool)
+        present = ~nan_mask
+        if color_baseline is None:
+            if is_float:
+                vals = t[present]
+                baseline = vals.min() if vals.numel() else torch.tensor(float("nan"), device=device, dtype=t.dtype)
+            else:
+                baseline = t.min()
+        else:
+            baseline = torch.tensor(color_baseline, device=device).to(t.dtype)
+        color_data = torch.where(present, t - baseline, t)
+        if color_baseline is not None and signed:
+            color_data = torch.where(color_data < 0, torch.zeros_like(color_data), color_data)      # np.maximum(color_data, 0)
+        color_data = torch.nan_to_num(color_data.to(torch.float32), nan=0.0)
+        color_total = color_data.sum(dim=2)
+        RGB = torch.tensor(colors, dtype=torch.float32, device=device)                              # (C, 3)
+        rgb_sum = color_data.reshape(-1, ncat) @ RGB
+        present_f = present.to(torch.float32)
+        rgb_avg_present = present_f.reshape(-1, ncat) @ RGB
+        rgb_array = (rgb_sum / color_total.reshape(-1, 1))
+        rgb2 = rgb_avg_present / present_f.sum(dim=2).reshape(-1, 1)
+        missing = (color_total == 0).reshape(-1, 1)
+        rgbv = torch.where(missing, rgb2, rgb_array)
+        rgbv = torch.nan_to_num(rgbv, nan=0.0, posinf=0.0, neginf=0.0).to(torch.int64) & 0xFF     # .astype(np.uint8) of in-range values
+        # total = nansum_missing(data, axis=2): NaN where every category is missing; alpha through the 2-D machinery
+        if is_float:
+            total = torch.where(present.any(dim=2), torch.nan_to_num(t, nan=0.0).sum(dim=2), torch.full((H, W), float("nan"), dtype=t.dtype, device=device))
+        else:
+            total = t.sum(dim=2)
+        total_agg = DataArray(total, coords=coords, dims=agg.dims[:-1])
+        if bool(torch.isnan(total).all()) if is_float else False:
+            a = torch.zeros((H, W), dtype=torch.int64, device=device)
+        else:
+            alpha_img = _interpolate(total_agg, "#000000", how, alpha, span, min_alpha, name, rescale_discrete_levels, device)
+            a = (torch.from_numpy(np.asarray(alpha_img.data).view(np.int32).astype(np.int64)).to(device) >> 24) & 0xFF
+        packed = rgbv[:, 0] | (rgbv[:, 1] << 8) | (rgbv[:, 2] << 16) | (a.reshape(-1) << 24)
+        img = packed.to(torch.int32) if False else (packed & 0xFFFFFFFF)
+        out = img.cpu().numpy().astype(np.uint32).reshape(H, W)
+    return Image(out, dims=agg.dims[:-1], coords=coords, name=name)
 
 
 def _interpolate(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_levels, device):

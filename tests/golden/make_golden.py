@@ -264,6 +264,35 @@ SPAN_CASES_2D = {"u32": [(2, 9), (0.5, 7.5)], "f64": [(-5.0, 12.5)], "f32": [(0.
 SPAN_CASES_CAT = {"poisson5": [(3, 20), (2.5, 15.5)], "dense3": [(40, 90), (30.5, 100.25)]}
 
 
+def shade_catfloat_cases():
+    """tf.shade on categorical aggregates that are not counts: by(cat, mean | max) -> float64 [H, W, C] with NaN for empty
+    cells, a float32 variant, and signed integers (_colorize, transfer_functions/__init__.py:382-452)."""
+    import xarray as xr
+    import datashader.transfer_functions as tf
+    out = {}
+    rng = np.random.default_rng(58)
+    H, Wd = 40, 56
+
+    def cat_agg(data):
+        C = data.shape[2]
+        return xr.DataArray(data, coords={"y": np.arange(H), "x": np.arange(Wd), "cat": [f"c{i}" for i in range(C)]},
+                            dims=["y", "x", "cat"])
+
+    a = rng.standard_normal((H, Wd, 4)) * 3 + 1
+    a[rng.random((H, Wd, 4)) < 0.4] = np.nan
+    a[rng.random((H, Wd)) < 0.2] = np.nan                  # pixels with no category at all
+    b = (rng.random((H, Wd, 3)) * 100).astype(np.float32)
+    b[rng.random((H, Wd, 3)) < 0.5] = np.nan
+    c = rng.integers(-5, 40, (H, Wd, 5)).astype(np.int32)
+    for name, data in (("f64", a), ("f32", b), ("i32", c)):
+        out[f"catf_{name}_in"] = data
+        for how in ("eq_hist", "log", "cbrt", "linear"):
+            out[f"catf_{name}_{how}"] = np.asarray(tf.shade(cat_agg(data), how=how).data)
+        out[f"catf_{name}_linear_base"] = np.asarray(tf.shade(cat_agg(data), how="linear", color_baseline=0.5 if name != "i32" else 2).data)
+        out[f"catf_{name}_linear_span"] = np.asarray(tf.shade(cat_agg(data), how="linear", span=(0, 20)).data)
+    return out
+
+
 def shade_span_cases():
     """tf.shade with an explicit span (clip + fixed normalisation range), on the shade.npz inputs."""
     import xarray as xr
@@ -629,6 +658,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "lines_aa3.npz"), **lines_aa3_cases())
         print("lines_aa3.npz", os.path.getsize(os.path.join(HERE, "lines_aa3.npz")) // 1024, "KiB")
         return
+    if "--shade-catfloat-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "shade_catfloat.npz"), **shade_catfloat_cases())
+        print("shade_catfloat.npz", os.path.getsize(os.path.join(HERE, "shade_catfloat.npz")) // 1024, "KiB")
+        return
     if "--tiles-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "tiles.npz"), **tiles_cases())
         print("tiles.npz", os.path.getsize(os.path.join(HERE, "tiles.npz")) // 1024, "KiB")
@@ -674,6 +707,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "tiles.npz"), **tiles_cases())
     np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
     np.savez_compressed(os.path.join(HERE, "shade_span.npz"), **shade_span_cases())
+    np.savez_compressed(os.path.join(HERE, "shade_catfloat.npz"), **shade_catfloat_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "points_negzero.npz"), **negzero_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())

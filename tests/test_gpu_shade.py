@@ -125,3 +125,28 @@ def test_shade_span_golden():
                 _check(ds.tf.shade(agg, how=how, span=span).data, gs[f"cat_{name}_s{k}_{how}"], how, f"{name} {span} {how}")
     with pytest.raises(ValueError, match="span is not"):
         ds.tf.shade(_agg2(g["d2_u32_in"]), how="eq_hist", span=(1, 5))
+
+
+@pytest.mark.parametrize("name", ["f64", "f32", "i32"])
+def test_shade_categorical_float_golden(name):
+    """by(cat, mean | sum | max ...) aggregates - float [H, W, C] with NaN for empty cells, and signed integers - through
+    tf.shade (_colorize :382-452) vs the real reference (tests/golden/shade_catfloat.npz).  Alpha: exact for eq_hist and
+    linear, +-1 level for log / cbrt like the 2-D path.  Colour bytes: +-1 level on < 2 % of the pixels (the float32 sums
+    over the category axis run in torch's order, numpy's are pairwise; a quotient that sits on an integer can flip)."""
+    import datashader_b200 as ds
+    g = load("shade_catfloat.npz")
+    agg = _cat_agg(ds, g[f"catf_{name}_in"])
+    cases = [(how, {}, f"catf_{name}_{how}") for how in ("eq_hist", "log", "cbrt", "linear")]
+    cases.append(("linear", dict(color_baseline=0.5 if name != "i32" else 2), f"catf_{name}_linear_base"))
+    cases.append(("linear", dict(span=(0, 20)), f"catf_{name}_linear_span"))
+    for how, kw, key in cases:
+        got, want = ds.tf.shade(agg, how=how, **kw).data, g[key]
+        assert got.dtype == np.uint32 and got.shape == want.shape, key
+        cg, cw = _channels(got), _channels(want)
+        if how in ("eq_hist", "linear"):
+            np.testing.assert_array_equal(cg[..., 3], cw[..., 3], err_msg=key + " alpha")
+        else:
+            assert np.abs(cg[..., 3] - cw[..., 3]).max() <= 1, key
+        visible = cw[..., 3] > 0
+        diff = np.abs(cg[..., :3] - cw[..., :3])[visible]
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.02, (key, int(diff.max()), float((diff > 0).mean()))
