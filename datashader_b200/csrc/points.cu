@@ -638,6 +638,7 @@ static long long g_priv_smem_kb_mean = 226;   // the same for the mean() shape
 static long long g_split_bytes = 48LL << 20;  // plans whose canvases total more than this run one pass per accumulator
 static long long g_count16_band_bytes = 0;   // dsb_points_count16: optional banding of the packed canvas (0 = off; measured on
                                              // config 3: 1 pass 8.5 ms, 2 bands 9.0 ms, 3 bands 13.4 ms - each pass pays the generic front end)
+static int g_count8 = 1;                     // dsb_points_count16: try 8-bit packed counters first (tight front end only)
 static int g_mono = 1;                       // use k_points_mono for single monotone accumulators
 static int g_mono_banded = 1;                //   ... also for the L2-banded passes of big canvases (without the filter)
 static int g_priv_threads = 1024;            // threads per CTA of the tight K2 kernels (one CTA per SM)
@@ -661,6 +662,7 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "mono")) { g_mono = value != 0; return DSB_OK; }
   if (!strcmp(key, "split_bytes")) { g_split_bytes = value; return DSB_OK; }
   if (!strcmp(key, "count16_band_bytes")) { g_count16_band_bytes = value; return DSB_OK; }
+  if (!strcmp(key, "count8")) { g_count8 = value != 0; return DSB_OK; }
   if (!strcmp(key, "mono_banded")) { g_mono_banded = value != 0; return DSB_OK; }
   if (!strcmp(key, "mono_min_rows")) { g_mono_min_rows = value; return DSB_OK; }
   if (!strcmp(key, "priv_smem_kb")) { if (value < 16 || value > 226) { dsb_set_error("dsb_configure: priv_smem_kb must be in [16, 226]"); return DSB_ERR_ARG; } g_priv_smem_kb = value; return DSB_OK; }
@@ -1076,10 +1078,13 @@ __global__ void __launch_bounds__(256) k_points_count16(const PointsArgs a, unsi
 // count16 with the tight front end: float32 coordinates on linear axes, optional 1-byte category codes (by('cat',
 // count()): four codes per 32-bit load beside the float4 of x and y), optional float32 column to NaN-check.  Same
 // contract as k_points_count16.
-template <bool CAT>
+// BITS = 16: two counters per word; BITS = 8: four (half the footprint again: 33 MB at config 3, comfortably L2-resident).
+// gate != nullptr: the launch runs only if *gate != 0 (the 16-bit stage after an 8-bit stage whose checksum failed).
+template <bool CAT, int BITS>
 __global__ void __launch_bounds__(256, 3) k_points_count16_tight(const __grid_constant__ PointsArgs a, const __grid_constant__ FastMap fm,
                                                                  const float* __restrict__ vcol, unsigned int* __restrict__ packed,
-                                                                 unsigned long long* __restrict__ accepted) {
+                                                                 unsigned long long* __restrict__ accepted, const unsigned int* __restrict__ gate) {
+  if (gate && *gate == 0) return;
   const float* __restrict__ x = (const float*)a.x;
   const float* __restrict__ y = (const float*)a.y;
   const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
@@ -1093,7 +1098,8 @@ __global__ void __launch_bounds__(256, 3) k_points_count16_tight(const __grid_co
     return (c < 0 || c >= ncat) ? -1 : c;
   };
   auto put = [&](long long cell) {
-    atomicAdd(packed + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
+    if (BITS == 16) atomicAdd(packed + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
+    else atomicAdd(packed + (cell >> 2), 1u << (8 * (int)(cell & 3)));
     mine++;
   };
   auto exact = [&](float xv, float yv, float vv, int code) {
@@ -1142,23 +1148,30 @@ __global__ void __launch_bounds__(256, 3) k_points_count16_tight(const __grid_co
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(accepted, mine);
 }
 
-__global__ void k_sum16(const unsigned int* __restrict__ packed, long long nwords, unsigned long long* __restrict__ total) {
+template <int BITS>
+__global__ void k_sum16(const unsigned int* __restrict__ packed, long long nwords, unsigned long long* __restrict__ total,
+                        const unsigned int* __restrict__ gate) {
+  if (gate && *gate == 0) return;
   unsigned long long t = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) {
     const unsigned int w = packed[i];
-    t += (w & 0xffffu) + (w >> 16);
+    if (BITS == 16) t += (w & 0xffffu) + (w >> 16);
+    else t += (w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24);
   }
   for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
   if ((threadIdx.x & 31) == 0 && t) atomicAdd(total, t);
 }
 
-// st[0] = accepted hits, st[1] = sum of the halves, st[2] = flag (1: a half wrapped, redo)
+// st[0] = accepted hits, st[1] = sum of the fields, st[2] = flag (1: a field wrapped, redo with the next wider counters)
+template <int BITS>
 __global__ void k_unpack16_if(unsigned int* __restrict__ canvas, const unsigned int* __restrict__ packed, long long ncell,
-                              unsigned long long* __restrict__ st) {
+                              unsigned long long* __restrict__ st, const unsigned int* __restrict__ gate) {
+  if (gate && *gate == 0) return;
   if (st[0] != st[1]) { if (blockIdx.x == 0 && threadIdx.x == 0) *(unsigned int*)(st + 2) = 1u; return; }
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
-    const unsigned int w = packed[c >> 1];
-    const unsigned int h = (c & 1) ? (w >> 16) : (w & 0xffffu);
+    unsigned int h;
+    if (BITS == 16) { const unsigned int w = packed[c >> 1]; h = (c & 1) ? (w >> 16) : (w & 0xffffu); }
+    else h = (packed[c >> 2] >> (8 * (int)(c & 3))) & 0xffu;
     if (h) canvas[c] += h;
   }
 }
@@ -1175,11 +1188,12 @@ extern "C" int dsb_points_count16(const dsb_view* view, const void* x, const voi
   if (!x || !y) { dsb_set_error("dsb_points_count16: null coordinate column"); return DSB_ERR_ARG; }
   const long long ncell = (long long)view->width * view->height * (plan->ncat > 0 ? plan->ncat : 1);
   const long long nwords = (ncell + 1) >> 1;
-  if (!scratch || scratch_bytes < nwords * 4 + 24) { dsb_set_error("dsb_points_count16: scratch must hold %lld bytes", nwords * 4 + 24); return DSB_ERR_ARG; }
-  unsigned long long* st = (unsigned long long*)scratch;               // [3] u64 header, then the packed canvas
+  if (!scratch || scratch_bytes < nwords * 4 + 48) { dsb_set_error("dsb_points_count16: scratch must hold %lld bytes", nwords * 4 + 48); return DSB_ERR_ARG; }
+  unsigned long long* st8 = (unsigned long long*)scratch;              // [3] u64 state of the 8-bit stage, [3] of the 16-bit stage,
+  unsigned long long* st = st8 + 3;                                    //   then the packed canvas (shared by both stages)
   unsigned int* packed = (unsigned int*)(st + 3);
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(scratch, 0, (size_t)(nwords * 4 + 24), s);
+  cudaMemsetAsync(scratch, 0, (size_t)(nwords * 4 + 48), s);
   PointsArgs a;
   a.v = *view; a.x = x; a.y = y; a.n = n; a.row_offset = row_offset; a.plan = *plan; a.band_lo = 0; a.band_hi = ncell;
   const int threads = 256;
@@ -1195,11 +1209,25 @@ extern "C" int dsb_points_count16(const dsb_view* view, const void* x, const voi
                         cb.chk_dtype == DSB_NONE && (cb.val_dtype == DSB_NONE || (cb.val_dtype == DSB_F32 && (((uintptr_t)cb.val) & 15) == 0)) &&
                         ((((uintptr_t)x | (uintptr_t)y)) & 15) == 0 && g_count16_band_bytes == 0 && !l2_persist_enabled();
   dsb_note_kernel(tight_ok ? "k_points_count16_tight<%s>" : "k_points_count16<%s>", tight_ok ? (plan->ncat > 0 ? "cat" : "nocat") : (xy_dtype == DSB_F32 ? "f32" : "f64"));
+  const unsigned int* gate16 = nullptr;          // non-null: the 16-bit stage runs only if the 8-bit stage's checksum failed
   if (tight_ok) {
     const float* vcol = cb.val_dtype == DSB_F32 ? (const float*)cb.val : nullptr;
     const int g3 = dsb_num_sms() * 3;
-    if (plan->ncat > 0) k_points_count16_tight<true><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st);
-    else k_points_count16_tight<false><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st);
+    if (g_count8) {
+      // stage 0: 8-bit counters, a quarter of the u32 footprint (config 3: 33 MB, L2-resident with room to spare).  A cell
+      // with more than 255 hits wraps, the sum of the fields then falls short of the accepted hits, and the 16-bit stage
+      // below (gated on that flag) redoes the pass.
+      const long long nwords8 = (ncell + 3) >> 2;
+      if (plan->ncat > 0) k_points_count16_tight<true, 8><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st8, nullptr);
+      else k_points_count16_tight<false, 8><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st8, nullptr);
+      k_sum16<8><<<(int)cap, 256, 0, s>>>(packed, nwords8, st8 + 1, nullptr);
+      k_unpack16_if<8><<<(int)cap, 256, 0, s>>>((unsigned int*)plan->ops[0].agg, packed, ncell, st8, nullptr);
+      gate16 = (const unsigned int*)(st8 + 2);
+      cudaMemsetAsync(packed, 0, (size_t)nwords * 4, s);
+      dsb_note_kernel("k_points_count16_tight<%s,8 bit>", plan->ncat > 0 ? "cat" : "nocat");
+    }
+    if (plan->ncat > 0) k_points_count16_tight<true, 16><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st, gate16);
+    else k_points_count16_tight<false, 16><<<g3, 256, 0, s>>>(a, fm, vcol, packed, st, gate16);
   } else if (l2_persist_enabled()) {
     // opt-in (DSB_L2_PERSIST=1): pin the packed canvas in L2, everything else streams
     cudaLaunchConfig_t cfg = {};
@@ -1229,8 +1257,8 @@ extern "C" int dsb_points_count16(const dsb_view* view, const void* x, const voi
     }
     a.band_lo = 0; a.band_hi = ncell;
   }
-  k_sum16<<<(int)cap, 256, 0, s>>>(packed, nwords, st + 1);
-  k_unpack16_if<<<(int)cap, 256, 0, s>>>((unsigned int*)plan->ops[0].agg, packed, ncell, st);
+  k_sum16<16><<<(int)cap, 256, 0, s>>>(packed, nwords, st + 1, gate16);
+  k_unpack16_if<16><<<(int)cap, 256, 0, s>>>((unsigned int*)plan->ops[0].agg, packed, ncell, st, gate16);
   want = (n + 255) / 256;
   const int g2 = (int)(want < cap ? want : cap);
   if (xy_dtype == DSB_F32) k_points_generic_if<float><<<g2, 256, 0, s>>>(a, (const unsigned int*)(st + 2));

@@ -203,7 +203,7 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
         # u32 canvas beyond L2 but its 16-bit packed form fits: one L2-resident pass instead of two banded ones
         scratch = getattr(ctx, "_count16_scratch", None)
         if scratch is None:
-            scratch = ctx._count16_scratch = torch.empty(4 * ((ncell + 1) // 2) + 24, dtype=torch.uint8, device=x.device)
+            scratch = ctx._count16_scratch = torch.empty(4 * ((ncell + 1) // 2) + 48, dtype=torch.uint8, device=x.device)
         rc = lib.dsb_points_count16(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
                                     scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
         if rc == 0:

@@ -288,10 +288,10 @@ int dsb_shade_map2d(const double* data, int64_t npix, int32_t how, const double*
                     const double* span, int32_t ncolors, const double* cspan, const double* rs, const double* gs,
                     const double* bs, double min_alpha, double alpha, uint32_t* out, void* stream);
 
-/* count() / by(cat, count()) on a u32 canvas of 1x..2x the L2 budget (config 3: 133 MB): one pass into 16-bit packed
- * counters in `scratch` (2 bytes per cell + 24: L2-resident), verified by a checksum (sum of the halves == accepted hits)
- * and then added into the canvas; on a mismatch (some cell took more than 65 535 hits) the pass is redone with u32
- * REDs by a flag-gated launch.  Same contract as dsb_points for a plan of exactly one COUNT accumulator; otherwise
+/* count() / by(cat, count()) on a u32 canvas of 1x..2x the L2 budget (config 3: 133 MB): one pass into packed counters in
+ * `scratch` (2 bytes per cell + 48) - 8-bit fields first (a quarter of the u32 footprint), verified by a checksum (sum of
+ * the fields == accepted hits) and then added into the canvas; on a mismatch (some cell took more than 255 hits) the pass
+ * is redone with 16-bit fields, and past 65 535 hits with u32 REDs, each by flag-gated launches (no host round trip).  Same contract as dsb_points for a plan of exactly one COUNT accumulator; otherwise
  * DSB_ERR_UNSUPPORTED. */
 int dsb_points_count16(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
                        const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream);

@@ -476,6 +476,21 @@ def test_count16_packed_path_matches_oracle(ds):
         got = cvs.points(frame, "x", "y", ds.by("cat", ds.count("v32"))).data
         assert_agg_equal(got, ora.points(cols, "x", "y", ("by", "cat", ("count", "v32")), view), "count16 by count(v32)")
         assert ds._lib.lib().dsb_launch_count() > before
+        # warm cell: 1 000 hits on one (pixel, category) -> an 8-bit field wraps -> the gated 16-bit stage redoes the pass
+        warm = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in cols.items()}
+        warm["x"][:1000], warm["y"][:1000], warm["cat"][:1000] = 0.31, 0.32, 2
+        wframe = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in warm.items() if k != "cat__ncat"},
+                                categories={"cat": [f"c{i}" for i in range(NC)]})
+        got = cvs.points(wframe, "x", "y", ds.by("cat", ds.count())).data
+        assert_agg_equal(got, ora.points(warm, "x", "y", ("by", "cat", ("count",)), view), "count16 warm cell (8-bit wrap)")
+        assert 1000 <= got.max() < 65536
+        # the same without the 8-bit stage
+        ds._lib.check(ds._lib.lib().dsb_configure(b"count8", 0), "cfg")
+        try:
+            got = cvs.points(wframe, "x", "y", ds.by("cat", ds.count())).data
+            assert_agg_equal(got, ora.points(warm, "x", "y", ("by", "cat", ("count",)), view), "count16 without the 8-bit stage")
+        finally:
+            ds._lib.check(ds._lib.lib().dsb_configure(b"count8", 1), "cfg")
         # hot cell: 200 000 hits on one (pixel, category) -> a 16-bit half wraps -> checksum mismatch -> exact redo
         cols["x"][:200_000] = 0.51
         cols["y"][:200_000] = 0.52
