@@ -494,6 +494,14 @@ __device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long
     case DSB_AA2_MIN:      // nanmin_in_place, utils.py:655-668
       atomicMin((long long*)b.out + cell, key);
       break;
+    case DSB_AA2_ARGMIN:   // where(min(col), ...): the selector's combine keeps the earlier line on ties (strict compare)
+      if (b.phase == 1) atomicMin((long long*)b.out + cell, key);
+      else if (((const long long*)b.out)[cell] == key) atomicMin((long long*)b.aux + cell, line);
+      break;
+    case DSB_AA2_ARGMAX:   // where(max(col), ...)
+      if (b.phase == 1) atomicMax((long long*)b.out + cell, key);
+      else if (((const long long*)b.out)[cell] == key) atomicMin((long long*)b.aux + cell, line);
+      break;
     case DSB_AA2_FIRST:    // nanfirst_in_place, utils.py:615-623: the lowest line index that touches the pixel wins
       if (b.phase == 1) atomicMin((long long*)b.aux + cell, line);
       else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
@@ -736,11 +744,12 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
                              int32_t val_dtype, int32_t combo, int32_t phase, double line_width, void* out, void* aux,
                              void* scratch, int64_t scratch_bytes, void* stream) {
   if (!view || view->width <= 0 || view->height <= 0 || !out) { dsb_set_error("dsb_lines_aa2: bad view/canvas"); return DSB_ERR_ARG; }
-  if (combo < DSB_AA2_SUM || combo > DSB_AA2_LAST) { dsb_set_error("dsb_lines_aa2: unknown combination %d", combo); return DSB_ERR_ARG; }
+  if (combo < DSB_AA2_SUM || combo > DSB_AA2_ARGMAX) { dsb_set_error("dsb_lines_aa2: unknown combination %d", combo); return DSB_ERR_ARG; }
   if (!(line_width > 0.0)) { dsb_set_error("dsb_lines_aa2: line_width must be > 0"); return DSB_ERR_ARG; }
   if (combo != DSB_AA2_COUNT && (val_dtype == DSB_NONE || !val)) { dsb_set_error("dsb_lines_aa2: this reduction needs a value column"); return DSB_ERR_ARG; }
-  if (combo != DSB_AA2_MIN && !aux) { dsb_set_error("dsb_lines_aa2: aux canvas required"); return DSB_ERR_ARG; }
-  if ((combo == DSB_AA2_FIRST || combo == DSB_AA2_LAST) && phase != 1 && phase != 2) { dsb_set_error("dsb_lines_aa2: phase must be 1 or 2"); return DSB_ERR_ARG; }
+  const bool two_phase = combo == DSB_AA2_FIRST || combo == DSB_AA2_LAST || combo == DSB_AA2_ARGMIN || combo == DSB_AA2_ARGMAX;
+  if (combo != DSB_AA2_MIN && !((combo == DSB_AA2_ARGMIN || combo == DSB_AA2_ARGMAX) && phase == 1) && !aux) { dsb_set_error("dsb_lines_aa2: aux canvas required"); return DSB_ERR_ARG; }
+  if (two_phase && phase != 1 && phase != 2) { dsb_set_error("dsb_lines_aa2: phase must be 1 or 2"); return DSB_ERR_ARG; }
   if (nlines <= 0 || nverts < 2) return DSB_OK;
   if (!xs || !ys) { dsb_set_error("dsb_lines_aa2: null vertex arrays"); return DSB_ERR_ARG; }
   const long long ncell = (long long)view->width * view->height;

@@ -556,16 +556,17 @@ def _lines_aa2_by(frame, schema, canvas, glyph, agg, line_width, dist):
 
 
 def _lines_aa_where(frame, canvas, glyph, agg, line_width, dist):
-    """where(first(col) | last(col)[, other]) on antialiased lines: the selector's 2-stage combination keeps, per pixel,
-    the first / last LINE that covers it with a non-null value (nanfirst / nanlast over whole lines, compiler.py:198-268,
-    reductions.py:1906-1914, 1992-2027) - exactly the line dsb_lines_aa2's first phase votes for."""
+    """where(first | last | max | min (col)[, other]) on antialiased lines.  first / last: the selector's 2-stage combination
+    keeps, per pixel, the first / last LINE that covers it with a non-null value (nanfirst / nanlast over whole lines,
+    compiler.py:198-268, reductions.py:1906-1914, 1992-2027) - exactly the line dsb_lines_aa2's first phase votes for.
+    max / min: the line whose value x coverage is the pixel's maximum / minimum of the per-line maxima, the earlier line on
+    ties (strict compare, reductions.py:2009-2016): value canvas first, then the lowest matching line index."""
     sel = agg.selector
-    if not isinstance(sel, (rd.first, rd.last)):
-        raise NotImplementedError("where(max | min) is not implemented for antialiased datashader_b200 lines yet")
+    combo = _aa2_combo(sel) if isinstance(sel, (rd.first, rd.last)) else (_lib.AA2_ARGMAX if isinstance(sel, rd.max) else _lib.AA2_ARGMIN)
     device = frame.device
     with torch.cuda.device(device):
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
-        rows, (x_range, y_range, x_st, y_st) = _lines_aa2(frame, canvas, glyph, sel, _aa2_combo(sel), line_width, dist, rows_only=True)
+        rows, (x_range, y_range, x_st, y_st) = _lines_aa2(frame, canvas, glyph, sel, combo, line_width, dist, rows_only=True)
         _lib.check(_lib.lib().dsb_finish_minrow(rows.data_ptr(), rows.numel(), stream_ptr), "dsb_finish_minrow")
         if agg.column == rd.SpecialColumn.RowIndex:
             out = rows
@@ -748,6 +749,21 @@ def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist, rows_only=Fal
                 dist._all_reduce(keys, "min")
             out = torch.empty((H, W), dtype=torch.float64, device=device)
             _lib.check(lib.dsb_decode_minmax(keys.data_ptr(), _lib.OP_MIN64, _lib.F64, out.data_ptr(), H * W, stream_ptr))
+        elif combo in (_lib.AA2_ARGMIN, _lib.AA2_ARGMAX):
+            # where(min | max): the value canvas first, then the lowest line index among the lines that reach it
+            is_max = combo == _lib.AA2_ARGMAX
+            keys = torch.empty((H, W), dtype=torch.int64, device=device)
+            _lib.check(lib.dsb_init_canvas(_lib.OP_MAX64 if is_max else _lib.OP_MIN64, keys.data_ptr(), H * W, stream_ptr))
+            launch(1, keys, None)
+            if dist is not None:
+                dist._all_reduce(keys, "max" if is_max else "min")
+            rows = torch.empty((H, W), dtype=torch.int64, device=device)
+            _lib.check(lib.dsb_init_canvas(_lib.OP_MINROW, rows.data_ptr(), H * W, stream_ptr))
+            launch(2, keys, rows)
+            if dist is not None:
+                dist._all_reduce(rows, "min")
+            assert rows_only
+            return rows, (x_range, y_range, x_st, y_st)
         else:
             first = combo == _lib.AA2_FIRST
             rows = torch.empty((H, W), dtype=torch.int64, device=device)

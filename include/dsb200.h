@@ -229,10 +229,15 @@ int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, i
  *   DSB_AA2_SUM   sum(self_intersect=False):   out f64 zero-initialised, aux u8 mask (zeroed)
  *   DSB_AA2_COUNT count(self_intersect=False): out f32 zero-initialised, aux u8 mask (zeroed); val optional (NaN check)
  *   DSB_AA2_MIN   min:                         out i64 key64 canvas (dsb_init_canvas(DSB_OP_MIN64)), aux unused
+ *   DSB_AA2_ARGMIN / DSB_AA2_ARGMAX (where(min | max)): phase 1 folds the per-line values into out (i64 key64 canvas,
+ *                 DSB_OP_MIN64 / DSB_OP_MAX64 init); phase 2 - on the finished (all-reduced) out - records in aux (i64,
+ *                 DSB_OP_MINROW init) the lowest line index whose per-line value equals it: the line the reference's
+ *                 strict compare keeps (reductions.py:2009-2016)
  *   DSB_AA2_FIRST / DSB_AA2_LAST:              aux i64 line-index canvas (DSB_OP_MINROW / DSB_OP_MAXROW init); call
  *                 with phase = 1 (votes the global line index row_offset + i into aux; all-reduce aux across GPUs
  *                 here), then phase = 2 (the winning line stores its value into out, f64, NaN-initialised). */
-typedef enum { DSB_AA2_SUM = 1, DSB_AA2_COUNT = 2, DSB_AA2_MIN = 3, DSB_AA2_FIRST = 4, DSB_AA2_LAST = 5 } dsb_aa2_combo;
+typedef enum { DSB_AA2_SUM = 1, DSB_AA2_COUNT = 2, DSB_AA2_MIN = 3, DSB_AA2_FIRST = 4, DSB_AA2_LAST = 5,
+               DSB_AA2_ARGMIN = 6, DSB_AA2_ARGMAX = 7 } dsb_aa2_combo;
 int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
                   int64_t nverts, const dsb_line_layout* layout, int64_t row_offset, const void* val,
                   int32_t val_dtype, int32_t combo, int32_t phase, double line_width, void* out, void* aux,

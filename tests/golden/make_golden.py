@@ -476,7 +476,9 @@ def lines_aa3_cases():
                          "sum_nsi": ds.sum("val", self_intersect=False), "count_nsi": ds.count(self_intersect=False)}.items():
         out[f"aa3_by_{aname}"] = np.asarray(cvs.line(df, agg=ds.by("cat", inner), **kw).data)
     for aname, agg in {"where_first_row": ds.where(ds.first("val")), "where_first_other": ds.where(ds.first("val"), "other"),
-                       "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other")}.items():
+                       "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other"),
+                       "where_max_row": ds.where(ds.max("val")), "where_max_other": ds.where(ds.max("val"), "other"),
+                       "where_min_row": ds.where(ds.min("val")), "where_min_other": ds.where(ds.min("val"), "other")}.items():
         out[f"aa3_{aname}"] = np.asarray(cvs.line(df, agg=agg, **kw).data)
     return out
 

@@ -291,6 +291,8 @@ def test_lines_antialiased_summary_by_where_golden():
         assert tuple(r.dims) == ("y", "x", "cat") and list(r.coords["cat"]) == ["a", "b", "c", "d"], aname
         _cmp_aa(r.data, g[f"aa3_by_{aname}"], f"aa by {aname}")
     for aname, agg in {"where_first_row": ds.where(ds.first("val")), "where_first_other": ds.where(ds.first("val"), "other"),
-                       "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other")}.items():
+                       "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other"),
+                       "where_max_row": ds.where(ds.max("val")), "where_max_other": ds.where(ds.max("val"), "other"),
+                       "where_min_row": ds.where(ds.min("val")), "where_min_other": ds.where(ds.min("val"), "other")}.items():
         got, want = cvs.line(frame, agg=agg, **kw).data, g[f"aa3_{aname}"]
         assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), aname
