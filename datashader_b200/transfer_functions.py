@@ -233,6 +233,93 @@ def _colorize_float(agg, colors, how, alpha, span, min_alpha, name, color_baseli
     return Image(out, dims=agg.dims[:-1], coords=coords, name=name)
 
 
+def _apply_discrete_colorkey(agg, color_key, alpha, name, color_baseline, device):
+    """2-D aggregate of category values + {value: colour}: _apply_discrete_colorkey (:535-612).  A pixel whose value is a key
+    gets that key's colour at `alpha`; the baseline arithmetic of the reference is kept as is (with an explicit
+    color_baseline that leaves 1 - baseline != 0 the colour stays black, as it does there)."""
+    if len(agg.data.shape) != 2:
+        raise ValueError("agg must be 2D")
+    if color_key is None or not isinstance(color_key, dict):
+        raise ValueError("Color key must be provided as a dictionary")
+    t = _device_tensor(agg.data, device)
+    if t.dtype == torch.uint32:
+        t = t.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    H, W = (int(v) for v in t.shape)
+    with torch.cuda.device(device):
+        matched = torch.zeros((H, W), dtype=torch.bool, device=device)
+        rgb2 = torch.zeros((H, W, 3), dtype=torch.int64, device=device)
+        for c, col in color_key.items():
+            m = t == c
+            matched |= m
+            rgb2[m] = torch.tensor(rgb(col), dtype=torch.int64, device=device)
+        data = torch.where(matched, 1.0, float("nan")).to(torch.float64)
+        baseline = (1.0 if bool(matched.any()) else float("nan")) if color_baseline is None else color_baseline
+        color_data = data.clone()
+        if baseline > 0:
+            color_data -= baseline
+        elif baseline < 0:
+            color_data += -baseline
+        if color_baseline is not None:
+            color_data = torch.where(color_data < 0, torch.zeros_like(color_data), color_data)
+        color_data = torch.where(torch.isnan(data), torch.zeros_like(color_data), color_data)
+        missing = (color_data == 0).unsqueeze(-1)
+        rgbv = torch.where(missing, rgb2, torch.zeros_like(rgb2))
+        a = torch.where(matched, int(np.uint8(alpha)), 0)
+        packed = rgbv[..., 0] | (rgbv[..., 1] << 8) | (rgbv[..., 2] << 16) | (a << 24)
+        out = packed.cpu().numpy().astype(np.uint32)
+    return Image(out, dims=agg.dims, coords=agg.coords, name=name)
+
+
+def _interpolate_host(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_levels, device):
+    """_interpolate (:251-357) for the two arguments that are Python callables and therefore run on the host: a callable
+    `how(data, mask)` (the transformed canvas then goes through the device's linear colour mapping) and a callable `cmap`
+    (a matplotlib colormap: `cmap(scaled, bytes=True)` - applied to the transformed canvas on the host, numpy on both sides)."""
+    data = np.array(to_host_array(_device_tensor(agg.data, device)))
+    if data.dtype == np.bool_:
+        mask = ~data
+        data = data.astype(np.int8)
+    elif data.dtype.kind == "u":
+        mask = data == 0
+    else:
+        mask = np.isnan(data)
+    if mask.all():
+        return Image(np.zeros(data.shape, dtype=np.uint32), coords=agg.coords, dims=agg.dims, attrs=agg.attrs, name=name)
+    if how == "eq_hist":
+        raise NotImplementedError("a callable cmap with how='eq_hist' is not supported by datashader_b200.tf.shade")
+    fn = how if callable(how) else {"log": lambda d, m: np.log1p(np.where(m, np.nan, d)),
+                                    "cbrt": lambda d, m: np.where(m, np.nan, d) ** (1 / 3.),
+                                    "linear": lambda d, m: np.where(m, np.nan, d)}[how]
+    if span is None:
+        offset = np.nanmin(data[~mask])
+    else:
+        offset = np.array(span, dtype=data.dtype)[0]
+        lo, hi = np.array(span).astype(data.dtype) if data.dtype.kind in "iu" else span
+        sel = ~mask
+        data[sel & (data < span[0])] = lo
+        data[sel & ~(data < span[0]) & (data > span[1])] = hi
+    data = data - offset
+    with np.errstate(invalid="ignore", divide="ignore"):
+        t = fn(data, mask)
+        if isinstance(t, (list, tuple)):
+            t = t[0]
+        if span is None:
+            md = np.where(~mask, t, np.nan)
+            nspan = (np.nanmin(md), np.nanmax(md))
+        else:
+            nspan = fn([0, span[1] - span[0]], 0)
+            if isinstance(nspan, (list, tuple)) and len(nspan) == 2 and not np.isscalar(nspan[0]):
+                nspan = nspan[0]
+    t = np.asarray(t, dtype=np.float64)
+    if callable(cmap):
+        scaled = (t - nspan[0]) / (nspan[1] - nspan[0])
+        rgba = np.ascontiguousarray(cmap(scaled, bytes=True))
+        rgba[:, :, 3] = np.where(np.isnan(scaled), 0, alpha).astype(np.uint8)
+        return Image(rgba.view(np.uint32).reshape(t.shape), coords=agg.coords, dims=agg.dims, name=name)
+    # callable `how`, ordinary cmap: the device's linear mapping of the transformed canvas over [nspan0, nspan1]
+    shifted = DataArray(torch.from_numpy(np.where(np.isnan(t), np.nan, t - nspan[0])).to(device), coords=agg.coords, dims=agg.dims)
+    return _interpolate(shifted, cmap, "linear", alpha, (0.0, float(nspan[1] - nspan[0])), min_alpha, name, False, device)
+
+
 def _interpolate(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_levels, device):
     """2-D path: _interpolate (:251-357) with a list / single-colour cmap."""
     data = agg.data
@@ -242,8 +329,8 @@ def _interpolate(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_
         cmap = list(cmap)
     if isinstance(cmap, tuple) and isinstance(cmap[0], str):
         cmap = list(cmap)
-    if callable(cmap):
-        raise NotImplementedError("matplotlib colormaps are not supported by datashader_b200.tf.shade")
+    if callable(cmap) or callable(how):
+        return _interpolate_host(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_levels, device)
     if not isinstance(cmap, (list, str, tuple)):
         raise TypeError("Expected `cmap` of `matplotlib.colors.Colormap`, "
                         f"`list`, `str`, or `tuple`; got: '{type(cmap)}'")
@@ -325,9 +412,7 @@ def shade(agg, cmap=["lightblue", "darkblue"], color_key=Sets1to3, how='eq_hist'
     name = agg.name if name is None else name
     if not ((0 <= min_alpha <= 255) and (0 <= alpha <= 255)):
         raise ValueError(f"min_alpha ({min_alpha}) and alpha ({alpha}) must be between 0 and 255")
-    if callable(how):
-        raise NotImplementedError("callable `how` is not supported by datashader_b200.tf.shade")
-    if how not in _HOW:
+    if not callable(how) and how not in _HOW:
         raise ValueError(f"Unknown interpolation method: {how}")
     if span is not None:
         if how == "eq_hist":
@@ -339,7 +424,7 @@ def shade(agg, cmap=["lightblue", "darkblue"], color_key=Sets1to3, how='eq_hist'
     ndim = len(agg.data.shape)
     if ndim == 2:
         if color_key is not None and isinstance(color_key, dict):
-            raise NotImplementedError("discrete colour keys on 2-D aggregates are not supported yet")
+            return _apply_discrete_colorkey(agg, color_key, alpha, name, color_baseline, device)
         return _interpolate(agg, cmap, how, alpha, span, min_alpha, name, rescale_discrete_levels, device)
     elif ndim == 3:
         return _colorize(agg, color_key, how, alpha, span, min_alpha, name, color_baseline, rescale_discrete_levels, device)

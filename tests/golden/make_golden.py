@@ -293,6 +293,49 @@ def shade_catfloat_cases():
     return out
 
 
+def sqrt_how(d, m):
+    return np.where(m, np.nan, np.sqrt(d))
+
+
+def fake_cmap(x, bytes=True):     # noqa: A002  (a stand-in for a matplotlib colormap: callable(scaled, bytes=True) -> uint8 RGBA)
+    v = np.nan_to_num(np.clip(x, 0, 1))
+    out = np.empty(x.shape + (4,), dtype=np.uint8)
+    out[..., 0] = (v * 255).astype(np.uint8)
+    out[..., 1] = 255 - (v * 200).astype(np.uint8)
+    out[..., 2] = 64
+    out[..., 3] = 255
+    return out
+
+
+def shade_extra_cases():
+    """tf.shade arguments that are Python objects: a callable `how`, a callable cmap (matplotlib-style) and a discrete
+    colour key on a 2-D aggregate (transfer_functions/__init__.py:218-231, 340-349, 535-612)."""
+    import xarray as xr
+    import datashader.transfer_functions as tf
+    out = {}
+    rng = np.random.default_rng(73)
+    H, Wd = 36, 44
+
+    def agg2(data):
+        return xr.DataArray(data, coords={"y": np.arange(H), "x": np.arange(Wd)}, dims=["y", "x"])
+
+    f = np.where(rng.random((H, Wd)) < 0.3, np.nan, rng.random((H, Wd)) * 50)
+    u = rng.poisson(3.0, (H, Wd)).astype(np.uint32)
+    out["x_f64_in"], out["x_u32_in"] = f, u
+    for name, data in (("f64", f), ("u32", u)):
+        out[f"x_{name}_callhow_list"] = np.asarray(tf.shade(agg2(data), cmap=["black", "red", "white"], how=sqrt_how).data)
+        out[f"x_{name}_callhow_single"] = np.asarray(tf.shade(agg2(data), cmap="#3070c0", how=sqrt_how, min_alpha=20).data)
+        for how in ("linear", "log", "cbrt"):
+            out[f"x_{name}_callcmap_{how}"] = np.asarray(tf.shade(agg2(data), cmap=fake_cmap, how=how, alpha=200).data)
+    cats = rng.integers(0, 5, (H, Wd)).astype(np.int32)
+    out["x_cats_in"] = cats
+    key = {1: "red", 2: "#00ff00", 4: (0, 0, 255)}
+    out["x_cats_key"] = np.asarray(tf.shade(agg2(cats), color_key=key).data)
+    out["x_cats_key_a100"] = np.asarray(tf.shade(agg2(cats), color_key=key, alpha=100).data)
+    out["x_cats_key_base"] = np.asarray(tf.shade(agg2(cats), color_key=key, color_baseline=0.25).data)
+    return out
+
+
 def shade_span_cases():
     """tf.shade with an explicit span (clip + fixed normalisation range), on the shade.npz inputs."""
     import xarray as xr
@@ -664,6 +707,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "shade_catfloat.npz"), **shade_catfloat_cases())
         print("shade_catfloat.npz", os.path.getsize(os.path.join(HERE, "shade_catfloat.npz")) // 1024, "KiB")
         return
+    if "--shade-extra-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "shade_extra.npz"), **shade_extra_cases())
+        print("shade_extra.npz", os.path.getsize(os.path.join(HERE, "shade_extra.npz")) // 1024, "KiB")
+        return
     if "--tiles-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "tiles.npz"), **tiles_cases())
         print("tiles.npz", os.path.getsize(os.path.join(HERE, "tiles.npz")) // 1024, "KiB")
@@ -710,6 +757,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "spread.npz"), **spread_cases())
     np.savez_compressed(os.path.join(HERE, "shade_span.npz"), **shade_span_cases())
     np.savez_compressed(os.path.join(HERE, "shade_catfloat.npz"), **shade_catfloat_cases())
+    np.savez_compressed(os.path.join(HERE, "shade_extra.npz"), **shade_extra_cases())
     np.savez_compressed(os.path.join(HERE, "points.npz"), **points_cases())
     np.savez_compressed(os.path.join(HERE, "points_negzero.npz"), **negzero_cases())
     np.savez_compressed(os.path.join(HERE, "partitioned.npz"), **partitioned_cases())

@@ -296,3 +296,30 @@ def test_lines_antialiased_summary_by_where_golden():
                        "where_min_row": ds.where(ds.min("val")), "where_min_other": ds.where(ds.min("val"), "other")}.items():
         got, want = cvs.line(frame, agg=agg, **kw).data, g[f"aa3_{aname}"]
         assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), aname
+
+
+def test_antialiased_lines_at_production_geometry_vs_oracle():
+    """BASELINE config 4's geometry - 3840 x 2160, LinesAxis1 random walks of 1000 samples, line_width 1 - on a 600-line
+    sample: antialiased max (single stage) and min (2-stage, lines long enough to overflow the shared-memory stage-1 table)
+    against the C oracle."""
+    import torch
+    import datashader_b200 as ds
+    from oracle import oracle as ora
+    rng = np.random.default_rng(404)
+    nl, nv = 600, 1000
+    xs = np.tile(np.arange(nv, dtype=np.float32), (nl, 1))
+    ys = np.cumsum(rng.standard_normal((nl, nv)), axis=1).astype(np.float32)
+    val = rng.random(nl).astype(np.float32)
+    cols = {f"x{j}": torch.from_numpy(np.ascontiguousarray(xs[:, j])).cuda() for j in range(nv)}
+    cols.update({f"y{j}": torch.from_numpy(np.ascontiguousarray(ys[:, j])).cuda() for j in range(nv)})
+    cols["value"] = torch.from_numpy(val).cuda()
+    frame = ds.DeviceFrame(cols)
+    xr, yr = (0.0, float(nv - 1)), (float(ys.min()), float(ys.max()))
+    W, H = 3840, 2160
+    cvs = ds.Canvas(W, H, x_range=xr, y_range=yr)
+    view = ora.make_view(W, H, xr, yr)
+    xc, yc = [f"x{j}" for j in range(nv)], [f"y{j}" for j in range(nv)]
+    got = cvs.line(frame, x=xc, y=yc, axis=1, agg=ds.max("value"), line_width=1).data
+    _cmp_aa(got, ora.lines_axis1(xs, ys, view, agg="max", values=val, line_width=1.0), "config-4 geometry, aa max")
+    got = cvs.line(frame, x=xc, y=yc, axis=1, agg=ds.min("value"), line_width=1).data
+    _cmp_aa(got, ora.lines_aa2(xs, ys, view, "min", val, 1.0), "config-4 geometry, aa min (2-stage)")

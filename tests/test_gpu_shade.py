@@ -150,3 +150,35 @@ def test_shade_categorical_float_golden(name):
         visible = cw[..., 3] > 0
         diff = np.abs(cg[..., :3] - cw[..., :3])[visible]
         assert diff.max() <= 1 and (diff > 0).mean() < 0.02, (key, int(diff.max()), float((diff > 0).mean()))
+
+
+def _sqrt_how(d, m):
+    return np.where(m, np.nan, np.sqrt(d))
+
+
+def _fake_cmap(x, bytes=True):     # noqa: A002  (stand-in for a matplotlib colormap; identical to tests/golden/make_golden.py)
+    v = np.nan_to_num(np.clip(x, 0, 1))
+    out = np.empty(x.shape + (4,), dtype=np.uint8)
+    out[..., 0] = (v * 255).astype(np.uint8)
+    out[..., 1] = 255 - (v * 200).astype(np.uint8)
+    out[..., 2] = 64
+    out[..., 3] = 255
+    return out
+
+
+def test_shade_python_callables_and_discrete_keys_golden():
+    """tf.shade with a callable `how`, a callable (matplotlib-style) cmap and a discrete colour key on a 2-D aggregate
+    (transfer_functions/__init__.py:218-231, 340-349, 535-612) vs the real reference (tests/golden/shade_extra.npz)."""
+    import datashader_b200 as ds
+    g = load("shade_extra.npz")
+    for name in ("f64", "u32"):
+        agg = _agg2(g[f"x_{name}_in"])
+        _check(ds.tf.shade(agg, cmap=["black", "red", "white"], how=_sqrt_how).data, g[f"x_{name}_callhow_list"], "linear", f"{name} callable how, list")
+        _check(ds.tf.shade(agg, cmap="#3070c0", how=_sqrt_how, min_alpha=20).data, g[f"x_{name}_callhow_single"], "linear", f"{name} callable how, single")
+        for how in ("linear", "log", "cbrt"):
+            _check(ds.tf.shade(agg, cmap=_fake_cmap, how=how, alpha=200).data, g[f"x_{name}_callcmap_{how}"], "linear", f"{name} callable cmap {how}")
+    cats = _agg2(g["x_cats_in"])
+    key = {1: "red", 2: "#00ff00", 4: (0, 0, 255)}
+    np.testing.assert_array_equal(ds.tf.shade(cats, color_key=key).data, g["x_cats_key"])
+    np.testing.assert_array_equal(ds.tf.shade(cats, color_key=key, alpha=100).data, g["x_cats_key_a100"])
+    np.testing.assert_array_equal(ds.tf.shade(cats, color_key=key, color_baseline=0.25).data, g["x_cats_key_base"])
