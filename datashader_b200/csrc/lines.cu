@@ -10,6 +10,9 @@
 #include "accum.cuh"
 #include <limits.h>
 
+static int g_lines_balanced = 1;       // antialiased single-stage lines: rows balanced over the warp (k_lines_aa_balanced)
+extern "C" int dsb_lines_configure(int balanced) { g_lines_balanced = balanced != 0; return DSB_OK; }
+
 struct LineArgs {
   dsb_view v;
   const void* xs;
@@ -409,6 +412,240 @@ __device__ void draw_segment(const LineArgs& a, const LineCtx& c, bool segment_s
   }
 }
 
+// ---- antialiased segments with the rows balanced over the warp ------------------------------------------------------------
+// ncu on k_lines_axis1 at config 4 (profiles/r02_lines_aa.md): 6.8 of 32 lanes active on average - a thread scans its own
+// segment row by row, and the rows per segment (2 .. 30, |dy| of a random walk) and the pixels per row differ from lane to lane.
+// The rows of a scan conversion are independent once the segment's invariants are known (the left / right edge index of a
+// row depends only on whether its y lies above the corner that follows the lowest one), so a warp first prepares its 32
+// segments (clip, map, corners, unit vectors: uniform work, AaSeg in shared memory), then hands the ROWS of all 32 segments out
+// evenly, 32 at a time.  Same pixels, same arithmetic per pixel, same appends as full_antialias.
+struct AaSeg {
+  double x0, y0, x1, y1, alongx, alongy, length, rightx, righty;
+  double bx[4], by[4];
+  double prev_alongx, prev_alongy, prev_length, prev_rightx, prev_righty;
+  double halfwidth, e0, scale, field;
+  long long row, line;
+  int xmax, ymax, ystart, nrows, lowindex, cat;
+  unsigned char flip_xy, overwrite, segment_start, segment_end, field_nan, pad[3];
+};
+
+// the invariants of full_antialias (line.py:830-905); g.nrows = 0 when nothing is drawn
+__device__ __forceinline__ void aa_prepare(AaSeg& g, double line_width, bool overwrite, double x0, double x1, double y0, double y1,
+                                           bool segment_start, bool segment_end, double xm, double ym, long long nx, long long ny) {
+  g.nrows = 0;
+  if (x0 == x1 && y0 == y1) return;
+  const bool flip_xy = fabs(fsub64(x0, x1)) < fabs(fsub64(y0, y1));
+  if (flip_xy) {
+    double t;
+    t = x0; x0 = y0; y0 = t;
+    t = x1; x1 = y1; y1 = t;
+    t = xm; xm = ym; ym = t;
+  }
+  double scale = 1.0;
+  if (line_width < 1.0) { scale = fmul64(scale, line_width); line_width = 1.0; }
+  const double aa = 1.0;
+  const double halfwidth = fmul64(0.5, fadd64(line_width, aa));
+  const bool flip_order = y1 < y0 || (y1 == y0 && x1 < x0);
+  double alongx = fsub64(x1, x0), alongy = fsub64(y1, y0);
+  const double length = __dsqrt_rn(fadd64(fmul64(alongx, alongx), fmul64(alongy, alongy)));
+  alongx = __ddiv_rn(alongx, length);
+  alongy = __ddiv_rn(alongy, length);
+  const double rightx = alongy, righty = -alongx;
+  if (flip_order) {
+    g.bx[0] = fsub64(x1, fmul64(halfwidth, fsub64(rightx, alongx)));
+    g.bx[1] = fsub64(x1, fmul64(halfwidth, fsub64(-rightx, alongx)));
+    g.bx[2] = fsub64(x0, fmul64(halfwidth, fadd64(-rightx, alongx)));
+    g.bx[3] = fsub64(x0, fmul64(halfwidth, fadd64(rightx, alongx)));
+    g.by[0] = fsub64(y1, fmul64(halfwidth, fsub64(righty, alongy)));
+    g.by[1] = fsub64(y1, fmul64(halfwidth, fsub64(-righty, alongy)));
+    g.by[2] = fsub64(y0, fmul64(halfwidth, fadd64(-righty, alongy)));
+    g.by[3] = fsub64(y0, fmul64(halfwidth, fadd64(righty, alongy)));
+  } else {
+    g.bx[0] = fadd64(x0, fmul64(halfwidth, fsub64(rightx, alongx)));
+    g.bx[1] = fadd64(x0, fmul64(halfwidth, fsub64(-rightx, alongx)));
+    g.bx[2] = fadd64(x1, fmul64(halfwidth, fadd64(-rightx, alongx)));
+    g.bx[3] = fadd64(x1, fmul64(halfwidth, fadd64(rightx, alongx)));
+    g.by[0] = fadd64(y0, fmul64(halfwidth, fsub64(righty, alongy)));
+    g.by[1] = fadd64(y0, fmul64(halfwidth, fsub64(-righty, alongy)));
+    g.by[2] = fadd64(y1, fmul64(halfwidth, fadd64(-righty, alongy)));
+    g.by[3] = fadd64(y1, fmul64(halfwidth, fadd64(righty, alongy)));
+  }
+  long long xmax = nx - 1, ymax = ny - 1;
+  if (flip_xy) { long long t = xmax; xmax = ymax; ymax = t; }
+  int lowindex;
+  if (flip_order) lowindex = x0 > x1 ? 0 : 1;
+  else lowindex = x1 > x0 ? 0 : 1;
+  g.prev_alongx = g.prev_alongy = g.prev_length = g.prev_rightx = g.prev_righty = 0.0;
+  if (!overwrite && !segment_start) {
+    double pax = fsub64(x0, xm), pay = fsub64(y0, ym);
+    const double pl = __dsqrt_rn(fadd64(fmul64(pax, pax), fmul64(pay, pay)));
+    if (pl > 0.0) {
+      pax = __ddiv_rn(pax, pl);
+      pay = __ddiv_rn(pay, pl);
+      g.prev_alongx = pax; g.prev_alongy = pay; g.prev_length = pl; g.prev_rightx = pay; g.prev_righty = -pax;
+    } else {
+      g.prev_alongx = pax; g.prev_alongy = pay; g.prev_length = pl;
+      overwrite = true;
+    }
+  }
+  const long long ystart = (long long)clampd(ceil(g.by[lowindex]), 0.0, (double)ymax);
+  const long long yend = (long long)clampd(floor(g.by[(lowindex + 2) & 3]), 0.0, (double)ymax);
+  g.x0 = x0; g.y0 = y0; g.x1 = x1; g.y1 = y1; g.alongx = alongx; g.alongy = alongy; g.length = length;
+  g.rightx = rightx; g.righty = righty; g.halfwidth = halfwidth; g.e0 = fmul64(0.5, fsub64(line_width, aa)); g.scale = scale;
+  g.xmax = (int)xmax; g.ymax = (int)ymax; g.ystart = (int)ystart; g.lowindex = lowindex;
+  g.flip_xy = flip_xy; g.overwrite = overwrite; g.segment_start = segment_start; g.segment_end = segment_end;
+  g.nrows = yend >= ystart ? (int)(yend - ystart + 1) : 0;
+}
+
+// one row of the scan conversion (line.py:906-981).  The edge indices are those the reference's running ll / rl hold at row y:
+// each advances once, at the first row above the corner that follows the lowest one.
+__device__ __forceinline__ void aa_row(const AaSeg& g, const LineCtx& c, long long y) {
+  const double yd = (double)y;
+  const int lowindex = g.lowindex;
+  int ll = lowindex, lu = (ll + 1) & 3, rl = lowindex, ru = (rl + 3) & 3;
+  if (yd > g.by[lu]) { ll = lu; lu = (ll + 1) & 3; }
+  if (yd > g.by[ru]) { rl = ru; ru = (rl + 3) & 3; }
+  const long long xleft = (long long)clampd(ceil(x_intercept(yd, g.bx[ll], g.by[ll], g.bx[lu], g.by[lu])), 0.0, (double)g.xmax);
+  const long long xright = (long long)clampd(floor(x_intercept(yd, g.bx[rl], g.by[rl], g.bx[ru], g.by[ru])), 0.0, (double)g.xmax);
+  const double x0 = g.x0, y0 = g.y0, x1 = g.x1, y1 = g.y1;
+  const double ry0 = fsub64(yd, y0), ry1 = fsub64(yd, y1);
+  const bool overwrite = g.overwrite, segment_start = g.segment_start, segment_end = g.segment_end;
+  for (long long x = xleft; x <= xright; x++) {
+    const double rx0 = fsub64((double)x, x0);
+    const double along = fadd64(fmul64(rx0, g.alongx), fmul64(ry0, g.alongy));
+    bool prev_correction = false;
+    double distance;
+    if (along < 0.0) {
+      if (overwrite || segment_start || fadd64(fmul64(rx0, g.prev_alongx), fmul64(ry0, g.prev_alongy)) > 0.0)
+        distance = __dsqrt_rn(fadd64(fmul64(rx0, rx0), fmul64(ry0, ry0)));
+      else continue;
+    } else if (along > g.length) {
+      if (overwrite || segment_end) {
+        const double rx1 = fsub64((double)x, x1);
+        distance = __dsqrt_rn(fadd64(fmul64(rx1, rx1), fmul64(ry1, ry1)));
+      } else continue;
+    } else {
+      distance = fabs(fadd64(fmul64(rx0, g.rightx), fmul64(ry0, g.righty)));
+      if (!overwrite && !segment_start) {
+        const double pa = fadd64(fmul64(rx0, g.prev_alongx), fmul64(ry0, g.prev_alongy));
+        if (-g.prev_length <= pa && pa <= 0.0 && fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty))) <= g.halfwidth)
+          prev_correction = true;
+      }
+    }
+    double value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, distance)), g.scale);
+    double prev_value = 0.0;
+    if (prev_correction) {
+      const double prev_distance = fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty)));
+      prev_value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, prev_distance)), g.scale);
+      if (value <= prev_value) value = 0.0;
+    }
+    if (value > 0.0) {
+      if (g.flip_xy) append_aa(c, y, x, value, prev_value);
+      else append_aa(c, x, y, value, prev_value);
+    }
+  }
+}
+
+// clip + map of draw_segment (line.py:1045-1085) for the antialiased form: false = nothing to draw
+template <typename XY>
+__device__ __forceinline__ bool aa_clip_map(const LineArgs& a, bool& segment_start, double& x0, double& x1, double& y0, double& y1,
+                                            double& xm, double& ym) {
+  const dsb_view& v = a.v;
+  bool skip = (x0 != x0) || (y0 != y0) || (x1 != x1) || (y1 != y1);
+  if (x0 < v.xmin && x1 < v.xmin) skip = true;
+  else if (x0 > v.xmax && x1 > v.xmax) skip = true;
+  else if (y0 < v.ymin && y1 < v.ymin) skip = true;
+  else if (y0 > v.ymax && y1 > v.ymax) skip = true;
+  double t0 = 0.0, t1 = 1.0;
+  const double dx1 = seg_delta<XY>(x1, x0);
+  if (!clipt(-dx1, fsub64(x0, v.xmin), t0, t1)) skip = true;
+  if (!clipt(dx1, fsub64(v.xmax, x0), t0, t1)) skip = true;
+  const double dy1 = seg_delta<XY>(y1, y0);
+  if (!clipt(-dy1, fsub64(y0, v.ymin), t0, t1)) skip = true;
+  if (!clipt(dy1, fsub64(v.ymax, y0), t0, t1)) skip = true;
+  if (skip) return false;
+  bool clipped_start = false;
+  if (t1 < 1) { x1 = fadd64(x0, fmul64(t1, dx1)); y1 = fadd64(y0, fmul64(t1, dy1)); }
+  if (t0 > 0) { clipped_start = true; x0 = fadd64(x0, fmul64(t0, dx1)); y0 = fadd64(y0, fmul64(t0, dy1)); }
+  segment_start = segment_start || clipped_start;
+  x0 = fsub64(fadd64(fmul64(map_axis<XY>(v.x_log, x0), v.sx), v.tx), 0.5);
+  y0 = fsub64(fadd64(fmul64(map_axis<XY>(v.y_log, y0), v.sy), v.ty), 0.5);
+  x1 = fsub64(fadd64(fmul64(map_axis<XY>(v.x_log, x1), v.sx), v.tx), 0.5);
+  y1 = fsub64(fadd64(fmul64(map_axis<XY>(v.y_log, y1), v.sy), v.ty), 0.5);
+  if (!segment_start) {
+    xm = fsub64(fadd64(fmul64(map_axis<XY>(v.x_log, xm), v.sx), v.tx), 0.5);
+    ym = fsub64(fadd64(fmul64(map_axis<XY>(v.y_log, ym), v.sy), v.ty), 0.5);
+  } else { xm = 0.0; ym = 0.0; }
+  return true;
+}
+
+template <typename XY>
+__global__ void __launch_bounds__(128) k_lines_aa_balanced(const LineArgs a) {
+  __shared__ AaSeg segs[128];
+  __shared__ int prefix[128];
+  const XY* __restrict__ xs = (const XY*)a.xs;
+  const XY* __restrict__ ys = (const XY*)a.ys;
+  const long long nseg = a.nverts - 1;
+  const long long total = a.nlines * nseg;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+  AaSeg* const wseg = segs + w0;
+  int* const wpre = prefix + w0;
+  // every warp walks whole batches of 32 consecutive segments; the loop bound is warp-uniform
+  for (long long s0 = (long long)blockIdx.x * blockDim.x + w0; s0 < total; s0 += stride) {
+    const long long s = s0 + lane;
+    AaSeg& g = wseg[lane];
+    g.nrows = 0;
+    if (s < total) {
+      const long long i = s / nseg, j = s - i * nseg;
+      const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+      double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
+      bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
+      double xm = 0.0, ym = 0.0;
+      if (j > 0) {
+        xm = (double)xs[ox - 1]; ym = (double)ys[oy - 1];
+        segment_start = (xm != xm) || (ym != ym);
+        if (segment_start) { xm = 0.0; ym = 0.0; }
+      }
+      bool segment_end = (j == a.nverts - 2);
+      if (!segment_end) {
+        const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
+        segment_end = (xn != xn) || (yn != yn);
+      }
+      const long long vi = a.value_per_vertex ? j : i;
+      if (aa_clip_map<XY>(a, segment_start, x0, x1, y0, y1, xm, ym))
+        aa_prepare(g, a.line_width, a.overwrite != 0, x0, x1, y0, y1, segment_start, segment_end, xm, ym, a.nx, a.ny);
+      g.field = a.val_dtype != DSB_NONE ? load_f64(a.val, a.val_dtype, vi) : 0.0;
+      g.field_nan = a.val_dtype != DSB_NONE && (g.field != g.field);
+      g.line = vi; g.row = a.row_offset + vi; g.cat = 0;
+      if (a.ncat > 0) {
+        int cc = load_cat(a.cat, a.cat_dtype, vi);
+        if (cc < 0) cc += a.ncat;
+        g.cat = (cc < 0 || cc >= a.ncat) ? -1 : cc;
+      }
+    }
+    // inclusive prefix of the row counts over the warp
+    int incl = g.nrows;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    wpre[lane] = incl;
+    const int rows_total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    for (int r = lane; r < rows_total; r += 32) {
+      int lo = 0, hi = 31;                       // first lane whose inclusive prefix exceeds r
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (wpre[mid] > r) hi = mid; else lo = mid + 1; }
+      const AaSeg& q = wseg[lo];
+      const long long y = (long long)q.ystart + (r - (wpre[lo] - q.nrows));
+      LineCtx c;
+      c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
+      c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row;
+      c.cat = q.cat; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
+      aa_row(q, c, y);
+    }
+    __syncwarp();
+  }
+}
+
 // one thread per (line, segment): extend_cuda, line.py:1321-1332 + perform_extend_line :1250-1275
 template <typename XY>
 __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
@@ -664,8 +901,11 @@ static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char*
   long long cap = (long long)dsb_num_sms() * 16;
   int grid = (int)(want < cap ? want : cap);
   cudaStream_t s = (cudaStream_t)stream;
-  dsb_note_kernel("k_lines_axis1<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
-  if (xy_dtype == DSB_F32) k_lines_axis1<float><<<grid, threads, 0, s>>>(a);
+  const bool balanced = g_lines_balanced && a.line_width > 0.0 && !a.use_plan;
+  dsb_note_kernel(balanced ? "k_lines_aa_balanced<%s>" : "k_lines_axis1<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
+  if (balanced && xy_dtype == DSB_F32) k_lines_aa_balanced<float><<<grid, threads, 0, s>>>(a);
+  else if (balanced && xy_dtype == DSB_F64) k_lines_aa_balanced<double><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F32) k_lines_axis1<float><<<grid, threads, 0, s>>>(a);
   else if (xy_dtype == DSB_F64) k_lines_axis1<double><<<grid, threads, 0, s>>>(a);
   else { dsb_set_error("%s: xy_dtype must be f32 or f64", what); return DSB_ERR_ARG; }
   DSB_CUDA_CHECK_LAUNCH(what);

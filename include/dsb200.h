@@ -141,6 +141,8 @@ int dsb_points_priv(const dsb_view* view, const void* x, const void* y, int32_t 
 int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t n);
 int dsb_points_routed(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
                       const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream);
+/* A/B switch of the antialiased single-stage line kernel: 1 (default) = rows of the scan conversion balanced over the warp */
+int dsb_lines_configure(int balanced);
 /* smallest n dsb_points_routed accepts (default 2^24; tests lower it) */
 int dsb_routed_configure(int64_t min_rows);
 

@@ -323,3 +323,39 @@ def test_antialiased_lines_at_production_geometry_vs_oracle():
     _cmp_aa(got, ora.lines_axis1(xs, ys, view, agg="max", values=val, line_width=1.0), "config-4 geometry, aa max")
     got = cvs.line(frame, x=xc, y=yc, axis=1, agg=ds.min("value"), line_width=1).data
     _cmp_aa(got, ora.lines_aa2(xs, ys, view, "min", val, 1.0), "config-4 geometry, aa min (2-stage)")
+
+
+def test_balanced_antialiased_kernel_equals_per_thread_kernel():
+    """k_lines_aa_balanced (rows of the scan conversion handed out evenly over the warp) against k_lines_axis1 (one thread
+    per segment): identical pixels and values for max / any (bit for bit), count / sum / mean within float-add ordering."""
+    import torch
+    import datashader_b200 as ds
+    from datashader_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(77)
+    nl, nv = 700, 60
+    xs = (np.cumsum(rng.normal(0, 0.02, (nl, nv)), axis=1) + rng.random((nl, 1))).astype(np.float32)
+    ys = (np.cumsum(rng.normal(0, 0.03, (nl, nv)), axis=1) + rng.random((nl, 1))).astype(np.float32)
+    xs[rng.random((nl, nv)) < 0.02] = np.nan
+    val = (rng.random(nl) * 5 - 1).astype(np.float32)
+    cols = {f"x{j}": torch.from_numpy(np.ascontiguousarray(xs[:, j])).cuda() for j in range(nv)}
+    cols.update({f"y{j}": torch.from_numpy(np.ascontiguousarray(ys[:, j])).cuda() for j in range(nv)})
+    cols["val"] = torch.from_numpy(val).cuda()
+    frame = ds.DeviceFrame(cols)
+    xc, yc = [f"x{j}" for j in range(nv)], [f"y{j}" for j in range(nv)]
+    cvs = ds.Canvas(500, 300, x_range=(0.1, 0.9), y_range=(0.0, 1.2))
+    for lw in (1.0, 3.5, 0.5):
+        for name, agg, exact in (("max", ds.max("val"), True), ("any", ds.any(), True), ("count", ds.count(), False),
+                                 ("sum", ds.sum("val"), False), ("mean", ds.mean("val"), False)):
+            res = {}
+            for balanced in (1, 0):
+                _lib.check(L.dsb_lines_configure(balanced))
+                try:
+                    res[balanced] = cvs.line(frame, x=xc, y=yc, axis=1, agg=agg, line_width=lw).data
+                    assert (b"balanced" in L.dsb_last_kernel()) == bool(balanced)
+                finally:
+                    _lib.check(L.dsb_lines_configure(1))
+            if exact:
+                assert np.array_equal(res[1], res[0], equal_nan=True), (name, lw)
+            else:
+                _cmp_aa(res[1], res[0], f"balanced {name} lw{lw}", rtol=1e-5)
