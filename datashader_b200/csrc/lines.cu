@@ -631,18 +631,23 @@ __global__ void __launch_bounds__(128) k_lines_aa_balanced(const LineArgs a) {
     wpre[lane] = incl;
     const int rows_total = __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
-    for (int r = lane; r < rows_total; r += 32) {
-      int lo = 0, hi = 31;                       // first lane whose inclusive prefix exceeds r
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (wpre[mid] > r) hi = mid; else lo = mid + 1; }
-      const AaSeg& q = wseg[lo];
-      const long long y = (long long)q.ystart + (r - (wpre[lo] - q.nrows));
-      LineCtx c;
-      c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
-      c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row;
-      c.cat = q.cat; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
-      aa_row(q, c, y);
+    // warp-uniform trip count and a __syncwarp() per round: without it the lanes drift apart over the rounds (a lane that
+    // finishes a short row starts its next one alone) - ncu showed 5.9 active lanes at the top of this loop
+    for (int r0 = 0; r0 < rows_total; r0 += 32) {
+      const int r = r0 + lane;
+      if (r < rows_total) {
+        int lo = 0, hi = 31;                     // first lane whose inclusive prefix exceeds r
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (wpre[mid] > r) hi = mid; else lo = mid + 1; }
+        const AaSeg& q = wseg[lo];
+        const long long y = (long long)q.ystart + (r - (wpre[lo] - q.nrows));
+        LineCtx c;
+        c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
+        c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row;
+        c.cat = q.cat; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
+        aa_row(q, c, y);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
