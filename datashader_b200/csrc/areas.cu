@@ -149,7 +149,10 @@ __global__ void __launch_bounds__(128) k_areas(const AreaArgs a) {
   const long long total = a.nlines * nseg;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool to_line = ys1 != nullptr;
-  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) {
+  // warp-uniform trip count + __syncwarp() per trapezoid: keeps the lanes together over the rounds (see k_lines_axis1)
+  for (long long s0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); s0 < total; s0 += stride, __syncwarp()) {
+    const long long s = s0 + (threadIdx.x & 31);
+    if (s >= total) continue;
     const long long i = s / nseg, j = s - i * nseg;
     const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
     const double x0 = (double)xs[ox], x1 = (double)xs[ox + 1];

@@ -659,7 +659,11 @@ __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
   const long long nseg = a.nverts - 1;
   const long long total = a.nlines * nseg;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) {
+  // warp-uniform trip count + __syncwarp() per segment: the pixel loops of the 32 segments differ in length, and without a
+  // reconvergence point per round the lanes drift apart over the rounds (ncu: 6.8 active lanes, profiles/r02_lines_aa.md)
+  for (long long s0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); s0 < total; s0 += stride, __syncwarp()) {
+    const long long s = s0 + (threadIdx.x & 31);
+    if (s >= total) continue;
     const long long i = s / nseg, j = s - i * nseg;
     const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
     const double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
