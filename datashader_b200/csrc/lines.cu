@@ -778,6 +778,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
   uint32_t* tlist = HASH ? nullptr : b.tlists + (long long)blockIdx.x * AA2_LIST_CAP * AA2_THREADS;
   __shared__ int s_bbox[2];
   __shared__ int s_skip;
+  __shared__ int s_prefix[AA2_THREADS];
   const long long nseg = a.nverts - 1;
   const long long nwork = HASH ? (a.nlines + G - 1) / G : (long long)*b.redo_n;
   if (HASH) {
@@ -802,6 +803,61 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
     }
     int bbox[2] = {INT_MAX, -1};
     int tn = 0;
+    if (!HASH) {
+      // global stage-1 path (long lines): the rows of the warp's 32 segments are handed out evenly, as in k_lines_aa_balanced
+      AaSeg* const wseg = (AaSeg*)aa2_smem + (threadIdx.x & ~31);
+      int* const wpre = s_prefix + (threadIdx.x & ~31);
+      const int lane = threadIdx.x & 31;
+      for (long long t0 = threadIdx.x & ~31; t0 < glines * nseg; t0 += blockDim.x) {
+        const long long t = t0 + lane;
+        AaSeg& g = wseg[lane];
+        g.nrows = 0;
+        if (t < glines * nseg) {
+          const long long gl = t / nseg, j = t - gl * nseg, i = i0 + gl;
+          const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+          double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
+          bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
+          if (j > 0) {
+            const double xm = (double)xs[ox - 1], ym = (double)ys[oy - 1];
+            segment_start = (xm != xm) || (ym != ym);
+          }
+          bool segment_end = (j == a.nverts - 2);
+          if (!segment_end) {
+            const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
+            segment_end = (xn != xn) || (yn != yn);
+          }
+          const long long vi = a.value_per_vertex ? j : i;
+          double xm0 = 0.0, ym0 = 0.0;          // xm = ym = 0 in 2-stage mode (line.py:1266-1268); unused: overwrite is True
+          if (aa_clip_map<XY>(a, segment_start, x0, x1, y0, y1, xm0, ym0))
+            aa_prepare(g, a.line_width, true, x0, x1, y0, y1, segment_start, segment_end, 0.0, 0.0, a.nx, a.ny);
+          g.field = a.val_dtype != DSB_NONE ? load_f64(a.val, a.val_dtype, vi) : 0.0;
+          g.field_nan = a.val_dtype != DSB_NONE && (g.field != g.field);
+          g.line = vi; g.row = a.row_offset + vi; g.cat = 0;
+        }
+        int incl = g.nrows;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
+        wpre[lane] = incl;
+        const int rows_total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        for (int r0 = 0; r0 < rows_total; r0 += 32) {
+          const int r = r0 + lane;
+          if (r < rows_total) {
+            int lo = 0, hi = 31;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (wpre[mid] > r) hi = mid; else lo = mid + 1; }
+            const AaSeg& q = wseg[lo];
+            const long long y = (long long)q.ystart + (r - (wpre[lo] - q.nrows));
+            LineCtx c;
+            c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = temp; c.mask = nullptr;
+            c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row; c.cat = 0; c.ncat = 0;
+            c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox; c.tlist = tlist; c.tn = &tn;
+            c.hkeys = nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = 0;
+            aa_row(q, c, y);
+          }
+          __syncwarp();
+        }
+      }
+    } else
     for (long long t = threadIdx.x; t < glines * nseg; t += blockDim.x) {
       const long long g = t / nseg, j = t - g * nseg, i = i0 + g;
       const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
@@ -1053,12 +1109,14 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
     cudaFuncSetAttribute(k_lines_aa2<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (use_hash) k_lines_aa2<float, true><<<(int)hgrid, AA2_THREADS, smem, s>>>(a, b, (int)G);
     else k_aa2_queue_all<<<dsb_num_sms(), 256, 0, s>>>(b.redo_n, b.redo, (unsigned int)nlines);
-    k_lines_aa2<float, false><<<(int)nctas, AA2_THREADS, 0, s>>>(a, b, 1);
+    cudaFuncSetAttribute(k_lines_aa2<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AA2_THREADS * sizeof(AaSeg)));
+    k_lines_aa2<float, false><<<(int)nctas, AA2_THREADS, AA2_THREADS * sizeof(AaSeg), s>>>(a, b, 1);
   } else if (xy_dtype == DSB_F64) {
     cudaFuncSetAttribute(k_lines_aa2<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (use_hash) k_lines_aa2<double, true><<<(int)hgrid, AA2_THREADS, smem, s>>>(a, b, (int)G);
     else k_aa2_queue_all<<<dsb_num_sms(), 256, 0, s>>>(b.redo_n, b.redo, (unsigned int)nlines);
-    k_lines_aa2<double, false><<<(int)nctas, AA2_THREADS, 0, s>>>(a, b, 1);
+    cudaFuncSetAttribute(k_lines_aa2<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AA2_THREADS * sizeof(AaSeg)));
+    k_lines_aa2<double, false><<<(int)nctas, AA2_THREADS, AA2_THREADS * sizeof(AaSeg), s>>>(a, b, 1);
   } else { dsb_set_error("dsb_lines_aa2: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
   DSB_CUDA_CHECK_LAUNCH("dsb_lines_aa2");
   return DSB_OK;
