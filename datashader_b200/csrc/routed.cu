@@ -273,11 +273,35 @@ __global__ void __launch_bounds__(256) k_route_slow(const __grid_constant__ Rout
 }
 
 // ---- pass 2 ----------------------------------------------------------------------------------------------------------
-template <int OP>
+// TMA bulk-copy helpers (cp.async.bulk + mbarrier, the 1-D form: a bucket's records are one contiguous run)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+               :: "r"(bar), "r"(parity) : "memory");
+}
+
+constexpr uint32_t RE_CHUNK = 2048;        // records per TMA chunk (16 KB): two per thread
+constexpr uint32_t RE_STAGES = 3;          // chunks in flight per SM (48 KB) next to the 176 KB tile
+
+// One CTA per SM takes buckets off a queue.  TMA = true: thread 0 streams the bucket's records through a 3-stage shared-memory
+// ring with bulk copies (48 KB in flight per SM without holding registers; the LDG form has 16 KB in flight), and the first chunks of
+// the NEXT bucket are already on their way while the tile is folded into the canvas.  TMA = false is the plain-load A/B arm.
+template <int OP, bool TMA>
 __global__ void __launch_bounds__(1024, 1) k_route_eat(const __grid_constant__ RouteArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* tile = (uint32_t*)smem;
   __shared__ uint32_t next;
+  __shared__ __align__(8) unsigned long long bars[RE_STAGES];
   constexpr uint32_t IDENT = OP == R_MAX32 ? (uint32_t)INT_MIN : OP == R_MIN32 ? (uint32_t)INT_MAX : OP == R_MINROW ? 0xffffffffu : 0u;
   auto eat = [&](uint32_t key, uint32_t pay) {
     const uint32_t l = key & 0xffffu;
@@ -287,25 +311,71 @@ __global__ void __launch_bounds__(1024, 1) k_route_eat(const __grid_constant__ R
     else if (OP == R_MAXROW) atomicMax(tile + l, pay + 1u);          // 0 = no row yet
     else atomicAdd(tile + l, 1u);
   };
+  // ring: [RE_STAGES][RE_CHUNK] records behind the tile (the tile is padded to 128 bytes by the launcher)
+  const uint32_t tile_bytes = (a.cpb * 4 + 127) & ~127u;
+  const uint4* ring = (const uint4*)(smem + tile_bytes);
+  const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(bars);
+  uint32_t g = 0;                                                     // chunks consumed so far: stage g % 3, parity (g / 3) & 1
+  auto issue = [&](uint32_t b, uint32_t c, uint32_t gi) {            // thread 0: chunk c of bucket b goes into stage gi % 3
+    const uint32_t nrec = min(a.cursor[b], a.cap[b]);
+    const uint32_t m = min(RE_CHUNK, nrec - c * RE_CHUNK);
+    const uint32_t bytes = ((m + 1) & ~1u) * 8;                       // cap[b] is even: the odd record's neighbour is inside the region
+    const uint32_t st = gi % RE_STAGES;
+    mbar_expect_tx(bar_s + 8 * st, bytes);
+    tma_load_1d(ring_s + st * (RE_CHUNK * 8), a.recs + a.off[b] + (size_t)c * RE_CHUNK, bytes, bar_s + 8 * st);
+  };
+  auto prefetch = [&](uint32_t b) {                                  // thread 0: the first chunks of a bucket
+    if (b >= a.nb) return;
+    const uint32_t nrec = min(a.cursor[b], a.cap[b]);
+    const uint32_t nch = (nrec + RE_CHUNK - 1) / RE_CHUNK;
+    for (uint32_t c = 0; c < nch && c < RE_STAGES; c++) issue(b, c, g + c);
+  };
+  if (TMA && threadIdx.x == 0) {
+    for (uint32_t i = 0; i < RE_STAGES; i++) mbar_init(bar_s + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x == 0) { next = atomicAdd(a.queue, 1u); }
+  __syncthreads();
+  if (TMA && threadIdx.x == 0) prefetch(next);
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) next = atomicAdd(a.queue, 1u);
-    __syncthreads();
     const uint32_t b = next;
     if (b >= a.nb) break;
     for (uint32_t q = threadIdx.x; q < a.cpb; q += 1024) tile[q] = IDENT;
-    __syncthreads();
+    __syncthreads();                                                  // tile ready; everyone has read `next`
     const uint32_t nrec = min(a.cursor[b], a.cap[b]);
-    const unsigned long long* base = a.recs + a.off[b];              // off and cap are even: 16-byte aligned
-    const uint4* r4 = (const uint4*)base;
-    const uint32_t n2 = nrec >> 1;
-    for (uint32_t i = threadIdx.x; i < n2; i += 1024) {
-      const uint4 q = __ldcs(r4 + i);
-      eat(q.x, q.y);
-      eat(q.z, q.w);
+    if (TMA) {
+      const uint32_t nch = (nrec + RE_CHUNK - 1) / RE_CHUNK;
+      for (uint32_t c = 0; c < nch; c++, g++) {
+        const uint32_t st = g % RE_STAGES;
+        mbar_wait(bar_s + 8 * st, (g / RE_STAGES) & 1u);
+        const uint32_t m = min(RE_CHUNK, nrec - c * RE_CHUNK);
+        if (2 * threadIdx.x < m) {
+          const uint4 q = ring[st * (RE_CHUNK / 2) + threadIdx.x];
+          eat(q.x, q.y);
+          if (2 * threadIdx.x + 1 < m) eat(q.z, q.w);
+        }
+        __syncthreads();                                              // the stage is free again
+        if (threadIdx.x == 0) {
+          if (c + RE_STAGES < nch) issue(b, c + RE_STAGES, g + RE_STAGES);
+          else if (c + 1 == nch) { next = atomicAdd(a.queue, 1u); g++; prefetch(next); g--; }   // all stages are free here
+        }
+      }
+      if (nch == 0) {
+        if (threadIdx.x == 0) { next = atomicAdd(a.queue, 1u); prefetch(next); }
+      }
+    } else {
+      const unsigned long long* base = a.recs + a.off[b];            // off and cap are even: 16-byte aligned
+      const uint4* r4 = (const uint4*)base;
+      const uint32_t n2 = nrec >> 1;
+      for (uint32_t i = threadIdx.x; i < n2; i += 1024) {
+        const uint4 q = __ldcs(r4 + i);
+        eat(q.x, q.y);
+        eat(q.z, q.w);
+      }
+      if ((nrec & 1) && threadIdx.x == 0) { const unsigned long long q = base[nrec - 1]; eat((uint32_t)q, (uint32_t)(q >> 32)); }
+      __syncthreads();
+      if (threadIdx.x == 0) next = atomicAdd(a.queue, 1u);
     }
-    if ((nrec & 1) && threadIdx.x == 0) { const unsigned long long q = base[nrec - 1]; eat((uint32_t)q, (uint32_t)(q >> 32)); }
-    __syncthreads();
     // fold the tile into the canvas: this CTA is the only writer of these cells now (pass 1 has finished)
     const uint32_t c0 = b * a.cpb;
     for (uint32_t q = threadIdx.x; q < a.cpb && c0 + q < a.ncell; q += 1024) {
@@ -317,11 +387,14 @@ __global__ void __launch_bounds__(1024, 1) k_route_eat(const __grid_constant__ R
       else if (OP == R_MAXROW) { long long* c = (long long*)a.canvas + c0 + q; const long long r = a.row_offset + (long long)t - 1; if (r > *c) *c = r; }
       else ((unsigned int*)a.canvas)[c0 + q] += t;
     }
+    __syncthreads();                                                  // `next` is visible; the tile may be cleared
   }
 }
 
 // ---- entry points ------------------------------------------------------------------------------------------------------
 static long long g_routed_min_rows = 1LL << 24;
+static bool g_routed_tma = true;
+void dsb_routed_set_tma(bool on) { g_routed_tma = on; }
 
 extern "C" int dsb_routed_configure(int64_t min_rows) { g_routed_min_rows = min_rows; return DSB_OK; }
 
@@ -345,10 +418,13 @@ extern "C" int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t
 template <int OP>
 static void route_launch(const RouteArgs& a, size_t smem1, size_t smem2, cudaStream_t s) {
   cudaFuncSetAttribute(k_route_bin<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-  cudaFuncSetAttribute(k_route_eat<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  const size_t smem2t = ((smem2 + 127) & ~(size_t)127) + (size_t)RE_STAGES * RE_CHUNK * 8;
+  cudaFuncSetAttribute(k_route_eat<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2t);
+  cudaFuncSetAttribute(k_route_eat<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   k_route_bin<OP><<<dsb_num_sms() * 2, RT, smem1, s>>>(a);
   k_route_slow<OP><<<dsb_num_sms() * 2, 256, 0, s>>>(a);
-  k_route_eat<OP><<<dsb_num_sms(), 1024, smem2, s>>>(a);
+  if (g_routed_tma) k_route_eat<OP, true><<<dsb_num_sms(), 1024, smem2t, s>>>(a);
+  else k_route_eat<OP, false><<<dsb_num_sms(), 1024, smem2, s>>>(a);
 }
 
 extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,

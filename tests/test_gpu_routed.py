@@ -13,15 +13,17 @@ pytestmark = pytest.mark.gpu
 NAMES = ["max_v32", "min_v32", "first_v32", "last_v32", "count", "count_v32", "where_first_v32_other", "where_last_v32_row"]
 
 
-@pytest.fixture()
-def routed():
+@pytest.fixture(params=[1, 0], ids=["tma", "ldg"])
+def routed(request):
     import datashader_b200 as ds
     from datashader_b200 import _lib
     L = _lib.lib()
     old = (ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16)
     ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16 = 0, 1, False, False
     _lib.check(L.dsb_routed_configure(0))
+    _lib.check(L.dsb_configure(b"routed_tma", request.param))      # pass 2 through the TMA ring / through plain loads
     yield ds
+    _lib.check(L.dsb_configure(b"routed_tma", 1))
     ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16 = old
     _lib.check(L.dsb_routed_configure(1 << 24))
 
