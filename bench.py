@@ -421,7 +421,8 @@ class Bench:
         cvs = ds.Canvas(8192, 8192, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
         out = {"workload": f"Canvas(8192x8192).points, {n_total:.0e} float32 points in total over {self.world} GPU(s)",
                "points_total": n_total}
-        for name, agg in (("max", ds.max("value")), ("first", ds.first("value")), ("where_max", ds.where(ds.max("value")))):
+        for name, agg in (("max", ds.max("value")), ("first", ds.first("value")),
+                          ("where_first", ds.where(ds.first("value"))), ("where_max", ds.where(ds.max("value")))):
             r = self.timed(lambda: cvs.points(frame, "x", "y", agg), 4, 3)
             out[name] = {"ms": r["ms"], "gpoints_per_s": n_total / r["ms"] / 1e6, "roofline": self.roofline(r, n, 12)}
         return out

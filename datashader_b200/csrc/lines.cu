@@ -497,53 +497,62 @@ __device__ __forceinline__ void aa_prepare(AaSeg& g, double line_width, bool ove
   g.nrows = yend >= ystart ? (int)(yend - ystart + 1) : 0;
 }
 
-// one row of the scan conversion (line.py:906-981).  The edge indices are those the reference's running ll / rl hold at row y:
-// each advances once, at the first row above the corner that follows the lowest one.
-__device__ __forceinline__ void aa_row(const AaSeg& g, const LineCtx& c, long long y) {
+// one row of the scan conversion (line.py:906-981): its pixel span.  The edge indices are those the reference's running ll / rl
+// hold at row y: each advances once, at the first row above the corner that follows the lowest one.
+__device__ __forceinline__ void aa_row_span(const AaSeg& g, long long y, long long& xleft, long long& xright) {
   const double yd = (double)y;
   const int lowindex = g.lowindex;
   int ll = lowindex, lu = (ll + 1) & 3, rl = lowindex, ru = (rl + 3) & 3;
   if (yd > g.by[lu]) { ll = lu; lu = (ll + 1) & 3; }
   if (yd > g.by[ru]) { rl = ru; ru = (rl + 3) & 3; }
-  const long long xleft = (long long)clampd(ceil(x_intercept(yd, g.bx[ll], g.by[ll], g.bx[lu], g.by[lu])), 0.0, (double)g.xmax);
-  const long long xright = (long long)clampd(floor(x_intercept(yd, g.bx[rl], g.by[rl], g.bx[ru], g.by[ru])), 0.0, (double)g.xmax);
+  xleft = (long long)clampd(ceil(x_intercept(yd, g.bx[ll], g.by[ll], g.bx[lu], g.by[lu])), 0.0, (double)g.xmax);
+  xright = (long long)clampd(floor(x_intercept(yd, g.bx[rl], g.by[rl], g.bx[ru], g.by[ru])), 0.0, (double)g.xmax);
+}
+
+// one pixel of that span: the body of the reference's inner loop (line.py:925-981)
+__device__ __forceinline__ void aa_pixel(const AaSeg& g, const LineCtx& c, long long y, long long x) {
+  const double yd = (double)y;
   const double x0 = g.x0, y0 = g.y0, x1 = g.x1, y1 = g.y1;
   const double ry0 = fsub64(yd, y0), ry1 = fsub64(yd, y1);
   const bool overwrite = g.overwrite, segment_start = g.segment_start, segment_end = g.segment_end;
-  for (long long x = xleft; x <= xright; x++) {
-    const double rx0 = fsub64((double)x, x0);
-    const double along = fadd64(fmul64(rx0, g.alongx), fmul64(ry0, g.alongy));
-    bool prev_correction = false;
-    double distance;
-    if (along < 0.0) {
-      if (overwrite || segment_start || fadd64(fmul64(rx0, g.prev_alongx), fmul64(ry0, g.prev_alongy)) > 0.0)
-        distance = __dsqrt_rn(fadd64(fmul64(rx0, rx0), fmul64(ry0, ry0)));
-      else continue;
-    } else if (along > g.length) {
-      if (overwrite || segment_end) {
-        const double rx1 = fsub64((double)x, x1);
-        distance = __dsqrt_rn(fadd64(fmul64(rx1, rx1), fmul64(ry1, ry1)));
-      } else continue;
-    } else {
-      distance = fabs(fadd64(fmul64(rx0, g.rightx), fmul64(ry0, g.righty)));
-      if (!overwrite && !segment_start) {
-        const double pa = fadd64(fmul64(rx0, g.prev_alongx), fmul64(ry0, g.prev_alongy));
-        if (-g.prev_length <= pa && pa <= 0.0 && fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty))) <= g.halfwidth)
-          prev_correction = true;
-      }
-    }
-    double value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, distance)), g.scale);
-    double prev_value = 0.0;
-    if (prev_correction) {
-      const double prev_distance = fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty)));
-      prev_value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, prev_distance)), g.scale);
-      if (value <= prev_value) value = 0.0;
-    }
-    if (value > 0.0) {
-      if (g.flip_xy) append_aa(c, y, x, value, prev_value);
-      else append_aa(c, x, y, value, prev_value);
+  const double rx0 = fsub64((double)x, x0);
+  const double along = fadd64(fmul64(rx0, g.alongx), fmul64(ry0, g.alongy));
+  bool prev_correction = false;
+  double distance;
+  if (along < 0.0) {
+    if (overwrite || segment_start || fadd64(fmul64(rx0, g.prev_alongx), fmul64(ry0, g.prev_alongy)) > 0.0)
+      distance = __dsqrt_rn(fadd64(fmul64(rx0, rx0), fmul64(ry0, ry0)));
+    else return;
+  } else if (along > g.length) {
+    if (overwrite || segment_end) {
+      const double rx1 = fsub64((double)x, x1);
+      distance = __dsqrt_rn(fadd64(fmul64(rx1, rx1), fmul64(ry1, ry1)));
+    } else return;
+  } else {
+    distance = fabs(fadd64(fmul64(rx0, g.rightx), fmul64(ry0, g.righty)));
+    if (!overwrite && !segment_start) {
+      const double pa = fadd64(fmul64(rx0, g.prev_alongx), fmul64(ry0, g.prev_alongy));
+      if (-g.prev_length <= pa && pa <= 0.0 && fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty))) <= g.halfwidth)
+        prev_correction = true;
     }
   }
+  double value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, distance)), g.scale);
+  double prev_value = 0.0;
+  if (prev_correction) {
+    const double prev_distance = fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty)));
+    prev_value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, prev_distance)), g.scale);
+    if (value <= prev_value) value = 0.0;
+  }
+  if (value > 0.0) {
+    if (g.flip_xy) append_aa(c, y, x, value, prev_value);
+    else append_aa(c, x, y, value, prev_value);
+  }
+}
+
+__device__ __forceinline__ void aa_row(const AaSeg& g, const LineCtx& c, long long y) {
+  long long xleft, xright;
+  aa_row_span(g, y, xleft, xright);
+  for (long long x = xleft; x <= xright; x++) aa_pixel(g, c, y, x);
 }
 
 // clip + map of draw_segment (line.py:1045-1085) for the antialiased form: false = nothing to draw
@@ -631,20 +640,45 @@ __global__ void __launch_bounds__(128) k_lines_aa_balanced(const LineArgs a) {
     wpre[lane] = incl;
     const int rows_total = __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
-    // warp-uniform trip count and a __syncwarp() per round: without it the lanes drift apart over the rounds (a lane that
-    // finishes a short row starts its next one alone) - ncu showed 5.9 active lanes at the top of this loop
+    // Rounds of 32 rows, warp-uniform trip counts, a __syncwarp() per round (without it the lanes drift apart over the rounds:
+    // ncu showed 5.9 active lanes).  Inside a round every lane works out the pixel span of ITS row; a second prefix sum over
+    // the 32 span lengths numbers the pixels of the round, and lane i draws pixels i, i + 32, ... whatever row they belong to
+    // (a row of a steep segment is 2-3 pixels, of a flat one 10+: per-row loops left 12.7 of 32 lanes active).
     for (int r0 = 0; r0 < rows_total; r0 += 32) {
       const int r = r0 + lane;
+      int segi = 0, yrow = 0, xl = 0, cnt = 0;
       if (r < rows_total) {
         int lo = 0, hi = 31;                     // first lane whose inclusive prefix exceeds r
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (wpre[mid] > r) hi = mid; else lo = mid + 1; }
         const AaSeg& q = wseg[lo];
         const long long y = (long long)q.ystart + (r - (wpre[lo] - q.nrows));
-        LineCtx c;
-        c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
-        c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row;
-        c.cat = q.cat; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
-        aa_row(q, c, y);
+        long long xleft, xright;
+        aa_row_span(q, y, xleft, xright);
+        segi = lo; yrow = (int)y; xl = (int)xleft; cnt = xright >= xleft ? (int)(xright - xleft + 1) : 0;
+      }
+      int incl2 = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl2, o); if (lane >= o) incl2 += t; }
+      const int npix = __shfl_sync(0xffffffffu, incl2, 31);
+      const int excl2 = incl2 - cnt;
+      for (int p0 = 0; p0 < npix; p0 += 32) {
+        const int p = min(p0 + lane, npix - 1);
+        int lo = 0, hi = 31;                     // first lane whose inclusive pixel prefix exceeds p: exactly five halvings
+#pragma unroll
+        for (int it = 0; it < 5; it++) {
+          const int mid = (lo + hi) >> 1;
+          if (__shfl_sync(0xffffffffu, incl2, mid) > p) hi = mid; else lo = mid + 1;
+        }
+        const int ssegi = __shfl_sync(0xffffffffu, segi, lo), sy = __shfl_sync(0xffffffffu, yrow, lo);
+        const int sxl = __shfl_sync(0xffffffffu, xl, lo), sex = __shfl_sync(0xffffffffu, excl2, lo);
+        if (p0 + lane < npix) {
+          const AaSeg& q = wseg[ssegi];
+          LineCtx c;
+          c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
+          c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row;
+          c.cat = q.cat; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
+          aa_pixel(q, c, (long long)sy, (long long)(sxl + (p - sex)));
+        }
       }
       __syncwarp();
     }
@@ -840,19 +874,42 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
         wpre[lane] = incl;
         const int rows_total = __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
-        for (int r0 = 0; r0 < rows_total; r0 += 32) {
-          const int r = r0 + lane;
+        for (int r0 = 0; r0 < rows_total; r0 += 32) {            // rows, then the pixels of those rows, spread over the warp
+          const int r = r0 + lane;                                 //   (see k_lines_aa_balanced)
+          int segi = 0, yrow = 0, xl = 0, cnt = 0;
           if (r < rows_total) {
             int lo = 0, hi = 31;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (wpre[mid] > r) hi = mid; else lo = mid + 1; }
             const AaSeg& q = wseg[lo];
             const long long y = (long long)q.ystart + (r - (wpre[lo] - q.nrows));
-            LineCtx c;
-            c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = temp; c.mask = nullptr;
-            c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row; c.cat = 0; c.ncat = 0;
-            c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox; c.tlist = tlist; c.tn = &tn;
-            c.hkeys = nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = 0;
-            aa_row(q, c, y);
+            long long xleft, xright;
+            aa_row_span(q, y, xleft, xright);
+            segi = lo; yrow = (int)y; xl = (int)xleft; cnt = xright >= xleft ? (int)(xright - xleft + 1) : 0;
+          }
+          int incl2 = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl2, o); if (lane >= o) incl2 += tt; }
+          const int npix = __shfl_sync(0xffffffffu, incl2, 31);
+          const int excl2 = incl2 - cnt;
+          for (int p0 = 0; p0 < npix; p0 += 32) {
+            const int p = min(p0 + lane, npix - 1);
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+              const int mid = (lo + hi) >> 1;
+              if (__shfl_sync(0xffffffffu, incl2, mid) > p) hi = mid; else lo = mid + 1;
+            }
+            const int ssegi = __shfl_sync(0xffffffffu, segi, lo), sy = __shfl_sync(0xffffffffu, yrow, lo);
+            const int sxl = __shfl_sync(0xffffffffu, xl, lo), sex = __shfl_sync(0xffffffffu, excl2, lo);
+            if (p0 + lane < npix) {
+              const AaSeg& q = wseg[ssegi];
+              LineCtx c;
+              c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = temp; c.mask = nullptr;
+              c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row; c.cat = 0; c.ncat = 0;
+              c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox; c.tlist = tlist; c.tn = &tn;
+              c.hkeys = nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = 0;
+              aa_pixel(q, c, (long long)sy, (long long)(sxl + (p - sex)));
+            }
           }
           __syncwarp();
         }

@@ -31,7 +31,7 @@ struct RouteArgs {
   FastMap fm;
   const float* x; const float* y; const float* vcol;
   long long n, row_offset;
-  uint32_t cpb, inv, nb, ncell;
+  uint32_t cpb, inv, sh, kmul, nb, ncell;     // inv, sh, kmul: route_key
   unsigned long long* recs;             // records; bucket b owns [off[b], off[b] + cap[b])
   const unsigned long long* off;        // [nb]
   const uint32_t* cap;                  // [nb]
@@ -43,11 +43,12 @@ struct RouteArgs {
   unsigned int* notes;
 };
 
+// bucket << 16 | cell in bucket.  The bucket is cell / cpb by multiplication with m = ceil(2^(32 + sh) / cpb): exact for every
+// cell below ncell because ncell * (m * cpb - 2^(32 + sh)) < 2^(32 + sh) (checked on the host, dsb_points_routed); the key
+// is then cell + bucket * (65536 - cpb): three instructions.
 __device__ __forceinline__ uint32_t route_key(const RouteArgs& a, uint32_t cell) {
-  uint32_t b = __umulhi(cell, a.inv);
-  uint32_t l = cell - b * a.cpb;
-  if (l >= a.cpb) { b++; l -= a.cpb; }
-  return (b << 16) | l;
+  const uint32_t b = __umulhi(cell, a.inv) >> a.sh;
+  return cell + b * a.kmul;
 }
 
 // the accumulator op on the canvas itself (overflow records of pass 1)
@@ -125,10 +126,10 @@ __global__ void __launch_bounds__(1024) k_route_plan(const uint32_t* __restrict_
 // ---- pass 1 ----------------------------------------------------------------------------------------------------------
 template <int OP>
 __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ RouteArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const uint32_t nbp = (a.nb + 1) & ~1u;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t nbp = (a.nb + 2) & ~1u;                               // + the dummy bucket a.nb: filtered rows, no branch per point
   unsigned long long* rec = (unsigned long long*)smem;                 // [RTILE]
-  uint4* run_of = (uint4*)(rec + RTILE);                               // [nbp] per bucket: {global offset of this tile's run
+  uint4* run_of = (uint4*)(rec + RTILE);                               // [nbp] per bucket: {&recs[global offset of this tile's run
                                                                        //   minus base (lo, hi), base, records that fit}
   uint32_t* hist = (uint32_t*)(run_of + nbp);                          // [nbp]
   uint32_t* wsum = hist + nbp;                                         // [64]
@@ -149,10 +150,12 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
 #pragma unroll
     for (int u = 0; u < RPPT / 4; u++) {
       const long long i4 = t4 + (long long)u * RT + tid;
-      float4 xa, ya, va;
-      const float4 nan4 = make_float4(NAN, NAN, NAN, NAN), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (i4 < n4) { xa = __ldcs(x4 + i4); ya = __ldcs(y4 + i4); va = v4 ? __ldcs(v4 + i4) : one4; }
-      else { xa = ya = va = nan4; }
+      const bool inr = i4 < n4;                                // rows past the end re-read the last vector and are masked
+      const long long i4c = inr ? i4 : n4 - 1;
+      const uint32_t row0 = (uint32_t)i4 << 2;                 // the row within this call (n < 2^32)
+      const float4 xa = __ldcs(x4 + i4c), ya = __ldcs(y4 + i4c);
+      float4 va = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (v4) va = __ldcs(v4 + i4c);
       const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w}, vs[4] = {va.x, va.y, va.z, va.w};
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -161,29 +164,27 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
         const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
         const float dx = xf - (float)xi, dy = yf - (float)yi;
         const bool sure = dx >= a.fm.ex && dx <= a.fm.omex && dy >= a.fm.ey && dy <= a.fm.omey;
-        const int cell = (sure && (uint32_t)xi < W && (uint32_t)yi < H) ? yi * (int)W + xi : -1;
-        const bool live = vs[k] == vs[k];                      // NaN rows are skipped by every op
-        unsure |= (uint32_t)(!sure && live && i4 < n4) << (u * 4 + k);      // ~0.1 % of the points
-        const bool ok = live && cell >= 0;
-        const uint32_t kk = ok ? route_key(a, (uint32_t)cell) : 0xffffffffu;
+        const bool live = inr && vs[k] == vs[k];               // NaN rows are skipped by every op
+        unsure |= (uint32_t)(!sure && live) << (u * 4 + k);    // ~0.1 % of the points
+        const bool ok = sure && live && (uint32_t)xi < W && (uint32_t)yi < H;
+        const uint32_t kk = ok ? route_key(a, (uint32_t)(yi * (int)W + xi)) : (a.nb << 16);
         key[u * 4 + k] = kk;
         if (OP == R_MAX32 || OP == R_MIN32) { pay[u * 4 + k] = __float_as_uint(vs[k]); negzero |= ok && is_negzero(vs[k]); }
-        else pay[u * 4 + k] = (uint32_t)(4 * i4 + k);          // the row within this call (n < 2^32)
-        rank[u * 4 + k] = ok ? atomicAdd(hist + (kk >> 16), 1u) : 0u;
+        else pay[u * 4 + k] = row0 + k;
+        rank[u * 4 + k] = atomicAdd(hist + (kk >> 16), 1u);
       }
     }
-    if (unsure) {                                              // out of the unrolled body: queue the rows for k_route_slow
-      for (int j = 0; j < RPPT; j++) {
-        if (!(unsure >> j & 1)) continue;
-        const uint32_t row = (uint32_t)(4 * (t4 + (long long)(j >> 2) * RT + tid) + (j & 3));
-        const uint32_t pos = atomicAdd(a.slow_n, 1u);
-        if (pos < a.slow_cap) a.slow[pos] = row;
-        else {                                                 // list full (adversarial data): map it here, straight to the canvas
-          const float vv = a.vcol ? a.vcol[row] : 1.f;
-          const int cell = map_exact_linear(a.v, a.x[row], a.y[row]);
-          if (cell >= 0) route_direct<OP>(a, (uint32_t)cell, (OP == R_MAX32 || OP == R_MIN32) ? __float_as_uint(vv) : row);
-          if (OP == R_MAX32 || OP == R_MIN32) negzero |= cell >= 0 && is_negzero(vv);
-        }
+    while (unsure) {                                           // out of the unrolled body: queue the rows for k_route_slow
+      const int j = __ffs(unsure) - 1;
+      unsure &= unsure - 1;
+      const uint32_t row = (uint32_t)(4 * (t4 + (long long)(j >> 2) * RT + tid) + (j & 3));
+      const uint32_t pos = atomicAdd(a.slow_n, 1u);
+      if (pos < a.slow_cap) a.slow[pos] = row;
+      else {                                                   // list full (adversarial data): map it here, straight to the canvas
+        const float vv = a.vcol ? a.vcol[row] : 1.f;
+        const int cell = map_exact_linear(a.v, a.x[row], a.y[row]);
+        if (cell >= 0) route_direct<OP>(a, (uint32_t)cell, (OP == R_MAX32 || OP == R_MIN32) ? __float_as_uint(vv) : row);
+        if (OP == R_MAX32 || OP == R_MIN32) negzero |= cell >= 0 && is_negzero(vv);
       }
     }
     __syncthreads();
@@ -212,18 +213,22 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
       if (h) {
         const uint32_t g = atomicAdd(a.cursor + b, h);         // one global atomic per non-empty bucket per tile
         const uint32_t c = a.cap[b];
-        const unsigned long long o = a.off[b] + g - run;
+        const unsigned long long o = (unsigned long long)(a.recs + (a.off[b] + g - run));
         r.x = (uint32_t)o; r.y = (uint32_t)(o >> 32); r.w = g >= c ? 0u : min(h, c - g);
       }
       run_of[b] = r;
       hist[b] = 0;                                             // ready for the next tile
       run += h;
     }
-    if (tid == RT - 1) wsum[31] = run;                         // records of the tile
+    if (tid == RT - 1) {                                       // records of the tile; the dummy bucket's run lies behind them
+      wsum[31] = run;
+      run_of[a.nb] = make_uint4(0u, 0u, run, 0u);
+      hist[a.nb] = 0;
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < RPPT; k++)
-      if (key[k] != 0xffffffffu) rec[run_of[key[k] >> 16].z + rank[k]] = ((unsigned long long)pay[k] << 32) | key[k];
+      rec[run_of[key[k] >> 16].z + rank[k]] = ((unsigned long long)pay[k] << 32) | key[k];
     __syncthreads();
     const uint32_t total = wsum[31];
 #pragma unroll
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
         if (q >= total) continue;
         const uint32_t b = ((uint32_t)rr[k]) >> 16;
         const uint4 r = run_of[b];
-        if (q - r.z < r.w) a.recs[(((unsigned long long)r.y << 32) | r.x) + q] = rr[k];
+        if (q - r.z < r.w) __stcs((unsigned long long*)(((unsigned long long)r.y << 32) | r.x) + q, rr[k]);
         else route_direct<OP>(a, b * a.cpb + ((uint32_t)rr[k] & 0xffffu), (uint32_t)(rr[k] >> 32));   // the region is full
       }
     }
@@ -460,7 +465,16 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   if (!a.fm.enabled) { dsb_set_error("dsb_points_routed: needs linear axes within the float32 fast mapping's error bound"); return DSB_ERR_UNSUPPORTED; }
   a.x = (const float*)x; a.y = (const float*)y; a.vcol = vcol; a.n = n; a.row_offset = row_offset;
   a.nb = route_nb(ncell, &a.cpb);
-  a.inv = (uint32_t)((1ull << 32) / a.cpb);
+  {                                           // the exact division by cpb of route_key
+    uint32_t lg = 0;
+    while ((2u << lg) <= a.cpb) lg++;         // floor(log2 cpb)
+    if ((1u << lg) == a.cpb && lg > 0) lg--;  // a power of two: keep m below 2^32
+    const unsigned __int128 one = (unsigned __int128)1 << (32 + lg);
+    const unsigned __int128 m = (one + a.cpb - 1) / a.cpb;
+    const unsigned __int128 e = m * a.cpb - one;
+    if (m >> 32 || (unsigned __int128)ncell * e >= one) { dsb_set_error("dsb_points_routed: no exact bucket divisor for this canvas"); return DSB_ERR_UNSUPPORTED; }
+    a.inv = (uint32_t)m; a.sh = lg; a.kmul = 65536u - a.cpb;
+  }
   a.ncell = (uint32_t)ncell;
   const size_t hdr = route_fixed_bytes(a.nb, n);
   if (a.nb > 65535 || scratch_bytes < (int64_t)(hdr + ((size_t)a.nb * 4096 + 1024) * 8)) { dsb_set_error("dsb_points_routed: scratch too small"); return DSB_ERR_ARG; }
@@ -481,7 +495,7 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   const long long stride_blocks = n >= (1LL << 28) ? 64 : 16;   // every 64th (16th) block of 1024 points is sampled
   k_route_sample<<<dsb_num_sms() * 4, 256, (size_t)a.nb * 4, s>>>(a, stride_blocks, hist);
   k_route_plan<<<1, 1024, 0, s>>>(hist, a.nb, (uint32_t)stride_blocks, capacity, off, cap, cursor, queue, a.slow_n);
-  const uint32_t nbp = (a.nb + 1) & ~1u;
+  const uint32_t nbp = (a.nb + 2) & ~1u;
   const size_t smem1 = (size_t)RTILE * 8 + (size_t)nbp * (16 + 4) + 64 * 4;
   const size_t smem2 = (size_t)a.cpb * 4;
   static const char* const names[] = {"max32", "min32", "minrow", "maxrow", "count"};
