@@ -761,6 +761,24 @@ struct Aa2Args {
 #define AA2_HASH_CAP 16384   // 16384 x (4 + 8) B = 192 KB of shared memory: one 512-thread CTA per SM
 #define AA2_CELL_BITS 27      // table key = (line within its group) << 27 | cell: canvases below 2^27 pixels, groups <= 32
 
+// first / last in ONE rasterisation (phase 3): out holds {line index, value bits} pairs, replaced as a whole with a
+// 128-bit compare-and-swap when this line precedes (follows) the one recorded - the two-phase form rasterises every line twice
+__device__ __forceinline__ void aa2_pair_update(void* out, uint32_t cell, long long line, long long key, bool first) {
+  unsigned long long* p = (unsigned long long*)out + 2 * (size_t)cell;
+  unsigned long long cl, cv;
+  asm volatile("ld.global.relaxed.gpu.v2.u64 {%0, %1}, [%2];" : "=l"(cl), "=l"(cv) : "l"(p) : "memory");
+  const unsigned long long nv = (unsigned long long)__double_as_longlong(f64_from_key64(key));
+  for (;;) {
+    if (first ? line >= (long long)cl : line <= (long long)cl) return;
+    unsigned long long ol, ov;
+    asm volatile("{\n.reg .b128 c, n, o;\nmov.b128 c, {%2, %3};\nmov.b128 n, {%4, %5};\n"
+                 "atom.global.relaxed.gpu.cas.b128 o, [%6], c, n;\nmov.b128 {%0, %1}, o;\n}"
+                 : "=l"(ol), "=l"(ov) : "l"(cl), "l"(cv), "l"((unsigned long long)line), "l"(nv), "l"(p) : "memory");
+    if (ol == cl && ov == cv) return;
+    cl = ol; cv = ov;
+  }
+}
+
 __device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long long key, long long line) {
   switch (b.combo) {
     case DSB_AA2_SUM:      // nansum_in_place, utils.py:885-897 (the NaN start is restored from the mask afterwards)
@@ -783,11 +801,13 @@ __device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long
       else if (((const long long*)b.out)[cell] == key) atomicMin((long long*)b.aux + cell, line);
       break;
     case DSB_AA2_FIRST:    // nanfirst_in_place, utils.py:615-623: the lowest line index that touches the pixel wins
-      if (b.phase == 1) atomicMin((long long*)b.aux + cell, line);
+      if (b.phase == 3) aa2_pair_update(b.out, cell, line, key, true);
+      else if (b.phase == 1) atomicMin((long long*)b.aux + cell, line);
       else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
       break;
     case DSB_AA2_LAST:     // nanlast_in_place, utils.py:627-635
-      if (b.phase == 1) atomicMax((long long*)b.aux + cell, line);
+      if (b.phase == 3) aa2_pair_update(b.out, cell, line, key, false);
+      else if (b.phase == 1) atomicMax((long long*)b.aux + cell, line);
       else if (((const long long*)b.aux)[cell] == line) ((double*)b.out)[cell] = f64_from_key64(key);
       break;
   }
@@ -1110,8 +1130,10 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   if (!(line_width > 0.0)) { dsb_set_error("dsb_lines_aa2: line_width must be > 0"); return DSB_ERR_ARG; }
   if (combo != DSB_AA2_COUNT && (val_dtype == DSB_NONE || !val)) { dsb_set_error("dsb_lines_aa2: this reduction needs a value column"); return DSB_ERR_ARG; }
   const bool two_phase = combo == DSB_AA2_FIRST || combo == DSB_AA2_LAST || combo == DSB_AA2_ARGMIN || combo == DSB_AA2_ARGMAX;
-  if (combo != DSB_AA2_MIN && !((combo == DSB_AA2_ARGMIN || combo == DSB_AA2_ARGMAX) && phase == 1) && !aux) { dsb_set_error("dsb_lines_aa2: aux canvas required"); return DSB_ERR_ARG; }
-  if (two_phase && phase != 1 && phase != 2) { dsb_set_error("dsb_lines_aa2: phase must be 1 or 2"); return DSB_ERR_ARG; }
+  const bool fused = (combo == DSB_AA2_FIRST || combo == DSB_AA2_LAST) && phase == 3;
+  if (combo != DSB_AA2_MIN && !((combo == DSB_AA2_ARGMIN || combo == DSB_AA2_ARGMAX) && phase == 1) && !fused && !aux) { dsb_set_error("dsb_lines_aa2: aux canvas required"); return DSB_ERR_ARG; }
+  if (two_phase && phase != 1 && phase != 2 && !fused) { dsb_set_error("dsb_lines_aa2: phase must be 1 or 2 (3: first / last in one pass)"); return DSB_ERR_ARG; }
+  if (fused && (((uintptr_t)out) & 15) != 0) { dsb_set_error("dsb_lines_aa2: the pair canvas must be 16-byte aligned"); return DSB_ERR_ARG; }
   if (nlines <= 0 || nverts < 2) return DSB_OK;
   if (!xs || !ys) { dsb_set_error("dsb_lines_aa2: null vertex arrays"); return DSB_ERR_ARG; }
   const long long ncell = (long long)view->width * view->height;

@@ -701,6 +701,9 @@ def _aa2_combo(agg):
     return None
 
 
+_NAN_BITS = 0x7ff8000000000000          # numpy's / torch's default quiet NaN
+
+
 def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist, rows_only=False):
     """Antialiased lines, 2-stage reductions: dsb_lines_aa2 (one CTA per line, per-line max then the stage-2 fold).
     rows_only (first / last): return the voted global row canvas (+ ranges and scale / translate) instead of the values."""
@@ -765,17 +768,23 @@ def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist, rows_only=Fal
             assert rows_only
             return rows, (x_range, y_range, x_st, y_st)
         else:
+            # first / last in one rasterisation: {line index, value bits} pairs updated with a 128-bit compare-and-swap
+            # (phase 3); the two-phase form (vote, then the winning line stores) rasterised every line twice
             first = combo == _lib.AA2_FIRST
-            rows = torch.empty((H, W), dtype=torch.int64, device=device)
-            _lib.check(lib.dsb_init_canvas(_lib.OP_MINROW if first else _lib.OP_MAXROW, rows.data_ptr(), H * W, stream_ptr))
-            out = torch.full((H, W), float("nan"), dtype=torch.float64, device=device)
-            launch(1, out, rows)
+            pairs = torch.empty((H * W, 2), dtype=torch.int64, device=device)
+            pairs[:, 0] = torch.iinfo(torch.int64).max if first else -1
+            pairs[:, 1] = _NAN_BITS
+            launch(3, pairs, None)
+            rows = pairs[:, 0].contiguous().view(H, W)
+            mine = rows
             if dist is not None:
+                rows = rows.clone()
                 dist._all_reduce(rows, "min" if first else "max")
             if rows_only:
                 return rows, (x_range, y_range, x_st, y_st)
-            launch(2, out, rows)
+            out = pairs[:, 1].contiguous().view(torch.float64).view(H, W)
             if dist is not None:      # exactly one rank owns each winning line: the others contribute 0 bits
+                out = torch.where(mine == rows, out, torch.zeros((), dtype=torch.float64, device=device))
                 out = dist.sum_bits_f64(torch.nan_to_num(out, nan=0.0), rows)
         data = _to_host(out)
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
