@@ -779,6 +779,25 @@ __device__ __forceinline__ void aa2_pair_update(void* out, uint32_t cell, long l
   }
 }
 
+// where(min | max) in one rasterisation: {key64, line index} pairs; a line replaces the pair when its value is better, or
+// equal with a lower line index (the reference's strict compare keeps the earlier line, reductions.py:2009-2016)
+__device__ __forceinline__ void aa2_pair_update_arg(void* out, uint32_t cell, long long line, long long key, bool is_max) {
+  unsigned long long* p = (unsigned long long*)out + 2 * (size_t)cell;
+  unsigned long long ck, cl;
+  asm volatile("ld.global.relaxed.gpu.v2.u64 {%0, %1}, [%2];" : "=l"(ck), "=l"(cl) : "l"(p) : "memory");
+  for (;;) {
+    const long long k0 = (long long)ck;
+    const bool better = is_max ? key > k0 : key < k0;
+    if (!(better || (key == k0 && line < (long long)cl))) return;
+    unsigned long long ok, ol;
+    asm volatile("{\n.reg .b128 c, n, o;\nmov.b128 c, {%2, %3};\nmov.b128 n, {%4, %5};\n"
+                 "atom.global.relaxed.gpu.cas.b128 o, [%6], c, n;\nmov.b128 {%0, %1}, o;\n}"
+                 : "=l"(ok), "=l"(ol) : "l"(ck), "l"(cl), "l"((unsigned long long)key), "l"((unsigned long long)line), "l"(p) : "memory");
+    if (ok == ck && ol == cl) return;
+    ck = ok; cl = ol;
+  }
+}
+
 __device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long long key, long long line) {
   switch (b.combo) {
     case DSB_AA2_SUM:      // nansum_in_place, utils.py:885-897 (the NaN start is restored from the mask afterwards)
@@ -793,11 +812,13 @@ __device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long
       atomicMin((long long*)b.out + cell, key);
       break;
     case DSB_AA2_ARGMIN:   // where(min(col), ...): the selector's combine keeps the earlier line on ties (strict compare)
-      if (b.phase == 1) atomicMin((long long*)b.out + cell, key);
+      if (b.phase == 3) aa2_pair_update_arg(b.out, cell, line, key, false);
+      else if (b.phase == 1) atomicMin((long long*)b.out + cell, key);
       else if (((const long long*)b.out)[cell] == key) atomicMin((long long*)b.aux + cell, line);
       break;
     case DSB_AA2_ARGMAX:   // where(max(col), ...)
-      if (b.phase == 1) atomicMax((long long*)b.out + cell, key);
+      if (b.phase == 3) aa2_pair_update_arg(b.out, cell, line, key, true);
+      else if (b.phase == 1) atomicMax((long long*)b.out + cell, key);
       else if (((const long long*)b.out)[cell] == key) atomicMin((long long*)b.aux + cell, line);
       break;
     case DSB_AA2_FIRST:    // nanfirst_in_place, utils.py:615-623: the lowest line index that touches the pixel wins
@@ -1130,7 +1151,7 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   if (!(line_width > 0.0)) { dsb_set_error("dsb_lines_aa2: line_width must be > 0"); return DSB_ERR_ARG; }
   if (combo != DSB_AA2_COUNT && (val_dtype == DSB_NONE || !val)) { dsb_set_error("dsb_lines_aa2: this reduction needs a value column"); return DSB_ERR_ARG; }
   const bool two_phase = combo == DSB_AA2_FIRST || combo == DSB_AA2_LAST || combo == DSB_AA2_ARGMIN || combo == DSB_AA2_ARGMAX;
-  const bool fused = (combo == DSB_AA2_FIRST || combo == DSB_AA2_LAST) && phase == 3;
+  const bool fused = two_phase && phase == 3;
   if (combo != DSB_AA2_MIN && !((combo == DSB_AA2_ARGMIN || combo == DSB_AA2_ARGMAX) && phase == 1) && !fused && !aux) { dsb_set_error("dsb_lines_aa2: aux canvas required"); return DSB_ERR_ARG; }
   if (two_phase && phase != 1 && phase != 2 && !fused) { dsb_set_error("dsb_lines_aa2: phase must be 1 or 2 (3: first / last in one pass)"); return DSB_ERR_ARG; }
   if (fused && (((uintptr_t)out) & 15) != 0) { dsb_set_error("dsb_lines_aa2: the pair canvas must be 16-byte aligned"); return DSB_ERR_ARG; }

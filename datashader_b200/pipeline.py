@@ -753,17 +753,20 @@ def _lines_aa2(frame, canvas, glyph, agg, combo, line_width, dist, rows_only=Fal
             out = torch.empty((H, W), dtype=torch.float64, device=device)
             _lib.check(lib.dsb_decode_minmax(keys.data_ptr(), _lib.OP_MIN64, _lib.F64, out.data_ptr(), H * W, stream_ptr))
         elif combo in (_lib.AA2_ARGMIN, _lib.AA2_ARGMAX):
-            # where(min | max): the value canvas first, then the lowest line index among the lines that reach it
+            # where(min | max): {value key, line index} pairs in one rasterisation (phase 3, 128-bit compare-and-swap): the best
+            # value, the lowest line index among the lines that reach it
             is_max = combo == _lib.AA2_ARGMAX
-            keys = torch.empty((H, W), dtype=torch.int64, device=device)
-            _lib.check(lib.dsb_init_canvas(_lib.OP_MAX64 if is_max else _lib.OP_MIN64, keys.data_ptr(), H * W, stream_ptr))
-            launch(1, keys, None)
+            i64 = torch.iinfo(torch.int64)
+            pairs = torch.empty((H * W, 2), dtype=torch.int64, device=device)
+            pairs[:, 0] = i64.min if is_max else i64.max
+            pairs[:, 1] = i64.max
+            launch(3, pairs, None)
+            rows = pairs[:, 1].contiguous().view(H, W)
             if dist is not None:
+                mine = pairs[:, 0].contiguous().view(H, W)
+                keys = mine.clone()
                 dist._all_reduce(keys, "max" if is_max else "min")
-            rows = torch.empty((H, W), dtype=torch.int64, device=device)
-            _lib.check(lib.dsb_init_canvas(_lib.OP_MINROW, rows.data_ptr(), H * W, stream_ptr))
-            launch(2, keys, rows)
-            if dist is not None:
+                rows = torch.where(mine == keys, rows, torch.full_like(rows, i64.max))
                 dist._all_reduce(rows, "min")
             assert rows_only
             return rows, (x_range, y_range, x_st, y_st)

@@ -239,7 +239,8 @@ int dsb_lines_axis1_plan(const dsb_view* view, const void* xs, const void* ys, i
  *                 with phase = 1 (votes the global line index row_offset + i into aux; all-reduce aux across GPUs
  *                 here), then phase = 2 (the winning line stores its value into out, f64, NaN-initialised).  Or ONE call
  *                 with phase = 3: out = [pixels] pairs {i64 line index, f64 value bits} (16-byte aligned, initialised to
- *                 {INT64_MAX | -1, NaN}), updated with a 128-bit compare-and-swap; aux unused. */
+ *                 {INT64_MAX | -1, NaN}), updated with a 128-bit compare-and-swap; aux unused.  ARGMIN / ARGMAX with
+ *                 phase = 3: out = pairs {i64 key64, i64 line index} initialised to {INT64_MAX | INT64_MIN, INT64_MAX}. */
 typedef enum { DSB_AA2_SUM = 1, DSB_AA2_COUNT = 2, DSB_AA2_MIN = 3, DSB_AA2_FIRST = 4, DSB_AA2_LAST = 5,
                DSB_AA2_ARGMIN = 6, DSB_AA2_ARGMAX = 7 } dsb_aa2_combo;
 int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* ys, int32_t xy_dtype, int64_t nlines,
