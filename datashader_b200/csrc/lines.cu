@@ -419,15 +419,28 @@ __device__ void draw_segment(const LineArgs& a, const LineCtx& c, bool segment_s
 // row depends only on whether its y lies above the corner that follows the lowest one), so a warp first prepares its 32
 // segments (clip, map, corners, unit vectors: uniform work, AaSeg in shared memory), then hands the ROWS of all 32 segments out
 // evenly, 32 at a time.  Same pixels, same arithmetic per pixel, same appends as full_antialias.
-struct AaSeg {
-  double x0, y0, x1, y1, alongx, alongy, length, rightx, righty;
+struct AaSeg {                 // 192 bytes: eight 128-thread CTAs per SM next to 64 registers per thread
+  double x0, y0, x1, y1, alongx, alongy, length;         // right = (alongy, -alongx), prev_right likewise: not stored
   double bx[4], by[4];
-  double prev_alongx, prev_alongy, prev_length, prev_rightx, prev_righty;
-  double halfwidth, e0, scale, field;
-  long long row, line;
+  double prev_alongx, prev_alongy, prev_length;
+  double field;
+  long long line;                                         // the global row id is row_offset + line
   int xmax, ymax, ystart, nrows, lowindex, cat;
   unsigned char flip_xy, overwrite, segment_start, segment_end, field_nan, pad[3];
 };
+static_assert(sizeof(AaSeg) == 192, "AaSeg layout");
+
+// the per-call constants of full_antialias (line.py:836-842): the same for every segment
+struct AaConst { double halfwidth, e0, scale; };
+__device__ __forceinline__ AaConst aa_const(double line_width) {
+  AaConst k;
+  k.scale = 1.0;
+  if (line_width < 1.0) { k.scale = fmul64(k.scale, line_width); line_width = 1.0; }
+  const double aa = 1.0;
+  k.halfwidth = fmul64(0.5, fadd64(line_width, aa));
+  k.e0 = fmul64(0.5, fsub64(line_width, aa));
+  return k;
+}
 
 // the invariants of full_antialias (line.py:830-905); g.nrows = 0 when nothing is drawn
 __device__ __forceinline__ void aa_prepare(AaSeg& g, double line_width, bool overwrite, double x0, double x1, double y0, double y1,
@@ -475,14 +488,14 @@ __device__ __forceinline__ void aa_prepare(AaSeg& g, double line_width, bool ove
   int lowindex;
   if (flip_order) lowindex = x0 > x1 ? 0 : 1;
   else lowindex = x1 > x0 ? 0 : 1;
-  g.prev_alongx = g.prev_alongy = g.prev_length = g.prev_rightx = g.prev_righty = 0.0;
+  g.prev_alongx = g.prev_alongy = g.prev_length = 0.0;
   if (!overwrite && !segment_start) {
     double pax = fsub64(x0, xm), pay = fsub64(y0, ym);
     const double pl = __dsqrt_rn(fadd64(fmul64(pax, pax), fmul64(pay, pay)));
     if (pl > 0.0) {
       pax = __ddiv_rn(pax, pl);
       pay = __ddiv_rn(pay, pl);
-      g.prev_alongx = pax; g.prev_alongy = pay; g.prev_length = pl; g.prev_rightx = pay; g.prev_righty = -pax;
+      g.prev_alongx = pax; g.prev_alongy = pay; g.prev_length = pl;
     } else {
       g.prev_alongx = pax; g.prev_alongy = pay; g.prev_length = pl;
       overwrite = true;
@@ -491,7 +504,6 @@ __device__ __forceinline__ void aa_prepare(AaSeg& g, double line_width, bool ove
   const long long ystart = (long long)clampd(ceil(g.by[lowindex]), 0.0, (double)ymax);
   const long long yend = (long long)clampd(floor(g.by[(lowindex + 2) & 3]), 0.0, (double)ymax);
   g.x0 = x0; g.y0 = y0; g.x1 = x1; g.y1 = y1; g.alongx = alongx; g.alongy = alongy; g.length = length;
-  g.rightx = rightx; g.righty = righty; g.halfwidth = halfwidth; g.e0 = fmul64(0.5, fsub64(line_width, aa)); g.scale = scale;
   g.xmax = (int)xmax; g.ymax = (int)ymax; g.ystart = (int)ystart; g.lowindex = lowindex;
   g.flip_xy = flip_xy; g.overwrite = overwrite; g.segment_start = segment_start; g.segment_end = segment_end;
   g.nrows = yend >= ystart ? (int)(yend - ystart + 1) : 0;
@@ -510,8 +522,9 @@ __device__ __forceinline__ void aa_row_span(const AaSeg& g, long long y, long lo
 }
 
 // one pixel of that span: the body of the reference's inner loop (line.py:925-981)
-__device__ __forceinline__ void aa_pixel(const AaSeg& g, const LineCtx& c, long long y, long long x) {
+__device__ __forceinline__ void aa_pixel(const AaSeg& g, const AaConst& k, const LineCtx& c, long long y, long long x) {
   const double yd = (double)y;
+  const double rightx = g.alongy, righty = -g.alongx, prev_rightx = g.prev_alongy, prev_righty = -g.prev_alongx;
   const double x0 = g.x0, y0 = g.y0, x1 = g.x1, y1 = g.y1;
   const double ry0 = fsub64(yd, y0), ry1 = fsub64(yd, y1);
   const bool overwrite = g.overwrite, segment_start = g.segment_start, segment_end = g.segment_end;
@@ -529,30 +542,24 @@ __device__ __forceinline__ void aa_pixel(const AaSeg& g, const LineCtx& c, long 
       distance = __dsqrt_rn(fadd64(fmul64(rx1, rx1), fmul64(ry1, ry1)));
     } else return;
   } else {
-    distance = fabs(fadd64(fmul64(rx0, g.rightx), fmul64(ry0, g.righty)));
+    distance = fabs(fadd64(fmul64(rx0, rightx), fmul64(ry0, righty)));
     if (!overwrite && !segment_start) {
       const double pa = fadd64(fmul64(rx0, g.prev_alongx), fmul64(ry0, g.prev_alongy));
-      if (-g.prev_length <= pa && pa <= 0.0 && fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty))) <= g.halfwidth)
+      if (-g.prev_length <= pa && pa <= 0.0 && fabs(fadd64(fmul64(rx0, prev_rightx), fmul64(ry0, prev_righty))) <= k.halfwidth)
         prev_correction = true;
     }
   }
-  double value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, distance)), g.scale);
+  double value = fmul64(fsub64(1.0, linearstep(k.e0, k.halfwidth, distance)), k.scale);
   double prev_value = 0.0;
   if (prev_correction) {
-    const double prev_distance = fabs(fadd64(fmul64(rx0, g.prev_rightx), fmul64(ry0, g.prev_righty)));
-    prev_value = fmul64(fsub64(1.0, linearstep(g.e0, g.halfwidth, prev_distance)), g.scale);
+    const double prev_distance = fabs(fadd64(fmul64(rx0, prev_rightx), fmul64(ry0, prev_righty)));
+    prev_value = fmul64(fsub64(1.0, linearstep(k.e0, k.halfwidth, prev_distance)), k.scale);
     if (value <= prev_value) value = 0.0;
   }
   if (value > 0.0) {
     if (g.flip_xy) append_aa(c, y, x, value, prev_value);
     else append_aa(c, x, y, value, prev_value);
   }
-}
-
-__device__ __forceinline__ void aa_row(const AaSeg& g, const LineCtx& c, long long y) {
-  long long xleft, xright;
-  aa_row_span(g, y, xleft, xright);
-  for (long long x = xleft; x <= xright; x++) aa_pixel(g, c, y, x);
 }
 
 // clip + map of draw_segment (line.py:1045-1085) for the antialiased form: false = nothing to draw
@@ -589,9 +596,10 @@ __device__ __forceinline__ bool aa_clip_map(const LineArgs& a, bool& segment_sta
 }
 
 template <typename XY>
-__global__ void __launch_bounds__(128) k_lines_aa_balanced(const LineArgs a) {
+__global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) {
   __shared__ AaSeg segs[128];
   __shared__ int prefix[128];
+  const AaConst kaa = aa_const(a.line_width);
   const XY* __restrict__ xs = (const XY*)a.xs;
   const XY* __restrict__ ys = (const XY*)a.ys;
   const long long nseg = a.nverts - 1;
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(128) k_lines_aa_balanced(const LineArgs a) {
         aa_prepare(g, a.line_width, a.overwrite != 0, x0, x1, y0, y1, segment_start, segment_end, xm, ym, a.nx, a.ny);
       g.field = a.val_dtype != DSB_NONE ? load_f64(a.val, a.val_dtype, vi) : 0.0;
       g.field_nan = a.val_dtype != DSB_NONE && (g.field != g.field);
-      g.line = vi; g.row = a.row_offset + vi; g.cat = 0;
+      g.line = vi; g.cat = 0;
       if (a.ncat > 0) {
         int cc = load_cat(a.cat, a.cat_dtype, vi);
         if (cc < 0) cc += a.ncat;
@@ -675,9 +683,9 @@ __global__ void __launch_bounds__(128) k_lines_aa_balanced(const LineArgs a) {
           const AaSeg& q = wseg[ssegi];
           LineCtx c;
           c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
-          c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row;
+          c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = a.row_offset + q.line;
           c.cat = q.cat; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
-          aa_pixel(q, c, (long long)sy, (long long)(sxl + (p - sex)));
+          aa_pixel(q, kaa, c, (long long)sy, (long long)(sxl + (p - sex)));
         }
       }
       __syncwarp();
@@ -880,6 +888,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
     int tn = 0;
     if (!HASH) {
       // global stage-1 path (long lines): the rows of the warp's 32 segments are handed out evenly, as in k_lines_aa_balanced
+      const AaConst kaa = aa_const(a.line_width);
       AaSeg* const wseg = (AaSeg*)aa2_smem + (threadIdx.x & ~31);
       int* const wpre = s_prefix + (threadIdx.x & ~31);
       const int lane = threadIdx.x & 31;
@@ -907,7 +916,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
             aa_prepare(g, a.line_width, true, x0, x1, y0, y1, segment_start, segment_end, 0.0, 0.0, a.nx, a.ny);
           g.field = a.val_dtype != DSB_NONE ? load_f64(a.val, a.val_dtype, vi) : 0.0;
           g.field_nan = a.val_dtype != DSB_NONE && (g.field != g.field);
-          g.line = vi; g.row = a.row_offset + vi; g.cat = 0;
+          g.line = vi; g.cat = 0;
         }
         int incl = g.nrows;
 #pragma unroll
@@ -946,10 +955,10 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
               const AaSeg& q = wseg[ssegi];
               LineCtx c;
               c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = temp; c.mask = nullptr;
-              c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = q.row; c.cat = 0; c.ncat = 0;
+              c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = a.row_offset + q.line; c.cat = 0; c.ncat = 0;
               c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox; c.tlist = tlist; c.tn = &tn;
               c.hkeys = nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = 0;
-              aa_pixel(q, c, (long long)sy, (long long)(sxl + (p - sex)));
+              aa_pixel(q, kaa, c, (long long)sy, (long long)(sxl + (p - sex)));
             }
           }
           __syncwarp();

@@ -217,13 +217,17 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
         if 0 < need <= config.routed_max_scratch_bytes:
             scratch = getattr(ctx, "_routed_scratch", None)
             if scratch is None or scratch.numel() < need:
-                scratch = ctx._routed_scratch = torch.empty(need, dtype=torch.uint8, device=x.device)
-            rc = lib.dsb_points_routed(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
-                                       scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
-            if rc == 0:
-                return
-            if rc != -3:
-                _lib.check(rc, "dsb_points_routed")
+                try:
+                    scratch = ctx._routed_scratch = torch.empty(need, dtype=torch.uint8, device=x.device)
+                except torch.OutOfMemoryError:           # no room for the records: the L2-banded kernels need no scratch
+                    scratch = None
+            if scratch is not None:
+                rc = lib.dsb_points_routed(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
+                                           scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
+                if rc == 0:
+                    return
+                if rc != -3:
+                    _lib.check(rc, "dsb_points_routed")
     _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n, row_offset, C.byref(plan),
                               ctx.stream_ptr), "dsb_points")
 
