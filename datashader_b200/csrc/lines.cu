@@ -363,7 +363,7 @@ __device__ __forceinline__ double map_axis(bool is_log, double v) {
 }
 
 // line.py:1045-1097
-template <typename XY>
+template <typename XY, bool AA>       // AA: line_width > 0 (a compile-time split keeps the antialiased code's registers out of Bresenham)
 __device__ void draw_segment(const LineArgs& a, const LineCtx& c, bool segment_start, bool segment_end, double x0,
                              double x1, double y0, double y1, double xm, double ym) {
   const dsb_view& v = a.v;
@@ -386,7 +386,7 @@ __device__ void draw_segment(const LineArgs& a, const LineCtx& c, bool segment_s
   if (t0 > 0) { clipped_start = true; x0 = fadd64(x0, fmul64(t0, dx1)); y0 = fadd64(y0, fmul64(t0, dy1)); }
   const bool clipped = clipped_start || clipped_end;
   segment_start = segment_start || clipped_start;
-  if (a.line_width > 0.0) {
+  if (AA) {
     // map_onto_pixel_no_snap, line.py:722-726
     const double x0p = fsub64(fadd64(fmul64(map_axis<XY>(v.x_log, x0), v.sx), v.tx), 0.5);
     const double y0p = fsub64(fadd64(fmul64(map_axis<XY>(v.y_log, y0), v.sy), v.ty), 0.5);
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) 
 }
 
 // one thread per (line, segment): extend_cuda, line.py:1321-1332 + perform_extend_line :1250-1275
-template <typename XY>
+template <typename XY, bool AA>
 __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
   const XY* __restrict__ xs = (const XY*)a.xs;
   const XY* __restrict__ ys = (const XY*)a.ys;
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
       if (cc < 0) cc += a.plan.ncat;
       c.cat = (cc < 0 || cc >= a.plan.ncat) ? -1 : cc;
     }
-    draw_segment<XY>(a, c, segment_start, segment_end, x0, x1, y0, y1, xm, ym);
+    draw_segment<XY, AA>(a, c, segment_start, segment_end, x0, x1, y0, y1, xm, ym);
   }
 }
 
@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
       c.touched_n = &s_touched; c.touched = touched; c.bbox = bbox; c.tlist = tlist; c.tn = &tn;
       c.hkeys = HASH ? hkeys : nullptr; c.hvals = hvals; c.hmask = AA2_HASH_CAP - 1; c.hgroup = (uint32_t)g << AA2_CELL_BITS;
       // xm = ym = 0 in 2-stage mode (line.py:1266-1268); unused because overwrite is True
-      draw_segment<XY>(a, c, segment_start, segment_end, x0, x1, y0, y1, 0.0, 0.0);
+      draw_segment<XY, true>(a, c, segment_start, segment_end, x0, x1, y0, y1, 0.0, 0.0);
     }
     if (!HASH && bbox[1] >= 0) { atomicMin(&s_bbox[0], bbox[0]); atomicMax(&s_bbox[1], bbox[1]); }
     __syncthreads();
@@ -1077,8 +1077,10 @@ static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char*
   dsb_note_kernel(balanced ? "k_lines_aa_balanced<%s>" : "k_lines_axis1<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
   if (balanced && xy_dtype == DSB_F32) k_lines_aa_balanced<float><<<grid, threads, 0, s>>>(a);
   else if (balanced && xy_dtype == DSB_F64) k_lines_aa_balanced<double><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F32) k_lines_axis1<float><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F64) k_lines_axis1<double><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F32 && a.line_width > 0.0) k_lines_axis1<float, true><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F32) k_lines_axis1<float, false><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F64 && a.line_width > 0.0) k_lines_axis1<double, true><<<grid, threads, 0, s>>>(a);
+  else if (xy_dtype == DSB_F64) k_lines_axis1<double, false><<<grid, threads, 0, s>>>(a);
   else { dsb_set_error("%s: xy_dtype must be f32 or f64", what); return DSB_ERR_ARG; }
   DSB_CUDA_CHECK_LAUNCH(what);
   return DSB_OK;

@@ -74,6 +74,26 @@ def main():
                 ok = ok and np.array_equal(got, want, equal_nan=got.dtype.kind == "f")
             if not ok:
                 bad.append(f"lines {name} lw={lw}")
+    # 2-stage antialiased reductions over lines sharded by line: min (key canvas all-reduced), first / last ({line, value}
+    # pairs per rank, line canvas all-reduced, the owning rank contributes the value bits), sum(self_intersect=False); and
+    # where(first) / where(max) row ids, which must be those of the single-rank run over all lines
+    for name, agg in [("min", ds.min("val")), ("first", ds.first("val")), ("last", ds.last("val")),
+                      ("sum", ds.sum("val", self_intersect=False))]:
+        got = lcvs.line(lframe, x=xc, y=yc, agg=agg, axis=1, line_width=2.0).data
+        if rank == 0:
+            want = ora.lines_aa2(lx, ly, lview, name, lval, 2.0)
+            ok = np.array_equal(np.isnan(got), np.isnan(want)) and np.allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True)
+            if not ok:
+                bad.append(f"lines 2-stage antialiased {name}")
+    full = ds.DeviceFrame({f"x{j}": torch.from_numpy(np.ascontiguousarray(lx[:, j])).cuda() for j in range(nv)}
+                          | {f"y{j}": torch.from_numpy(np.ascontiguousarray(ly[:, j])).cuda() for j in range(nv)}
+                          | {"val": torch.from_numpy(lval).cuda()})
+    for name, agg in [("where(first)", ds.where(ds.first("val"))), ("where(last)", ds.where(ds.last("val"))),
+                      ("where(max)", ds.where(ds.max("val"))), ("where(min)", ds.where(ds.min("val")))]:
+        got = lcvs.line(lframe, x=xc, y=yc, agg=agg, axis=1, line_width=2.0).data
+        want = lcvs.line(full, x=xc, y=yc, agg=agg, axis=1, line_width=2.0).data      # one rank, all the lines
+        if rank == 0 and not np.array_equal(got, want):
+            bad.append(f"lines antialiased {name}: sharded != single-rank row ids")
     # LineAxis0 / AreaToZeroAxis0: ONE long curve sharded by rows; each rank receives the previous shard's last vertex
     # (data_libraries/dask.py:244-266) so that the segment across the shard boundary is drawn exactly once
     nv0 = 4001

@@ -103,6 +103,25 @@ def test_routed_overflow_falls_back_to_canvas_atomics(routed):
         assert np.array_equal(outs[0], outs[1]), f"op {op}"
 
 
+def test_routed_everything_filtered(routed):
+    """Every row lands in the dummy bucket (out of range, or a NaN value): canvases stay at their initial state."""
+    import torch
+    from oracle import oracle as ora
+    ds = routed
+    rng = np.random.default_rng(3)
+    n, W, H = 70_001, 301, 257
+    cols = {"x": (rng.random(n, dtype=np.float32) + 2.0), "y": rng.random(n, dtype=np.float32),
+            "v32": rng.standard_normal(n).astype(np.float32)}
+    cols2 = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32), "v32": np.full(n, np.nan, np.float32)}
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    for c in (cols, cols2):
+        frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in c.items()})
+        for name in ("max_v32", "first_v32", "count_v32"):
+            got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
+            assert_agg_equal(got, ora.points(c, "x", "y", SPECS[name], view), f"routed all-filtered {name}")
+
+
 def test_routed_negzero(routed):
     import torch
     from oracle import oracle as ora
