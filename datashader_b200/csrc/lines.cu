@@ -599,7 +599,6 @@ template <typename XY>
 __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) {
   __shared__ AaSeg segs[128];
   __shared__ int prefix[128];
-  __shared__ int4 rows[128];                   // per warp: the 32 rows of a round {segment, y, first x, inclusive pixel prefix}
   const AaConst kaa = aa_const(a.line_width);
   const XY* __restrict__ xs = (const XY*)a.xs;
   const XY* __restrict__ ys = (const XY*)a.ys;
@@ -609,7 +608,6 @@ __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) 
   const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
   AaSeg* const wseg = segs + w0;
   int* const wpre = prefix + w0;
-  int4* const wrow = rows + w0;
   // every warp walks whole batches of 32 consecutive segments; the loop bound is warp-uniform
   for (long long s0 = (long long)blockIdx.x * blockDim.x + w0; s0 < total; s0 += stride) {
     const long long s = s0 + lane;
@@ -670,33 +668,24 @@ __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) 
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl2, o); if (lane >= o) incl2 += t; }
       const int npix = __shfl_sync(0xffffffffu, incl2, 31);
-      wrow[lane] = make_int4(segi, yrow, xl, incl2);
-      __syncwarp();
-      // lane j draws the pixels [j * per, (j + 1) * per) of the round: one search for its first pixel, then it walks along the
-      // row and steps to the next non-empty row when the row ends (a search per pixel cost 11 % of the kernel's samples)
-      const int per = (npix + 31) >> 5;
-      int p = lane * per;
-      const int pend = min(p + per, npix);
-      if (p < pend) {
-        int lo = 0, hi = 31;                     // first row whose inclusive pixel prefix exceeds p
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (wrow[mid].w > p) hi = mid; else lo = mid + 1; }
-        int4 rw = wrow[lo];
-        int x = rw.z + (p - (lo ? wrow[lo - 1].w : 0));
-        const AaSeg* q = wseg + rw.x;
-        LineCtx c;
-        c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
-        c.plan = nullptr; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
-        c.field = q->field; c.field_nan = q->field_nan != 0; c.line = q->line; c.row = a.row_offset + q->line; c.cat = q->cat;
-        for (;;) {
-          aa_pixel(*q, kaa, c, (long long)rw.y, (long long)x);
-          if (++p >= pend) break;
-          x++;
-          if (p >= rw.w) {                        // the row is finished: on to the next one that has pixels
-            do { rw = wrow[++lo]; } while (rw.w <= p);
-            x = rw.z;
-            q = wseg + rw.x;
-            c.field = q->field; c.field_nan = q->field_nan != 0; c.line = q->line; c.row = a.row_offset + q->line; c.cat = q->cat;
-          }
+      const int excl2 = incl2 - cnt;
+      for (int p0 = 0; p0 < npix; p0 += 32) {
+        const int p = min(p0 + lane, npix - 1);
+        int lo = 0, hi = 31;                     // first lane whose inclusive pixel prefix exceeds p: exactly five halvings
+#pragma unroll
+        for (int it = 0; it < 5; it++) {
+          const int mid = (lo + hi) >> 1;
+          if (__shfl_sync(0xffffffffu, incl2, mid) > p) hi = mid; else lo = mid + 1;
+        }
+        const int ssegi = __shfl_sync(0xffffffffu, segi, lo), sy = __shfl_sync(0xffffffffu, yrow, lo);
+        const int sxl = __shfl_sync(0xffffffffu, xl, lo), sex = __shfl_sync(0xffffffffu, excl2, lo);
+        if (p0 + lane < npix) {
+          const AaSeg& q = wseg[ssegi];
+          LineCtx c;
+          c.agg = a.agg; c.has_field = a.val_dtype != DSB_NONE; c.width = a.v.width; c.canvas = a.canvas; c.mask = a.mask;
+          c.field = q.field; c.field_nan = q.field_nan != 0; c.plan = nullptr; c.line = q.line; c.row = a.row_offset + q.line;
+          c.cat = q.cat; c.ncat = a.ncat; c.hkeys = nullptr; c.touched = nullptr;
+          aa_pixel(q, kaa, c, (long long)sy, (long long)(sxl + (p - sex)));
         }
       }
       __syncwarp();
