@@ -4,16 +4,17 @@
 // bit-identical to the one Canvas.points would produce for that view alone; the canvases are stacked [V, H, W(, C)] and a
 // hit in view t updates cell t * view_cells + cell of the plan's accumulators (the ops of accum.cuh, unchanged).
 //
-// Regular grids (nx * ny views, row-major, equal extents) find their view from the coarse grid index and test it and its
-// eight neighbours with the exact mapping (a point on a shared edge belongs to both tiles, as it does for separate calls);
-// short lists of arbitrary views (<= 64) are all tested.
+// Regular grids (nx * ny views, row-major, equal extents) find their view from the coarse grid index; a point within 1/1024 of
+// a tile from a tile edge is also tested against the neighbour(s) across that edge with the exact mapping (a point ON a
+// shared edge belongs to both tiles, as it does for separate calls; the margin covers the rounding of the coarse index and of the
+// caller's tile extents, which the host checks against the grid).  Short lists of arbitrary views (<= 64) are all tested.
 #include "common.cuh"
 #include "accum.cuh"
 
 struct ViewsArgs {
   const dsb_view* views;
   int nviews, grid_nx, grid_ny;
-  double gx0, gy0, gtw, gth;
+  double gx0, gy0, inv_gtw, inv_gth;
   const void* x; const void* y;
   long long n, row_offset, view_cells;
   dsb_plan plan;
@@ -39,11 +40,15 @@ __global__ void __launch_bounds__(256) k_points_views(const ViewsArgs a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
     const XY xv = __ldcs(x + i), yv = __ldcs(y + i);
     if (a.grid_nx > 0) {
-      const double fx = ((double)xv - a.gx0) / a.gtw, fy = ((double)yv - a.gy0) / a.gth;
+      const double fx = ((double)xv - a.gx0) * a.inv_gtw, fy = ((double)yv - a.gy0) * a.inv_gth;
       if (!(fx >= -1.0 && fx <= a.grid_nx + 1.0 && fy >= -1.0 && fy <= a.grid_ny + 1.0)) continue;    // NaN or far outside
-      const int ix = (int)floor(fx), iy = (int)floor(fy);
-      for (int ty = max(iy - 1, 0); ty <= min(iy + 1, a.grid_ny - 1); ty++)
-        for (int tx = max(ix - 1, 0); tx <= min(ix + 1, a.grid_nx - 1); tx++) hit(ty * a.grid_nx + tx, xv, yv, i);
+      const double flx = floor(fx), fly = floor(fy);
+      const int ix = (int)flx, iy = (int)fly;
+      constexpr double D = 1.0 / 1024.0;
+      const int x_lo = max(fx - flx < D ? ix - 1 : ix, 0), x_hi = min(fx - flx > 1.0 - D ? ix + 1 : ix, a.grid_nx - 1);
+      const int y_lo = max(fy - fly < D ? iy - 1 : iy, 0), y_hi = min(fy - fly > 1.0 - D ? iy + 1 : iy, a.grid_ny - 1);
+      for (int ty = y_lo; ty <= y_hi; ty++)
+        for (int tx = x_lo; tx <= x_hi; tx++) hit(ty * a.grid_nx + tx, xv, yv, i);
     } else {
       for (int t = 0; t < a.nviews; t++) hit(t, xv, yv, i);
     }
@@ -64,7 +69,7 @@ extern "C" int dsb_points_views(const dsb_view* views, int32_t nviews, int32_t g
   if (n == 0) return DSB_OK;
   if (!x || !y) { dsb_set_error("dsb_points_views: null coordinate column"); return DSB_ERR_ARG; }
   ViewsArgs a;
-  a.views = views; a.nviews = nviews; a.grid_nx = grid_nx; a.grid_ny = grid_ny; a.gx0 = gx0; a.gy0 = gy0; a.gtw = gtw; a.gth = gth;
+  a.views = views; a.nviews = nviews; a.grid_nx = grid_nx; a.grid_ny = grid_ny; a.gx0 = gx0; a.gy0 = gy0; a.inv_gtw = grid_nx > 0 ? 1.0 / gtw : 0.0; a.inv_gth = grid_nx > 0 ? 1.0 / gth : 0.0;
   a.x = x; a.y = y; a.n = n; a.row_offset = row_offset; a.view_cells = view_cells; a.plan = *plan;
   const long long want = (n + 255) / 256, cap = (long long)dsb_num_sms() * 8;
   const int grid = (int)(want < cap ? want : cap);

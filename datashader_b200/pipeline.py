@@ -392,6 +392,14 @@ def points_batch(source, canvas, glyph: Point, agg, views, grid=None, dist=None)
             raise ValueError("grid=(nx, ny) must describe len(views) views")
         (x0, x1), (y0, y1) = views[0]
         gx = (nx, ny, x0, y0, x1 - x0, y1 - y0)
+        # the kernel finds a point's tile from the grid and looks across an edge only within 1/1024 of a tile of it: the views
+        # must BE that grid (up to rounding of the tile extents)
+        tw, th = x1 - x0, y1 - y0
+        for k, ((ax0, ax1), (ay0, ay1)) in enumerate(views):
+            ix, iy = k % nx, k // nx
+            if (abs(ax0 - (x0 + ix * tw)) > 1e-6 * tw or abs(ax1 - (x0 + (ix + 1) * tw)) > 1e-6 * tw
+                    or abs(ay0 - (y0 + iy * th)) > 1e-6 * th or abs(ay1 - (y0 + (iy + 1) * th)) > 1e-6 * th):
+                raise ValueError("grid=(nx, ny): the views are not a row-major grid of equal extents")
     elif nv > 64:
         raise ValueError("more than 64 views need grid=(nx, ny)")
     device = frame.device
@@ -410,17 +418,43 @@ def points_batch(source, canvas, glyph: Point, agg, views, grid=None, dist=None)
         def launch(view, chunk, glyph_, accs, canv, ctx, categorizer, ncat):
             x, y, xy_dtype = _xy_columns(chunk, glyph_.x, glyph_.y)
             cells = int(canvas.plot_height) * int(canvas.plot_width) * max(ncat, 1)
-            for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
-                _lib.check(_lib.lib().dsb_points_views(dev_views.data_ptr(), nv, gx[0], gx[1], gx[2], gx[3], gx[4], gx[5],
-                                                       x.data_ptr(), y.data_ptr(), xy_dtype, len(chunk), chunk.row_offset,
-                                                       C.byref(plan), cells, ctx.stream_ptr), "dsb_points_views")
+            lib = _lib.lib()
+            for gi, (plan, _keep) in enumerate(_plans(chunk, accs, canv, ctx, categorizer, ncat)):
+                group = accs[gi * _lib.DSB_MAX_OPS:(gi + 1) * _lib.DSB_MAX_OPS]
+                sizes = [(canv[acc.key].element_size(), canv[acc.aux.key].element_size() if acc.aux is not None else 0) for acc in group]
+                # a tile level whose stacked canvases exceed L2 is done in bands of tile ROWS (one launch per band over all the
+                # points): random REDs into DRAM-resident canvases cost far more than re-reading the columns
+                bands = [(0, gx[1] if gx[0] else 0)]
+                per_row = sum(a_ + b_ for a_, b_ in sizes) * cells * max(gx[0], 1)
+                if gx[0] and gx[1] > 1 and per_row * gx[1] > config.l2_budget_bytes:
+                    rows = max(1, int(config.l2_budget_bytes // per_row))
+                    bands = [(r0, min(r0 + rows, gx[1])) for r0 in range(0, gx[1], rows)]
+                for r0, r1 in bands:
+                    sub, v0 = plan, 0
+                    if r0 or (gx[0] and r1 != gx[1]):
+                        v0 = r0 * gx[0]
+                        sub = _sub_plan(plan, list(range(plan.nops)))
+                        for k, (sa, sx) in enumerate(sizes):
+                            sub.ops[k].agg = plan.ops[k].agg + v0 * cells * sa
+                            if sx:
+                                sub.ops[k].aux = plan.ops[k].aux + v0 * cells * sx
+                    nvb = (r1 - r0) * gx[0] if gx[0] else nv
+                    _lib.check(lib.dsb_points_views(dev_views.data_ptr() + v0 * C.sizeof(_lib.View), nvb, gx[0], (r1 - r0) if gx[0] else 0,
+                                                    gx[2], gx[3] + r0 * gx[5], gx[4], gx[5],
+                                                    x.data_ptr(), y.data_ptr(), xy_dtype, len(chunk), chunk.row_offset,
+                                                    C.byref(sub), cells, ctx.stream_ptr), "dsb_points_views")
 
         reds, results, labels = _accumulate_and_finalize(frame, resident, needed, schema, vstructs[0], canvas, glyph, agg, dist,
                                                          launch, ctx_extra={"nviews": nv})
     out = []
+    xcache, ycache = {}, {}                    # a tile level has nx distinct x ranges and ny distinct y ranges, not nx * ny
     for k, ((xr, yr), (x_st, y_st)) in enumerate(zip(views, sts)):
-        x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
-        y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+        x_axis = xcache.get(xr)
+        if x_axis is None:
+            x_axis = xcache[xr] = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+        y_axis = ycache.get(yr)
+        if y_axis is None:
+            y_axis = ycache[yr] = canvas.y_axis.compute_index(y_st, canvas.plot_height)
         out.append(_wrap(agg, reds, [t[k] for t in results], glyph, x_axis, y_axis, xr, yr, labels))
     return out
 

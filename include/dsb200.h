@@ -151,7 +151,8 @@ int dsb_routed_configure(int64_t min_rows);
  * views: DEVICE array of dsb_view.  The plan's canvases are stacked [nviews, H, W(, ncat)], view_cells = H * W * max(ncat, 1);
  * every view keeps its own scale / translate / bounds, so each canvas equals the one dsb_points produces for that view.
  * grid_nx > 0: the views form a row-major grid_nx x grid_ny grid of equal extents (gtw x gth) starting at (gx0, gy0) and a
- * point is tested against its grid cell and the eight neighbours only; grid_nx == 0: at most 64 arbitrary views, all tested. */
+ * point is tested against its grid cell, and against the neighbour(s) across an edge when it lies within 1/1024 of a tile of that
+ * edge (the views' own bounds decide; they must match the grid to 1e-6 of a tile); grid_nx == 0: at most 64 arbitrary views, all tested. */
 int dsb_points_views(const dsb_view* views, int32_t nviews, int32_t grid_nx, int32_t grid_ny, double gx0, double gy0,
                      double gtw, double gth, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
                      const dsb_plan* plan, int64_t view_cells, void* stream);

@@ -45,17 +45,34 @@ def _same(a, b, name):
             _same(a[k], b[k], f"{name}.{k}")
 
 
-def test_tile_grid_equals_single_calls():
+@pytest.mark.parametrize("l2_budget", [None, 1, 64 * 48 * 4 * 12 * 4], ids=["one-launch", "band-per-tile-row", "bands-of-rows"])
+def test_tile_grid_equals_single_calls(l2_budget):
+    """l2_budget: the stacked canvases 'exceed L2' and the level is done in bands of tile rows (one launch per band)."""
     import datashader_b200 as ds
     frame = _frame(ds, 300_000, 3)
     cvs = ds.Canvas(64, 48)
     views = [((float(ix), float(ix + 1)), (float(iy), float(iy + 1))) for iy in range(4) for ix in range(4)]
+    old = ds.config.l2_budget_bytes
     for name in AGGS:
-        got = cvs.points_batch(frame, "x", "y", _agg(ds, name), views, grid=(4, 4))
+        if l2_budget is not None:
+            ds.config.l2_budget_bytes = l2_budget
+        try:
+            got = cvs.points_batch(frame, "x", "y", _agg(ds, name), views, grid=(4, 4))
+        finally:
+            ds.config.l2_budget_bytes = old
         assert len(got) == 16
         for (xr, yr), g in zip(views, got):
             want = ds.Canvas(64, 48, x_range=xr, y_range=yr).points(frame, "x", "y", _agg(ds, name))
             _same(g, want, f"{name} tile {xr} {yr}")
+
+
+def test_grid_views_must_form_the_grid():
+    import datashader_b200 as ds
+    frame = _frame(ds, 300_000, 3)
+    views = [((float(ix), float(ix + 1)), (float(iy), float(iy + 1))) for iy in range(2) for ix in range(2)]
+    views[3] = ((1.0, 2.5), (1.0, 2.0))
+    with pytest.raises(ValueError, match="grid"):
+        ds.Canvas(16, 16).points_batch(frame, "x", "y", ds.count(), views, grid=(2, 2))
 
 
 def test_arbitrary_views_equal_single_calls():

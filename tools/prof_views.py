@@ -24,5 +24,5 @@ for name, agg in (("count", ds.count()), ("mean", ds.mean("v")), ("max", ds.max(
     print(name, "host ms", round((t1 - t0) * 1e3, 2), "wall ms", round((t2 - t0) * 1e3, 2), "gpu ms", round(e0.elapsed_time(e1), 2), _lib.lib().dsb_last_kernel())
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
-cvs.points_batch(frame, "x", "y", ds.count(), views, grid=(16, 16)); torch.cuda.synchronize()
-pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+cvs.points_batch(frame, "x", "y", ds.max("v"), views, grid=(16, 16)); torch.cuda.synchronize()
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
