@@ -476,6 +476,10 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
     a.inv = (uint32_t)m; a.sh = lg; a.kmul = 65536u - a.cpb;
   }
   a.ncell = (uint32_t)ncell;
+  // pass 1 keeps a 20-byte entry per bucket next to its 64 KB tile: canvases beyond ~8000 buckets (360 M cells) stay with the banded kernels
+  if ((size_t)RTILE * 8 + (size_t)((a.nb + 2) & ~1u) * (16 + 4) + 64 * 4 > 226 * 1024) {
+    dsb_set_error("dsb_points_routed: too many buckets for the shared-memory tables"); return DSB_ERR_UNSUPPORTED;
+  }
   const size_t hdr = route_fixed_bytes(a.nb, n);
   if (a.nb > 65535 || scratch_bytes < (int64_t)(hdr + ((size_t)a.nb * 4096 + 1024) * 8)) { dsb_set_error("dsb_points_routed: scratch too small"); return DSB_ERR_ARG; }
   unsigned char* p = (unsigned char*)scratch;

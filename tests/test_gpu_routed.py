@@ -122,6 +122,33 @@ def test_routed_everything_filtered(routed):
             assert_agg_equal(got, ora.points(c, "x", "y", SPECS[name], view), f"routed all-filtered {name}")
 
 
+def test_routed_declines_canvases_with_too_many_buckets(routed):
+    """24 000 x 24 000 cells = 12 784 buckets: their tables do not fit pass 1's shared memory; the call must fall back to the
+    banded kernels and still be right (compared with the unbanded generic kernel)."""
+    import torch
+    from datashader_b200 import _lib
+    ds = routed
+    rng = np.random.default_rng(9)
+    n, W, H = 200_000, 24_000, 24_000
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32), "v32": rng.standard_normal(n).astype(np.float32)}
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    ds.config.device_results = True
+    try:
+        got = cvs.points(frame, "x", "y", ds.max("v32")).data
+        assert b"k_route" not in _lib.lib().dsb_last_kernel()
+        xi = np.minimum((cols["x"].astype(np.float64) * W).astype(np.int64), W - 1)
+        yi = np.minimum((cols["y"].astype(np.float64) * H).astype(np.int64), H - 1)
+        cells = torch.from_numpy(yi * W + xi).cuda()
+        want = torch.full((H * W,), float("-inf"), dtype=torch.float32, device="cuda")
+        want.scatter_reduce_(0, cells, torch.from_numpy(cols["v32"]).cuda(), "amax")
+        hit = torch.isfinite(want)
+        assert int(hit.sum()) > 0.99 * n
+        assert torch.equal(got.reshape(-1)[hit].float(), want[hit]) and bool(torch.isnan(got.reshape(-1)[~hit]).all())
+    finally:
+        ds.config.device_results = False
+
+
 def test_routed_negzero(routed):
     import torch
     from oracle import oracle as ora
