@@ -37,8 +37,8 @@ struct RouteArgs {
   const uint32_t* cap;                  // [nb]
   uint32_t* cursor;                     // [nb] records offered so far (beyond cap: applied to the canvas directly)
   uint32_t* queue;                      // pass 2: next bucket to hand out
-  uint32_t* slow; uint32_t* slow_n;     // rows whose fast pixel is not certain (near a pixel edge): mapped exactly by k_route_slow
-  uint32_t slow_cap;
+  uint32_t* slow; uint32_t* slow_n;     // points whose fast pixel is not certain (near a pixel edge) as {x bits, y bits, payload}:
+  uint32_t slow_cap;                    //   mapped exactly by k_route_slow (12-byte entries: it streams them instead of gathering rows)
   void* canvas;
   unsigned int* notes;
 };
@@ -174,16 +174,25 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
         rank[u * 4 + k] = atomicAdd(hist + (kk >> 16), 1u);
       }
     }
-    while (unsure) {                                           // out of the unrolled body: queue the rows for k_route_slow
+    while (unsure) {                                           // out of the unrolled body: queue the points for k_route_slow
       const int j = __ffs(unsure) - 1;
       unsure &= unsure - 1;
       const uint32_t row = (uint32_t)(4 * (t4 + (long long)(j >> 2) * RT + tid) + (j & 3));
-      const uint32_t pos = atomicAdd(a.slow_n, 1u);
-      if (pos < a.slow_cap) a.slow[pos] = row;
-      else {                                                   // list full (adversarial data): map it here, straight to the canvas
-        const float vv = a.vcol ? a.vcol[row] : 1.f;
-        const int cell = map_exact_linear(a.v, a.x[row], a.y[row]);
-        if (cell >= 0) route_direct<OP>(a, (uint32_t)cell, (OP == R_MAX32 || OP == R_MIN32) ? __float_as_uint(vv) : row);
+      const float xr = a.x[row], yr = a.y[row];                // re-read (the streaming loads above do not stay in L2: +1.1 GB of DRAM
+      const float vv = a.vcol ? a.vcol[row] : 1.f;             //   reads per 1e9 points at 8192^2, against 3 GB of row gathers in k_route_slow)
+      const uint32_t payload = (OP == R_MAX32 || OP == R_MIN32) ? __float_as_uint(vv) : row;
+      // one counter update per warp iteration, not per lane (0.8 % of 1e9 points on ONE address otherwise)
+      const unsigned m = __activemask();
+      const int leader = __ffs(m) - 1, lane = tid & 31;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(a.slow_n, (uint32_t)__popc(m));
+      const uint32_t pos = __shfl_sync(m, base, leader) + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (pos < a.slow_cap) {
+        uint32_t* e = a.slow + 3 * (size_t)pos;
+        e[0] = __float_as_uint(xr); e[1] = __float_as_uint(yr); e[2] = payload;
+      } else {                                                 // list full (adversarial data): map it here, straight to the canvas
+        const int cell = map_exact_linear(a.v, xr, yr);
+        if (cell >= 0) route_direct<OP>(a, (uint32_t)cell, payload);
         if (OP == R_MAX32 || OP == R_MIN32) negzero |= cell >= 0 && is_negzero(vv);
       }
     }
@@ -267,12 +276,12 @@ __global__ void __launch_bounds__(256) k_route_slow(const __grid_constant__ Rout
   const uint32_t n = min(*a.slow_n, a.slow_cap);
   bool negzero = false;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const uint32_t i = a.slow[j];
-    const float vv = a.vcol ? a.vcol[i] : 1.f;
-    const int cell = map_exact_linear(a.v, a.x[i], a.y[i]);
+    const uint32_t* e = a.slow + 3 * (size_t)j;
+    const uint32_t payload = e[2];
+    const int cell = map_exact_linear(a.v, __uint_as_float(e[0]), __uint_as_float(e[1]));
     if (cell < 0) continue;
-    if (OP == R_MAX32 || OP == R_MIN32) { negzero |= is_negzero(vv); route_direct<OP>(a, (uint32_t)cell, __float_as_uint(vv)); }
-    else route_direct<OP>(a, (uint32_t)cell, i);
+    if (OP == R_MAX32 || OP == R_MIN32) negzero |= is_negzero(__uint_as_float(payload));
+    route_direct<OP>(a, (uint32_t)cell, payload);
   }
   if ((OP == R_MAX32 || OP == R_MIN32) && negzero && a.notes) *a.notes = DSB_NOTE_NEGZERO;
 }
@@ -409,8 +418,8 @@ static uint32_t route_nb(long long ncell, uint32_t* cpb) {
   return (uint32_t)nb;
 }
 static size_t route_header_bytes(uint32_t nb) { return (((size_t)nb * (8 + 4 + 4 + 4) + 64) + 255) & ~(size_t)255; }
-static size_t route_slow_entries(int64_t n) { return (size_t)(n / 16) + 65536; }        // ~6 % of the rows (typical: 0.1 %)
-static size_t route_fixed_bytes(uint32_t nb, int64_t n) { return route_header_bytes(nb) + ((route_slow_entries(n) * 4 + 255) & ~(size_t)255); }
+static size_t route_slow_entries(int64_t n) { return (size_t)(n / 32) + 65536; }        // ~3 % of the rows (0.8 % at 8192^2, less on smaller canvases)
+static size_t route_fixed_bytes(uint32_t nb, int64_t n) { return route_header_bytes(nb) + ((route_slow_entries(n) * 12 + 255) & ~(size_t)255); }
 
 extern "C" int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t n) {
   if (!view || view->width <= 0 || view->height <= 0 || n < 0) return 0;

@@ -79,7 +79,7 @@ def test_routed_overflow_falls_back_to_canvas_atomics(routed):
     view, _, _ = pipeline.make_view(ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0)), (0.0, 1.0), (0.0, 1.0))
     stream = torch.cuda.current_stream().cuda_stream
     nb = -(-W * H // 45056)
-    small = (((nb * 20 + 64) + 255) & ~255) + (((n // 16 + 65536) * 4 + 255) & ~255) + (nb * 4096 + 1024) * 8   # the minimum accepted
+    small = (((nb * 20 + 64) + 255) & ~255) + (((n // 32 + 65536) * 12 + 255) & ~255) + (nb * 4096 + 1024) * 8   # the minimum accepted
     for op, dtype, use_chk in ((_lib.OP_MAX32, torch.int32, False), (_lib.OP_MINROW, torch.int64, True), (_lib.OP_MAXROW, torch.int64, True),
                                (_lib.OP_COUNT, torch.int32, False)):
         outs = []
