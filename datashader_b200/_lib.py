@@ -26,7 +26,7 @@ _NP_TO_DSB = {
 OP_COUNT, OP_ANY, OP_SUM, OP_MAX32, OP_MIN32, OP_MAX64, OP_MIN64 = 1, 2, 3, 4, 5, 6, 7
 OP_MAXROW, OP_MINROW, OP_ARGMAX32, OP_ARGMIN32, OP_MATCHROW64 = 8, 9, 10, 11, 12
 
-LINE_ANY, LINE_COUNT, LINE_SUM, LINE_MAX, LINE_MIN, LINE_MEAN = 1, 2, 3, 4, 5, 6
+LINE_ANY, LINE_COUNT, LINE_SUM, LINE_MAX, LINE_MIN, LINE_MEAN, LINE_MEAN_2STAGE = 1, 2, 3, 4, 5, 6, 7
 AA2_SUM, AA2_COUNT, AA2_MIN, AA2_FIRST, AA2_LAST, AA2_ARGMIN, AA2_ARGMAX = 1, 2, 3, 4, 5, 6, 7
 
 

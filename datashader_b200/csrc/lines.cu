@@ -1133,8 +1133,11 @@ extern "C" int dsb_lines_axis1_cat(const dsb_view* view, const void* xs, const v
   if (ncat < 0 || (ncat > 0 && (!cat || cat_dtype == DSB_NONE))) { dsb_set_error("dsb_lines_axis1_cat: bad category column"); return DSB_ERR_ARG; }
   if (ncat > 0 && !(line_width > 0.0)) { dsb_set_error("dsb_lines_axis1_cat: categories are for the antialiased form (use dsb_lines_axis1_plan)"); return DSB_ERR_UNSUPPORTED; }
   if (!view || view->width <= 0 || view->height <= 0 || !canvas) { dsb_set_error("dsb_lines_axis1: bad view/canvas"); return DSB_ERR_ARG; }
-  if (agg < DSB_LINE_ANY || agg > DSB_LINE_MEAN) { dsb_set_error("dsb_lines_axis1: unknown agg %d", agg); return DSB_ERR_ARG; }
+  if (agg < DSB_LINE_ANY || agg > DSB_LINE_MEAN_2STAGE) { dsb_set_error("dsb_lines_axis1: unknown agg %d", agg); return DSB_ERR_ARG; }
   const bool aa = line_width > 0.0;
+  // mean's bases next to a 2-stage reduction: the same appends, drawn in overwrite mode (antialias.py:47-56: no SUM_1AGG left)
+  const bool mean_overwrite = agg == DSB_LINE_MEAN_2STAGE;
+  if (mean_overwrite) agg = DSB_LINE_MEAN;
   if (aa && agg == DSB_LINE_MIN) { dsb_set_error("dsb_lines_axis1: antialiased min needs the 2-stage combine"); return DSB_ERR_UNSUPPORTED; }
   if (agg == DSB_LINE_MEAN && !aa) { dsb_set_error("dsb_lines_axis1: mean is the antialiased form only (use dsb_lines_axis1_plan)"); return DSB_ERR_UNSUPPORTED; }
   if ((agg == DSB_LINE_SUM || agg == DSB_LINE_MAX || agg == DSB_LINE_MIN || agg == DSB_LINE_MEAN) && (val_dtype == DSB_NONE || !val)) {
@@ -1146,7 +1149,7 @@ extern "C" int dsb_lines_axis1_cat(const dsb_view* view, const void* xs, const v
   LineArgs a;
   a.v = *view; a.xs = xs; a.ys = ys; a.nlines = nlines; a.nverts = nverts; a.val = val; a.val_dtype = val_dtype;
   a.agg = agg; a.line_width = line_width; a.canvas = canvas; a.mask = mask;
-  a.overwrite = !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM || agg == DSB_LINE_MEAN);   // antialias.py:47-56
+  a.overwrite = mean_overwrite || !(agg == DSB_LINE_COUNT || agg == DSB_LINE_SUM || agg == DSB_LINE_MEAN);   // antialias.py:47-56
   a.use_plan = 0; a.row_offset = 0; a.cat = cat; a.cat_dtype = cat_dtype; a.ncat = ncat;
   int rc = apply_layout(a, layout, "dsb_lines_axis1");
   if (rc != DSB_OK) return rc;

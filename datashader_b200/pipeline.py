@@ -546,7 +546,10 @@ def _lines_antialiased(frame, schema, canvas, glyph, agg, line_width, dist):
             inner = type(inner)(inner.column, self_intersect=False)
             r = rd.by(r.categorizer, inner) if isinstance(r, rd.by) else inner
         if force and isinstance(inner, rd.mean):
-            raise NotImplementedError("mean() next to a 2-stage antialiased reduction is not implemented in datashader_b200")
+            if isinstance(r, rd.by):
+                raise NotImplementedError("by(cat, mean()) next to a 2-stage antialiased reduction is not implemented in datashader_b200")
+            outs.append(_lines_aa_mean_2stage(frame, canvas, glyph, inner, line_width, dist))
+            continue
         if isinstance(inner, rd.where):
             if isinstance(r, rd.by):
                 raise NotImplementedError("by(where(...)) is not implemented for antialiased datashader_b200 lines")
@@ -591,6 +594,34 @@ def _lines_aa2_by(frame, schema, canvas, glyph, agg, line_width, dist):
     coords = dict(first.coords)
     coords[agg.cat_column] = list(labels)
     return DataArray(data, coords=coords, dims=list(first.dims) + [agg.cat_column], attrs=dict(first.attrs))
+
+
+def _lines_aa_mean_2stage(frame, canvas, glyph, agg, line_width, dist):
+    """mean(col) in a summary that also holds a 2-stage reduction.  Its bases (_sum_zero, _count_ignore_antialiasing) are
+    plain FloatingReductions: they keep their single-stage appends (reductions.py:965-973, 679-685), but everything is now
+    drawn in overwrite mode (antialias.py:47-56, so prev_aa_factor is always 0) into a per-line canvas that is summed into the
+    result (SUM_2AGG, :946-950, 673-677) - i.e. every (segment, pixel) touch adds value x coverage and counts 1."""
+    device = frame.device
+    with torch.cuda.device(device):
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+        x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout) = _line_setup(frame, canvas, glyph, dist)
+        H, W = canvas.plot_height, canvas.plot_width
+        sums = torch.zeros((H, W), dtype=torch.float64, device=device)
+        counts = torch.zeros((H, W), dtype=torch.int32, device=device)
+        val = frame[agg.column]
+        _lib.check(_lib.lib().dsb_lines_axis1_cat(C.byref(view), xs.data_ptr(), ys.data_ptr(), xy_dtype, nlines, nverts, C.byref(layout),
+                                                  val.data_ptr(), _lib.dsb_dtype(frame.np_dtype(agg.column)), _lib.LINE_MEAN_2STAGE,
+                                                  line_width, sums.data_ptr(), counts.data_ptr(), None, _lib.NONE, 0, stream_ptr),
+                   "dsb_lines_axis1_cat")
+        if dist is not None:
+            dist._all_reduce(sums, "sum")
+            dist._all_reduce(counts, "sum")
+        out = torch.where(counts > 0, sums / counts.to(torch.float64), torch.full_like(sums, float("nan")))
+        data = _to_host(out)
+    x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
+    y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
+    return DataArray(data, coords={glyph.y_label: y_axis, glyph.x_label: x_axis}, dims=[glyph.y_label, glyph.x_label],
+                     attrs=dict(x_range=x_range, y_range=y_range))
 
 
 def _lines_aa_where(frame, canvas, glyph, agg, line_width, dist):

@@ -1,11 +1,13 @@
-"""tf.shade on the GPU (the reference's datashader/transfer_functions/__init__.py:616-745).
+"""tf.shade and the post-shade image operations on the GPU (the reference's datashader/transfer_functions/__init__.py:148-745,
+748-1051; composite.py).
 
-Covered: 3-D categorical aggregates (uint32 counts, e.g. by('cat', count())) -> colour mix + alpha, and
-2-D aggregates with a list colormap or a single colour; how in {'eq_hist', 'log', 'cbrt', 'linear'},
-span=None.  The canvas-sized work (totals, histogram, scan/CDF, per-pixel lookup and colour mixing) runs
-in libdsb200 (csrc/shade.cu); the host only picks scalars (offset, histogram range) exactly the way
-_interpolate_alpha / eq_hist do.  Not covered (raise NotImplementedError): span=..., callable how/cmap,
-float categorical aggregates, discrete colour keys on 2-D aggregates, spread/dynspread/stack.
+shade: 3-D categorical aggregates (uint32 counts such as by('cat', count()), and float aggregates such as by('cat', mean()))
+-> colour mix + alpha; 2-D aggregates with a list colormap, a single colour or a discrete colour key; how in {'eq_hist',
+'log', 'cbrt', 'linear'} with span=None or an explicit span, alpha / min_alpha / rescale_discrete_levels.  The canvas-sized
+work (totals, histogram, scan / CDF, per-pixel lookup and colour mixing) runs in libdsb200 (csrc/shade.cu); the host only
+picks scalars (offset, histogram range) exactly the way _interpolate_alpha / eq_hist do.  A callable `how` or a callable
+(matplotlib-style) cmap is applied on the host like the reference does (_interpolate_host); a callable cmap with
+how='eq_hist' raises NotImplementedError.  spread / dynspread / stack / set_background run on the GPU (csrc/imageops.cu).
 """
 from __future__ import annotations
 

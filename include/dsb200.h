@@ -185,7 +185,10 @@ int dsb_finalize_sum_counted(const double* sum, const void* count_u32, double* o
 
 /* ---- lines ---------------------------------------------------------------------------------- */
 typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5,
-               DSB_LINE_MEAN = 6 /* antialiased only: canvas f64 sum (zeroed), `mask` = u32 count canvas (zeroed) */ } dsb_line_agg;
+               DSB_LINE_MEAN = 6 /* antialiased only: canvas f64 sum (zeroed), `mask` = u32 count canvas (zeroed) */,
+               DSB_LINE_MEAN_2STAGE = 7 /* DSB_LINE_MEAN drawn in overwrite mode: mean when a 2-stage reduction shares its summary (its
+                                           bases are FloatingReductions: every touch adds value x coverage and counts 1,
+                                           reductions.py:965-973, 687-693; compiler.py:539-554) */ } dsb_line_agg;
 
 /* Vertex addressing of the other line layouts.  NULL = LinesAxis1: dense [nlines, nverts] matrices, one value per
  * line.  x_line_stride / y_line_stride = elements between consecutive lines (0 = one vertex vector shared by all

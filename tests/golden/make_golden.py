@@ -510,7 +510,8 @@ def lines_aa3_cases():
         "s2": ds.summary(count=ds.count("val", self_intersect=True), sum=ds.sum("val", self_intersect=True)),
         "s3": ds.summary(cnt=ds.count(), mx=ds.max("val"), first=ds.first("val"), anyv=ds.any()),
         "s4": ds.summary(count=ds.count(self_intersect=True), sum=ds.sum("val", self_intersect=False)),
-    }
+        "s5": ds.summary(mean=ds.mean("val"), min=ds.min("val")),                         # mean next to a 2-stage member: its sum and
+    }                                                                                     #   count are combined per line (SUM_2AGG)
     for sname, agg in summaries.items():
         res = cvs.line(df, agg=agg, **kw)
         for k in agg.keys:

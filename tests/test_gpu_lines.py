@@ -280,6 +280,7 @@ def test_lines_antialiased_summary_by_where_golden():
         "s2": ds.summary(count=ds.count("val", self_intersect=True), sum=ds.sum("val", self_intersect=True)),
         "s3": ds.summary(cnt=ds.count(), mx=ds.max("val"), first=ds.first("val"), anyv=ds.any()),
         "s4": ds.summary(count=ds.count(self_intersect=True), sum=ds.sum("val", self_intersect=False)),
+        "s5": ds.summary(mean=ds.mean("val"), min=ds.min("val")),      # mean's bases drawn in overwrite mode, combined per line
     }
     for sname, agg in summaries.items():
         res = cvs.line(frame, agg=agg, **kw)
