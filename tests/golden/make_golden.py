@@ -511,7 +511,11 @@ def lines_aa3_cases():
         "s3": ds.summary(cnt=ds.count(), mx=ds.max("val"), first=ds.first("val"), anyv=ds.any()),
         "s4": ds.summary(count=ds.count(self_intersect=True), sum=ds.sum("val", self_intersect=False)),
         "s5": ds.summary(mean=ds.mean("val"), min=ds.min("val")),                         # mean next to a 2-stage member: its sum and
-    }                                                                                     #   count are combined per line (SUM_2AGG)
+                                                                                          #   count are combined per line (SUM_2AGG)
+        "s6": ds.summary(anyv=ds.any(), mn=ds.min("val"), mx=ds.max("val")),
+        "s7": ds.summary(mx=ds.max("val"), last=ds.last("val"), sum=ds.sum("val"), mean=ds.mean("val")),
+        "s8": ds.summary(mean=ds.mean("val"), count=ds.count(), sum=ds.sum("val")),       # nothing 2-stage: all single-stage
+    }
     for sname, agg in summaries.items():
         res = cvs.line(df, agg=agg, **kw)
         for k in agg.keys:

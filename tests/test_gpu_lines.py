@@ -281,6 +281,9 @@ def test_lines_antialiased_summary_by_where_golden():
         "s3": ds.summary(cnt=ds.count(), mx=ds.max("val"), first=ds.first("val"), anyv=ds.any()),
         "s4": ds.summary(count=ds.count(self_intersect=True), sum=ds.sum("val", self_intersect=False)),
         "s5": ds.summary(mean=ds.mean("val"), min=ds.min("val")),      # mean's bases drawn in overwrite mode, combined per line
+        "s6": ds.summary(anyv=ds.any(), mn=ds.min("val"), mx=ds.max("val")),
+        "s7": ds.summary(mx=ds.max("val"), last=ds.last("val"), sum=ds.sum("val"), mean=ds.mean("val")),
+        "s8": ds.summary(mean=ds.mean("val"), count=ds.count(), sum=ds.sum("val")),
     }
     for sname, agg in summaries.items():
         res = cvs.line(frame, agg=agg, **kw)
