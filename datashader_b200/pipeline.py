@@ -546,14 +546,12 @@ def _lines_antialiased(frame, schema, canvas, glyph, agg, line_width, dist):
             inner = type(inner)(inner.column, self_intersect=False)
             r = rd.by(r.categorizer, inner) if isinstance(r, rd.by) else inner
         if force and isinstance(inner, rd.mean):
-            if isinstance(r, rd.by):
-                raise NotImplementedError("by(cat, mean()) next to a 2-stage antialiased reduction is not implemented in datashader_b200")
-            outs.append(_lines_aa_mean_2stage(frame, canvas, glyph, inner, line_width, dist))
+            outs.append(_lines_aa2_by(frame, schema, canvas, glyph, r, line_width, dist) if isinstance(r, rd.by)
+                        else _lines_aa_mean_2stage(frame, canvas, glyph, inner, line_width, dist))
             continue
         if isinstance(inner, rd.where):
-            if isinstance(r, rd.by):
-                raise NotImplementedError("by(where(...)) is not implemented for antialiased datashader_b200 lines")
-            outs.append(_lines_aa_where(frame, canvas, glyph, inner, line_width, dist))
+            outs.append(_lines_aa2_by(frame, schema, canvas, glyph, r, line_width, dist) if isinstance(r, rd.by)
+                        else _lines_aa_where(frame, canvas, glyph, inner, line_width, dist))
         elif _aa2_combo(inner) is None:
             if getattr(inner, "_line_agg", None) is None:
                 raise NotImplementedError(f"{type(inner).__name__} is not implemented for antialiased datashader_b200 lines yet")
@@ -568,14 +566,18 @@ def _lines_antialiased(frame, schema, canvas, glyph, agg, line_width, dist):
 
 
 def _lines_aa2_by(frame, schema, canvas, glyph, agg, line_width, dist):
-    """by(cat, <2-stage reduction>) on antialiased lines: the stage-2 combination is per category plane (categorical=True,
-    reductions.py:782-787), i.e. each category's lines are folded on their own - one dsb_lines_aa2 run per category over
-    that category's lines (line order, hence first / last, is preserved inside a category)."""
+    """by(cat, <2-stage reduction | where(...) | mean next to a 2-stage member>) on antialiased lines: the stage-2
+    combination is per category plane (categorical=True, reductions.py:782-787), i.e. each category's lines are folded on
+    their own - one run per category over that category's lines (line order, hence first / last and the row ids of
+    where(), is preserved inside a category; where()'s row ids are mapped back to the rows of the whole frame)."""
     if glyph_per_vertex(glyph):
         raise NotImplementedError("by() over per-vertex line glyphs is not implemented for 2-stage antialiasing")
     categorizer, ncat, labels = _categorical_setup([agg], schema)
     codes = categorizer.codes(frame)
     inner = agg.reduction
+    is_where = isinstance(inner, rd.where)
+    if is_where and dist is not None:
+        raise NotImplementedError("by(cat, where(...)) on antialiased lines over sharded frames")
     # ranges must be those of the whole frame, not of a category's subset
     x_range, y_range = _line_setup(frame, canvas, glyph, dist)[:2]
     import copy
@@ -586,9 +588,19 @@ def _lines_aa2_by(frame, schema, canvas, glyph, agg, line_width, dist):
         sel = (codes == c) | (codes == c - ncat)            # negative codes wrap like numba's agg[:, :, -1]
         sub = DeviceFrame({k: frame[k][sel].contiguous() for k in frame.columns}, frame.categories, 0, None)
         sub.sharded, sub.group = getattr(frame, "sharded", False), getattr(frame, "group", None)
-        part = _lines_aa2(sub, sub_canvas, glyph, inner, _aa2_combo(inner), line_width, dist)
+        if is_where:
+            part = _lines_aa_where(sub, sub_canvas, glyph, inner, line_width, dist)
+        elif isinstance(inner, rd.mean):
+            part = _lines_aa_mean_2stage(sub, sub_canvas, glyph, inner, line_width, dist)
+        else:
+            part = _lines_aa2(sub, sub_canvas, glyph, inner, _aa2_combo(inner), line_width, dist)
         first = first or part
-        planes.append(torch.as_tensor(part.data))
+        plane = torch.as_tensor(part.data, device=frame.device)
+        if is_where and inner.column == rd.SpecialColumn.RowIndex:      # rows of the subset -> rows of the frame
+            idx = torch.nonzero(sel).squeeze(1)
+            if idx.numel():
+                plane = torch.where(plane >= 0, idx[plane.clamp(min=0)] + frame.row_offset, torch.full_like(plane, -1))
+        planes.append(plane)
     data = torch.stack(planes, dim=-1)
     data = data if config.device_results else data.cpu().numpy()
     coords = dict(first.coords)

@@ -523,6 +523,13 @@ def lines_aa3_cases():
     for aname, inner in {"min": ds.min("val"), "first": ds.first("val"), "last": ds.last("val"),
                          "sum_nsi": ds.sum("val", self_intersect=False), "count_nsi": ds.count(self_intersect=False)}.items():
         out[f"aa3_by_{aname}"] = np.asarray(cvs.line(df, agg=ds.by("cat", inner), **kw).data)
+    for aname, agg in {"by_where_first_row": ds.by("cat", ds.where(ds.first("val"))),
+                       "by_where_last_other": ds.by("cat", ds.where(ds.last("val"), "other")),
+                       "by_where_max_row": ds.by("cat", ds.where(ds.max("val"))),
+                       "by_where_min_other": ds.by("cat", ds.where(ds.min("val"), "other"))}.items():
+        out[f"aa3_{aname}"] = np.asarray(cvs.line(df, agg=agg, **kw).data)
+    res = cvs.line(df, agg=ds.summary(m=ds.by("cat", ds.mean("val")), mn=ds.min("val")), **kw)
+    out["aa3_s9_m"], out["aa3_s9_mn"] = np.asarray(res["m"].data), np.asarray(res["mn"].data)
     for aname, agg in {"where_first_row": ds.where(ds.first("val")), "where_first_other": ds.where(ds.first("val"), "other"),
                        "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other"),
                        "where_max_row": ds.where(ds.max("val")), "where_max_other": ds.where(ds.max("val"), "other"),

@@ -258,8 +258,6 @@ def test_lines_aa_by_category_golden():
         want = g[f"aaby_lw2_{aname}"]
         assert tuple(r.dims) == ("y", "x", "cat") and list(r.coords["cat"]) == ["a", "b", "c", "d"], aname
         _cmp_aa(r.data, want, f"aa by {aname}")
-    with pytest.raises(NotImplementedError):
-        cvs.line(frame, x=xcols, y=ycols, axis=1, agg=ds.by("cat", ds.where(ds.first("val"))), line_width=2)
 
 
 def test_lines_antialiased_summary_by_where_golden():
@@ -294,6 +292,16 @@ def test_lines_antialiased_summary_by_where_golden():
         r = cvs.line(frame, agg=ds.by("cat", inner), **kw)
         assert tuple(r.dims) == ("y", "x", "cat") and list(r.coords["cat"]) == ["a", "b", "c", "d"], aname
         _cmp_aa(r.data, g[f"aa3_by_{aname}"], f"aa by {aname}")
+    # by(cat, where(...)): per category plane, row ids of the whole frame; by(cat, mean) next to a 2-stage member
+    for aname, agg in {"by_where_first_row": ds.by("cat", ds.where(ds.first("val"))),
+                       "by_where_last_other": ds.by("cat", ds.where(ds.last("val"), "other")),
+                       "by_where_max_row": ds.by("cat", ds.where(ds.max("val"))),
+                       "by_where_min_other": ds.by("cat", ds.where(ds.min("val"), "other"))}.items():
+        got, want = cvs.line(frame, agg=agg, **kw).data, g[f"aa3_{aname}"]
+        assert got.shape == want.shape and got.dtype == want.dtype and np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), aname
+    res = cvs.line(frame, agg=ds.summary(m=ds.by("cat", ds.mean("val")), mn=ds.min("val")), **kw)
+    _cmp_aa(res["m"].data, g["aa3_s9_m"], "summary s9.m (by(cat, mean) next to min)")
+    _cmp_aa(res["mn"].data, g["aa3_s9_mn"], "summary s9.mn")
     for aname, agg in {"where_first_row": ds.where(ds.first("val")), "where_first_other": ds.where(ds.first("val"), "other"),
                        "where_last_row": ds.where(ds.last("val")), "where_last_other": ds.where(ds.last("val"), "other"),
                        "where_max_row": ds.where(ds.max("val")), "where_max_other": ds.where(ds.max("val"), "other"),
