@@ -1,6 +1,7 @@
 """Differential fuzz of Canvas.points against the C oracle: random canvas sizes, ranges (including ranges far from the
 origin, where the float32 fast mapping must hand over to the exact one), coordinate dtypes, reductions and NaN patterns,
-with every specialised kernel forced on at small n (K2 privatised count, K1 mono, 16-bit packed count)."""
+with every specialised kernel forced on at small n (K2 privatised count, K1 mono, 16-bit packed count; every fourth seed the
+routed path - float32 coordinates only, it declines the rest and the call falls back)."""
 import numpy as np
 import pytest
 
@@ -22,7 +23,10 @@ def forced(monkeypatch):
     monkeypatch.setattr(ds.config, "count16_min_rows", 0)
     ds._lib.check(lib.dsb_configure(b"mono_min_rows", 0), "cfg")
     ds._lib.check(lib.dsb_configure(b"band_min_rows", 0), "cfg")
+    old = (ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16)
     yield ds
+    ds.config.routed_min_rows, ds.config.l2_budget_bytes, ds.config.priv_count, ds.config.count16 = old
+    ds._lib.check(lib.dsb_routed_configure(1 << 24), "cfg")
     ds._lib.check(lib.dsb_configure(b"mono_min_rows", 1 << 20), "cfg")
     ds._lib.check(lib.dsb_configure(b"band_min_rows", 1 << 22), "cfg")
     ds._lib.check(lib.dsb_configure(b"l2_band_bytes", 96 << 20), "cfg")
@@ -58,6 +62,10 @@ def test_points_fuzz_vs_oracle(forced, seed):
     frame = ds.DeviceFrame({k_: torch.from_numpy(v).cuda() for k_, v in cols.items() if k_ != "cat__ncat"},
                            categories={"cat": [f"c{i}" for i in range(ncat)]})
     picks = [SPECS[i] for i in rng.choice(len(SPECS), 8, replace=False)]
+    if seed % 4 == 2:        # every fourth seed: single-accumulator plans take the routed path (bin, then accumulate in shared memory)
+        ds.config.routed_min_rows, ds.config.l2_budget_bytes = 0, 1
+        ds.config.priv_count, ds.config.count16 = False, False
+        ds._lib.check(ds._lib.lib().dsb_routed_configure(0), "cfg")
     if seed % 4 == 3:        # every fourth seed: tiny L2 bands, so the mono / generic kernels run their BANDED forms
         ds._lib.check(ds._lib.lib().dsb_configure(b"l2_band_bytes", int(rng.choice([4096, 32768]))), "cfg")
     for spec in picks:
