@@ -7,7 +7,7 @@ C ABI (include/dsb200.h).  There is no CPU fallback.
 """
 from .core import Canvas, bypixel  # noqa: F401
 from . import config  # noqa: F401
-from .frame import DeviceFrame, HostFrame  # noqa: F401
+from .frame import DeviceFrame, HostFrame, RaggedColumn  # noqa: F401
 from .reductions import (any, by, category_binning, category_codes, category_modulo, count, count_cat,  # noqa: F401,A004
                          first, last, max, mean, min, sum, summary, where)
 from . import palette  # noqa: F401

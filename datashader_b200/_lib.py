@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdsb200.so")
 
 DSB_MAX_OPS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 NOTE_NEGZERO = 1
 
 # dsb_dtype
@@ -48,7 +48,10 @@ class Plan(C.Structure):
 
 class LineLayout(C.Structure):
     _fields_ = [("x_line_stride", C.c_int64), ("y_line_stride", C.c_int64), ("value_per_vertex", C.c_int32),
-                ("plot_start", C.c_int32)]
+                ("plot_start", C.c_int32),
+                # ragged layouts: start index per row of the flat vertex arrays (NULL x_starts = dense)
+                ("x_starts", C.c_void_p), ("y_starts", C.c_void_p), ("y1_starts", C.c_void_p),
+                ("x_flat_len", C.c_int64), ("y_flat_len", C.c_int64), ("y1_flat_len", C.c_int64)]
 
 
 class Dsb200Error(RuntimeError):

@@ -10,8 +10,8 @@ from numbers import Number
 import numpy as np
 
 from . import reductions as rd
-from .glyphs import (AreaGlyph, LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1XConstant, LinesAxis1YConstant, Point,
-                     _LineGlyph)
+from .glyphs import (AreaGlyph, LineAxis0, LineAxis0Multi, LinesAxis1, LinesAxis1Ragged, LinesAxis1XConstant,
+                     LinesAxis1YConstant, Point, _LineGlyph)
 
 
 class Axis:
@@ -166,7 +166,7 @@ See docstring for more information on valid usage""")
             elif isinstance(x, (list, tuple)) and isinstance(y, np.ndarray):
                 glyph = LinesAxis1YConstant(tuple(x), y)
             elif isinstance(x, (Number, str)) and isinstance(y, (Number, str)):
-                raise NotImplementedError("LinesAxis1Ragged is outside the B200 hot path")
+                glyph = LinesAxis1Ragged(x, y)
             else:
                 raise ValueError(f"""
 Invalid combination of x and y arguments to Canvas.line when axis=1.
@@ -233,7 +233,7 @@ See docstring for more information on valid usage""")
                 elif isinstance(x, seq) and isinstance(y, np.ndarray):
                     glyph = AreaGlyph(LinesAxis1YConstant(tuple(x), y))
                 elif isinstance(x, scalar) and isinstance(y, scalar):
-                    raise NotImplementedError("AreaToZeroAxis1Ragged is outside the B200 hot path")
+                    glyph = AreaGlyph(LinesAxis1Ragged(x, y))
                 else:
                     raise ValueError(f"""
 Invalid combination of x and y arguments to Canvas.area when axis=1.
@@ -249,7 +249,7 @@ See docstring for more information on valid usage""")
                 elif isinstance(x, seq) and isinstance(y, np.ndarray) and isinstance(y_stack, np.ndarray):
                     glyph = AreaGlyph(LinesAxis1YConstant(tuple(x), y), LinesAxis1YConstant(tuple(x), y_stack))
                 elif isinstance(x, scalar) and isinstance(y, scalar) and isinstance(y_stack, scalar):
-                    raise NotImplementedError("AreaToLineAxis1Ragged is outside the B200 hot path")
+                    glyph = AreaGlyph(LinesAxis1Ragged(x, y), LinesAxis1Ragged(x, y_stack))
                 else:
                     raise ValueError(f"""
 Invalid combination of x, y, and y_stack arguments to Canvas.area when axis=1.

@@ -16,6 +16,10 @@ struct AreaArgs {
   long long row_offset;
   long long xxmax, yymax;   // round(mapper(max) * s + t), map_onto_pixel_snap (line.py:714-715)
   long long xmaxi, ymaxi;   // map_onto_pixel(xmax, ymax) (area.py:1178-1180)
+  const long long* rg_x;    // ragged layouts (AreaToZeroAxis1Ragged / AreaToLineAxis1Ragged, area.py:1939-2083): first flat vertex
+  const long long* rg_y;    //   of every row in xs / ys0 / ys1; NULL = dense
+  const long long* rg_y1;
+  long long rg_xlen, rg_ylen, rg_y1len;
   dsb_plan plan;
 };
 
@@ -140,30 +144,54 @@ __device__ void draw_trapezoid_y(const AreaArgs& a, const AreaCtx& c, double x0,
   }
 }
 
-template <typename XY>
+template <typename XY, bool RG>
 __global__ void __launch_bounds__(128) k_areas(const AreaArgs a) {
   const XY* __restrict__ xs = (const XY*)a.xs;
   const XY* __restrict__ ys0 = (const XY*)a.ys0;
   const XY* __restrict__ ys1 = (const XY*)a.ys1;
   const long long nseg = a.nverts - 1;
-  const long long total = a.nlines * nseg;
+  const long long total = RG ? a.rg_xlen - a.rg_x[0] : a.nlines * nseg;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool to_line = ys1 != nullptr;
   // warp-uniform trip count + __syncwarp() per trapezoid: keeps the lanes together over the rounds (see k_lines_axis1)
   for (long long s0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); s0 < total; s0 += stride, __syncwarp()) {
     const long long s = s0 + (threadIdx.x & 31);
     if (s >= total) continue;
-    const long long i = s / nseg, j = s - i * nseg;
-    const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+    long long i, j, ox, oy, oy1;
+    if (!RG) {
+      i = s / nseg; j = s - i * nseg;
+      ox = i * a.x_line_stride + j; oy = oy1 = i * a.y_line_stride + j;
+    } else {
+      // perform_extend_area_to_{zero,line}_axis1_ragged, area.py:1959-2004, 2033-2081: the slots are the flat x vertices; the row
+      // is the last one that starts at or before the slot and it draws min(x, y0 (, y1) lengths) vertices
+      const long long p = a.rg_x[0] + s;
+      long long lo = 0, hi = a.nlines - 1;
+      while (lo < hi) { const long long mid = (lo + hi + 1) >> 1; if (a.rg_x[mid] <= p) lo = mid; else hi = mid - 1; }
+      const bool last = lo + 1 >= a.nlines;
+      const long long xb = a.rg_x[lo], yb = a.rg_y[lo];
+      long long nv = (last ? a.rg_xlen : a.rg_x[lo + 1]) - xb;
+      const long long yn = (last ? a.rg_ylen : a.rg_y[lo + 1]) - yb;
+      nv = nv < yn ? nv : yn;
+      long long y1b = 0;
+      if (to_line) {
+        y1b = a.rg_y1[lo];
+        const long long y1n = (last ? a.rg_y1len : a.rg_y1[lo + 1]) - y1b;
+        nv = nv < y1n ? nv : y1n;
+      }
+      i = lo; j = p - xb;
+      if (j + 1 >= nv) continue;
+      ox = p; oy = yb + j; oy1 = y1b + j;
+    }
     const double x0 = (double)xs[ox], x1 = (double)xs[ox + 1];
     const double y0 = (double)ys0[oy], y3 = (double)ys0[oy + 1];
-    const double y1 = to_line ? (double)ys1[oy] : 0.0, y2 = to_line ? (double)ys1[oy + 1] : 0.0;
+    const double y1 = to_line ? (double)ys1[oy1] : 0.0, y2 = to_line ? (double)ys1[oy1 + 1] : 0.0;
     bool trapezoid_start;
-    if (j == 0) trapezoid_start = a.plot_start != 0;
+    if (j == 0) trapezoid_start = RG ? true : a.plot_start != 0;
     else {
       const double xm = (double)xs[ox - 1], ym = (double)ys0[oy - 1];
       trapezoid_start = (xm != xm) || (ym != ym);
-      if (to_line) { const double ym1 = (double)ys1[oy - 1]; trapezoid_start = trapezoid_start || (ym1 != ym1); }
+      // the ragged to-line form tests `isnull(y1_flat[y1_start_i + j] - 1)` (area.py:2069): the CURRENT vertex of the second curve
+      if (to_line) { const double ym1 = RG ? y1 : (double)ys1[oy1 - 1]; trapezoid_start = trapezoid_start || (ym1 != ym1); }
     }
     AreaCtx c;
     c.plan = &a.plan; c.width = a.v.width;
@@ -195,7 +223,15 @@ extern "C" int dsb_areas_plan(const dsb_view* view, const void* xs, const void* 
   if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("dsb_areas_plan: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
   AreaArgs a;
   a.v = *view; a.xs = xs; a.ys0 = ys0; a.ys1 = ys1; a.nlines = nlines; a.nverts = nverts; a.row_offset = row_offset; a.plan = *plan;
-  if (layout) {
+  a.rg_x = a.rg_y = a.rg_y1 = nullptr; a.rg_xlen = a.rg_ylen = a.rg_y1len = 0;
+  if (layout && layout->x_starts) {
+    if (!layout->y_starts || (ys1 && !layout->y1_starts) || layout->x_flat_len < 0 || layout->y_flat_len < 0 || layout->y1_flat_len < 0) {
+      dsb_set_error("dsb_areas_plan: ragged layout needs the start indices and flat lengths of every vertex array"); return DSB_ERR_ARG;
+    }
+    a.rg_x = (const long long*)layout->x_starts; a.rg_y = (const long long*)layout->y_starts; a.rg_y1 = (const long long*)layout->y1_starts;
+    a.rg_xlen = layout->x_flat_len; a.rg_ylen = layout->y_flat_len; a.rg_y1len = layout->y1_flat_len;
+    a.x_line_stride = a.y_line_stride = 0; a.value_per_vertex = 0; a.plot_start = 1;
+  } else if (layout) {
     if (layout->x_line_stride < 0 || layout->y_line_stride < 0) { dsb_set_error("dsb_areas_plan: negative line stride"); return DSB_ERR_ARG; }
     a.x_line_stride = layout->x_line_stride; a.y_line_stride = layout->y_line_stride;
     a.value_per_vertex = layout->value_per_vertex; a.plot_start = layout->plot_start;
@@ -208,14 +244,16 @@ extern "C" int dsb_areas_plan(const dsb_view* view, const void* xs, const void* 
   long long xi = (long long)(mx * view->sx + view->tx), yi = (long long)(my * view->sy + view->ty);   // int() truncation
   a.xmaxi = (xi == a.xxmax) ? xi - 1 : xi;
   a.ymaxi = (yi == a.yymax) ? yi - 1 : yi;
-  const long long total = nlines * (nverts - 1);
+  const bool rg = a.rg_x != nullptr;
+  const long long total = rg ? a.rg_xlen : nlines * (nverts - 1);
+  if (total <= 0) return DSB_OK;
   const int threads = 128;
   long long want = (total + threads - 1) / threads, cap = (long long)dsb_num_sms() * 16;
   int grid = (int)(want < cap ? want : cap);
   cudaStream_t s = (cudaStream_t)stream;
-  dsb_note_kernel("k_areas<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
-  if (xy_dtype == DSB_F32) k_areas<float><<<grid, threads, 0, s>>>(a);
-  else k_areas<double><<<grid, threads, 0, s>>>(a);
+  dsb_note_kernel("k_areas<%s%s>", xy_dtype == DSB_F32 ? "f32" : "f64", rg ? ", ragged" : "");
+  if (xy_dtype == DSB_F32) { if (rg) k_areas<float, true><<<grid, threads, 0, s>>>(a); else k_areas<float, false><<<grid, threads, 0, s>>>(a); }
+  else { if (rg) k_areas<double, true><<<grid, threads, 0, s>>>(a); else k_areas<double, false><<<grid, threads, 0, s>>>(a); }
   DSB_CUDA_CHECK_LAUNCH("dsb_areas_plan");
   return DSB_OK;
 }

@@ -34,8 +34,40 @@ struct LineArgs {
   int plot_start;           // axis=0: whether vertex 0 starts a line (False for a continued dask partition)
   const void* cat;          // antialiased by(): category code per line / vertex row, canvases are [H, W, ncat]
   int cat_dtype, ncat;
+  const long long* rg_x;    // ragged layouts (LinesAxis1Ragged): first flat vertex of every row in xs / ys; NULL = dense
+  const long long* rg_y;
+  long long rg_xlen, rg_ylen;
   dsb_plan plan;
 };
+
+// Which (row i, vertex j) a work slot is, where its vertices live and how many vertices the row has.  Dense layouts: slot t of
+// the rows [i0, i0 + nl) is segment t % (nverts - 1) of row i0 + t / (nverts - 1).  Ragged layouts (extend_cpu_numba,
+// line.py:1559-1600): the slots are the flat x vertices of those rows; the row is found by bisection of the start indices, it
+// draws min(x length, y length) vertices and a slot past its last segment is idle.
+struct SegLoc { long long i, j, ox, oy, nv; };
+
+template <bool RG>
+__device__ __forceinline__ long long seg_slots(const LineArgs& a, long long i0, long long nl) {
+  if (!RG) return nl * (a.nverts - 1);
+  return (i0 + nl < a.nlines ? a.rg_x[i0 + nl] : a.rg_xlen) - a.rg_x[i0];
+}
+
+template <bool RG>
+__device__ __forceinline__ bool seg_locate(const LineArgs& a, long long i0, long long nl, long long t, SegLoc& q) {
+  if (!RG) {
+    const long long nseg = a.nverts - 1, g = t / nseg;
+    q.i = i0 + g; q.j = t - g * nseg; q.nv = a.nverts;
+    q.ox = q.i * a.x_line_stride + q.j; q.oy = q.i * a.y_line_stride + q.j;
+    return true;
+  }
+  const long long p = a.rg_x[i0] + t;
+  long long lo = i0, hi = i0 + nl - 1;                    // the last row that starts at or before p (empty rows sort before it)
+  while (lo < hi) { const long long mid = (lo + hi + 1) >> 1; if (a.rg_x[mid] <= p) lo = mid; else hi = mid - 1; }
+  const long long x0 = a.rg_x[lo], y0 = a.rg_y[lo];
+  const long long xn = (lo + 1 < a.nlines ? a.rg_x[lo + 1] : a.rg_xlen) - x0, yn = (lo + 1 < a.nlines ? a.rg_y[lo + 1] : a.rg_ylen) - y0;
+  q.i = lo; q.j = p - x0; q.nv = xn < yn ? xn : yn; q.ox = p; q.oy = y0 + q.j;
+  return q.j + 1 < q.nv;
+}
 
 __device__ __forceinline__ double fmul64(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double fadd64(double a, double b) { return __dadd_rn(a, b); }
@@ -595,15 +627,14 @@ __device__ __forceinline__ bool aa_clip_map(const LineArgs& a, bool& segment_sta
   return true;
 }
 
-template <typename XY>
+template <typename XY, bool RG>
 __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) {
   __shared__ AaSeg segs[128];
   __shared__ int prefix[128];
   const AaConst kaa = aa_const(a.line_width);
   const XY* __restrict__ xs = (const XY*)a.xs;
   const XY* __restrict__ ys = (const XY*)a.ys;
-  const long long nseg = a.nverts - 1;
-  const long long total = a.nlines * nseg;
+  const long long total = seg_slots<RG>(a, 0, a.nlines);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
   AaSeg* const wseg = segs + w0;
@@ -613,9 +644,9 @@ __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) 
     const long long s = s0 + lane;
     AaSeg& g = wseg[lane];
     g.nrows = 0;
-    if (s < total) {
-      const long long i = s / nseg, j = s - i * nseg;
-      const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+    SegLoc q;
+    if (s < total && seg_locate<RG>(a, 0, a.nlines, s, q)) {
+      const long long i = q.i, j = q.j, ox = q.ox, oy = q.oy;
       double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
       bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
       double xm = 0.0, ym = 0.0;
@@ -624,7 +655,7 @@ __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) 
         segment_start = (xm != xm) || (ym != ym);
         if (segment_start) { xm = 0.0; ym = 0.0; }
       }
-      bool segment_end = (j == a.nverts - 2);
+      bool segment_end = (j == q.nv - 2);
       if (!segment_end) {
         const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
         segment_end = (xn != xn) || (yn != yn);
@@ -694,20 +725,26 @@ __global__ void __launch_bounds__(128, 8) k_lines_aa_balanced(const LineArgs a) 
 }
 
 // one thread per (line, segment): extend_cuda, line.py:1321-1332 + perform_extend_line :1250-1275
-template <typename XY, bool AA>
+template <typename XY, bool AA, bool RG>
 __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
   const XY* __restrict__ xs = (const XY*)a.xs;
   const XY* __restrict__ ys = (const XY*)a.ys;
-  const long long nseg = a.nverts - 1;
-  const long long total = a.nlines * nseg;
+  const long long total = seg_slots<RG>(a, 0, a.nlines);
   const long long stride = (long long)gridDim.x * blockDim.x;
   // warp-uniform trip count + __syncwarp() per segment: the pixel loops of the 32 segments differ in length, and without a
   // reconvergence point per round the lanes drift apart over the rounds (ncu: 6.8 active lanes, profiles/r02_lines_aa.md)
   for (long long s0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); s0 < total; s0 += stride, __syncwarp()) {
     const long long s = s0 + (threadIdx.x & 31);
     if (s >= total) continue;
-    const long long i = s / nseg, j = s - i * nseg;
-    const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+    long long i, j, ox, oy, nv;
+    if (!RG) {
+      const long long nseg = a.nverts - 1;
+      i = s / nseg; j = s - i * nseg; ox = i * a.x_line_stride + j; oy = i * a.y_line_stride + j; nv = a.nverts;
+    } else {
+      SegLoc q;
+      if (!seg_locate<true>(a, 0, a.nlines, s, q)) continue;
+      i = q.i; j = q.j; ox = q.ox; oy = q.oy; nv = q.nv;
+    }
     const double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
     bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
     double xm = 0.0, ym = 0.0;
@@ -716,7 +753,7 @@ __global__ void __launch_bounds__(128) k_lines_axis1(const LineArgs a) {
       segment_start = (xm != xm) || (ym != ym);
       if (segment_start) { xm = 0.0; ym = 0.0; }
     }
-    bool segment_end = (j == a.nverts - 2);
+    bool segment_end = (j == nv - 2);
     if (!segment_end) {
       const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
       segment_end = (xn != xn) || (yn != yn);
@@ -846,7 +883,7 @@ __device__ __forceinline__ void aa2_stage2(const Aa2Args& b, uint32_t cell, long
 // at a time (G = 1 for long lines; short lines are batched so that all threads have a segment) and flushes the table
 // after each group.  Groups that fill more than 3/4 of the table are queued in b.redo and handled, line by line, by a
 // second launch with HASH = false, whose stage 1 is the CTA's private full-size global canvas.
-template <typename XY, bool HASH>
+template <typename XY, bool HASH, bool RG>
 __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, const Aa2Args b, const int G) {
   extern __shared__ long long aa2_smem[];
   __shared__ unsigned int s_touched;
@@ -862,7 +899,6 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
   __shared__ int s_bbox[2];
   __shared__ int s_skip;
   __shared__ int s_prefix[AA2_THREADS];
-  const long long nseg = a.nverts - 1;
   const long long nwork = HASH ? (a.nlines + G - 1) / G : (long long)*b.redo_n;
   if (HASH) {
     for (int k = threadIdx.x; k < AA2_HASH_CAP; k += blockDim.x) { hkeys[k] = 0xffffffffu; hvals[k] = LLONG_MIN; }
@@ -886,26 +922,27 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
     }
     int bbox[2] = {INT_MAX, -1};
     int tn = 0;
+    const long long nslots = seg_slots<RG>(a, i0, glines);
     if (!HASH) {
       // global stage-1 path (long lines): the rows of the warp's 32 segments are handed out evenly, as in k_lines_aa_balanced
       const AaConst kaa = aa_const(a.line_width);
       AaSeg* const wseg = (AaSeg*)aa2_smem + (threadIdx.x & ~31);
       int* const wpre = s_prefix + (threadIdx.x & ~31);
       const int lane = threadIdx.x & 31;
-      for (long long t0 = threadIdx.x & ~31; t0 < glines * nseg; t0 += blockDim.x) {
+      for (long long t0 = threadIdx.x & ~31; t0 < nslots; t0 += blockDim.x) {
         const long long t = t0 + lane;
         AaSeg& g = wseg[lane];
         g.nrows = 0;
-        if (t < glines * nseg) {
-          const long long gl = t / nseg, j = t - gl * nseg, i = i0 + gl;
-          const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+        SegLoc q;
+        if (t < nslots && seg_locate<RG>(a, i0, glines, t, q)) {
+          const long long i = q.i, j = q.j, ox = q.ox, oy = q.oy;
           double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
           bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
           if (j > 0) {
             const double xm = (double)xs[ox - 1], ym = (double)ys[oy - 1];
             segment_start = (xm != xm) || (ym != ym);
           }
-          bool segment_end = (j == a.nverts - 2);
+          bool segment_end = (j == q.nv - 2);
           if (!segment_end) {
             const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
             segment_end = (xn != xn) || (yn != yn);
@@ -965,16 +1002,17 @@ __global__ void __launch_bounds__(AA2_THREADS, 1) k_lines_aa2(const LineArgs a, 
         }
       }
     } else
-    for (long long t = threadIdx.x; t < glines * nseg; t += blockDim.x) {
-      const long long g = t / nseg, j = t - g * nseg, i = i0 + g;
-      const long long ox = i * a.x_line_stride + j, oy = i * a.y_line_stride + j;
+    for (long long t = threadIdx.x; t < nslots; t += blockDim.x) {
+      SegLoc q;
+      if (!seg_locate<RG>(a, i0, glines, t, q)) continue;
+      const long long i = q.i, j = q.j, ox = q.ox, oy = q.oy, g = i - i0;
       const double x0 = (double)xs[ox], y0 = (double)ys[oy], x1 = (double)xs[ox + 1], y1 = (double)ys[oy + 1];
       bool segment_start = (j == 0) ? (a.plot_start != 0) : false;
       if (j > 0) {
         const double xm = (double)xs[ox - 1], ym = (double)ys[oy - 1];
         segment_start = (xm != xm) || (ym != ym);
       }
-      bool segment_end = (j == a.nverts - 2);
+      bool segment_end = (j == q.nv - 2);
       if (!segment_end) {
         const double xn = (double)xs[ox + 2], yn = (double)ys[oy + 2];
         segment_end = (xn != xn) || (yn != yn);
@@ -1067,21 +1105,30 @@ static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char*
   a.yymax = py_round(my * view->sy + view->ty);
   a.nx = py_round((view->xmax - view->xmin) * view->sx);
   a.ny = py_round((view->ymax - view->ymin) * view->sy);
-  const long long total = a.nlines * (a.nverts - 1);
+  const bool rg = a.rg_x != nullptr;
+  const long long total = rg ? a.rg_xlen : a.nlines * (a.nverts - 1);
+  if (total <= 0) return DSB_OK;
   const int threads = 128;
   long long want = (total + threads - 1) / threads;
   long long cap = (long long)dsb_num_sms() * 16;
   int grid = (int)(want < cap ? want : cap);
   cudaStream_t s = (cudaStream_t)stream;
   const bool balanced = g_lines_balanced && a.line_width > 0.0 && !a.use_plan;
-  dsb_note_kernel(balanced ? "k_lines_aa_balanced<%s>" : "k_lines_axis1<%s>", xy_dtype == DSB_F32 ? "f32" : "f64");
-  if (balanced && xy_dtype == DSB_F32) k_lines_aa_balanced<float><<<grid, threads, 0, s>>>(a);
-  else if (balanced && xy_dtype == DSB_F64) k_lines_aa_balanced<double><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F32 && a.line_width > 0.0) k_lines_axis1<float, true><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F32) k_lines_axis1<float, false><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F64 && a.line_width > 0.0) k_lines_axis1<double, true><<<grid, threads, 0, s>>>(a);
-  else if (xy_dtype == DSB_F64) k_lines_axis1<double, false><<<grid, threads, 0, s>>>(a);
-  else { dsb_set_error("%s: xy_dtype must be f32 or f64", what); return DSB_ERR_ARG; }
+  if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("%s: xy_dtype must be f32 or f64", what); return DSB_ERR_ARG; }
+  dsb_note_kernel(balanced ? "k_lines_aa_balanced<%s%s>" : "k_lines_axis1<%s%s>", xy_dtype == DSB_F32 ? "f32" : "f64",
+                  rg ? ", ragged" : "");
+  const bool f32 = xy_dtype == DSB_F32, aa = a.line_width > 0.0;
+#define DSB_LINES_GO(RG)                                                                              \
+  do {                                                                                                \
+    if (balanced && f32) k_lines_aa_balanced<float, RG><<<grid, threads, 0, s>>>(a);                  \
+    else if (balanced) k_lines_aa_balanced<double, RG><<<grid, threads, 0, s>>>(a);                   \
+    else if (f32 && aa) k_lines_axis1<float, true, RG><<<grid, threads, 0, s>>>(a);                   \
+    else if (f32) k_lines_axis1<float, false, RG><<<grid, threads, 0, s>>>(a);                        \
+    else if (aa) k_lines_axis1<double, true, RG><<<grid, threads, 0, s>>>(a);                         \
+    else k_lines_axis1<double, false, RG><<<grid, threads, 0, s>>>(a);                                \
+  } while (0)
+  if (rg) DSB_LINES_GO(true); else DSB_LINES_GO(false);
+#undef DSB_LINES_GO
   DSB_CUDA_CHECK_LAUNCH(what);
   return DSB_OK;
 }
@@ -1089,8 +1136,16 @@ static int launch_lines(LineArgs& a, int32_t xy_dtype, void* stream, const char*
 // Bresenham lines with a full accumulator plan: any reduction Canvas.points supports, applied to every pixel a
 // line touches, with i = the line's row (the reference passes the row index i to append, line.py:1046-1097).
 static int apply_layout(LineArgs& a, const dsb_line_layout* L, const char* what) {
+  a.rg_x = a.rg_y = nullptr; a.rg_xlen = a.rg_ylen = 0;
   if (!L) {   // LinesAxis1 default: dense [nlines, nverts]
     a.x_line_stride = a.nverts; a.y_line_stride = a.nverts; a.value_per_vertex = 0; a.plot_start = 1;
+    return DSB_OK;
+  }
+  if (L->x_starts) {   // LinesAxis1Ragged: flat vertex arrays + a start index per row
+    if (!L->y_starts || L->x_flat_len < 0 || L->y_flat_len < 0) { dsb_set_error("%s: ragged layout needs y_starts and the flat lengths", what); return DSB_ERR_ARG; }
+    a.rg_x = (const long long*)L->x_starts; a.rg_y = (const long long*)L->y_starts;
+    a.rg_xlen = L->x_flat_len; a.rg_ylen = L->y_flat_len;
+    a.x_line_stride = a.y_line_stride = 0; a.value_per_vertex = 0; a.plot_start = 1;
     return DSB_OK;
   }
   if (L->x_line_stride < 0 || L->y_line_stride < 0) { dsb_set_error("%s: negative line stride", what); return DSB_ERR_ARG; }
@@ -1213,25 +1268,26 @@ extern "C" int dsb_lines_aa2(const dsb_view* view, const void* xs, const void* y
   k_fill_i64<<<dsb_num_sms() * 8, 256, 0, s>>>(b.temp, LLONG_MIN, nctas * ncell);
   const size_t smem = (size_t)AA2_HASH_CAP * 12;
   // short lines are batched G to a group so that every thread of the CTA has a segment (at most 32 lines per group)
-  long long G = AA2_THREADS / (nverts - 1);
+  const bool rg = a.rg_x != nullptr;
+  long long segs_per_line = rg ? a.rg_xlen / nlines : nverts - 1;       // ragged: the average row
+  long long G = AA2_THREADS / (segs_per_line < 1 ? 1 : segs_per_line);
   G = G < 1 ? 1 : (G > 32 ? 32 : G);
   const bool use_hash = ncell < (1LL << AA2_CELL_BITS) - 1;
   if (!use_hash) G = 1;
   long long hgrid = (long long)dsb_num_sms();
   if (hgrid > (nlines + G - 1) / G) hgrid = (nlines + G - 1) / G;
-  if (xy_dtype == DSB_F32) {
-    cudaFuncSetAttribute(k_lines_aa2<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (use_hash) k_lines_aa2<float, true><<<(int)hgrid, AA2_THREADS, smem, s>>>(a, b, (int)G);
-    else k_aa2_queue_all<<<dsb_num_sms(), 256, 0, s>>>(b.redo_n, b.redo, (unsigned int)nlines);
-    cudaFuncSetAttribute(k_lines_aa2<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AA2_THREADS * sizeof(AaSeg)));
-    k_lines_aa2<float, false><<<(int)nctas, AA2_THREADS, AA2_THREADS * sizeof(AaSeg), s>>>(a, b, 1);
-  } else if (xy_dtype == DSB_F64) {
-    cudaFuncSetAttribute(k_lines_aa2<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (use_hash) k_lines_aa2<double, true><<<(int)hgrid, AA2_THREADS, smem, s>>>(a, b, (int)G);
-    else k_aa2_queue_all<<<dsb_num_sms(), 256, 0, s>>>(b.redo_n, b.redo, (unsigned int)nlines);
-    cudaFuncSetAttribute(k_lines_aa2<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AA2_THREADS * sizeof(AaSeg)));
-    k_lines_aa2<double, false><<<(int)nctas, AA2_THREADS, AA2_THREADS * sizeof(AaSeg), s>>>(a, b, 1);
-  } else { dsb_set_error("dsb_lines_aa2: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+  if (xy_dtype != DSB_F32 && xy_dtype != DSB_F64) { dsb_set_error("dsb_lines_aa2: xy_dtype must be f32 or f64"); return DSB_ERR_ARG; }
+#define DSB_AA2_GO(XY, RG)                                                                                                          \
+  do {                                                                                                                              \
+    cudaFuncSetAttribute(k_lines_aa2<XY, true, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    if (use_hash) k_lines_aa2<XY, true, RG><<<(int)hgrid, AA2_THREADS, smem, s>>>(a, b, (int)G);                                    \
+    else k_aa2_queue_all<<<dsb_num_sms(), 256, 0, s>>>(b.redo_n, b.redo, (unsigned int)nlines);                                     \
+    cudaFuncSetAttribute(k_lines_aa2<XY, false, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AA2_THREADS * sizeof(AaSeg))); \
+    k_lines_aa2<XY, false, RG><<<(int)nctas, AA2_THREADS, AA2_THREADS * sizeof(AaSeg), s>>>(a, b, 1);                               \
+  } while (0)
+  if (xy_dtype == DSB_F32) { if (rg) DSB_AA2_GO(float, true); else DSB_AA2_GO(float, false); }
+  else { if (rg) DSB_AA2_GO(double, true); else DSB_AA2_GO(double, false); }
+#undef DSB_AA2_GO
   DSB_CUDA_CHECK_LAUNCH("dsb_lines_aa2");
   return DSB_OK;
 }

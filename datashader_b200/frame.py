@@ -90,6 +90,50 @@ def _to_tensor(arr: np.ndarray, device, pin=False, stream=None):
     return t.to(device, non_blocking=True)
 
 
+class RaggedColumn:
+    """A column of variable-length rows: `flat` holds every row's values back to back, `starts[i]` (int64) is the first
+    element of row i - the storage of a RaggedArray (datatypes.py: flat_array / start_indices), which is what the ragged
+    line and area glyphs read (line.py:1545-1552, area.py:1945-1952).  Host tensors inside a HostFrame, CUDA tensors inside
+    a DeviceFrame."""
+
+    def __init__(self, flat, starts):
+        self.flat, self.starts = flat.contiguous(), starts.to(torch.int64).contiguous()
+
+    @classmethod
+    def from_array(cls, arr):
+        """anything with flat_array / start_indices (this package's RaggedArray or the reference's)."""
+        flat = np.ascontiguousarray(arr.flat_array)
+        starts = np.ascontiguousarray(arr.start_indices).astype(np.int64)
+        if flat.dtype not in _TORCH_OK:
+            flat = flat.astype(np.float64)
+        if len(starts) and (np.any(np.diff(starts) < 0) or starts[0] < 0 or starts[-1] > len(flat)):
+            raise ValueError("start_indices must be non-decreasing and inside flat_array")
+        return cls(_from_numpy(flat), _from_numpy(starts))
+
+    @property
+    def shape(self):
+        return (int(self.starts.shape[0]),)
+
+    @property
+    def dtype(self):
+        return self.flat.dtype
+
+    @property
+    def is_cuda(self):
+        return self.flat.is_cuda
+
+    @property
+    def device(self):
+        return self.flat.device
+
+    def contiguous(self):
+        return self
+
+
+def _is_ragged_array(a):
+    return hasattr(a, "flat_array") and hasattr(a, "start_indices")
+
+
 class DeviceFrame:
     """Device-resident columns for Canvas.points / Canvas.line.
 
@@ -101,7 +145,10 @@ class DeviceFrame:
     def __init__(self, columns, categories=None, row_offset=0, n_global=None):
         self.columns = {}
         for name, t in dict(columns).items():
-            if not isinstance(t, torch.Tensor):
+            if _is_ragged_array(t):
+                t = RaggedColumn.from_array(t)
+                t = RaggedColumn(t.flat.cuda(), t.starts.cuda())
+            if not isinstance(t, (torch.Tensor, RaggedColumn)):
                 # cupy / numba / cudf-column style device arrays (__cuda_array_interface__, DLPack): borrowed, not copied
                 t = torch.as_tensor(t, device="cuda")
             if not t.is_cuda:
@@ -142,6 +189,9 @@ class DeviceFrame:
             if isinstance(s.dtype, pd.CategoricalDtype):
                 cats[name] = list(s.cat.categories)
                 cols[name] = _to_tensor(np.asarray(s.cat.codes.values), device, pin)
+            elif _is_ragged_array(s.array):
+                r = RaggedColumn.from_array(s.array)
+                cols[name] = RaggedColumn(r.flat.to(device), r.starts.to(device))
             else:
                 cols[name] = _to_tensor(s.to_numpy(), device, pin)
         return cls(cols, cats, row_offset)
@@ -151,6 +201,8 @@ class DeviceFrame:
         for name, t in self.columns.items():
             if name in self.categories:
                 out[name] = ("categorical", list(self.categories[name]))
+            elif isinstance(t, RaggedColumn):
+                out[name] = ("ragged", None)
             else:
                 out[name] = ("float" if t.dtype.is_floating_point else "int", None)
         return out
@@ -181,7 +233,13 @@ class HostFrame:
     def __init__(self, columns, categories=None, row_offset=0, device=None):
         self.columns = {}
         for name, a in columns.items():
-            if isinstance(a, torch.Tensor):
+            if _is_ragged_array(a):
+                a = RaggedColumn.from_array(a)
+            if isinstance(a, RaggedColumn):
+                if a.is_cuda:
+                    raise ValueError("HostFrame columns must live on the host; use DeviceFrame")
+                self.columns[name] = a
+            elif isinstance(a, torch.Tensor):
                 if a.is_cuda:
                     raise ValueError("HostFrame columns must live on the host; use DeviceFrame")
                 self.columns[name] = a.contiguous()
@@ -217,6 +275,8 @@ class HostFrame:
             if isinstance(s.dtype, pd.CategoricalDtype):
                 cats[name] = list(s.cat.categories)
                 cols[name] = np.asarray(s.cat.codes.values)
+            elif _is_ragged_array(s.array):
+                cols[name] = RaggedColumn.from_array(s.array)
             else:
                 cols[name] = s.to_numpy()
         off = getattr(df, "_datashader_row_offset", 0)
@@ -265,6 +325,8 @@ class HostFrame:
         for name, t in self.columns.items():
             if name in self.categories:
                 out[name] = ("categorical", list(self.categories[name]))
+            elif isinstance(t, RaggedColumn):
+                out[name] = ("ragged", None)
             else:
                 out[name] = ("float" if t.dtype.is_floating_point else "int", None)
         return out
@@ -273,17 +335,21 @@ class HostFrame:
         return np.dtype(str(self.columns[name].dtype).replace("torch.", ""))
 
     def n_chunks(self):
+        if any(isinstance(t, RaggedColumn) for t in self.columns.values()):
+            return 1          # ragged rows are staged whole (lines and areas take the resident frame)
         return max(1, -(-self._len // self.CHUNK_ROWS))
 
     def resident(self, needed):
         """The whole frame on the device (single-chunk sources and gathers)."""
         stream = torch.cuda.current_stream(self.device)
         cols = {}
-        for c in needed:
-            src = self.columns[c]
+        def up(src):
             dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
             _h2d(dst, src, stream)
-            cols[c] = dst
+            return dst
+        for c in needed:
+            src = self.columns[c]
+            cols[c] = RaggedColumn(up(src.flat), up(src.starts)) if isinstance(src, RaggedColumn) else up(src)
         return DeviceFrame(cols, self.categories, self.row_offset)
 
     def chunks(self, needed):

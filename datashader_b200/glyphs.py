@@ -80,6 +80,7 @@ class _LineGlyph(Glyph):
     """Common host side of the line layouts: every layout is presented to the kernel as vertex vectors
     `xs, ys` of shape [nlines, nverts] (or one shared [nverts] vector), plus a dsb_line_layout."""
     antialiased = False
+    ragged = False
     _line_width = 0
     x_label = "x"
     y_label = "y"
@@ -243,6 +244,46 @@ class LinesAxis1YConstant(LinesAxis1):
         return xs, ys.reshape(1, -1).contiguous(), (xs.shape[1], 0)
 
 
+class LinesAxis1Ragged(_LineGlyph):
+    """One line per row, the row's vertices held by two RaggedArray columns (glyphs/line.py:457-523; extend :1538-1600).
+    The kernels read the flat arrays in place: `vertices` returns them as [1, flat length] and `ragged_starts` the start
+    index of every row (dsb_line_layout.x_starts / y_starts)."""
+    ragged = True
+
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    @property
+    def x_label(self):
+        return self.x
+
+    @property
+    def y_label(self):
+        return self.y
+
+    def required_columns(self):
+        return [self.x, self.y]
+
+    def validate(self, schema):
+        if schema[str(self.x)][0] != "ragged":
+            raise ValueError('x must be a RaggedArray')
+        elif schema[str(self.y)][0] != "ragged":
+            raise ValueError('y must be a RaggedArray')
+
+    def _x_tensors(self, frame):
+        return [frame[self.x].flat]
+
+    def _y_tensors(self, frame):
+        return [frame[self.y].flat]
+
+    def vertices(self, frame):
+        xs, ys = _to_float_matrix([frame[self.x].flat]), _to_float_matrix([frame[self.y].flat])
+        return xs, ys, (0, 0)
+
+    def ragged_starts(self, frame):
+        return [frame[self.x].starts, frame[self.y].starts]
+
+
 class AreaGlyph(Glyph):
     """Filled area between the curve of `line` and y = 0 (stack is None) or the curve of `stack`
     (glyphs/area.py:60-900: AreaToZero* / AreaToLine* for the axis0, axis0-multi, axis1 and constant-x/y layouts).
@@ -282,6 +323,16 @@ class AreaGlyph(Glyph):
 
     def y_bounds_include_zero(self):
         return self.stack is None      # area.py:71-79
+
+    @property
+    def ragged(self):
+        return getattr(self.line, "ragged", False)
+
+    def ragged_starts(self, frame):
+        st = self.line.ragged_starts(frame)
+        if self.stack is not None:
+            st = st + [self.stack.ragged_starts(frame)[1]]
+        return st
 
     def vertices(self, frame):
         xs, ys0, (xls, yls) = self.line.vertices(frame)

@@ -499,7 +499,21 @@ def _line_setup(frame, canvas, glyph, dist):
     xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
     nlines, nverts = int(max(xs.shape[0], ys.shape[0])), int(xs.shape[1])
     layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), int(getattr(frame, "plot_start", True)))
+    if glyph.ragged:
+        nlines, nverts = _ragged_layout(layout, glyph.ragged_starts(frame), [xs, ys]), 2
     return x_range, y_range, view, x_st, y_st, (xs, ys, xy_dtype, nlines, nverts, layout)
+
+
+def _ragged_layout(layout, starts, flats):
+    """Fill the ragged half of a dsb_line_layout: a start index per row for every flat vertex array (x, y[, y stack])."""
+    names = ("x", "y", "y1")
+    for name, st, flat in zip(names, starts, flats):
+        setattr(layout, name + "_starts", st.data_ptr())
+        setattr(layout, name + "_flat_len", int(flat.numel()))
+    if len({int(st.shape[0]) for st in starts}) != 1:
+        raise ValueError("ragged columns must have the same number of rows")
+    layout._keep = list(starts)          # ctypes holds the addresses only
+    return int(starts[0].shape[0])
 
 
 def lines(source, canvas, glyph, agg, antialias=False, dist=None):
@@ -931,6 +945,8 @@ def areas(source, canvas, glyph, agg, dist=None):
         xy_dtype = _lib.F32 if xs.dtype == torch.float32 else _lib.F64
         nlines, nverts = int(max(xs.shape[0], ys0.shape[0])), int(xs.shape[1])
         layout = _lib.LineLayout(int(xls), int(yls), int(glyph.value_per_vertex), int(getattr(frame, "plot_start", True)))
+        if glyph.ragged:
+            nlines, nverts = _ragged_layout(layout, glyph.ragged_starts(frame), [xs, ys0] + ([ys1] if ys1 is not None else [])), 2
         reds, results, labels = _accumulate_and_finalize(
             frame, frame, needed, schema, view, canvas, glyph, agg, dist, _launch_areas,
             ctx_extra={"area_vertices": (xs, ys0, ys1, xy_dtype, nlines, nverts, layout)})

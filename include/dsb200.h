@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define DSB_ABI_VERSION 2
+#define DSB_ABI_VERSION 3
 #define DSB_MAX_OPS 8
 
 typedef enum {
@@ -194,11 +194,21 @@ typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_
  * line.  x_line_stride / y_line_stride = elements between consecutive lines (0 = one vertex vector shared by all
  * lines: LinesAxis1XConstant / YConstant, line.py:1340-1535).  value_per_vertex = 1 for the axis=0 layouts
  * (LineAxis0, LineAxis0Multi, line.py:1099-1242): value / category / row index are those of the segment's first
- * vertex.  plot_start: whether vertex 0 starts a line (line.py:1112-1113). */
+ * vertex.  plot_start: whether vertex 0 starts a line (line.py:1112-1113).
+ * Ragged layouts (LinesAxis1Ragged, line.py:457-523 + 1538-1600; AreaToZeroAxis1Ragged / AreaToLineAxis1Ragged,
+ * area.py:1939-2083; the columns are datatypes.py RaggedArrays): x_starts != NULL.  xs / ys (/ ys1 of dsb_areas_plan) are
+ * then the FLAT vertex arrays of x_flat_len / y_flat_len / y1_flat_len elements and row i owns the vertices
+ * [starts[i], starts[i + 1]) of each (the last row up to the flat length); starts are int64 device arrays of nlines
+ * non-decreasing entries.  A row draws min(its x, y (, y1) lengths) vertices; value / category / row index are per row.
+ * The strides, value_per_vertex and nverts are ignored (pass nverts >= 2). */
 typedef struct {
   int64_t x_line_stride, y_line_stride;
   int32_t value_per_vertex;
   int32_t plot_start;
+  const int64_t* x_starts;
+  const int64_t* y_starts;
+  const int64_t* y1_starts;
+  int64_t x_flat_len, y_flat_len, y1_flat_len;
 } dsb_line_layout;
 
 /* LinesAxis1 (glyphs/line.py:1244-1337): xs, ys are [nlines, nverts] row-major of xy_dtype, `val`

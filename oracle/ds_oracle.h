@@ -107,6 +107,10 @@ void ora_lines(const ora_view* v, const void* xs, const void* ys, int32_t xy_dty
 void ora_areas(const ora_view* v, const void* xs, const void* ys0, const void* ys1, int32_t xy_dtype, int64_t nlines,
                int64_t nverts, int64_t x_line_stride, int64_t y_line_stride, int32_t value_per_vertex, const void* val,
                int32_t val_dtype, int32_t agg_op, void* agg);
+/* ragged area layouts (area.py:1939-2083): flat vertex arrays + int64 start index per row; ys1 == NULL: to zero */
+void ora_areas_ragged(const ora_view* v, const void* xs, const int64_t* x_starts, int64_t x_len, const void* ys0,
+                      const int64_t* y0_starts, int64_t y0_len, const void* ys1, const int64_t* y1_starts, int64_t y1_len,
+                      int32_t xy_dtype, int64_t nrows, const void* val, int32_t val_dtype, int32_t agg_op, void* agg);
 
 /* Antialiased lines whose reduction needs the 2-stage combine (compiler.py:198-268): combo = ORA_SUM / ORA_COUNT
  * (self_intersect=False; f64 / f32 canvas), ORA_MIN, ORA_FIRST, ORA_LAST (f64).  agg must be NaN-initialised. */

@@ -447,6 +447,38 @@ void ora_areas(const ora_view* v, const void* xs, const void* ys0, const void* y
   }
 }
 
+/* AreaToZeroAxis1Ragged / AreaToLineAxis1Ragged (perform_extend_area_to_zero_axis1_ragged, area.py:1959-2004;
+ * perform_extend_area_to_line_axis1_ragged, :2033-2081): flat vertex arrays + a start index per row; a row draws the shortest of
+ * its x / y0 (/ y1) lengths; append() receives the row.  ys1 == NULL: to zero.  The to-line form tests
+ * `isnull(y1_flat[y1_start_i + j] - 1)` (:2069) - the CURRENT vertex of the second curve, not the previous one. */
+void ora_areas_ragged(const ora_view* v, const void* xs, const int64_t* x_starts, int64_t x_len, const void* ys0,
+                      const int64_t* y0_starts, int64_t y0_len, const void* ys1, const int64_t* y1_starts, int64_t y1_len,
+                      int32_t xy_dtype, int64_t nrows, const void* val, int32_t val_dtype, int32_t agg_op, void* agg) {
+  line_ctx c;
+  c.agg_op = agg_op; c.antialias = 0; c.has_field = val_dtype != ORA_NONE; c.width = v->width; c.agg = agg; c.field = 0.0;
+  const int to_line = ys1 != NULL;
+  for (int64_t i = 0; i < nrows; i++) {
+    const int64_t xb = x_starts[i], xe = i < nrows - 1 ? x_starts[i + 1] : x_len;
+    const int64_t yb = y0_starts[i], ye = i < nrows - 1 ? y0_starts[i + 1] : y0_len;
+    int64_t n = xe - xb < ye - yb ? xe - xb : ye - yb, sb = 0;
+    if (to_line) {
+      sb = y1_starts[i];
+      const int64_t se = i < nrows - 1 ? y1_starts[i + 1] : y1_len;
+      if (se - sb < n) n = se - sb;
+    }
+    if (c.has_field) c.field = ldxy(val, val_dtype, i);
+    for (int64_t j = 0; j + 1 < n; j++) {
+      double x0 = ldxy(xs, xy_dtype, xb + j), x1 = ldxy(xs, xy_dtype, xb + j + 1);
+      double y0 = ldxy(ys0, xy_dtype, yb + j), y3 = ldxy(ys0, xy_dtype, yb + j + 1);
+      double y1 = to_line ? ldxy(ys1, xy_dtype, sb + j) : 0.0, y2 = to_line ? ldxy(ys1, xy_dtype, sb + j + 1) : 0.0;
+      int trapezoid_start = (j == 0) || isnan(ldxy(xs, xy_dtype, xb + j - 1)) || isnan(ldxy(ys0, xy_dtype, yb + j - 1)) ||
+                            (to_line && isnan(y1));
+      draw_trapezoid_y(v, &c, x0, x1, y0, y1, y2, y3, trapezoid_start, to_line, xy_dtype == ORA_F32,
+                       to_line && xy_dtype == ORA_F32);
+    }
+  }
+}
+
 /* ---- 2-stage antialiased lines (compiler.py:198-268; line.py:1291-1319 and its per-layout twins) ------------------
  * For min / first / last and count / sum with self_intersect=False every line is first rendered on its own into a
  * cleared canvas with a max() combination (stage 1: overlapping segments of ONE line do not accumulate), then that

@@ -684,6 +684,74 @@ def area_cases():
     return out
 
 
+def ragged_cases():
+    """The ragged layouts: LinesAxis1Ragged (core.py:443-444, line.py:457-523 + 1538-1600) Bresenham, antialiased single- and
+    2-stage; AreaToZeroAxis1Ragged / AreaToLineAxis1Ragged (core.py:676-677, 698-699; area.py:916-1073, 1939-2083).  Rows of
+    different lengths, an empty row, a one-vertex row, NaN vertices, x / y rows of different lengths (the shorter one counts),
+    float32 and float64 flat arrays."""
+    from datashader.datatypes import RaggedArray
+    out = {}
+    rng = np.random.default_rng(1212)
+    lens_x = [7, 1, 0, 12, 5, 9, 2, 30, 3, 16]
+    lens_y = [7, 1, 0, 12, 8, 6, 2, 30, 3, 16]          # rows 4 and 5: x and y lengths differ
+    lens_s = [7, 1, 0, 12, 8, 6, 2, 25, 3, 16]          # row 7: the stack curve is shorter still
+    nl = len(lens_x)
+
+    def walk(n, lo=-0.1, hi=1.1):
+        return np.sort(rng.random(n) * (hi - lo) + lo) if n else np.empty(0)
+
+    xr = [walk(n) for n in lens_x]
+    yr = [np.clip(np.cumsum(rng.normal(0, 0.15, n)) + rng.random(), -0.4, 1.3) for n in lens_y]
+    sr = [yr[i][:n] - rng.random(n) * 0.4 if n <= len(yr[i]) else np.r_[yr[i], yr[i][-1:].repeat(n - len(yr[i]))] - 0.2
+          for i, n in enumerate(lens_s)]
+    xr[3][2] = np.nan
+    yr[7][20] = np.nan
+    sr[9][5] = np.nan
+    yr[3][:] = yr[3][::-1]
+    xr[8] = xr[8][::-1].copy()                           # a right-to-left row
+    val = (rng.random(nl) * 5 - 1).astype(np.float32)
+    val[6] = np.nan
+    cat = rng.integers(0, 3, nl).astype(np.int8)
+    for dt in ("float32", "float64"):
+        d = {"x": RaggedArray(xr, dtype=dt), "y": RaggedArray(yr, dtype=dt), "s": RaggedArray(sr, dtype=dt), "val": val,
+             "cat": pd.Categorical.from_codes(cat, categories=["a", "b", "c"])}
+        df = pd.DataFrame(d)
+        t = "f32" if dt == "float32" else "f64"
+        for k in ("x", "y", "s"):
+            out[f"{t}_{k}_flat"] = np.asarray(df[k].array.flat_array)
+            out[f"{t}_{k}_starts"] = np.asarray(df[k].array.start_indices).astype(np.int64)
+        out["val"], out["cat"] = val, cat
+        cvs = ds.Canvas(plot_width=48, plot_height=36, x_range=(0, 1), y_range=(-0.2, 1.1))
+        auto = ds.Canvas(plot_width=31, plot_height=23)
+        aggs = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "min": ds.min("val"),
+                "mean": ds.mean("val"), "first": ds.first("val"), "last": ds.last("val"),
+                "where_max_row": ds.where(ds.max("val")), "by_count": ds.by("cat", ds.count())}
+        for name, agg in aggs.items():
+            out[f"{t}_line_lw0_{name}"] = np.asarray(cvs.line(df, "x", "y", agg=agg, axis=1).data)
+        r = auto.line(df, "x", "y", agg=ds.count(), axis=1)
+        out[f"{t}_line_auto_count"] = np.asarray(r.data)
+        out[f"{t}_line_auto_ranges"] = np.asarray(list(r.attrs["x_range"]) + list(r.attrs["y_range"]), dtype=np.float64)
+        aa = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"), "mean": ds.mean("val"),
+              "min": ds.min("val"), "first": ds.first("val"), "last": ds.last("val"),
+              "count_nsi": ds.count(self_intersect=False), "sum_nsi": ds.sum("val", self_intersect=False),
+              "where_max_row": ds.where(ds.max("val")), "by_max": ds.by("cat", ds.max("val"))}
+        for name, agg in aa.items():
+            for lw in (1, 2.5):
+                out[f"{t}_line_lw{lw}_{name}"] = np.asarray(cvs.line(df, "x", "y", agg=agg, axis=1, line_width=lw).data)
+        area_aggs = {"any": ds.any(), "count": ds.count(), "sum": ds.sum("val"), "max": ds.max("val"),
+                     "first": ds.first("val"), "by_count": ds.by("cat", ds.count())}
+        for name, agg in area_aggs.items():
+            out[f"{t}_area_zero_{name}"] = np.asarray(cvs.area(df, "x", "y", agg=agg, axis=1).data)
+            out[f"{t}_area_line_{name}"] = np.asarray(cvs.area(df, "x", "y", agg=agg, axis=1, y_stack="s").data)
+        r = auto.area(df, "x", "y", agg=ds.count(), axis=1)
+        out[f"{t}_area_zero_auto_count"] = np.asarray(r.data)
+        out[f"{t}_area_zero_auto_ranges"] = np.asarray(list(r.attrs["x_range"]) + list(r.attrs["y_range"]), dtype=np.float64)
+        r = auto.area(df, "x", "y", agg=ds.count(), axis=1, y_stack="s")
+        out[f"{t}_area_line_auto_count"] = np.asarray(r.data)
+        out[f"{t}_area_line_auto_ranges"] = np.asarray(list(r.attrs["x_range"]) + list(r.attrs["y_range"]), dtype=np.float64)
+    return out
+
+
 def negzero_cases():
     """max / min keep whichever zero ARRIVED FIRST when the extreme of a pixel is a zero (strict compare,
     reductions.py:1178-1183, 1222-1227): columns mixing -0.0 and +0.0 with values on one side of zero only."""
@@ -711,6 +779,10 @@ def negzero_cases():
 
 
 def main():
+    if "--ragged-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "ragged.npz"), **ragged_cases())
+        print("ragged.npz", os.path.getsize(os.path.join(HERE, "ragged.npz")) // 1024, "KiB")
+        return
     if "--lines-aa3-only" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "lines_aa3.npz"), **lines_aa3_cases())
         print("lines_aa3.npz", os.path.getsize(os.path.join(HERE, "lines_aa3.npz")) // 1024, "KiB")
@@ -763,6 +835,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "lines_extra.npz"), **lines_extra_cases())
     np.savez_compressed(os.path.join(HERE, "line_layouts.npz"), **line_layout_cases())
     np.savez_compressed(os.path.join(HERE, "areas.npz"), **area_cases())
+    np.savez_compressed(os.path.join(HERE, "ragged.npz"), **ragged_cases())
     np.savez_compressed(os.path.join(HERE, "lines_aa2.npz"), **lines_aa2_cases())
     np.savez_compressed(os.path.join(HERE, "lines_aa3.npz"), **lines_aa3_cases())
     np.savez_compressed(os.path.join(HERE, "tiles.npz"), **tiles_cases())

@@ -24,6 +24,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.View) == 16 + 64
     assert ctypes.sizeof(_lib.Base) == 48
     assert ctypes.sizeof(_lib.Plan) == 8 + 48 * 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.LineLayout) == 24 + 3 * 8 + 3 * 8      # strides, flags, ragged starts + flat lengths
 
 
 def test_argument_errors_do_not_need_a_gpu():

@@ -2,6 +2,7 @@
 null handling, without touching the GPU."""
 import numpy as np
 import pytest
+import torch
 
 from datashader_b200.frame import HostFrame, as_frame
 
@@ -58,3 +59,53 @@ def test_dict_source():
         as_frame({"x": np.arange(4.0)}, ["x", "y"], device="cpu")
     with pytest.raises(ValueError, match="source must be a pandas or dask DataFrame"):
         as_frame([1, 2, 3], ["x"], device="cpu")
+
+
+def test_ragged_array_container_and_frame():
+    """RaggedArray (the input type of the ragged line / area glyphs, reference datatypes.py:209-300) as a pandas column, and its
+    trip into a HostFrame: flat values + int64 start index per row, schema kind 'ragged'."""
+    import pandas as pd
+    from datashader_b200.datatypes import RaggedArray, RaggedDtype
+    from datashader_b200.frame import HostFrame, RaggedColumn
+    ra = RaggedArray([[0.0, 1, 2], [1.0, 3, 4, 2], None, [0.5]], dtype="float32")
+    assert isinstance(ra.dtype, RaggedDtype) and ra.dtype.name == "ragged[float32]" and len(ra) == 4
+    np.testing.assert_array_equal(ra.start_indices, [0, 3, 7, 7])
+    np.testing.assert_array_equal(ra.flat_array, np.array([0, 1, 2, 1, 3, 4, 2, 0.5], np.float32))
+    np.testing.assert_array_equal(ra.isna(), [False, False, True, False])
+    np.testing.assert_array_equal(ra[1], np.array([1, 3, 4, 2], np.float32))
+    df = pd.DataFrame({"x": ra, "v": [1.0, 2.0, 3.0, 4.0]})
+    sub = df.iloc[1:4]["x"].array                      # slicing re-bases the start indices
+    np.testing.assert_array_equal(sub.start_indices, [0, 4, 4])
+    np.testing.assert_array_equal(pd.concat([df, df])["x"].array.start_indices, [0, 3, 7, 7, 8, 11, 15, 15])
+    assert pd.Series([[1, 2], [3]], dtype="ragged[float64]").array.flat_array.dtype == np.float64
+    wrapped = RaggedArray({"start_indices": np.array([0, 2]), "flat_array": np.arange(5.0)})
+    np.testing.assert_array_equal(wrapped[1], [2.0, 3.0, 4.0])
+    with pytest.raises(ValueError):
+        RaggedArray({"start_indices": np.array([3, 1]), "flat_array": np.arange(5.0)})
+    hf = HostFrame.from_pandas(df, columns=["x", "v"])
+    assert hf.schema()["x"] == ("ragged", None) and hf.schema()["v"][0] == "float" and len(hf) == 4 and hf.n_chunks() == 1
+    col = hf.columns["x"]
+    assert isinstance(col, RaggedColumn) and col.starts.dtype == torch.int64 and col.flat.dtype == torch.float32
+    np.testing.assert_array_equal(col.starts.numpy(), [0, 3, 7, 7])
+
+    class Foreign:                                     # the reference's own RaggedArray is read by attribute
+        flat_array = np.arange(4.0)
+        start_indices = np.array([0, 1], dtype=np.uint8)
+    hf2 = HostFrame({"x": Foreign(), "v": np.zeros(2)})
+    assert hf2.schema()["x"][0] == "ragged" and hf2.columns["x"].starts.tolist() == [0, 1]
+
+
+def test_ragged_glyph_selection_and_validation():
+    """Canvas.line / Canvas.area with axis=1 and scalar column names select the ragged glyphs (core.py:443-444, 676-677, 698-699)
+    and reject non-ragged columns with the reference's messages (line.py:458-467, area.py:917-926) before any kernel runs."""
+    import pandas as pd
+    import datashader_b200 as ds
+    from datashader_b200.datatypes import RaggedArray
+    df = pd.DataFrame({"x": RaggedArray([[0.0, 1.0], [0.5]]), "y": [1.0, 2.0]})
+    cvs = ds.Canvas(plot_width=8, plot_height=8, x_range=(0, 1), y_range=(0, 1))
+    with pytest.raises(ValueError, match="y must be a RaggedArray"):
+        cvs.line(df, "x", "y", axis=1)
+    with pytest.raises(ValueError, match="x must be a RaggedArray"):
+        cvs.area(df, "y", "x", axis=1)
+    with pytest.raises(ValueError, match="y must be a RaggedArray"):
+        cvs.area(df, "x", "x", axis=1, y_stack="y")

@@ -300,3 +300,44 @@ def test_device_log10f_restatement_equals_the_c_library():
         ora.build()
     r = subprocess.run([exe, "61"], capture_output=True, text=True)
     assert r.returncode == 0 and " 0 differ" in r.stdout, r.stdout + r.stderr
+
+
+def _ragged_inputs(g, tag):
+    return {k: (g[f"{tag}_{k}_flat"], g[f"{tag}_{k}_starts"]) for k in ("x", "y", "s")}
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_ragged_golden(tag):
+    """LinesAxis1Ragged / AreaToZeroAxis1Ragged / AreaToLineAxis1Ragged restated in the oracle (row loops of line.py:1559-1600,
+    area.py:1959-2004, 2033-2081) vs the real reference (tests/golden/ragged.npz: uneven rows, an empty and a one-vertex row,
+    x / y / stack rows of different lengths, NaN vertices)."""
+    g = load("ragged.npz")
+    r = _ragged_inputs(g, tag)
+    (xf, xs), (yf, ys), (sf, ss) = r["x"], r["y"], r["s"]
+    val = g["val"]
+    view = ora.make_view(48, 36, (0, 1), (-0.2, 1.1))
+    for name in ("any", "count", "sum", "max", "min"):
+        vals = None if name in ("any", "count") else val
+        _eq(ora.lines_ragged(xf, xs, yf, ys, view, name, vals, 0), g[f"{tag}_line_lw0_{name}"], f"ragged lw0 {name}", name == "sum")
+    for lw in (1, 2.5):
+        for name in ("any", "count", "sum", "max", "mean"):
+            vals = None if name in ("any", "count") else val
+            got, want = ora.lines_ragged(xf, xs, yf, ys, view, name, vals, lw), g[f"{tag}_line_lw{lw}_{name}"]
+            assert got.dtype == want.dtype and np.array_equal(np.isnan(got), np.isnan(want)), (lw, name)
+            np.testing.assert_allclose(got, want, rtol=1e-6 if name in ("any", "count") else 1e-12, equal_nan=True, err_msg=f"{lw} {name}")
+        for gname, oname in (("min", "min"), ("first", "first"), ("last", "last"), ("sum_nsi", "sum"), ("count_nsi", "count")):
+            got = ora.lines_ragged_aa2(xf, xs, yf, ys, view, oname, None if gname == "count_nsi" else val, lw)
+            want = g[f"{tag}_line_lw{lw}_{gname}"]
+            assert got.dtype == want.dtype and np.array_equal(np.isnan(got), np.isnan(want)), (lw, gname)
+            np.testing.assert_allclose(got, want, rtol=1e-6 if oname == "count" else 1e-12, equal_nan=True, err_msg=f"{lw} {gname}")
+    # auto ranges: bounds of the flat arrays (line.py:472-478); area-to-zero includes y = 0 (area.py:932-939)
+    xr, yr = ora.compute_bounds(xf), ora.compute_bounds(yf)
+    np.testing.assert_array_equal(np.array(list(xr) + list(yr)), g[f"{tag}_line_auto_ranges"])
+    _eq(ora.lines_ragged(xf, xs, yf, ys, ora.make_view(31, 23, xr, yr), "count", None, 0), g[f"{tag}_line_auto_count"], "auto count")
+    for name in ("any", "count", "sum", "max"):
+        vals = None if name in ("any", "count") else val
+        _eq(ora.areas_ragged(xf, xs, yf, ys, view, None, None, name, vals), g[f"{tag}_area_zero_{name}"], f"area zero {name}", name == "sum")
+        _eq(ora.areas_ragged(xf, xs, yf, ys, view, sf, ss, name, vals), g[f"{tag}_area_line_{name}"], f"area line {name}", name == "sum")
+    yz = (min(yr[0], 0), max(yr[1], 0))
+    np.testing.assert_array_equal(np.array(list(xr) + list(yz)), g[f"{tag}_area_zero_auto_ranges"])
+    _eq(ora.areas_ragged(xf, xs, yf, ys, ora.make_view(31, 23, xr, yz), None, None, "count"), g[f"{tag}_area_zero_auto_count"], "area auto")
