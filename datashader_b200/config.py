@@ -33,3 +33,7 @@ lines_simple_path = True
 routed = True
 routed_min_rows = 1 << 24
 routed_max_scratch_bytes = 64 << 30
+
+# where(max | min) of a float32 selector on canvases beyond L2: the plain extreme first (routed), then a filtered pass that
+# finds the row holding it (dsb_points_match32), instead of packed {key, row} atomics into an L2-banded 8-byte canvas.
+where_two_pass = True

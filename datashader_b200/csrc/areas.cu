@@ -1,6 +1,6 @@
 // Area glyphs: one thread per trapezoid, x-driven double-Bresenham scan fill fused with the accumulator plan.
 // Replaces _build_draw_trapezoid_y (glyphs/area.py:1076-1320), _skip_or_clip_trapezoid_y (:1323-1380) and the
-// extend_cuda kernels of the ten non-ragged area layouts (:1383-2083).  "to zero" areas pass ys1 == NULL
+// extend kernels of the twelve area layouts (:1383-2083; the ragged ones read flat arrays + start indices).  "to zero" areas pass ys1 == NULL
 // (y1 = y2 = 0.0, stacked = False); "to line" areas pass the second curve (stacked = True).
 #include "common.cuh"
 #include "accum.cuh"

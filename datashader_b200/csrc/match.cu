@@ -1,0 +1,191 @@
+// where(max | min) of a float32 selector on canvases beyond L2, second pass ("which row holds the extreme").
+//
+// dsb_points answers where(max('v')) in one pass with packed {key32, row} 64-bit atomics (DSB_OP_ARGMAX32): on an 8192 x 8192
+// canvas that is a 537 MB accumulator, five L2-banded re-reads of the columns and a global RED per hit (95 ms for 4e9 points).
+// Split in two the extreme itself is a single 4-byte accumulator, which the routed path (routed.cu) computes without global
+// atomics; what remains is this pass: every row whose key equals its pixel's finished extreme votes its global row with
+// atomicMin - the earliest row among the ties, the row the reference's strict compare keeps (reductions.py:1178-1183,
+// 1222-1227, 2009-2016).  Only ~1 row per pixel can match, but finding them naively gathers the key of every row's pixel from
+// a 268 MB canvas.  A COARSE map removes that: the least extreme of every 16 x 16 pixel block (1 MB at 8192^2, L2-resident).
+// A row that does not reach its block's entry cannot be the extreme of its own pixel and is dropped after one L2 hit; the
+// survivors (~10 % for 60 uniform rows per pixel) pay the DRAM gather and, if equal, the RED.  Exact for any distribution:
+// the filter only ever drops rows that provably lose.
+#include "common.cuh"
+#include "fastmap.cuh"
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+
+constexpr int MB_SHIFT = 4;       // 16 x 16 pixels per coarse entry.  Measured at 8192^2, 4e9 rows (tools/bench_match.py, profiles/r02_where_two_pass.md):
+                                  // 4 x 4 ... 32 x 32 all within 2 % - the pass is bound by its dependent loads, not by the survivors
+
+struct MatchArgs {
+  dsb_view v;
+  FastMap fm;
+  const float* x; const float* y; const float* val;
+  long long n, row_offset;
+  const int* keys;        // finished MAX32 / MIN32 key canvas [H, W]
+  long long* rows;        // i64 canvas, DSB_OP_MINROW-initialised
+  int* coarse;            // [ch, cw]
+  int cw, ch, shift;
+};
+
+// coarse[by][bx] = the least extreme key of the block: min of the maxima (IS_MAX) / max of the minima
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) k_match_coarse(const MatchArgs a) {
+  __shared__ int part[8];
+  const int B = 1 << a.shift;
+  int k = IS_MAX ? INT_MAX : INT_MIN;
+  // one warp per coarse entry when the block is small (<= 8 x 8), one CTA otherwise
+  const bool per_warp = a.shift <= 3;
+  const long long e = per_warp ? (long long)blockIdx.x * 8 + (threadIdx.x >> 5) : blockIdx.x;
+  const int nthr = per_warp ? 32 : 256, t = per_warp ? (threadIdx.x & 31) : threadIdx.x;
+  if (e < (long long)a.cw * a.ch) {
+    const int bx = (int)(e % a.cw), by = (int)(e / a.cw);
+    for (int p = t; p < B * B; p += nthr) {
+      const int px = (bx << a.shift) + (p & (B - 1)), py = (by << a.shift) + (p >> a.shift);
+      if (px < a.v.width && py < a.v.height) {
+        const int q = a.keys[(long long)py * a.v.width + px];
+        k = IS_MAX ? min(k, q) : max(k, q);
+      }
+    }
+  }
+  k = IS_MAX ? __reduce_min_sync(0xffffffffu, k) : __reduce_max_sync(0xffffffffu, k);
+  if (per_warp) {
+    if ((threadIdx.x & 31) == 0 && e < (long long)a.cw * a.ch) a.coarse[e] = k;
+    return;
+  }
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) k = IS_MAX ? min(k, part[w]) : max(k, part[w]);
+    a.coarse[blockIdx.x] = k;
+  }
+}
+
+template <bool IS_MAX, int PPT, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) k_points_match32(const __grid_constant__ MatchArgs a) {
+  const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
+  const FastMap& fm = a.fm;
+  const int* __restrict__ keys = a.keys;
+  const int* __restrict__ coarse = a.coarse;
+  const int sh = a.shift;
+  auto exact = [&](float xv, float yv, float vv, long long i) {      // rows near a pixel edge: exact f64 mapping, no filter
+    if (vv != vv) return;
+    const int cell = map_exact_linear(a.v, xv, yv);
+    if (cell >= 0 && __ldcg(keys + cell) == key32_from_f32(vv)) atomicMin(a.rows + cell, a.row_offset + i);
+  };
+  constexpr int NV = PPT / 4;                                        // 16-byte loads per column per step
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const float4* __restrict__ v4 = (const float4*)a.val;
+  const long long n4 = a.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += NV * stride) {
+    float xs[PPT], ys[PPT], vs[PPT];
+#pragma unroll
+    for (int u = 0; u < NV; u++) {
+      const long long q = i4 + u * stride;
+      const bool in = q < n4;
+      const float4 xa = in ? __ldcs(x4 + q) : nan4, ya = in ? __ldcs(y4 + q) : nan4, va = in ? __ldcs(v4 + q) : nan4;
+      xs[4 * u] = xa.x; xs[4 * u + 1] = xa.y; xs[4 * u + 2] = xa.z; xs[4 * u + 3] = xa.w;
+      ys[4 * u] = ya.x; ys[4 * u + 1] = ya.y; ys[4 * u + 2] = ya.z; ys[4 * u + 3] = ya.w;
+      vs[4 * u] = va.x; vs[4 * u + 1] = va.y; vs[4 * u + 2] = va.z; vs[4 * u + 3] = va.w;
+    }
+    int cell[PPT], key[PPT], thr[PPT];
+    uint32_t okm = 0, slow = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {                   // the K2-tight mapping: see k_points_priv_tight
+      const float xf = fmaf(xs[k], fm.sx, fm.tx), yf = fmaf(ys[k], fm.sy, fm.ty);
+      const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+      const float dx = xf - (float)xi, dy = yf - (float)yi;
+      const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
+      const bool ok = sure && (uint32_t)xi < W && (uint32_t)yi < H && vs[k] == vs[k];
+      cell[k] = ok ? yi * (int)W + xi : 0;
+      thr[k] = __ldg(coarse + (ok ? (yi >> sh) * a.cw + (xi >> sh) : 0));      // independent L2 / L1 hits in flight
+      key[k] = key32_from_f32(vs[k]);
+      okm |= (uint32_t)ok << k;
+      slow |= (uint32_t)(!sure && vs[k] == vs[k]) << k;
+    }
+    uint32_t live = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) live |= (uint32_t)(IS_MAX ? key[k] >= thr[k] : key[k] <= thr[k]) << k;
+    live &= okm;
+    if (live) {
+      int cur[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; k++) cur[k] = (live >> k) & 1u ? __ldcg(keys + cell[k]) : (IS_MAX ? INT_MAX : INT_MIN);
+#pragma unroll
+      for (int k = 0; k < PPT; k++)
+        if (((live >> k) & 1u) && cur[k] == key[k]) atomicMin(a.rows + cell[k], a.row_offset + 4 * (i4 + (k >> 2) * stride) + (k & 3));
+    }
+    if (slow) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++)
+        if (slow & (1u << k)) exact(xs[k], ys[k], vs[k], 4 * (i4 + (k >> 2) * stride) + (k & 3));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {           // tail rows
+    const long long i = (n4 << 2) + threadIdx.x;
+    exact(a.x[i], a.y[i], a.val[i], i);
+  }
+}
+
+// any axes / alignment: the exact mapping for every row, no filter (log axes, or ranges beyond the float32 mapping's error bound)
+template <int DUMMY>
+__global__ void __launch_bounds__(256) k_points_match32_exact(const MatchArgs a) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const float vv = a.val[i];
+    if (vv != vv) continue;
+    const long long cell = map_to_cell<float>(a.v, a.x[i], a.y[i]);
+    if (cell >= 0 && __ldcg(a.keys + cell) == key32_from_f32(vv)) atomicMin(a.rows + cell, a.row_offset + i);
+  }
+}
+
+extern "C" int64_t dsb_points_match32_scratch_bytes(const dsb_view* view) {
+  if (!view || view->width <= 0 || view->height <= 0) return 0;
+  const long long cw = (view->width + (1 << MB_SHIFT) - 1) >> MB_SHIFT, ch = (view->height + (1 << MB_SHIFT) - 1) >> MB_SHIFT;
+  return cw * ch * 4;
+}
+
+extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                                  int64_t row_offset, const void* val, int32_t val_dtype, const void* keys, int32_t is_max,
+                                  void* rows, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points_match32: bad view"); return DSB_ERR_ARG; }
+  if (!keys || !rows) { dsb_set_error("dsb_points_match32: null canvas"); return DSB_ERR_ARG; }
+  if (n < 0 || n > (1LL << 32)) { dsb_set_error("dsb_points_match32: n must be in [0, 2^32] per call"); return DSB_ERR_ARG; }
+  if (n == 0) return DSB_OK;
+  if (!x || !y || !val) { dsb_set_error("dsb_points_match32: null column"); return DSB_ERR_ARG; }
+  if (xy_dtype != DSB_F32 || val_dtype != DSB_F32) { dsb_set_error("dsb_points_match32: float32 columns only"); return DSB_ERR_UNSUPPORTED; }
+  if ((long long)view->width * view->height >= (1LL << 31)) { dsb_set_error("dsb_points_match32: canvas too large"); return DSB_ERR_UNSUPPORTED; }
+  MatchArgs a;
+  a.v = *view;
+  a.fm = make_fast_map(view);
+  a.shift = MB_SHIFT;
+  a.cw = (view->width + (1 << a.shift) - 1) >> a.shift; a.ch = (view->height + (1 << a.shift) - 1) >> a.shift;
+  if (!scratch || scratch_bytes < (long long)a.cw * a.ch * 4) { dsb_set_error("dsb_points_match32: scratch too small"); return DSB_ERR_ARG; }
+  a.x = (const float*)x; a.y = (const float*)y; a.val = (const float*)val; a.n = n; a.row_offset = row_offset;
+  a.keys = (const int*)keys; a.rows = (long long*)rows; a.coarse = (int*)scratch;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool fast = a.fm.enabled && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)val) & 15) == 0;
+  {   // the label names both passes when the extreme was computed just before (bench.py reads it back as roofline.kernel)
+    char prev[96];
+    snprintf(prev, sizeof(prev), "%s", dsb_last_kernel());
+    const bool chained = strstr(prev, is_max ? "max32" : "min32") != nullptr && strstr(prev, "k_points_match32") == nullptr;
+    dsb_note_kernel(chained ? "%s<%s> after %s" : "%s<%s>", fast ? "k_points_match32" : "k_points_match32_exact", is_max ? "max" : "min", prev);
+  }
+  if (!fast) {
+    k_points_match32_exact<0><<<dsb_num_sms() * 8, 256, 0, s>>>(a);
+  } else {
+    const int cgrid = a.shift <= 3 ? (int)(((long long)a.cw * a.ch + 7) / 8) : a.cw * a.ch;
+    if (is_max) k_match_coarse<true><<<cgrid, 256, 0, s>>>(a); else k_match_coarse<false><<<cgrid, 256, 0, s>>>(a);
+    // 4 rows per thread per step, 6 CTAs of 256 threads per SM: 23.4 ms for 4e9 rows against 28.0 ms with 8 rows per step and
+    // 3 CTAs - the step is a chain of three dependent loads (columns, coarse entry, key) and wants warps, not registers
+    if (is_max) k_points_match32<true, 4, 6><<<dsb_num_sms() * 6, 256, 0, s>>>(a);
+    else k_points_match32<false, 4, 6><<<dsb_num_sms() * 6, 256, 0, s>>>(a);
+  }
+  DSB_CUDA_CHECK_LAUNCH("dsb_points_match32");
+  return DSB_OK;
+}

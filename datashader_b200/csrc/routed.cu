@@ -426,7 +426,7 @@ extern "C" int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t
   uint32_t cpb;
   const uint32_t nb = route_nb((long long)view->width * view->height, &cpb);
   // records: 1.10 n + 4096 per bucket (k_route_plan scales the capacities down to whatever it is given)
-  return (int64_t)(route_fixed_bytes(nb, n) + ((size_t)((double)n * 1.10) + (size_t)nb * 4096) * 8);
+  return (int64_t)(route_fixed_bytes(nb, n) + ((size_t)((double)n * 1.10) + (size_t)nb * 4096 + 1024) * 8);   // + the floor dsb_points_routed asks for
 }
 
 template <int OP>

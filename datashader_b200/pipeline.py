@@ -171,6 +171,9 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
     n, row_offset = len(chunk), chunk.row_offset
     if n > (1 << 32):
         raise NotImplementedError("more than 2^32 rows per device chunk")
+    for acc in [a for a in accs if a.kind == "matchrow32"]:
+        _launch_match32(view, chunk, x, y, xy_dtype, acc, canv, ctx)
+    accs = [a for a in accs if a.kind != "matchrow32"]
     for plan, _keep in _plans(chunk, accs, canv, ctx, categorizer, ncat):
         groups = None
         if (config.split_summary and plan.nops >= 3 and ncat == 0 and xy_dtype == _lib.F32 and n >= config.priv_min_rows
@@ -178,6 +181,20 @@ def _launch_points(view, chunk, glyph, accs, canv, ctx, categorizer, ncat):
             groups = _specialised_groups(plan)
         for sub in ([_sub_plan(plan, g) for g in groups] if groups else [plan]):
             _launch_points_plan(view, x, y, xy_dtype, n, row_offset, sub, ctx)
+
+
+def _launch_match32(view, chunk, x, y, xy_dtype, acc, canv, ctx):
+    """Second pass of the two-pass where(max | min): rows whose key equals the finished extreme vote their row id."""
+    lib = _lib.lib()
+    need = int(lib.dsb_points_match32_scratch_bytes(C.byref(view)))
+    scratch = getattr(ctx, "_match32_scratch", None)
+    if scratch is None or scratch.numel() < need:
+        scratch = ctx._match32_scratch = torch.empty(need, dtype=torch.uint8, device=x.device)
+    val = chunk[acc.col]
+    _lib.check(lib.dsb_points_match32(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, len(chunk), chunk.row_offset,
+                                      val.data_ptr(), ctx.dsb_dtype(acc.col), canv[acc.aux.key].data_ptr(),
+                                      int(acc.aux.kind == "max32"), canv[acc.key].data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                      ctx.stream_ptr), "dsb_points_match32")
 
 
 def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
@@ -368,8 +385,14 @@ def points(source, canvas, glyph: Point, agg, dist=None):
             x_range, y_range = canvas.x_range, canvas.y_range
         canvas.validate_ranges(x_range, y_range)
         view, x_st, y_st = make_view(canvas, x_range, y_range)
+        # where(max | min) as two passes when the packed {key, row} canvas would not fit L2 and the routed kernels apply
+        # (float32 coordinates, linear axes, enough rows): see where._row_accs
+        match32 = (config.where_two_pass and config.routed and len(frame) >= config.routed_min_rows
+                   and 8 * canvas.plot_width * canvas.plot_height > config.l2_budget_bytes
+                   and frame.np_dtype(glyph.x) == np.float32 and frame.np_dtype(glyph.y) == np.float32
+                   and not canvas.x_axis.is_log and not canvas.y_axis.is_log)
         reds, results, labels = _accumulate_and_finalize(frame, resident, needed, schema, view, canvas, glyph, agg, dist,
-                                                         _launch_points)
+                                                         _launch_points, ctx_extra={"match32": match32})
     x_axis = canvas.x_axis.compute_index(x_st, canvas.plot_width)
     y_axis = canvas.y_axis.compute_index(y_st, canvas.plot_height)
     return _wrap(agg, reds, results, glyph, x_axis, y_axis, x_range, y_range, labels)

@@ -49,12 +49,14 @@ ACC_INFO = {
     "max64": (torch.int64, "max"), "min64": (torch.int64, "min"),
     "maxrow": (torch.int64, "max"), "minrow": (torch.int64, "min"),
     "argmax32": (torch.int64, "max"), "argmin32": (torch.int64, "min"),
-    "matchrow64": (torch.int64, "min"),
+    "matchrow64": (torch.int64, "min"), "matchrow32": (torch.int64, "min"),
 }
 ACC_OP = {
     "count": _lib.OP_COUNT, "any": _lib.OP_ANY, "sum": _lib.OP_SUM, "max32": _lib.OP_MAX32, "min32": _lib.OP_MIN32,
     "max64": _lib.OP_MAX64, "min64": _lib.OP_MIN64, "maxrow": _lib.OP_MAXROW, "minrow": _lib.OP_MINROW,
     "argmax32": _lib.OP_ARGMAX32, "argmin32": _lib.OP_ARGMIN32, "matchrow64": _lib.OP_MATCHROW64,
+    # initialised like a MINROW canvas; never part of a plan: pipeline._launch_points hands it to dsb_points_match32
+    "matchrow32": _lib.OP_MINROW,
 }
 
 
@@ -420,6 +422,12 @@ class where(_FloatingReduction):
             return [sel._row_acc()]
         which = sel._which
         if _is_key32(ctx.np_dtype(sel.column)):
+            if getattr(ctx, "match32", False) and np.dtype(ctx.np_dtype(sel.column)) == np.float32 and len(ctx.shape) == 2:
+                # canvases beyond L2 (pipeline.points sets ctx.match32): the packed {key, row} accumulator would be 8 bytes per
+                # pixel, L2-banded, with a global RED per hit; two passes instead - the plain extreme (4 bytes per pixel, served
+                # by the routed kernels), then "which row holds it" against the finished canvas (dsb_points_match32)
+                value = Acc(which + "32", sel.column)
+                return [value, Acc("matchrow32", sel.column, None, aux=value)]
             return [Acc("arg" + which + "32", sel.column)]
         value = Acc(which + "64", sel.column)
         return [value, Acc("matchrow64", sel.column, None, aux=value)]
@@ -439,7 +447,7 @@ class where(_FloatingReduction):
                                                  ctx.frame.row_offset, None, rows.data_ptr(), c.numel(), ctx.stream_ptr),
                        "dsb_decode_arg")
             return rows
-        if last_acc.kind in ("minrow", "matchrow64"):
+        if last_acc.kind in ("minrow", "matchrow64", "matchrow32"):
             return _finish_rows(ctx, c.clone())
         return c
 

@@ -183,6 +183,19 @@ int dsb_finalize_sum(const double* sum, const uint8_t* mask, double* out, int64_
  * its two accumulators with mean() and ride the privatised count kernel (dsb_points_priv). */
 int dsb_finalize_sum_counted(const double* sum, const void* count_u32, double* out, int64_t ncell, void* stream);
 
+/* where(max | min) of a float32 selector as TWO passes, for canvases beyond L2 (csrc/match.cu): pass 1 is the plain
+ * DSB_OP_MAX32 / MIN32 accumulator of the selector column (dsb_points_routed serves it without global atomics); this is pass 2.
+ * `keys` = the finished (all ranks combined) key32 canvas [H, W]; every row whose key equals its pixel's entry votes its
+ * global row row_offset + i into `rows` (i64 [H, W], dsb_init_canvas(DSB_OP_MINROW)) with an atomic min: the earliest row among
+ * the ties, the one the reference's strict compare keeps (reductions.py:1178-1183, 1222-1227, 2009-2016).  A coarse map in
+ * `scratch` (dsb_points_match32_scratch_bytes: the least extreme of every 16 x 16 pixel block) drops the rows that cannot
+ * match after one L2 hit.  float32 x / y / val; any axes (linear axes inside the float32 mapping's error bound take the
+ * filtered kernel, everything else the exact mapping per row). */
+int64_t dsb_points_match32_scratch_bytes(const dsb_view* view);
+int dsb_points_match32(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                       const void* val, int32_t val_dtype, const void* keys, int32_t is_max, void* rows, void* scratch,
+                       int64_t scratch_bytes, void* stream);
+
 /* ---- lines ---------------------------------------------------------------------------------- */
 typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5,
                DSB_LINE_MEAN = 6 /* antialiased only: canvas f64 sum (zeroed), `mask` = u32 count canvas (zeroed) */,

@@ -49,6 +49,23 @@ def main():
                 assert_agg_equal(got, want, f"{name} world={world}")
             except AssertionError as e:   # noqa: PERF203
                 bad.append(f"{name}: {str(e)[:200]}")
+    # where(max | min) as two passes (config 5's form, forced on at this size): the key canvas is all-reduced between the passes,
+    # so every rank matches its rows against the GLOBAL extreme, and the row canvas (min) after
+    from datashader_b200 import _lib
+    knobs = (ds.config.routed_min_rows, ds.config.l2_budget_bytes)
+    ds.config.routed_min_rows, ds.config.l2_budget_bytes = 0, 1
+    _lib.check(_lib.lib().dsb_routed_configure(0))
+    for name in ("where_max_v32_other", "where_min_v32_row"):
+        got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
+        if b"k_points_match32" not in _lib.lib().dsb_last_kernel():
+            bad.append(f"two-pass {name}: took {_lib.lib().dsb_last_kernel()}")
+        if rank == 0:
+            try:
+                assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view), f"two-pass {name} world={world}")
+            except AssertionError as e:
+                bad.append(f"two-pass {name}: {str(e)[:200]}")
+    ds.config.routed_min_rows, ds.config.l2_budget_bytes = knobs
+    _lib.check(_lib.lib().dsb_routed_configure(1 << 24))
     # LinesAxis1 sharded by line: each rank rasterises its lines, canvases all-reduced (sum / max / min per accumulator)
     nl, nv = 2001, 9
     lx = np.cumsum(rng.normal(0, 0.05, (nl, nv)), axis=1).astype(np.float32) + np.float32(0.5)
@@ -129,6 +146,42 @@ def main():
     whole = lcvs.line(full, "x", "y", agg=ds.first("val")).data if rank == 0 else None
     if rank == 0 and not np.array_equal(got, whole, equal_nan=True):
         bad.append("line axis0 sharded first")
+    # LinesAxis1Ragged / AreaToZeroAxis1Ragged sharded by row: every rank holds whole rows (its slice of the start indices,
+    # re-based) and the global row offset; Bresenham / fill / antialiased max / 2-stage first against the oracle's row loop,
+    # where(first) row ids against the single-rank run
+    nr = 801
+    rlen = rng.integers(0, 14, nr)
+    rst = (np.cumsum(rlen) - rlen).astype(np.int64)
+    rx = (np.cumsum(rng.normal(0, 0.04, int(rlen.sum()))) % 1.0).astype(np.float32)
+    ry = rng.random(int(rlen.sum())).astype(np.float32)
+    rval = rng.normal(size=nr)
+    rlo, rhi = shard_bounds(nr, rank, world)
+    flo, fhi = int(rst[rlo]) if rlo < nr else len(rx), (int(rst[rhi]) if rhi < nr else len(rx))
+
+    def rcol(flat, a, b, fa, fb):
+        return ds.RaggedColumn(torch.from_numpy(flat[fa:fb].copy()).cuda(), torch.from_numpy(rst[a:b] - fa).cuda())
+    rframe = ds.DeviceFrame({"x": rcol(rx, rlo, rhi, flo, fhi), "y": rcol(ry, rlo, rhi, flo, fhi),
+                             "val": torch.from_numpy(rval[rlo:rhi].copy()).cuda()}, row_offset=rlo)
+    rframe.sharded = True
+    rfull = ds.DeviceFrame({"x": rcol(rx, 0, nr, 0, len(rx)), "y": rcol(ry, 0, nr, 0, len(ry)), "val": torch.from_numpy(rval).cuda()})
+    for name, agg, lw in [("count", ds.count(), 0), ("max", ds.max("val"), 0), ("max", ds.max("val"), 2.0), ("first", ds.first("val"), 2.0)]:
+        got = lcvs.line(rframe, "x", "y", agg=agg, axis=1, line_width=lw).data
+        if rank == 0:
+            want = (ora.lines_ragged_aa2(rx, rst, ry, rst, lview, name, rval, lw) if name == "first"
+                    else ora.lines_ragged(rx, rst, ry, rst, lview, name, None if name == "count" else rval, lw))
+            ok = got.dtype == want.dtype and np.array_equal(np.isnan(got.astype("f8")), np.isnan(want.astype("f8")))
+            ok = ok and np.allclose(got, want, rtol=1e-6, atol=1e-6, equal_nan=True)
+            if lw == 0:
+                ok = ok and np.array_equal(got, want, equal_nan=got.dtype.kind == "f")
+            if not ok:
+                bad.append(f"ragged lines sharded {name} lw={lw}")
+    got = lcvs.area(rframe, "x", "y", agg=ds.count(), axis=1).data
+    if rank == 0 and not np.array_equal(got, ora.areas_ragged(rx, rst, ry, rst, lview, None, None, "count", None)):
+        bad.append("ragged area sharded count")
+    got = lcvs.line(rframe, "x", "y", agg=ds.where(ds.first("val")), axis=1, line_width=2.0).data
+    want = lcvs.line(rfull, "x", "y", agg=ds.where(ds.first("val")), axis=1, line_width=2.0).data
+    if rank == 0 and not np.array_equal(got, want):
+        bad.append("ragged lines antialiased where(first): sharded != single-rank row ids")
     # auto-ranging across shards
     got = ds.Canvas(31, 17).points(frame, "x", "y").data
     if rank == 0:

@@ -165,6 +165,44 @@ def test_routed_negzero(routed):
     assert_agg_equal(got, want, "routed negzero max")
 
 
+@pytest.mark.parametrize("shape,n,clustered", [((301, 257), 200_003, False), ((640, 480), 250_000, True)])
+def test_where_two_pass_matches_oracle(routed, shape, n, clustered):
+    """where(max | min) as two passes (the routed extreme, then dsb_points_match32 with its coarse filter) against the oracle:
+    values rounded to 0.1, so nearly every pixel's extreme is held by several rows and the earliest must win."""
+    import torch
+    from datashader_b200 import _lib
+    from oracle import oracle as ora
+    ds = routed
+    W, H = shape
+    cols = _cols(np.random.default_rng(n + 1), n, clustered)
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    for name in ("where_max_v32_other", "where_min_v32_row", "where_max_v32_row", "where_min_v32_other"):
+        spec = SPECS.get(name) or ("where", (name.split("_")[1], "v32"), None if name.endswith("row") else "other")
+        got = cvs.points(frame, "x", "y", make_agg(spec)).data
+        assert b"k_points_match32<" in _lib.lib().dsb_last_kernel(), (name, _lib.lib().dsb_last_kernel())
+        assert_agg_equal(got, ora.points(cols, "x", "y", spec, view), f"two-pass {name} {shape} clustered={clustered}")
+    # summary sharing the extreme's canvas with the where()
+    both = cvs.points(frame, "x", "y", ds.summary(m=ds.max("v32"), w=ds.where(ds.max("v32"), "other")))
+    assert_agg_equal(both["m"].data, ora.points(cols, "x", "y", ("max", "v32"), view), "summary max")
+    assert_agg_equal(both["w"].data, ora.points(cols, "x", "y", ("where", ("max", "v32"), "other"), view), "summary where")
+    # a frame 1e7 from the origin: the float32 fast mapping is off, every row takes the exact mapping (k_points_match32_exact)
+    far = dict(cols)
+    far["x"] = (cols["x"] * 64 + np.float32(1e7)).astype(np.float32)
+    fframe = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in far.items()})
+    fview = ora.make_view(64, 48, (1e7, 1e7 + 64.0), (0.0, 1.0))
+    got = ds.Canvas(64, 48, x_range=(1e7, 1e7 + 64.0), y_range=(0.0, 1.0)).points(fframe, "x", "y", ds.where(ds.max("v32"))).data
+    assert b"k_points_match32_exact" in _lib.lib().dsb_last_kernel(), _lib.lib().dsb_last_kernel()
+    assert_agg_equal(got, ora.points(far, "x", "y", ("where", ("max", "v32"), None), fview), "two-pass exact mapping")
+    # -0.0 and +0.0 tie (reductions.py:1224: strict compare): the earliest of them is the row
+    z = {"x": np.full(6, 0.5, np.float32), "y": np.full(6, 0.5, np.float32),
+         "v32": np.array([-1.0, -0.0, 0.0, -0.0, np.nan, -2.0], np.float32), "other": np.arange(6, dtype=np.float32)}
+    zf = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in z.items()})
+    got = ds.Canvas(2, 2, x_range=(0.0, 1.0), y_range=(0.0, 1.0)).points(zf, "x", "y", ds.where(ds.max("v32"))).data
+    assert got[1, 1] == 1 and (got.ravel()[[0, 1, 2]] == -1).all()
+
+
 def test_routed_equals_banded_at_production_geometry():
     """8192 x 8192, 1e8 points, real budgets: the routed path, the L2-banded mono kernels and the unbanded generic kernel
     agree bit for bit on max / first / count (BASELINE config 5's geometry)."""
@@ -197,8 +235,19 @@ def test_routed_equals_banded_at_production_geometry():
                 same = torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)) if a.dtype.is_floating_point else torch.equal(a, b)
                 assert same, f"{agg} routed vs {mode}"
             del res
+        # where(max): the two-pass form (routed max + dsb_points_match32) against the packed {key, row} accumulator, L2-banded
+        rows = {}
+        ds.config.routed = True
+        _lib.check(L.dsb_configure(b"l2_band_bytes", 96 << 20))
+        _lib.check(L.dsb_configure(b"mono", 1))
+        for two in (True, False):
+            ds.config.where_two_pass = two
+            rows[two] = cvs.points(frame, "x", "y", ds.where(ds.max("value"))).data.clone()
+            assert (b"k_points_match32<" in L.dsb_last_kernel()) == two, L.dsb_last_kernel()
+        assert torch.equal(rows[True], rows[False]), "where(max): two-pass vs packed accumulator"
     finally:
         ds.config.device_results = False
         ds.config.routed = True
+        ds.config.where_two_pass = True
         _lib.check(L.dsb_configure(b"l2_band_bytes", 96 << 20))
         _lib.check(L.dsb_configure(b"mono", 1))
