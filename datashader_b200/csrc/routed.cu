@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "fastmap.cuh"
 #include <limits.h>
+#include <stdlib.h>
 
 enum { R_MAX32 = 0, R_MIN32 = 1, R_MINROW = 2, R_MAXROW = 3, R_COUNT = 4 };
 
@@ -41,7 +42,13 @@ struct RouteArgs {
   uint32_t slow_cap;                    //   mapped exactly by k_route_slow (12-byte entries: it streams them instead of gathering rows)
   void* canvas;
   unsigned int* notes;
-};
+  const unsigned long long* gate;       // first / last, rest of the rows (dsb_points_routed): {sampled rows, sampled rows whose pixel is still open};
+};                                      //   the routed kernels run only if the sample says the filter would not pay (route_gate_open)
+
+// first / last: the routed pass over the REST of the rows is the fallback of the filtered pass (k_rows_rest); both are launched and
+// the sample decides on the device which of them does the work - no host round trip
+__device__ __forceinline__ bool rest_wants_route(const unsigned long long* g) { return g[1] * 8ull > g[0]; }
+__device__ __forceinline__ bool route_gate_closed(const RouteArgs& a) { return a.gate != nullptr && !rest_wants_route(a.gate); }
 
 // bucket << 16 | cell in bucket.  The bucket is cell / cpb by multiplication with m = ceil(2^(32 + sh) / cpb): exact for every
 // cell below ncell because ncell * (m * cpb - 2^(32 + sh)) < 2^(32 + sh) (checked on the host, dsb_points_routed); the key
@@ -65,6 +72,7 @@ __device__ __forceinline__ void route_direct(const RouteArgs& a, uint32_t cell, 
 __global__ void __launch_bounds__(256) k_route_sample(const RouteArgs a, long long stride_blocks, uint32_t* __restrict__ hist) {
   // every stride_blocks-th block of 256 vectors (4 KB per column, fully used sectors) is mapped and histogrammed
   extern __shared__ uint32_t sh[];
+  if (route_gate_closed(a)) return;
   for (uint32_t b = threadIdx.x; b < a.nb; b += blockDim.x) sh[b] = 0;
   __syncthreads();
   const float4* __restrict__ x4 = (const float4*)a.x;
@@ -127,6 +135,7 @@ __global__ void __launch_bounds__(1024) k_route_plan(const uint32_t* __restrict_
 template <int OP>
 __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ RouteArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
+  if (route_gate_closed(a)) return;
   const uint32_t nbp = (a.nb + 2) & ~1u;                               // + the dummy bucket a.nb: filtered rows, no branch per point
   unsigned long long* rec = (unsigned long long*)smem;                 // [RTILE]
   uint4* run_of = (uint4*)(rec + RTILE);                               // [nbp] per bucket: {&recs[global offset of this tile's run
@@ -273,6 +282,7 @@ __global__ void __launch_bounds__(RT, 2) k_route_bin(const __grid_constant__ Rou
 // the rows pass 1 could not place with the float32 mapping: exact f64 mapping, straight to the canvas
 template <int OP>
 __global__ void __launch_bounds__(256) k_route_slow(const __grid_constant__ RouteArgs a) {
+  if (route_gate_closed(a)) return;
   const uint32_t n = min(*a.slow_n, a.slow_cap);
   bool negzero = false;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -313,6 +323,7 @@ constexpr uint32_t RE_STAGES = 3;          // chunks in flight per SM (48 KB) ne
 template <int OP, bool TMA>
 __global__ void __launch_bounds__(1024, 1) k_route_eat(const __grid_constant__ RouteArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
+  if (route_gate_closed(a)) return;
   uint32_t* tile = (uint32_t*)smem;
   __shared__ uint32_t next;
   __shared__ __align__(8) unsigned long long bars[RE_STAGES];
@@ -406,7 +417,169 @@ __global__ void __launch_bounds__(1024, 1) k_route_eat(const __grid_constant__ R
 }
 
 // ---- entry points ------------------------------------------------------------------------------------------------------
+// ---- first / last: only the head (tail) of the rows can win ---------------------------------------------------------------
+// first = the smallest row id of a pixel (reductions.py:2318-2324, 1346-1360).  Once a pixel holds a row of the HEAD of the call
+// (its first ~10 rows per canvas cell, routed as above), no later row can replace it - and with 60 rows per pixel (config 5) that is
+// every pixel but a handful.  The REST of the rows is therefore only tested against a bitmap of the pixels the head left open
+// (1 bit per pixel: 8 MB at 8192^2, L2-resident): x and y are streamed (8 B/row), the row is dropped after one L2 hit, and the few
+// rows of open pixels check their NaN column and vote with an atomic.  last = the largest row id: the same from the tail.
+// Exact for any data; data whose head does not cover the canvas (rows sorted in space) would send most of the rest to DRAM
+// atomics, so a sample of the rest decides ON THE DEVICE between this pass and the routed pass over the rest (RouteArgs::gate).
+struct RestArgs {
+  dsb_view v;
+  FastMap fm;
+  const float* x; const float* y; const float* chk;
+  long long n, row_offset;          // the rest: rows [0, n) of these pointers, global row = row_offset + i
+  long long* canvas;
+  uint32_t* bits;                   // [ceil(ncell / 32)] 1 = the pixel is settled
+  uint32_t* blocks;                 // [ceil(cw * ch / 32)] 1 = every pixel of the 2^bs x 2^bs block is settled (16 x 16 blocks, 32 KB at 8192^2:
+  int cw, ch, bs;                   //   every CTA of k_rows_rest keeps a copy in shared memory)
+  unsigned long long* gate;         // {sampled rows, sampled rows of open pixels}
+  long long limit;                  // first: rows below it settle a pixel; last: rows at or above it
+  long long ncell;
+};
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_rows_settled(const RestArgs a) {
+  const long long nw = (a.ncell + 31) >> 5;
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nw; w += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long c = (w << 5) + (threadIdx.x & 31);
+    bool done = false;
+    if (c < a.ncell) { const long long r = a.canvas[c]; done = FIRST ? r < a.limit : r >= a.limit; }
+    const uint32_t m = __ballot_sync(0xffffffffu, done);
+    if ((threadIdx.x & 31) == 0) a.bits[w] = m;
+  }
+}
+
+// a 2^bs x 2^bs block is settled when all of its pixels are (pixels beyond the canvas edge count as settled); one warp per block
+__global__ void __launch_bounds__(256) k_rows_settled_blocks(const RestArgs a) {
+  const long long nblk = (long long)a.cw * a.ch, nbw = (nblk + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nbw; w += (long long)gridDim.x * (blockDim.x >> 5)) {
+    uint32_t word = 0;
+    for (int j = 0; j < 32; j++) {
+      const long long b = (w << 5) + j;
+      bool all = true;
+      if (b < nblk) {
+        const int bx = (int)(b % a.cw), by = (int)(b / a.cw);
+        for (int p = lane; p < (1 << (2 * a.bs)); p += 32) {
+          const int px = (bx << a.bs) + (p & ((1 << a.bs) - 1)), py = (by << a.bs) + (p >> a.bs);
+          if (px < a.v.width && py < a.v.height) {
+            const long long c = (long long)py * a.v.width + px;
+            all = all && ((a.bits[c >> 5] >> (c & 31)) & 1u);
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, all) && b < nblk) word |= 1u << j;
+    }
+    if (lane == 0) a.blocks[w] = word;
+  }
+}
+
+// every 64th block of 1024 rows of the rest: how many land on the canvas, how many of those on a pixel that is still open
+__global__ void __launch_bounds__(256) k_rows_rest_sample(const RestArgs a, long long stride_blocks) {
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const long long n4 = a.n >> 2;
+  uint32_t tot = 0, open = 0;
+  for (long long blk = blockIdx.x; blk * stride_blocks * 256 < n4; blk += gridDim.x) {
+    const long long i4 = blk * stride_blocks * 256 + threadIdx.x;
+    if (i4 >= n4) continue;
+    const float4 xa = __ldg(x4 + i4), ya = __ldg(y4 + i4);
+    const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float xf = fmaf(xs[k], a.fm.sx, a.fm.tx), yf = fmaf(ys[k], a.fm.sy, a.fm.ty);
+      const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+      if ((uint32_t)xi < (uint32_t)a.v.width && (uint32_t)yi < (uint32_t)a.v.height) {        // an estimate: the fast pixel is enough
+        const uint32_t cell = (uint32_t)(yi * a.v.width + xi);
+        tot++;
+        open += ((__ldg(a.bits + (cell >> 5)) >> (cell & 31)) & 1u) ^ 1u;
+      }
+    }
+  }
+  tot = __reduce_add_sync(0xffffffffu, tot); open = __reduce_add_sync(0xffffffffu, open);
+  if ((threadIdx.x & 31) == 0 && tot) { atomicAdd(a.gate, (unsigned long long)tot); atomicAdd(a.gate + 1, (unsigned long long)open); }
+}
+
+template <bool FIRST, int PPT, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) k_rows_rest(const __grid_constant__ RestArgs a) {
+  extern __shared__ uint32_t blocks[];                         // the block map: a random 4-byte read per row costs a few bank conflicts
+  if (rest_wants_route(a.gate)) return;                        //   here, but one L1 tag lookup per LANE as a global load (measured: 279 Gpts/s)
+  for (int w = threadIdx.x; w < (a.cw * a.ch + 31) >> 5; w += blockDim.x) blocks[w] = a.blocks[w];
+  __syncthreads();
+  const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
+  const FastMap& fm = a.fm;
+  const uint32_t* __restrict__ bits = a.bits;
+  const int bs = a.bs;
+  auto vote = [&](int cell, long long i) {                     // an open pixel: NaN rows are skipped (the nan-check column), the rest vote
+    const float c = a.chk[i];
+    if (c != c) return;
+    if (FIRST) atomicMin(a.canvas + cell, a.row_offset + i); else atomicMax(a.canvas + cell, a.row_offset + i);
+  };
+  auto exact = [&](float xv, float yv, long long i) {          // rows near a pixel edge: exact f64 mapping
+    const int cell = map_exact_linear(a.v, xv, yv);
+    if (cell >= 0 && !((__ldg(bits + (cell >> 5)) >> (cell & 31)) & 1u)) vote(cell, i);
+  };
+  constexpr int NV = PPT / 4;
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const long long n4 = a.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += NV * stride) {
+    float xs[PPT], ys[PPT];
+#pragma unroll
+    for (int u = 0; u < NV; u++) {
+      const long long q = i4 + u * stride;
+      const bool in = q < n4;
+      const float4 xa = in ? __ldcs(x4 + q) : nan4, ya = in ? __ldcs(y4 + q) : nan4;
+      xs[4 * u] = xa.x; xs[4 * u + 1] = xa.y; xs[4 * u + 2] = xa.z; xs[4 * u + 3] = xa.w;
+      ys[4 * u] = ya.x; ys[4 * u + 1] = ya.y; ys[4 * u + 2] = ya.z; ys[4 * u + 3] = ya.w;
+    }
+    int cell[PPT];
+    uint32_t bword[PPT], bsh[PPT];
+    uint32_t okm = 0, slow = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {                   // the K2-tight mapping: see k_points_priv_tight
+      const float xf = fmaf(xs[k], fm.sx, fm.tx), yf = fmaf(ys[k], fm.sy, fm.ty);
+      const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+      const float dx = xf - (float)xi, dy = yf - (float)yi;
+      const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
+      const bool ok = sure && (uint32_t)xi < W && (uint32_t)yi < H;
+      cell[k] = ok ? yi * (int)W + xi : 0;
+      const int b = ok ? (yi >> bs) * a.cw + (xi >> bs) : 0;
+      bword[k] = blocks[b >> 5];
+      bsh[k] = (uint32_t)b & 31u;
+      okm |= (uint32_t)ok << k;
+      slow |= (uint32_t)(!sure && xs[k] == xs[k] && ys[k] == ys[k]) << k;
+    }
+    uint32_t open = 0;                                // rows of blocks that still hold an open pixel: ~8 % after 8 rows per cell
+#pragma unroll
+    for (int k = 0; k < PPT; k++) open |= (((bword[k] >> bsh[k]) & 1u) ^ 1u) << k;
+    open &= okm;
+    if (open | slow) {
+      uint32_t cword[PPT];                            // the pixels' own bits: independent L2 hits, all in flight before the first vote
+#pragma unroll
+      for (int k = 0; k < PPT; k++) cword[k] = (open >> k) & 1u ? __ldg(bits + (cell[k] >> 5)) : 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const long long i = 4 * (i4 + (k >> 2) * stride) + (k & 3);
+        if ((open >> k) & 1u) { if (!((cword[k] >> (cell[k] & 31)) & 1u)) vote(cell[k], i); }
+        else if ((slow >> k) & 1u) exact(xs[k], ys[k], i);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {           // tail rows
+    const long long i = (n4 << 2) + threadIdx.x;
+    exact(a.x[i], a.y[i], i);
+  }
+}
+
 static long long g_routed_min_rows = 1LL << 24;
+static long long g_head_per_cell = 10;          // first / last: rows per canvas cell that are routed before the rest is only filtered (0 = off);
+                                                // 6 / 8 / 10 / 12 / 16 at 8192^2, 4e9 rows: 25.7 / 19.5 / 17.7 / 17.5 / 19.0 ms (tools/bench_first.py)
+void dsb_routed_set_head(long long rows_per_cell) { g_head_per_cell = rows_per_cell; }
 static bool g_routed_tma = true;
 void dsb_routed_set_tma(bool on) { g_routed_tma = on; }
 
@@ -421,12 +594,25 @@ static size_t route_header_bytes(uint32_t nb) { return (((size_t)nb * (8 + 4 + 4
 static size_t route_slow_entries(int64_t n) { return (size_t)(n / 32) + 65536; }        // ~3 % of the rows (0.8 % at 8192^2, less on smaller canvases)
 static size_t route_fixed_bytes(uint32_t nb, int64_t n) { return route_header_bytes(nb) + ((route_slow_entries(n) * 12 + 255) & ~(size_t)255); }
 
+static size_t route_rest_cell_bits_bytes(long long ncell) { return (size_t)((((ncell + 31) >> 5) * 4 + 255) & ~255LL); }
+// blocks of 16 x 16 pixels, or the smallest power of two whose bitmap fits 32 KB of shared memory (6 CTAs per SM)
+static int route_rest_block_shift(long long W, long long H) {
+  int bs = 4;
+  while ((((W + (1LL << bs) - 1) >> bs) * ((H + (1LL << bs) - 1) >> bs)) > 32 * 1024 * 8) bs++;
+  return bs;
+}
+// gate counters (256 B) + a bit per pixel + a bit per block
+static size_t route_rest_bytes(long long W, long long H) {
+  return 256 + route_rest_cell_bits_bytes(W * H) + 32 * 1024 + 256;
+}
+
 extern "C" int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t n) {
   if (!view || view->width <= 0 || view->height <= 0 || n < 0) return 0;
   uint32_t cpb;
   const uint32_t nb = route_nb((long long)view->width * view->height, &cpb);
   // records: 1.10 n + 4096 per bucket (k_route_plan scales the capacities down to whatever it is given)
-  return (int64_t)(route_fixed_bytes(nb, n) + ((size_t)((double)n * 1.10) + (size_t)nb * 4096 + 1024) * 8);   // + the floor dsb_points_routed asks for
+  // + the floor dsb_points_routed asks for, + first / last: a bit per pixel and the gate counters
+  return (int64_t)(route_fixed_bytes(nb, n) + ((size_t)((double)n * 1.10) + (size_t)nb * 4096 + 1024) * 8 + route_rest_bytes(view->width, view->height));
 }
 
 template <int OP>
@@ -441,11 +627,12 @@ static void route_launch(const RouteArgs& a, size_t smem1, size_t smem2, cudaStr
   else k_route_eat<OP, false><<<dsb_num_sms(), 1024, smem2, s>>>(a);
 }
 
-extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
-                                 const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream) {
+// one routed aggregation (sample, plan, bin, slow, eat) of rows [0, n); gate != NULL: the device decides whether it runs
+static int route_one(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                     const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream, const unsigned long long* gate) {
   if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points_routed: bad view"); return DSB_ERR_ARG; }
   if (!plan || plan->nops != 1 || plan->ncat != 0) { dsb_set_error("dsb_points_routed: one accumulator, no categories"); return DSB_ERR_UNSUPPORTED; }
-  if (n < g_routed_min_rows || n >= (1LL << 32) - 1) { dsb_set_error("dsb_points_routed: n out of range"); return DSB_ERR_UNSUPPORTED; }
+  if (n <= 0 || n >= (1LL << 32) - 1) { dsb_set_error("dsb_points_routed: n out of range"); return DSB_ERR_UNSUPPORTED; }
   if (!x || !y || !scratch) { dsb_set_error("dsb_points_routed: null pointer"); return DSB_ERR_ARG; }
   const dsb_base& b = plan->ops[0];
   if (!b.agg) { dsb_set_error("dsb_points_routed: op has no canvas"); return DSB_ERR_ARG; }
@@ -501,7 +688,7 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   a.slow = (uint32_t*)(p + route_header_bytes(a.nb));
   a.slow_cap = (uint32_t)route_slow_entries(n);
   a.recs = (unsigned long long*)(p + hdr);
-  a.off = off; a.cap = cap; a.cursor = cursor; a.queue = queue; a.canvas = b.agg; a.notes = plan->notes;
+  a.off = off; a.cap = cap; a.cursor = cursor; a.queue = queue; a.canvas = b.agg; a.notes = plan->notes; a.gate = gate;
   const unsigned long long capacity = ((unsigned long long)scratch_bytes - hdr) / 8 - 4096;   // k_route_plan rounds every thread's start up
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(hist, 0, (size_t)a.nb * 4, s);
@@ -521,5 +708,53 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
     default: route_launch<R_COUNT>(a, smem1, smem2, s); break;
   }
   DSB_CUDA_CHECK_LAUNCH("dsb_points_routed");
+  return DSB_OK;
+}
+
+extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                                 const dsb_plan* plan, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (n < g_routed_min_rows) { dsb_set_error("dsb_points_routed: n out of range"); return DSB_ERR_UNSUPPORTED; }
+  const bool rowop = plan && plan->nops == 1 && (plan->ops[0].op == DSB_OP_MINROW || plan->ops[0].op == DSB_OP_MAXROW);
+  const long long ncell = view ? (long long)view->width * view->height : 0;
+  const long long head = (g_head_per_cell * ncell + 3) & ~3LL;
+  const size_t rest_bytes = view ? route_rest_bytes(view->width, view->height) : 0;
+  if (!rowop || g_head_per_cell <= 0 || head < 4 || n < 2 * head || !scratch || scratch_bytes < (int64_t)rest_bytes + (1 << 20) ||
+      plan->ops[0].chk_dtype != DSB_F32 || !plan->ops[0].chk || xy_dtype != DSB_F32 || !x || !y)
+    return route_one(view, x, y, xy_dtype, n, row_offset, plan, scratch, scratch_bytes, stream, nullptr);
+
+  // first / last with many rows per pixel: route the head (tail) of the rows, only filter the rest (see k_rows_rest)
+  const bool first = plan->ops[0].op == DSB_OP_MINROW;
+  const long long n_rest = first ? n - head : (n - head) & ~3LL;          // both parts start 16-byte aligned
+  const long long n_head = n - n_rest;
+  const long long off_head = first ? 0 : n_rest, off_rest = first ? n_head : 0;
+  const int64_t routed_bytes = (scratch_bytes - (int64_t)rest_bytes) & ~(int64_t)255;
+  unsigned char* tailp = (unsigned char*)scratch + routed_bytes;
+  const float* xf = (const float*)x; const float* yf = (const float*)y; const float* cf = (const float*)plan->ops[0].chk;
+  dsb_plan ph = *plan, pr = *plan;
+  ph.ops[0].chk = cf + off_head; pr.ops[0].chk = cf + off_rest;
+  int rc = route_one(view, xf + off_head, yf + off_head, xy_dtype, n_head, row_offset + off_head, &ph, scratch, routed_bytes, stream, nullptr);
+  if (rc != DSB_OK) return rc;                          // nothing was launched: the caller takes the banded kernels
+  RestArgs r;
+  r.v = *view; r.fm = make_fast_map(view);
+  r.x = xf + off_rest; r.y = yf + off_rest; r.chk = cf + off_rest; r.n = n_rest; r.row_offset = row_offset + off_rest;
+  r.canvas = (long long*)plan->ops[0].agg; r.ncell = ncell;
+  r.gate = (unsigned long long*)tailp; r.bits = (uint32_t*)(tailp + 256);
+  r.blocks = (uint32_t*)(tailp + 256 + route_rest_cell_bits_bytes(ncell));
+  r.bs = route_rest_block_shift(view->width, view->height);
+  r.cw = (int)((view->width + (1LL << r.bs) - 1) >> r.bs); r.ch = (int)((view->height + (1LL << r.bs) - 1) >> r.bs);
+  const size_t rest_smem = (size_t)(((long long)r.cw * r.ch + 31) >> 5) * 4;
+  r.limit = first ? row_offset + n_head : row_offset + off_head;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(r.gate, 0, 16, s);
+  const long long stride_blocks = n_rest >= (1LL << 28) ? 64 : 16;
+  if (first) k_rows_settled<true><<<dsb_num_sms() * 8, 256, 0, s>>>(r); else k_rows_settled<false><<<dsb_num_sms() * 8, 256, 0, s>>>(r);
+  k_rows_settled_blocks<<<dsb_num_sms() * 8, 256, 0, s>>>(r);
+  k_rows_rest_sample<<<dsb_num_sms() * 4, 256, 0, s>>>(r, stride_blocks);
+  // 4 rows per thread per step, 6 CTAs of 256 threads per SM: the best of seven shapes (gpurun_out/rest_sweep.log)
+  if (first) k_rows_rest<true, 4, 6><<<dsb_num_sms() * 6, 256, rest_smem, s>>>(r); else k_rows_rest<false, 4, 6><<<dsb_num_sms() * 6, 256, rest_smem, s>>>(r);
+  rc = route_one(view, r.x, r.y, xy_dtype, n_rest, r.row_offset, &pr, scratch, routed_bytes, stream, r.gate);   // the gated fallback
+  if (rc != DSB_OK) return rc;
+  dsb_note_kernel("k_rows_rest<%s> after k_route_bin + k_route_eat<%s> of %lld head rows", first ? "first" : "last", first ? "minrow" : "maxrow", n_head);
+  DSB_CUDA_CHECK_LAUNCH("dsb_points_routed(rest)");
   return DSB_OK;
 }

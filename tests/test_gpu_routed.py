@@ -203,6 +203,69 @@ def test_where_two_pass_matches_oracle(routed, shape, n, clustered):
     assert got[1, 1] == 1 and (got.ravel()[[0, 1, 2]] == -1).all()
 
 
+@pytest.mark.parametrize("order", ["shuffled", "sorted_by_y", "reverse_sorted"])
+def test_first_last_head_then_filtered_rest(routed, order):
+    """first / last / where(first | last) with the rows split into a routed head (tail) and a filtered rest (k_rows_rest), forced
+    on at small n: shuffled rows (the head settles nearly every pixel: the filter does the rest) and rows sorted in space (the head
+    covers a strip of the canvas, the device-side sample hands the rest to the routed kernels) against the oracle."""
+    import torch
+    from datashader_b200 import _lib
+    from oracle import oracle as ora
+    ds = routed
+    L = _lib.lib()
+    W, H, n = 301, 257, 400_003
+    cols = _cols(np.random.default_rng(99), n)
+    if order != "shuffled":
+        idx = np.argsort(cols["y"], kind="stable")
+        if order == "reverse_sorted":
+            idx = idx[::-1]
+        cols = {k: np.ascontiguousarray(v[idx]) for k, v in cols.items()}
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    _lib.check(L.dsb_configure(b"routed_head_per_cell", 1))          # head = one row per canvas cell (77 357 rows)
+    try:
+        for name in ("first_v32", "last_v32", "where_first_v32_other", "where_last_v32_row"):
+            got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
+            assert b"k_rows_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
+            assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view, npartitions=2), f"head + rest {name} {order}")
+    finally:
+        _lib.check(L.dsb_configure(b"routed_head_per_cell", 10))
+
+
+def test_first_last_split_equals_banded_at_production_scale():
+    """4096 x 4096 (134 MB of row ids: beyond L2), 1e8 points, head = 2 rows per cell: the split form against the L2-banded kernels."""
+    import torch
+    import datashader_b200 as ds
+    from datashader_b200 import _lib
+    L = _lib.lib()
+    n = 100_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(6)
+    x = torch.rand(n, generator=g, device="cuda") * 1.02 - 0.01
+    y = torch.rand(n, generator=g, device="cuda") * 1.02 - 0.01
+    v = torch.randn(n, generator=g, device="cuda")
+    v[::13] = float("nan")
+    frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
+    cvs = ds.Canvas(4096, 4096, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    ds.config.device_results = True
+    _lib.check(L.dsb_configure(b"routed_head_per_cell", 2))
+    try:
+        for agg in (ds.first("value"), ds.last("value"), ds.where(ds.first("value"))):
+            res = {}
+            for mode in ("split", "banded"):
+                ds.config.routed = mode == "split"
+                res[mode] = cvs.points(frame, "x", "y", agg).data.clone()
+                assert (b"k_rows_rest<" in L.dsb_last_kernel()) == (mode == "split"), (mode, L.dsb_last_kernel())
+            a, b = res["split"], res["banded"]
+            same = torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)) if a.dtype.is_floating_point else torch.equal(a, b)
+            assert same, f"{agg} split vs banded"
+    finally:
+        ds.config.device_results = False
+        ds.config.routed = True
+        _lib.check(L.dsb_configure(b"routed_head_per_cell", 10))
+
+
 def test_routed_equals_banded_at_production_geometry():
     """8192 x 8192, 1e8 points, real budgets: the routed path, the L2-banded mono kernels and the unbanded generic kernel
     agree bit for bit on max / first / count (BASELINE config 5's geometry)."""
