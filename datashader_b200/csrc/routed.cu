@@ -432,7 +432,7 @@ struct RestArgs {
   long long n, row_offset;          // the rest: rows [0, n) of these pointers, global row = row_offset + i
   long long* canvas;
   uint32_t* bits;                   // [ceil(ncell / 32)] 1 = the pixel is settled
-  uint32_t* blocks;                 // [ceil(cw * ch / 32)] 1 = every pixel of the 2^bs x 2^bs block is settled (16 x 16 blocks, 32 KB at 8192^2:
+  uint32_t* blocks;                 // [ceil(cw * ch / 32)] 1 = every pixel of the 2^bs x 2^bs block is settled (8 x 8 blocks, 128 KB at 8192^2:
   int cw, ch, bs;                   //   every CTA of k_rows_rest keeps a copy in shared memory)
   unsigned long long* gate;         // {sampled rows, sampled rows of open pixels}
   long long limit;                  // first: rows below it settle a pixel; last: rows at or above it
@@ -502,77 +502,86 @@ __global__ void __launch_bounds__(256) k_rows_rest_sample(const RestArgs a, long
   if ((threadIdx.x & 31) == 0 && tot) { atomicAdd(a.gate, (unsigned long long)tot); atomicAdd(a.gate + 1, (unsigned long long)open); }
 }
 
-template <bool FIRST, int PPT, int CTAS>
-__global__ void __launch_bounds__(256, CTAS) k_rows_rest(const __grid_constant__ RestArgs a) {
+template <bool FIRST, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) k_rows_rest(const __grid_constant__ RestArgs a) {
   extern __shared__ uint32_t blocks[];                         // the block map: a random 4-byte read per row costs a few bank conflicts
-  if (rest_wants_route(a.gate)) return;                        //   here, but one L1 tag lookup per LANE as a global load (measured: 279 Gpts/s)
+  if (rest_wants_route(a.gate)) return;                        // the routed kernels take the rest
   for (int w = threadIdx.x; w < (a.cw * a.ch + 31) >> 5; w += blockDim.x) blocks[w] = a.blocks[w];
   __syncthreads();
   const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
   const FastMap& fm = a.fm;
   const uint32_t* __restrict__ bits = a.bits;
-  const int bs = a.bs;
-  auto vote = [&](int cell, long long i) {                     // an open pixel: NaN rows are skipped (the nan-check column), the rest vote
+  const int bs = a.bs, cw = a.cw;
+  // The loop of k_points_priv_tight: two vectors (8 rows) per thread per step, every row finished as it is mapped, nothing but
+  // two mask bits kept per row.  bit 0: the fast pixel is certain, on the canvas, and its block still holds an open pixel;
+  // bit 8: the fast pixel is not certain (near a pixel edge, NaN, inf).  The instruction count of this kernel is its bound
+  // (ncu: 65 % of the issue slots busy), and the rows that need a closer look cost a whole warp each time ONE lane has one:
+  // the block map is therefore as fine as shared memory allows (8 x 8 pixels at 8192^2) and the closer look is cheap.
+  auto one = [&](float xv, float yv) -> uint32_t {
+    const float xf = fmaf(xv, fm.sx, fm.tx), yf = fmaf(yv, fm.sy, fm.ty);
+    const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+    const float dx = xf - (float)xi, dy = yf - (float)yi;
+    const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
+    const bool inside = (uint32_t)xi < W && (uint32_t)yi < H;
+    const int b = inside ? (yi >> bs) * cw + (xi >> bs) : 0;
+    const uint32_t open = ((blocks[b >> 5] >> (b & 31)) & 1u) ^ 1u;
+    return sure ? (uint32_t)inside & open : 0x100u;
+  };
+  auto vote = [&](int cell, long long i) {                     // the pixel's own bit (L2), the NaN check, the vote
+    if ((__ldg(bits + (cell >> 5)) >> (cell & 31)) & 1u) return;
     const float c = a.chk[i];
     if (c != c) return;
     if (FIRST) atomicMin(a.canvas + cell, a.row_offset + i); else atomicMax(a.canvas + cell, a.row_offset + i);
   };
-  auto exact = [&](float xv, float yv, long long i) {          // rows near a pixel edge: exact f64 mapping
-    const int cell = map_exact_linear(a.v, xv, yv);
-    if (cell >= 0 && !((__ldg(bits + (cell >> 5)) >> (cell & 31)) & 1u)) vote(cell, i);
+  auto open_row = [&](float xv, float yv, long long i) {       // a certain pixel of an open block: the fast pixel again, 6 instructions
+    const int xi = __float2int_rd(fmaf(xv, fm.sx, fm.tx)), yi = __float2int_rd(fmaf(yv, fm.sy, fm.ty));
+    vote(yi * (int)W + xi, i);
   };
-  constexpr int NV = PPT / 4;
+  auto closer = [&](float xv, float yv, long long i) {         // ~0.07 % of the rows: the exact f64 mapping
+    const int cell = map_exact_linear(a.v, xv, yv);
+    if (cell >= 0) vote(cell, i);
+  };
   const float4* __restrict__ x4 = (const float4*)a.x;
   const float4* __restrict__ y4 = (const float4*)a.y;
   const long long n4 = a.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const float4 nan4 = make_float4(NAN, NAN, NAN, NAN);
-  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += NV * stride) {
-    float xs[PPT], ys[PPT];
-#pragma unroll
-    for (int u = 0; u < NV; u++) {
-      const long long q = i4 + u * stride;
-      const bool in = q < n4;
-      const float4 xa = in ? __ldcs(x4 + q) : nan4, ya = in ? __ldcs(y4 + q) : nan4;
-      xs[4 * u] = xa.x; xs[4 * u + 1] = xa.y; xs[4 * u + 2] = xa.z; xs[4 * u + 3] = xa.w;
-      ys[4 * u] = ya.x; ys[4 * u + 1] = ya.y; ys[4 * u + 2] = ya.z; ys[4 * u + 3] = ya.w;
-    }
-    int cell[PPT];
-    uint32_t bword[PPT], bsh[PPT];
-    uint32_t okm = 0, slow = 0;
-#pragma unroll
-    for (int k = 0; k < PPT; k++) {                   // the K2-tight mapping: see k_points_priv_tight
-      const float xf = fmaf(xs[k], fm.sx, fm.tx), yf = fmaf(ys[k], fm.sy, fm.ty);
-      const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
-      const float dx = xf - (float)xi, dy = yf - (float)yi;
-      const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
-      const bool ok = sure && (uint32_t)xi < W && (uint32_t)yi < H;
-      cell[k] = ok ? yi * (int)W + xi : 0;
-      const int b = ok ? (yi >> bs) * a.cw + (xi >> bs) : 0;
-      bword[k] = blocks[b >> 5];
-      bsh[k] = (uint32_t)b & 31u;
-      okm |= (uint32_t)ok << k;
-      slow |= (uint32_t)(!sure && xs[k] == xs[k] && ys[k] == ys[k]) << k;
-    }
-    uint32_t open = 0;                                // rows of blocks that still hold an open pixel: ~8 % after 8 rows per cell
-#pragma unroll
-    for (int k = 0; k < PPT; k++) open |= (((bword[k] >> bsh[k]) & 1u) ^ 1u) << k;
-    open &= okm;
-    if (open | slow) {
-      uint32_t cword[PPT];                            // the pixels' own bits: independent L2 hits, all in flight before the first vote
-#pragma unroll
-      for (int k = 0; k < PPT; k++) cword[k] = (open >> k) & 1u ? __ldg(bits + (cell[k] >> 5)) : 0xffffffffu;
-#pragma unroll
-      for (int k = 0; k < PPT; k++) {
-        const long long i = 4 * (i4 + (k >> 2) * stride) + (k & 3);
-        if ((open >> k) & 1u) { if (!((cword[k] >> (cell[k] & 31)) & 1u)) vote(cell[k], i); }
-        else if ((slow >> k) & 1u) exact(xs[k], ys[k], i);
+  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i4 + stride < n4; i4 += 2 * stride) {
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
+    const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride);
+    const uint32_t m = one(xa.x, ya.x) | one(xa.y, ya.y) << 1 | one(xa.z, ya.z) << 2 | one(xa.w, ya.w) << 3 |
+                       one(xb.x, yb.x) << 4 | one(xb.y, yb.y) << 5 | one(xb.z, yb.z) << 6 | one(xb.w, yb.w) << 7;
+    if (m) {
+      const long long ia = 4 * i4, ib = 4 * (i4 + stride);
+      if (m & 0xff) {
+        if (m & 1) open_row(xa.x, ya.x, ia);
+        if (m & 2) open_row(xa.y, ya.y, ia + 1);
+        if (m & 4) open_row(xa.z, ya.z, ia + 2);
+        if (m & 8) open_row(xa.w, ya.w, ia + 3);
+        if (m & 16) open_row(xb.x, yb.x, ib);
+        if (m & 32) open_row(xb.y, yb.y, ib + 1);
+        if (m & 64) open_row(xb.z, yb.z, ib + 2);
+        if (m & 128) open_row(xb.w, yb.w, ib + 3);
+      }
+      if (m >> 8) {
+        if (m & 0x100) closer(xa.x, ya.x, ia);
+        if (m & 0x200) closer(xa.y, ya.y, ia + 1);
+        if (m & 0x400) closer(xa.z, ya.z, ia + 2);
+        if (m & 0x800) closer(xa.w, ya.w, ia + 3);
+        if (m & 0x1000) closer(xb.x, yb.x, ib);
+        if (m & 0x2000) closer(xb.y, yb.y, ib + 1);
+        if (m & 0x4000) closer(xb.z, yb.z, ib + 2);
+        if (m & 0x8000) closer(xb.w, yb.w, ib + 3);
       }
     }
   }
+  if (i4 < n4) {
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
+    closer(xa.x, ya.x, 4 * i4); closer(xa.y, ya.y, 4 * i4 + 1); closer(xa.z, ya.z, 4 * i4 + 2); closer(xa.w, ya.w, 4 * i4 + 3);
+  }
   if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {           // tail rows
     const long long i = (n4 << 2) + threadIdx.x;
-    exact(a.x[i], a.y[i], i);
+    closer(a.x[i], a.y[i], i);
   }
 }
 
@@ -595,15 +604,16 @@ static size_t route_slow_entries(int64_t n) { return (size_t)(n / 32) + 65536; }
 static size_t route_fixed_bytes(uint32_t nb, int64_t n) { return route_header_bytes(nb) + ((route_slow_entries(n) * 12 + 255) & ~(size_t)255); }
 
 static size_t route_rest_cell_bits_bytes(long long ncell) { return (size_t)((((ncell + 31) >> 5) * 4 + 255) & ~255LL); }
-// blocks of 16 x 16 pixels, or the smallest power of two whose bitmap fits 32 KB of shared memory (6 CTAs per SM)
+// blocks of 8 x 8 pixels, or the smallest power of two whose bitmap fits REST_MAP_BYTES of shared memory (one CTA per SM)
+constexpr long long REST_MAP_BYTES = 160 * 1024;
 static int route_rest_block_shift(long long W, long long H) {
-  int bs = 4;
-  while ((((W + (1LL << bs) - 1) >> bs) * ((H + (1LL << bs) - 1) >> bs)) > 32 * 1024 * 8) bs++;
+  int bs = 3;
+  while ((((W + (1LL << bs) - 1) >> bs) * ((H + (1LL << bs) - 1) >> bs)) > REST_MAP_BYTES * 8) bs++;
   return bs;
 }
 // gate counters (256 B) + a bit per pixel + a bit per block
 static size_t route_rest_bytes(long long W, long long H) {
-  return 256 + route_rest_cell_bits_bytes(W * H) + 32 * 1024 + 256;
+  return 256 + route_rest_cell_bits_bytes(W * H) + (size_t)REST_MAP_BYTES + 256;
 }
 
 extern "C" int64_t dsb_points_routed_scratch_bytes(const dsb_view* view, int64_t n) {
@@ -750,8 +760,9 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   if (first) k_rows_settled<true><<<dsb_num_sms() * 8, 256, 0, s>>>(r); else k_rows_settled<false><<<dsb_num_sms() * 8, 256, 0, s>>>(r);
   k_rows_settled_blocks<<<dsb_num_sms() * 8, 256, 0, s>>>(r);
   k_rows_rest_sample<<<dsb_num_sms() * 4, 256, 0, s>>>(r, stride_blocks);
-  // 4 rows per thread per step, 6 CTAs of 256 threads per SM: the best of seven shapes (gpurun_out/rest_sweep.log)
-  if (first) k_rows_rest<true, 4, 6><<<dsb_num_sms() * 6, 256, rest_smem, s>>>(r); else k_rows_rest<false, 4, 6><<<dsb_num_sms() * 6, 256, rest_smem, s>>>(r);
+  cudaFuncSetAttribute(k_rows_rest<true, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REST_MAP_BYTES);
+  cudaFuncSetAttribute(k_rows_rest<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REST_MAP_BYTES);
+  if (first) k_rows_rest<true, 1024, 1><<<dsb_num_sms(), 1024, rest_smem, s>>>(r); else k_rows_rest<false, 1024, 1><<<dsb_num_sms(), 1024, rest_smem, s>>>(r);
   rc = route_one(view, r.x, r.y, xy_dtype, n_rest, r.row_offset, &pr, scratch, routed_bytes, stream, r.gate);   // the gated fallback
   if (rc != DSB_OK) return rc;
   dsb_note_kernel("k_rows_rest<%s> after k_route_bin + k_route_eat<%s> of %lld head rows", first ? "first" : "last", first ? "minrow" : "maxrow", n_head);
