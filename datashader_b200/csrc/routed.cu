@@ -728,7 +728,8 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   const long long ncell = view ? (long long)view->width * view->height : 0;
   const long long head = (g_head_per_cell * ncell + 3) & ~3LL;
   const size_t rest_bytes = view ? route_rest_bytes(view->width, view->height) : 0;
-  if (!rowop || g_head_per_cell <= 0 || head < 4 || n < 2 * head || !scratch || scratch_bytes < (int64_t)rest_bytes + (1 << 20) ||
+  if (!rowop || g_head_per_cell <= 0 || head < 4 || n < head + head / 4 ||      // worth it from 1.25 x the head on (the rest costs a quarter of the routed pass per row)
+      !scratch || scratch_bytes < (int64_t)rest_bytes + (1 << 20) ||
       plan->ops[0].chk_dtype != DSB_F32 || !plan->ops[0].chk || xy_dtype != DSB_F32 || !x || !y)
     return route_one(view, x, y, xy_dtype, n, row_offset, plan, scratch, scratch_bytes, stream, nullptr);
 
