@@ -33,6 +33,9 @@ lines_simple_path = True
 routed = True
 routed_min_rows = 1 << 24
 routed_max_scratch_bytes = 64 << 30
+# first / last on canvases that DO fit L2: taken by dsb_points_routed as well once the frame holds this many rows per canvas cell
+# (the library routes 10 rows per cell and only filters the rest; below 1.25 x that it would route every row)
+routed_rows_per_cell_for_first = 16
 
 # where(max | min) of a float32 selector on canvases beyond L2: the plain extreme first (routed), then a filtered pass that
 # finds the row holding it (dsb_points_match32), instead of packed {key, row} atomics into an L2-banded 8-byte canvas.

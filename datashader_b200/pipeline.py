@@ -228,8 +228,12 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
         if rc != -3:
             _lib.check(rc, "dsb_points_count16")
     if (config.routed and plan.nops == 1 and plan.ncat == 0 and xy_dtype == _lib.F32 and n >= config.routed_min_rows
-            and plan.ops[0].op in _ROUTED_OPS and ncell * _ROUTED_OPS[plan.ops[0].op] > config.l2_budget_bytes):
-        # the accumulator canvas is beyond L2: route the points to shared-memory-sized buckets instead of banding
+            and plan.ops[0].op in _ROUTED_OPS
+            and (ncell * _ROUTED_OPS[plan.ops[0].op] > config.l2_budget_bytes
+                 or (plan.ops[0].op in (_lib.OP_MINROW, _lib.OP_MAXROW) and n >= config.routed_rows_per_cell_for_first * ncell))):
+        # the accumulator canvas is beyond L2: route the points to shared-memory-sized buckets instead of banding.  first / last
+        # with many rows per pixel, on ANY canvas: dsb_points_routed routes only the head (tail) of the rows - 10 per canvas cell -
+        # and drops the rest against a bitmap of settled pixels (k_rows_rest); the filtered mono kernel pays an L2 load per row
         need = int(lib.dsb_points_routed_scratch_bytes(C.byref(view), n))
         if 0 < need <= config.routed_max_scratch_bytes:
             scratch = getattr(ctx, "_routed_scratch", None)

@@ -233,6 +233,37 @@ def test_first_last_head_then_filtered_rest(routed, order):
         _lib.check(L.dsb_configure(b"routed_head_per_cell", 10))
 
 
+def test_first_last_split_on_an_l2_resident_canvas():
+    """first / last with many rows per pixel take the head + filtered-rest form on canvases that fit L2 as well (pipeline gate
+    `routed_rows_per_cell_for_first`): the real L2 budget, 301 x 257, against the oracle - and against the mono kernel."""
+    import torch
+    import datashader_b200 as ds
+    from datashader_b200 import _lib
+    from oracle import oracle as ora
+    L = _lib.lib()
+    W, H, n = 301, 257, 500_001
+    cols = _cols(np.random.default_rng(7), n)
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    old = (ds.config.routed_min_rows, ds.config.routed_rows_per_cell_for_first)
+    ds.config.routed_min_rows, ds.config.routed_rows_per_cell_for_first = 0, 2
+    _lib.check(L.dsb_routed_configure(0))
+    _lib.check(L.dsb_configure(b"routed_head_per_cell", 1))
+    try:
+        for name in ("first_v32", "last_v32", "where_first_v32_other", "where_last_v32_row"):
+            got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
+            assert b"k_rows_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
+            assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view, npartitions=2), f"L2-resident head + rest {name}")
+        got = cvs.points(frame, "x", "y", ds.max("v32")).data        # other reductions keep their kernels
+        assert b"k_route" not in L.dsb_last_kernel() and b"k_rows_rest" not in L.dsb_last_kernel(), L.dsb_last_kernel()
+        assert_agg_equal(got, ora.points(cols, "x", "y", ("max", "v32"), view), "max unaffected")
+    finally:
+        ds.config.routed_min_rows, ds.config.routed_rows_per_cell_for_first = old
+        _lib.check(L.dsb_routed_configure(1 << 24))
+        _lib.check(L.dsb_configure(b"routed_head_per_cell", 10))
+
+
 def test_first_last_split_equals_banded_at_production_scale():
     """4096 x 4096 (134 MB of row ids: beyond L2), 1e8 points, head = 2 rows per cell: the split form against the L2-banded kernels."""
     import torch
