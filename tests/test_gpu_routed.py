@@ -255,6 +255,18 @@ def test_first_last_split_on_an_l2_resident_canvas():
             got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
             assert b"k_rows_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
             assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view, npartitions=2), f"L2-resident head + rest {name}")
+        # the same frame streamed from the host in two row chunks: every chunk call splits on its own, the canvas carries the
+        # earlier chunks' rows (first: they settle their pixels; last: the later chunk's rows must still replace them)
+        hf = ds.HostFrame(cols)
+        chunk_rows = ds.HostFrame.CHUNK_ROWS
+        ds.HostFrame.CHUNK_ROWS = 250_001
+        try:
+            for name in ("first_v32", "last_v32", "where_last_v32_row"):
+                got = cvs.points(hf, "x", "y", make_agg(SPECS[name])).data
+                assert b"k_rows_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
+                assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view, npartitions=2), f"chunked head + rest {name}")
+        finally:
+            ds.HostFrame.CHUNK_ROWS = chunk_rows
         got = cvs.points(frame, "x", "y", ds.max("v32")).data        # other reductions keep their kernels
         assert b"k_route" not in L.dsb_last_kernel() and b"k_rows_rest" not in L.dsb_last_kernel(), L.dsb_last_kernel()
         assert_agg_equal(got, ora.points(cols, "x", "y", ("max", "v32"), view), "max unaffected")
