@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Soak of the routed path: random canvas shapes (1 .. ~1500 buckets), row counts and ranges; every routed reduction must be
-bit-equal to the unbanded generic kernel on the same frame.    python tools/soak_routed.py [configs=40] [seed=0]"""
+bit-equal to the unbanded generic kernel on the same frame - including first / last through a random head size of the
+head-then-filter split (0 = off, rows shuffled or sorted in space) and where(max | min) through the two-pass form.
+    python tools/soak_routed.py [configs=40] [seed=0]"""
 import os
 import sys
 
@@ -20,6 +22,8 @@ g = torch.Generator(device="cuda")
 bad = 0
 for it in range(nconf):
     W, H = int(rng.integers(3, 9000)), int(rng.integers(3, 9000))
+    if rng.random() < 0.5:                    # small canvases: many rows per pixel, so first / last take the head-then-filter split
+        W, H = int(rng.integers(3, 1200)), int(rng.integers(3, 1200))
     if W * H > 70_000_000:
         H = 70_000_000 // W
     n = int(rng.integers(1, 6_000_000))
@@ -28,10 +32,18 @@ for it in range(nconf):
     x = lo + span * (torch.rand(n, generator=g, device="cuda") * 1.1 - 0.05)
     y = lo + span * (torch.rand(n, generator=g, device="cuda") * 1.1 - 0.05)
     v = torch.randn(n, generator=g, device="cuda")
+    if rng.random() < 0.5:
+        v = torch.round(v * 4) / 4            # ties everywhere: where(max | min) must pick the earliest row
     v[::53] = float("nan")
+    if rng.random() < 0.3:                    # rows sorted in space: the head of first / last covers a strip of the canvas only
+        order = torch.argsort(y if rng.random() < 0.5 else -y)
+        x, y, v = x[order].contiguous(), y[order].contiguous(), v[order].contiguous()
+    head = int(rng.choice([0, 1, 2, 5, 10]))
+    _lib.check(L.dsb_configure(b"routed_head_per_cell", head))
     frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
     cvs = ds.Canvas(W, H, x_range=(lo, lo + span), y_range=(lo, lo + span))
-    for agg in (ds.max("value"), ds.min("value"), ds.first("value"), ds.last("value"), ds.count()):
+    for agg in (ds.max("value"), ds.min("value"), ds.first("value"), ds.last("value"), ds.count(), ds.where(ds.max("value")),
+                ds.where(ds.min("value")), ds.where(ds.first("value")), ds.where(ds.last("value"))):
         res = {}
         for mode in ("routed", "generic"):
             ds.config.routed = mode == "routed"
@@ -46,5 +58,6 @@ for it in range(nconf):
         if not same:
             bad += 1
             print("MISMATCH", it, W, H, n, lo, span, type(agg).__name__, res["routed_kernel"])
-    print(it, W, H, n, res["routed_kernel"].decode()[:60], flush=True)
+    print(it, W, H, n, "head", head, res["routed_kernel"].decode()[:60], flush=True)
+_lib.check(L.dsb_configure(b"routed_head_per_cell", 10))
 print("soak done, mismatches:", bad)
