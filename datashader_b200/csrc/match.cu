@@ -19,6 +19,9 @@
 constexpr int MB_SHIFT = 4;       // 16 x 16 pixels per coarse entry.  Measured at 8192^2, 4e9 rows (tools/bench_match.py, profiles/r02_where_two_pass.md):
                                   // 4 x 4 ... 32 x 32 all within 2 % - the pass is bound by its dependent loads, not by the survivors
 
+static bool g_match_queue = true;      // the shared-memory / queued form of the second pass (k_points_match32q); false: the first form
+void dsb_match_set_queue(bool on) { g_match_queue = on; }
+
 struct MatchArgs {
   dsb_view v;
   FastMap fm;
@@ -132,6 +135,108 @@ __global__ void __launch_bounds__(256, CTAS) k_points_match32(const __grid_const
   }
 }
 
+// The shipped form of the second pass.  What the first form (k_points_match32 above, kept as the A/B arm: dsb_configure("match_queue", 0))
+// taught: a global lookup per row costs an L1 tag cycle per LANE (281 G rows/s at best), and whatever only some rows need costs the
+// whole warp each time one lane has it.  So (1) the coarse thresholds live in SHARED memory - 16-bit, blocks of 32 x 32 pixels, 128 KB at
+// 8192^2; more rows pass than with the 16 x 16 map (ncu: DRAM 70 % busy with 64 x 64 blocks); (2) the rows that pass are not handled where they are found: each warp appends
+// them to its own queue in shared memory ({pixel, key, row}) and gathers the pixels' keys 32 queue entries at a time, every lane
+// busy; (3) the loop is k_points_priv_tight's: two vectors per thread per step, nothing kept per row but its queue entry.
+constexpr int MQ_CAP = 64;                 // queue entries per warp (drained at 32): {pixel, key, row}
+constexpr int MQ_THR_MAX = 65536;          // thresholds: the upper 16 bits of the keys (128 KB) - 32 x 32 pixel blocks at 8192^2
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_constant__ MatchArgs a) {
+  extern __shared__ int msm[];
+  short* thr = (short*)msm;                                              // [cw * ch] key >> 16: order-preserving, so the test stays conservative
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* q = (uint32_t*)(msm + MQ_THR_MAX / 2) + warp * 3 * MQ_CAP;   // pixel[MQ_CAP], key[MQ_CAP], row[MQ_CAP] (row within the call)
+  for (int j = threadIdx.x; j < a.cw * a.ch; j += blockDim.x) thr[j] = (short)(a.coarse[j] >> 16);
+  __syncthreads();
+  const uint32_t W = (uint32_t)a.v.width, H = (uint32_t)a.v.height;
+  const FastMap& fm = a.fm;
+  const int* __restrict__ keys = a.keys;
+  const int sh = a.shift, cw = a.cw;
+  int qn = 0;                                                            // warp-uniform
+  auto settle = [&](uint32_t cell, int key, uint32_t row) {
+    if (__ldcg(keys + cell) == key) atomicMin(a.rows + cell, a.row_offset + (long long)row);
+  };
+  // (measured and dropped: consulting the finer 16 x 16 L2 map for queued rows before their DRAM gather - a third fewer gathers,
+  // but a second dependent load per drain: 21.0 vs 19.6 ms)
+  auto settle_queued = [&](int e) { settle(q[e], (int)q[MQ_CAP + e], q[2 * MQ_CAP + e]); };
+  auto drain32 = [&]() {                                                 // the first 32 entries, one per lane; the rest moves to the front
+    __syncwarp();
+    settle_queued(lane);
+    const int rest = qn - 32;
+    uint32_t c = 0, k = 0, r = 0;
+    if (lane < rest) { c = q[32 + lane]; k = q[MQ_CAP + 32 + lane]; r = q[2 * MQ_CAP + 32 + lane]; }
+    __syncwarp();
+    if (lane < rest) { q[lane] = c; q[MQ_CAP + lane] = k; q[2 * MQ_CAP + lane] = r; }
+    qn = rest;
+  };
+  // one row: 1 = the fast pixel is not certain (exact mapping, out of line); rows that reach their block's threshold are queued
+  auto one = [&](float xv, float yv, float vv, uint32_t row) -> uint32_t {
+    const float xf = fmaf(xv, fm.sx, fm.tx), yf = fmaf(yv, fm.sy, fm.ty);
+    const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
+    const float dx = xf - (float)xi, dy = yf - (float)yi;
+    const bool sure = dx >= fm.ex && dx <= fm.omex && dy >= fm.ey && dy <= fm.omey;
+    const bool inside = (uint32_t)xi < W && (uint32_t)yi < H;
+    const int key = key32_from_f32(vv);
+    const int t = thr[inside ? (yi >> sh) * cw + (xi >> sh) : 0];
+    const bool live = sure && inside && vv == vv && (IS_MAX ? (key >> 16) >= t : (key >> 16) <= t);
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (bal) {
+      if (live) {
+        const int pos = qn + __popc(bal & ((1u << lane) - 1u));
+        q[pos] = (uint32_t)(yi * (int)W + xi); q[MQ_CAP + pos] = (uint32_t)key; q[2 * MQ_CAP + pos] = row;
+      }
+      qn += __popc(bal);
+      if (qn >= 32) drain32();
+    }
+    return (uint32_t)(!sure && vv == vv);
+  };
+  auto exact = [&](float xv, float yv, float vv, long long i) {
+    if (vv != vv) return;
+    const int cell = map_exact_linear(a.v, xv, yv);
+    if (cell >= 0) settle((uint32_t)cell, key32_from_f32(vv), (uint32_t)i);
+  };
+  const float4* __restrict__ x4 = (const float4*)a.x;
+  const float4* __restrict__ y4 = (const float4*)a.y;
+  const float4* __restrict__ v4 = (const float4*)a.val;
+  const long long n4 = a.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // warp-uniform trip count (the ballots need every lane): whole steps only; what is left takes the exact path below
+  long long w4 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (; w4 + stride + 31 < n4; w4 += 2 * stride) {
+    const long long i4 = w4 + lane;
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = __ldcs(v4 + i4);
+    const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride), vb = __ldcs(v4 + i4 + stride);
+    const uint32_t ra = (uint32_t)(4 * i4), rb = (uint32_t)(4 * (i4 + stride));
+    const uint32_t m = one(xa.x, ya.x, va.x, ra) | one(xa.y, ya.y, va.y, ra + 1) << 1 | one(xa.z, ya.z, va.z, ra + 2) << 2 |
+                       one(xa.w, ya.w, va.w, ra + 3) << 3 | one(xb.x, yb.x, vb.x, rb) << 4 | one(xb.y, yb.y, vb.y, rb + 1) << 5 |
+                       one(xb.z, yb.z, vb.z, rb + 2) << 6 | one(xb.w, yb.w, vb.w, rb + 3) << 7;
+    if (m) {
+      if (m & 1) exact(xa.x, ya.x, va.x, ra);
+      if (m & 2) exact(xa.y, ya.y, va.y, ra + 1);
+      if (m & 4) exact(xa.z, ya.z, va.z, ra + 2);
+      if (m & 8) exact(xa.w, ya.w, va.w, ra + 3);
+      if (m & 16) exact(xb.x, yb.x, vb.x, rb);
+      if (m & 32) exact(xb.y, yb.y, vb.y, rb + 1);
+      if (m & 64) exact(xb.z, yb.z, vb.z, rb + 2);
+      if (m & 128) exact(xb.w, yb.w, vb.w, rb + 3);
+    }
+  }
+  __syncwarp();
+  if (lane < qn) settle_queued(lane);                                                      // what is left in the queue (< 32 entries)
+  for (long long i4 = w4 + lane; i4 < n4; i4 += stride) {                                   // the last, partial steps
+    const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4), va = __ldcs(v4 + i4);
+    exact(xa.x, ya.x, va.x, 4 * i4); exact(xa.y, ya.y, va.y, 4 * i4 + 1); exact(xa.z, ya.z, va.z, 4 * i4 + 2); exact(xa.w, ya.w, va.w, 4 * i4 + 3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {           // tail rows
+    const long long i = (n4 << 2) + threadIdx.x;
+    exact(a.x[i], a.y[i], a.val[i], i);
+  }
+}
+
 // any axes / alignment: the exact mapping for every row, no filter (log axes, or ranges beyond the float32 mapping's error bound)
 template <int DUMMY>
 __global__ void __launch_bounds__(256) k_points_match32_exact(const MatchArgs a) {
@@ -147,7 +252,7 @@ __global__ void __launch_bounds__(256) k_points_match32_exact(const MatchArgs a)
 extern "C" int64_t dsb_points_match32_scratch_bytes(const dsb_view* view) {
   if (!view || view->width <= 0 || view->height <= 0) return 0;
   const long long cw = (view->width + (1 << MB_SHIFT) - 1) >> MB_SHIFT, ch = (view->height + (1 << MB_SHIFT) - 1) >> MB_SHIFT;
-  return cw * ch * 4;
+  return cw * ch * 4;      // the 16 x 16-block map of the first form; the shared-memory form's map (<= 64 KB) is never larger
 }
 
 extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
@@ -165,7 +270,7 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
   a.fm = make_fast_map(view);
   a.shift = MB_SHIFT;
   a.cw = (view->width + (1 << a.shift) - 1) >> a.shift; a.ch = (view->height + (1 << a.shift) - 1) >> a.shift;
-  if (!scratch || scratch_bytes < (long long)a.cw * a.ch * 4) { dsb_set_error("dsb_points_match32: scratch too small"); return DSB_ERR_ARG; }
+  if (!scratch || scratch_bytes < dsb_points_match32_scratch_bytes(view)) { dsb_set_error("dsb_points_match32: scratch too small"); return DSB_ERR_ARG; }
   a.x = (const float*)x; a.y = (const float*)y; a.val = (const float*)val; a.n = n; a.row_offset = row_offset;
   a.keys = (const int*)keys; a.rows = (long long*)rows; a.coarse = (int*)scratch;
   cudaStream_t s = (cudaStream_t)stream;
@@ -179,12 +284,23 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
   if (!fast) {
     k_points_match32_exact<0><<<dsb_num_sms() * 8, 256, 0, s>>>(a);
   } else {
+    if (g_match_queue)        // thresholds in shared memory: the finest power-of-two blocks (>= 16 x 16) whose 16-bit map fits 128 KB (32 x 32 at 8192^2)
+      while ((long long)((view->width + (1 << a.shift) - 1) >> a.shift) * ((view->height + (1 << a.shift) - 1) >> a.shift) > MQ_THR_MAX) a.shift++;
+    a.cw = (view->width + (1 << a.shift) - 1) >> a.shift; a.ch = (view->height + (1 << a.shift) - 1) >> a.shift;
     const int cgrid = a.shift <= 3 ? (int)(((long long)a.cw * a.ch + 7) / 8) : a.cw * a.ch;
     if (is_max) k_match_coarse<true><<<cgrid, 256, 0, s>>>(a); else k_match_coarse<false><<<cgrid, 256, 0, s>>>(a);
-    // 4 rows per thread per step, 6 CTAs of 256 threads per SM: 23.4 ms for 4e9 rows against 28.0 ms with 8 rows per step and
-    // 3 CTAs - the step is a chain of three dependent loads (columns, coarse entry, key) and wants warps, not registers
-    if (is_max) k_points_match32<true, 4, 6><<<dsb_num_sms() * 6, 256, 0, s>>>(a);
-    else k_points_match32<false, 4, 6><<<dsb_num_sms() * 6, 256, 0, s>>>(a);
+    if (g_match_queue) {
+      const size_t smem = (size_t)MQ_THR_MAX * 2 + 32 * 3 * MQ_CAP * 4;
+      cudaFuncSetAttribute(k_points_match32q<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_points_match32q<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (is_max) k_points_match32q<true><<<dsb_num_sms(), 1024, smem, s>>>(a);
+      else k_points_match32q<false><<<dsb_num_sms(), 1024, smem, s>>>(a);
+    } else {
+      // first form: 4 rows per thread per step, 6 CTAs of 256 threads per SM: 23.4 ms for 4e9 rows against 28.0 ms with 8 rows per
+      // step and 3 CTAs - the step is a chain of three dependent loads (columns, coarse entry, key) and wants warps, not registers
+      if (is_max) k_points_match32<true, 4, 6><<<dsb_num_sms() * 6, 256, 0, s>>>(a);
+      else k_points_match32<false, 4, 6><<<dsb_num_sms() * 6, 256, 0, s>>>(a);
+    }
   }
   DSB_CUDA_CHECK_LAUNCH("dsb_points_match32");
   return DSB_OK;

@@ -656,6 +656,7 @@ static long long l2_band_budget_bytes() {
 
 // runtime knobs (tests and tuning): "l2_band_bytes" (0 disables banding), "band_min_rows"
 void dsb_routed_set_head(long long rows_per_cell);   // routed.cu: first / last route this many rows per canvas cell and only filter the rest (0 = off)
+void dsb_match_set_queue(bool on);   // match.cu: the queued shared-memory form of dsb_points_match32 (default) or its first form (A/B arm)
 void dsb_routed_set_tma(bool on);   // routed.cu: pass 2 through the TMA ring (default) or plain loads (A/B arm)
 
 extern "C" int dsb_configure(const char* key, int64_t value) {
@@ -669,6 +670,7 @@ extern "C" int dsb_configure(const char* key, int64_t value) {
   if (!strcmp(key, "count16_band_bytes")) { g_count16_band_bytes = value; return DSB_OK; }
   if (!strcmp(key, "count8")) { g_count8 = value != 0; return DSB_OK; }
   if (!strcmp(key, "routed_tma")) { dsb_routed_set_tma(value != 0); return DSB_OK; }
+  if (!strcmp(key, "match_queue")) { dsb_match_set_queue(value != 0); return DSB_OK; }
   if (!strcmp(key, "routed_head_per_cell")) { if (value < 0) { dsb_set_error("dsb_configure: routed_head_per_cell must be >= 0"); return DSB_ERR_ARG; } dsb_routed_set_head(value); return DSB_OK; }
   if (!strcmp(key, "mono_banded")) { g_mono_banded = value != 0; return DSB_OK; }
   if (!strcmp(key, "mono_min_rows")) { g_mono_min_rows = value; return DSB_OK; }

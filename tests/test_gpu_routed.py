@@ -178,11 +178,14 @@ def test_where_two_pass_matches_oracle(routed, shape, n, clustered):
     frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
     view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
     cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
-    for name in ("where_max_v32_other", "where_min_v32_row", "where_max_v32_row", "where_min_v32_other"):
-        spec = SPECS.get(name) or ("where", (name.split("_")[1], "v32"), None if name.endswith("row") else "other")
-        got = cvs.points(frame, "x", "y", make_agg(spec)).data
-        assert b"k_points_match32<" in _lib.lib().dsb_last_kernel(), (name, _lib.lib().dsb_last_kernel())
-        assert_agg_equal(got, ora.points(cols, "x", "y", spec, view), f"two-pass {name} {shape} clustered={clustered}")
+    for queue in (1, 0):          # the queued shared-memory form of the second pass (shipped) and its first form
+        _lib.check(_lib.lib().dsb_configure(b"match_queue", queue))
+        for name in ("where_max_v32_other", "where_min_v32_row", "where_max_v32_row", "where_min_v32_other"):
+            spec = SPECS.get(name) or ("where", (name.split("_")[1], "v32"), None if name.endswith("row") else "other")
+            got = cvs.points(frame, "x", "y", make_agg(spec)).data
+            assert b"k_points_match32<" in _lib.lib().dsb_last_kernel(), (name, _lib.lib().dsb_last_kernel())
+            assert_agg_equal(got, ora.points(cols, "x", "y", spec, view), f"two-pass {name} {shape} clustered={clustered} queue={queue}")
+    _lib.check(_lib.lib().dsb_configure(b"match_queue", 1))
     # summary sharing the extreme's canvas with the where()
     both = cvs.points(frame, "x", "y", ds.summary(m=ds.max("v32"), w=ds.where(ds.max("v32"), "other")))
     assert_agg_equal(both["m"].data, ora.points(cols, "x", "y", ("max", "v32"), view), "summary max")

@@ -30,6 +30,8 @@ ref = None
 for shift, variant in combos:
     if hasattr(L, "dsb_match_configure"):      # experiment builds only (profiles/r02_where_two_pass.md)
         L.dsb_match_configure(shift, variant)
+    else:                                      # shipped library: variant 0 = the queued shared-memory form, 1 = the first form
+        _lib.check(L.dsb_configure(b"match_queue", int(variant == 0)))
     best = None
     for it in range(4):
         config.kernel_events.clear()
