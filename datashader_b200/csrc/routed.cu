@@ -502,6 +502,8 @@ __global__ void __launch_bounds__(256) k_rows_rest_sample(const RestArgs a, long
   if ((threadIdx.x & 31) == 0 && tot) { atomicAdd(a.gate, (unsigned long long)tot); atomicAdd(a.gate + 1, (unsigned long long)open); }
 }
 
+constexpr int RQ_CAP = 64;                 // k_rows_rest: queue entries per warp (drained at 32)
+
 template <bool FIRST, int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS) k_rows_rest(const __grid_constant__ RestArgs a) {
   extern __shared__ uint32_t blocks[];                         // the block map: a random 4-byte read per row costs a few bank conflicts
@@ -512,12 +514,32 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_rows_rest(const __grid_consta
   const FastMap& fm = a.fm;
   const uint32_t* __restrict__ bits = a.bits;
   const int bs = a.bs, cw = a.cw;
-  // The loop of k_points_priv_tight: two vectors (8 rows) per thread per step, every row finished as it is mapped, nothing but
-  // two mask bits kept per row.  bit 0: the fast pixel is certain, on the canvas, and its block still holds an open pixel;
-  // bit 8: the fast pixel is not certain (near a pixel edge, NaN, inf).  The instruction count of this kernel is its bound
-  // (ncu: 65 % of the issue slots busy), and the rows that need a closer look cost a whole warp each time ONE lane has one:
-  // the block map is therefore as fine as shared memory allows (8 x 8 pixels at 8192^2) and the closer look is cheap.
-  auto one = [&](float xv, float yv) -> uint32_t {
+  // The loop of k_points_priv_tight: two vectors (8 rows) per thread per step, every row finished as it is mapped.  The instruction
+  // count of this kernel is its bound (ncu: 65 % of the issue slots busy), and the rows that need a closer look - the fast pixel is
+  // not certain (0.8 % at 8192^2), or its block still holds an open pixel (0.3 %) - cost a whole warp each time ONE lane has one when
+  // they are handled in place (23 % of the instructions executed).  They go to a per-warp queue in shared memory instead ({x, y, row})
+  // and are looked at 32 at a time, every lane busy: the exact mapping, the pixel's own bit (L2), the NaN check, the vote.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* q = blocks + ((a.cw * a.ch + 31) >> 5) + warp * 3 * RQ_CAP;          // x[RQ_CAP], y[RQ_CAP], row[RQ_CAP] (row within the rest)
+  int qn = 0;                                                                      // warp-uniform
+  auto closer = [&](float xv, float yv, long long i) {
+    const int cell = map_exact_linear(a.v, xv, yv);
+    if (cell < 0 || ((__ldg(bits + (cell >> 5)) >> (cell & 31)) & 1u)) return;
+    const float c = a.chk[i];
+    if (c != c) return;
+    if (FIRST) atomicMin(a.canvas + cell, a.row_offset + i); else atomicMax(a.canvas + cell, a.row_offset + i);
+  };
+  auto drain32 = [&]() {                                                 // the first 32 entries, one per lane; the rest moves to the front
+    __syncwarp();
+    closer(__uint_as_float(q[lane]), __uint_as_float(q[RQ_CAP + lane]), (long long)q[2 * RQ_CAP + lane]);
+    const int rest = qn - 32;
+    uint32_t c = 0, k = 0, r = 0;
+    if (lane < rest) { c = q[32 + lane]; k = q[RQ_CAP + 32 + lane]; r = q[2 * RQ_CAP + 32 + lane]; }
+    __syncwarp();
+    if (lane < rest) { q[lane] = c; q[RQ_CAP + lane] = k; q[2 * RQ_CAP + lane] = r; }
+    qn = rest;
+  };
+  auto one = [&](float xv, float yv, uint32_t row) {
     const float xf = fmaf(xv, fm.sx, fm.tx), yf = fmaf(yv, fm.sy, fm.ty);
     const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
     const float dx = xf - (float)xi, dy = yf - (float)yi;
@@ -525,57 +547,34 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_rows_rest(const __grid_consta
     const bool inside = (uint32_t)xi < W && (uint32_t)yi < H;
     const int b = inside ? (yi >> bs) * cw + (xi >> bs) : 0;
     const uint32_t open = ((blocks[b >> 5] >> (b & 31)) & 1u) ^ 1u;
-    return sure ? (uint32_t)inside & open : 0x100u;
-  };
-  auto vote = [&](int cell, long long i) {                     // the pixel's own bit (L2), the NaN check, the vote
-    if ((__ldg(bits + (cell >> 5)) >> (cell & 31)) & 1u) return;
-    const float c = a.chk[i];
-    if (c != c) return;
-    if (FIRST) atomicMin(a.canvas + cell, a.row_offset + i); else atomicMax(a.canvas + cell, a.row_offset + i);
-  };
-  auto open_row = [&](float xv, float yv, long long i) {       // a certain pixel of an open block: the fast pixel again, 6 instructions
-    const int xi = __float2int_rd(fmaf(xv, fm.sx, fm.tx)), yi = __float2int_rd(fmaf(yv, fm.sy, fm.ty));
-    vote(yi * (int)W + xi, i);
-  };
-  auto closer = [&](float xv, float yv, long long i) {         // ~0.07 % of the rows: the exact f64 mapping
-    const int cell = map_exact_linear(a.v, xv, yv);
-    if (cell >= 0) vote(cell, i);
+    const bool look = sure ? (inside && open) : true;
+    const unsigned bal = __ballot_sync(0xffffffffu, look);
+    if (bal) {
+      if (look) {
+        const int pos = qn + __popc(bal & ((1u << lane) - 1u));
+        q[pos] = __float_as_uint(xv); q[RQ_CAP + pos] = __float_as_uint(yv); q[2 * RQ_CAP + pos] = row;
+      }
+      qn += __popc(bal);
+      if (qn >= 32) drain32();
+    }
   };
   const float4* __restrict__ x4 = (const float4*)a.x;
   const float4* __restrict__ y4 = (const float4*)a.y;
   const long long n4 = a.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i4 + stride < n4; i4 += 2 * stride) {
+  // warp-uniform trip count (the ballots need every lane): whole steps only; what is left takes the closer look directly
+  long long w4 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (; w4 + stride + 31 < n4; w4 += 2 * stride) {
+    const long long i4 = w4 + lane;
     const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
     const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride);
-    const uint32_t m = one(xa.x, ya.x) | one(xa.y, ya.y) << 1 | one(xa.z, ya.z) << 2 | one(xa.w, ya.w) << 3 |
-                       one(xb.x, yb.x) << 4 | one(xb.y, yb.y) << 5 | one(xb.z, yb.z) << 6 | one(xb.w, yb.w) << 7;
-    if (m) {
-      const long long ia = 4 * i4, ib = 4 * (i4 + stride);
-      if (m & 0xff) {
-        if (m & 1) open_row(xa.x, ya.x, ia);
-        if (m & 2) open_row(xa.y, ya.y, ia + 1);
-        if (m & 4) open_row(xa.z, ya.z, ia + 2);
-        if (m & 8) open_row(xa.w, ya.w, ia + 3);
-        if (m & 16) open_row(xb.x, yb.x, ib);
-        if (m & 32) open_row(xb.y, yb.y, ib + 1);
-        if (m & 64) open_row(xb.z, yb.z, ib + 2);
-        if (m & 128) open_row(xb.w, yb.w, ib + 3);
-      }
-      if (m >> 8) {
-        if (m & 0x100) closer(xa.x, ya.x, ia);
-        if (m & 0x200) closer(xa.y, ya.y, ia + 1);
-        if (m & 0x400) closer(xa.z, ya.z, ia + 2);
-        if (m & 0x800) closer(xa.w, ya.w, ia + 3);
-        if (m & 0x1000) closer(xb.x, yb.x, ib);
-        if (m & 0x2000) closer(xb.y, yb.y, ib + 1);
-        if (m & 0x4000) closer(xb.z, yb.z, ib + 2);
-        if (m & 0x8000) closer(xb.w, yb.w, ib + 3);
-      }
-    }
+    const uint32_t ra = (uint32_t)(4 * i4), rb = (uint32_t)(4 * (i4 + stride));
+    one(xa.x, ya.x, ra); one(xa.y, ya.y, ra + 1); one(xa.z, ya.z, ra + 2); one(xa.w, ya.w, ra + 3);
+    one(xb.x, yb.x, rb); one(xb.y, yb.y, rb + 1); one(xb.z, yb.z, rb + 2); one(xb.w, yb.w, rb + 3);
   }
-  if (i4 < n4) {
+  __syncwarp();
+  if (lane < qn) closer(__uint_as_float(q[lane]), __uint_as_float(q[RQ_CAP + lane]), (long long)q[2 * RQ_CAP + lane]);
+  for (long long i4 = w4 + lane; i4 < n4; i4 += stride) {                                   // the last, partial steps
     const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
     closer(xa.x, ya.x, 4 * i4); closer(xa.y, ya.y, 4 * i4 + 1); closer(xa.z, ya.z, 4 * i4 + 2); closer(xa.w, ya.w, 4 * i4 + 3);
   }
@@ -753,7 +752,7 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   r.blocks = (uint32_t*)(tailp + 256 + route_rest_cell_bits_bytes(ncell));
   r.bs = route_rest_block_shift(view->width, view->height);
   r.cw = (int)((view->width + (1LL << r.bs) - 1) >> r.bs); r.ch = (int)((view->height + (1LL << r.bs) - 1) >> r.bs);
-  const size_t rest_smem = (size_t)(((long long)r.cw * r.ch + 31) >> 5) * 4;
+  const size_t rest_smem = (size_t)(((long long)r.cw * r.ch + 31) >> 5) * 4 + 32 * 3 * RQ_CAP * 4;
   r.limit = first ? row_offset + n_head : row_offset + off_head;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(r.gate, 0, 16, s);
@@ -761,8 +760,8 @@ extern "C" int dsb_points_routed(const dsb_view* view, const void* x, const void
   if (first) k_rows_settled<true><<<dsb_num_sms() * 8, 256, 0, s>>>(r); else k_rows_settled<false><<<dsb_num_sms() * 8, 256, 0, s>>>(r);
   k_rows_settled_blocks<<<dsb_num_sms() * 8, 256, 0, s>>>(r);
   k_rows_rest_sample<<<dsb_num_sms() * 4, 256, 0, s>>>(r, stride_blocks);
-  cudaFuncSetAttribute(k_rows_rest<true, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REST_MAP_BYTES);
-  cudaFuncSetAttribute(k_rows_rest<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REST_MAP_BYTES);
+  cudaFuncSetAttribute(k_rows_rest<true, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REST_MAP_BYTES + 32 * 3 * RQ_CAP * 4));
+  cudaFuncSetAttribute(k_rows_rest<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REST_MAP_BYTES + 32 * 3 * RQ_CAP * 4));
   if (first) k_rows_rest<true, 1024, 1><<<dsb_num_sms(), 1024, rest_smem, s>>>(r); else k_rows_rest<false, 1024, 1><<<dsb_num_sms(), 1024, rest_smem, s>>>(r);
   rc = route_one(view, r.x, r.y, xy_dtype, n_rest, r.row_offset, &pr, scratch, routed_bytes, stream, r.gate);   // the gated fallback
   if (rc != DSB_OK) return rc;
