@@ -234,7 +234,13 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
         # the accumulator canvas is beyond L2: route the points to shared-memory-sized buckets instead of banding.  first / last
         # with many rows per pixel, on ANY canvas: dsb_points_routed routes only the head (tail) of the rows - 10 per canvas cell -
         # and drops the rest against a bitmap of settled pixels (k_rows_rest); the filtered mono kernel pays an L2 load per row
-        need = int(lib.dsb_points_routed_scratch_bytes(C.byref(view), n))
+        n_scratch = n
+        if ncell * _ROUTED_OPS[plan.ops[0].op] <= config.l2_budget_bytes:
+            # first / last on an L2-resident canvas: only the head of the rows is routed.  The record buffer is sized for that; should
+            # the device-side sample hand the rest to the routed kernels too (rows sorted in space), the records that do not fit are
+            # applied with direct atomics - on a canvas that sits in L2
+            n_scratch = min(n, 2 * config.routed_rows_per_cell_for_first * ncell)
+        need = int(lib.dsb_points_routed_scratch_bytes(C.byref(view), n_scratch))
         if 0 < need <= config.routed_max_scratch_bytes:
             scratch = getattr(ctx, "_routed_scratch", None)
             if scratch is None or scratch.numel() < need:
