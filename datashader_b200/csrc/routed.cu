@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_rows_rest(const __grid_consta
     if (lane < rest) { q[lane] = c; q[RQ_CAP + lane] = k; q[2 * RQ_CAP + lane] = r; }
     qn = rest;
   };
-  auto one = [&](float xv, float yv, uint32_t row) {
+  auto one = [&](float xv, float yv) -> uint32_t {            // 1 = this row needs a closer look
     const float xf = fmaf(xv, fm.sx, fm.tx), yf = fmaf(yv, fm.sy, fm.ty);
     const int xi = __float2int_rd(xf), yi = __float2int_rd(yf);
     const float dx = xf - (float)xi, dy = yf - (float)yi;
@@ -547,7 +547,9 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_rows_rest(const __grid_consta
     const bool inside = (uint32_t)xi < W && (uint32_t)yi < H;
     const int b = inside ? (yi >> bs) * cw + (xi >> bs) : 0;
     const uint32_t open = ((blocks[b >> 5] >> (b & 31)) & 1u) ^ 1u;
-    const bool look = sure ? (inside && open) : true;
+    return sure ? (uint32_t)inside & open : 1u;
+  };
+  auto push = [&](bool look, float xv, float yv, uint32_t row) {
     const unsigned bal = __ballot_sync(0xffffffffu, look);
     if (bal) {
       if (look) {
@@ -568,9 +570,13 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_rows_rest(const __grid_consta
     const long long i4 = w4 + lane;
     const float4 xa = __ldcs(x4 + i4), ya = __ldcs(y4 + i4);
     const float4 xb = __ldcs(x4 + i4 + stride), yb = __ldcs(y4 + i4 + stride);
-    const uint32_t ra = (uint32_t)(4 * i4), rb = (uint32_t)(4 * (i4 + stride));
-    one(xa.x, ya.x, ra); one(xa.y, ya.y, ra + 1); one(xa.z, ya.z, ra + 2); one(xa.w, ya.w, ra + 3);
-    one(xb.x, yb.x, rb); one(xb.y, yb.y, rb + 1); one(xb.z, yb.z, rb + 2); one(xb.w, yb.w, rb + 3);
+    const uint32_t m = one(xa.x, ya.x) | one(xa.y, ya.y) << 1 | one(xa.z, ya.z) << 2 | one(xa.w, ya.w) << 3 |
+                       one(xb.x, yb.x) << 4 | one(xb.y, yb.y) << 5 | one(xb.z, yb.z) << 6 | one(xb.w, yb.w) << 7;
+    if (__any_sync(0xffffffffu, m != 0)) {         // one vote per step on small canvases (0.07 % of the rows), the eight ballots only then
+      const uint32_t ra = (uint32_t)(4 * i4), rb = (uint32_t)(4 * (i4 + stride));
+      push(m & 1, xa.x, ya.x, ra); push(m & 2, xa.y, ya.y, ra + 1); push(m & 4, xa.z, ya.z, ra + 2); push(m & 8, xa.w, ya.w, ra + 3);
+      push(m & 16, xb.x, yb.x, rb); push(m & 32, xb.y, yb.y, rb + 1); push(m & 64, xb.z, yb.z, rb + 2); push(m & 128, xb.w, yb.w, rb + 3);
+    }
   }
   __syncwarp();
   if (lane < qn) closer(__uint_as_float(q[lane]), __uint_as_float(q[RQ_CAP + lane]), (long long)q[2 * RQ_CAP + lane]);
@@ -685,7 +691,17 @@ static int route_one(const dsb_view* view, const void* x, const void* y, int32_t
   if ((size_t)RTILE * 8 + (size_t)((a.nb + 2) & ~1u) * (16 + 4) + 64 * 4 > 226 * 1024) {
     dsb_set_error("dsb_points_routed: too many buckets for the shared-memory tables"); return DSB_ERR_UNSUPPORTED;
   }
-  const size_t hdr = route_fixed_bytes(a.nb, n);
+  // the list of rows for k_route_slow shrinks to what a smaller scratch leaves (the caller sized it for fewer rows: first / last on an
+  // L2-resident canvas, whose rest is routed only if the device-side sample says so); a full list maps its rows in place
+  size_t slow_entries = route_slow_entries(n);
+  {
+    const size_t fixed = route_header_bytes(a.nb) + ((size_t)a.nb * 4096 + 1024) * 8 + 4096;
+    if ((size_t)scratch_bytes > fixed) {
+      const size_t room = ((size_t)scratch_bytes - fixed) / 4 / 12;
+      if (slow_entries > room) slow_entries = room > 1024 ? room : 1024;
+    }
+  }
+  const size_t hdr = route_header_bytes(a.nb) + ((slow_entries * 12 + 255) & ~(size_t)255);
   if (a.nb > 65535 || scratch_bytes < (int64_t)(hdr + ((size_t)a.nb * 4096 + 1024) * 8)) { dsb_set_error("dsb_points_routed: scratch too small"); return DSB_ERR_ARG; }
   unsigned char* p = (unsigned char*)scratch;
   unsigned long long* off = (unsigned long long*)p;
@@ -695,7 +711,7 @@ static int route_one(const dsb_view* view, const void* x, const void* y, int32_t
   uint32_t* queue = hist + a.nb;
   a.slow_n = queue + 1;
   a.slow = (uint32_t*)(p + route_header_bytes(a.nb));
-  a.slow_cap = (uint32_t)route_slow_entries(n);
+  a.slow_cap = (uint32_t)slow_entries;
   a.recs = (unsigned long long*)(p + hdr);
   a.off = off; a.cap = cap; a.cursor = cursor; a.queue = queue; a.canvas = b.agg; a.notes = plan->notes; a.gate = gate;
   const unsigned long long capacity = ((unsigned long long)scratch_bytes - hdr) / 8 - 4096;   // k_route_plan rounds every thread's start up

@@ -258,6 +258,15 @@ def test_first_last_split_on_an_l2_resident_canvas():
             got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
             assert b"k_rows_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
             assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view, npartitions=2), f"L2-resident head + rest {name}")
+        # rows sorted in space: the head covers a strip of the canvas, the device-side sample hands the rest to the routed kernels -
+        # with a record buffer the pipeline sized for the head only (L2-resident canvas): the overflow goes to direct atomics
+        idx = np.argsort(cols["y"], kind="stable")
+        scols = {k: np.ascontiguousarray(v[idx]) for k, v in cols.items()}
+        sframe = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in scols.items()})
+        for name in ("first_v32", "last_v32"):
+            got = cvs.points(sframe, "x", "y", make_agg(SPECS[name])).data
+            assert b"k_rows_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
+            assert_agg_equal(got, ora.points(scols, "x", "y", SPECS[name], view, npartitions=2), f"L2-resident, sorted rows {name}")
         # the same frame streamed from the host in two row chunks: every chunk call splits on its own, the canvas carries the
         # earlier chunks' rows (first: they settle their pixels; last: the later chunk's rows must still replace them)
         hf = ds.HostFrame(cols)
