@@ -40,3 +40,9 @@ routed_rows_per_cell_for_first = 16
 # where(max | min) of a float32 selector on canvases beyond L2: the plain extreme first (routed), then a filtered pass that
 # finds the row holding it (dsb_points_match32), instead of packed {key, row} atomics into an L2-banded 8-byte canvas.
 where_two_pass = True
+
+# max / min of a float32 column on an L2-resident canvas once the frame holds this many rows per canvas cell: the first
+# `minmax_head_rows_per_cell` rows per cell go through dsb_points, the rest through dsb_points_minmax_rest (block thresholds in shared
+# memory drop the rows that cannot win any more).  0 = off.
+minmax_split_rows_per_cell = 512
+minmax_head_rows_per_cell = 128

@@ -31,6 +31,7 @@ struct MatchArgs {
   long long* rows;        // i64 canvas, DSB_OP_MINROW-initialised
   int* coarse;            // [ch, cw]
   int cw, ch, shift;
+  unsigned int* notes;    // UPDATE form: DSB_NOTE_NEGZERO
 };
 
 // coarse[by][bx] = the least extreme key of the block: min of the maxima (IS_MAX) / max of the minima
@@ -141,10 +142,13 @@ __global__ void __launch_bounds__(256, CTAS) k_points_match32(const __grid_const
 // 8192^2; more rows pass than with the 16 x 16 map (ncu: DRAM 70 % busy with 64 x 64 blocks); (2) the rows that pass are not handled where they are found: each warp appends
 // them to its own queue in shared memory ({pixel, key, row}) and gathers the pixels' keys 32 queue entries at a time, every lane
 // busy; (3) the loop is k_points_priv_tight's: two vectors per thread per step, nothing kept per row but its queue entry.
-constexpr int MQ_CAP = 64;                 // queue entries per warp (drained at 32): {pixel, key, row}
+constexpr int MQ_CAP = 64;                 // queue entries per warp (drained at 32): {pixel, value bits, row}
 constexpr int MQ_THR_MAX = 65536;          // thresholds: the upper 16 bits of the keys (128 KB) - 32 x 32 pixel blocks at 8192^2
 
-template <bool IS_MAX>
+// UPDATE = true is the same loop serving max / min THEMSELVES on a small canvas with many rows per pixel (dsb_points_minmax_rest):
+// `keys` then is the live accumulator, already holding the extreme of the head of the rows; a queued row replaces its pixel's key if
+// it beats it.  The thresholds were taken from the head and only get staler - a row below a stale bound still cannot win.
+template <bool IS_MAX, bool UPDATE>
 __global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_constant__ MatchArgs a) {
   extern __shared__ int msm[];
   short* thr = (short*)msm;                                              // [cw * ch] key >> 16: order-preserving, so the test stays conservative
@@ -157,12 +161,20 @@ __global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_consta
   const int* __restrict__ keys = a.keys;
   const int sh = a.shift, cw = a.cw;
   int qn = 0;                                                            // warp-uniform
-  auto settle = [&](uint32_t cell, int key, uint32_t row) {
-    if (__ldcg(keys + cell) == key) atomicMin(a.rows + cell, a.row_offset + (long long)row);
+  bool negzero = false;                                                  // UPDATE: a candidate was -0.0 (DSB_NOTE_NEGZERO)
+  auto settle = [&](uint32_t cell, uint32_t vbits, uint32_t row) {      // vbits: the row's float32 value as stored
+    const int key = key32_from_f32(__uint_as_float(vbits));
+    const int cur = __ldcg(keys + cell);
+    if (UPDATE) {
+      if (IS_MAX ? key > cur : key < cur) { if (IS_MAX) atomicMax((int*)keys + cell, key); else atomicMin((int*)keys + cell, key); }
+      // the keys fold -0.0 onto +0.0: a -0.0 that takes or ties the extreme puts the sign of that pixel's zero in doubt
+      // (one that loses here cannot be the extreme)
+      if (vbits == 0x80000000u && !(IS_MAX ? key < cur : key > cur)) negzero = true;
+    } else if (cur == key) atomicMin(a.rows + cell, a.row_offset + (long long)row);
   };
   // (measured and dropped: consulting the finer 16 x 16 L2 map for queued rows before their DRAM gather - a third fewer gathers,
   // but a second dependent load per drain: 21.0 vs 19.6 ms)
-  auto settle_queued = [&](int e) { settle(q[e], (int)q[MQ_CAP + e], q[2 * MQ_CAP + e]); };
+  auto settle_queued = [&](int e) { settle(q[e], q[MQ_CAP + e], q[2 * MQ_CAP + e]); };
   auto drain32 = [&]() {                                                 // the first 32 entries, one per lane; the rest moves to the front
     __syncwarp();
     settle_queued(lane);
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_consta
     if (bal) {
       if (live) {
         const int pos = qn + __popc(bal & ((1u << lane) - 1u));
-        q[pos] = (uint32_t)(yi * (int)W + xi); q[MQ_CAP + pos] = (uint32_t)key; q[2 * MQ_CAP + pos] = row;
+        q[pos] = (uint32_t)(yi * (int)W + xi); q[MQ_CAP + pos] = __float_as_uint(vv); q[2 * MQ_CAP + pos] = row;
       }
       qn += __popc(bal);
       if (qn >= 32) drain32();
@@ -197,7 +209,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_consta
   auto exact = [&](float xv, float yv, float vv, long long i) {
     if (vv != vv) return;
     const int cell = map_exact_linear(a.v, xv, yv);
-    if (cell >= 0) settle((uint32_t)cell, key32_from_f32(vv), (uint32_t)i);
+    if (cell >= 0) settle((uint32_t)cell, __float_as_uint(vv), (uint32_t)i);
   };
   const float4* __restrict__ x4 = (const float4*)a.x;
   const float4* __restrict__ y4 = (const float4*)a.y;
@@ -235,6 +247,7 @@ __global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_consta
     const long long i = (n4 << 2) + threadIdx.x;
     exact(a.x[i], a.y[i], a.val[i], i);
   }
+  if (UPDATE && negzero && a.notes) *a.notes = DSB_NOTE_NEGZERO;
 }
 
 // any axes / alignment: the exact mapping for every row, no filter (log axes, or ranges beyond the float32 mapping's error bound)
@@ -272,7 +285,7 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
   a.cw = (view->width + (1 << a.shift) - 1) >> a.shift; a.ch = (view->height + (1 << a.shift) - 1) >> a.shift;
   if (!scratch || scratch_bytes < dsb_points_match32_scratch_bytes(view)) { dsb_set_error("dsb_points_match32: scratch too small"); return DSB_ERR_ARG; }
   a.x = (const float*)x; a.y = (const float*)y; a.val = (const float*)val; a.n = n; a.row_offset = row_offset;
-  a.keys = (const int*)keys; a.rows = (long long*)rows; a.coarse = (int*)scratch;
+  a.keys = (const int*)keys; a.rows = (long long*)rows; a.coarse = (int*)scratch; a.notes = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   const bool fast = a.fm.enabled && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)val) & 15) == 0;
   {   // the label names both passes when the extreme was computed just before (bench.py reads it back as roofline.kernel)
@@ -291,10 +304,10 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
     if (is_max) k_match_coarse<true><<<cgrid, 256, 0, s>>>(a); else k_match_coarse<false><<<cgrid, 256, 0, s>>>(a);
     if (g_match_queue) {
       const size_t smem = (size_t)MQ_THR_MAX * 2 + 32 * 3 * MQ_CAP * 4;
-      cudaFuncSetAttribute(k_points_match32q<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_points_match32q<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (is_max) k_points_match32q<true><<<dsb_num_sms(), 1024, smem, s>>>(a);
-      else k_points_match32q<false><<<dsb_num_sms(), 1024, smem, s>>>(a);
+      cudaFuncSetAttribute(k_points_match32q<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_points_match32q<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (is_max) k_points_match32q<true, false><<<dsb_num_sms(), 1024, smem, s>>>(a);
+      else k_points_match32q<false, false><<<dsb_num_sms(), 1024, smem, s>>>(a);
     } else {
       // first form: 4 rows per thread per step, 6 CTAs of 256 threads per SM: 23.4 ms for 4e9 rows against 28.0 ms with 8 rows per
       // step and 3 CTAs - the step is a chain of three dependent loads (columns, coarse entry, key) and wants warps, not registers
@@ -303,5 +316,44 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
     }
   }
   DSB_CUDA_CHECK_LAUNCH("dsb_points_match32");
+  return DSB_OK;
+}
+
+// max / min of a float32 column on a canvas that fits L2, the REST of the rows after the head went through dsb_points: `keys` is the
+// live DSB_OP_MAX32 / MIN32 accumulator.  Block thresholds (the least extreme of every block after the head, 16 bits, shared memory)
+// drop the rows that cannot win - 98 % of them once a pixel has seen a few hundred rows; the others are queued per warp and compared
+// with their pixel's key 32 at a time.  Linear axes inside the float32 mapping's error bound and 16-byte aligned columns only
+// (DSB_ERR_UNSUPPORTED otherwise: the caller runs dsb_points over these rows as well).
+extern "C" int dsb_points_minmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                                      int64_t row_offset, const void* val, int32_t val_dtype, void* keys, int32_t is_max,
+                                      unsigned int* notes, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points_minmax_rest: bad view"); return DSB_ERR_ARG; }
+  if (!keys) { dsb_set_error("dsb_points_minmax_rest: null canvas"); return DSB_ERR_ARG; }
+  if (n < 0 || n > (1LL << 32)) { dsb_set_error("dsb_points_minmax_rest: n must be in [0, 2^32] per call"); return DSB_ERR_ARG; }
+  if (n == 0) return DSB_OK;
+  if (!x || !y || !val) { dsb_set_error("dsb_points_minmax_rest: null column"); return DSB_ERR_ARG; }
+  if (xy_dtype != DSB_F32 || val_dtype != DSB_F32) { dsb_set_error("dsb_points_minmax_rest: float32 columns only"); return DSB_ERR_UNSUPPORTED; }
+  if ((long long)view->width * view->height >= (1LL << 31)) { dsb_set_error("dsb_points_minmax_rest: canvas too large"); return DSB_ERR_UNSUPPORTED; }
+  if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)val) & 15) { dsb_set_error("dsb_points_minmax_rest: columns must be 16-byte aligned"); return DSB_ERR_UNSUPPORTED; }
+  MatchArgs a;
+  a.v = *view;
+  a.fm = make_fast_map(view);
+  if (!a.fm.enabled) { dsb_set_error("dsb_points_minmax_rest: linear axes inside the float32 mapping's error bound only"); return DSB_ERR_UNSUPPORTED; }
+  a.shift = 1;              // the finest power-of-two blocks whose 16-bit map fits 128 KB: 4 x 4 pixels at 900 x 525
+  while ((long long)((view->width + (1 << a.shift) - 1) >> a.shift) * ((view->height + (1 << a.shift) - 1) >> a.shift) > MQ_THR_MAX) a.shift++;
+  a.cw = (view->width + (1 << a.shift) - 1) >> a.shift; a.ch = (view->height + (1 << a.shift) - 1) >> a.shift;
+  if (!scratch || scratch_bytes < (long long)a.cw * a.ch * 4) { dsb_set_error("dsb_points_minmax_rest: scratch too small (%lld bytes needed)", (long long)a.cw * a.ch * 4); return DSB_ERR_ARG; }
+  a.x = (const float*)x; a.y = (const float*)y; a.val = (const float*)val; a.n = n; a.row_offset = row_offset;
+  a.keys = (const int*)keys; a.rows = nullptr; a.coarse = (int*)scratch; a.notes = notes;
+  cudaStream_t s = (cudaStream_t)stream;
+  dsb_note_kernel("k_points_minmax_rest<%s> after %.100s", is_max ? "max" : "min", dsb_last_kernel());
+  const int cgrid = a.shift <= 3 ? (int)(((long long)a.cw * a.ch + 7) / 8) : a.cw * a.ch;
+  if (is_max) k_match_coarse<true><<<cgrid, 256, 0, s>>>(a); else k_match_coarse<false><<<cgrid, 256, 0, s>>>(a);
+  const size_t smem = (size_t)MQ_THR_MAX * 2 + 32 * 3 * MQ_CAP * 4;
+  cudaFuncSetAttribute(k_points_match32q<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_points_match32q<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (is_max) k_points_match32q<true, true><<<dsb_num_sms(), 1024, smem, s>>>(a);
+  else k_points_match32q<false, true><<<dsb_num_sms(), 1024, smem, s>>>(a);
+  DSB_CUDA_CHECK_LAUNCH("dsb_points_minmax_rest");
   return DSB_OK;
 }

@@ -196,6 +196,17 @@ int dsb_points_match32(const dsb_view* view, const void* x, const void* y, int32
                        const void* val, int32_t val_dtype, const void* keys, int32_t is_max, void* rows, void* scratch,
                        int64_t scratch_bytes, void* stream);
 
+/* max / min of a float32 column on a canvas that fits L2, for frames with hundreds of rows per pixel: the caller runs dsb_points
+ * (DSB_OP_MAX32 / MIN32) over the HEAD of the rows and this entry over the rest.  `keys` is that live accumulator; the least extreme
+ * of every small block of pixels after the head (16 bits each, shared memory) drops the rows that cannot win any more - ~98 % - and
+ * the others are compared with their pixel's key and replace it if they beat it (max._append / min._append, reductions.py:1222-1227,
+ * 1178-1183: the same strict compare).  `notes`: DSB_NOTE_NEGZERO is set when a zero takes or ties an extreme (its sign is then
+ * resolved by the caller as for dsb_points).  scratch: 4 bytes per block (<= 256 KB).  float32 x / y / val, linear axes inside the
+ * float32 mapping's error bound, 16-byte aligned columns; DSB_ERR_UNSUPPORTED otherwise (run dsb_points over these rows as well). */
+int dsb_points_minmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                           const void* val, int32_t val_dtype, void* keys, int32_t is_max, unsigned int* notes, void* scratch,
+                           int64_t scratch_bytes, void* stream);
+
 /* ---- lines ---------------------------------------------------------------------------------- */
 typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5,
                DSB_LINE_MEAN = 6 /* antialiased only: canvas f64 sum (zeroed), `mask` = u32 count canvas (zeroed) */,

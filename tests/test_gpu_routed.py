@@ -288,6 +288,43 @@ def test_first_last_split_on_an_l2_resident_canvas():
         _lib.check(L.dsb_configure(b"routed_head_per_cell", 10))
 
 
+@pytest.mark.parametrize("values", ["normal", "zeros"])
+def test_max_min_head_then_threshold_filtered_rest(values):
+    """max / min of a float32 column on an L2-resident canvas with many rows per pixel: dsb_points over the head of the rows,
+    dsb_points_minmax_rest (block thresholds in shared memory, queued survivors) over the rest - forced on at small n, against the
+    oracle bit for bit, including the sign of a zero extreme (-0.0 / +0.0 rows that tie)."""
+    import torch
+    import datashader_b200 as ds
+    from datashader_b200 import _lib
+    from oracle import oracle as ora
+    L = _lib.lib()
+    W, H, n = 301, 257, 600_003
+    rng = np.random.default_rng(31)
+    cols = _cols(rng, n)
+    if values == "zeros":          # extremes that are zeros of either sign, in either order of arrival
+        v = np.where(rng.random(n) < 0.5, -np.abs(cols["v32"]), 0.0).astype(np.float32)
+        v[rng.random(n) < 0.3] *= np.float32(-1.0)        # -0.0 and positive values appear as well
+        v[rng.random(n) < 0.02] = np.nan
+        cols["v32"] = v
+        assert np.signbit(v[v == 0]).any() and (~np.signbit(v[v == 0])).any()
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items()})
+    view = ora.make_view(W, H, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(W, H, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    old = (ds.config.routed_min_rows, ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell)
+    ds.config.routed_min_rows, ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell = 0, 2, 1
+    try:
+        for name in ("max_v32", "min_v32"):
+            got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
+            if values == "normal":     # (with zeros the -0.0 redo runs last and leaves its own kernel name)
+                assert b"k_points_minmax_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
+            assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view), f"head + threshold rest {name} {values}")
+        both = cvs.points(frame, "x", "y", ds.summary(a=ds.max("v32"), b=ds.min("v32"), c=ds.count()))
+        assert_agg_equal(both["a"].data, ora.points(cols, "x", "y", ("max", "v32"), view), f"summary max {values}")
+        assert_agg_equal(both["b"].data, ora.points(cols, "x", "y", ("min", "v32"), view), f"summary min {values}")
+    finally:
+        ds.config.routed_min_rows, ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell = old
+
+
 def test_first_last_split_equals_banded_at_production_scale():
     """4096 x 4096 (134 MB of row ids: beyond L2), 1e8 points, head = 2 rows per cell: the split form against the L2-banded kernels."""
     import torch

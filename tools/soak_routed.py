@@ -48,16 +48,22 @@ for it in range(nconf):
         for mode in ("routed", "generic"):
             ds.config.routed = mode == "routed"
             ds.config.routed_min_rows, ds.config.l2_budget_bytes = (0, 1) if mode == "routed" else (1 << 24, 96 << 20)
+            if it % 3 == 2 and mode == "routed":      # every third configuration keeps the real L2 budget: max / min then take the
+                ds.config.l2_budget_bytes = 96 << 20  # head + threshold-filtered rest (dsb_points_minmax_rest), first / last the split
+            ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell = (2, 1) if mode == "routed" else (0, 128)
             _lib.check(L.dsb_routed_configure(0 if mode == "routed" else 1 << 24))
             _lib.check(L.dsb_configure(b"l2_band_bytes", 0 if mode == "generic" else 96 << 20))
             _lib.check(L.dsb_configure(b"mono", 0 if mode == "generic" else 1))
             res[mode] = cvs.points(frame, "x", "y", agg).data.clone()
             res[mode + "_kernel"] = L.dsb_last_kernel()
+            if mode == "routed" and isinstance(agg, ds.max):
+                kern_max = L.dsb_last_kernel().decode()
         a, b = res["routed"], res["generic"]
         same = torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)) if a.dtype.is_floating_point else torch.equal(a, b)
         if not same:
             bad += 1
             print("MISMATCH", it, W, H, n, lo, span, type(agg).__name__, res["routed_kernel"])
-    print(it, W, H, n, "head", head, res["routed_kernel"].decode()[:60], flush=True)
+    print(it, W, H, n, "head", head, res["routed_kernel"].decode()[:60], "| max:", kern_max[:40], flush=True)
 _lib.check(L.dsb_configure(b"routed_head_per_cell", 10))
+ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell = 512, 128
 print("soak done, mismatches:", bad)
