@@ -81,6 +81,7 @@ _SIGNATURES = {
     "dsb_routed_configure": ([_i64], C.c_int),
     "dsb_points_match32_scratch_bytes": ([C.POINTER(View)], C.c_int64),
     "dsb_points_minmax_rest": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p], C.c_int),
+    "dsb_points_argminmax_rest": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, _p, _i32, _p, _i32, _p, _i64, _p], C.c_int),
     "dsb_points_match32": ([C.POINTER(View), _p, _p, _i32, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p], C.c_int),
     "dsb_lines_configure": ([C.c_int], C.c_int),
     "dsb_points_views": ([_p, _i32, _i32, _i32, _f64, _f64, _f64, _f64, _p, _p, _i32, _i64, _i64, C.POINTER(Plan), _i64, _p],

@@ -32,6 +32,8 @@ struct MatchArgs {
   int* coarse;            // [ch, cw]
   int cw, ch, shift;
   unsigned int* notes;    // UPDATE form: DSB_NOTE_NEGZERO
+  int kstride, koff;      // k_match_coarse reads keys[pixel * kstride + koff]: 1, 0 for a key32 canvas; 2, 1 for the key half of a packed
+                          //   {key32, row} canvas (DSB_OP_ARGMAX32 / ARGMIN32)
 };
 
 // coarse[by][bx] = the least extreme key of the block: min of the maxima (IS_MAX) / max of the minima
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(256) k_match_coarse(const MatchArgs a) {
     for (int p = t; p < B * B; p += nthr) {
       const int px = (bx << a.shift) + (p & (B - 1)), py = (by << a.shift) + (p >> a.shift);
       if (px < a.v.width && py < a.v.height) {
-        const int q = a.keys[(long long)py * a.v.width + px];
+        const int q = a.keys[((long long)py * a.v.width + px) * a.kstride + a.koff];
         k = IS_MAX ? min(k, q) : max(k, q);
       }
     }
@@ -148,8 +150,11 @@ constexpr int MQ_THR_MAX = 65536;          // thresholds: the upper 16 bits of t
 // UPDATE = true is the same loop serving max / min THEMSELVES on a small canvas with many rows per pixel (dsb_points_minmax_rest):
 // `keys` then is the live accumulator, already holding the extreme of the head of the rows; a queued row replaces its pixel's key if
 // it beats it.  The thresholds were taken from the head and only get staler - a row below a stale bound still cannot win.
-template <bool IS_MAX, bool UPDATE>
+// MODE 2: the same for where(max | min) on such a canvas - `keys` is the live packed {key32, row} accumulator (DSB_OP_ARGMAX32 /
+// ARGMIN32: the earliest row among the ties), a queued row swaps itself in if its packed value beats the pixel's.
+template <bool IS_MAX, int MODE>
 __global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_constant__ MatchArgs a) {
+  constexpr bool UPDATE = MODE == 1;
   extern __shared__ int msm[];
   short* thr = (short*)msm;                                              // [cw * ch] key >> 16: order-preserving, so the test stays conservative
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -164,6 +169,14 @@ __global__ void __launch_bounds__(1024, 1) k_points_match32q(const __grid_consta
   bool negzero = false;                                                  // UPDATE: a candidate was -0.0 (DSB_NOTE_NEGZERO)
   auto settle = [&](uint32_t cell, uint32_t vbits, uint32_t row) {      // vbits: the row's float32 value as stored
     const int key = key32_from_f32(__uint_as_float(vbits));
+    if (MODE == 2) {           // value first, the earliest row on ties: the row field of a max is complemented (accum.cuh, DSB_OP_ARGMAX32)
+      const uint32_t grow = (uint32_t)(a.row_offset + (long long)row);
+      const long long p = ((long long)key << 32) | (long long)(IS_MAX ? ~grow : grow);
+      long long* canvas = (long long*)a.rows;
+      const long long curp = __ldcg(canvas + cell);
+      if (IS_MAX ? p > curp : p < curp) { if (IS_MAX) atomicMax(canvas + cell, p); else atomicMin(canvas + cell, p); }
+      return;
+    }
     const int cur = __ldcg(keys + cell);
     if (UPDATE) {
       if (IS_MAX ? key > cur : key < cur) { if (IS_MAX) atomicMax((int*)keys + cell, key); else atomicMin((int*)keys + cell, key); }
@@ -285,7 +298,7 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
   a.cw = (view->width + (1 << a.shift) - 1) >> a.shift; a.ch = (view->height + (1 << a.shift) - 1) >> a.shift;
   if (!scratch || scratch_bytes < dsb_points_match32_scratch_bytes(view)) { dsb_set_error("dsb_points_match32: scratch too small"); return DSB_ERR_ARG; }
   a.x = (const float*)x; a.y = (const float*)y; a.val = (const float*)val; a.n = n; a.row_offset = row_offset;
-  a.keys = (const int*)keys; a.rows = (long long*)rows; a.coarse = (int*)scratch; a.notes = nullptr;
+  a.keys = (const int*)keys; a.rows = (long long*)rows; a.coarse = (int*)scratch; a.notes = nullptr; a.kstride = 1; a.koff = 0;
   cudaStream_t s = (cudaStream_t)stream;
   const bool fast = a.fm.enabled && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)val) & 15) == 0;
   {   // the label names both passes when the extreme was computed just before (bench.py reads it back as roofline.kernel)
@@ -304,10 +317,10 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
     if (is_max) k_match_coarse<true><<<cgrid, 256, 0, s>>>(a); else k_match_coarse<false><<<cgrid, 256, 0, s>>>(a);
     if (g_match_queue) {
       const size_t smem = (size_t)MQ_THR_MAX * 2 + 32 * 3 * MQ_CAP * 4;
-      cudaFuncSetAttribute(k_points_match32q<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_points_match32q<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (is_max) k_points_match32q<true, false><<<dsb_num_sms(), 1024, smem, s>>>(a);
-      else k_points_match32q<false, false><<<dsb_num_sms(), 1024, smem, s>>>(a);
+      cudaFuncSetAttribute(k_points_match32q<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_points_match32q<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (is_max) k_points_match32q<true, 0><<<dsb_num_sms(), 1024, smem, s>>>(a);
+      else k_points_match32q<false, 0><<<dsb_num_sms(), 1024, smem, s>>>(a);
     } else {
       // first form: 4 rows per thread per step, 6 CTAs of 256 threads per SM: 23.4 ms for 4e9 rows against 28.0 ms with 8 rows per
       // step and 3 CTAs - the step is a chain of three dependent loads (columns, coarse entry, key) and wants warps, not registers
@@ -324,9 +337,9 @@ extern "C" int dsb_points_match32(const dsb_view* view, const void* x, const voi
 // drop the rows that cannot win - 98 % of them once a pixel has seen a few hundred rows; the others are queued per warp and compared
 // with their pixel's key 32 at a time.  Linear axes inside the float32 mapping's error bound and 16-byte aligned columns only
 // (DSB_ERR_UNSUPPORTED otherwise: the caller runs dsb_points over these rows as well).
-extern "C" int dsb_points_minmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
-                                      int64_t row_offset, const void* val, int32_t val_dtype, void* keys, int32_t is_max,
-                                      unsigned int* notes, void* scratch, int64_t scratch_bytes, void* stream) {
+static int minmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                       const void* val, int32_t val_dtype, void* keys, int32_t is_max, bool packed, unsigned int* notes, void* scratch,
+                       int64_t scratch_bytes, void* stream) {
   if (!view || view->width <= 0 || view->height <= 0) { dsb_set_error("dsb_points_minmax_rest: bad view"); return DSB_ERR_ARG; }
   if (!keys) { dsb_set_error("dsb_points_minmax_rest: null canvas"); return DSB_ERR_ARG; }
   if (n < 0 || n > (1LL << 32)) { dsb_set_error("dsb_points_minmax_rest: n must be in [0, 2^32] per call"); return DSB_ERR_ARG; }
@@ -344,16 +357,33 @@ extern "C" int dsb_points_minmax_rest(const dsb_view* view, const void* x, const
   a.cw = (view->width + (1 << a.shift) - 1) >> a.shift; a.ch = (view->height + (1 << a.shift) - 1) >> a.shift;
   if (!scratch || scratch_bytes < (long long)a.cw * a.ch * 4) { dsb_set_error("dsb_points_minmax_rest: scratch too small (%lld bytes needed)", (long long)a.cw * a.ch * 4); return DSB_ERR_ARG; }
   a.x = (const float*)x; a.y = (const float*)y; a.val = (const float*)val; a.n = n; a.row_offset = row_offset;
-  a.keys = (const int*)keys; a.rows = nullptr; a.coarse = (int*)scratch; a.notes = notes;
+  a.keys = (const int*)keys; a.rows = nullptr; a.coarse = (int*)scratch; a.notes = notes; a.kstride = 1; a.koff = 0;
+  if (packed) { a.rows = (long long*)keys; a.kstride = 2; a.koff = 1; a.notes = nullptr; }      // little endian: the key is the high word
   cudaStream_t s = (cudaStream_t)stream;
-  dsb_note_kernel("k_points_minmax_rest<%s> after %.100s", is_max ? "max" : "min", dsb_last_kernel());
+  dsb_note_kernel(packed ? "k_points_argminmax_rest<%s> after %.100s" : "k_points_minmax_rest<%s> after %.100s", is_max ? "max" : "min", dsb_last_kernel());
   const int cgrid = a.shift <= 3 ? (int)(((long long)a.cw * a.ch + 7) / 8) : a.cw * a.ch;
   if (is_max) k_match_coarse<true><<<cgrid, 256, 0, s>>>(a); else k_match_coarse<false><<<cgrid, 256, 0, s>>>(a);
   const size_t smem = (size_t)MQ_THR_MAX * 2 + 32 * 3 * MQ_CAP * 4;
-  cudaFuncSetAttribute(k_points_match32q<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(k_points_match32q<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (is_max) k_points_match32q<true, true><<<dsb_num_sms(), 1024, smem, s>>>(a);
-  else k_points_match32q<false, true><<<dsb_num_sms(), 1024, smem, s>>>(a);
+  cudaFuncSetAttribute(k_points_match32q<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_points_match32q<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_points_match32q<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_points_match32q<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (packed) { if (is_max) k_points_match32q<true, 2><<<dsb_num_sms(), 1024, smem, s>>>(a); else k_points_match32q<false, 2><<<dsb_num_sms(), 1024, smem, s>>>(a); }
+  else if (is_max) k_points_match32q<true, 1><<<dsb_num_sms(), 1024, smem, s>>>(a);
+  else k_points_match32q<false, 1><<<dsb_num_sms(), 1024, smem, s>>>(a);
   DSB_CUDA_CHECK_LAUNCH("dsb_points_minmax_rest");
   return DSB_OK;
+}
+
+extern "C" int dsb_points_minmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                                      int64_t row_offset, const void* val, int32_t val_dtype, void* keys, int32_t is_max,
+                                      unsigned int* notes, void* scratch, int64_t scratch_bytes, void* stream) {
+  return minmax_rest(view, x, y, xy_dtype, n, row_offset, val, val_dtype, keys, is_max, false, notes, scratch, scratch_bytes, stream);
+}
+
+// the same for where(max | min): `packed` is the live DSB_OP_ARGMAX32 / ARGMIN32 accumulator (i64 {key32, row} per pixel)
+extern "C" int dsb_points_argminmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n,
+                                         int64_t row_offset, const void* val, int32_t val_dtype, void* packed, int32_t is_max,
+                                         void* scratch, int64_t scratch_bytes, void* stream) {
+  return minmax_rest(view, x, y, xy_dtype, n, row_offset, val, val_dtype, packed, is_max, true, nullptr, scratch, scratch_bytes, stream);
 }

@@ -257,8 +257,10 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
                     _lib.check(rc, "dsb_points_routed")
     op0 = plan.ops[0]
     if (config.minmax_split_rows_per_cell and plan.nops == 1 and plan.ncat == 0 and xy_dtype == _lib.F32
-            and op0.op in (_lib.OP_MAX32, _lib.OP_MIN32) and op0.val_dtype == _lib.F32 and op0.chk_dtype == _lib.NONE
-            and 4 * ncell <= config.l2_budget_bytes and n >= config.routed_min_rows and n >= config.minmax_split_rows_per_cell * ncell):
+            and op0.op in (_lib.OP_MAX32, _lib.OP_MIN32, _lib.OP_ARGMAX32, _lib.OP_ARGMIN32) and op0.val_dtype == _lib.F32
+            and op0.chk_dtype == _lib.NONE and (4 if op0.op in (_lib.OP_MAX32, _lib.OP_MIN32) else 8) * ncell <= config.l2_budget_bytes
+            and n >= config.routed_min_rows and n >= config.minmax_split_rows_per_cell * ncell
+            and (op0.op in (_lib.OP_MAX32, _lib.OP_MIN32) or (row_offset + n) < (1 << 32))):
         # many rows per pixel: after the head the extreme of a pixel rarely changes - the rest only needs a threshold test per row
         n_head = (config.minmax_head_rows_per_cell * ncell + 3) & ~3
         _lib.check(lib.dsb_points(C.byref(view), x.data_ptr(), y.data_ptr(), xy_dtype, n_head, row_offset, C.byref(plan),
@@ -266,13 +268,18 @@ def _launch_points_plan(view, x, y, xy_dtype, n, row_offset, plan, ctx):
         scratch = getattr(ctx, "_minmax_scratch", None)
         if scratch is None:
             scratch = ctx._minmax_scratch = torch.empty(1 << 18, dtype=torch.uint8, device=x.device)
-        rc = lib.dsb_points_minmax_rest(C.byref(view), x.data_ptr() + 4 * n_head, y.data_ptr() + 4 * n_head, xy_dtype, n - n_head,
-                                        row_offset + n_head, op0.val + 4 * n_head, op0.val_dtype, op0.agg, int(op0.op == _lib.OP_MAX32),
-                                        plan.notes, scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
+        if op0.op in (_lib.OP_MAX32, _lib.OP_MIN32):
+            rc = lib.dsb_points_minmax_rest(C.byref(view), x.data_ptr() + 4 * n_head, y.data_ptr() + 4 * n_head, xy_dtype, n - n_head,
+                                            row_offset + n_head, op0.val + 4 * n_head, op0.val_dtype, op0.agg,
+                                            int(op0.op == _lib.OP_MAX32), plan.notes, scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
+        else:       # where(max | min): the packed {key32, row} accumulator
+            rc = lib.dsb_points_argminmax_rest(C.byref(view), x.data_ptr() + 4 * n_head, y.data_ptr() + 4 * n_head, xy_dtype, n - n_head,
+                                               row_offset + n_head, op0.val + 4 * n_head, op0.val_dtype, op0.agg,
+                                               int(op0.op == _lib.OP_ARGMAX32), scratch.data_ptr(), scratch.numel(), ctx.stream_ptr)
         if rc == 0:
             return
         if rc != -3:
-            _lib.check(rc, "dsb_points_minmax_rest")
+            _lib.check(rc, "dsb_points_minmax_rest / dsb_points_argminmax_rest")
         rest = _lib.Plan.from_buffer_copy(plan)          # not served (axes / alignment): the same rows through dsb_points
         rest.ops[0].val = op0.val + 4 * n_head
         _lib.check(lib.dsb_points(C.byref(view), x.data_ptr() + 4 * n_head, y.data_ptr() + 4 * n_head, xy_dtype, n - n_head,

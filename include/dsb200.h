@@ -206,6 +206,12 @@ int dsb_points_match32(const dsb_view* view, const void* x, const void* y, int32
 int dsb_points_minmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
                            const void* val, int32_t val_dtype, void* keys, int32_t is_max, unsigned int* notes, void* scratch,
                            int64_t scratch_bytes, void* stream);
+/* The same for where(max | min) of a float32 selector: `packed` is the live DSB_OP_ARGMAX32 / ARGMIN32 accumulator (i64 {key32, row}
+ * per pixel, the head of the rows already in it); a row that reaches its block's threshold swaps itself in if its packed value beats
+ * the pixel's - value first, the earliest row on ties (reductions.py:2009-2016). */
+int dsb_points_argminmax_rest(const dsb_view* view, const void* x, const void* y, int32_t xy_dtype, int64_t n, int64_t row_offset,
+                              const void* val, int32_t val_dtype, void* packed, int32_t is_max, void* scratch, int64_t scratch_bytes,
+                              void* stream);
 
 /* ---- lines ---------------------------------------------------------------------------------- */
 typedef enum { DSB_LINE_ANY = 1, DSB_LINE_COUNT = 2, DSB_LINE_SUM = 3, DSB_LINE_MAX = 4, DSB_LINE_MIN = 5,

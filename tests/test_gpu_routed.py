@@ -318,6 +318,10 @@ def test_max_min_head_then_threshold_filtered_rest(values):
             if values == "normal":     # (with zeros the -0.0 redo runs last and leaves its own kernel name)
                 assert b"k_points_minmax_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
             assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view), f"head + threshold rest {name} {values}")
+        for name in ("where_max_v32_other", "where_min_v32_row"):      # the packed {key, row} accumulator through the same split
+            got = cvs.points(frame, "x", "y", make_agg(SPECS[name])).data
+            assert b"k_points_argminmax_rest<" in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
+            assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view), f"head + threshold rest {name} {values}")
         both = cvs.points(frame, "x", "y", ds.summary(a=ds.max("v32"), b=ds.min("v32"), c=ds.count()))
         assert_agg_equal(both["a"].data, ora.points(cols, "x", "y", ("max", "v32"), view), f"summary max {values}")
         assert_agg_equal(both["b"].data, ora.points(cols, "x", "y", ("min", "v32"), view), f"summary min {values}")
