@@ -56,12 +56,32 @@ def _lib_shade():
 class Image(DataArray):
     """An RGBA image stored as uint32 (transfer_functions/__init__.py:30-78)."""
     __slots__ = ()
+    __array_priority__ = 70
+    border = 1
 
     def to_pil(self, origin="lower"):
         from PIL import Image as PILImage
         data = np.asarray(self.data)
         arr = np.flipud(data) if origin == "lower" else data
         return PILImage.fromarray(np.ascontiguousarray(arr).view(np.uint8).reshape(arr.shape + (4,)), "RGBA")
+
+    def to_bytesio(self, format="png", origin="lower"):   # noqa: A002 - the reference's argument name
+        """The encoded image in a rewound in-memory file (transfer_functions/__init__.py:48-52)."""
+        import io
+        buf = io.BytesIO()
+        self.to_pil(origin).save(buf, format)
+        buf.seek(0)
+        return buf
+
+    def _repr_png_(self):
+        """Notebook PNG display (transfer_functions/__init__.py:54-56)."""
+        return self.to_bytesio().getvalue()
+
+    def _repr_html_(self):
+        """Notebook HTML display: the PNG inlined as a data URI with the reference's border (:58-71)."""
+        import base64
+        blob = base64.b64encode(self.to_bytesio().getvalue()).decode("ascii")
+        return f"<img style=\"margin: auto; border:{self.border}px solid\" src='data:image/png;base64,{blob}'/>"
 
 
 def _device_tensor(data, device):

@@ -64,3 +64,25 @@ def test_spread_masks_and_argument_checks():
     assert ds.tf.set_background(img, None) is img and ds.tf.stack(img) is img
     with pytest.raises(ValueError, match="span is not"):
         ds.tf.shade(arr, how="eq_hist", span=(0, 1))
+
+
+def test_image_png_and_html_display():
+    """Image.to_bytesio / _repr_png_ / _repr_html_ (transfer_functions/__init__.py:48-71): a PNG that decodes back to the
+    same RGBA bytes (flipped for origin='lower'), and the data-URI <img> with the reference's 1 px border."""
+    import base64
+    import io
+    import datashader_b200 as ds
+    from PIL import Image as PILImage
+    px = np.arange(12, dtype=np.uint32).reshape(3, 4) * np.uint32(0x01020304) + np.uint32(0xFF000000)
+    img = ds.tf.Image(px, coords={"y": np.arange(3), "x": np.arange(4)}, dims=["y", "x"])
+    fp = img.to_bytesio()
+    assert fp.tell() == 0 and fp.getvalue()[:8] == b"\x89PNG\r\n\x1a\n"
+    back = np.asarray(PILImage.open(fp).convert("RGBA"))
+    assert np.array_equal(back, np.flipud(px).view(np.uint8).reshape(3, 4, 4))
+    top = np.asarray(PILImage.open(img.to_bytesio(origin="upper")).convert("RGBA"))
+    assert np.array_equal(top, px.view(np.uint8).reshape(3, 4, 4))
+    assert img._repr_png_() == img.to_bytesio().getvalue()
+    html = img._repr_html_()
+    assert html.startswith("<img style=\"margin: auto; border:1px solid\" src='data:image/png;base64,")
+    blob = html.split("base64,")[1].split("'")[0]
+    assert np.array_equal(np.asarray(PILImage.open(io.BytesIO(base64.b64decode(blob))).convert("RGBA")), back)
