@@ -117,3 +117,40 @@ def test_count16_equals_u32_count_at_scale(big):
     assert np.array_equal(a, b)
     inside = int(((x[:m] >= 0) & (x[:m] <= 1) & (y[:m] >= 0) & (y[:m] <= 1)).sum().item())
     assert int(a.sum(dtype=np.int64)) == inside
+
+
+def test_head_then_filtered_rest_equals_single_pass_at_scale(big):
+    """The head-then-filter forms at 2e8 points (423 rows per canvas cell, NaN values, points outside the canvas): max / min /
+    where(max | min) through dsb_points over a head + dsb_points_minmax_rest / dsb_points_argminmax_rest over the rest, and
+    first / last through the routed head + k_rows_rest, each bit-equal to the same reduction with the split switched off
+    (k_points_mono over every row) - and the result is a fixed point: max over the row-reversed frame is the same canvas."""
+    ds, torch, n, x, y, v = big
+    from datashader_b200 import _lib
+    L = _lib.lib()
+    frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
+    aggs = {"max": ds.max("value"), "min": ds.min("value"), "where_max_row": ds.where(ds.max("value")),
+            "where_min_row": ds.where(ds.min("value")), "first": ds.first("value"), "last": ds.last("value")}
+    old = (ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell, ds.config.routed)
+    got = {}
+    try:
+        for name, agg in aggs.items():
+            ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell, ds.config.routed = 64, 32, True
+            a = _run(ds, frame, agg, False)
+            kern = L.dsb_last_kernel()
+            if name in ("max", "min"):
+                assert b"k_points_minmax_rest<" in kern, (name, kern)
+            elif name.startswith("where"):
+                assert b"k_points_argminmax_rest<" in kern, (name, kern)
+            else:
+                assert b"k_rows_rest<" in kern, (name, kern)
+            ds.config.minmax_split_rows_per_cell, ds.config.routed = 0, False
+            b = _run(ds, frame, agg, False)
+            assert b"rest<" not in L.dsb_last_kernel(), (name, L.dsb_last_kernel())
+            assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), name
+            got[name] = a
+        ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell, ds.config.routed = 64, 32, True
+        flipped = ds.DeviceFrame({"x": x.flip(0), "y": y.flip(0), "value": v.flip(0)})
+        assert np.array_equal(_run(ds, flipped, ds.max("value"), False), got["max"], equal_nan=True)
+        assert np.array_equal(_run(ds, flipped, ds.first("value"), False), got["last"], equal_nan=True)
+    finally:
+        ds.config.minmax_split_rows_per_cell, ds.config.minmax_head_rows_per_cell, ds.config.routed = old
