@@ -68,6 +68,27 @@ def _is_key32(np_dtype):
     return d == np.float32 or (d.kind in "iub" and d.itemsize <= 2)
 
 
+def _rows_fit_packed32(ctx):
+    """The packed {key32, row} accumulators of where(max | min) keep the low 32 bits of the global row id and break ties on
+    them (dsb_decode_arg restores the rest from the frame's row offset).  That is the reference's "first row of the extreme
+    wins" (reductions.py:2009-2016) only while the rows of this frame - a shard of a bigger one, or a chunk-streamed host source -
+    do not cross a multiple of 2^32; a frame that does takes the 64-bit path (extreme, then the first matching row)."""
+    cached = getattr(ctx, "_packed32_ok", None)
+    if cached is not None:
+        return cached
+    frame = getattr(ctx, "frame", None)
+    if frame is None:
+        return True
+    lo, n = int(getattr(frame, "row_offset", 0)), len(frame)
+    ok = n == 0 or (lo >> 32) == ((lo + n - 1) >> 32)
+    if getattr(ctx, "dist", None) is not None:
+        # every rank must declare the same accumulators (their canvases are all-reduced pairwise): one flag, agreed once per query
+        flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=frame.device)
+        ok = int(ctx.dist._all_reduce(flag, "max").item()) == 0
+    ctx._packed32_ok = ok
+    return ok
+
+
 # ---------------------------------------------------------------------------------------------
 # category preprocessors (reductions.py:123-260)
 class CategoryPreprocess:
@@ -428,7 +449,8 @@ class where(_FloatingReduction):
                 # by the routed kernels), then "which row holds it" against the finished canvas (dsb_points_match32)
                 value = Acc(which + "32", sel.column)
                 return [value, Acc("matchrow32", sel.column, None, aux=value)]
-            return [Acc("arg" + which + "32", sel.column)]
+            if _rows_fit_packed32(ctx):
+                return [Acc("arg" + which + "32", sel.column)]
         value = Acc(which + "64", sel.column)
         return [value, Acc("matchrow64", sel.column, None, aux=value)]
 

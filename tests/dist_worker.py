@@ -49,6 +49,20 @@ def main():
                 assert_agg_equal(got, want, f"{name} world={world}")
             except AssertionError as e:   # noqa: PERF203
                 bad.append(f"{name}: {str(e)[:200]}")
+    # the same shards as part of a frame whose global rows cross 2^32 INSIDE rank 1's shard: the packed {key32, row} accumulator
+    # breaks ties on 32 row bits, so every rank must agree on the 64-bit form (reductions._rows_fit_packed32) - v32 is full of ties
+    base = (1 << 32) - (n // 2) - 100
+    shifted = ds.DeviceFrame(dict(frame.columns), categories=frame.categories, row_offset=base + lo)
+    shifted.sharded = True
+    for name in ("where_max_v32_other", "where_min_v32_row"):
+        got = cvs.points(shifted, "x", "y", make_agg(SPECS[name])).data
+        if rank == 0:
+            if name.endswith("_row"):
+                got = np.where(got >= 0, got - base, got)
+            try:
+                assert_agg_equal(got, ora.points(cols, "x", "y", SPECS[name], view), f"rows across 2^32 {name} world={world}")
+            except AssertionError as e:
+                bad.append(f"rows across 2^32 {name}: {str(e)[:200]}")
     # where(max | min) as two passes (config 5's form, forced on at this size): the key canvas is all-reduced between the passes,
     # so every rank matches its rows against the GLOBAL extreme, and the row canvas (min) after
     from datashader_b200 import _lib

@@ -597,3 +597,36 @@ def test_summary_mixes_categorical_and_plain_reductions(ds):
     assert_agg_equal(agg["m"].data, g["pts_f32_c37x23_mean_v32"], "summary mean_v32")
     assert_agg_equal(agg["catmax"].data, g["pts_f32_c37x23_by_max_v32"], "summary by_max_v32")
     assert tuple(agg["cats"].dims) == ("y", "x", "cat") and tuple(agg["n"].dims) == ("y", "x")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mono_rows", [0, 1 << 20])
+def test_where_rows_of_a_frame_that_crosses_2_to_the_32(ds, mono_rows):
+    """where(max | min) keeps the FIRST row of the extreme (reductions.py:2009-2016).  The packed {key32, row} accumulator breaks
+    ties on the low 32 bits of the global row id, so a frame whose rows cross a multiple of 2^32 (a shard of a bigger frame) must not
+    use it: with values full of ties, the rows found at row_offset = 2^32 - 7000 are the rows found at offset 0, shifted - and both
+    are the oracle's."""
+    import torch
+    from datashader_b200 import _lib
+    from oracle import oracle as ora
+    rng = np.random.default_rng(77)
+    n = 20_000
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": rng.integers(-3, 4, n).astype(np.float32), "other": rng.random(n).astype(np.float32)}
+    dev = {k: torch.from_numpy(v).cuda() for k, v in cols.items()}
+    view = ora.make_view(16, 12, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(16, 12, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    base = (1 << 32) - 7000
+    L = _lib.lib()
+    _lib.check(L.dsb_configure(b"mono_min_rows", mono_rows))
+    try:
+        for which in ("max", "min"):
+            want = ora.points(cols, "x", "y", ("where", (which, "v32"), None), view)
+            r0 = cvs.points(ds.DeviceFrame(dev), "x", "y", ds.where(getattr(ds, which)("v32"))).data
+            r1 = cvs.points(ds.DeviceFrame(dev, row_offset=base), "x", "y", ds.where(getattr(ds, which)("v32"))).data
+            assert np.array_equal(r0, want), which
+            assert np.array_equal(np.where(r1 >= 0, r1 - base, r1), want), which
+            o1 = cvs.points(ds.DeviceFrame(dev, row_offset=base), "x", "y", ds.where(getattr(ds, which)("v32"), "other")).data
+            assert_agg_equal(o1, ora.points(cols, "x", "y", ("where", (which, "v32"), "other"), view), f"{which} other")
+    finally:
+        _lib.check(L.dsb_configure(b"mono_min_rows", 1 << 20))
