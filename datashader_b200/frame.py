@@ -210,14 +210,23 @@ class DeviceFrame:
     def np_dtype(self, name):
         return np.dtype(str(self.columns[name].dtype).replace("torch.", ""))
 
+    CHUNK_ROWS = 1 << 32     # rows per kernel call (the ABI takes n <= 2^32); a multiple of 4, so the vector loads stay aligned
+
     def n_chunks(self):
-        return 1
+        return max(1, -(-self._len // self.CHUNK_ROWS))
 
     def resident(self, needed):
         return self
 
     def chunks(self, needed):
-        yield self
+        """Point glyphs walk a resident frame of more than 2^32 rows in slices of the same device columns (no copy), each with
+        its own global row offset - like the row chunks of a HostFrame, minus the transfer."""
+        if self.n_chunks() == 1:
+            yield self
+            return
+        for lo in range(0, self._len, self.CHUNK_ROWS):
+            hi = min(lo + self.CHUNK_ROWS, self._len)
+            yield DeviceFrame({c: self.columns[c][lo:hi] for c in needed}, self.categories, self.row_offset + lo)
 
 
 class HostFrame:

@@ -630,3 +630,38 @@ def test_where_rows_of_a_frame_that_crosses_2_to_the_32(ds, mono_rows):
             assert_agg_equal(o1, ora.points(cols, "x", "y", ("where", (which, "v32"), "other"), view), f"{which} other")
     finally:
         _lib.check(L.dsb_configure(b"mono_min_rows", 1 << 20))
+
+
+@pytest.mark.parametrize("chunk", [7_001, 8_192])
+def test_device_frame_beyond_the_rows_of_one_call(ds, monkeypatch, force_priv, chunk):
+    """A resident frame with more rows than one kernel call takes (2^32 in production, a few thousand here) is walked in
+    slices of the same device columns: every reduction equals the single pass (global row ids keep first / last / where exact
+    across the slices), auto-ranging and a batched tile level included."""
+    import torch
+    from oracle import oracle as ora
+    rng = np.random.default_rng(23)
+    n = 50_000
+    cols = {"x": rng.random(n, dtype=np.float32), "y": rng.random(n, dtype=np.float32),
+            "v32": np.round(rng.standard_normal(n), 1).astype(np.float32), "other": rng.random(n).astype(np.float32),
+            "v64": np.round(rng.standard_normal(n), 1), "cat": rng.integers(0, NCAT, n).astype(np.int8), "cat__ncat": NCAT}
+    cols["v32"][rng.integers(0, n, 50)] = np.nan
+    frame = ds.DeviceFrame({k: torch.from_numpy(v).cuda() for k, v in cols.items() if k != "cat__ncat"},
+                           categories={"cat": [f"c{i}" for i in range(NCAT)]})
+    view = ora.make_view(64, 48, (0.0, 1.0), (0.0, 1.0))
+    cvs = ds.Canvas(64, 48, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
+    views = [((0.0, 0.5), (0.0, 0.5)), ((0.5, 1.0), (0.0, 0.5)), ((0.0, 0.5), (0.5, 1.0)), ((0.5, 1.0), (0.5, 1.0))]
+    tiles_whole = [t.data for t in cvs.points_batch(frame, "x", "y", ds.count(), views, grid=(2, 2))]
+    monkeypatch.setattr(ds.DeviceFrame, "CHUNK_ROWS", chunk)
+    assert frame.n_chunks() == -(-n // chunk)
+    for rname in ("count", "mean_v32", "max_v32", "first_v32", "last_v32", "where_max_v32_other", "where_min_v32_row",
+                  "where_first_v32_other", "by_count", "by_max_v32"):
+        assert_agg_equal(cvs.points(frame, "x", "y", make_agg(SPECS[rname])).data,
+                         ora.points(cols, "x", "y", SPECS[rname], view, npartitions=2 if "first" in rname or "last" in rname else 1),
+                         f"sliced {rname}")
+    spec = ("where", ("max", "v64"), "other")
+    assert_agg_equal(cvs.points(frame, "x", "y", make_agg(spec)).data, ora.points(cols, "x", "y", spec, view), "sliced 2-pass")
+    got = ds.Canvas(31, 17).points(frame, "x", "y")
+    v2 = ora.make_view(31, 17, ora.compute_bounds(cols["x"]), ora.compute_bounds(cols["y"]))
+    assert_agg_equal(got.data, ora.points(cols, "x", "y", ("count",), v2), "sliced auto-range")
+    for a, b in zip(tiles_whole, cvs.points_batch(frame, "x", "y", ds.count(), views, grid=(2, 2))):
+        assert np.array_equal(a, b.data)
