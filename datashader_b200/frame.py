@@ -210,7 +210,8 @@ class DeviceFrame:
     def np_dtype(self, name):
         return np.dtype(str(self.columns[name].dtype).replace("torch.", ""))
 
-    CHUNK_ROWS = 1 << 32     # rows per kernel call (the ABI takes n <= 2^32); a multiple of 4, so the vector loads stay aligned
+    CHUNK_ROWS = 1 << 31     # rows per slice: the ABI takes n <= 2^32 per call, the routed / privatised-any forms a little less - at 2^31
+                             # every specialised kernel stays eligible; a multiple of 4, so the vector loads stay aligned
 
     def n_chunks(self):
         return max(1, -(-self._len // self.CHUNK_ROWS))
