@@ -214,7 +214,9 @@ class DeviceFrame:
                              # every specialised kernel stays eligible; a multiple of 4, so the vector loads stay aligned
 
     def n_chunks(self):
-        return max(1, -(-self._len // self.CHUNK_ROWS))
+        # one call while the frame fits one (n <= 2^32 - 2: every kernel form takes it - slicing config 5's 4e9 rows would route the
+        # head of first / last once per slice), slices of CHUNK_ROWS beyond
+        return 1 if self._len <= 2 * self.CHUNK_ROWS - 2 else -(-self._len // self.CHUNK_ROWS)
 
     def resident(self, needed):
         return self

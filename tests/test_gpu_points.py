@@ -652,7 +652,7 @@ def test_device_frame_beyond_the_rows_of_one_call(ds, monkeypatch, force_priv, c
     views = [((0.0, 0.5), (0.0, 0.5)), ((0.5, 1.0), (0.0, 0.5)), ((0.0, 0.5), (0.5, 1.0)), ((0.5, 1.0), (0.5, 1.0))]
     tiles_whole = [t.data for t in cvs.points_batch(frame, "x", "y", ds.count(), views, grid=(2, 2))]
     monkeypatch.setattr(ds.DeviceFrame, "CHUNK_ROWS", chunk)
-    assert frame.n_chunks() == -(-n // chunk)
+    assert frame.n_chunks() == -(-n // chunk) and ds.DeviceFrame({"x": frame["x"][:2 * chunk - 2]}).n_chunks() == 1
     for rname in ("count", "mean_v32", "max_v32", "first_v32", "last_v32", "where_max_v32_other", "where_min_v32_row",
                   "where_first_v32_other", "by_count", "by_max_v32"):
         assert_agg_equal(cvs.points(frame, "x", "y", make_agg(SPECS[rname])).data,

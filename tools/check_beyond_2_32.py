@@ -26,6 +26,7 @@ frame = ds.DeviceFrame({"x": x, "y": y, "value": v})
 assert frame.n_chunks() == -(-n // ds.DeviceFrame.CHUNK_ROWS) >= 3
 lo = ds.DeviceFrame({"x": x[:cut], "y": y[:cut], "value": v[:cut]})
 hi = ds.DeviceFrame({"x": x[cut:], "y": y[cut:], "value": v[cut:]}, row_offset=cut)
+assert lo.n_chunks() == 2 and hi.n_chunks() == 1      # 2^32 rows are one too many for a single call; 2e8 are not
 cvs = ds.Canvas(900, 525, x_range=(0.0, 1.0), y_range=(0.0, 1.0))
 run = lambda f, agg: cvs.points(f, "x", "y", agg).data   # noqa: E731
 ok = True
