@@ -360,7 +360,11 @@ static int minmax_rest(const dsb_view* view, const void* x, const void* y, int32
   a.keys = (const int*)keys; a.rows = nullptr; a.coarse = (int*)scratch; a.notes = notes; a.kstride = 1; a.koff = 0;
   if (packed) { a.rows = (long long*)keys; a.kstride = 2; a.koff = 1; a.notes = nullptr; }      // little endian: the key is the high word
   cudaStream_t s = (cudaStream_t)stream;
-  dsb_note_kernel(packed ? "k_points_argminmax_rest<%s> after %.100s" : "k_points_minmax_rest<%s> after %.100s", is_max ? "max" : "min", dsb_last_kernel());
+  {   // the head's kernel, copied first: dsb_note_kernel formats into the buffer dsb_last_kernel() returns
+    char prev[104];
+    snprintf(prev, sizeof(prev), "%s", dsb_last_kernel());
+    dsb_note_kernel(packed ? "k_points_argminmax_rest<%s> after %.100s" : "k_points_minmax_rest<%s> after %.100s", is_max ? "max" : "min", prev);
+  }
   const int cgrid = a.shift <= 3 ? (int)(((long long)a.cw * a.ch + 7) / 8) : a.cw * a.ch;
   if (is_max) k_match_coarse<true><<<cgrid, 256, 0, s>>>(a); else k_match_coarse<false><<<cgrid, 256, 0, s>>>(a);
   const size_t smem = (size_t)MQ_THR_MAX * 2 + 32 * 3 * MQ_CAP * 4;
