@@ -628,6 +628,13 @@ def test_where_rows_of_a_frame_that_crosses_2_to_the_32(ds, mono_rows):
             assert np.array_equal(np.where(r1 >= 0, r1 - base, r1), want), which
             o1 = cvs.points(ds.DeviceFrame(dev, row_offset=base), "x", "y", ds.where(getattr(ds, which)("v32"), "other")).data
             assert_agg_equal(o1, ora.points(cols, "x", "y", ("where", (which, "v32"), "other"), view), f"{which} other")
+        # per category plane as well: by(cat, where(...)) at the offset == at offset 0
+        cat = torch.from_numpy(rng.integers(0, 3, n).astype(np.int8)).cuda()
+        cats = {"cat": ["a", "b", "c"]}
+        agg = ds.by("cat", ds.where(ds.max("v32")))
+        b0 = cvs.points(ds.DeviceFrame({**dev, "cat": cat}, categories=cats), "x", "y", agg).data
+        b1 = cvs.points(ds.DeviceFrame({**dev, "cat": cat}, categories=cats, row_offset=base), "x", "y", agg).data
+        assert b0.shape == (12, 16, 3) and (b0 >= 0).any() and np.array_equal(np.where(b1 >= 0, b1 - base, b1), b0)
     finally:
         _lib.check(L.dsb_configure(b"mono_min_rows", 1 << 20))
 
